@@ -1,0 +1,334 @@
+"""B200-native Go-ICP engine: thin ctypes driver over the C ABI (include/goicp_b200.h).
+
+Python is test/bench plumbing only.  The product is ``libgoicp_b200.so`` (hand-written sm_100a
+CUDA + C++ host, built in-tree by ``cuda-go-icp_b200/Makefile``); the C++ mirror of the
+reference's ``class GoICP`` lives in ``host/goicp_b200.hpp``.  Nothing here falls back to the
+CPU: if the library or a GPU is missing the calls raise.
+
+The ``GoICP`` class below keeps the reference's member names (``pModel``/``Nm``/``pData``/``Nd``,
+``MSEThresh``, ``trimFraction``, ``dt.SIZE``, ``BuildDT()``, ``Register()``, ``optR``/``optT``/
+``optError`` -- jly_goicp.h:82-141) so the parity tests read like the reference's usage in
+src/main.cpp:47-59,154-159.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoicp_b200.so")
+
+EXIT_PATHS = {0: "none", 1: "certified", 2: "early_sse_below_thresh", 3: "queue_empty", 4: "cancelled"}
+
+
+class GoicpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"goicp status {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("mse_threshold", C.c_float), ("trim_fraction", C.c_float), ("do_trim", C.c_int),
+                ("dt_size", C.c_int), ("dt_expand", C.c_double),
+                ("rot_cube", C.c_float * 4), ("trans_cube", C.c_float * 4),
+                ("icp_max_iter", C.c_int), ("device", C.c_int), ("spec_cubes", C.c_int), ("dt_mode", C.c_int),
+                ("rank", C.c_int), ("world_size", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("sse", C.c_float), ("sse_thresh", C.c_float),
+                ("best_lb", C.c_float), ("exit_path", C.c_int),
+                ("rot_pops", C.c_int64), ("trans_pops", C.c_int64), ("bound_evals", C.c_int64),
+                ("bound_evals_executed", C.c_int64), ("icp_calls", C.c_int64), ("rounds", C.c_int64),
+                ("seconds_total", C.c_double), ("seconds_bnb_kernels", C.c_double), ("seconds_icp", C.c_double)]
+
+    def as_dict(self):
+        return {"R": np.array(self.R, np.float32).reshape(3, 3), "t": np.array(self.t, np.float32),
+                "sse": float(self.sse), "sse_thresh": float(self.sse_thresh), "best_lb": float(self.best_lb),
+                "exit_path": EXIT_PATHS[self.exit_path], "rot_pops": self.rot_pops, "trans_pops": self.trans_pops,
+                "bound_evals": self.bound_evals, "bound_evals_executed": self.bound_evals_executed,
+                "icp_calls": self.icp_calls, "rounds": self.rounds, "seconds_total": self.seconds_total,
+                "seconds_bnb_kernels": self.seconds_bnb_kernels, "seconds_icp": self.seconds_icp}
+
+
+class IcpResult(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("err", C.c_float), ("iterations", C.c_int)]
+
+
+class Snapshot(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("sse", C.c_float),
+                ("rot_pops", C.c_int64), ("trans_pops", C.c_int64), ("bound_evals", C.c_int64), ("finished", C.c_int)]
+
+
+class InnerResult(C.Structure):
+    _fields_ = [("value", C.c_float), ("node", C.c_float * 4), ("pops", C.c_uint32), ("evals", C.c_uint32), ("status", C.c_int32)]
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+
+# every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
+ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
+               "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
+               "goicp_eval_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_set_exchange", "goicp_run_toml"]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libgoicp_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libgoicp_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run __graft_entry__.build() (make -C cuda-go-icp_b200)")
+        L = C.CDLL(LIB_PATH)
+        f32p = C.POINTER(C.c_float)
+        L.goicp_default_params.argtypes = [C.POINTER(Params)]
+        L.goicp_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.goicp_destroy.argtypes = [C.c_void_p]
+        L.goicp_last_error.argtypes = [C.c_void_p]
+        L.goicp_last_error.restype = C.c_char_p
+        L.goicp_set_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.goicp_set_data.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.goicp_build_dt.argtypes = [C.c_void_p]
+        L.goicp_set_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.goicp_get_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.goicp_dt_size.argtypes = [C.c_void_p]
+        L.goicp_dt_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.goicp_eval_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.goicp_inner_bnb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.goicp_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.goicp_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.POINTER(IcpResult)]
+        L.goicp_icp_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
+        L.goicp_dt_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
+        L.goicp_register.argtypes = [C.c_void_p, C.POINTER(Result)]
+        L.goicp_poll.argtypes = [C.c_void_p, C.POINTER(Snapshot)]
+        L.goicp_cancel.argtypes = [C.c_void_p]
+        L.goicp_set_exchange.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p, C.c_int]
+        L.goicp_run_toml.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.POINTER(Result)]
+        _lib = L
+    return _lib
+
+
+def _f32(a, cols=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols:
+        a = a.reshape(-1, cols)
+    return a
+
+
+class _DT:
+    """Mirror of GoICP::dt's public knobs (jly_3ddt.h:100-111)."""
+    def __init__(self):
+        self.SIZE = 300
+        self.expandFactor = 2.0
+
+
+class GoICP:
+    """Mirror of the reference's ``class GoICP`` on top of the C ABI."""
+
+    def __init__(self, mse_threshold: float = 1e-3, device: int = 0):
+        self.L = lib()
+        p = Params()
+        self.L.goicp_default_params(C.byref(p))
+        p.mse_threshold = mse_threshold
+        p.device = device
+        self._p = p
+        self.MSEThresh = mse_threshold
+        self.trimFraction = 0.0
+        self.doTrim = True
+        self.dt = _DT()
+        self.dt_mode = 0
+        self.spec_cubes = 0
+        self.initNodeRot = [p.rot_cube[i] for i in range(4)]
+        self.initNodeTrans = [p.trans_cube[i] for i in range(4)]
+        self.pModel = None
+        self.pData = None
+        self.optR = np.eye(3, dtype=np.float32)
+        self.optT = np.zeros(3, np.float32)
+        self.optError = 1e10
+        self.finished = False
+        self._h = None
+        self._dt_pending = None
+        self._keep = []
+        self.rank, self.world_size = 0, 1
+        self._exchange = None
+
+    # -- handle management ---------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.L.goicp_last_error(self._h).decode() if self._h else ""
+            raise GoicpError(rc, msg)
+
+    def _handle(self):
+        if self._h is None:
+            p = self._p
+            p.mse_threshold = self.MSEThresh
+            p.trim_fraction = self.trimFraction
+            p.do_trim = int(self.doTrim)
+            p.dt_size = int(self.dt.SIZE)
+            p.dt_expand = float(self.dt.expandFactor)
+            p.dt_mode = int(self.dt_mode)
+            p.spec_cubes = int(self.spec_cubes)
+            p.rank, p.world_size = self.rank, self.world_size
+            for i in range(4):
+                p.rot_cube[i] = self.initNodeRot[i]
+                p.trans_cube[i] = self.initNodeTrans[i]
+            h = C.c_void_p()
+            rc = self.L.goicp_create(C.byref(p), C.byref(h))
+            if rc:
+                raise GoicpError(rc, "goicp_create")
+            self._h = h
+            if self.pModel is not None:
+                m = _f32(self.pModel, 3)
+                self._check(self.L.goicp_set_model(self._h, m.ctypes.data, len(m)))
+            if self.pData is not None:
+                d = _f32(self.pData, 3)
+                self._check(self.L.goicp_set_data(self._h, d.ctypes.data, len(d)))
+            if self._exchange is not None:
+                self._check(self.L.goicp_set_exchange(self._h, self._exchange, None, 0))
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            self.L.goicp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def Nm(self):
+        return 0 if self.pModel is None else len(_f32(self.pModel, 3))
+
+    @property
+    def Nd(self):
+        return 0 if self.pData is None else len(_f32(self.pData, 3))
+
+    def set_exchange(self, fn, rank, world_size):
+        """fn(send: bytes-like np.uint8 array, world) -> np.uint8 array of world*len(send) (rank-major)."""
+        self.rank, self.world_size = rank, world_size
+
+        def _cb(user, send, recv, nbytes, is_device):
+            try:
+                s = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(nbytes,))
+                out = fn(s)
+                r = np.ctypeslib.as_array(C.cast(recv, C.POINTER(C.c_uint8)), shape=(nbytes * world_size,))
+                r[:] = np.asarray(out, np.uint8).reshape(-1)
+                return 0
+            except Exception as e:  # never raise through the C frame
+                print("exchange callback failed:", e)
+                return 1
+
+        self._exchange = ALLGATHER_FN(_cb)
+
+    # -- the reference's protocol --------------------------------------------------------------
+    def BuildDT(self):
+        """GoICP::BuildDT (jly_goicp.cpp:75-90), on the GPU."""
+        self._check(self.L.goicp_build_dt(self._handle()))
+
+    def SetDT(self, grid, meta):
+        g = _f32(grid).reshape(-1)
+        S = round(g.size ** (1 / 3))
+        assert S * S * S == g.size
+        m = np.ascontiguousarray(meta, np.float64)
+        self._check(self.L.goicp_set_dt(self._handle(), g.ctypes.data, S, m.ctypes.data))
+
+    def GetDT(self):
+        h = self._handle()
+        S = self.L.goicp_dt_size(h)
+        g = np.zeros(S * S * S, np.float32)
+        m = np.zeros(4, np.float64)
+        self._check(self.L.goicp_get_dt(h, g.ctypes.data, m.ctypes.data))
+        return g.reshape(S, S, S), m
+
+    def Register(self):
+        """GoICP::Register (jly_goicp.cpp:569-585); returns optError, fills optR/optT."""
+        res = Result()
+        self._check(self.L.goicp_register(self._handle(), C.byref(res)))
+        self.result = res.as_dict()
+        self.optR, self.optT, self.optError = self.result["R"], self.result["t"], self.result["sse"]
+        self.finished = True
+        return self.optError
+
+    # -- pieces of the path, exposed for parity tests and the bench -----------------------------
+    def Distance(self, q, with_index=False):
+        """DT3D::Distance for a batch (jly_3ddt.cpp:981-1026)."""
+        q = _f32(q, 3)
+        out = np.zeros(len(q), np.float32)
+        idx = np.zeros((len(q), 3), np.int32) if with_index else None
+        self._check(self.L.goicp_dt_distance(self._handle(), q.ctypes.data, len(q), out.ctypes.data,
+                                             idx.ctypes.data if with_index else None))
+        return (out, idx) if with_index else out
+
+    def EvalBounds(self, R, level, tcube):
+        R = _f32(R).reshape(-1, 9)
+        level = np.ascontiguousarray(level, np.int32)
+        tcube = _f32(tcube, 4)
+        n = len(R)
+        ub = np.zeros(n, np.float32)
+        lb = np.zeros(n, np.float32)
+        self._check(self.L.goicp_eval_bounds(self._handle(), n, R.ctypes.data, level.ctypes.data, tcube.ctypes.data,
+                                             ub.ctypes.data, lb.ctypes.data))
+        return ub, lb
+
+    def InnerBnB(self, R, level, opt_error):
+        """Batch of GoICP::InnerBnB calls (jly_goicp.cpp:227-340)."""
+        R = _f32(R).reshape(-1, 9)
+        level = np.ascontiguousarray(level, np.int32).reshape(-1)
+        oe = _f32(opt_error).reshape(-1)
+        n = len(R)
+        out = (InnerResult * n)()
+        self._check(self.L.goicp_inner_bnb(self._handle(), n, R.ctypes.data, level.ctypes.data, oe.ctypes.data, out))
+        return [{"value": float(o.value), "node": np.array(o.node, np.float32), "pops": o.pops, "evals": o.evals} for o in out]
+
+    def NN(self, q):
+        q = _f32(q, 3)
+        idx = np.zeros(len(q), np.int32)
+        d2 = np.zeros(len(q), np.float32)
+        self._check(self.L.goicp_nn(self._handle(), q.ctypes.data, len(q), idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    def ICP(self, R0=None, t0=None, max_iter=0, err_diff=-1.0):
+        """ICP3D<float>::Run (jly_icp3d.hpp:180-295)."""
+        R0 = _f32(np.eye(3) if R0 is None else R0).reshape(9)
+        t0 = _f32(np.zeros(3) if t0 is None else t0).reshape(3)
+        r = IcpResult()
+        self._check(self.L.goicp_icp(self._handle(), R0.ctypes.data, t0.ctypes.data, max_iter, err_diff, C.byref(r)))
+        return float(r.err), np.array(r.R, np.float32).reshape(3, 3), np.array(r.t, np.float32), r.iterations
+
+    def DTScore(self, R=None, t=None):
+        out = C.c_float()
+        if R is None:
+            self._check(self.L.goicp_dt_score(self._handle(), None, None, C.byref(out)))
+        else:
+            R = _f32(R).reshape(9)
+            t = _f32(t).reshape(3)
+            self._check(self.L.goicp_dt_score(self._handle(), R.ctypes.data, t.ctypes.data, C.byref(out)))
+        return out.value
+
+    def Poll(self):
+        s = Snapshot()
+        self.L.goicp_poll(self._handle(), C.byref(s))
+        return {"R": np.array(s.R, np.float32).reshape(3, 3), "t": np.array(s.t, np.float32), "sse": s.sse,
+                "rot_pops": s.rot_pops, "trans_pops": s.trans_pops, "bound_evals": s.bound_evals, "finished": bool(s.finished)}
+
+    def Cancel(self):
+        self.L.goicp_cancel(self._handle())

@@ -1,0 +1,792 @@
+// engine.cu -- host side of the B200 Go-ICP engine and its C ABI (include/goicp_b200.h).
+//
+// Mirrors the object protocol of the reference's `class GoICP` (jly_goicp.h:82-141):
+// set clouds -> BuildDT -> Register (Initialize + OuterBnB) -> optR/optT/optError.
+//
+// Search strategy.  The reference's outer loop is a strictly sequential best-first search whose
+// result (which cube triggers which ICP refinement) depends on the visiting order, including
+// the order std::priority_queue gives to nodes with equal (lb, w).  Between two improvements of
+// the best error E, however, every inner BnB is a pure function of (rotation cube, pass, E).  The
+// engine therefore keeps the reference's queue semantics *exactly* (same libstdc++ heap
+// algorithms, same commit order) but evaluates cubes ahead of time: each device round expands
+// the cube at the top of the queue plus the next-best `spec_cubes-1` queue entries, all
+// (child, pass) inner BnBs of a round running concurrently, one CTA each.  Results are cached
+// per cube and committed strictly in the reference's order; an improvement of E invalidates
+// the cache (epoch bump).  The committed trajectory, counters and certificate are those of the
+// sequential algorithm; speculative work only shows up in bound_evals_executed.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/goicp_b200.h"
+#include "goicp_kernels.h"
+#include "kdtree_host.h"
+#include "dt_kernels.h"
+
+using namespace goicp;
+
+namespace {
+
+constexpr double kPi = 3.1415926536;       // PI,    jly_goicp.h:35
+constexpr double kSqrt3 = 1.732050808;     // SQRT3, jly_goicp.h:36
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct RotNode { float a, b, c, w, ub, lb; int l; };                  // ROTNODE, jly_goicp.h:44-58
+struct RotLower {                                                      // its operator<
+    bool operator()(const RotNode& n1, const RotNode& n2) const { return n1.lb != n2.lb ? n1.lb > n2.lb : n1.w < n2.w; }
+};
+
+struct CubeKey {
+    uint32_t a, b, c; int l;
+    bool operator==(const CubeKey& o) const { return a == o.a && b == o.b && c == o.c && l == o.l; }
+};
+struct CubeKeyHash {
+    size_t operator()(const CubeKey& k) const
+    {
+        uint64_t h = 1469598103934665603ULL;
+        for (uint32_t v : {k.a, k.b, k.c, (uint32_t)k.l}) { h ^= v; h *= 1099511628211ULL; }
+        return (size_t)h;
+    }
+};
+inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline CubeKey key_of(const RotNode& n) { return CubeKey{fbits(n.a), fbits(n.b), fbits(n.c), n.l}; }
+
+struct ChildEval {
+    bool skipped = true;            // outside the pi-ball (jly_goicp.cpp:443)
+    float R[9];
+    InnerResult ub, lb;
+};
+struct CubeEval { long epoch = -1; ChildEval ch[8]; };
+
+// Angle-axis vector of the cube centre -> rotation matrix, in float with glibc sinf/cosf exactly
+// like jly_goicp.cpp:437-467.  false = cube wholly outside the pi-ball.
+bool cube_rotation(float a, float b, float c, float w, float* R)
+{
+    float v1 = a + w / 2, v2 = b + w / 2, v3 = c + w / 2;
+    if ((double)std::sqrt(v1 * v1 + v2 * v2 + v3 * v3) - kSqrt3 * (double)w / 2 > kPi) return false;
+    float t = std::sqrt(v1 * v1 + v2 * v2 + v3 * v3);
+    if (t > 0) {
+        v1 /= t; v2 /= t; v3 /= t;
+        const float ct = std::cos(t), ct2 = 1 - ct, st = std::sin(t);
+        const float tmp121 = v1 * v2 * ct2, tmp122 = v3 * st, tmp131 = v1 * v3 * ct2, tmp132 = v2 * st,
+                    tmp231 = v2 * v3 * ct2, tmp232 = v1 * st;
+        R[0] = ct + v1 * v1 * ct2; R[1] = tmp121 - tmp122;    R[2] = tmp131 + tmp132;
+        R[3] = tmp121 + tmp122;    R[4] = ct + v2 * v2 * ct2; R[5] = tmp231 - tmp232;
+        R[6] = tmp131 - tmp132;    R[7] = tmp231 + tmp232;    R[8] = ct + v3 * v3 * ct2;
+    } else {
+        for (int i = 0; i < 9; i++) R[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    }
+    return true;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t reserve(size_t count)
+    {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+} // namespace
+
+struct goicp_handle {
+    goicp_params p;
+    std::string err;
+    bool cuda_ready = false;
+    int sm_count = 0, max_smem_optin = 0;
+    cudaStream_t stream = nullptr;
+
+    std::vector<float> model, data;     // xyz triples
+    int nm = 0, nd = 0;
+
+    // distance transform
+    DevBuf<float> d_dt; int dt_size = 0; double dt_meta[4] = {0, 0, 0, 0}; bool have_dt = false;
+    // data cloud on device (x,y,z,norm)
+    DevBuf<float4> d_data; bool data_uploaded = false;
+    // kd-tree
+    HostKdTree kd_host; DevBuf<KdNode> d_kd_nodes; DevBuf<int32_t> d_kd_vind; DevBuf<float4> d_kd_leaf; DevBuf<float> d_model;
+    bool kd_ready = false;
+    // scratch
+    DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
+    DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
+    DevBuf<IcpState> d_icp_state; DevBuf<double> d_icp_partials; int icp_blocks = 0;
+    InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
+    InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
+
+    // Initialize() products
+    float sse_thresh = 0; int inlier_num = 0; float cgamma[kMaxRotLevel]; bool initialized = false;
+
+    // live state for poll/cancel
+    std::mutex snap_mtx; goicp_snapshot snap; std::atomic<int> cancel_flag{0};
+
+    // multi-GPU exchange
+    goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
+
+    // timing
+    double t_kernels = 0, t_icp = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int fail(goicp_handle* h, int code, const std::string& msg) { if (h) h->err = msg; return code; }
+#define CUDA_TRY(h, expr)                                                                         \
+    do { cudaError_t _e = (expr);                                                                 \
+         if (_e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+int ensure_cuda(goicp_handle* h)
+{
+    if (h->cuda_ready) return GOICP_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(h, GOICP_ERR_CUDA, std::string("no CUDA device available (this engine has no CPU fallback): ") + cudaGetErrorString(e));
+    CUDA_TRY(h, cudaSetDevice(h->p.device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->p.device));
+    if (prop.major < 10) return fail(h, GOICP_ERR_CUDA, "device is not sm_100-class; this library ships sm_100a code only");
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaEventCreate(&h->ev0));
+    CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    CUDA_TRY(h, inner_bnb_configure(h->max_smem_optin - 2048));   // minus the kernel's static shared memory
+    h->cuda_ready = true;
+    return GOICP_OK;
+}
+
+int upload_data(goicp_handle* h)
+{
+    if (h->data_uploaded) return GOICP_OK;
+    if (h->nd <= 0) return fail(h, GOICP_ERR_INVALID, "no data cloud set");
+    std::vector<float4> tmp(h->nd);
+    for (int i = 0; i < h->nd; i++) {
+        const float x = h->data[3 * i], y = h->data[3 * i + 1], z = h->data[3 * i + 2];
+        tmp[i] = make_float4(x, y, z, std::sqrt(x * x + y * y + z * z));     // normData (jly_goicp.cpp:143-147)
+    }
+    CUDA_TRY(h, h->d_data.reserve(h->nd));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_data.p, tmp.data(), sizeof(float4) * h->nd, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->data_uploaded = true;
+    return GOICP_OK;
+}
+
+int ensure_kdtree(goicp_handle* h)
+{
+    if (h->kd_ready) return GOICP_OK;
+    if (h->nm <= 0) return fail(h, GOICP_ERR_INVALID, "no model cloud set");
+    h->kd_host.build(h->model.data(), h->nm, 10);                              // ICP3D::Build (jly_icp3d.hpp:129-154)
+    std::vector<float4> leaf(h->nm);
+    for (int i = 0; i < h->nm; i++) {
+        const int id = h->kd_host.vind[i];
+        float w; std::memcpy(&w, &id, 4);
+        leaf[i] = make_float4(h->model[3 * id], h->model[3 * id + 1], h->model[3 * id + 2], w);
+    }
+    CUDA_TRY(h, h->d_kd_nodes.reserve(h->kd_host.nodes.size()));
+    CUDA_TRY(h, h->d_kd_vind.reserve(h->nm));
+    CUDA_TRY(h, h->d_kd_leaf.reserve(h->nm));
+    CUDA_TRY(h, h->d_model.reserve((size_t)3 * h->nm));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_nodes.p, h->kd_host.nodes.data(), sizeof(KdNode) * h->kd_host.nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_vind.p, h->kd_host.vind.data(), sizeof(int32_t) * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->icp_blocks = icp_max_grid_blocks(h->p.device);
+    if (h->icp_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
+    CUDA_TRY(h, h->d_icp_state.reserve(1));
+    CUDA_TRY(h, h->d_icp_partials.reserve((size_t)h->icp_blocks * 16));
+    h->kd_ready = true;
+    return GOICP_OK;
+}
+
+KdView kd_view(const goicp_handle* h)
+{
+    KdView v;
+    v.nodes = h->d_kd_nodes.p; v.vind = h->d_kd_vind.p; v.pts_leaf = h->d_kd_leaf.p; v.model = h->d_model.p; v.nm = h->nm;
+    for (int i = 0; i < 3; i++) { v.bb_lo[i] = h->kd_host.bb_lo[i]; v.bb_hi[i] = h->kd_host.bb_hi[i]; }
+    return v;
+}
+
+// Initialize() (jly_goicp.cpp:134-209): thresholds and the per-level rotation-uncertainty scale.
+int initialize(goicp_handle* h)
+{
+    int rc = ensure_cuda(h); if (rc) return rc;
+    rc = upload_data(h); if (rc) return rc;
+    for (int i = 0; i < kMaxRotLevel; i++) {
+        float sigma = (float)((double)h->p.rot_cube[3] / std::pow(2.0, i) / 2.0);
+        float max_angle = (float)(kSqrt3 * (double)sigma);
+        if ((double)max_angle > kPi) max_angle = (float)kPi;
+        h->cgamma[i] = 2 * std::sin(max_angle / 2);              // maxRotDis[i][j] = cgamma[i]*normData[j]
+    }
+    h->inlier_num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;
+    h->sse_thresh = h->p.mse_threshold * (float)h->inlier_num;
+    h->initialized = true;
+    return GOICP_OK;
+}
+
+int make_const(goicp_handle* h, BnbConst& c)
+{
+    if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "distance transform not built (call goicp_build_dt or goicp_set_dt first)");
+    if (!h->initialized) { int rc = initialize(h); if (rc) return rc; }
+    if (h->inlier_num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the bound kernels yet");
+    c.dt.grid = h->d_dt.p; c.dt.S = h->dt_size; c.dt.S2 = h->dt_size * h->dt_size;
+    c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3];
+    c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.sse_thresh = h->sse_thresh;
+    c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
+    for (int i = 0; i < kMaxRotLevel; i++) c.cgamma[i] = h->cgamma[i];
+    return GOICP_OK;
+}
+
+// Shared-memory plan of the persistent inner-BnB kernel: rotated points on chip when two CTAs
+// per SM still fit, the rest of the per-CTA budget goes to the priority queue.
+struct InnerPlan { bool pts_smem; int heap_cap_sm; };
+InnerPlan plan_inner(const goicp_handle* h)
+{
+    const size_t per_cta = ((size_t)h->max_smem_optin + 1024) / 2 - 4096;      // two CTAs per SM, minus static smem + slack
+    const size_t pts = (size_t)h->nd * sizeof(float4);
+    InnerPlan p;
+    p.pts_smem = pts + 16 * 1024 <= per_cta;
+    size_t heap_bytes = per_cta - (p.pts_smem ? pts : 0);
+    p.heap_cap_sm = (int)std::min<size_t>(heap_bytes / sizeof(HeapEntry), 6144);
+    return p;
+}
+
+int ensure_task_buffers(goicp_handle* h, size_t n)
+{
+    CUDA_TRY(h, h->d_tasks.reserve(n));
+    CUDA_TRY(h, h->d_results.reserve(n));
+    if (h->h_results_n < n) {
+        if (h->h_results) cudaFreeHost(h->h_results);
+        if (h->h_tasks) cudaFreeHost(h->h_tasks);
+        h->h_results = nullptr; h->h_tasks = nullptr;
+        size_t cap = std::max<size_t>(n, 1024);
+        CUDA_TRY(h, cudaMallocHost((void**)&h->h_results, cap * sizeof(InnerResult)));
+        CUDA_TRY(h, cudaMallocHost((void**)&h->h_tasks, cap * sizeof(InnerTask)));
+        h->h_results_n = cap; h->h_tasks_n = cap;
+    }
+    // spill region: one slab per concurrently launched CTA (grid == n)
+    const int spill_cap = 1 << 16;        // 65536 entries (1 MiB) per task beyond the shared-memory part
+    if ((size_t)h->spill_slots < n || h->spill_cap != spill_cap) {
+        size_t slots = std::max<size_t>(n, 512);
+        CUDA_TRY(h, h->d_spill.reserve(slots * (size_t)spill_cap));
+        h->spill_slots = (int)slots; h->spill_cap = spill_cap;
+    }
+    return GOICP_OK;
+}
+
+// Runs `n` inner BnBs (tasks in h->h_tasks) and leaves the results in h->h_results.
+// With an exchange hook installed, rank r runs tasks r, r+W, r+2W, ... and the per-rank result
+// blocks are all-gathered, so every rank ends up with all n results.
+int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed_evals)
+{
+    if (n <= 0) return GOICP_OK;
+    int rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
+    const InnerPlan plan = plan_inner(h);
+    const int W = (h->xchg && h->p.world_size > 1) ? h->p.world_size : 1;
+    const int r = W > 1 ? h->p.rank : 0;
+    const int per_rank = (n + W - 1) / W;
+    int mine = 0;
+    std::vector<InnerTask> local;
+    const InnerTask* src = h->h_tasks;
+    if (W > 1) {
+        local.reserve(per_rank);
+        for (int t = r; t < n; t += W) local.push_back(h->h_tasks[t]);
+        mine = (int)local.size();
+        src = local.data();
+    } else mine = n;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    if (mine > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, launch_inner_bnb(c, h->d_tasks.p, h->d_results.p, mine, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->stream));
+    }
+    if (W == 1) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results.p, sizeof(InnerResult) * n, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else {
+        std::vector<InnerResult> send(per_rank), recv((size_t)per_rank * W);
+        std::memset(send.data(), 0, sizeof(InnerResult) * per_rank);
+        if (mine > 0) CUDA_TRY(h, cudaMemcpyAsync(send.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        if (h->xchg(h->xchg_user, send.data(), recv.data(), sizeof(InnerResult) * per_rank, 0) != 0)
+            return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
+        for (int t = 0; t < n; t++) h->h_results[t] = recv[(size_t)(t % W) * per_rank + t / W];
+    }
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->t_kernels += ms * 1e-3;
+    for (int t = 0; t < n; t++) {
+        if (h->h_results[t].status == 3) return fail(h, GOICP_ERR_CAPACITY, "translation priority queue overflowed its device capacity");
+        if (h->h_results[t].status == 4) return fail(h, GOICP_ERR_DEPTH, "translation search exceeded 21 levels");
+        if (executed_evals) *executed_evals += h->h_results[t].evals;
+    }
+    return GOICP_OK;
+}
+
+int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* t, float* out)
+{
+    float Rt[12]; int use = R ? 1 : 0;
+    for (int i = 0; i < 9; i++) Rt[i] = R ? R[i] : 0.0f;
+    for (int i = 0; i < 3; i++) Rt[9 + i] = R ? t[i] : 0.0f;
+    CUDA_TRY(h, h->d_f32a.reserve(64));
+    CUDA_TRY(h, h->d_i32.reserve(16));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_f32a.p + 16, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, float err_diff, goicp_icp_result* out)
+{
+    int rc = ensure_cuda(h); if (rc) return rc;
+    rc = upload_data(h); if (rc) return rc;
+    rc = ensure_kdtree(h); if (rc) return rc;
+    const int num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;
+    if (num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the ICP kernel yet");
+    IcpState st; std::memset(&st, 0, sizeof st);
+    for (int i = 0; i < 9; i++) st.R[i] = R0[i];
+    for (int i = 0; i < 3; i++) st.t[i] = t0[i];
+    st.err = -1.0f;
+    const double t_begin = now_s();
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
+    const int blocks = std::max(1, std::min(h->icp_blocks, (h->nd + 127) / 128));
+    CUDA_TRY(h, launch_icp(kd_view(h), h->d_data.p, h->nd, h->d_icp_state.p, h->d_icp_partials.p, max_iter, err_diff, num, blocks, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->t_icp += now_s() - t_begin;
+    for (int i = 0; i < 9; i++) out->R[i] = st.R[i];
+    for (int i = 0; i < 3; i++) out->t[i] = st.t[i];
+    out->err = st.err_new; out->iterations = st.iter;
+    return GOICP_OK;
+}
+
+// GoICP::ICP (jly_goicp.cpp:93-132)
+int icp_then_dt(goicp_handle* h, const BnbConst& c, float* R, float* t, float* err)
+{
+    goicp_icp_result r;
+    int rc = run_icp(h, R, t, h->p.icp_max_iter, h->p.mse_threshold / 10000, &r);      // err_diff_def = MSEThresh/10000 (jly_goicp.cpp:186)
+    if (rc) return rc;
+    std::memcpy(R, r.R, sizeof r.R); std::memcpy(t, r.t, sizeof r.t);
+    return score_pose(h, c, R, t, err);
+}
+
+void publish(goicp_handle* h, const goicp_result& res, int finished)
+{
+    std::lock_guard<std::mutex> lk(h->snap_mtx);
+    std::memcpy(h->snap.R, res.R, sizeof res.R); std::memcpy(h->snap.t, res.t, sizeof res.t);
+    h->snap.sse = res.sse; h->snap.rot_pops = res.rot_pops; h->snap.trans_pops = res.trans_pops;
+    h->snap.bound_evals = res.bound_evals; h->snap.finished = finished;
+}
+
+} // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+void goicp_default_params(goicp_params* p)
+{
+    std::memset(p, 0, sizeof *p);
+    p->mse_threshold = 1e-3f;
+    p->trim_fraction = 0.0f; p->do_trim = 1;
+    p->dt_size = 300; p->dt_expand = 2.0;
+    p->rot_cube[0] = p->rot_cube[1] = p->rot_cube[2] = (float)-kPi; p->rot_cube[3] = (float)(2 * kPi);
+    p->trans_cube[0] = p->trans_cube[1] = p->trans_cube[2] = -0.5f; p->trans_cube[3] = 1.0f;
+    p->icp_max_iter = 10000;
+    p->device = 0; p->spec_cubes = 0; p->dt_mode = GOICP_DT_REFERENCE;
+    p->rank = 0; p->world_size = 1;
+}
+
+int goicp_create(const goicp_params* p, goicp_handle** out)
+{
+    if (!p || !out) return GOICP_ERR_INVALID;
+    goicp_handle* h = new goicp_handle();
+    h->p = *p;
+    std::memset(&h->snap, 0, sizeof h->snap);
+    *out = h;
+    return GOICP_OK;
+}
+
+int goicp_destroy(goicp_handle* h)
+{
+    if (!h) return GOICP_OK;
+    if (h->cuda_ready) {
+        cudaSetDevice(h->p.device);
+        h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
+        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
+        h->d_i32.release(); h->d_q.release(); h->d_icp_state.release(); h->d_icp_partials.release();
+        if (h->h_results) cudaFreeHost(h->h_results);
+        if (h->h_tasks) cudaFreeHost(h->h_tasks);
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+    return GOICP_OK;
+}
+
+const char* goicp_last_error(const goicp_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int goicp_set_model(goicp_handle* h, const float* xyz, int n)
+{
+    if (!h || !xyz || n <= 0) return fail(h, GOICP_ERR_INVALID, "set_model: bad arguments");
+    h->model.assign(xyz, xyz + 3 * (size_t)n); h->nm = n; h->kd_ready = false;
+    return GOICP_OK;
+}
+int goicp_set_data(goicp_handle* h, const float* xyz, int n)
+{
+    if (!h || !xyz || n <= 0) return fail(h, GOICP_ERR_INVALID, "set_data: bad arguments");
+    h->data.assign(xyz, xyz + 3 * (size_t)n); h->nd = n; h->data_uploaded = false; h->initialized = false;
+    return GOICP_OK;
+}
+
+int goicp_set_dt(goicp_handle* h, const float* grid, int size, const double meta4[4])
+{
+    if (!h || !grid || size <= 1 || !meta4) return fail(h, GOICP_ERR_INVALID, "set_dt: bad arguments");
+    int rc = ensure_cuda(h); if (rc) return rc;
+    const size_t n3 = (size_t)size * size * size;
+    CUDA_TRY(h, h->d_dt.reserve(n3));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_dt.p, grid, n3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->dt_size = size; std::memcpy(h->dt_meta, meta4, sizeof h->dt_meta); h->have_dt = true;
+    return GOICP_OK;
+}
+int goicp_get_dt(goicp_handle* h, float* grid_out, double meta4_out[4])
+{
+    if (!h || !h->have_dt) return fail(h, GOICP_ERR_INVALID, "get_dt: no distance transform");
+    if (meta4_out) std::memcpy(meta4_out, h->dt_meta, sizeof h->dt_meta);
+    if (grid_out) {
+        const size_t n3 = (size_t)h->dt_size * h->dt_size * h->dt_size;
+        CUDA_TRY(h, cudaMemcpy(grid_out, h->d_dt.p, n3 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    return GOICP_OK;
+}
+int goicp_dt_size(const goicp_handle* h) { return h && h->have_dt ? h->dt_size : 0; }
+
+int goicp_build_dt(goicp_handle* h)
+{
+    if (!h || h->nm <= 0) return fail(h, GOICP_ERR_INVALID, "build_dt: no model cloud set");
+    int rc = ensure_cuda(h); if (rc) return rc;
+    const int S = h->p.dt_size;
+    if (S < 2 || S > 1024) return fail(h, GOICP_ERR_INVALID, "build_dt: dt_size out of range [2,1024]");
+    const size_t n3 = (size_t)S * S * S;
+    CUDA_TRY(h, h->d_dt.reserve(n3));
+    std::string msg;
+    cudaError_t e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
+    if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "dt_build_device: " + msg + ": " + cudaGetErrorString(e));
+    h->dt_size = S; h->have_dt = true;
+    return GOICP_OK;
+}
+
+int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_out, int32_t* ixyz_out)
+{
+    if (!h || !q_xyz || !dist_out || n < 0) return fail(h, GOICP_ERR_INVALID, "dt_distance: bad arguments");
+    if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "dt_distance: no distance transform");
+    if (n == 0) return GOICP_OK;
+    DtView dt; dt.grid = h->d_dt.p; dt.S = h->dt_size; dt.S2 = h->dt_size * h->dt_size;
+    dt.xmin = h->dt_meta[0]; dt.ymin = h->dt_meta[1]; dt.zmin = h->dt_meta[2]; dt.scale = h->dt_meta[3];
+    CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
+    CUDA_TRY(h, h->d_f32b.reserve(n));
+    CUDA_TRY(h, h->d_i32.reserve((size_t)3 * n + 16));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_dt_lookup(dt, h->d_q.p, n, h->d_f32b.p, ixyz_out ? h->d_i32.p : nullptr, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dist_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (ixyz_out) CUDA_TRY(h, cudaMemcpyAsync(ixyz_out, h->d_i32.p, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_t* level, const float* tcube, float* ub_out, float* lb_out)
+{
+    if (!h || npairs < 0 || !R9 || !level || !tcube || !ub_out || !lb_out) return fail(h, GOICP_ERR_INVALID, "eval_bounds: bad arguments");
+    if (npairs == 0) return GOICP_OK;
+    BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    std::vector<PairTask> tasks(npairs);
+    for (int k = 0; k < npairs; k++) {
+        if (level[k] >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "eval_bounds: rotation level >= 20");
+        std::memcpy(tasks[k].R, R9 + 9 * (size_t)k, 9 * sizeof(float));
+        tasks[k].level = level[k];
+        std::memcpy(tasks[k].tc, tcube + 4 * (size_t)k, 4 * sizeof(float));
+        tasks[k].pad[0] = tasks[k].pad[1] = 0;
+    }
+    CUDA_TRY(h, h->d_pairs.reserve(npairs));
+    CUDA_TRY(h, h->d_f32b.reserve((size_t)2 * npairs));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pairs.p, tasks.data(), sizeof(PairTask) * npairs, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_pair_bounds(c, h->d_pairs.p, npairs, reinterpret_cast<float2*>(h->d_f32b.p), h->stream));
+    std::vector<float> out((size_t)2 * npairs);
+    CUDA_TRY(h, cudaMemcpyAsync(out.data(), h->d_f32b.p, sizeof(float) * 2 * npairs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < npairs; k++) { ub_out[k] = out[2 * k]; lb_out[k] = out[2 * k + 1]; }
+    return GOICP_OK;
+}
+
+int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* level, const float* opt_error, goicp_inner_result* out)
+{
+    if (!h || n < 0 || !R9 || !level || !opt_error || !out) return fail(h, GOICP_ERR_INVALID, "inner_bnb: bad arguments");
+    if (n == 0) return GOICP_OK;
+    BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
+    for (int k = 0; k < n; k++) {
+        if (level[k] >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "inner_bnb: rotation level >= 20");
+        std::memcpy(h->h_tasks[k].R, R9 + 9 * (size_t)k, 9 * sizeof(float));
+        h->h_tasks[k].level = level[k]; h->h_tasks[k].opt_error = opt_error[k]; h->h_tasks[k].pad = 0;
+    }
+    goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;       // this entry point is single-GPU
+    rc = run_inner_batch(h, c, n, nullptr);
+    h->xchg = saved;
+    if (rc) return rc;
+    for (int k = 0; k < n; k++) {
+        out[k].value = h->h_results[k].value; std::memcpy(out[k].node, h->h_results[k].node, sizeof out[k].node);
+        out[k].pops = h->h_results[k].pops; out[k].evals = h->h_results[k].evals; out[k].status = h->h_results[k].status;
+    }
+    return GOICP_OK;
+}
+
+int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float* d2_out)
+{
+    if (!h || !q_xyz || n < 0 || !idx_out || !d2_out) return fail(h, GOICP_ERR_INVALID, "nn: bad arguments");
+    if (n == 0) return GOICP_OK;
+    int rc = ensure_cuda(h); if (rc) return rc;
+    rc = ensure_kdtree(h); if (rc) return rc;
+    CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
+    CUDA_TRY(h, h->d_f32b.reserve(n));
+    CUDA_TRY(h, h->d_i32.reserve((size_t)n + 16));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_nn(kd_view(h), h->d_q.p, n, h->d_i32.p, h->d_f32b.p, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(idx_out, h->d_i32.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d2_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff, goicp_icp_result* out)
+{
+    if (!h || !R0 || !t0 || !out) return fail(h, GOICP_ERR_INVALID, "icp: bad arguments");
+    if (max_iter <= 0) max_iter = h->p.icp_max_iter;
+    if (err_diff < 0) err_diff = h->p.mse_threshold / 10000;
+    return run_icp(h, R0, t0, max_iter, err_diff, out);
+}
+
+int goicp_dt_score(goicp_handle* h, const float* R, const float* t, float* sse_out)
+{
+    if (!h || !sse_out || (R && !t)) return fail(h, GOICP_ERR_INVALID, "dt_score: bad arguments");
+    BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    return score_pose(h, c, R, t, sse_out);
+}
+
+int goicp_icp_dt(goicp_handle* h, float R[9], float t[3], float* dt_error_out)
+{
+    if (!h || !R || !t || !dt_error_out) return fail(h, GOICP_ERR_INVALID, "icp_dt: bad arguments");
+    BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    return icp_then_dt(h, c, R, t, dt_error_out);
+}
+
+int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int use_device_buffers)
+{
+    if (!h) return GOICP_ERR_INVALID;
+    h->xchg = fn; h->xchg_user = user; h->xchg_device = use_device_buffers;
+    return GOICP_OK;
+}
+
+int goicp_cancel(goicp_handle* h) { if (!h) return GOICP_ERR_INVALID; h->cancel_flag.store(1); return GOICP_OK; }
+int goicp_poll(goicp_handle* h, goicp_snapshot* out)
+{
+    if (!h || !out) return GOICP_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(h->snap_mtx);
+    *out = h->snap;
+    return GOICP_OK;
+}
+
+// GoICP::Register = Initialize + OuterBnB (jly_goicp.cpp:569-585, 342-567)
+int goicp_register(goicp_handle* h, goicp_result* out)
+{
+    if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
+    std::memset(out, 0, sizeof *out);
+    h->cancel_flag.store(0);
+    h->t_kernels = 0; h->t_icp = 0;
+    const double t_begin = now_s();
+    h->initialized = false;
+    int rc = initialize(h); if (rc) return rc;
+    BnbConst c; rc = make_const(h, c); if (rc) return rc;
+    rc = ensure_kdtree(h); if (rc) return rc;
+
+    goicp_result res; std::memset(&res, 0, sizeof res);
+    res.sse_thresh = h->sse_thresh;
+    float E = 1e+10f;                                    // optError
+    float optR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, optT[3] = {0, 0, 0};
+    auto sync_res = [&]() { std::memcpy(res.R, optR, sizeof optR); std::memcpy(res.t, optT, sizeof optT); res.sse = E; };
+
+    // initial error (jly_goicp.cpp:357-372) and ICP from the identity (:378-391)
+    rc = score_pose(h, c, nullptr, nullptr, &E); if (rc) return rc;
+    {
+        float R_icp[9], t_icp[3], error;
+        std::memcpy(R_icp, optR, sizeof optR); std::memcpy(t_icp, optT, sizeof optT);
+        rc = icp_then_dt(h, c, R_icp, t_icp, &error); if (rc) return rc;
+        res.icp_calls++;
+        if (error < E) { E = error; std::memcpy(optR, R_icp, sizeof optR); std::memcpy(optT, t_icp, sizeof optT); }
+    }
+    sync_res(); publish(h, res, 0);
+
+    std::vector<RotNode> heap;                            // std::priority_queue<ROTNODE> == vector + push_heap/pop_heap
+    RotLower lower;
+    RotNode init; init.a = h->p.rot_cube[0]; init.b = h->p.rot_cube[1]; init.c = h->p.rot_cube[2]; init.w = h->p.rot_cube[3];
+    init.ub = 0; init.lb = 0; init.l = 0;
+    heap.push_back(init); std::push_heap(heap.begin(), heap.end(), lower);
+
+    std::unordered_map<CubeKey, CubeEval, CubeKeyHash> cache;
+    long epoch = 0;
+    int spec = h->p.spec_cubes > 0 ? h->p.spec_cubes : std::max(1, (2 * h->sm_count) / 16);
+    if (h->xchg && h->p.world_size > 1) spec *= h->p.world_size;
+
+    // Evaluate `first` (must be evaluated) plus the best not-yet-evaluated queue entries.
+    auto evaluate_round = [&](const RotNode& first) -> int {
+        std::vector<RotNode> cubes;
+        cubes.push_back(first);
+        if (spec > 1 && !heap.empty()) {
+            std::vector<const RotNode*> cand;
+            cand.reserve(heap.size());
+            const CubeKey fk = key_of(first);
+            for (const RotNode& n : heap) {
+                const CubeKey k = key_of(n);
+                if (k == fk) continue;
+                auto it = cache.find(k);
+                if (it != cache.end() && it->second.epoch == epoch) continue;
+                if ((E - n.lb) <= h->sse_thresh) continue;         // would certify, never expanded
+                cand.push_back(&n);
+            }
+            const size_t want = std::min<size_t>(cand.size(), (size_t)spec - 1);
+            std::partial_sort(cand.begin(), cand.begin() + want, cand.end(),
+                              [&](const RotNode* x, const RotNode* y) { return lower(*y, *x); });
+            for (size_t i = 0; i < want; i++) cubes.push_back(*cand[i]);
+        }
+        // task list: for every in-ball child an upper-bound pass and a lower-bound pass
+        struct Slot { size_t cube; int child; int pass; };
+        std::vector<Slot> slots;
+        std::vector<CubeEval> evs(cubes.size());
+        int rcl = ensure_task_buffers(h, cubes.size() * 16 + 64); if (rcl) return rcl;
+        int n = 0;
+        for (size_t ci = 0; ci < cubes.size(); ci++) {
+            const RotNode& P = cubes[ci];
+            if (P.l + 1 >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "rotation search reached level 20 (the reference indexes maxRotDis out of bounds there)");
+            const float w = P.w / 2;
+            for (int j = 0; j < 8; j++) {
+                const float a = P.a + (j & 1) * w, b = P.b + (j >> 1 & 1) * w, cc = P.c + (j >> 2 & 1) * w;
+                ChildEval& ce = evs[ci].ch[j];
+                ce.skipped = !cube_rotation(a, b, cc, w, ce.R);
+                if (ce.skipped) continue;
+                for (int pass = 0; pass < 2; pass++) {
+                    InnerTask& t = h->h_tasks[n++];
+                    std::memcpy(t.R, ce.R, sizeof ce.R);
+                    t.level = pass == 0 ? -1 : P.l + 1;              // maxRotDis[nodeRot.l] (jly_goicp.cpp:551)
+                    t.opt_error = E; t.pad = 0;
+                    slots.push_back(Slot{ci, j, pass});
+                }
+            }
+        }
+        rcl = run_inner_batch(h, c, n, &res.bound_evals_executed); if (rcl) return rcl;
+        res.rounds++;
+        for (int t = 0; t < n; t++) {
+            ChildEval& ce = evs[slots[t].cube].ch[slots[t].child];
+            (slots[t].pass == 0 ? ce.ub : ce.lb) = h->h_results[t];
+        }
+        for (size_t ci = 0; ci < cubes.size(); ci++) { evs[ci].epoch = epoch; cache[key_of(cubes[ci])] = evs[ci]; }
+        return GOICP_OK;
+    };
+
+    int exit_path = GOICP_EXIT_NONE;
+    float exit_lb = 0;
+    while (exit_path == GOICP_EXIT_NONE) {
+        if (h->cancel_flag.load()) { exit_path = GOICP_EXIT_CANCELLED; break; }           // goicp_finished (jly_goicp.cpp:400)
+        if (heap.empty()) { exit_path = GOICP_EXIT_QUEUE_EMPTY; break; }                  // :402-407
+        RotNode P = heap.front();
+        if ((E - P.lb) <= h->sse_thresh) {                                                // :416-420
+            std::pop_heap(heap.begin(), heap.end(), lower); heap.pop_back(); res.rot_pops++;
+            exit_path = GOICP_EXIT_CERTIFIED; exit_lb = P.lb; break;
+        }
+        {
+            auto it = cache.find(key_of(P));
+            if (it == cache.end() || it->second.epoch != epoch) { rc = evaluate_round(P); if (rc) return rc; }
+        }
+        std::pop_heap(heap.begin(), heap.end(), lower); heap.pop_back(); res.rot_pops++;
+        const CubeKey pk = key_of(P);
+        int j0 = 0; bool skip_ub = false;
+        bool restart = true;
+        while (restart && exit_path == GOICP_EXIT_NONE) {
+            restart = false;
+            const CubeEval ev = cache[pk];
+            const float w = P.w / 2;
+            for (int j = j0; j < 8; j++) {
+                const ChildEval& ce = ev.ch[j];
+                if (ce.skipped) continue;
+                RotNode nd; nd.w = w; nd.l = P.l + 1;
+                nd.a = P.a + (j & 1) * w; nd.b = P.b + (j >> 1 & 1) * w; nd.c = P.c + (j >> 2 & 1) * w;
+                float ub = ce.ub.value;
+                if (!(j == j0 && skip_ub)) {
+                    res.trans_pops += ce.ub.pops; res.bound_evals += ce.ub.evals;
+                    if (ub < E) {                                                          // :495-544
+                        E = ub;
+                        std::memcpy(optR, ce.R, sizeof optR);
+                        optT[0] = ce.ub.node[0] + ce.ub.node[3] / 2; optT[1] = ce.ub.node[1] + ce.ub.node[3] / 2; optT[2] = ce.ub.node[2] + ce.ub.node[3] / 2;
+                        float R_icp[9], t_icp[3], error;
+                        std::memcpy(R_icp, optR, sizeof optR); std::memcpy(t_icp, optT, sizeof optT);
+                        rc = icp_then_dt(h, c, R_icp, t_icp, &error); if (rc) return rc;
+                        res.icp_calls++;
+                        if (error < E) { E = error; std::memcpy(optR, R_icp, sizeof optR); std::memcpy(optT, t_icp, sizeof optT); }
+                        sync_res(); publish(h, res, 0);
+                        if (E < h->sse_thresh) { exit_path = GOICP_EXIT_EARLY_SSE; break; }       // :527-530
+                        {   // discard queue nodes with lb >= E, rebuilding in pop order (:533-543)
+                            std::vector<RotNode> fresh;
+                            while (!heap.empty()) {
+                                std::pop_heap(heap.begin(), heap.end(), lower);
+                                RotNode n2 = heap.back(); heap.pop_back();
+                                if (n2.lb < E) { fresh.push_back(n2); std::push_heap(fresh.begin(), fresh.end(), lower); }
+                                else break;
+                            }
+                            heap.swap(fresh);
+                        }
+                        epoch++; cache.clear();
+                        rc = evaluate_round(P); if (rc) return rc;                        // rest of P under the new E
+                        j0 = j; skip_ub = true; restart = true;
+                        break;
+                    }
+                }
+                const float lb = ce.lb.value;                                              // :551
+                res.trans_pops += ce.lb.pops; res.bound_evals += ce.lb.evals;
+                if (lb >= E) continue;                                                    // :554
+                nd.ub = ub; nd.lb = lb;
+                heap.push_back(nd); std::push_heap(heap.begin(), heap.end(), lower);      // :560-562
+            }
+            if (!restart) break;
+        }
+        if ((res.rot_pops & 15) == 0) { sync_res(); publish(h, res, 0); }
+    }
+
+    sync_res();
+    res.exit_path = exit_path; res.best_lb = exit_lb;
+    res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp;
+    publish(h, res, 1);
+    *out = res;
+    return exit_path == GOICP_EXIT_CANCELLED ? GOICP_ERR_CANCELLED : GOICP_OK;
+}
+
+} // extern "C"

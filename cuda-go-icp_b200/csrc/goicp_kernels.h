@@ -1,0 +1,46 @@
+// goicp_kernels.h -- host-callable launchers of the CUDA kernels (implemented in *.cu).
+#pragma once
+#include "goicp_types.h"
+
+namespace goicp {
+
+// ---- bnb_kernels.cu ---------------------------------------------------------------------
+cudaError_t launch_dt_lookup(const DtView& dt, const float* d_q, int n, float* d_out, int32_t* d_idx, cudaStream_t s);
+cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float2* d_out, cudaStream_t s);
+cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
+cudaError_t inner_bnb_configure(int max_dyn_smem);
+cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n,
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, cudaStream_t s);
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_out, cudaStream_t s);
+
+// ---- icp_kernels.cu ---------------------------------------------------------------------
+// Flattened copy of the reference-ordered kd-tree (built on the host by kdtree_host.cpp).
+struct KdNode {             // 32 B
+    int32_t child1, child2; // -1/-1 = leaf
+    int32_t left, right;    // leaf: [left,right) into vind
+    int32_t divfeat;
+    float divlow, divhigh;
+    int32_t pad;
+};
+struct KdView {
+    const KdNode* __restrict__ nodes;
+    const int32_t* __restrict__ vind;
+    const float4* __restrict__ pts_leaf;   // model points permuted into leaf order: x,y,z,(original index as int bits)
+    const float* __restrict__ model;       // original xyz triples
+    int nm;
+    float bb_lo[3], bb_hi[3];
+};
+struct IcpState {           // lives in device memory; written by block 0 of the ICP kernel
+    float R[9], t[3];
+    float mu_m[3], mu_d[3];
+    float err, err_new;
+    int iter, converged;
+    double sums[16];
+};
+cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);
+// Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
+cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, double* d_partials,
+                       int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s);
+int icp_max_grid_blocks(int device);
+
+} // namespace goicp

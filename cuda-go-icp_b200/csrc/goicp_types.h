@@ -1,0 +1,61 @@
+// goicp_types.h -- plain structs shared between the host engine and the kernels.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "goicp_device.cuh"
+
+namespace goicp {
+
+constexpr int kMaxRotLevel = 20;        // MAXROTLEVEL, jly_goicp.h:78
+constexpr int kMaxTransLevel = 21;      // 3 path bits per level in a 64-bit word
+constexpr int kBnbThreads = 512;        // CTA size of the translation-BnB / bound kernels
+constexpr int kBnbWarps = kBnbThreads / 32;
+
+// Everything a bound evaluation needs that is constant over a Register() call.
+struct BnbConst {
+    DtView dt;
+    const float4* __restrict__ data;    // data cloud: x, y, z, ||p|| (normData, jly_goicp.cpp:143-147)
+    int nd;
+    int inlier_num;                     // == nd unless trimming
+    float sse_thresh;                   // SSEThresh (jly_goicp.cpp:208)
+    float tx, ty, tz, tw;               // initNodeTrans (jly_goicp.cpp:50-53)
+    float cgamma[kMaxRotLevel];         // 2*sinf(maxAngle_l/2): maxRotDis[l][i] = cgamma[l]*||p_i|| (jly_goicp.cpp:150-160)
+};
+
+// One inner (translation) BnB to run: a rotation-cube child and a pass.
+struct InnerTask {
+    float R[9];          // rotation of the cube centre, row-major (computed on the host with glibc
+                         // sincosf exactly like jly_goicp.cpp:449-467)
+    int32_t level;       // rotation level for the lower-bound pass, -1 for the upper-bound pass
+    float opt_error;     // optError the sequential reference would hold when making this call
+    int32_t pad;
+};
+
+struct InnerResult {
+    float value;         // optErrorT returned by InnerBnB
+    float node[4];       // best translation cube (x,y,z,w) of the ub pass
+    uint32_t pops;       // tNodeCount increments of this call
+    uint32_t evals;      // bound evaluations of this call
+    int32_t status;      // goicp_status
+    uint32_t max_heap;
+    uint32_t pad[2];
+};
+
+// Translation-BnB heap entry (16 B): lb, level, and the octant path from the root cube.
+// Priority order of std::priority_queue<TRANSNODE> (jly_goicp.h:60-72): lower lb first,
+// equal lb -> larger w first == smaller level first.
+struct __align__(16) HeapEntry {
+    float lb;
+    uint32_t level;
+    uint32_t path_lo, path_hi;
+};
+
+// A generic (rotation, translation cube) pair for goicp_eval_bounds.
+struct PairTask {
+    float R[9];
+    int32_t level;
+    float tc[4];
+    int32_t pad[2];
+};
+
+} // namespace goicp

@@ -1,0 +1,444 @@
+// icp_kernels.cu -- ICP refinement on sm_100a: reference-ordered kd-tree nearest neighbour,
+// fused transform + NN + moment reduction, device-side 3x3 SVD / Procrustes and SE(3) compose,
+// all iterations inside ONE cooperative kernel (no host round trip per iteration).
+//
+// Replaces ICP3D<float>::Run (jly_icp3d.hpp:180-295), KDTreeSingleIndexAdaptor::searchLevel
+// (nanoflann_goicp.hpp:1136-1184) and Matrix::svd (matrix.cpp:602-830) for the GPU.
+#include <cooperative_groups.h>
+#include "goicp_kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace goicp {
+
+constexpr int kIcpThreads = 128;
+constexpr int kKdStack = 64;
+
+// ------------------------------------------------------------------------------------------
+// Exact 1-NN with the reference's traversal order.  The reference recursion
+//     search(best child); if (mindistsq + cut - dists[idx] <= worst) search(other child)
+// is unrolled onto an explicit stack; leaves are scanned in ascending vind order and a point is
+// accepted only if strictly closer than the incumbent, so the first-visited of several
+// exactly-equidistant model points wins, as in the reference (nanoflann_goicp.hpp:95-116,1143-1150).
+// ------------------------------------------------------------------------------------------
+struct KdFrame { int32_t other; float m2; int32_t idx; float cut; float dst; int32_t state; };
+
+__device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
+
+__device__ int kd_nearest(const KdView& kd, float qx, float qy, float qz, float& d2_out)
+{
+    float worst = 3.402823466e+38f;     // KNNResultSet::init (nanoflann_goicp.hpp:79)
+    int best = 0;
+    float ds0 = 0.0f, ds1 = 0.0f, ds2 = 0.0f;
+    float distsq = 0.0f;                // computeInitialDistances (:1113-1130)
+    {
+        const float q[3] = {qx, qy, qz};
+        float ds[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (q[i] < kd.bb_lo[i]) { float d = q[i] - kd.bb_lo[i]; ds[i] = d * d; distsq += ds[i]; }
+            if (q[i] > kd.bb_hi[i]) { float d = q[i] - kd.bb_hi[i]; ds[i] = d * d; distsq += ds[i]; }
+        }
+        ds0 = ds[0]; ds1 = ds[1]; ds2 = ds[2];
+    }
+    KdFrame stack[kKdStack];
+    int sp = 0;
+    int cur = 0;
+    float cur_min = distsq;
+    for (;;) {
+        // descend along the preferred children
+        for (;;) {
+            const KdNode nd = kd.nodes[cur];
+            if (nd.child1 < 0 && nd.child2 < 0) {
+                const float worst_at_entry = worst;          // cached once per leaf (:1143)
+                for (int i = nd.left; i < nd.right; i++) {
+                    const float4 p = __ldg(kd.pts_leaf + i);
+                    const float d0 = qx - p.x, d1 = qy - p.y, d2 = qz - p.z;
+                    const float dist = d0 * d0 + d1 * d1 + d2 * d2;     // kdtree_distance (jly_icp3d.hpp:48-54)
+                    if (dist < worst_at_entry && worst > dist) { worst = dist; best = __float_as_int(p.w); }
+                }
+                break;
+            }
+            const int idx = nd.divfeat;
+            const float val = sel3(qx, qy, qz, idx);
+            const float diff1 = val - nd.divlow, diff2 = val - nd.divhigh;
+            int bestc, otherc; float cut;
+            if ((diff1 + diff2) < 0) { bestc = nd.child1; otherc = nd.child2; cut = (val - nd.divhigh) * (val - nd.divhigh); }
+            else                     { bestc = nd.child2; otherc = nd.child1; cut = (val - nd.divlow) * (val - nd.divlow); }
+            const float dst = sel3(ds0, ds1, ds2, idx);
+            if (sp < kKdStack) {
+                KdFrame& f = stack[sp++];
+                f.other = otherc; f.m2 = cur_min + cut - dst; f.idx = idx; f.cut = cut; f.dst = dst; f.state = 0;
+            }
+            cur = bestc;
+        }
+        // unwind
+        bool descend = false;
+        while (sp > 0) {
+            KdFrame& f = stack[sp - 1];
+            if (f.state == 0) {
+                if (f.m2 * 1.0f <= worst) {       // epsError = 1 (:809, :1178)
+                    f.state = 1;
+                    if (f.idx == 0) ds0 = f.cut; else if (f.idx == 1) ds1 = f.cut; else ds2 = f.cut;
+                    cur = f.other; cur_min = f.m2; descend = true;
+                    break;
+                }
+                sp--;
+            } else {
+                if (f.idx == 0) ds0 = f.dst; else if (f.idx == 1) ds1 = f.dst; else ds2 = f.dst;
+                sp--;
+            }
+        }
+        if (!descend) break;
+    }
+    d2_out = worst;
+    return best;
+}
+
+__global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t* __restrict__ idx, float* __restrict__ d2)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d;
+    idx[i] = kd_nearest(kd, q[3 * i], q[3 * i + 1], q[3 * i + 2], d);
+    d2[i] = d;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 SVD: Numerical-Recipes svdcmp in float with the reference's double promotions, followed by
+// the descending sort and the sign normalisation (matrix.cpp:602-830).  One thread.
+// ------------------------------------------------------------------------------------------
+__device__ float svd_pythag(float a, float b)
+{
+    float absa = fabsf(a), absb = fabsf(b);
+    if (absa > absb) { float r = absb / absa; return (float)((double)absa * sqrt(1.0 + (r == 0.0f ? 0.0 : (double)(r * r)))); }
+    if (absb == 0.0f) return 0.0f;
+    float r = absa / absb;
+    return (float)((double)absb * sqrt(1.0 + (r == 0.0f ? 0.0 : (double)(r * r))));
+}
+__device__ __forceinline__ float svd_sign(float a, float b) { return b >= 0.0f ? fabsf(a) : -fabsf(a); }
+
+__device__ void svd3_ref(const float* A9, float* U9, float* W3, float* V9)
+{
+    const int m = 3, n = 3;
+    float U[3][3], V[3][3], w[3], rv1[3];
+    int flag, i, its, j, jj, k, l = 0, nm = 0;
+    float anorm, c, f, g, h, s, scale, x, y, z;
+    for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { U[i][j] = A9[3 * i + j]; V[i][j] = 0.0f; }
+    g = scale = anorm = 0.0f;
+    for (i = 0; i < n; i++) {
+        l = i + 1;
+        rv1[i] = scale * g;
+        g = s = scale = 0.0f;
+        if (i < m) {
+            for (k = i; k < m; k++) scale += fabsf(U[k][i]);
+            if (scale != 0.0f) {
+                for (k = i; k < m; k++) { U[k][i] /= scale; s += U[k][i] * U[k][i]; }
+                f = U[i][i];
+                g = -svd_sign(sqrtf(s), f);
+                h = f * g - s;
+                U[i][i] = f - g;
+                for (j = l; j < n; j++) {
+                    for (s = 0.0f, k = i; k < m; k++) s += U[k][i] * U[k][j];
+                    f = s / h;
+                    for (k = i; k < m; k++) U[k][j] += f * U[k][i];
+                }
+                for (k = i; k < m; k++) U[k][i] *= scale;
+            }
+        }
+        w[i] = scale * g;
+        g = s = scale = 0.0f;
+        if (i < m && i != n - 1) {
+            for (k = l; k < n; k++) scale += fabsf(U[i][k]);
+            if (scale != 0.0f) {
+                for (k = l; k < n; k++) { U[i][k] /= scale; s += U[i][k] * U[i][k]; }
+                f = U[i][l];
+                g = -svd_sign(sqrtf(s), f);
+                h = f * g - s;
+                U[i][l] = f - g;
+                for (k = l; k < n; k++) rv1[k] = U[i][k] / h;
+                for (j = l; j < m; j++) {
+                    for (s = 0.0f, k = l; k < n; k++) s += U[j][k] * U[i][k];
+                    for (k = l; k < n; k++) U[j][k] += s * rv1[k];
+                }
+                for (k = l; k < n; k++) U[i][k] *= scale;
+            }
+        }
+        { float t2 = fabsf(w[i]) + fabsf(rv1[i]); anorm = anorm > t2 ? anorm : t2; }
+    }
+    for (i = n - 1; i >= 0; i--) {
+        if (i < n - 1) {
+            if (g != 0.0f) {
+                for (j = l; j < n; j++) V[j][i] = (U[i][j] / U[i][l]) / g;
+                for (j = l; j < n; j++) {
+                    for (s = 0.0f, k = l; k < n; k++) s += U[i][k] * V[k][j];
+                    for (k = l; k < n; k++) V[k][j] += s * V[k][i];
+                }
+            }
+            for (j = l; j < n; j++) V[i][j] = V[j][i] = 0.0f;
+        }
+        V[i][i] = 1.0f;
+        g = rv1[i];
+        l = i;
+    }
+    for (i = 2; i >= 0; i--) {
+        l = i + 1;
+        g = w[i];
+        for (j = l; j < n; j++) U[i][j] = 0.0f;
+        if (g != 0.0f) {
+            g = (float)(1.0 / (double)g);
+            for (j = l; j < n; j++) {
+                for (s = 0.0f, k = l; k < m; k++) s += U[k][i] * U[k][j];
+                f = (s / U[i][i]) * g;
+                for (k = i; k < m; k++) U[k][j] += f * U[k][i];
+            }
+            for (j = i; j < m; j++) U[j][i] *= g;
+        } else for (j = i; j < m; j++) U[j][i] = 0.0f;
+        U[i][i] = U[i][i] + 1.0f;
+    }
+    for (k = n - 1; k >= 0; k--) {
+        for (its = 0; its < 30; its++) {
+            flag = 1;
+            for (l = k; l >= 0; l--) {
+                nm = l - 1;
+                if ((float)(fabsf(rv1[l]) + anorm) == anorm) { flag = 0; break; }
+                if (nm >= 0 && (float)(fabsf(w[nm]) + anorm) == anorm) break;
+            }
+            if (l < 0) l = 0;
+            if (flag) {
+                c = 0.0f; s = 1.0f;
+                for (i = l; i <= k; i++) {
+                    f = s * rv1[i];
+                    rv1[i] = c * rv1[i];
+                    if ((float)(fabsf(f) + anorm) == anorm) break;
+                    g = w[i];
+                    h = svd_pythag(f, g);
+                    w[i] = h;
+                    h = (float)(1.0 / (double)h);
+                    c = g * h;
+                    s = -f * h;
+                    for (j = 0; j < m; j++) {
+                        y = U[j][nm]; z = U[j][i];
+                        U[j][nm] = y * c + z * s;
+                        U[j][i] = z * c - y * s;
+                    }
+                }
+            }
+            z = w[k];
+            if (l == k) {
+                if (z < 0.0f) { w[k] = -z; for (j = 0; j < n; j++) V[j][k] = -V[j][k]; }
+                break;
+            }
+            x = w[l]; nm = k - 1; y = w[nm]; g = rv1[nm]; h = rv1[k];
+            f = (float)((double)((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * (double)h * (double)y));
+            g = svd_pythag(f, 1.0f);
+            f = ((x - z) * (x + z) + h * ((y / (f + svd_sign(g, f))) - h)) / x;
+            c = s = 1.0f;
+            for (j = l; j <= nm; j++) {
+                i = j + 1;
+                g = rv1[i]; y = w[i];
+                h = s * g; g = c * g;
+                z = svd_pythag(f, h);
+                rv1[j] = z;
+                c = f / z; s = h / z;
+                f = x * c + g * s;
+                g = g * c - x * s;
+                h = y * s;
+                y *= c;
+                for (jj = 0; jj < n; jj++) {
+                    x = V[jj][j]; z = V[jj][i];
+                    V[jj][j] = x * c + z * s;
+                    V[jj][i] = z * c - x * s;
+                }
+                z = svd_pythag(f, h);
+                w[j] = z;
+                if (z != 0.0f) { z = (float)(1.0 / (double)z); c = f * z; s = h * z; }
+                f = c * g + s * y;
+                x = c * y - s * g;
+                for (jj = 0; jj < m; jj++) {
+                    y = U[jj][j]; z = U[jj][i];
+                    U[jj][j] = y * c + z * s;
+                    U[jj][i] = z * c - y * s;
+                }
+            }
+            rv1[l] = 0.0f; rv1[k] = f; w[k] = x;
+        }
+    }
+    // descending sort (insertion with gap 1 for n=3) + sign normalisation (matrix.cpp:783-818)
+    for (i = 1; i < n; i++) {
+        float sw = w[i], su[3], sv[3];
+        for (k = 0; k < 3; k++) { su[k] = U[k][i]; sv[k] = V[k][i]; }
+        j = i;
+        while (w[j - 1] < sw) {
+            w[j] = w[j - 1];
+            for (k = 0; k < 3; k++) { U[k][j] = U[k][j - 1]; V[k][j] = V[k][j - 1]; }
+            j -= 1;
+            if (j < 1) break;
+        }
+        w[j] = sw;
+        for (k = 0; k < 3; k++) { U[k][j] = su[k]; V[k][j] = sv[k]; }
+    }
+    for (k = 0; k < n; k++) {
+        int s2 = 0;
+        for (i = 0; i < 3; i++) if (U[i][k] < 0.0f) s2++;
+        for (j = 0; j < 3; j++) if (V[j][k] < 0.0f) s2++;
+        if (s2 > 3) {
+            for (i = 0; i < 3; i++) U[i][k] = -U[i][k];
+            for (j = 0; j < 3; j++) V[j][k] = -V[j][k];
+        }
+    }
+    for (i = 0; i < 3; i++) { W3[i] = w[i]; for (j = 0; j < 3; j++) { U9[3 * i + j] = U[i][j]; V9[3 * i + j] = V[i][j]; } }
+}
+
+__device__ void mat3_mul(const float* A, const float* B, float* C)   // accumulate from 0 in k order (matrix.cpp:287-301)
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        float acc = 0.0f;
+        for (int k = 0; k < 3; k++) acc += A[3 * i + k] * B[3 * k + j];
+        C[3 * i + j] = acc;
+    }
+}
+
+// Procrustes step + SE(3) composition (jly_icp3d.hpp:259-291) from the 16 reduced moments:
+// sums[0..2]=sum m, [3..5]=sum q, [6..14]=sum q_a m_b, [15]=sum d^2 ; q = transformed data point.
+__device__ void icp_update(IcpState* st, const double* sums, int n, int num)
+{
+    for (int c = 0; c < 3; c++) {
+        // mu accumulates on top of the PREVIOUS mean (never reset, :205-206) and is divided by n (:262-263)
+        float sm = (float)((double)st->mu_m[c] + sums[c]);
+        float sd = (float)((double)st->mu_d[c] + sums[3 + c]);
+        st->mu_m[c] = sm / (float)n;
+        st->mu_d[c] = sd / (float)n;
+    }
+    float H[9];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        double md = st->mu_d[a], mm = st->mu_m[b];
+        H[3 * a + b] = (float)(sums[6 + 3 * a + b] - md * sums[b] - sums[3 + a] * mm + (double)num * md * mm);
+    }
+    float U[9], W[3], V[9], Ut[9], Rn[9], VT[9], tmp[9];
+    svd3_ref(H, U, W, V);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ut[3 * j + i] = U[3 * i + j];
+    mat3_mul(V, Ut, Rn);
+    float da = Rn[0] * (Rn[4] * Rn[8] - Rn[5] * Rn[7]);
+    float db = -Rn[1] * (Rn[3] * Rn[8] - Rn[5] * Rn[6]);
+    float dc = Rn[2] * (Rn[3] * Rn[7] - Rn[4] * Rn[6]);
+    float det = da + db + dc;
+    float D[9] = {1, 0, 0, 0, 1, 0, 0, 0, det};
+    mat3_mul(V, D, VT);
+    mat3_mul(VT, Ut, Rn);
+    float tn[3], tt[3];
+    for (int a = 0; a < 3; a++) {
+        float acc = 0.0f;
+        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->mu_d[k];
+        tn[a] = st->mu_m[a] - acc;
+    }
+    mat3_mul(Rn, st->R, tmp);
+    for (int a = 0; a < 3; a++) {
+        float acc = 0.0f;
+        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->t[k];
+        tt[a] = acc + tn[a];
+    }
+    for (int i = 0; i < 9; i++) st->R[i] = tmp[i];
+    for (int i = 0; i < 3; i++) st->t[i] = tt[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// ICP3D::Run as one cooperative kernel.  Per iteration: every thread transforms its data points
+// (float, reference order), finds the nearest model point, and accumulates 16 moments in double;
+// fixed-order block + grid reduction; block 0 thread 0 applies the convergence test (:257), the
+// stale-mean quirk, the SVD and the compose; one grid.sync() publishes the new pose.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIcpThreads)
+icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, double* partials,
+           int max_iter, float err_diff, int num)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double wsum[kIcpThreads / 32][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+
+    for (int iter = 0; iter < max_iter; iter++) {
+        float R[9], t[3];
+        const volatile IcpState* vst = st;       // re-read the pose published by block 0
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = vst->R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) t[i] = vst->t[i];
+        double acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = 0.0;
+        for (int i = gtid; i < nd; i += gsize) {
+            const float4 p = __ldg(data + i);
+            // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
+            const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+            const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+            const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+            float d2;
+            const int id = kd_nearest(kd, qx, qy, qz, d2);
+            const float mx = __ldg(kd.model + 3 * id), my = __ldg(kd.model + 3 * id + 1), mz = __ldg(kd.model + 3 * id + 2);
+            acc[0] += mx; acc[1] += my; acc[2] += mz;
+            acc[3] += qx; acc[4] += qy; acc[5] += qz;
+            acc[6] += (double)qx * mx; acc[7] += (double)qx * my; acc[8] += (double)qx * mz;
+            acc[9] += (double)qy * mx; acc[10] += (double)qy * my; acc[11] += (double)qy * mz;
+            acc[12] += (double)qz * mx; acc[13] += (double)qz * my; acc[14] += (double)qz * mz;
+            acc[15] += d2;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) wsum[warp][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            double v = 0.0;
+            for (int w = 0; w < kIcpThreads / 32; w++) v += wsum[w][threadIdx.x];
+            partials[blockIdx.x * 16 + threadIdx.x] = v;
+        }
+        grid.sync();
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < 16) {
+                double v = 0.0;
+                for (unsigned b = 0; b < gridDim.x; b++) v += partials[b * 16 + threadIdx.x];
+                st->sums[threadIdx.x] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const float err_new = (float)st->sums[15];
+                st->err_new = err_new;
+                st->iter = iter;
+                if (st->err > 0.0f && st->err - err_new < err_diff * (float)num) st->converged = 1;   // :257
+                else { st->err = err_new; icp_update(st, st->sums, nd, num); }
+                __threadfence();
+            }
+        }
+        grid.sync();
+        if (vst->converged) break;
+        if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
+    }
+}
+
+cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    nn_kernel<<<(n + 127) / 128, 128, 0, s>>>(kd, d_q, n, d_idx, d_d2);
+    return cudaGetLastError();
+}
+int icp_max_grid_blocks(int device)
+{
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return per_sm * sms;
+}
+cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, double* d_partials,
+                       int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s)
+{
+    KdView kdv = kd;
+    void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&d_partials,
+                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers};
+    return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args, 0, s);
+}
+
+} // namespace goicp

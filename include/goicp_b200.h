@@ -1,0 +1,180 @@
+/*
+ * goicp_b200.h -- C ABI of the B200-native Go-ICP registration engine.
+ *
+ * The reference (zjsun1017/CUDA-Go-ICP) has no FFI: its boundary is the C++ object protocol
+ * that src/main.cpp and src/goicp_kernel.cu use on `class GoICP` (src/goicp/jly_goicp.h:82-141).
+ * Every entry point below names the piece of that protocol it replaces.  Plain pointers and
+ * sizes only; all buffers are HOST memory owned by the caller unless stated otherwise; the
+ * library copies what it needs to the device.  Every call returns a goicp_status; nothing
+ * exits the process or throws across the boundary (the reference exit()s on CUDA errors,
+ * src/kernel.cu:29-38).  Calls on one handle must be serialised by the caller, except
+ * goicp_poll() and goicp_cancel(), which may be called from another thread while
+ * goicp_register() runs (replaces the unlocked polling of optR/optT/optError from the GL
+ * thread, src/goicp_kernel.cu:82-149, and the global `goicp_finished`, jly_goicp.cpp:36,400).
+ *
+ * There is NO CPU fallback: every numeric entry point runs hand-written sm_100a CUDA and
+ * returns GOICP_ERR_CUDA if no usable device is present.
+ */
+#ifndef GOICP_B200_H
+#define GOICP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct goicp_handle goicp_handle;
+
+typedef enum {
+    GOICP_OK = 0,
+    GOICP_ERR_INVALID = 1,      /* bad argument / call order (e.g. register before build_dt) */
+    GOICP_ERR_CUDA = 2,         /* CUDA runtime failure or no device; see goicp_last_error() */
+    GOICP_ERR_CAPACITY = 3,     /* a device queue/heap overflowed its configured capacity */
+    GOICP_ERR_DEPTH = 4,        /* search needed rotation level >= 20 (reference reads maxRotDis[20] out of bounds, jly_goicp.cpp:551) or translation level > 21 */
+    GOICP_ERR_IO = 5,           /* file / TOML problems (std::runtime_error in the reference, src/common.cpp:25-226) */
+    GOICP_ERR_CANCELLED = 6
+} goicp_status;
+
+/* Which exit the search took (jly_goicp.cpp:402-406, :416-420, :527-530, :400). */
+typedef enum {
+    GOICP_EXIT_NONE = 0,
+    GOICP_EXIT_CERTIFIED = 1,         /* optError - lowest lb <= SSEThresh : global-optimality certificate */
+    GOICP_EXIT_EARLY_SSE = 2,         /* optError < SSEThresh right after an ICP refinement */
+    GOICP_EXIT_QUEUE_EMPTY = 3,
+    GOICP_EXIT_CANCELLED = 4
+} goicp_exit_path;
+
+typedef enum {
+    GOICP_DT_REFERENCE = 0,   /* bit-exact with DT3D::Build's sequential vector propagation (jly_3ddt.cpp:710-742) */
+    GOICP_DT_EXACT_EDT = 1    /* exact Euclidean DT (fast, fully parallel); differs from the reference on a few voxels */
+} goicp_dt_mode;
+
+/* Replaces the public tunables of class GoICP (jly_goicp.h:85-120) and its constructor
+ * defaults (jly_goicp.cpp:40-72). */
+typedef struct {
+    float  mse_threshold;    /* GoICP(float mse_threshold); SSEThresh = mse*inlierNum (jly_goicp.cpp:208) */
+    float  trim_fraction;    /* GoICP::trimFraction (default 0) */
+    int    do_trim;          /* GoICP::doTrim (default 1) */
+    int    dt_size;          /* GoICP::dt.SIZE (default 300) */
+    double dt_expand;        /* GoICP::dt.expandFactor (default 2.0) */
+    float  rot_cube[4];      /* initNodeRot a,b,c,w  (default -pi,-pi,-pi,2pi) */
+    float  trans_cube[4];    /* initNodeTrans x,y,z,w (default -0.5,-0.5,-0.5,1) */
+    int    icp_max_iter;     /* ICP3D::max_iter_def (10000, jly_icp3d.hpp:113) */
+    int    device;           /* CUDA device ordinal */
+    int    spec_cubes;       /* rotation cubes expanded speculatively per round (0 = auto) */
+    int    dt_mode;          /* goicp_dt_mode used by goicp_build_dt */
+    /* multi-GPU sharding of the rotation frontier (all ranks hold identical inputs) */
+    int    rank, world_size;
+} goicp_params;
+
+/* Replaces the public results of class GoICP (optR/optT/optError/optNodeRot/optNodeTrans,
+ * jly_goicp.h:107-120) plus the counters the reference prints (tNodeCount/rNodeCount,
+ * jly_goicp.cpp:34-35,579-580). */
+typedef struct {
+    float  R[9];             /* row-major, x' = R x + t maps data -> model (jly_goicp.cpp:105-107) */
+    float  t[3];
+    float  sse;              /* optError */
+    float  sse_thresh;       /* SSEThresh */
+    float  best_lb;          /* lower bound of the cube popped at the certificate (0 otherwise) */
+    int    exit_path;        /* goicp_exit_path */
+    int64_t rot_pops;        /* rNodeCount */
+    int64_t trans_pops;      /* tNodeCount (committed = what the sequential reference would count) */
+    int64_t bound_evals;     /* committed bound evaluations (body of jly_goicp.cpp:265-336) */
+    int64_t bound_evals_executed;   /* incl. speculative work that was later discarded */
+    int64_t icp_calls;
+    int64_t rounds;          /* device rounds (one batch of rotation cubes each) */
+    double seconds_total, seconds_bnb_kernels, seconds_icp;
+} goicp_result;
+
+typedef struct {
+    float R[9], t[3];
+    float err;               /* return value of ICP3D::Run: sum of squared NN distances of the last iteration */
+    int   iterations;
+} goicp_icp_result;
+
+typedef struct {
+    float R[9], t[3];        /* best so far (optR/optT) */
+    float sse;               /* optError */
+    int64_t rot_pops, trans_pops, bound_evals;
+    int   finished;          /* GoICP::finished */
+} goicp_snapshot;
+
+/* One inner (translation) branch-and-bound: replaces GoICP::InnerBnB (jly_goicp.cpp:227-340). */
+typedef struct {
+    float value;             /* returned optErrorT */
+    float node[4];           /* nodeTransOut x,y,z,w (upper-bound pass only) */
+    uint32_t pops, evals;
+    int32_t status;
+} goicp_inner_result;
+
+void goicp_default_params(goicp_params* p);
+
+/* GoICP::GoICP + ~GoICP */
+int goicp_create(const goicp_params* p, goicp_handle** out);
+int goicp_destroy(goicp_handle* h);
+const char* goicp_last_error(const goicp_handle* h);
+
+/* pModel/Nm, pData/Nd (jly_goicp.h:85-86; borrowed glm::vec3* in the reference, main.cpp:50-53):
+ * packed xyz float triples, copied. */
+int goicp_set_model(goicp_handle* h, const float* xyz, int n);
+int goicp_set_data(goicp_handle* h, const float* xyz, int n);
+
+/* GoICP::BuildDT (jly_goicp.cpp:75-90) on the GPU. */
+int goicp_build_dt(goicp_handle* h);
+/* Install / read back a distance grid ([z][y][x] floats + {xMin,yMin,zMin,scale}); lets a caller
+ * cache the model-only precompute across runs (the reference cannot). */
+int goicp_set_dt(goicp_handle* h, const float* grid, int size, const double meta4[4]);
+int goicp_get_dt(goicp_handle* h, float* grid_out, double meta4_out[4]);
+int goicp_dt_size(const goicp_handle* h);
+
+/* DT3D::Distance (jly_3ddt.cpp:981-1026) for n query points; optionally also the raw voxel
+ * indices ROUND((q-min)*scale) (3 ints per query, un-clamped). */
+int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_out, int32_t* ixyz_out);
+
+/* Batched bound evaluation over (rotation cube x translation cube) pairs -- the unit of work
+ * of the metric (loop body jly_goicp.cpp:265-336).  Pair k: rotation R9[9k..] (row-major, as
+ * produced at jly_goicp.cpp:449-467), rotation level level[k] (-1: no rotation uncertainty, i.e.
+ * the upper-bound pass), translation cube tcube[4k..] = x,y,z,w.  Outputs ub[k], lb[k]. */
+int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_t* level,
+                      const float* tcube, float* ub_out, float* lb_out);
+
+/* n independent inner BnBs (GoICP::InnerBnB): rotation R9[9k..], level[k] (-1 = ub pass),
+ * starting optError opt_error[k]. */
+int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* level,
+                    const float* opt_error, goicp_inner_result* out);
+
+/* Nearest model point of each query in the reference's kd-tree visiting order (ties included):
+ * KDTreeSingleIndexAdaptor::knnSearch(k=1) (nanoflann_goicp.hpp:821-826). */
+int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float* d2_out);
+
+/* ICP3D<float>::Run (jly_icp3d.hpp:180-295) from (R0,t0). err_diff<0 -> mse_threshold/10000
+ * (jly_goicp.cpp:186); max_iter<=0 -> params.icp_max_iter. */
+int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff,
+              goicp_icp_result* out);
+/* GoICP::ICP (jly_goicp.cpp:93-132): ICP then (trimmed) DT re-scoring; returns the DT error. */
+int goicp_icp_dt(goicp_handle* h, float R[9], float t[3], float* dt_error_out);
+/* (trimmed) sum of squared DT distances under (R,t); R==NULL scores the raw data (jly_goicp.cpp:357-371). */
+int goicp_dt_score(goicp_handle* h, const float* R, const float* t, float* sse_out);
+
+/* GoICP::Register (jly_goicp.cpp:569-585): Initialize + OuterBnB; blocking. */
+int goicp_register(goicp_handle* h, goicp_result* out);
+int goicp_poll(goicp_handle* h, goicp_snapshot* out);
+int goicp_cancel(goicp_handle* h);
+
+/* Multi-GPU: every rank evaluates its slice of each round's cubes; `exchange` must all-gather
+ * `bytes_per_rank` bytes from every rank into recv (rank-major).  The Python driver implements it
+ * with torch.distributed (NCCL on device buffers is_device=1, gloo on host buffers). */
+typedef int (*goicp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank, int is_device);
+int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int use_device_buffers);
+
+/* Convenience driver over the reference's TOML keys (src/common.cpp:39-74) and cloud formats
+ * (src/common.cpp:79-228): loads [io].target/source (.txt / .ply), applies subsample (seeded)
+ * and resize, builds the DT, registers, writes [io].output if non-empty. */
+int goicp_run_toml(const char* toml_path, unsigned seed_model, unsigned seed_data, goicp_result* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOICP_B200_H */

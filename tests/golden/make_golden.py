@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.json|*.f32|*.npz from the UNMODIFIED reference (oracle/_ref).
+
+Run in the build container only (needs /root/reference and `make -C oracle ref`):
+
+    python tests/golden/make_golden.py clouds      # deterministic bunny subsamples (seeds 1234/1235)
+    python tests/golden/make_golden.py runs        # 5 full reference Go-ICP runs, S=300 (~13 min CPU)
+    python tests/golden/make_golden.py small       # small-S DT grids / NN / ICP / inner-BnB vectors (seconds)
+
+The committed fixtures were produced by exactly these commands; the GPU box never runs this.
+"""
+import json, os, re, subprocess, sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REFBIN = os.path.join(ROOT, "oracle", "_ref", "ref_goicp")
+REFDATA = "/root/reference/data"
+
+RUNS = {  # name: (model fixture, data fixture, mse, trim)
+    "bunny_s0.1_mse1e-3": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "1e-3", "0"),
+    "bunny_s0.1_mse7e-4": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "7e-4", "0"),
+    "bunny_s0.1_mse5e-4": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "5e-4", "0"),
+    "bunny_s0.033_mse1e-3": ("bunny_model_s0.033_seed1234.f32", "bunny_data_s0.033_seed1235.f32", "1e-3", "0"),
+    "bunny_s0.1_mse1e-3_trim0.1": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "1e-3", "0.1"),
+}
+
+
+def clouds():
+    for sub in ("0.1", "0.033"):
+        for kind, seed in (("model", 1234), ("data", 1235)):
+            out = os.path.join(HERE, f"bunny_{kind}_s{sub}_seed{seed}.f32")
+            subprocess.run([REFBIN, "subsample", f"{REFDATA}/bunny/{kind}_bunny.txt", sub, "1.0", str(seed), out], check=True)
+
+
+def parse_run(text):
+    """REFJSON line + the reference's own 'Error*:' narration (improvement sequence) + certificate line."""
+    js = json.loads(re.search(r"REFJSON (\{.*\})", text).group(1))
+    js["improvements"] = [float(x) for x in re.findall(r"^Error\*: ([0-9.eE+-]+)", text, re.M)]
+    m = re.search(r"Error\*: [0-9.eE+-]+, LB: ([0-9.eE+-]+), epsilon: ([0-9.eE+-]+)", text)
+    js["exit_path"] = "certified" if m else "early_sse_below_thresh"
+    if m:
+        js["exit_lb"] = float(m.group(1))
+        js["improvements"] = js["improvements"][:-1]  # the certificate line also starts with "Error*:"
+    js["icp_calls"] = len(re.findall(r"\(ICP ", text)) and None
+    js["bound_evals_plus_icp"] = js["select_calls"] - 1
+    return js
+
+
+def runs(from_logs=None):
+    out = {}
+    for name, (m, d, mse, trim) in RUNS.items():
+        if from_logs and os.path.exists(os.path.join(from_logs, name + ".log")):
+            text = open(os.path.join(from_logs, name + ".log")).read()
+        else:
+            text = subprocess.run([REFBIN, "goicp", os.path.join(HERE, m), os.path.join(HERE, d), mse, trim],
+                                  check=True, capture_output=True, text=True).stdout
+        out[name] = parse_run(text)
+        out[name]["model"], out[name]["data"] = m, d
+        print(name, out[name]["sse"], out[name]["rot_pops"], out[name]["trans_pops"])
+    json.dump(out, open(os.path.join(HERE, "goicp_runs.json"), "w"), indent=1)
+
+
+def small():
+    from oracle.oracle import Reference
+    rf = Reference()
+    model = np.fromfile(os.path.join(HERE, "bunny_model_s0.1_seed1234.f32"), np.float32).reshape(-1, 3)
+    data = np.fromfile(os.path.join(HERE, "bunny_data_s0.1_seed1235.f32"), np.float32).reshape(-1, 3)
+    model_s = np.fromfile(os.path.join(HERE, "bunny_model_s0.033_seed1234.f32"), np.float32).reshape(-1, 3)
+    data_s = np.fromfile(os.path.join(HERE, "bunny_data_s0.033_seed1235.f32"), np.float32).reshape(-1, 3)
+    rng = np.random.default_rng(20261018)
+    g = {}
+    # --- DT: full grid at S=48 (+ propagation vectors), meta + FNV at S=300
+    S = 48
+    dt = rf.dt_build(model, S, 2.0)
+    g["dt48_meta"] = rf.dt_meta(dt)
+    g["dt48_grid"] = rf.dt_grid(dt, S)
+    g["dt48_vec"] = rf.dt_vectors(dt, S)
+    q = np.concatenate([data, rng.uniform(-2.6, 2.6, (4000, 3)).astype(np.float32)])
+    g["dt48_query"] = q
+    g["dt48_dist"] = rf.dt_distance(dt, q)
+    # --- NN (incl. ties on a lattice with duplicates) + one ICP3D::Run
+    icp = rf.icp_build(model)
+    g["nn_idx"], g["nn_d2"] = rf.icp_nn(icp, data)
+    lat = np.stack(np.meshgrid(*[np.arange(6)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lat = np.concatenate([lat, lat[::3]])
+    ql = (rng.integers(0, 11, (2000, 3)) / 2).astype(np.float32)
+    icpl = rf.icp_build(lat)
+    g["lat_model"], g["lat_query"] = lat, ql
+    g["lat_idx"], g["lat_d2"] = rf.icp_nn(icpl, ql)
+    for trim in (0.0, 0.1):
+        e, R, t = rf.icp_run(icp, data, np.eye(3), np.zeros(3), 10000, 1e-7, trim, True)
+        g[f"icp_trim{trim}_err"], g[f"icp_trim{trim}_R"], g[f"icp_trim{trim}_t"] = np.float32(e), R, t
+    H = (rng.normal(size=(32, 3, 3)) * 10 ** rng.uniform(-3, 3, (32, 1, 1))).astype(np.float32)
+    H[::8, :, 2] = H[::8, :, 0]
+    g["svd_H"] = H
+    g["svd_U"], g["svd_W"], g["svd_V"] = (np.stack(x) for x in zip(*[rf.svd3(h) for h in H]))
+    # --- inner BnB known answers on a coarse DT (S=64), small cloud
+    gg = rf.create(model_s, data_s[::2].copy(), 1e-3, 0.0, 64)
+    rf.build_dt(gg)
+    rf.initialize(gg)
+    g["inner_meta"] = rf.dt_meta(rf.goicp_dt(gg))
+    g["inner_grid"] = rf.dt_grid(rf.goicp_dt(gg), 64)
+    g["inner_gamma"] = np.stack([rf.max_rot_dis(gg, l, len(data_s[::2])) for l in range(20)])
+    rows = []
+    from oracle.oracle import Restated
+    rs = Restated()
+    for k in range(24):
+        a, b, c = rng.uniform(-np.pi, np.pi / 2, 3)
+        w = np.pi / 2 ** (k % 4)
+        ok, R = rs.cube_rotation(a, b, c, w)   # rotation formula only; pinned separately against the full runs
+        if not ok:
+            continue
+        for lvl in (-1, 1 + k % 4):
+            oe = [1e10, 15.6, 3.0][k % 3]
+            r = rf.inner(gg, R, lvl, oe)
+            rows.append(np.concatenate([R.ravel(), [lvl, oe, r["value"]], r["node"], [r["pops"], r["evals"]]]))
+    g["inner_cases"] = np.array(rows, np.float64)
+    np.savez_compressed(os.path.join(HERE, "small_vectors.npz"), **g)
+    print({k: (v.shape if hasattr(v, "shape") else v) for k, v in g.items()})
+
+
+if __name__ == "__main__":
+    cmd = sys.argv[1]
+    if cmd == "clouds":
+        clouds()
+    elif cmd == "runs":
+        runs(sys.argv[2] if len(sys.argv) > 2 else None)
+    elif cmd == "small":
+        small()

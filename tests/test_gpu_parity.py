@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): DT voxel indices and NN indices bit-exact; final R within
+1e-4 rad, t within 1e-4 units, SSE within 1e-5 relative, same certificate / exit path.
+Per-evaluation bound sums are float32 sums taken in a different (parallel, fixed) order than the
+reference's sequential loop, hence 2e-6 relative there.
+"""
+import numpy as np
+import pytest
+
+from conftest import rot_angle
+
+pytestmark = pytest.mark.gpu
+
+SUM_RTOL = 4e-6
+
+
+@pytest.fixture(scope="module")
+def eng_small(pkg, small, bunny):
+    """engine on the golden S=64 inner-BnB fixture (data = every 2nd point of the 0.033 subsample)"""
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model_s"], bunny["data_s"][::2].copy()
+    g.dt.SIZE = 64
+    g.SetDT(small["inner_grid"], small["inner_meta"])
+    yield g
+    g.close()
+
+
+def test_dt_distance_and_voxel_indices_bit_exact(pkg, small, restated, bunny):
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.SetDT(small["dt48_grid"], small["dt48_meta"])
+    d, idx = g.Distance(small["dt48_query"], with_index=True)
+    assert np.array_equal(d.view(np.uint32), small["dt48_dist"].view(np.uint32))
+    dt = restated.dt_wrap(small["dt48_grid"], 48, small["dt48_meta"])
+    assert np.array_equal(idx, restated.dt_index(dt, small["dt48_query"]))
+    # raw-data score = initial error of OuterBnB
+    ref = restated.dt_distance(dt, bunny["data"]).astype(np.float64)
+    assert g.DTScore() == pytest.approx(float((ref ** 2).sum()), rel=SUM_RTOL)
+    g.close()
+
+
+def test_eval_bounds_pairs(eng_small, small, restated, bunny):
+    data = bunny["data_s"][::2].copy()
+    dt = restated.dt_wrap(small["inner_grid"], 64, small["inner_meta"])
+    cases = small["inner_cases"]
+    rng = np.random.default_rng(5)
+    R, lvl, tc = [], [], []
+    for row in cases[:16]:
+        for _ in range(4):
+            w = 2.0 ** -rng.integers(0, 6)
+            R.append(row[:9]); lvl.append(int(row[9]))
+            tc.append([rng.uniform(-0.5, 0.5 - w), rng.uniform(-0.5, 0.5 - w), rng.uniform(-0.5, 0.5 - w), w])
+    R = np.array(R, np.float32); lvl = np.array(lvl, np.int32); tc = np.array(tc, np.float32)
+    ub, lb = eng_small.EvalBounds(R, lvl, tc)
+    gam = small["inner_gamma"]
+    for k in range(len(R)):
+        Rk = R[k].reshape(3, 3)
+        p = data
+        # float32 op order of jly_goicp.cpp:470-476
+        rot = np.stack([(Rk[i, 0] * p[:, 0] + Rk[i, 1] * p[:, 1]) + Rk[i, 2] * p[:, 2] for i in range(3)], 1).astype(np.float32)
+        t = (tc[k, :3] + tc[k, 3] / np.float32(2)).astype(np.float32)
+        d = restated.dt_distance(dt, (rot + t).astype(np.float32))
+        if lvl[k] >= 0:
+            d = d - gam[lvl[k]]
+        d = np.maximum(d, 0).astype(np.float32)
+        gt = np.float32(1.732050808 / 2.0 * float(tc[k, 3]))
+        e = np.maximum(d - gt, 0).astype(np.float32)
+        assert ub[k] == pytest.approx(float((d.astype(np.float64) ** 2).sum()), rel=SUM_RTOL, abs=1e-7)
+        assert lb[k] == pytest.approx(float((e.astype(np.float64) ** 2).sum()), rel=SUM_RTOL, abs=1e-7)
+
+
+def test_inner_bnb_matches_reference_known_answers(eng_small, small):
+    cases = small["inner_cases"]
+    out = eng_small.InnerBnB(cases[:, :9], cases[:, 9].astype(np.int32), cases[:, 10].astype(np.float32))
+    for row, o in zip(cases, out):
+        assert o["value"] == pytest.approx(row[11], rel=1e-5, abs=1e-6)
+        assert (o["pops"], o["evals"]) == (int(row[16]), int(row[17]))
+        if int(row[9]) < 0 and row[11] < row[10]:      # ub pass that improved: arg-min translation cube
+            assert np.array_equal(o["node"], row[12:16].astype(np.float32))
+
+
+def test_nn_indices_bit_exact(pkg, small, bunny):
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    idx, d2 = g.NN(bunny["data"])
+    assert np.array_equal(idx, small["nn_idx"])
+    assert np.array_equal(d2.view(np.uint32), small["nn_d2"].view(np.uint32))
+    g.close()
+    # exact ties: lattice with duplicated points, half-integer queries
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = small["lat_model"], small["lat_query"]
+    idx, d2 = g.NN(small["lat_query"])
+    assert np.array_equal(idx, small["lat_idx"])
+    assert np.array_equal(d2, small["lat_d2"])
+    g.close()
+
+
+def test_icp_matches_reference(pkg, small, bunny):
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    err, R, t, iters = g.ICP(np.eye(3), np.zeros(3), 10000, 1e-7)
+    assert err == pytest.approx(float(small["icp_trim0.0_err"]), rel=1e-4)
+    assert rot_angle(R, small["icp_trim0.0_R"]) < 1e-4
+    assert np.abs(t - small["icp_trim0.0_t"]).max() < 1e-4
+    g.close()
+
+
+@pytest.mark.parametrize("S", [48])
+def test_dt_build_reference_mode_bit_exact_small(pkg, small, bunny, S):
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.dt.SIZE = S
+    g.BuildDT()
+    grid, meta = g.GetDT()
+    assert np.array_equal(meta, small["dt48_meta"])
+    assert np.array_equal(grid.view(np.uint32), small["dt48_grid"].view(np.uint32))
+    g.close()
+
+
+def test_dt_build_exact_edt_mode(pkg, small, bunny):
+    from scipy import ndimage
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.dt.SIZE = 48
+    g.dt_mode = 1
+    g.BuildDT()
+    grid, meta = g.GetDT()
+    idx = np.floor((bunny["model"].astype(np.float64) - meta[:3]) * meta[3] + 0.5).astype(int)
+    occ = np.ones((48, 48, 48), bool)
+    occ[idx[:, 2], idx[:, 1], idx[:, 0]] = False
+    exact = ndimage.distance_transform_edt(occ)
+    want = (np.sqrt((exact ** 2).round()).astype(np.float32).astype(np.float64) / meta[3]).astype(np.float32)
+    assert np.array_equal(grid, want)
+    g.close()
+
+
+def _check_run(res, gold):
+    assert res["exit_path"] == gold["exit_path"]
+    assert res["sse"] == pytest.approx(gold["sse"], rel=1e-5)
+    assert rot_angle(res["R"], np.array(gold["R"]).reshape(3, 3)) < 1e-4
+    assert np.abs(res["t"] - np.array(gold["t"])).max() < 1e-4
+    if gold["exit_path"] == "certified":
+        assert res["best_lb"] == pytest.approx(gold["exit_lb"], rel=1e-4, abs=1e-5)
+
+
+def test_register_bunny_full_size_reference_dt_on_gpu(pkg, runs, bunny, restated):
+    """BASELINE config 1 end to end on the GPU: build the S=300 DT (reference mode), check its
+    checksum against the reference's, run Go-ICP, compare with the reference's own run."""
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.BuildDT()
+    grid, meta = g.GetDT()
+    assert np.array_equal(meta, [-1.7215785086154938, -1.735278993844986, -1.7175954878330231, 87.099870706007081])
+    assert "%016x" % restated.fnv(grid) == "2da64ee1865a968e"
+    gold = runs["bunny_s0.1_mse1e-3"]
+    g.Register()
+    _check_run(g.result, gold)
+    assert (g.result["rot_pops"], g.result["trans_pops"]) == (gold["rot_pops"], gold["trans_pops"])
+    # certificate paths reuse the same DT
+    for name in ("bunny_s0.1_mse7e-4", "bunny_s0.1_mse5e-4"):
+        gold = runs[name]
+        g2 = pkg.GoICP(gold["mse"])
+        g2.pModel, g2.pData = bunny["model"], bunny["data"]
+        g2.SetDT(grid, meta)
+        g2.Register()
+        _check_run(g2.result, gold)
+        assert (g2.result["rot_pops"], g2.result["trans_pops"]) == (gold["rot_pops"], gold["trans_pops"])
+        g2.close()
+    g.close()
