@@ -42,7 +42,7 @@ class Result(C.Structure):
     _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("sse", C.c_float), ("sse_thresh", C.c_float),
                 ("best_lb", C.c_float), ("exit_path", C.c_int),
                 ("rot_pops", C.c_int64), ("trans_pops", C.c_int64), ("bound_evals", C.c_int64),
-                ("bound_evals_executed", C.c_int64), ("icp_calls", C.c_int64), ("rounds", C.c_int64),
+                ("bound_evals_executed", C.c_int64), ("icp_calls", C.c_int64), ("rounds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("seconds_total", C.c_double), ("seconds_bnb_kernels", C.c_double), ("seconds_icp", C.c_double)]
 
     def as_dict(self):
@@ -50,7 +50,7 @@ class Result(C.Structure):
                 "sse": float(self.sse), "sse_thresh": float(self.sse_thresh), "best_lb": float(self.best_lb),
                 "exit_path": EXIT_PATHS[self.exit_path], "rot_pops": self.rot_pops, "trans_pops": self.trans_pops,
                 "bound_evals": self.bound_evals, "bound_evals_executed": self.bound_evals_executed,
-                "icp_calls": self.icp_calls, "rounds": self.rounds, "seconds_total": self.seconds_total,
+                "icp_calls": self.icp_calls, "rounds": self.rounds, "kernel_launches": self.kernel_launches, "seconds_total": self.seconds_total,
                 "seconds_bnb_kernels": self.seconds_bnb_kernels, "seconds_icp": self.seconds_icp}
 
 
@@ -72,8 +72,8 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
-               "goicp_eval_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
-               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_set_exchange", "goicp_run_toml"]
+               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_set_exchange", "goicp_selftest_shard", "goicp_run_toml"]
 
 
 def build(verbose: bool = False) -> str:
@@ -110,6 +110,7 @@ def lib():
         L.goicp_dt_size.argtypes = [C.c_void_p]
         L.goicp_dt_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_eval_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.goicp_expand_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.goicp_inner_bnb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.goicp_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.POINTER(IcpResult)]
@@ -119,6 +120,7 @@ def lib():
         L.goicp_poll.argtypes = [C.c_void_p, C.POINTER(Snapshot)]
         L.goicp_cancel.argtypes = [C.c_void_p]
         L.goicp_set_exchange.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p, C.c_int]
+        L.goicp_selftest_shard.argtypes = [C.c_int, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, C.POINTER(C.c_int)]
         L.goicp_run_toml.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.POINTER(Result)]
         _lib = L
     return _lib
@@ -288,6 +290,18 @@ class GoICP:
         self._check(self.L.goicp_eval_bounds(self._handle(), n, R.ctypes.data, level.ctypes.data, tcube.ctypes.data,
                                              ub.ctypes.data, lb.ctypes.data))
         return ub, lb
+
+    def ExpandBounds(self, R, level, tcube, repeats=0):
+        """8 children of each parent translation cube: returns (ub[n,8], lb[n,8][, ms per launch])."""
+        R = _f32(R).reshape(-1, 9)
+        level = np.ascontiguousarray(level, np.int32)
+        tcube = _f32(tcube, 4)
+        n = len(R)
+        out = np.zeros((n, 16), np.float32)
+        ms = C.c_float(0)
+        self._check(self.L.goicp_expand_bounds(self._handle(), n, R.ctypes.data, level.ctypes.data, tcube.ctypes.data,
+                                               out.ctypes.data, repeats, C.byref(ms) if repeats > 0 else None))
+        return (out[:, :8], out[:, 8:], ms.value) if repeats > 0 else (out[:, :8], out[:, 8:])
 
     def InnerBnB(self, R, level, opt_error):
         """Batch of GoICP::InnerBnB calls (jly_goicp.cpp:227-340)."""

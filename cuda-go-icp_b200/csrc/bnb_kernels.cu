@@ -7,6 +7,7 @@
 // contraction anywhere, so no tensor cores (DESIGN.md "Kernels").
 #include "goicp_types.h"
 #include "goicp_kernels.h"
+#include "strict_sum.cuh"
 
 namespace goicp {
 
@@ -178,7 +179,10 @@ struct InnerCtrl {
     float tx[2], ty[2], tz[2];
     float gt;
     int done;
+    int n_cand;          // upper-bound pass: contenders for the arg-min (see strict_sum.cuh)
+    float final_fast;
 };
+constexpr int kMaxCand = 128;
 
 template <bool PTS_SMEM>
 __global__ void __launch_bounds__(kBnbThreads, 2)
@@ -189,6 +193,8 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
     __shared__ float red[kBnbWarps][16];
     __shared__ float tot[16];
     __shared__ InnerCtrl ctrl;
+    __shared__ float4 cand_node[kMaxCand];
+    __shared__ float cand_ub[kMaxCand];
 
     HeapEntry* hsm = reinterpret_cast<HeapEntry*>(smem_raw);
     float4* pts = reinterpret_cast<float4*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry));
@@ -216,6 +222,10 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
     float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     uint32_t pops = 0, evals = 0, max_heap = 0;
     int status = 0;
+    const bool ub_pass = task.level < 0;
+    // |sequential float sum - tree float sum| <= ~Nd*2^-24 relative; contenders within twice that
+    const float cand_eps = fminf(1e-2f, 2.0f * (float)c.nd * 5.9604645e-8f) + 1e-6f;
+    int n_cand = 0; uint32_t flags = 0;
     // parent being expanded
     float px = 0, py = 0, pz = 0, cw = 0;
     uint32_t plevel = 0, ppath_lo = 0, ppath_hi = 0;
@@ -298,6 +308,19 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
                     best[2] = __fadd_rn(pz, (j & 4) ? cw : 0.0f);
                     best[3] = cw;
                 }
+                if (ub_pass && ub <= opt_t * (1.0f + cand_eps)) {
+                    if (n_cand == kMaxCand) {           // drop contenders the running minimum has left behind
+                        int k = 0;
+                        for (int q = 0; q < n_cand; q++)
+                            if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; k++; }
+                        n_cand = k;
+                    }
+                    if (n_cand < kMaxCand) {
+                        cand_node[n_cand] = make_float4(__fadd_rn(px, (j & 1) ? cw : 0.0f), __fadd_rn(py, (j & 2) ? cw : 0.0f),
+                                                        __fadd_rn(pz, (j & 4) ? cw : 0.0f), cw);
+                        cand_ub[n_cand] = ub; n_cand++;
+                    } else flags |= 1u;                 // could not keep every contender: result is the tree-sum one
+                }
                 if (lb >= opt_t) continue;
                 HeapEntry e; e.lb = lb; e.level = plevel + 1;
                 unsigned long long path = (((unsigned long long)ppath_hi << 32) | ppath_lo) | ((unsigned long long)j << (3 * plevel));
@@ -309,30 +332,85 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
         // a failed push (status != 0) ends the task at the top of the next iteration
     }
 
+    // ---- strict resolution of the arg-min (upper-bound pass only) ---------------------------
+    // The search above used fixed-order tree sums.  The reference's optErrorT is the first strict
+    // minimum of its own sequential sums over the same evaluated cubes; re-evaluate the contenders
+    // in reference order (strict_sum.cuh) and replay that rule.
+    float strict_value = opt_t;
+    if (ub_pass) {
+        if (tid == 0) {
+            int k = 0;
+            for (int q = 0; q < n_cand; q++)
+                if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; k++; }
+            ctrl.n_cand = (flags & 1u) ? 0 : k;
+        }
+        __syncthreads();
+        const int nc = ctrl.n_cand;
+        float* scratch = reinterpret_cast<float*>(spill + (size_t)blockIdx.x * spill_cap);
+        const size_t scratch_floats = (size_t)spill_cap * (sizeof(HeapEntry) / sizeof(float));
+        int per_chunk = (int)min((size_t)kBnbWarps, scratch_floats / (size_t)max(c.nd, 1));
+        if (nc > 0 && per_chunk == 0) { if (tid == 0) flags |= 2u; }
+        else if (nc > 0) {
+            float so = task.opt_error;                       // thread 0: the reference's running optErrorT
+            bool have = false;
+            for (int base = 0; base < nc; base += per_chunk) {
+                const int cnt = min(per_chunk, nc - base);
+                for (int q = 0; q < cnt; q++) {
+                    const float4 nd4 = cand_node[base + q];
+                    const float half = nd4.w / 2;
+                    const float tx = __fadd_rn(nd4.x, half), ty = __fadd_rn(nd4.y, half), tz = __fadd_rn(nd4.z, half);
+                    float* m = scratch + (size_t)q * c.nd;
+                    for (int i = tid; i < c.nd; i += kBnbThreads) {
+                        float rx, ry, rz;
+                        if (PTS_SMEM) { const float4 p = pts[i]; rx = p.x; ry = p.y; rz = p.z; }
+                        else {
+                            const float4 p = __ldg(c.data + i);
+                            rx = dot3_ref(R0, R1, R2, p.x, p.y, p.z); ry = dot3_ref(R3, R4, R5, p.x, p.y, p.z); rz = dot3_ref(R6, R7, R8, p.x, p.y, p.z);
+                        }
+                        float d = dt_distance(c.dt, __fadd_rn(rx, tx), __fadd_rn(ry, ty), __fadd_rn(rz, tz));
+                        m[i] = d < 0.0f ? 0.0f : d;
+                    }
+                }
+                __syncthreads();
+                if (lane == 0 && warp < cnt) {
+                    float ub, lb;
+                    ss_select_and_sum(scratch + (size_t)warp * c.nd, c.nd, c.inlier_num, c.do_trim != 0, 0.0f, false, ub, lb);
+                    cand_ub[base + warp] = ub;                   // now the reference-order sum
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    for (int q = 0; q < cnt; q++)
+                        if (cand_ub[base + q] < so) {            // `if(ub < optErrorT)` in evaluation order (:319-324)
+                            so = cand_ub[base + q]; have = true;
+                            best[0] = cand_node[base + q].x; best[1] = cand_node[base + q].y; best[2] = cand_node[base + q].z; best[3] = cand_node[base + q].w;
+                        }
+                }
+            }
+            if (tid == 0) { strict_value = so; if (!have) { best[0] = best[1] = best[2] = best[3] = 0.0f; } }
+        }
+    }
+
     if (tid == 0) {
         InnerResult r;
-        r.value = opt_t; r.node[0] = best[0]; r.node[1] = best[1]; r.node[2] = best[2]; r.node[3] = best[3];
-        r.pops = pops; r.evals = evals; r.status = status; r.max_heap = max_heap; r.pad[0] = r.pad[1] = 0;
+        r.value = strict_value; r.node[0] = best[0]; r.node[1] = best[1]; r.node[2] = best[2]; r.node[3] = best[3];
+        r.pops = pops; r.evals = evals; r.status = status; r.max_heap = max_heap; r.pad[0] = flags; r.pad[1] = __float_as_uint(opt_t);
         results[blockIdx.x] = r;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// (Trim-free) sum of squared DT distances of the data under a pose: the initial error
-// (jly_goicp.cpp:357-371) and the DT re-scoring of GoICP::ICP (:100-131).  Single CTA per
-// pose; poses batched over blockIdx.x.  use_pose[k]==0 scores the raw data.
+// (Trimmed) sum of squared DT distances of the data under a pose: the initial error
+// (jly_goicp.cpp:357-371) and the DT re-scoring of GoICP::ICP (:100-131).  These few values
+// become optError itself, so they are formed in the reference's order: gathers in parallel, then
+// intro_select + sequential float sum by one thread (strict_sum.cuh).  One CTA per pose;
+// use_pose[k]==0 scores the raw data.  scratch: nposes * nd floats.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBnbThreads)
-dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ out)
+dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ scratch, float* __restrict__ out)
 {
-    __shared__ float red[kBnbWarps][16];
-    __shared__ float tot[16];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* Rt = Rt12 + 12 * blockIdx.x;
     const bool pose = use_pose[blockIdx.x] != 0;
-    float acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+    float* m = scratch + (size_t)blockIdx.x * c.nd;
     for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
         float4 p = __ldg(c.data + i);
         float x = p.x, y = p.y, z = p.z;
@@ -341,11 +419,14 @@ dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restric
             y = __fadd_rn(dot3_ref(Rt[3], Rt[4], Rt[5], p.x, p.y, p.z), Rt[10]);
             z = __fadd_rn(dot3_ref(Rt[6], Rt[7], Rt[8], p.x, p.y, p.z), Rt[11]);
         }
-        float d = dt_distance(c.dt, x, y, z);
-        acc[0] = __fadd_rn(acc[0], __fmul_rn(d, d));
+        m[i] = dt_distance(c.dt, x, y, z);
     }
-    block_reduce16(acc, red, tot, warp, lane);
-    if (threadIdx.x == 0) out[blockIdx.x] = tot[0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ub, lb;
+        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb);
+        out[blockIdx.x] = ub;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -369,11 +450,21 @@ cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int
     expand_bounds_kernel<<<n, kBnbThreads, 0, s>>>(c, d_tasks, d_out16);
     return cudaGetLastError();
 }
-cudaError_t inner_bnb_configure(int max_dyn_smem)
+// Opts the kernels into the full shared-memory carve-out; returns the dynamic bytes one CTA may use.
+cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
 {
-    cudaError_t e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+    cudaFuncAttributes a0, a1;
+    cudaError_t e = cudaFuncGetAttributes(&a0, inner_bnb_kernel<true>);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+    e = cudaFuncGetAttributes(&a1, inner_bnb_kernel<false>);
+    if (e != cudaSuccess) return e;
+    const int stat = (int)(a0.sharedSizeBytes > a1.sharedSizeBytes ? a0.sharedSizeBytes : a1.sharedSizeBytes);
+    const int dyn = smem_optin - stat;
+    e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    *max_dyn_out = dyn;
+    return e;
 }
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n,
                              bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, cudaStream_t s)
@@ -384,10 +475,10 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     else             inner_bnb_kernel<false><<<n, kBnbThreads, smem, s>>>(c, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_out, cudaStream_t s)
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, cudaStream_t s)
 {
     if (nposes <= 0) return cudaSuccess;
-    dt_score_kernel<<<nposes, kBnbThreads, 0, s>>>(c, d_Rt12, d_use_pose, d_out);
+    dt_score_kernel<<<nposes, kBnbThreads, 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out);
     return cudaGetLastError();
 }
 

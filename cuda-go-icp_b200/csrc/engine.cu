@@ -111,7 +111,7 @@ struct goicp_handle {
     goicp_params p;
     std::string err;
     bool cuda_ready = false;
-    int sm_count = 0, max_smem_optin = 0;
+    int sm_count = 0, max_smem_optin = 0, inner_dyn_smem = 0;
     cudaStream_t stream = nullptr;
 
     std::vector<float> model, data;     // xyz triples
@@ -126,8 +126,8 @@ struct goicp_handle {
     bool kd_ready = false;
     // scratch
     DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
-    DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
-    DevBuf<IcpState> d_icp_state; DevBuf<double> d_icp_partials; int icp_blocks = 0;
+    DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
+    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn; DevBuf<unsigned long long> d_icp_keys; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
     InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
 
@@ -142,6 +142,7 @@ struct goicp_handle {
 
     // timing
     double t_kernels = 0, t_icp = 0;
+    int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -168,7 +169,7 @@ int ensure_cuda(goicp_handle* h)
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(h, cudaEventCreate(&h->ev0));
     CUDA_TRY(h, cudaEventCreate(&h->ev1));
-    CUDA_TRY(h, inner_bnb_configure(h->max_smem_optin - 2048));   // minus the kernel's static shared memory
+    CUDA_TRY(h, inner_bnb_configure(h->max_smem_optin, &h->inner_dyn_smem));
     h->cuda_ready = true;
     return GOICP_OK;
 }
@@ -212,7 +213,6 @@ int ensure_kdtree(goicp_handle* h)
     h->icp_blocks = icp_max_grid_blocks(h->p.device);
     if (h->icp_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     CUDA_TRY(h, h->d_icp_state.reserve(1));
-    CUDA_TRY(h, h->d_icp_partials.reserve((size_t)h->icp_blocks * 16));
     h->kd_ready = true;
     return GOICP_OK;
 }
@@ -249,7 +249,7 @@ int make_const(goicp_handle* h, BnbConst& c)
     if (h->inlier_num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the bound kernels yet");
     c.dt.grid = h->d_dt.p; c.dt.S = h->dt_size; c.dt.S2 = h->dt_size * h->dt_size;
     c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3];
-    c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.sse_thresh = h->sse_thresh;
+    c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
     c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
     for (int i = 0; i < kMaxRotLevel; i++) c.cgamma[i] = h->cgamma[i];
     return GOICP_OK;
@@ -260,7 +260,8 @@ int make_const(goicp_handle* h, BnbConst& c)
 struct InnerPlan { bool pts_smem; int heap_cap_sm; };
 InnerPlan plan_inner(const goicp_handle* h)
 {
-    const size_t per_cta = ((size_t)h->max_smem_optin + 1024) / 2 - 4096;      // two CTAs per SM, minus static smem + slack
+    // two CTAs per SM: each may take half of the SM's 228 KB minus its static part and the 1 KB the driver reserves per CTA
+    const size_t per_cta = (size_t)(h->inner_dyn_smem + (h->max_smem_optin - h->inner_dyn_smem)) / 2 - (size_t)(h->max_smem_optin - h->inner_dyn_smem) - 2048;
     const size_t pts = (size_t)h->nd * sizeof(float4);
     InnerPlan p;
     p.pts_smem = pts + 16 * 1024 <= per_cta;
@@ -292,6 +293,20 @@ int ensure_task_buffers(goicp_handle* h, size_t n)
     return GOICP_OK;
 }
 
+// Round-robin sharding of a round's tasks: rank r owns tasks r, r+W, r+2W, ...  Every rank sends
+// its results (padded to ceil(n/W) records); after the all-gather task t is found at
+// recv[(t % W) * per_rank + t / W].
+int shard_exchange(goicp_allgather_fn fn, void* user, int W, int n, const InnerResult* mine, int n_mine, InnerResult* all)
+{
+    const int per_rank = (n + W - 1) / W;
+    std::vector<InnerResult> send(per_rank), recv((size_t)per_rank * W);
+    std::memset(send.data(), 0, sizeof(InnerResult) * per_rank);
+    if (n_mine > 0) std::memcpy(send.data(), mine, sizeof(InnerResult) * n_mine);
+    if (fn(user, send.data(), recv.data(), sizeof(InnerResult) * per_rank, 0) != 0) return 1;
+    for (int t = 0; t < n; t++) all[t] = recv[(size_t)(t % W) * per_rank + t / W];
+    return 0;
+}
+
 // Runs `n` inner BnBs (tasks in h->h_tasks) and leaves the results in h->h_results.
 // With an exchange hook installed, rank r runs tasks r, r+W, r+2W, ... and the per-rank result
 // blocks are all-gathered, so every rank ends up with all n results.
@@ -316,20 +331,19 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     if (mine > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, launch_inner_bnb(c, h->d_tasks.p, h->d_results.p, mine, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->stream));
+        h->launches++;
     }
     if (W == 1) {
         CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results.p, sizeof(InnerResult) * n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     } else {
-        std::vector<InnerResult> send(per_rank), recv((size_t)per_rank * W);
-        std::memset(send.data(), 0, sizeof(InnerResult) * per_rank);
-        if (mine > 0) CUDA_TRY(h, cudaMemcpyAsync(send.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
+        std::vector<InnerResult> mine_res(std::max(mine, 1));
+        if (mine > 0) CUDA_TRY(h, cudaMemcpyAsync(mine_res.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        if (h->xchg(h->xchg_user, send.data(), recv.data(), sizeof(InnerResult) * per_rank, 0) != 0)
+        if (shard_exchange(h->xchg, h->xchg_user, W, n, mine_res.data(), mine, h->h_results) != 0)
             return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
-        for (int t = 0; t < n; t++) h->h_results[t] = recv[(size_t)(t % W) * per_rank + t / W];
     }
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->t_kernels += ms * 1e-3;
     for (int t = 0; t < n; t++) {
@@ -349,7 +363,9 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     CUDA_TRY(h, h->d_i32.reserve(16));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_f32a.p + 16, h->stream));
+    CUDA_TRY(h, h->d_score_scratch.reserve((size_t)h->nd));
+    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->stream));
+    h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
@@ -360,16 +376,20 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     int rc = ensure_cuda(h); if (rc) return rc;
     rc = upload_data(h); if (rc) return rc;
     rc = ensure_kdtree(h); if (rc) return rc;
-    const int num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;
-    if (num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the ICP kernel yet");
+    const int num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;     // jly_icp3d.hpp:189-196
+    size_t npad = 1; while (npad < (size_t)h->nd) npad <<= 1;
+    CUDA_TRY(h, h->d_icp_q.reserve((size_t)3 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd));
+    CUDA_TRY(h, h->d_icp_keys.reserve(npad)); CUDA_TRY(h, h->d_icp_stage.reserve((size_t)8 * h->nd));
+    IcpWork wk; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p;
     IcpState st; std::memset(&st, 0, sizeof st);
     for (int i = 0; i < 9; i++) st.R[i] = R0[i];
     for (int i = 0; i < 3; i++) st.t[i] = t0[i];
     st.err = -1.0f;
     const double t_begin = now_s();
     CUDA_TRY(h, cudaMemcpyAsync(h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
-    const int blocks = std::max(1, std::min(h->icp_blocks, (h->nd + 127) / 128));
-    CUDA_TRY(h, launch_icp(kd_view(h), h->d_data.p, h->nd, h->d_icp_state.p, h->d_icp_partials.p, max_iter, err_diff, num, blocks, h->stream));
+    const int blocks = std::max(1, std::min(h->icp_blocks, (h->nd + icp_threads() - 1) / icp_threads()));
+    CUDA_TRY(h, launch_icp(kd_view(h), h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->stream));
+    h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->t_icp += now_s() - t_begin;
@@ -434,7 +454,7 @@ int goicp_destroy(goicp_handle* h)
         cudaSetDevice(h->p.device);
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
-        h->d_i32.release(); h->d_q.release(); h->d_icp_state.release(); h->d_icp_partials.release();
+        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release();
         if (h->h_results) cudaFreeHost(h->h_results);
         if (h->h_tasks) cudaFreeHost(h->h_tasks);
         if (h->ev0) cudaEventDestroy(h->ev0);
@@ -540,6 +560,38 @@ int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_
     return GOICP_OK;
 }
 
+int goicp_expand_bounds(goicp_handle* h, int n, const float* R9, const int32_t* level, const float* tcube, float* out16, int repeats, float* device_ms)
+{
+    if (!h || n < 0 || !R9 || !level || !tcube || !out16) return fail(h, GOICP_ERR_INVALID, "expand_bounds: bad arguments");
+    if (n == 0) return GOICP_OK;
+    BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    std::vector<PairTask> tasks(n);
+    for (int k = 0; k < n; k++) {
+        if (level[k] >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "expand_bounds: rotation level >= 20");
+        std::memcpy(tasks[k].R, R9 + 9 * (size_t)k, 9 * sizeof(float));
+        tasks[k].level = level[k];
+        std::memcpy(tasks[k].tc, tcube + 4 * (size_t)k, 4 * sizeof(float));
+        tasks[k].pad[0] = tasks[k].pad[1] = 0;
+    }
+    CUDA_TRY(h, h->d_pairs.reserve(n));
+    CUDA_TRY(h, h->d_f32b.reserve((size_t)16 * n));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pairs.p, tasks.data(), sizeof(PairTask) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_expand_bounds(c, h->d_pairs.p, n, h->d_f32b.p, h->stream));
+    if (device_ms) {
+        if (repeats < 1) repeats = 1;
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        for (int r = 0; r < repeats; r++) CUDA_TRY(h, launch_expand_bounds(c, h->d_pairs.p, n, h->d_f32b.p, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0; CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        *device_ms = ms / repeats;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(out16, h->d_f32b.p, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
 int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* level, const float* opt_error, goicp_inner_result* out)
 {
     if (!h || n < 0 || !R9 || !level || !opt_error || !out) return fail(h, GOICP_ERR_INVALID, "inner_bnb: bad arguments");
@@ -608,6 +660,21 @@ int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int u
     return GOICP_OK;
 }
 
+// Host-only self test of the multi-rank result exchange (no GPU): fabricates the results of `n`
+// tasks, runs the same shard_exchange() as a real round and counts wrong records.
+int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void* user, int* mismatches)
+{
+    if (!fn || !mismatches || world < 1 || rank < 0 || rank >= world) return GOICP_ERR_INVALID;
+    auto fake = [](int t) { InnerResult r; std::memset(&r, 0, sizeof r); r.value = (float)t * 0.5f; r.pops = 7u * t + 1; r.evals = 8u * t; r.node[3] = (float)t; return r; };
+    std::vector<InnerResult> mine, all(std::max(n, 1));
+    for (int t = rank; t < n; t += world) mine.push_back(fake(t));
+    if (shard_exchange(fn, user, world, n, mine.data(), (int)mine.size(), all.data()) != 0) return GOICP_ERR_INVALID;
+    int bad = 0;
+    for (int t = 0; t < n; t++) { InnerResult e = fake(t); if (std::memcmp(&e, &all[t], sizeof e) != 0) bad++; }
+    *mismatches = bad;
+    return GOICP_OK;
+}
+
 int goicp_cancel(goicp_handle* h) { if (!h) return GOICP_ERR_INVALID; h->cancel_flag.store(1); return GOICP_OK; }
 int goicp_poll(goicp_handle* h, goicp_snapshot* out)
 {
@@ -623,7 +690,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
-    h->t_kernels = 0; h->t_icp = 0;
+    h->t_kernels = 0; h->t_icp = 0; h->launches = 0;
     const double t_begin = now_s();
     h->initialized = false;
     int rc = initialize(h); if (rc) return rc;
@@ -783,6 +850,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
 
     sync_res();
     res.exit_path = exit_path; res.best_lb = exit_lb;
+    res.kernel_launches = h->launches;
     res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp;
     publish(h, res, 1);
     *out = res;

@@ -8,10 +8,10 @@ namespace goicp {
 cudaError_t launch_dt_lookup(const DtView& dt, const float* d_q, int n, float* d_out, int32_t* d_idx, cudaStream_t s);
 cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float2* d_out, cudaStream_t s);
 cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
-cudaError_t inner_bnb_configure(int max_dyn_smem);
+cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n,
                              bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, cudaStream_t s);
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_out, cudaStream_t s);
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, cudaStream_t s);
 
 // ---- icp_kernels.cu ---------------------------------------------------------------------
 // Flattened copy of the reference-ordered kd-tree (built on the host by kdtree_host.cpp).
@@ -35,12 +35,19 @@ struct IcpState {           // lives in device memory; written by block 0 of the
     float mu_m[3], mu_d[3];
     float err, err_new;
     int iter, converged;
-    double sums[16];
+};
+struct IcpWork {            // per-iteration device scratch of the ICP kernel
+    float* q;               // 3*nd transformed data points
+    int32_t* nn;            // nd nearest model indices
+    float* d2;              // nd squared distances
+    unsigned long long* keys;   // next_pow2(nd) sort keys (d2 bits << 32 | point index)
+    float* stage;           // 8*nd: correspondences in sorted order
 };
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
-cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, double* d_partials,
+cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s);
+int icp_threads();
 int icp_max_grid_blocks(int device);
 
 } // namespace goicp

@@ -17,6 +17,7 @@ struct BnbConst {
     const float4* __restrict__ data;    // data cloud: x, y, z, ||p|| (normData, jly_goicp.cpp:143-147)
     int nd;
     int inlier_num;                     // == nd unless trimming
+    int do_trim;                        // GoICP::doTrim: the reference runs intro_select iff set (even when nothing is trimmed)
     float sse_thresh;                   // SSEThresh (jly_goicp.cpp:208)
     float tx, ty, tz, tw;               // initNodeTrans (jly_goicp.cpp:50-53)
     float cgamma[kMaxRotLevel];         // 2*sinf(maxAngle_l/2): maxRotDis[l][i] = cgamma[l]*||p_i|| (jly_goicp.cpp:150-160)

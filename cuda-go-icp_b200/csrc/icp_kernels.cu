@@ -11,7 +11,7 @@ namespace cg = cooperative_groups;
 
 namespace goicp {
 
-constexpr int kIcpThreads = 128;
+constexpr int kIcpThreads = 512;
 constexpr int kKdStack = 64;
 
 // ------------------------------------------------------------------------------------------
@@ -299,41 +299,28 @@ __device__ void mat3_mul(const float* A, const float* B, float* C)   // accumula
     }
 }
 
-// Procrustes step + SE(3) composition (jly_icp3d.hpp:259-291) from the 16 reduced moments:
-// sums[0..2]=sum m, [3..5]=sum q, [6..14]=sum q_a m_b, [15]=sum d^2 ; q = transformed data point.
-__device__ void icp_update(IcpState* st, const double* sums, int n, int num)
+// Procrustes step + SE(3) composition (jly_icp3d.hpp:268-291) from H = q_d^T q_m and the means.
+__device__ void icp_update(IcpState* st, const float* H)
 {
-    for (int c = 0; c < 3; c++) {
-        // mu accumulates on top of the PREVIOUS mean (never reset, :205-206) and is divided by n (:262-263)
-        float sm = (float)((double)st->mu_m[c] + sums[c]);
-        float sd = (float)((double)st->mu_d[c] + sums[3 + c]);
-        st->mu_m[c] = sm / (float)n;
-        st->mu_d[c] = sd / (float)n;
-    }
-    float H[9];
-    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-        double md = st->mu_d[a], mm = st->mu_m[b];
-        H[3 * a + b] = (float)(sums[6 + 3 * a + b] - md * sums[b] - sums[3 + a] * mm + (double)num * md * mm);
-    }
     float U[9], W[3], V[9], Ut[9], Rn[9], VT[9], tmp[9];
     svd3_ref(H, U, W, V);
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ut[3 * j + i] = U[3 * i + j];
-    mat3_mul(V, Ut, Rn);
+    mat3_mul(V, Ut, Rn);                                                     // R_ = V * ~U
     float da = Rn[0] * (Rn[4] * Rn[8] - Rn[5] * Rn[7]);
     float db = -Rn[1] * (Rn[3] * Rn[8] - Rn[5] * Rn[6]);
     float dc = Rn[2] * (Rn[3] * Rn[7] - Rn[4] * Rn[6]);
     float det = da + db + dc;
     float D[9] = {1, 0, 0, 0, 1, 0, 0, 0, det};
     mat3_mul(V, D, VT);
-    mat3_mul(VT, Ut, Rn);
+    mat3_mul(VT, Ut, Rn);                                                    // R_ = V * diag(1,1,det) * ~U
     float tn[3], tt[3];
-    for (int a = 0; a < 3; a++) {
+    for (int a = 0; a < 3; a++) {                                            // t_ = ~mu_m - R_ * ~mu_d
         float acc = 0.0f;
         for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->mu_d[k];
         tn[a] = st->mu_m[a] - acc;
     }
-    mat3_mul(Rn, st->R, tmp);
-    for (int a = 0; a < 3; a++) {
+    mat3_mul(Rn, st->R, tmp);                                                // R = R_ * R
+    for (int a = 0; a < 3; a++) {                                            // t = R_ * t + t_
         float acc = 0.0f;
         for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->t[k];
         tt[a] = acc + tn[a];
@@ -343,30 +330,61 @@ __device__ void icp_update(IcpState* st, const double* sums, int n, int num)
 }
 
 // ------------------------------------------------------------------------------------------
-// ICP3D::Run as one cooperative kernel.  Per iteration: every thread transforms its data points
-// (float, reference order), finds the nearest model point, and accumulates 16 moments in double;
-// fixed-order block + grid reduction; block 0 thread 0 applies the convergence test (:257), the
-// stale-mean quirk, the SVD and the compose; one grid.sync() publishes the new pose.
+// ICP3D::Run as ONE cooperative kernel.  Per iteration:
+//  (all CTAs)  transform every data point in float (reference order), exact kd-tree NN, store
+//              (query, index, d^2) and a 64-bit sort key (d^2 bits, point index);
+//  grid.sync
+//  (CTA 0)     bitonic sort of the keys == the reference's qsort by distance (stable for ties,
+//              like glibc's merge sort with the reference's never-zero comparator, :156-160,:238);
+//              then the reference's SEQUENTIAL float accumulations in that order -- means on top of
+//              the previous means (never reset, :205-206,:244-252), error (:254), H (:268) -- one
+//              lane per accumulator; convergence test (:257); SVD, det fix, compose (:268-291);
+//  grid.sync   publishes the new pose.
+// The whole refinement therefore follows the reference's trajectory bit for bit, which is what
+// makes the final pose agree to 1e-4: ICP stops on a loose relative criterion far from its fixed
+// point, so its end point depends on the exact path.
 // ------------------------------------------------------------------------------------------
+constexpr int kSortSmem = 4096;
+constexpr int kIcpChunk = 384;
+
+__device__ void bitonic_sort_block(unsigned long long* a, int n_pow2)
+{
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = a[i], y = a[ixj];
+                    const bool up = (i & k) == 0;
+                    if (up ? (x > y) : (x < y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 __global__ void __launch_bounds__(kIcpThreads)
-icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, double* partials,
+icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
            int max_iter, float err_diff, int num)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double wsum[kIcpThreads / 32][16];
+    __shared__ unsigned long long skeys[kSortSmem];
+    __shared__ float sh_H[9];
+    __shared__ float sh_acc[8];
+    __shared__ __align__(16) float chunk[kIcpChunk * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    int npad = 1; while (npad < nd) npad <<= 1;
+    const volatile IcpState* vst = st;
+
+    for (int i = nd + gtid; i < npad; i += gsize) wk.keys[i] = ~0ull;
 
     for (int iter = 0; iter < max_iter; iter++) {
         float R[9], t[3];
-        const volatile IcpState* vst = st;       // re-read the pose published by block 0
 #pragma unroll
         for (int i = 0; i < 9; i++) R[i] = vst->R[i];
 #pragma unroll
         for (int i = 0; i < 3; i++) t[i] = vst->t[i];
-        double acc[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) acc[k] = 0.0;
         for (int i = gtid; i < nd; i += gsize) {
             const float4 p = __ldg(data + i);
             // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
@@ -375,43 +393,90 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, dou
             const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
             float d2;
             const int id = kd_nearest(kd, qx, qy, qz, d2);
-            const float mx = __ldg(kd.model + 3 * id), my = __ldg(kd.model + 3 * id + 1), mz = __ldg(kd.model + 3 * id + 2);
-            acc[0] += mx; acc[1] += my; acc[2] += mz;
-            acc[3] += qx; acc[4] += qy; acc[5] += qz;
-            acc[6] += (double)qx * mx; acc[7] += (double)qx * my; acc[8] += (double)qx * mz;
-            acc[9] += (double)qy * mx; acc[10] += (double)qy * my; acc[11] += (double)qy * mz;
-            acc[12] += (double)qz * mx; acc[13] += (double)qz * my; acc[14] += (double)qz * mz;
-            acc[15] += d2;
-        }
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) wsum[warp][k] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x < 16) {
-            double v = 0.0;
-            for (int w = 0; w < kIcpThreads / 32; w++) v += wsum[w][threadIdx.x];
-            partials[blockIdx.x * 16 + threadIdx.x] = v;
+            wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
+            wk.nn[i] = id; wk.d2[i] = d2;
+            wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
         }
         grid.sync();
         if (blockIdx.x == 0) {
-            if (threadIdx.x < 16) {
-                double v = 0.0;
-                for (unsigned b = 0; b < gridDim.x; b++) v += partials[b * 16 + threadIdx.x];
-                st->sums[threadIdx.x] = v;
+            // ---- sort by (distance, index)
+            unsigned long long* keys = wk.keys;
+            if (npad <= kSortSmem) {
+                for (int i = threadIdx.x; i < npad; i += blockDim.x) skeys[i] = __ldcg(wk.keys + i);
+                __syncthreads();
+                bitonic_sort_block(skeys, npad);
+                keys = skeys;
+            } else {
+                __syncthreads();
+                bitonic_sort_block(wk.keys, npad);
+            }
+            // ---- reference-order accumulations.  Correspondences are gathered in sorted order in
+            // chunks of kIcpChunk rows into shared memory (and kept in wk.stage for the second
+            // pass); one lane per accumulator then adds them up strictly sequentially.
+            float acc = 0.0f;
+            if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
+            for (int base = 0; base < num; base += kIcpChunk) {
+                const int cnt = min(kIcpChunk, num - base);
+                for (int rr = threadIdx.x; rr < cnt; rr += blockDim.x) {
+                    const int i = (int)(keys[base + rr] & 0xffffffffu);
+                    const int id = __ldcg(wk.nn + i);
+                    float4 lo = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), __ldcg(wk.q + 3 * i));
+                    float4 hi = make_float4(__ldcg(wk.q + 3 * i + 1), __ldcg(wk.q + 3 * i + 2), __ldcg(wk.d2 + i), 0.0f);
+                    reinterpret_cast<float4*>(chunk)[2 * rr] = lo; reinterpret_cast<float4*>(chunk)[2 * rr + 1] = hi;
+                    reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi;
+                }
+                __syncthreads();
+                if (warp == 0 && lane < 7) {
+                    const float* sg = chunk + lane;
+                    if (lane < 6) {
+#pragma unroll 8
+                        for (int rr = 0; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
+                    } else {
+#pragma unroll 8
+                        for (int rr = 0; rr < cnt; rr++) acc = (float)((double)acc + (double)sg[8 * rr]);      // float += double (:254)
+                    }
+                }
+                __syncthreads();
+            }
+            if (warp == 0) {
+                if (lane < 7) sh_acc[lane] = acc;
+                __syncwarp();
+                if (lane == 0) {
+                    const float err_new = sh_acc[6];
+                    st->err_new = err_new;
+                    st->iter = iter;
+                    if (st->err > 0.0f && st->err - err_new < err_diff * (float)num) st->converged = 1;          // :257
+                    else {
+                        st->err = err_new;
+                        for (int c = 0; c < 3; c++) { st->mu_m[c] = sh_acc[c] / (float)nd; st->mu_d[c] = sh_acc[3 + c] / (float)nd; }   // :262-263
+                    }
+                    __threadfence_block();
+                }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                const float err_new = (float)st->sums[15];
-                st->err_new = err_new;
-                st->iter = iter;
-                if (st->err > 0.0f && st->err - err_new < err_diff * (float)num) st->converged = 1;   // :257
-                else { st->err = err_new; icp_update(st, st->sums, nd, num); }
-                __threadfence();
+            if (!vst->converged) {
+                float mud = 0.0f, mum = 0.0f; int a = 0, b = 0;
+                if (warp == 0 && lane < 9) { a = lane / 3; b = lane % 3; mud = vst->mu_d[a]; mum = vst->mu_m[b]; }
+                acc = 0.0f;
+                for (int base = 0; base < num; base += kIcpChunk) {
+                    const int cnt = min(kIcpChunk, num - base);
+                    for (int v = threadIdx.x; v < 2 * cnt; v += blockDim.x)
+                        reinterpret_cast<float4*>(chunk)[v] = reinterpret_cast<const float4*>(wk.stage)[2 * (size_t)base + v];
+                    __syncthreads();
+                    if (warp == 0 && lane < 9) {
+#pragma unroll 8
+                        for (int rr = 0; rr < cnt; rr++)
+                            acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(chunk[8 * rr + 3 + a], mud), __fsub_rn(chunk[8 * rr + b], mum)));
+                    }
+                    __syncthreads();
+                }
+                if (warp == 0) {
+                    if (lane < 9) sh_H[lane] = acc;
+                    __syncwarp();
+                    if (lane == 0) icp_update(st, sh_H);
+                }
             }
+            if (threadIdx.x == 0) __threadfence();
         }
         grid.sync();
         if (vst->converged) break;
@@ -432,11 +497,12 @@ int icp_max_grid_blocks(int device)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
-cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, double* d_partials,
+int icp_threads() { return kIcpThreads; }
+cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s)
 {
-    KdView kdv = kd;
-    void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&d_partials,
+    KdView kdv = kd; IcpWork wk = work;
+    void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
                     (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers};
     return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args, 0, s);
 }

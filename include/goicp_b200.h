@@ -85,6 +85,7 @@ typedef struct {
     int64_t bound_evals_executed;   /* incl. speculative work that was later discarded */
     int64_t icp_calls;
     int64_t rounds;          /* device rounds (one batch of rotation cubes each) */
+    int64_t kernel_launches; /* CUDA kernels this call launched */
     double seconds_total, seconds_bnb_kernels, seconds_icp;
 } goicp_result;
 
@@ -140,6 +141,14 @@ int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_ou
 int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_t* level,
                       const float* tcube, float* ub_out, float* lb_out);
 
+/* One expansion step of InnerBnB for n (rotation, PARENT translation cube) pairs: the 8 octant
+ * children of tcube[4k..] are evaluated together (6 voxel-index computations serve 8 gathers per
+ * point).  out16[16k..] = ub[0..7], lb[0..7] in the child order j of jly_goicp.cpp:265-269.
+ * If device_ms != NULL the kernel is launched `repeats` times on resident inputs and the mean
+ * CUDA-event time of one launch is returned (used by bench.py for the DT-gather roofline). */
+int goicp_expand_bounds(goicp_handle* h, int n, const float* R9, const int32_t* level, const float* tcube,
+                        float* out16, int repeats, float* device_ms);
+
 /* n independent inner BnBs (GoICP::InnerBnB): rotation R9[9k..], level[k] (-1 = ub pass),
  * starting optError opt_error[k]. */
 int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* level,
@@ -168,6 +177,9 @@ int goicp_cancel(goicp_handle* h);
  * with torch.distributed (NCCL on device buffers is_device=1, gloo on host buffers). */
 typedef int (*goicp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank, int is_device);
 int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int use_device_buffers);
+
+/* Host-only self test of the sharding + exchange plumbing used by multi-GPU rounds (no GPU needed). */
+int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void* user, int* mismatches);
 
 /* Convenience driver over the reference's TOML keys (src/common.cpp:39-74) and cloud formats
  * (src/common.cpp:79-228): loads [io].target/source (.txt / .ply), applies subsample (seeded)

@@ -59,6 +59,8 @@ def bunny():
 
 
 def rot_angle(Ra, Rb):
-    """geodesic distance between two rotations, radians"""
-    M = np.asarray(Ra, np.float64) @ np.asarray(Rb, np.float64).T
-    return float(np.arccos(np.clip((np.trace(M) - 1) / 2, -1, 1)))
+    """angle between two (nearly orthonormal float32) rotations, radians.  For small angles
+    ||Ra - Rb||_F = 2*sqrt(2)*sin(theta/2); unlike arccos((tr-1)/2) this does not blow the 1e-5
+    non-orthonormality of a float32 matrix up to 1e-3 rad."""
+    d = np.linalg.norm(np.asarray(Ra, np.float64) - np.asarray(Rb, np.float64))
+    return float(2 * np.arcsin(min(1.0, d / (2 * np.sqrt(2)))))
