@@ -17,6 +17,8 @@
 #include "dt_kernels.h"
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 namespace goicp {
@@ -57,130 +59,227 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
 }
 
 // ---- the sequential propagation ------------------------------------------------------------
+// One persistent CTA, thread z owns column z of every row it visits.  Shared memory holds the
+// three relevant rows of the adjacent slice and the previous row of the current slice (padded
+// with "unset" voxels so that the reference's bounds tests need no branches); every global
+// access is a thread's own column, prefetched one row ahead, so HBM/L2 latency stays off the
+// critical path.  A row scan is resolved as
+//   own_z   = first minimum (mask order) of all candidates that do not depend on the scan,
+//   T_z     = the squared norm the running-scan candidate must beat at z (ties by mask order),
+//   chain   = runs: a run starts at s when (own_s + (0,0,1)) beats T_{s+1} and lives while
+//             own_s + (0,0,k) beats T_{s+k}; where it dies the voxel falls back to own.
+// Runs are found in parallel (one thread per possible run head, first wins are exactly the
+// "static" wins against the neighbour's own value), then the few heads are filtered in scan
+// order so that a head inside an earlier run is ignored -- the sequential semantics exactly.
 struct Cand { int n2; Vox vec; };
+__device__ unsigned long long* g_dt_stats = nullptr;   // optional instrumentation (GOICP_DT_STATS=1)
 
-__device__ __forceinline__ void consider(Cand& best, const Vox* G, int S, int x, int y, int z, int iv, int ih, int id)
+__device__ __forceinline__ Vox vox_unset_value() { Vox u; u.v = u.h = u.d = 32767; u.pad = 0; return u; }
+
+__device__ __forceinline__ void consider(Cand& best, Vox s, int iv, int ih, int id)
 {
-    if ((unsigned)x >= (unsigned)S || (unsigned)y >= (unsigned)S || (unsigned)z >= (unsigned)S) return;
-    Vox s = G[((size_t)x * S + y) * S + z];
     if (vox_unset(s)) return;                       // scores ~56755 > 32767 in the reference: never chosen
     s.v = (short)(s.v + iv); s.h = (short)(s.h + ih); s.d = (short)(s.d + id);
-    int n2 = vox_norm2(s);
+    const int n2 = vox_norm2(s);
     if (n2 < best.n2) { best.n2 = n2; best.vec = s; }
 }
 
 // Row-scan kinds (mask functions of jly_3ddt.cpp and where the running-scan entry sits in the
 // tie order): F1 = MINforwardDE1 (:502-706), F3 = MINforwardDE3 (:51-131), B1 = MINbackwardDE1
 // (:295-500), B3 = MINbackwardDE3 (:171-252), C_UP = MINforwardDE4 (:133-169, scan z ascending),
-// C_DN = MINforwardDE2 (:254-293, scan z descending).
+// C_DN = MINforwardDE2 (:254-293, scan z descending).  The two "quirk" entries of DE3/backwardDE1
+// (read (z+1,y) but add (0,1,1)) can never win: the entry just before them offers the same source
+// voxel with a strictly smaller increment; they are omitted.
 enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 
-struct RowShared {
-    int nP[kMaxS]; int nQ[kMaxS];
-    short dP[kMaxS]; short dQ[kMaxS];
-    Vox vP[kMaxS]; Vox vQ[kMaxS];
-    short start[kMaxS]; unsigned char tag[kMaxS];      // 0 = P, 1 = chain, 2 = Q, 3 = none
+struct RowSmem {
+    Vox* xs[3];          // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
+    Vox* prev;           // final previous row of the current slice in this pass, padded
+    int* T; int* own_n; short* own_d; Vox* own_v;
+    short* run_start; short* run_end; unsigned char* accept;
+    unsigned* wmask;
 };
 
 template <int KIND>
-__device__ void row_scan(Vox* G, int S, int x, int y, RowShared& sh)
+__device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox self)
 {
     const int z = threadIdx.x;
     const bool active = z < S;
-    // scan direction: +1 = z ascending (recurrence reads z-1), -1 = z descending (reads z+1)
-    constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;
+    constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;     // +1: recurrence reads z-1
+    const int k = dir > 0 ? z : S - 1 - z;                                      // position in scan order
     Cand P, Q;
-    P.n2 = kInf; Q.n2 = kInf; P.vec.v = P.vec.h = P.vec.d = 32767; P.vec.pad = 0; Q.vec = P.vec;
+    P.n2 = kInf; Q.n2 = kInf; P.vec = vox_unset_value(); Q.vec = P.vec;
     if (active) {
+        const int zp = z + 1;                                                    // padded index
         if (KIND == F1 || KIND == B1) {
-            const int xs = KIND == F1 ? x - 1 : x + 1;
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dz = -1; dz <= 1; dz++)
-                    consider(P, G, S, xs, y + dy, z + dz, 1, dy != 0, dz != 0);
-        }
-        if (KIND == F1 || KIND == B3) {              // previous row y-1, then self; recurrence comes last
-            consider(P, G, S, x, y - 1, z - 1, 0, 1, 1);
-            consider(P, G, S, x, y - 1, z, 0, 1, 0);
-            consider(P, G, S, x, y - 1, z + 1, 0, 1, 1);
-            consider(P, G, S, x, y, z, 0, 0, 0);
-        } else if (KIND == F3 || KIND == B1) {       // recurrence first, then (z,y+1), self, (z-1,y+1)
-            consider(Q, G, S, x, y + 1, z, 0, 1, 0);
-            consider(Q, G, S, x, y, z, 0, 0, 0);
-            consider(Q, G, S, x, y + 1, z - 1, 0, 1, 1);
-        } else {                                     // pure chains: recurrence first, then self
-            consider(Q, G, S, x, y, z, 0, 0, 0);
-        }
-        sh.nP[z] = P.n2; sh.dP[z] = P.vec.d; sh.vP[z] = P.vec;
-        sh.nQ[z] = Q.n2; sh.dQ[z] = Q.vec.d; sh.vQ[z] = Q.vec;
-    }
-    __syncthreads();
-    // Static test: would the recurrence win anywhere if its source were the neighbour's own
-    // (recurrence-free) result?  If nowhere, it wins nowhere (induction along the scan) and the
-    // row is settled without any serial work.
-    int win = 0;
-    if (active) {
-        const int zp = z - dir;
-        if (zp >= 0 && zp < S) {
-            int n0 = sh.nP[zp], d0 = sh.dP[zp];
-            if (sh.nQ[zp] < n0) { n0 = sh.nQ[zp]; d0 = sh.dQ[zp]; }
-            if (n0 < kInf) {
-                const int nc = n0 + 2 * d0 + 1;
-                win = (nc < P.n2) && (nc <= Q.n2);
+            for (int dy = -1; dy <= 1; dy++) {
+                const Vox* row = sh.xs[(y + dy + 3) % 3];
+                consider(P, row[zp - 1], 1, dy != 0, 1);
+                consider(P, row[zp], 1, dy != 0, 0);
+                consider(P, row[zp + 1], 1, dy != 0, 1);
             }
         }
+        if (KIND == F1 || KIND == B3) {              // previous row y-1, then self; recurrence comes last
+            consider(P, sh.prev[zp - 1], 0, 1, 1);
+            consider(P, sh.prev[zp], 0, 1, 0);
+            consider(P, sh.prev[zp + 1], 0, 1, 1);
+            consider(P, self, 0, 0, 0);
+        } else if (KIND == F3 || KIND == B1) {       // recurrence first, then (z,y+1), self, (z-1,y+1)
+            consider(Q, sh.prev[zp], 0, 1, 0);
+            consider(Q, self, 0, 0, 0);
+            consider(Q, sh.prev[zp - 1], 0, 1, 1);
+        } else {                                     // pure chains: recurrence first, then self
+            consider(Q, self, 0, 0, 0);
+        }
+        const bool p_first = P.n2 <= Q.n2;
+        sh.own_n[k] = p_first ? P.n2 : Q.n2;
+        sh.own_d[k] = p_first ? P.vec.d : Q.vec.d;
+        sh.own_v[k] = p_first ? P.vec : Q.vec;
+        sh.T[k] = min(P.n2, Q.n2 + 1);               // recurrence wins iff nc < nP and nc <= nQ
+        sh.run_start[k] = -1;
     }
+    __syncthreads();
+    // A run can only begin with a win against the neighbour's OWN value.  A "win" whose vector is
+    // identical to the voxel's own result changes nothing (state == own either way) and is not a
+    // head; likewise a run that arrives at a voxel carrying exactly the vector the voxel would
+    // hold anyway simply ends there.  Most recurrence wins are such ties (the chain entry precedes
+    // `self` in four of the six masks), so real heads are few and runs short.
+    Vox out = (P.n2 <= Q.n2) ? P.vec : Q.vec;
+    int win = 0, nc = 0, d0 = 0; short v0 = 0, h0 = 0;
+    if (active && k >= 1) {
+        const int n0 = sh.own_n[k - 1];
+        if (n0 < kInf) {
+            const Vox o = sh.own_v[k - 1];
+            d0 = o.d; v0 = o.v; h0 = o.h; nc = n0 + 2 * d0 + 1;
+            win = (nc < sh.T[k]) && !(o.v == out.v && o.h == out.h && d0 + 1 == out.d);
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, win);
+    if ((threadIdx.x & 31) == 0) sh.wmask[threadIdx.x >> 5] = ballot;
     const int any = __syncthreads_or(win);
+    if (g_dt_stats && threadIdx.x == 0) { atomicAdd(&g_dt_stats[0], 1ull); if (any) atomicAdd(&g_dt_stats[1], 1ull); }
     if (any) {
-        if (threadIdx.x == 0) {
-            int n_prev = kInf, d_prev = 0, s_prev = 0;
-            for (int k = 0; k < S; k++) {
-                const int zz = dir > 0 ? k : S - 1 - k;
-                const int nP = sh.nP[zz], nQ = sh.nQ[zz];
-                const int nc = n_prev < kInf ? n_prev + 2 * d_prev + 1 : kInf;
-                int t, n, d, s;
-                if (nP <= nc && nP <= nQ) { t = nP < kInf ? 0 : 3; n = nP; d = sh.dP[zz]; s = zz; }
-                else if (nc <= nQ)        { t = 1; n = nc; d = d_prev + 1; s = s_prev; }
-                else                      { t = 2; n = nQ; d = sh.dQ[zz]; s = zz; }
-                sh.tag[zz] = (unsigned char)t; sh.start[zz] = (short)s;
-                n_prev = n; d_prev = d; s_prev = s;
+        if (win) {                                   // extent of the run that starts at k-1
+            int n = nc, d = d0 + 1, pos = k + 1;
+            while (pos < S) {
+                n += 2 * d + 1; d++;
+                if (!(n < sh.T[pos])) break;
+                if (n == sh.own_n[pos]) { const Vox o = sh.own_v[pos]; if (o.v == v0 && o.h == h0 && o.d == d) break; }
+                pos++;
+            }
+            sh.run_end[k] = (short)pos;
+            if (g_dt_stats) { atomicAdd(&g_dt_stats[2], 1ull); atomicAdd(&g_dt_stats[3], (unsigned long long)(pos - k)); atomicMax(&g_dt_stats[4], (unsigned long long)(pos - k)); }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // heads in scan order; a head whose start lies inside an accepted run is void.
+            // (lane 0 walks the ballots: the number of heads per row is small)
+            if (threadIdx.x == 0) {
+                int last_end = -1;
+                const int nw = (S + 31) / 32;
+                if (dir > 0) {
+                    for (int w = 0; w < nw; w++) {
+                        unsigned m = sh.wmask[w];
+                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; const int kk = w * 32 + b;      // kk == z
+                            const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
+                    }
+                } else {
+                    for (int w = nw - 1; w >= 0; w--) {
+                        unsigned m = sh.wmask[w];
+                        while (m) { const int b = 31 - __clz(m); m &= ~(1u << b); const int kk = S - 1 - (w * 32 + b);   // thread z -> k
+                            const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
+                    }
+                }
             }
         }
         __syncthreads();
-    }
-    if (active) {
-        Vox out;
-        bool write = true;
-        if (!any) {
-            if (P.n2 <= Q.n2) { out = P.vec; write = P.n2 < kInf; } else out = Q.vec;
-        } else {
-            const int t = sh.tag[z];
-            if (t == 0) out = P.vec;
-            else if (t == 2) out = Q.vec;
-            else if (t == 1) {
-                const int s = sh.start[z];
-                out = sh.tag[s] == 0 ? sh.vP[s] : sh.vQ[s];
-                out.d = (short)(out.d + (dir > 0 ? z - s : s - z));
-            } else write = false;
+        if (win && sh.accept[k]) { const int e = sh.run_end[k]; for (int pos = k; pos < e; pos++) sh.run_start[pos] = (short)(k - 1); }
+        __syncthreads();
+        if (active) {
+            const int rs = sh.run_start[k];
+            if (rs >= 0) { out = sh.own_v[rs]; out.d = (short)(out.d + (k - rs)); }
         }
-        if (write) G[((size_t)x * S + y) * S + z] = out;
     }
+    return out;
+}
+
+// one pass over the rows of slice x: K1 then K2 on every row, rows in direction ydir
+template <int K1, int K2>
+__device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem& sh)
+{
+    const int z = threadIdx.x;
+    const bool active = z < S;
+    const Vox unset = vox_unset_value();
+    const bool use_xs = (K1 == F1 || K1 == B1) && xs >= 0 && xs < S;
+    const int y0 = ydir > 0 ? 0 : S - 1;
+    auto gload = [&](int xx, int yy) -> Vox { return (active && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset; };
+    // prime the shared rows: adjacent-slice rows y0-1, y0, y0+1 ; previous row of this slice = outside
+    if (active) {
+        for (int r = -1; r <= 1; r++) sh.xs[(y0 + r + 3) % 3][z + 1] = use_xs ? gload(xs, y0 + r) : unset;
+        sh.prev[z + 1] = unset;
+    }
+    Vox self_next = gload(x, y0);
+    Vox xs_next = use_xs ? gload(xs, y0 + 2 * ydir) : unset;
     __syncthreads();
+    for (int i = 0, y = y0; i < S; i++, y += ydir) {
+        const Vox self = self_next;
+        const Vox xs_row = xs_next;                         // adjacent-slice row y + 2*ydir ... consumed after this row
+        self_next = gload(x, y + ydir);                     // prefetch: own column only
+        xs_next = use_xs ? gload(xs, y + 3 * ydir) : unset;
+        Vox v = row_scan<K1>(sh, S, y, self);
+        __syncthreads();                                    // scan records are reused by the second scan
+        v = row_scan<K2>(sh, S, y, v);
+        if (active) {
+            G[((size_t)x * S + y) * S + z] = v;
+            sh.prev[z + 1] = v;
+            // the adjacent-slice row that falls out of the 3-row window is replaced by the incoming one
+            if (K1 == F1 || K1 == B1) sh.xs[(y + 2 * ydir + 3 + 3) % 3][z + 1] = xs_row;
+        }
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(kMaxS)
 dt_propagate_kernel(Vox* G, int S)
 {
-    __shared__ RowShared sh;
+    extern __shared__ __align__(16) unsigned char dt_smem[];
+    RowSmem sh;
+    {
+        unsigned char* p = dt_smem;
+        const size_t row = (size_t)(S + 2) * sizeof(Vox);
+        for (int r = 0; r < 3; r++) { sh.xs[r] = reinterpret_cast<Vox*>(p); p += row; }
+        sh.prev = reinterpret_cast<Vox*>(p); p += row;
+        sh.own_v = reinterpret_cast<Vox*>(p); p += (size_t)S * sizeof(Vox);
+        sh.T = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int);
+        sh.own_n = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int);
+        sh.wmask = reinterpret_cast<unsigned*>(p); p += 32 * sizeof(unsigned);
+        sh.own_d = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
+        sh.run_start = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
+        sh.run_end = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
+        sh.accept = p;
+    }
+    // pads of the shared rows stay "unset" for the whole kernel
+    if (threadIdx.x == 0) {
+        const Vox u = vox_unset_value();
+        for (int r = 0; r < 3; r++) { sh.xs[r][0] = u; sh.xs[r][S + 1] = u; }
+        sh.prev[0] = u; sh.prev[S + 1] = u;
+    }
+    __syncthreads();
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
-        for (int y = 0; y < S; y++) { row_scan<F1>(G, S, x, y, sh); row_scan<C_DN>(G, S, x, y, sh); }
-        for (int y = S - 1; y >= 0; y--) { row_scan<F3>(G, S, x, y, sh); row_scan<C_UP>(G, S, x, y, sh); }
+        slice_pass<F1, C_DN>(G, S, x, x - 1, +1, sh);
+        slice_pass<F3, C_UP>(G, S, x, -1, -1, sh);
     }
     for (int x = S - 1; x >= 0; x--) {                              // :729-739
-        for (int y = S - 1; y >= 0; y--) { row_scan<B1>(G, S, x, y, sh); row_scan<C_UP>(G, S, x, y, sh); }
-        for (int y = 0; y < S; y++) { row_scan<B3>(G, S, x, y, sh); row_scan<C_DN>(G, S, x, y, sh); }
+        slice_pass<B1, C_UP>(G, S, x, x + 1, -1, sh);
+        slice_pass<B3, C_DN>(G, S, x, -1, +1, sh);
     }
+}
+
+static size_t dt_propagate_smem(int S)
+{
+    return 4 * (size_t)(S + 2) * sizeof(Vox) + (size_t)S * sizeof(Vox) + 2 * (size_t)S * sizeof(int) + 32 * sizeof(unsigned)
+         + 3 * (size_t)(S + 2) * sizeof(short) + (size_t)S + 64;
 }
 
 // distance = float( double(float(sqrt(double(n2)))) / scale ), clamped at 0 (jly_3ddt.cpp:970-978);
@@ -288,7 +387,24 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     DT_TRY(cudaGetLastError());
     if (mode == 0) {
         const int threads = ((S + 31) / 32) * 32;
-        dt_propagate_kernel<<<1, threads, 0, stream>>>(G, S);
+        const size_t smem = dt_propagate_smem(S);
+        DT_TRY(cudaFuncSetAttribute(dt_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned long long* d_stats = nullptr;
+        if (getenv("GOICP_DT_STATS")) {
+            DT_TRY(cudaMalloc((void**)&d_stats, 8 * sizeof(unsigned long long)));
+            DT_TRY(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), stream));
+            DT_TRY(cudaMemcpyToSymbolAsync(g_dt_stats, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, stream));
+        }
+        dt_propagate_kernel<<<1, threads, smem, stream>>>(G, S);
+        if (d_stats) {
+            unsigned long long hs[8];
+            DT_TRY(cudaMemcpyAsync(hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, stream));
+            DT_TRY(cudaStreamSynchronize(stream));
+            fprintf(stderr, "[dt stats] row scans %llu, with runs %llu, run heads %llu, total run length %llu, max run %llu\n", hs[0], hs[1], hs[2], hs[3], hs[4]);
+            unsigned long long* null_ptr = nullptr;
+            DT_TRY(cudaMemcpyToSymbolAsync(g_dt_stats, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, stream));
+            cudaFree(d_stats);
+        }
         DT_TRY(cudaGetLastError());
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);
         dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, meta[3], d_out);
