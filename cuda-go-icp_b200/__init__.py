@@ -34,7 +34,7 @@ class Params(C.Structure):
     _fields_ = [("mse_threshold", C.c_float), ("trim_fraction", C.c_float), ("do_trim", C.c_int),
                 ("dt_size", C.c_int), ("dt_expand", C.c_double),
                 ("rot_cube", C.c_float * 4), ("trans_cube", C.c_float * 4),
-                ("icp_max_iter", C.c_int), ("device", C.c_int), ("spec_cubes", C.c_int), ("dt_mode", C.c_int),
+                ("icp_max_iter", C.c_int), ("device", C.c_int), ("spec_cubes", C.c_int), ("cluster_size", C.c_int), ("dt_mode", C.c_int),
                 ("rank", C.c_int), ("world_size", C.c_int)]
 
 
@@ -156,6 +156,7 @@ class GoICP:
         self.dt = _DT()
         self.dt_mode = 0
         self.spec_cubes = 0
+        self.cluster_size = 0
         self.initNodeRot = [p.rot_cube[i] for i in range(4)]
         self.initNodeTrans = [p.trans_cube[i] for i in range(4)]
         self.pModel = None
@@ -186,6 +187,7 @@ class GoICP:
             p.dt_expand = float(self.dt.expandFactor)
             p.dt_mode = int(self.dt_mode)
             p.spec_cubes = int(self.spec_cubes)
+            p.cluster_size = int(self.cluster_size)
             p.rank, p.world_size = self.rank, self.world_size
             for i in range(4):
                 p.rot_cube[i] = self.initNodeRot[i]

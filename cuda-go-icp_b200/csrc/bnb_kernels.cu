@@ -8,6 +8,7 @@
 #include "goicp_types.h"
 #include "goicp_kernels.h"
 #include "strict_sum.cuh"
+#include <cooperative_groups.h>
 
 namespace goicp {
 
@@ -91,14 +92,13 @@ expand_bounds_kernel(BnbConst c, const PairTask* __restrict__ tasks, float* __re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float w = t.tc[3] / 2;                     // child width (jly_goicp.cpp:262)
     const float half = w / 2;
-    float tx[2], ty[2], tz[2];
-#pragma unroll
-    for (int b = 0; b < 2; b++) {                    // nodeTrans.x = parent.x + bit*w ; transX = nodeTrans.x + w/2
-        tx[b] = __fadd_rn(__fadd_rn(t.tc[0], b ? w : 0.0f), half);
-        ty[b] = __fadd_rn(__fadd_rn(t.tc[1], b ? w : 0.0f), half);
-        tz[b] = __fadd_rn(__fadd_rn(t.tc[2], b ? w : 0.0f), half);
+    __shared__ float tr[8];
+    if (threadIdx.x < 6) {                           // nodeTrans.x = parent.x + bit*w ; transX = nodeTrans.x + w/2
+        const int b = threadIdx.x & 1;
+        tr[threadIdx.x] = __fadd_rn(__fadd_rn(t.tc[threadIdx.x >> 1], b ? w : 0.0f), half);
     }
-    const float gt = max_trans_dis(w);
+    if (threadIdx.x == 6) tr[6] = max_trans_dis(w);
+    __syncthreads();
     const float cg = t.level >= 0 ? c.cgamma[t.level] : 0.0f;
     float acc[16];
 #pragma unroll
@@ -108,7 +108,7 @@ expand_bounds_kernel(BnbConst c, const PairTask* __restrict__ tasks, float* __re
         float rx = dot3_ref(t.R[0], t.R[1], t.R[2], p.x, p.y, p.z);
         float ry = dot3_ref(t.R[3], t.R[4], t.R[5], p.x, p.y, p.z);
         float rz = dot3_ref(t.R[6], t.R[7], t.R[8], p.x, p.y, p.z);
-        accumulate_point8(c.dt, rx, ry, rz, __fmul_rn(cg, p.w), tx, ty, tz, gt, acc);
+        accumulate_point8(c.dt, rx, ry, rz, __fmul_rn(cg, p.w), tr, acc);
     }
     block_reduce16(acc, red, tot, warp, lane);
     if (threadIdx.x < 16) out16[blockIdx.x * 16 + threadIdx.x] = tot[threadIdx.x];
@@ -171,80 +171,101 @@ __device__ __forceinline__ HeapEntry heap_pop(Heap& h)
 }
 
 // ------------------------------------------------------------------------------------------
-// Persistent translation branch-and-bound: ONE CTA runs one whole GoICP::InnerBnB call
-// (jly_goicp.cpp:227-340) -- pop, expand into 8 children, 8*Nd DT gathers, reduce, prune,
-// push -- without leaving the SM.  Thread 0 owns the priority queue; all threads gather.
+// Persistent translation branch-and-bound: ONE THREAD-BLOCK CLUSTER runs one whole
+// GoICP::InnerBnB call (jly_goicp.cpp:227-340) -- pop, expand into 8 children, 8*Nd DT gathers,
+// reduce, prune, push -- without leaving the chip.
+//
+// Why a cluster: a scattered 4-byte gather costs one L1TEX sector lookup, and an SM retires about
+// one such lookup per clock (measured: the pure gather kernel runs at 0.98 lookups/clk/SM).  One
+// expansion step is 8*Nd lookups, so a single CTA needs >= 8*Nd clocks per step and the longest
+// inner BnB of a round (hundreds of steps) bounds the whole round.  A cluster of C CTAs on C SMs
+// splits the data points C ways: every CTA keeps its slice of the rotated points in its own shared
+// memory, gathers for it, and sends 16 partial sums to the leader CTA through distributed shared
+// memory; the leader owns the priority queue (libstdc++ heap order) and broadcasts the next cube.
+// Two cluster barriers per step.
 // ------------------------------------------------------------------------------------------
 struct InnerCtrl {
-    float tx[2], ty[2], tz[2];
-    float gt;
+    float tr[8];         // child translations per axis bit (x0,x1,y0,y1,z0,z1) and maxTransDis
     int done;
-    int n_cand;          // upper-bound pass: contenders for the arg-min (see strict_sum.cuh)
-    float final_fast;
 };
-constexpr int kMaxCand = 128;
+// State only the leader's thread 0 touches; kept in shared memory so that it costs the gathering
+// threads no registers.
+struct OwnerState {
+    float opt_t; float best[4];
+    uint32_t pops, evals, max_heap; int status; int heap_n;
+    float px, py, pz, cw; uint32_t plevel, ppath_lo, ppath_hi;
+    int n_cand; uint32_t flags;
+};
+constexpr int kMaxCluster = 16;
 
 template <bool PTS_SMEM>
 __global__ void __launch_bounds__(kBnbThreads, 2)
 inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
-                 int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap)
+                 int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int task_id = blockIdx.x / C;
+
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float red[kBnbWarps][16];
     __shared__ float tot[16];
-    __shared__ InnerCtrl ctrl;
+    __shared__ InnerCtrl ctrl;                       // written by the leader into every CTA of the cluster
+    __shared__ float partials[kMaxCluster][16];      // leader: one row per CTA
+    __shared__ OwnerState own;
     __shared__ float4 cand_node[kMaxCand];
     __shared__ float cand_ub[kMaxCand];
 
     HeapEntry* hsm = reinterpret_cast<HeapEntry*>(smem_raw);
     float4* pts = reinterpret_cast<float4*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry));
 
-    const InnerTask& task = tasks[blockIdx.x];
+    const long long t_begin = clock64();
+    const InnerTask& task = tasks[task_id];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float cg = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
-    const float R0 = task.R[0], R1 = task.R[1], R2 = task.R[2], R3 = task.R[3], R4 = task.R[4], R5 = task.R[5],
-                R6 = task.R[6], R7 = task.R[7], R8 = task.R[8];
-
-    if (PTS_SMEM) {
-        // rotate once (jly_goicp.cpp:470-476) and keep (R p, gamma) on chip for the whole search
-        for (int i = tid; i < c.nd; i += kBnbThreads) {
-            float4 p = __ldg(c.data + i);
-            pts[i] = make_float4(dot3_ref(R0, R1, R2, p.x, p.y, p.z), dot3_ref(R3, R4, R5, p.x, p.y, p.z),
-                                 dot3_ref(R6, R7, R8, p.x, p.y, p.z), __fmul_rn(cg, p.w));
-        }
-    }
-
-    // ---- thread-0 state -----------------------------------------------------------------
-    Heap heap;
-    heap.sm = hsm; heap.gl = spill + (size_t)blockIdx.x * spill_cap; heap.cap_sm = heap_cap_sm;
-    heap.cap_total = heap_cap_sm + spill_cap; heap.n = 0;
-    float opt_t = task.opt_error;
-    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    uint32_t pops = 0, evals = 0, max_heap = 0;
-    int status = 0;
+    const bool leader = rank == 0;
     const bool ub_pass = task.level < 0;
     // |sequential float sum - tree float sum| <= ~Nd*2^-24 relative; contenders within twice that
     const float cand_eps = fminf(1e-2f, 2.0f * (float)c.nd * 5.9604645e-8f) + 1e-6f;
-    int n_cand = 0; uint32_t flags = 0;
-    // parent being expanded
-    float px = 0, py = 0, pz = 0, cw = 0;
-    uint32_t plevel = 0, ppath_lo = 0, ppath_hi = 0;
+    // this CTA's slice of the data points
+    const int per = (c.nd + C - 1) / C;
+    const int p_begin = min(rank * per, c.nd), p_end = min(p_begin + per, c.nd);
+    const int np = p_end - p_begin;
 
-    if (tid == 0) {
+    if (PTS_SMEM) {
+        // rotate once (jly_goicp.cpp:470-476) and keep (R p, gamma) on chip for the whole search
+        const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+        for (int i = tid; i < np; i += kBnbThreads) {
+            float4 p = __ldg(c.data + p_begin + i);
+            pts[i] = make_float4(dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                 dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w));
+        }
+    }
+    HeapEntry* const spill_mine = spill + (size_t)task_id * spill_cap;
+    if (leader && tid == 0) {
+        own.opt_t = task.opt_error;
+        own.best[0] = own.best[1] = own.best[2] = own.best[3] = 0.0f;
+        own.pops = own.evals = own.max_heap = 0; own.status = 0; own.n_cand = 0; own.flags = 0;
+        Heap heap; heap.sm = hsm; heap.gl = spill_mine; heap.cap_sm = heap_cap_sm; heap.cap_total = heap_cap_sm + spill_cap; heap.n = 0;
         HeapEntry root; root.lb = 0.0f; root.level = 0; root.path_lo = 0; root.path_hi = 0;   // initNodeTrans.lb = 0 (jly_goicp.cpp:63)
         heap_push(heap, root);
+        own.heap_n = heap.n;
     }
 
     for (;;) {
-        if (tid == 0) {
-            int done = 0;
-            if (status) done = 1;                                                 // heap capacity exceeded: give up loudly
-            else if (heap.n == 0) done = 1;                                      // :243-244
+        if (leader && tid == 0) {
+            Heap heap; heap.sm = hsm; heap.gl = spill_mine; heap.cap_sm = heap_cap_sm; heap.cap_total = heap_cap_sm + spill_cap; heap.n = own.heap_n;
+            InnerCtrl next; next.done = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) next.tr[k] = 0.0f;
+            if (own.status) next.done = 1;                                        // heap capacity exceeded: give up loudly
+            else if (heap.n == 0) next.done = 1;                                  // :243-244
             else {
                 HeapEntry e = heap_pop(heap);
-                pops++;                                                           // tNodeCount++ (:248)
-                if (__fsub_rn(opt_t, e.lb) < c.sse_thresh) done = 1;              // :257
-                else if (e.level >= (uint32_t)kMaxTransLevel) { done = 1; status = 4; }
+                own.pops++;                                                       // tNodeCount++ (:248)
+                if (__fsub_rn(own.opt_t, e.lb) < c.sse_thresh) next.done = 1;     // :257
+                else if (e.level >= (uint32_t)kMaxTransLevel) { next.done = 1; own.status = 4; }
                 else {
                     // rebuild the cube corner by replaying the reference's float additions
                     // parent.x + (j&1)*w down the octant path (:267-269)
@@ -257,58 +278,64 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
                         y = __fadd_rn(y, (b & 2) ? w : 0.0f);
                         z = __fadd_rn(z, (b & 4) ? w : 0.0f);
                     }
-                    px = x; py = y; pz = z; cw = w / 2;                           // nodeTrans.w = parent.w/2 (:262)
-                    plevel = e.level; ppath_lo = e.path_lo; ppath_hi = e.path_hi;
+                    const float cw = w / 2;                                       // nodeTrans.w = parent.w/2 (:262)
+                    own.px = x; own.py = y; own.pz = z; own.cw = cw;
+                    own.plevel = e.level; own.ppath_lo = e.path_lo; own.ppath_hi = e.path_hi;
                     const float half = cw / 2;
 #pragma unroll
                     for (int b = 0; b < 2; b++) {
-                        ctrl.tx[b] = __fadd_rn(__fadd_rn(px, b ? cw : 0.0f), half);
-                        ctrl.ty[b] = __fadd_rn(__fadd_rn(py, b ? cw : 0.0f), half);
-                        ctrl.tz[b] = __fadd_rn(__fadd_rn(pz, b ? cw : 0.0f), half);
+                        next.tr[b] = __fadd_rn(__fadd_rn(x, b ? cw : 0.0f), half);
+                        next.tr[2 + b] = __fadd_rn(__fadd_rn(y, b ? cw : 0.0f), half);
+                        next.tr[4 + b] = __fadd_rn(__fadd_rn(z, b ? cw : 0.0f), half);
                     }
-                    ctrl.gt = max_trans_dis(cw);
+                    next.tr[6] = max_trans_dis(cw);
                 }
             }
-            ctrl.done = done;
+            own.heap_n = heap.n;
+            for (int r = 0; r < C; r++) *cluster.map_shared_rank(&ctrl, r) = next;   // broadcast through DSMEM
         }
-        __syncthreads();
+        cluster.sync();
         if (ctrl.done) break;
 
-        // ---- 8 x Nd distance-transform gathers -----------------------------------------
+        // ---- 8 x (Nd / C) distance-transform gathers ------------------------------------
         float acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0.0f;
-        {
-            const float tx[2] = {ctrl.tx[0], ctrl.tx[1]}, ty[2] = {ctrl.ty[0], ctrl.ty[1]}, tz[2] = {ctrl.tz[0], ctrl.tz[1]};
-            const float gt = ctrl.gt;
-            if (PTS_SMEM) {
-                for (int i = tid; i < c.nd; i += kBnbThreads) {
-                    float4 p = pts[i];
-                    accumulate_point8(c.dt, p.x, p.y, p.z, p.w, tx, ty, tz, gt, acc);
-                }
-            } else {
-                for (int i = tid; i < c.nd; i += kBnbThreads) {
-                    float4 p = __ldg(c.data + i);
-                    accumulate_point8(c.dt, dot3_ref(R0, R1, R2, p.x, p.y, p.z), dot3_ref(R3, R4, R5, p.x, p.y, p.z),
-                                      dot3_ref(R6, R7, R8, p.x, p.y, p.z), __fmul_rn(cg, p.w), tx, ty, tz, gt, acc);
-                }
+        if (PTS_SMEM) {
+            for (int i = tid; i < np; i += kBnbThreads) {
+                const float4 p = pts[i];
+                accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+            }
+        } else {
+            const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+            for (int i = p_begin + tid; i < p_end; i += kBnbThreads) {
+                const float4 p = __ldg(c.data + i);
+                accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                  dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
             }
         }
-        block_reduce16(acc, red, tot, warp, lane);      // contains a __syncthreads()
+        block_reduce16(acc, red, tot, warp, lane);      // contains a __syncthreads(); tot valid in warp 0
+        if (warp == 0 && lane < 16) cluster.map_shared_rank(&partials[0][0], 0)[rank * 16 + lane] = tot[lane];
+        cluster.sync();
 
         // ---- sequential bookkeeping of the 8 children (jly_goicp.cpp:317-336) -------------
-        if (tid == 0) {
-            evals += 8;
+        if (leader && tid == 0) {
+            Heap heap; heap.sm = hsm; heap.gl = spill_mine; heap.cap_sm = heap_cap_sm; heap.cap_total = heap_cap_sm + spill_cap; heap.n = own.heap_n;
+            float opt_t = own.opt_t;
+            const float px = own.px, py = own.py, pz = own.pz, cw = own.cw;
+            own.evals += 8;
             for (int j = 0; j < 8; j++) {
-                const float ub = tot[j], lb = tot[8 + j];
+                float ub = 0.0f, lb = 0.0f;                 // fixed-order sum over the cluster's CTAs
+                for (int r = 0; r < C; r++) { ub += partials[r][j]; lb += partials[r][8 + j]; }
                 if (ub < opt_t) {
                     opt_t = ub;
-                    best[0] = __fadd_rn(px, (j & 1) ? cw : 0.0f);
-                    best[1] = __fadd_rn(py, (j & 2) ? cw : 0.0f);
-                    best[2] = __fadd_rn(pz, (j & 4) ? cw : 0.0f);
-                    best[3] = cw;
+                    own.best[0] = __fadd_rn(px, (j & 1) ? cw : 0.0f);
+                    own.best[1] = __fadd_rn(py, (j & 2) ? cw : 0.0f);
+                    own.best[2] = __fadd_rn(pz, (j & 4) ? cw : 0.0f);
+                    own.best[3] = cw;
                 }
                 if (ub_pass && ub <= opt_t * (1.0f + cand_eps)) {
+                    int n_cand = own.n_cand;
                     if (n_cand == kMaxCand) {           // drop contenders the running minimum has left behind
                         int k = 0;
                         for (int q = 0; q < n_cand; q++)
@@ -319,83 +346,90 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
                         cand_node[n_cand] = make_float4(__fadd_rn(px, (j & 1) ? cw : 0.0f), __fadd_rn(py, (j & 2) ? cw : 0.0f),
                                                         __fadd_rn(pz, (j & 4) ? cw : 0.0f), cw);
                         cand_ub[n_cand] = ub; n_cand++;
-                    } else flags |= 1u;                 // could not keep every contender: result is the tree-sum one
+                    } else own.flags |= 1u;             // could not keep every contender
+                    own.n_cand = n_cand;
                 }
                 if (lb >= opt_t) continue;
-                HeapEntry e; e.lb = lb; e.level = plevel + 1;
-                unsigned long long path = (((unsigned long long)ppath_hi << 32) | ppath_lo) | ((unsigned long long)j << (3 * plevel));
+                HeapEntry e; e.lb = lb; e.level = own.plevel + 1;
+                unsigned long long path = (((unsigned long long)own.ppath_hi << 32) | own.ppath_lo) | ((unsigned long long)j << (3 * own.plevel));
                 e.path_lo = (uint32_t)path; e.path_hi = (uint32_t)(path >> 32);
-                if (!heap_push(heap, e)) { status = 3; break; }
+                if (!heap_push(heap, e)) { own.status = 3; break; }
             }
-            if ((uint32_t)heap.n > max_heap) max_heap = heap.n;
+            own.opt_t = opt_t;
+            own.heap_n = heap.n;
+            if ((uint32_t)heap.n > own.max_heap) own.max_heap = heap.n;
         }
         // a failed push (status != 0) ends the task at the top of the next iteration
     }
+    if (!leader) return;
 
-    // ---- strict resolution of the arg-min (upper-bound pass only) ---------------------------
-    // The search above used fixed-order tree sums.  The reference's optErrorT is the first strict
-    // minimum of its own sequential sums over the same evaluated cubes; re-evaluate the contenders
-    // in reference order (strict_sum.cuh) and replay that rule.
-    float strict_value = opt_t;
+    // ---- results.  The search used fixed-order tree sums.  For an upper-bound pass the cubes
+    // whose sum is within rounding distance of the minimum are handed to the host: if this call
+    // turns out to improve the global optimum, strict_eval_kernel re-evaluates exactly those in
+    // the reference's summation order to settle the arg-min (strict_sum.cuh).
     if (ub_pass) {
         if (tid == 0) {
             int k = 0;
-            for (int q = 0; q < n_cand; q++)
-                if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; k++; }
-            ctrl.n_cand = (flags & 1u) ? 0 : k;
+            for (int q = 0; q < own.n_cand; q++)
+                if (cand_ub[q] <= own.opt_t * (1.0f + cand_eps)) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; k++; }
+            own.n_cand = k;
         }
         __syncthreads();
-        const int nc = ctrl.n_cand;
-        float* scratch = reinterpret_cast<float*>(spill + (size_t)blockIdx.x * spill_cap);
-        const size_t scratch_floats = (size_t)spill_cap * (sizeof(HeapEntry) / sizeof(float));
-        int per_chunk = (int)min((size_t)kBnbWarps, scratch_floats / (size_t)max(c.nd, 1));
-        if (nc > 0 && per_chunk == 0) { if (tid == 0) flags |= 2u; }
-        else if (nc > 0) {
-            float so = task.opt_error;                       // thread 0: the reference's running optErrorT
-            bool have = false;
-            for (int base = 0; base < nc; base += per_chunk) {
-                const int cnt = min(per_chunk, nc - base);
-                for (int q = 0; q < cnt; q++) {
-                    const float4 nd4 = cand_node[base + q];
-                    const float half = nd4.w / 2;
-                    const float tx = __fadd_rn(nd4.x, half), ty = __fadd_rn(nd4.y, half), tz = __fadd_rn(nd4.z, half);
-                    float* m = scratch + (size_t)q * c.nd;
-                    for (int i = tid; i < c.nd; i += kBnbThreads) {
-                        float rx, ry, rz;
-                        if (PTS_SMEM) { const float4 p = pts[i]; rx = p.x; ry = p.y; rz = p.z; }
-                        else {
-                            const float4 p = __ldg(c.data + i);
-                            rx = dot3_ref(R0, R1, R2, p.x, p.y, p.z); ry = dot3_ref(R3, R4, R5, p.x, p.y, p.z); rz = dot3_ref(R6, R7, R8, p.x, p.y, p.z);
-                        }
-                        float d = dt_distance(c.dt, __fadd_rn(rx, tx), __fadd_rn(ry, ty), __fadd_rn(rz, tz));
-                        m[i] = d < 0.0f ? 0.0f : d;
-                    }
-                }
-                __syncthreads();
-                if (lane == 0 && warp < cnt) {
-                    float ub, lb;
-                    ss_select_and_sum(scratch + (size_t)warp * c.nd, c.nd, c.inlier_num, c.do_trim != 0, 0.0f, false, ub, lb);
-                    cand_ub[base + warp] = ub;                   // now the reference-order sum
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    for (int q = 0; q < cnt; q++)
-                        if (cand_ub[base + q] < so) {            // `if(ub < optErrorT)` in evaluation order (:319-324)
-                            so = cand_ub[base + q]; have = true;
-                            best[0] = cand_node[base + q].x; best[1] = cand_node[base + q].y; best[2] = cand_node[base + q].z; best[3] = cand_node[base + q].w;
-                        }
-                }
-            }
-            if (tid == 0) { strict_value = so; if (!have) { best[0] = best[1] = best[2] = best[3] = 0.0f; } }
-        }
+        CandList& cl = cands[task_id];
+        for (int q = tid; q < own.n_cand; q += kBnbThreads) { cl.node[q] = cand_node[q]; cl.ub[q] = cand_ub[q]; }
+        if (tid == 0) { cl.n = own.n_cand; cl.flags = own.flags; cl.final_fast = own.opt_t; cl.eps = cand_eps; }
     }
-
     if (tid == 0) {
         InnerResult r;
-        r.value = strict_value; r.node[0] = best[0]; r.node[1] = best[1]; r.node[2] = best[2]; r.node[3] = best[3];
-        r.pops = pops; r.evals = evals; r.status = status; r.max_heap = max_heap; r.pad[0] = flags; r.pad[1] = __float_as_uint(opt_t);
-        results[blockIdx.x] = r;
+        r.value = own.opt_t; r.node[0] = own.best[0]; r.node[1] = own.best[1]; r.node[2] = own.best[2]; r.node[3] = own.best[3];
+        r.pops = own.pops; r.evals = own.evals; r.status = own.status; r.max_heap = own.max_heap;
+        r.pad[0] = own.flags; r.pad[1] = ub_pass ? (uint32_t)own.n_cand : 0u;
+        r.kcycles = (uint32_t)((clock64() - t_begin) >> 10);
+        results[task_id] = r;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Strict resolution of one upper-bound pass (on demand, when the pass may improve the optimum).
+// One CTA per contender: gathers in parallel into shared memory, then one thread applies the
+// reference's intro_select + sequential float sum.  strict_pick_kernel replays the reference's
+// `if (ub < optErrorT)` over the contenders in evaluation order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+strict_eval_kernel(BnbConst c, const InnerTask* __restrict__ task_p, const CandList* __restrict__ cl, float* __restrict__ strict_ub,
+                   float* __restrict__ gscratch, int use_smem)
+{
+    extern __shared__ float m_sm[];
+    const int q = blockIdx.x;
+    if (q >= cl->n) return;
+    if (!(cl->ub[q] <= cl->final_fast * (1.0f + cl->eps))) { if (threadIdx.x == 0) strict_ub[q] = 3.402823466e+38f; return; }
+    const InnerTask& task = *task_p;
+    float* m = use_smem ? m_sm : gscratch + (size_t)q * c.nd;
+    const float4 nd4 = cl->node[q];
+    const float half = nd4.w / 2;
+    const float tx = __fadd_rn(nd4.x, half), ty = __fadd_rn(nd4.y, half), tz = __fadd_rn(nd4.z, half);   // :270-272
+    for (int i = threadIdx.x; i < c.nd; i += blockDim.x) {
+        const float4 p = __ldg(c.data + i);
+        const float rx = dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z);
+        const float ry = dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z);
+        const float rz = dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z);
+        const float d = dt_distance(c.dt, __fadd_rn(rx, tx), __fadd_rn(ry, ty), __fadd_rn(rz, tz));
+        m[i] = d < 0.0f ? 0.0f : d;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ub, lb;
+        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb);
+        strict_ub[q] = ub;
+    }
+}
+__global__ void strict_pick_kernel(const InnerTask* __restrict__ task_p, const CandList* __restrict__ cl, const float* __restrict__ strict_ub, float* __restrict__ out5)
+{
+    float so = task_p->opt_error;                    // optErrorT starts at optError (:238)
+    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int q = 0; q < cl->n; q++)
+        if (strict_ub[q] < so) { so = strict_ub[q]; best[0] = cl->node[q].x; best[1] = cl->node[q].y; best[2] = cl->node[q].z; best[3] = cl->node[q].w; }   // :319-324
+    out5[0] = so; out5[1] = best[0]; out5[2] = best[1]; out5[3] = best[2]; out5[4] = best[3];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -406,11 +440,12 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
 // use_pose[k]==0 scores the raw data.  scratch: nposes * nd floats.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBnbThreads)
-dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ scratch, float* __restrict__ out)
+dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ scratch, float* __restrict__ out, int use_smem)
 {
+    extern __shared__ float m_sm[];
     const float* Rt = Rt12 + 12 * blockIdx.x;
     const bool pose = use_pose[blockIdx.x] != 0;
-    float* m = scratch + (size_t)blockIdx.x * c.nd;
+    float* m = use_smem ? m_sm : scratch + (size_t)blockIdx.x * c.nd;
     for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
         float4 p = __ldg(c.data + i);
         float x = p.x, y = p.y, z = p.z;
@@ -463,22 +498,51 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dt_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
     *max_dyn_out = dyn;
     return e;
 }
-cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, cudaStream_t s)
+cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)c.nd * sizeof(float4) : 0);
-    if (pts_in_smem) inner_bnb_kernel<true><<<n, kBnbThreads, smem, s>>>(c, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap);
-    else             inner_bnb_kernel<false><<<n, kBnbThreads, smem, s>>>(c, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap);
+    const int per = (c.nd + cluster - 1) / cluster;
+    size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n * cluster); cfg.blockDim = dim3(kBnbThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    BnbConst cc = c;
+    if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+}
+// out5 = {strict optErrorT, node x, y, z, w}; d_strict: kMaxCand floats; d_scratch: kMaxCand*nd floats (only if nd does not fit in smem)
+cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
+                                  float* d_out5, int smem_limit, cudaStream_t s)
+{
+    const size_t need = (size_t)c.nd * sizeof(float);
+    const int use_smem = need <= (size_t)smem_limit ? 1 : 0;
+    strict_eval_kernel<<<kMaxCand, 256, use_smem ? need : 0, s>>>(c, d_task, d_list, d_strict, d_scratch, use_smem);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    strict_pick_kernel<<<1, 1, 0, s>>>(d_task, d_list, d_strict, d_out5);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, cudaStream_t s)
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, cudaStream_t s)
 {
     if (nposes <= 0) return cudaSuccess;
-    dt_score_kernel<<<nposes, kBnbThreads, 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out);
+    const size_t need = (size_t)c.nd * sizeof(float);
+    const int use_smem = need <= (size_t)smem_limit ? 1 : 0;
+    dt_score_kernel<<<nposes, kBnbThreads, use_smem ? need : 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out, use_smem);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -66,6 +68,8 @@ struct ChildEval {
     bool skipped = true;            // outside the pi-ball (jly_goicp.cpp:443)
     float R[9];
     InnerResult ub, lb;
+    float ub_opt_error = 0;         // optError the ub pass was run with
+    std::shared_ptr<CandList> cands;    // arg-min contenders of the ub pass (when it has any)
 };
 struct CubeEval { long epoch = -1; ChildEval ch[8]; };
 
@@ -126,6 +130,8 @@ struct goicp_handle {
     bool kd_ready = false;
     // scratch
     DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
+    DevBuf<CandList> d_cands; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
+    int64_t strict_resolves = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
     DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn; DevBuf<unsigned long long> d_icp_keys; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
@@ -248,7 +254,7 @@ int make_const(goicp_handle* h, BnbConst& c)
     if (!h->initialized) { int rc = initialize(h); if (rc) return rc; }
     if (h->inlier_num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the bound kernels yet");
     c.dt.grid = h->d_dt.p; c.dt.S = h->dt_size; c.dt.S2 = h->dt_size * h->dt_size;
-    c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3];
+    c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3]; c.dt.inv_scale = 1.0 / h->dt_meta[3];
     c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
     c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
     for (int i = 0; i < kMaxRotLevel; i++) c.cgamma[i] = h->cgamma[i];
@@ -257,23 +263,31 @@ int make_const(goicp_handle* h, BnbConst& c)
 
 // Shared-memory plan of the persistent inner-BnB kernel: rotated points on chip when two CTAs
 // per SM still fit, the rest of the per-CTA budget goes to the priority queue.
-struct InnerPlan { bool pts_smem; int heap_cap_sm; };
+struct InnerPlan { bool pts_smem; int heap_cap_sm; int cluster; };
 InnerPlan plan_inner(const goicp_handle* h)
 {
-    // two CTAs per SM: each may take half of the SM's 228 KB minus its static part and the 1 KB the driver reserves per CTA
-    const size_t per_cta = (size_t)(h->inner_dyn_smem + (h->max_smem_optin - h->inner_dyn_smem)) / 2 - (size_t)(h->max_smem_optin - h->inner_dyn_smem) - 2048;
-    const size_t pts = (size_t)h->nd * sizeof(float4);
     InnerPlan p;
+    // Cluster size: one expansion step costs 8*Nd scattered lookups and an SM retires ~1 per clock,
+    // so split each inner BnB over as many SMs as keeps a slice worth a CTA (>= ~256 points).
+    int cl = h->p.cluster_size;
+    if (cl <= 0) { cl = 1; while (cl < 8 && h->nd / (cl * 2) >= 192) cl *= 2; }
+    if (cl > 16) cl = 16;
+    p.cluster = cl;
+    // two CTAs per SM: each may take half of the SM's shared memory minus its static part and the 1 KB the driver reserves per CTA
+    const size_t stat = (size_t)(h->max_smem_optin - h->inner_dyn_smem);
+    const size_t per_cta = (size_t)h->max_smem_optin / 2 - stat - 2048;
+    const size_t pts = (size_t)((h->nd + cl - 1) / cl) * sizeof(float4);
     p.pts_smem = pts + 16 * 1024 <= per_cta;
     size_t heap_bytes = per_cta - (p.pts_smem ? pts : 0);
-    p.heap_cap_sm = (int)std::min<size_t>(heap_bytes / sizeof(HeapEntry), 6144);
+    p.heap_cap_sm = (int)std::min<size_t>(heap_bytes / sizeof(HeapEntry), 4096);
     return p;
 }
 
 int ensure_task_buffers(goicp_handle* h, size_t n)
 {
-    CUDA_TRY(h, h->d_tasks.reserve(n));
+    CUDA_TRY(h, h->d_tasks.reserve(n + 1));
     CUDA_TRY(h, h->d_results.reserve(n));
+    CUDA_TRY(h, h->d_cands.reserve(n + 1));
     if (h->h_results_n < n) {
         if (h->h_results) cudaFreeHost(h->h_results);
         if (h->h_tasks) cudaFreeHost(h->h_tasks);
@@ -310,7 +324,7 @@ int shard_exchange(goicp_allgather_fn fn, void* user, int W, int n, const InnerR
 // Runs `n` inner BnBs (tasks in h->h_tasks) and leaves the results in h->h_results.
 // With an exchange hook installed, rank r runs tasks r, r+W, r+2W, ... and the per-rank result
 // blocks are all-gathered, so every rank ends up with all n results.
-int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed_evals)
+int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed_evals, std::vector<std::shared_ptr<CandList>>* lists = nullptr)
 {
     if (n <= 0) return GOICP_OK;
     int rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
@@ -330,7 +344,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     if (mine > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, launch_inner_bnb(c, h->d_tasks.p, h->d_results.p, mine, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->stream));
+        CUDA_TRY(h, launch_inner_bnb(c, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->stream));
         h->launches++;
     }
     if (W == 1) {
@@ -346,11 +360,51 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
     }
     float ms = 0; cudaEventElapsedTime(&ms, h->ev0, h->ev1); h->t_kernels += ms * 1e-3;
+    if (getenv("GOICP_ROUND_STATS")) {
+        uint32_t maxc = 0, maxp = 0, sump = 0, maxh = 0; uint64_t sumc = 0; int arg = 0, flagged = 0;
+        for (int t = 0; t < n; t++) { const InnerResult& q = h->h_results[t]; sumc += q.kcycles; sump += q.pops; if (q.kcycles > maxc) { maxc = q.kcycles; arg = t; } if (q.pops > maxp) maxp = q.pops; if (q.max_heap > maxh) maxh = q.max_heap; if (q.pad[1]) flagged++; }
+        fprintf(stderr, "[round] tasks %d kernel %.3f ms; slowest task %.3f Mcyc (pops %u, level %d); max pops %u; total pops %u; sum task cycles %.1f Mcyc; max heap %u; tasks with contenders %d\n",
+                n, ms, maxc * 1024e-6, h->h_results[arg].pops, h->h_tasks[arg].level, maxp, sump, sumc * 1024e-6, maxh, flagged);
+    }
+    if (lists) {
+        // contender lists of the upper-bound passes that have any (local tasks only; a rank that
+        // needs a list it does not hold re-runs that one task, see commit)
+        lists->assign(n, nullptr);
+        for (int k = 0; k < mine; k++) {
+            const int t = W > 1 ? r + k * W : k;
+            if (h->h_tasks[t].level < 0 && h->h_results[t].pad[1] > 0) {
+                auto cl = std::make_shared<CandList>();
+                CUDA_TRY(h, cudaMemcpyAsync(cl.get(), h->d_cands.p + k, sizeof(CandList), cudaMemcpyDeviceToHost, h->stream));
+                (*lists)[t] = cl;
+            }
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
     for (int t = 0; t < n; t++) {
         if (h->h_results[t].status == 3) return fail(h, GOICP_ERR_CAPACITY, "translation priority queue overflowed its device capacity");
         if (h->h_results[t].status == 4) return fail(h, GOICP_ERR_DEPTH, "translation search exceeded 21 levels");
         if (executed_evals) *executed_evals += h->h_results[t].evals;
     }
+    return GOICP_OK;
+}
+
+// Settles value and arg-min cube of one upper-bound pass in the reference's summation order
+// (strict_sum.cuh).  `list` are the contenders the search kernel reported for that task.
+int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, const CandList& list, float* value, float* node4)
+{
+    const size_t scratch = (size_t)h->nd * sizeof(float) <= (size_t)(h->max_smem_optin - 2048) ? 0 : (size_t)kMaxCand * h->nd;
+    CUDA_TRY(h, h->d_strict.reserve(256 + scratch));
+    CUDA_TRY(h, h->d_tasks.reserve(1)); CUDA_TRY(h, h->d_cands.reserve(1));
+    InnerTask* d_task = h->d_tasks.p + (h->d_tasks.n - 1);          // last slots are reserved for this
+    CandList* d_list = h->d_cands.p + (h->d_cands.n - 1);
+    CUDA_TRY(h, cudaMemcpyAsync(d_task, &task, sizeof task, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(d_list, &list, sizeof list, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_strict_resolve(c, d_task, d_list, h->d_strict.p, h->d_strict.p + 256, h->d_strict.p + 128, h->max_smem_optin - 2048, h->stream));
+    h->launches += 2; h->strict_resolves++;
+    float out5[5];
+    CUDA_TRY(h, cudaMemcpyAsync(out5, h->d_strict.p + 128, sizeof out5, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *value = out5[0]; node4[0] = out5[1]; node4[1] = out5[2]; node4[2] = out5[3]; node4[3] = out5[4];
     return GOICP_OK;
 }
 
@@ -364,7 +418,7 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     CUDA_TRY(h, cudaMemcpyAsync(h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, h->d_score_scratch.reserve((size_t)h->nd));
-    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->stream));
+    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->max_smem_optin - 2048, h->stream));
     h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -396,6 +450,9 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     for (int i = 0; i < 9; i++) out->R[i] = st.R[i];
     for (int i = 0; i < 3; i++) out->t[i] = st.t[i];
     out->err = st.err_new; out->iterations = st.iter;
+    if (getenv("GOICP_ICP_STATS"))
+        fprintf(stderr, "[icp] iters %d blocks %d cycles: nn %lld wait %lld sort %lld pass1 %lld pass2 %lld total %lld\n", st.iter, blocks,
+                st.dbg[0], st.dbg[1], st.dbg[2], st.dbg[3], st.dbg[4], st.dbg[5]);
     return GOICP_OK;
 }
 
@@ -433,7 +490,7 @@ void goicp_default_params(goicp_params* p)
     p->rot_cube[0] = p->rot_cube[1] = p->rot_cube[2] = (float)-kPi; p->rot_cube[3] = (float)(2 * kPi);
     p->trans_cube[0] = p->trans_cube[1] = p->trans_cube[2] = -0.5f; p->trans_cube[3] = 1.0f;
     p->icp_max_iter = 10000;
-    p->device = 0; p->spec_cubes = 0; p->dt_mode = GOICP_DT_REFERENCE;
+    p->device = 0; p->spec_cubes = 0; p->cluster_size = 0; p->dt_mode = GOICP_DT_REFERENCE;
     p->rank = 0; p->world_size = 1;
 }
 
@@ -453,7 +510,7 @@ int goicp_destroy(goicp_handle* h)
     if (h->cuda_ready) {
         cudaSetDevice(h->p.device);
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
-        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
+        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release();
         if (h->h_results) cudaFreeHost(h->h_results);
         if (h->h_tasks) cudaFreeHost(h->h_tasks);
@@ -524,7 +581,7 @@ int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_ou
     if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "dt_distance: no distance transform");
     if (n == 0) return GOICP_OK;
     DtView dt; dt.grid = h->d_dt.p; dt.S = h->dt_size; dt.S2 = h->dt_size * h->dt_size;
-    dt.xmin = h->dt_meta[0]; dt.ymin = h->dt_meta[1]; dt.zmin = h->dt_meta[2]; dt.scale = h->dt_meta[3];
+    dt.xmin = h->dt_meta[0]; dt.ymin = h->dt_meta[1]; dt.zmin = h->dt_meta[2]; dt.scale = h->dt_meta[3]; dt.inv_scale = 1.0 / h->dt_meta[3];
     CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
     CUDA_TRY(h, h->d_f32b.reserve(n));
     CUDA_TRY(h, h->d_i32.reserve((size_t)3 * n + 16));
@@ -604,9 +661,15 @@ int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* leve
         h->h_tasks[k].level = level[k]; h->h_tasks[k].opt_error = opt_error[k]; h->h_tasks[k].pad = 0;
     }
     goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;       // this entry point is single-GPU
-    rc = run_inner_batch(h, c, n, nullptr);
+    std::vector<std::shared_ptr<CandList>> lists;
+    rc = run_inner_batch(h, c, n, nullptr, &lists);
     h->xchg = saved;
     if (rc) return rc;
+    std::vector<InnerTask> tasks(h->h_tasks, h->h_tasks + n);
+    std::vector<InnerResult> results(h->h_results, h->h_results + n);
+    for (int k = 0; k < n; k++)
+        if (lists[k]) { rc = resolve_strict(h, c, tasks[k], *lists[k], &results[k].value, results[k].node); if (rc) return rc; }
+    std::memcpy(h->h_results, results.data(), sizeof(InnerResult) * n);
     for (int k = 0; k < n; k++) {
         out[k].value = h->h_results[k].value; std::memcpy(out[k].node, h->h_results[k].node, sizeof out[k].node);
         out[k].pops = h->h_results[k].pops; out[k].evals = h->h_results[k].evals; out[k].status = h->h_results[k].status;
@@ -770,11 +833,13 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 }
             }
         }
-        rcl = run_inner_batch(h, c, n, &res.bound_evals_executed); if (rcl) return rcl;
+        std::vector<std::shared_ptr<CandList>> lists;
+        rcl = run_inner_batch(h, c, n, &res.bound_evals_executed, &lists); if (rcl) return rcl;
         res.rounds++;
         for (int t = 0; t < n; t++) {
             ChildEval& ce = evs[slots[t].cube].ch[slots[t].child];
             (slots[t].pass == 0 ? ce.ub : ce.lb) = h->h_results[t];
+            if (slots[t].pass == 0) { ce.cands = lists[t]; ce.ub_opt_error = E; }
         }
         for (size_t ci = 0; ci < cubes.size(); ci++) { evs[ci].epoch = epoch; cache[key_of(cubes[ci])] = evs[ci]; }
         return GOICP_OK;
@@ -808,12 +873,29 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 RotNode nd; nd.w = w; nd.l = P.l + 1;
                 nd.a = P.a + (j & 1) * w; nd.b = P.b + (j >> 1 & 1) * w; nd.c = P.c + (j >> 2 & 1) * w;
                 float ub = ce.ub.value;
+                float ub_node[4] = {ce.ub.node[0], ce.ub.node[1], ce.ub.node[2], ce.ub.node[3]};
                 if (!(j == j0 && skip_ub)) {
                     res.trans_pops += ce.ub.pops; res.bound_evals += ce.ub.evals;
+                    if (ce.ub.pad[1] > 0) {
+                        // this pass may improve the optimum: settle value and arg-min cube in the
+                        // reference's summation order before deciding (strict_sum.cuh)
+                        InnerTask task; std::memcpy(task.R, ce.R, sizeof ce.R); task.level = -1; task.opt_error = ce.ub_opt_error; task.pad = 0;
+                        std::shared_ptr<CandList> cl = ce.cands;
+                        if (!cl) {      // evaluated on another rank: re-derive the contender list here (deterministic)
+                            h->h_tasks[0] = task;
+                            goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;
+                            std::vector<std::shared_ptr<CandList>> one;
+                            rc = run_inner_batch(h, c, 1, nullptr, &one);
+                            h->xchg = saved;
+                            if (rc) return rc;
+                            cl = one[0];
+                        }
+                        if (cl) { rc = resolve_strict(h, c, task, *cl, &ub, ub_node); if (rc) return rc; }
+                    }
                     if (ub < E) {                                                          // :495-544
                         E = ub;
                         std::memcpy(optR, ce.R, sizeof optR);
-                        optT[0] = ce.ub.node[0] + ce.ub.node[3] / 2; optT[1] = ce.ub.node[1] + ce.ub.node[3] / 2; optT[2] = ce.ub.node[2] + ce.ub.node[3] / 2;
+                        optT[0] = ub_node[0] + ub_node[3] / 2; optT[1] = ub_node[1] + ub_node[3] / 2; optT[2] = ub_node[2] + ub_node[3] / 2;
                         float R_icp[9], t_icp[3], error;
                         std::memcpy(R_icp, optR, sizeof optR); std::memcpy(t_icp, optT, sizeof optT);
                         rc = icp_then_dt(h, c, R_icp, t_icp, &error); if (rc) return rc;

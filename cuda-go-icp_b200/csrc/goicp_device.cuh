@@ -18,6 +18,7 @@ struct DtView {
     int S;
     int S2;                 // S*S
     double xmin, ymin, zmin, scale;
+    double inv_scale;       // 1/scale, used only by the search kernels' tree-sum path (see accumulate_point8)
 };
 
 // One axis of DT3D::Distance (jly_3ddt.cpp:983-1016): idx = int((q - min)*scale + 0.5) in
@@ -103,41 +104,54 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane)
 
 // ---- one data point against the 8 children of a translation cube -------------------------
 // P = rotated point (x,y,z) and its rotation-uncertainty radius gamma (0 in the upper-bound
-// pass).  t?[b] = translation of the children whose axis bit is b (jly_goicp.cpp:265-272);
-// gt = maxTransDis (:263).  acc[j] += d^2 (ub, :302-306), acc[8+j] += max(d-gt,0)^2 (lb, :308-315)
-// with d = max(DT(P+t_j) - gamma, 0) (:276-291).  The three per-axis voxel indices are shared
-// between children: 6 double-precision index computations serve 8 gathers.
+// pass).  tr[0..1]/[2..3]/[4..5] = x/y/z translation of the children whose axis bit is 0/1
+// (jly_goicp.cpp:265-272), tr[6] = maxTransDis (:263); tr may live in shared memory.
+// acc[j] += d^2 (ub, :302-306), acc[8+j] += max(d-gt,0)^2 (lb, :308-315) with
+// d = max(DT(P+t_j) - gamma, 0) (:276-291).  The three per-axis voxel indices are shared between
+// children: 6 double-precision index computations serve 8 gathers.  The in-grid case (all six
+// indices inside) is the fast path; anything else goes through the reference's clamp +
+// overshoot formula per child.
 __device__ __forceinline__ void accumulate_point8(const DtView& dt, float px, float py, float pz, float gamma,
-                                                  const float (&tx)[2], const float (&ty)[2], const float (&tz)[2],
-                                                  float gt, float (&acc)[16])
+                                                  const float* __restrict__ tr, float (&acc)[16])
 {
-    int ix[2], oy[2], oz[2];
-    float ax[2], ay[2], az[2];
+    // per axis and axis bit: clamped voxel index and squared overshoot (0 inside the grid);
+    // overshoot a = x (x<0) or x-S+1 (x>=S) == raw - clamped (jly_3ddt.cpp:991-1023)
+    int xi[2], yo[2], zo[2];
+    float ax2[2], ay2[2], az2[2];
+    const int Sm1 = dt.S - 1;
 #pragma unroll
     for (int b = 0; b < 2; b++) {
-        int i;
-        dt_axis(__fadd_rn(px, tx[b]), dt.xmin, dt.scale, dt.S, i, ax[b]); ix[b] = i;
-        dt_axis(__fadd_rn(py, ty[b]), dt.ymin, dt.scale, dt.S, i, ay[b]); oy[b] = i * dt.S;
-        dt_axis(__fadd_rn(pz, tz[b]), dt.zmin, dt.scale, dt.S, i, az[b]); oz[b] = i * dt.S2;
+        int i = dt_axis_raw(__fadd_rn(px, tr[b]), dt.xmin, dt.scale);
+        int cl = min(max(i, 0), Sm1); float a = (float)(i - cl);
+        xi[b] = cl; ax2[b] = __fmul_rn(a, a);
+        i = dt_axis_raw(__fadd_rn(py, tr[2 + b]), dt.ymin, dt.scale);
+        cl = min(max(i, 0), Sm1); a = (float)(i - cl);
+        yo[b] = cl * dt.S; ay2[b] = __fmul_rn(a, a);
+        i = dt_axis_raw(__fadd_rn(pz, tr[4 + b]), dt.zmin, dt.scale);
+        cl = min(max(i, 0), Sm1); a = (float)(i - cl);
+        zo[b] = cl * dt.S2; az2[b] = __fmul_rn(a, a);
     }
     float d[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++)
-        d[j] = __ldg(dt.grid + (oz[(j >> 2) & 1] + oy[(j >> 1) & 1] + ix[j & 1]));
-    const bool any_out = (ax[0] != 0.0f) | (ax[1] != 0.0f) | (ay[0] != 0.0f) | (ay[1] != 0.0f) | (az[0] != 0.0f) | (az[1] != 0.0f);
-    if (any_out) {
+    for (int j = 0; j < 8; j++) d[j] = __ldg(dt.grid + (zo[(j >> 2) & 1] + yo[(j >> 1) & 1] + xi[j & 1]));
+    if ((ax2[0] + ax2[1] + ay2[0] + ay2[1] + az2[0] + az2[1]) != 0.0f) {
+        // some child of this point leaves the grid: sqrt(a^2+b^2+c^2)/scale + clamped distance
+        // (jly_3ddt.cpp:1025).  The search path multiplies by 1/scale instead of dividing in double
+        // (a 1-ulp(double) difference before the final rounding to float, far below the float
+        // summation-order noise of this path); the strict paths divide exactly (dt_outside).
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            float a = ax[j & 1], b = ay[(j >> 1) & 1], c = az[(j >> 2) & 1];
-            if (a != 0.0f || b != 0.0f || c != 0.0f) d[j] = dt_outside(d[j], a, b, c, dt.scale);
+            const float s2 = __fadd_rn(__fadd_rn(ax2[j & 1], ay2[(j >> 1) & 1]), az2[(j >> 2) & 1]);
+            if (s2 != 0.0f) d[j] = __double2float_rn(__dadd_rn(__dmul_rn((double)__fsqrt_rn(s2), dt.inv_scale), (double)d[j]));
         }
     }
+    const float gt = tr[6];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         float m = __fsub_rn(d[j], gamma);
         m = m < 0.0f ? 0.0f : m;
         acc[j] = __fadd_rn(acc[j], __fmul_rn(m, m));
-        float e = __fsub_rn(m, gt);
+        const float e = __fsub_rn(m, gt);
         if (e > 0.0f) acc[8 + j] = __fadd_rn(acc[8 + j], __fmul_rn(e, e));
     }
 }

@@ -9,9 +9,11 @@ cudaError_t launch_dt_lookup(const DtView& dt, const float* d_q, int n, float* d
 cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float2* d_out, cudaStream_t s);
 cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
 cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
-cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, cudaStream_t s);
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, cudaStream_t s);
+cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, cudaStream_t s);
+cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
+                                  float* d_out5, int smem_limit, cudaStream_t s);
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, cudaStream_t s);
 
 // ---- icp_kernels.cu ---------------------------------------------------------------------
 // Flattened copy of the reference-ordered kd-tree (built on the host by kdtree_host.cpp).
@@ -35,6 +37,7 @@ struct IcpState {           // lives in device memory; written by block 0 of the
     float mu_m[3], mu_d[3];
     float err, err_new;
     int iter, converged;
+    long long dbg[6];       // cycles spent by CTA 0 in: NN, wait, sort, pass 1, pass 2 + SVD, total
 };
 struct IcpWork {            // per-iteration device scratch of the ICP kernel
     float* q;               // 3*nd transformed data points

@@ -39,7 +39,8 @@ struct InnerResult {
     uint32_t evals;      // bound evaluations of this call
     int32_t status;      // goicp_status
     uint32_t max_heap;
-    uint32_t pad[2];
+    uint32_t pad[2];     // [0] flags, [1] number of arg-min contenders (ub pass)
+    uint32_t kcycles;    // SM cycles / 1024 this task took
 };
 
 // Translation-BnB heap entry (16 B): lb, level, and the octant path from the root cube.
@@ -49,6 +50,14 @@ struct __align__(16) HeapEntry {
     float lb;
     uint32_t level;
     uint32_t path_lo, path_hi;
+};
+
+// Contenders for the arg-min of one upper-bound pass (see strict_sum.cuh), in evaluation order.
+constexpr int kMaxCand = 128;
+struct CandList {
+    int32_t n; uint32_t flags; float final_fast; float eps;
+    float4 node[kMaxCand];   // translation cube x,y,z,w
+    float ub[kMaxCand];      // its tree-sum upper bound
 };
 
 // A generic (rotation, translation cube) pair for goicp_eval_bounds.

@@ -379,7 +379,9 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
 
     for (int i = nd + gtid; i < npad; i += gsize) wk.keys[i] = ~0ull;
 
+    long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
+        long long c0 = clock64();
         float R[9], t[3];
 #pragma unroll
         for (int i = 0; i < 9; i++) R[i] = vst->R[i];
@@ -397,7 +399,9 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             wk.nn[i] = id; wk.d2[i] = d2;
             wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
         }
+        long long c1 = clock64(); c_nn += c1 - c0;
         grid.sync();
+        c0 = clock64(); c_wait += c0 - c1;
         if (blockIdx.x == 0) {
             // ---- sort by (distance, index)
             unsigned long long* keys = wk.keys;
@@ -410,6 +414,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 __syncthreads();
                 bitonic_sort_block(wk.keys, npad);
             }
+            c1 = clock64(); c_sort += c1 - c0; c0 = c1;
             // ---- reference-order accumulations.  Correspondences are gathered in sorted order in
             // chunks of kIcpChunk rows into shared memory (and kept in wk.stage for the second
             // pass); one lane per accumulator then adds them up strictly sequentially.
@@ -454,6 +459,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 }
             }
             __syncthreads();
+            c1 = clock64(); c_p1 += c1 - c0; c0 = c1;
             if (!vst->converged) {
                 float mud = 0.0f, mum = 0.0f; int a = 0, b = 0;
                 if (warp == 0 && lane < 9) { a = lane / 3; b = lane % 3; mud = vst->mu_d[a]; mum = vst->mu_m[b]; }
@@ -476,12 +482,14 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     if (lane == 0) icp_update(st, sh_H);
                 }
             }
+            c1 = clock64(); c_p2 += c1 - c0;
             if (threadIdx.x == 0) __threadfence();
         }
         grid.sync();
         if (vst->converged) break;
         if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = clock64() - c_begin; }
 }
 
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s)

@@ -64,6 +64,7 @@ typedef struct {
     int    icp_max_iter;     /* ICP3D::max_iter_def (10000, jly_icp3d.hpp:113) */
     int    device;           /* CUDA device ordinal */
     int    spec_cubes;       /* rotation cubes expanded speculatively per round (0 = auto) */
+    int    cluster_size;     /* CTAs (SMs) cooperating on one translation BnB via a thread-block cluster (0 = auto, max 16) */
     int    dt_mode;          /* goicp_dt_mode used by goicp_build_dt */
     /* multi-GPU sharding of the rotation frontier (all ranks hold identical inputs) */
     int    rank, world_size;
