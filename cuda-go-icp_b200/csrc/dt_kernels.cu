@@ -72,7 +72,6 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
 // "static" wins against the neighbour's own value), then the few heads are filtered in scan
 // order so that a head inside an earlier run is ignored -- the sequential semantics exactly.
 struct Cand { int n2; Vox vec; };
-__device__ unsigned long long* g_dt_stats = nullptr;   // optional instrumentation (GOICP_DT_STATS=1)
 
 __device__ __forceinline__ Vox vox_unset_value() { Vox u; u.v = u.h = u.d = 32767; u.pad = 0; return u; }
 
@@ -95,20 +94,35 @@ enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 struct RowSmem {
     Vox* xs[3];          // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
     Vox* prev;           // final previous row of the current slice in this pass, padded
-    int* T; int* own_n; short* own_d; Vox* own_v;
+    int2* tn[2];         // per scan position k: {T_k, own squared norm}; double-buffered across the two scans of a row
+    Vox* own_v[2];       // own vector
     short* run_start; short* run_end; unsigned char* accept;
     unsigned* wmask;
 };
 
+#ifdef GOICP_DT_INSTRUMENT
+__device__ unsigned long long g_dt_stats_buf[8];
+#define DT_STAT(i, v) atomicAdd(&g_dt_stats_buf[i], (unsigned long long)(v))
+#else
+#define DT_STAT(i, v) ((void)0)
+#endif
+
+// One row scan.  `buf` selects the record buffer (0 for the first scan of a row, 1 for the second)
+// so that the second scan may start writing its records while slow threads still read the first's.
+// If prev_out != nullptr the scan is the last of its row: the result is also stored as the row's
+// entry of sh.prev -- optimistically BEFORE the barrier that decides whether any run exists, so the
+// common run-free row needs no extra barrier; rows with runs rewrite it afterwards.
 template <int KIND>
-__device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox self)
+__device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox self, int buf, bool last_of_row, bool& had_runs)
 {
     const int z = threadIdx.x;
     const bool active = z < S;
     constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;     // +1: recurrence reads z-1
     const int k = dir > 0 ? z : S - 1 - z;                                      // position in scan order
+    int2* tn = sh.tn[buf]; Vox* own_v = sh.own_v[buf];
     Cand P, Q;
     P.n2 = kInf; Q.n2 = kInf; P.vec = vox_unset_value(); Q.vec = P.vec;
+    Vox out = P.vec; int Tk = kInf;
     if (active) {
         const int zp = z + 1;                                                    // padded index
         if (KIND == F1 || KIND == B1) {
@@ -133,11 +147,10 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
             consider(Q, self, 0, 0, 0);
         }
         const bool p_first = P.n2 <= Q.n2;
-        sh.own_n[k] = p_first ? P.n2 : Q.n2;
-        sh.own_d[k] = p_first ? P.vec.d : Q.vec.d;
-        sh.own_v[k] = p_first ? P.vec : Q.vec;
-        sh.T[k] = min(P.n2, Q.n2 + 1);               // recurrence wins iff nc < nP and nc <= nQ
-        sh.run_start[k] = -1;
+        out = p_first ? P.vec : Q.vec;
+        Tk = min(P.n2, Q.n2 + 1);                    // recurrence wins iff nc < nP and nc <= nQ
+        tn[k] = make_int2(Tk, p_first ? P.n2 : Q.n2);
+        own_v[k] = out;
     }
     __syncthreads();
     // A run can only begin with a win against the neighbour's OWN value.  A "win" whose vector is
@@ -145,51 +158,51 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
     // head; likewise a run that arrives at a voxel carrying exactly the vector the voxel would
     // hold anyway simply ends there.  Most recurrence wins are such ties (the chain entry precedes
     // `self` in four of the six masks), so real heads are few and runs short.
-    Vox out = (P.n2 <= Q.n2) ? P.vec : Q.vec;
     int win = 0, nc = 0, d0 = 0; short v0 = 0, h0 = 0;
     if (active && k >= 1) {
-        const int n0 = sh.own_n[k - 1];
+        const int n0 = tn[k - 1].y;
         if (n0 < kInf) {
-            const Vox o = sh.own_v[k - 1];
+            const Vox o = own_v[k - 1];
             d0 = o.d; v0 = o.v; h0 = o.h; nc = n0 + 2 * d0 + 1;
-            win = (nc < sh.T[k]) && !(o.v == out.v && o.h == out.h && d0 + 1 == out.d);
+            win = (nc < Tk) && !(o.v == out.v && o.h == out.h && d0 + 1 == out.d);
         }
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, win);
     if ((threadIdx.x & 31) == 0) sh.wmask[threadIdx.x >> 5] = ballot;
+    if (last_of_row && active) sh.prev[z + 1] = out;         // optimistic: valid unless a run covers z
     const int any = __syncthreads_or(win);
-    if (g_dt_stats && threadIdx.x == 0) { atomicAdd(&g_dt_stats[0], 1ull); if (any) atomicAdd(&g_dt_stats[1], 1ull); }
+    DT_STAT(0, threadIdx.x == 0); DT_STAT(1, threadIdx.x == 0 && any);
+    had_runs = any != 0;
     if (any) {
+        if (active) sh.run_start[k] = -1;
         if (win) {                                   // extent of the run that starts at k-1
             int n = nc, d = d0 + 1, pos = k + 1;
             while (pos < S) {
                 n += 2 * d + 1; d++;
-                if (!(n < sh.T[pos])) break;
-                if (n == sh.own_n[pos]) { const Vox o = sh.own_v[pos]; if (o.v == v0 && o.h == h0 && o.d == d) break; }
+                const int2 t2 = tn[pos];
+                if (!(n < t2.x)) break;
+                if (n == t2.y) { const Vox o = own_v[pos]; if (o.v == v0 && o.h == h0 && o.d == d) break; }
                 pos++;
             }
             sh.run_end[k] = (short)pos;
-            if (g_dt_stats) { atomicAdd(&g_dt_stats[2], 1ull); atomicAdd(&g_dt_stats[3], (unsigned long long)(pos - k)); atomicMax(&g_dt_stats[4], (unsigned long long)(pos - k)); }
+            DT_STAT(2, 1); DT_STAT(3, pos - k);
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            // heads in scan order; a head whose start lies inside an accepted run is void.
-            // (lane 0 walks the ballots: the number of heads per row is small)
-            if (threadIdx.x == 0) {
-                int last_end = -1;
-                const int nw = (S + 31) / 32;
-                if (dir > 0) {
-                    for (int w = 0; w < nw; w++) {
-                        unsigned m = sh.wmask[w];
-                        while (m) { const int b = __ffs(m) - 1; m &= m - 1; const int kk = w * 32 + b;      // kk == z
-                            const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
-                    }
-                } else {
-                    for (int w = nw - 1; w >= 0; w--) {
-                        unsigned m = sh.wmask[w];
-                        while (m) { const int b = 31 - __clz(m); m &= ~(1u << b); const int kk = S - 1 - (w * 32 + b);   // thread z -> k
-                            const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
-                    }
+        if (threadIdx.x == 0) {
+            // heads in scan order; a head whose start lies inside an accepted run is void
+            int last_end = -1;
+            const int nw = (S + 31) / 32;
+            if (dir > 0) {
+                for (int w = 0; w < nw; w++) {
+                    unsigned m = sh.wmask[w];
+                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; const int kk = w * 32 + b;      // kk == z
+                        const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
+                }
+            } else {
+                for (int w = nw - 1; w >= 0; w--) {
+                    unsigned m = sh.wmask[w];
+                    while (m) { const int b = 31 - __clz(m); m &= ~(1u << b); const int kk = S - 1 - (w * 32 + b);   // thread z -> k
+                        const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
                 }
             }
         }
@@ -198,7 +211,10 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
         __syncthreads();
         if (active) {
             const int rs = sh.run_start[k];
-            if (rs >= 0) { out = sh.own_v[rs]; out.d = (short)(out.d + (k - rs)); }
+            if (rs >= 0) {
+                out = own_v[rs]; out.d = (short)(out.d + (k - rs));
+                if (last_of_row) sh.prev[z + 1] = out;
+            }
         }
     }
     return out;
@@ -224,20 +240,19 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem
     __syncthreads();
     for (int i = 0, y = y0; i < S; i++, y += ydir) {
         const Vox self = self_next;
-        const Vox xs_row = xs_next;                         // adjacent-slice row y + 2*ydir ... consumed after this row
+        const Vox xs_row = xs_next;                         // adjacent-slice row y + 2*ydir: needed from the next row on
         self_next = gload(x, y + ydir);                     // prefetch: own column only
         xs_next = use_xs ? gload(xs, y + 3 * ydir) : unset;
-        Vox v = row_scan<K1>(sh, S, y, self);
-        __syncthreads();                                    // scan records are reused by the second scan
-        v = row_scan<K2>(sh, S, y, v);
-        if (active) {
-            G[((size_t)x * S + y) * S + z] = v;
-            sh.prev[z + 1] = v;
-            // the adjacent-slice row that falls out of the 3-row window is replaced by the incoming one
-            if (K1 == F1 || K1 == B1) sh.xs[(y + 2 * ydir + 3 + 3) % 3][z + 1] = xs_row;
-        }
-        __syncthreads();
+        bool runs1, runs2;
+        Vox v = row_scan<K1>(sh, S, y, self, 0, false, runs1);
+        // the adjacent-slice row that leaves the 3-row window is replaced by the incoming one; nobody
+        // reads that slot again in this row, and the next row's reads come after >= 2 barriers
+        if ((K1 == F1 || K1 == B1) && active) sh.xs[(y + 2 * ydir + 3 + 3) % 3][z + 1] = xs_row;
+        v = row_scan<K2>(sh, S, y, v, 1, true, runs2);
+        if (active) G[((size_t)x * S + y) * S + z] = v;
+        if (runs2) __syncthreads();                         // prev[] was patched after the deciding barrier
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kMaxS)
@@ -250,11 +265,9 @@ dt_propagate_kernel(Vox* G, int S)
         const size_t row = (size_t)(S + 2) * sizeof(Vox);
         for (int r = 0; r < 3; r++) { sh.xs[r] = reinterpret_cast<Vox*>(p); p += row; }
         sh.prev = reinterpret_cast<Vox*>(p); p += row;
-        sh.own_v = reinterpret_cast<Vox*>(p); p += (size_t)S * sizeof(Vox);
-        sh.T = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int);
-        sh.own_n = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int);
+        for (int b = 0; b < 2; b++) { sh.own_v[b] = reinterpret_cast<Vox*>(p); p += (size_t)S * sizeof(Vox); }
+        for (int b = 0; b < 2; b++) { sh.tn[b] = reinterpret_cast<int2*>(p); p += (size_t)S * sizeof(int2); }
         sh.wmask = reinterpret_cast<unsigned*>(p); p += 32 * sizeof(unsigned);
-        sh.own_d = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
         sh.run_start = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
         sh.run_end = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
         sh.accept = p;
@@ -278,8 +291,8 @@ dt_propagate_kernel(Vox* G, int S)
 
 static size_t dt_propagate_smem(int S)
 {
-    return 4 * (size_t)(S + 2) * sizeof(Vox) + (size_t)S * sizeof(Vox) + 2 * (size_t)S * sizeof(int) + 32 * sizeof(unsigned)
-         + 3 * (size_t)(S + 2) * sizeof(short) + (size_t)S + 64;
+    return 4 * (size_t)(S + 2) * sizeof(Vox) + 2 * (size_t)S * sizeof(Vox) + 2 * (size_t)S * sizeof(int2) + 32 * sizeof(unsigned)
+         + 2 * (size_t)(S + 2) * sizeof(short) + (size_t)S + 64;
 }
 
 // distance = float( double(float(sqrt(double(n2)))) / scale ), clamped at 0 (jly_3ddt.cpp:970-978);
@@ -389,23 +402,16 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         const int threads = ((S + 31) / 32) * 32;
         const size_t smem = dt_propagate_smem(S);
         DT_TRY(cudaFuncSetAttribute(dt_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned long long* d_stats = nullptr;
-        if (getenv("GOICP_DT_STATS")) {
-            DT_TRY(cudaMalloc((void**)&d_stats, 8 * sizeof(unsigned long long)));
-            DT_TRY(cudaMemsetAsync(d_stats, 0, 8 * sizeof(unsigned long long), stream));
-            DT_TRY(cudaMemcpyToSymbolAsync(g_dt_stats, &d_stats, sizeof(d_stats), 0, cudaMemcpyHostToDevice, stream));
-        }
         dt_propagate_kernel<<<1, threads, smem, stream>>>(G, S);
-        if (d_stats) {
-            unsigned long long hs[8];
-            DT_TRY(cudaMemcpyAsync(hs, d_stats, sizeof hs, cudaMemcpyDeviceToHost, stream));
-            DT_TRY(cudaStreamSynchronize(stream));
-            fprintf(stderr, "[dt stats] row scans %llu, with runs %llu, run heads %llu, total run length %llu, max run %llu\n", hs[0], hs[1], hs[2], hs[3], hs[4]);
-            unsigned long long* null_ptr = nullptr;
-            DT_TRY(cudaMemcpyToSymbolAsync(g_dt_stats, &null_ptr, sizeof(null_ptr), 0, cudaMemcpyHostToDevice, stream));
-            cudaFree(d_stats);
-        }
         DT_TRY(cudaGetLastError());
+#ifdef GOICP_DT_INSTRUMENT
+        {
+            unsigned long long hs[8];
+            DT_TRY(cudaStreamSynchronize(stream));
+            DT_TRY(cudaMemcpyFromSymbol(hs, g_dt_stats_buf, sizeof hs));
+            fprintf(stderr, "[dt stats] row scans %llu, with runs %llu, run heads %llu, total run length %llu\n", hs[0], hs[1], hs[2], hs[3]);
+        }
+#endif
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);
         dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, meta[3], d_out);
         DT_TRY(cudaGetLastError());

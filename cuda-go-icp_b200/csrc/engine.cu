@@ -216,8 +216,6 @@ int ensure_kdtree(goicp_handle* h)
     CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    h->icp_blocks = icp_max_grid_blocks(h->p.device);
-    if (h->icp_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     CUDA_TRY(h, h->d_icp_state.reserve(1));
     h->kd_ready = true;
     return GOICP_OK;
@@ -441,8 +439,12 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     st.err = -1.0f;
     const double t_begin = now_s();
     CUDA_TRY(h, cudaMemcpyAsync(h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
-    const int blocks = std::max(1, std::min(h->icp_blocks, (h->nd + icp_threads() - 1) / icp_threads()));
-    CUDA_TRY(h, launch_icp(kd_view(h), h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->stream));
+    const int n_nodes = (int)h->kd_host.nodes.size();
+    const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin);
+    if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
+    // queries are interleaved over the CTAs: ~128 per CTA keeps every SM's search short
+    const int blocks = std::max(1, std::min(max_blocks, (h->nd + 127) / 128));
+    CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->max_smem_optin, h->stream));
     h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));

@@ -48,9 +48,9 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
 };
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
-cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
-                       int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s);
+cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
+                       int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s);
 int icp_threads();
-int icp_max_grid_blocks(int device);
+int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin);
 
 } // namespace goicp

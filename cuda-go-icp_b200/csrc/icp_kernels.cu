@@ -25,7 +25,7 @@ struct KdFrame { int32_t other; float m2; int32_t idx; float cut; float dst; int
 
 __device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
 
-__device__ int kd_nearest(const KdView& kd, float qx, float qy, float qz, float& d2_out)
+__device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, float qx, float qy, float qz, float& d2_out)
 {
     float worst = 3.402823466e+38f;     // KNNResultSet::init (nanoflann_goicp.hpp:79)
     int best = 0;
@@ -48,11 +48,16 @@ __device__ int kd_nearest(const KdView& kd, float qx, float qy, float qz, float&
     for (;;) {
         // descend along the preferred children
         for (;;) {
-            const KdNode nd = kd.nodes[cur];
+            KdNode nd;
+            {
+                const uint4 a = reinterpret_cast<const uint4*>(nodes + cur)[0], b = reinterpret_cast<const uint4*>(nodes + cur)[1];
+                nd.child1 = (int)a.x; nd.child2 = (int)a.y; nd.left = (int)a.z; nd.right = (int)a.w;
+                nd.divfeat = (int)b.x; nd.divlow = __uint_as_float(b.y); nd.divhigh = __uint_as_float(b.z); nd.pad = 0;
+            }
             if (nd.child1 < 0 && nd.child2 < 0) {
                 const float worst_at_entry = worst;          // cached once per leaf (:1143)
                 for (int i = nd.left; i < nd.right; i++) {
-                    const float4 p = __ldg(kd.pts_leaf + i);
+                    const float4 p = leaf[i];
                     const float d0 = qx - p.x, d1 = qy - p.y, d2 = qz - p.z;
                     const float dist = d0 * d0 + d1 * d1 + d2 * d2;     // kdtree_distance (jly_icp3d.hpp:48-54)
                     if (dist < worst_at_entry && worst > dist) { worst = dist; best = __float_as_int(p.w); }
@@ -100,7 +105,7 @@ __global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float d;
-    idx[i] = kd_nearest(kd, q[3 * i], q[3 * i + 1], q[3 * i + 2], d);
+    idx[i] = kd_nearest(kd, kd.nodes, kd.pts_leaf, q[3 * i], q[3 * i + 1], q[3 * i + 2], d);
     d2[i] = d;
 }
 
@@ -344,40 +349,56 @@ __device__ void icp_update(IcpState* st, const float* H)
 // makes the final pose agree to 1e-4: ICP stops on a loose relative criterion far from its fixed
 // point, so its end point depends on the exact path.
 // ------------------------------------------------------------------------------------------
-constexpr int kSortSmem = 4096;
 constexpr int kIcpChunk = 384;
 
 __device__ void bitonic_sort_block(unsigned long long* a, int n_pow2)
 {
+    const int half = n_pow2 >> 1;
     for (int k = 2; k <= n_pow2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long x = a[i], y = a[ixj];
-                    const bool up = (i & k) == 0;
-                    if (up ? (x > y) : (x < y)) { a[i] = y; a[ixj] = x; }
-                }
+            for (int p = threadIdx.x; p < half; p += blockDim.x) {          // one compare-exchange per pair
+                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+                const int ixj = i + j;
+                const unsigned long long x = a[i], y = a[ixj];
+                const bool up = (i & k) == 0;
+                if (up ? (x > y) : (x < y)) { a[i] = y; a[ixj] = x; }
             }
             __syncthreads();
         }
 }
 
+// dynamic shared memory plan of the ICP kernel (decided on the host)
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int sort_bytes; int stage_bytes; };
+
 __global__ void __launch_bounds__(kIcpThreads)
 icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
-           int max_iter, float err_diff, int num)
+           int max_iter, float err_diff, int num, IcpSmemPlan plan)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned long long skeys[kSortSmem];
+    extern __shared__ __align__(16) unsigned char icp_smem[];
     __shared__ float sh_H[9];
     __shared__ float sh_acc[8];
     __shared__ __align__(16) float chunk[kIcpChunk * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
     int npad = 1; while (npad < nd) npad <<= 1;
     const volatile IcpState* vst = st;
 
-    for (int i = nd + gtid; i < npad; i += gsize) wk.keys[i] = ~0ull;
+    // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [sort keys] [staged rows]
+    const KdNode* nodes = kd.nodes; const float4* leaf = kd.pts_leaf;
+    unsigned char* sp = icp_smem;
+    if (plan.tree_bytes) {
+        KdNode* sn = reinterpret_cast<KdNode*>(sp);
+        float4* sl = reinterpret_cast<float4*>(sp + (size_t)plan.tree_nodes * sizeof(KdNode));
+        for (int i = threadIdx.x; i < plan.tree_nodes * 2; i += blockDim.x) reinterpret_cast<uint4*>(sn)[i] = reinterpret_cast<const uint4*>(kd.nodes)[i];
+        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
+        nodes = sn; leaf = sl; sp += plan.tree_bytes;
+    }
+    unsigned long long* skeys = plan.sort_bytes ? reinterpret_cast<unsigned long long*>(sp) : nullptr;
+    sp += plan.sort_bytes;
+    float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
+    __syncthreads();
+
+    for (int i = nd + blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += gridDim.x * blockDim.x) wk.keys[i] = ~0ull;
 
     long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
@@ -387,14 +408,15 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         for (int i = 0; i < 9; i++) R[i] = vst->R[i];
 #pragma unroll
         for (int i = 0; i < 3; i++) t[i] = vst->t[i];
-        for (int i = gtid; i < nd; i += gsize) {
+        // queries interleaved over CTAs so that every SM of the grid searches
+        for (int i = threadIdx.x * gridDim.x + blockIdx.x; i < nd; i += gridDim.x * blockDim.x) {
             const float4 p = __ldg(data + i);
             // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
             const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
             const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
             const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
             float d2;
-            const int id = kd_nearest(kd, qx, qy, qz, d2);
+            const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
             wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
             wk.nn[i] = id; wk.d2[i] = d2;
             wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
@@ -405,7 +427,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         if (blockIdx.x == 0) {
             // ---- sort by (distance, index)
             unsigned long long* keys = wk.keys;
-            if (npad <= kSortSmem) {
+            if (skeys) {
                 for (int i = threadIdx.x; i < npad; i += blockDim.x) skeys[i] = __ldcg(wk.keys + i);
                 __syncthreads();
                 bitonic_sort_block(skeys, npad);
@@ -415,24 +437,27 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 bitonic_sort_block(wk.keys, npad);
             }
             c1 = clock64(); c_sort += c1 - c0; c0 = c1;
-            // ---- reference-order accumulations.  Correspondences are gathered in sorted order in
-            // chunks of kIcpChunk rows into shared memory (and kept in wk.stage for the second
-            // pass); one lane per accumulator then adds them up strictly sequentially.
+            // ---- reference-order accumulations: correspondences (model point, query, d^2) are laid
+            // out in sorted order -- all of them in shared memory when they fit, else in chunks of
+            // kIcpChunk rows (kept in wk.stage for the second pass); one lane per accumulator then
+            // adds them up strictly sequentially.
             float acc = 0.0f;
             if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
-            for (int base = 0; base < num; base += kIcpChunk) {
-                const int cnt = min(kIcpChunk, num - base);
+            const int step = sstage ? num : kIcpChunk;
+            for (int base = 0; base < num; base += step) {
+                const int cnt = min(step, num - base);
+                float* rows = sstage ? sstage : chunk;
                 for (int rr = threadIdx.x; rr < cnt; rr += blockDim.x) {
                     const int i = (int)(keys[base + rr] & 0xffffffffu);
                     const int id = __ldcg(wk.nn + i);
                     float4 lo = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), __ldcg(wk.q + 3 * i));
                     float4 hi = make_float4(__ldcg(wk.q + 3 * i + 1), __ldcg(wk.q + 3 * i + 2), __ldcg(wk.d2 + i), 0.0f);
-                    reinterpret_cast<float4*>(chunk)[2 * rr] = lo; reinterpret_cast<float4*>(chunk)[2 * rr + 1] = hi;
-                    reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi;
+                    reinterpret_cast<float4*>(rows)[2 * rr] = lo; reinterpret_cast<float4*>(rows)[2 * rr + 1] = hi;
+                    if (!sstage) { reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi; }
                 }
                 __syncthreads();
                 if (warp == 0 && lane < 7) {
-                    const float* sg = chunk + lane;
+                    const float* sg = rows + lane;
                     if (lane < 6) {
 #pragma unroll 8
                         for (int rr = 0; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
@@ -464,17 +489,20 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 float mud = 0.0f, mum = 0.0f; int a = 0, b = 0;
                 if (warp == 0 && lane < 9) { a = lane / 3; b = lane % 3; mud = vst->mu_d[a]; mum = vst->mu_m[b]; }
                 acc = 0.0f;
-                for (int base = 0; base < num; base += kIcpChunk) {
-                    const int cnt = min(kIcpChunk, num - base);
-                    for (int v = threadIdx.x; v < 2 * cnt; v += blockDim.x)
-                        reinterpret_cast<float4*>(chunk)[v] = reinterpret_cast<const float4*>(wk.stage)[2 * (size_t)base + v];
-                    __syncthreads();
+                for (int base = 0; base < num; base += step) {
+                    const int cnt = min(step, num - base);
+                    const float* rows = sstage ? sstage : chunk;
+                    if (!sstage) {
+                        for (int v = threadIdx.x; v < 2 * cnt; v += blockDim.x)
+                            reinterpret_cast<float4*>(chunk)[v] = reinterpret_cast<const float4*>(wk.stage)[2 * (size_t)base + v];
+                        __syncthreads();
+                    }
                     if (warp == 0 && lane < 9) {
 #pragma unroll 8
                         for (int rr = 0; rr < cnt; rr++)
-                            acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(chunk[8 * rr + 3 + a], mud), __fsub_rn(chunk[8 * rr + b], mum)));
+                            acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(rows[8 * rr + 3 + a], mud), __fsub_rn(rows[8 * rr + b], mum)));
                     }
-                    __syncthreads();
+                    if (!sstage) __syncthreads();
                 }
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;
@@ -498,21 +526,45 @@ cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx,
     nn_kernel<<<(n + 127) / 128, 128, 0, s>>>(kd, d_q, n, d_idx, d_d2);
     return cudaGetLastError();
 }
-int icp_max_grid_blocks(int device)
+static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int smem_limit)
 {
+    IcpSmemPlan p = {0, 0, 0, 0};
+    int left = smem_limit;
+    size_t npad = 1; while (npad < (size_t)nd) npad <<= 1;
+    const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
+    const size_t sort = npad * sizeof(unsigned long long);
+    const size_t stage = (size_t)num * 8 * sizeof(float);
+    if (sort <= (size_t)left) { p.sort_bytes = (int)sort; left -= (int)sort; }
+    if (stage <= (size_t)left) { p.stage_bytes = (int)stage; left -= (int)stage; }
+    if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
+    return p;
+}
+int icp_threads() { return kIcpThreads; }
+int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin)
+{
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, icp_kernel) != cudaSuccess) return 0;
+    const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
+    cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.sort_bytes + p.stage_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
-int icp_threads() { return kIcpThreads; }
-cudaError_t launch_icp(const KdView& kd, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
-                       int max_iter, float err_diff, int num_inliers, int grid_blocks, cudaStream_t s)
+cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
+                       int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s)
 {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, icp_kernel);
+    if (e != cudaSuccess) return e;
+    const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
+    IcpSmemPlan plan = icp_plan(kd, n_nodes, nd, num_inliers, limit);
     KdView kdv = kd; IcpWork wk = work;
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
-                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers};
-    return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args, 0, s);
+                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&plan};
+    return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args,
+                                       (size_t)plan.tree_bytes + plan.sort_bytes + plan.stage_bytes, s);
 }
 
 } // namespace goicp
