@@ -71,16 +71,23 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
 // Runs are found in parallel (one thread per possible run head, first wins are exactly the
 // "static" wins against the neighbour's own value), then the few heads are filtered in scan
 // order so that a head inside an earlier run is ignored -- the sequential semantics exactly.
-struct Cand { int n2; Vox vec; };
+// Working representation on chip: 32-bit components plus the squared norm, 16 bytes per voxel
+// (one LDS.128), so that a candidate costs a handful of integer instructions:
+//   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1}.
+// Global memory keeps the compact 8-byte (short) form.
+struct __align__(16) V4 { int v, h, d, n; };
 
-__device__ __forceinline__ Vox vox_unset_value() { Vox u; u.v = u.h = u.d = 32767; u.pad = 0; return u; }
+__device__ __forceinline__ V4 v4_unset() { V4 u; u.v = u.h = u.d = 32767; u.n = kInf; return u; }
+__device__ __forceinline__ V4 v4_from(const Vox& a) { V4 r; r.v = a.v; r.h = a.h; r.d = a.d; r.n = vox_unset(a) ? kInf : vox_norm2(a); return r; }
+__device__ __forceinline__ Vox v4_to(const V4& a) { Vox r; r.v = (short)a.v; r.h = (short)a.h; r.d = (short)a.d; r.pad = 0; return r; }
 
-__device__ __forceinline__ void consider(Cand& best, Vox s, int iv, int ih, int id)
+// candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order
+template <int IV, int IH, int ID>
+__device__ __forceinline__ void consider(V4& best, const V4 s)
 {
-    if (vox_unset(s)) return;                       // scores ~56755 > 32767 in the reference: never chosen
-    s.v = (short)(s.v + iv); s.h = (short)(s.h + ih); s.d = (short)(s.d + id);
-    const int n2 = vox_norm2(s);
-    if (n2 < best.n2) { best.n2 = n2; best.vec = s; }
+    if (s.n >= kInf) return;                        // unset source: scores ~56755 > 32767 in the reference, never chosen
+    const int n = s.n + 2 * (IV * s.v + IH * s.h + ID * s.d) + (IV + IH + ID);
+    if (n < best.n) { best.n = n; best.v = s.v + IV; best.h = s.h + IH; best.d = s.d + ID; }
 }
 
 // Row-scan kinds (mask functions of jly_3ddt.cpp and where the running-scan entry sits in the
@@ -92,10 +99,10 @@ __device__ __forceinline__ void consider(Cand& best, Vox s, int iv, int ih, int 
 enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 
 struct RowSmem {
-    Vox* xs[3];          // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
-    Vox* prev;           // final previous row of the current slice in this pass, padded
-    int2* tn[2];         // per scan position k: {T_k, own squared norm}; double-buffered across the two scans of a row
-    Vox* own_v[2];       // own vector
+    V4* xs[3];           // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
+    V4* prev;            // final previous row of the current slice in this pass, padded
+    V4* own[2];          // per scan position k: the voxel's own (recurrence-free) result; double-buffered across the two scans of a row
+    int* T[2];           // the squared norm the recurrence must beat at k
     short* run_start; short* run_end; unsigned char* accept;
     unsigned* wmask;
 };
@@ -109,48 +116,42 @@ __device__ unsigned long long g_dt_stats_buf[8];
 
 // One row scan.  `buf` selects the record buffer (0 for the first scan of a row, 1 for the second)
 // so that the second scan may start writing its records while slow threads still read the first's.
-// If prev_out != nullptr the scan is the last of its row: the result is also stored as the row's
-// entry of sh.prev -- optimistically BEFORE the barrier that decides whether any run exists, so the
-// common run-free row needs no extra barrier; rows with runs rewrite it afterwards.
+// If last_of_row the result is also stored as the row's entry of sh.prev -- optimistically BEFORE
+// the barrier that decides whether any run exists, so the common run-free row needs no extra
+// barrier; rows with runs rewrite it afterwards.
 template <int KIND>
-__device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox self, int buf, bool last_of_row, bool& had_runs)
+__device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4 self, int buf, bool last_of_row, bool& had_runs)
 {
     const int z = threadIdx.x;
     const bool active = z < S;
     constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;     // +1: recurrence reads z-1
     const int k = dir > 0 ? z : S - 1 - z;                                      // position in scan order
-    int2* tn = sh.tn[buf]; Vox* own_v = sh.own_v[buf];
-    Cand P, Q;
-    P.n2 = kInf; Q.n2 = kInf; P.vec = vox_unset_value(); Q.vec = P.vec;
-    Vox out = P.vec; int Tk = kInf;
+    V4* own = sh.own[buf]; int* T = sh.T[buf];
+    V4 P = v4_unset(), Q = v4_unset();
+    V4 out = P; int Tk = kInf;
     if (active) {
         const int zp = z + 1;                                                    // padded index
         if (KIND == F1 || KIND == B1) {
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const Vox* row = sh.xs[(y + dy + 3) % 3];
-                consider(P, row[zp - 1], 1, dy != 0, 1);
-                consider(P, row[zp], 1, dy != 0, 0);
-                consider(P, row[zp + 1], 1, dy != 0, 1);
-            }
+            const V4* r0 = sh.xs[(y - 1 + 3) % 3]; const V4* r1 = sh.xs[(y + 3) % 3]; const V4* r2 = sh.xs[(y + 1 + 3) % 3];
+            consider<1, 1, 1>(P, r0[zp - 1]); consider<1, 1, 0>(P, r0[zp]); consider<1, 1, 1>(P, r0[zp + 1]);
+            consider<1, 0, 1>(P, r1[zp - 1]); consider<1, 0, 0>(P, r1[zp]); consider<1, 0, 1>(P, r1[zp + 1]);
+            consider<1, 1, 1>(P, r2[zp - 1]); consider<1, 1, 0>(P, r2[zp]); consider<1, 1, 1>(P, r2[zp + 1]);
         }
         if (KIND == F1 || KIND == B3) {              // previous row y-1, then self; recurrence comes last
-            consider(P, sh.prev[zp - 1], 0, 1, 1);
-            consider(P, sh.prev[zp], 0, 1, 0);
-            consider(P, sh.prev[zp + 1], 0, 1, 1);
-            consider(P, self, 0, 0, 0);
+            consider<0, 1, 1>(P, sh.prev[zp - 1]);
+            consider<0, 1, 0>(P, sh.prev[zp]);
+            consider<0, 1, 1>(P, sh.prev[zp + 1]);
+            consider<0, 0, 0>(P, self);
         } else if (KIND == F3 || KIND == B1) {       // recurrence first, then (z,y+1), self, (z-1,y+1)
-            consider(Q, sh.prev[zp], 0, 1, 0);
-            consider(Q, self, 0, 0, 0);
-            consider(Q, sh.prev[zp - 1], 0, 1, 1);
+            consider<0, 1, 0>(Q, sh.prev[zp]);
+            consider<0, 0, 0>(Q, self);
+            consider<0, 1, 1>(Q, sh.prev[zp - 1]);
         } else {                                     // pure chains: recurrence first, then self
-            consider(Q, self, 0, 0, 0);
+            consider<0, 0, 0>(Q, self);
         }
-        const bool p_first = P.n2 <= Q.n2;
-        out = p_first ? P.vec : Q.vec;
-        Tk = min(P.n2, Q.n2 + 1);                    // recurrence wins iff nc < nP and nc <= nQ
-        tn[k] = make_int2(Tk, p_first ? P.n2 : Q.n2);
-        own_v[k] = out;
+        out = P.n <= Q.n ? P : Q;
+        Tk = min(P.n, Q.n + 1);                      // recurrence wins iff nc < nP and nc <= nQ
+        own[k] = out; T[k] = Tk;
     }
     __syncthreads();
     // A run can only begin with a win against the neighbour's OWN value.  A "win" whose vector is
@@ -158,13 +159,13 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
     // head; likewise a run that arrives at a voxel carrying exactly the vector the voxel would
     // hold anyway simply ends there.  Most recurrence wins are such ties (the chain entry precedes
     // `self` in four of the six masks), so real heads are few and runs short.
-    int win = 0, nc = 0, d0 = 0; short v0 = 0, h0 = 0;
+    int win = 0, nc = 0;
+    V4 o = out;
     if (active && k >= 1) {
-        const int n0 = tn[k - 1].y;
-        if (n0 < kInf) {
-            const Vox o = own_v[k - 1];
-            d0 = o.d; v0 = o.v; h0 = o.h; nc = n0 + 2 * d0 + 1;
-            win = (nc < Tk) && !(o.v == out.v && o.h == out.h && d0 + 1 == out.d);
+        o = own[k - 1];
+        if (o.n < kInf) {
+            nc = o.n + 2 * o.d + 1;
+            win = (nc < Tk) && !(o.v == out.v && o.h == out.h && o.d + 1 == out.d);
         }
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, win);
@@ -176,12 +177,12 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
     if (any) {
         if (active) sh.run_start[k] = -1;
         if (win) {                                   // extent of the run that starts at k-1
-            int n = nc, d = d0 + 1, pos = k + 1;
+            int n = nc, d = o.d + 1, pos = k + 1;
             while (pos < S) {
                 n += 2 * d + 1; d++;
-                const int2 t2 = tn[pos];
-                if (!(n < t2.x)) break;
-                if (n == t2.y) { const Vox o = own_v[pos]; if (o.v == v0 && o.h == h0 && o.d == d) break; }
+                if (!(n < T[pos])) break;
+                const V4 w = own[pos];
+                if (n == w.n && w.v == o.v && w.h == o.h && w.d == d) break;
                 pos++;
             }
             sh.run_end[k] = (short)pos;
@@ -212,7 +213,9 @@ __device__ __forceinline__ Vox row_scan(const RowSmem& sh, int S, int y, Vox sel
         if (active) {
             const int rs = sh.run_start[k];
             if (rs >= 0) {
-                out = own_v[rs]; out.d = (short)(out.d + (k - rs));
+                const V4 s0 = own[rs];
+                const int m = k - rs;
+                out.v = s0.v; out.h = s0.h; out.d = s0.d + m; out.n = s0.n + 2 * s0.d * m + m * m;
                 if (last_of_row) sh.prev[z + 1] = out;
             }
         }
@@ -226,30 +229,37 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem
 {
     const int z = threadIdx.x;
     const bool active = z < S;
-    const Vox unset = vox_unset_value();
+    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
     const bool use_xs = (K1 == F1 || K1 == B1) && xs >= 0 && xs < S;
     const int y0 = ydir > 0 ? 0 : S - 1;
-    auto gload = [&](int xx, int yy) -> Vox { return (active && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset; };
+    auto gload = [&](int xx, int yy) -> Vox { return (active && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset_g; };
     // prime the shared rows: adjacent-slice rows y0-1, y0, y0+1 ; previous row of this slice = outside
     if (active) {
-        for (int r = -1; r <= 1; r++) sh.xs[(y0 + r + 3) % 3][z + 1] = use_xs ? gload(xs, y0 + r) : unset;
-        sh.prev[z + 1] = unset;
+        for (int r = -1; r <= 1; r++) sh.xs[(y0 + r + 3) % 3][z + 1] = use_xs ? v4_from(gload(xs, y0 + r)) : v4_unset();
+        sh.prev[z + 1] = v4_unset();
     }
     Vox self_next = gload(x, y0);
-    Vox xs_next = use_xs ? gload(xs, y0 + 2 * ydir) : unset;
+    Vox xs_next = use_xs ? gload(xs, y0 + 2 * ydir) : unset_g;
     __syncthreads();
     for (int i = 0, y = y0; i < S; i++, y += ydir) {
-        const Vox self = self_next;
-        const Vox xs_row = xs_next;                         // adjacent-slice row y + 2*ydir: needed from the next row on
+        const V4 self = v4_from(self_next);
+        const V4 xs_row = v4_from(xs_next);                 // adjacent-slice row y + 2*ydir: needed from the next row on
         self_next = gload(x, y + ydir);                     // prefetch: own column only
-        xs_next = use_xs ? gload(xs, y + 3 * ydir) : unset;
+        xs_next = use_xs ? gload(xs, y + 3 * ydir) : unset_g;
+        {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed a few iterations from now into L2
+            const int yf = y + 8 * ydir;
+            if (active && (z & 15) == 0 && yf >= 0 && yf < S) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + yf) * S + z));
+                if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + yf) * S + z));
+            }
+        }
         bool runs1, runs2;
-        Vox v = row_scan<K1>(sh, S, y, self, 0, false, runs1);
+        V4 v = row_scan<K1>(sh, S, y, self, 0, false, runs1);
         // the adjacent-slice row that leaves the 3-row window is replaced by the incoming one; nobody
         // reads that slot again in this row, and the next row's reads come after >= 2 barriers
         if ((K1 == F1 || K1 == B1) && active) sh.xs[(y + 2 * ydir + 3 + 3) % 3][z + 1] = xs_row;
         v = row_scan<K2>(sh, S, y, v, 1, true, runs2);
-        if (active) G[((size_t)x * S + y) * S + z] = v;
+        if (active) G[((size_t)x * S + y) * S + z] = v4_to(v);
         if (runs2) __syncthreads();                         // prev[] was patched after the deciding barrier
     }
     __syncthreads();
@@ -262,11 +272,11 @@ dt_propagate_kernel(Vox* G, int S)
     RowSmem sh;
     {
         unsigned char* p = dt_smem;
-        const size_t row = (size_t)(S + 2) * sizeof(Vox);
-        for (int r = 0; r < 3; r++) { sh.xs[r] = reinterpret_cast<Vox*>(p); p += row; }
-        sh.prev = reinterpret_cast<Vox*>(p); p += row;
-        for (int b = 0; b < 2; b++) { sh.own_v[b] = reinterpret_cast<Vox*>(p); p += (size_t)S * sizeof(Vox); }
-        for (int b = 0; b < 2; b++) { sh.tn[b] = reinterpret_cast<int2*>(p); p += (size_t)S * sizeof(int2); }
+        const size_t row = (size_t)(S + 2) * sizeof(V4);
+        for (int r = 0; r < 3; r++) { sh.xs[r] = reinterpret_cast<V4*>(p); p += row; }
+        sh.prev = reinterpret_cast<V4*>(p); p += row;
+        for (int b = 0; b < 2; b++) { sh.own[b] = reinterpret_cast<V4*>(p); p += (size_t)S * sizeof(V4); }
+        for (int b = 0; b < 2; b++) { sh.T[b] = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int); }
         sh.wmask = reinterpret_cast<unsigned*>(p); p += 32 * sizeof(unsigned);
         sh.run_start = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
         sh.run_end = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
@@ -274,7 +284,7 @@ dt_propagate_kernel(Vox* G, int S)
     }
     // pads of the shared rows stay "unset" for the whole kernel
     if (threadIdx.x == 0) {
-        const Vox u = vox_unset_value();
+        const V4 u = v4_unset();
         for (int r = 0; r < 3; r++) { sh.xs[r][0] = u; sh.xs[r][S + 1] = u; }
         sh.prev[0] = u; sh.prev[S + 1] = u;
     }
@@ -291,7 +301,7 @@ dt_propagate_kernel(Vox* G, int S)
 
 static size_t dt_propagate_smem(int S)
 {
-    return 4 * (size_t)(S + 2) * sizeof(Vox) + 2 * (size_t)S * sizeof(Vox) + 2 * (size_t)S * sizeof(int2) + 32 * sizeof(unsigned)
+    return 4 * (size_t)(S + 2) * 16 + 2 * (size_t)S * 16 + 2 * (size_t)S * sizeof(int) + 32 * sizeof(unsigned)
          + 2 * (size_t)(S + 2) * sizeof(short) + (size_t)S + 64;
 }
 
