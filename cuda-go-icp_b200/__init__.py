@@ -73,7 +73,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
                "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
-               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_set_exchange", "goicp_selftest_shard", "goicp_run_toml"]
+               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_set_exchange", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 
 def build(verbose: bool = False) -> str:
@@ -121,6 +121,9 @@ def lib():
         L.goicp_cancel.argtypes = [C.c_void_p]
         L.goicp_set_exchange.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p, C.c_int]
         L.goicp_selftest_shard.argtypes = [C.c_int, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, C.POINTER(C.c_int)]
+        L.goicp_load_cloud.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_uint, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int)]
+        L.goicp_free_cloud.argtypes = [C.POINTER(C.c_float)]
+        L.goicp_io_last_error.restype = C.c_char_p
         L.goicp_run_toml.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.POINTER(Result)]
         _lib = L
     return _lib
@@ -348,3 +351,24 @@ class GoICP:
 
     def Cancel(self):
         self.L.goicp_cancel(self._handle())
+
+
+def load_cloud(path, subsample=1.0, resize=1.0, seed=1234):
+    """load_cloud (src/common.cpp:205-228) through the C ABI, with a seeded subsample."""
+    L = lib()
+    p = C.POINTER(C.c_float)()
+    n = C.c_int(0)
+    rc = L.goicp_load_cloud(os.fsencode(path), subsample, resize, seed, C.byref(p), C.byref(n))
+    if rc:
+        raise GoicpError(rc, L.goicp_io_last_error().decode())
+    out = np.ctypeslib.as_array(p, shape=(n.value * 3,)).copy().reshape(-1, 3) if n.value else np.zeros((0, 3), np.float32)
+    L.goicp_free_cloud(p)
+    return out
+
+
+def run_toml(path, seed_model=1234, seed_data=1235):
+    res = Result()
+    rc = lib().goicp_run_toml(os.fsencode(path), seed_model, seed_data, C.byref(res))
+    if rc:
+        raise GoicpError(rc, lib().goicp_io_last_error().decode())
+    return res.as_dict()

@@ -186,6 +186,10 @@ int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void
  * (src/common.cpp:79-228): loads [io].target/source (.txt / .ply), applies subsample (seeded)
  * and resize, builds the DT, registers, writes [io].output if non-empty. */
 int goicp_run_toml(const char* toml_path, unsigned seed_model, unsigned seed_data, goicp_result* out);
+/* load_cloud (src/common.cpp:205-228) with a seeded subsample; *xyz_out is malloc'ed, release with goicp_free_cloud. */
+int goicp_load_cloud(const char* path, float subsample, float resize, unsigned seed, float** xyz_out, int* n_out);
+void goicp_free_cloud(float* xyz);
+const char* goicp_io_last_error(void);
 
 #ifdef __cplusplus
 }

@@ -182,3 +182,20 @@ def test_register_bunny_full_size_reference_dt_on_gpu(pkg, runs, bunny, restated
         _check_run(g2.result, gold)
         g2.close()
     g.close()
+
+
+def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
+    """the reference's own workflow: TOML -> load clouds -> DT -> Go-ICP -> output file, on the GPU"""
+    for name, arr in (("model.txt", bunny["model"]), ("data.txt", bunny["data"])):
+        with open(tmp_path / name, "w") as f:
+            f.write(f"{len(arr)}\n")
+            for q in arr:
+                f.write("%.9g %.9g %.9g\n" % tuple(q))
+    cfg = tmp_path / "bunny.toml"
+    out = tmp_path / "output.toml"
+    cfg.write_text(f'[io]\ntarget = "model.txt"\nsource = "data.txt"\noutput = "{out}"\nvisualization = ""\n'
+                   '[params]\nmode = 3\ntrim = true\nsubsample = 1.0\nmse_threshold = 1e-3\nresize = 1.0\n')
+    res = pkg.run_toml(str(cfg))
+    _check_run(res, runs["bunny_s0.1_mse1e-3"])
+    text = out.read_text()
+    assert "exit_path = \"early_sse_below_thresh\"" in text and "rotation_nodes = 206" in text
