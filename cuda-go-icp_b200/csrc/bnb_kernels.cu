@@ -198,7 +198,7 @@ struct OwnerState {
 };
 constexpr int kMaxCluster = 16;
 
-template <bool PTS_SMEM>
+template <bool PTS_SMEM, bool TRIM>
 __global__ void __launch_bounds__(kBnbThreads, 2)
 inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
                  int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
@@ -217,6 +217,10 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
     __shared__ OwnerState own;
     __shared__ float4 cand_node[kMaxCand];
     __shared__ float cand_ub[kMaxCand];
+    // trimming (inlier_num < nd): cluster-wide radix select of the inlier_num smallest residuals per child
+    __shared__ int hist[8][256];
+    __shared__ unsigned sel_prefix[8];
+    __shared__ int sel_k[8];
 
     HeapEntry* hsm = reinterpret_cast<HeapEntry*>(smem_raw);
     float4* pts = reinterpret_cast<float4*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry));
@@ -232,6 +236,9 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
     const int per = (c.nd + C - 1) / C;
     const int p_begin = min(rank * per, c.nd), p_end = min(p_begin + per, c.nd);
     const int np = p_end - p_begin;
+    constexpr bool trim = TRIM;
+    // residual keys of this CTA's points for the 8 children (trimming only): after the points (if staged)
+    unsigned* mk = reinterpret_cast<unsigned*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry) + (PTS_SMEM ? (size_t)per * sizeof(float4) : 0));
 
     if (PTS_SMEM) {
         // rotate once (jly_goicp.cpp:470-476) and keep (R p, gamma) on chip for the whole search
@@ -301,18 +308,95 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
         float acc[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0.0f;
-        if (PTS_SMEM) {
-            for (int i = tid; i < np; i += kBnbThreads) {
-                const float4 p = pts[i];
-                accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+        if (!trim) {
+            if (PTS_SMEM) {
+                for (int i = tid; i < np; i += kBnbThreads) {
+                    const float4 p = pts[i];
+                    accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+                }
+            } else {
+                const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+                for (int i = p_begin + tid; i < p_end; i += kBnbThreads) {
+                    const float4 p = __ldg(c.data + i);
+                    accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                      dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
+                }
             }
         } else {
+            // Trimmed bounds (jly_goicp.cpp:293-315): only the inlier_num smallest residuals of each
+            // child count.  Residuals go to shared memory as order-preserving keys (non-negative
+            // floats), the k-th smallest is found by a 4 x 8-bit radix select whose histograms are
+            // merged in the leader through DSMEM atomics, then everything below the threshold is
+            // summed and the leader adds the ties it still needs.
             const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
-            for (int i = p_begin + tid; i < p_end; i += kBnbThreads) {
-                const float4 p = __ldg(c.data + i);
-                accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
-                                  dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
+            for (int i = tid; i < np; i += kBnbThreads) {
+                float px, py, pz, gm;
+                if (PTS_SMEM) { const float4 p = pts[i]; px = p.x; py = p.y; pz = p.z; gm = p.w; }
+                else {
+                    const float4 p = __ldg(c.data + p_begin + i);
+                    px = dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z); py = dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z);
+                    pz = dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z); gm = __fmul_rn(cg_, p.w);
+                }
+                float m[8];
+                point_residuals8(c.dt, px, py, pz, gm, ctrl.tr, m);
+#pragma unroll
+                for (int j = 0; j < 8; j++) mk[j * per + i] = __float_as_uint(m[j]);
             }
+            if (tid < 8) { sel_prefix[tid] = 0u; sel_k[tid] = c.inlier_num; }
+            for (int pass = 0; pass < 4; pass++) {
+                const int shift = 24 - 8 * pass;
+                __syncthreads();                                  // the leader's scan of the previous pass is done with hist
+                for (int b = tid; b < 8 * 256; b += kBnbThreads) (&hist[0][0])[b] = 0;
+                cluster.sync();                                   // histograms zeroed everywhere, keys / prefixes visible
+                const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+                for (int i = tid; i < np; i += kBnbThreads)
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const unsigned key = mk[j * per + i];
+                        if ((key & himask) == sel_prefix[j]) atomicAdd(&hist[j][(key >> shift) & 255u], 1);
+                    }
+                __syncthreads();
+                if (!leader) {                                    // merge into the leader's histogram
+                    int* lh = cluster.map_shared_rank(&hist[0][0], 0);
+                    for (int b = tid; b < 8 * 256; b += kBnbThreads) { const int v = (&hist[0][0])[b]; if (v) atomicAdd(lh + b, v); }
+                }
+                cluster.sync();
+                if (leader && warp < 8) {                         // warp j: find the digit holding the k-th smallest of child j
+                    const int j = warp;
+                    int carry = 0, found = -1, kk = sel_k[j];
+                    for (int base = 0; base < 256 && found < 0; base += 32) {
+                        const int v = hist[j][base + lane];
+                        int incl = v;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                        const unsigned hit = __ballot_sync(0xffffffffu, carry + incl >= kk);
+                        if (hit) {
+                            const int l0 = __ffs(hit) - 1;
+                            const int before = carry + __shfl_sync(0xffffffffu, incl - v, l0);
+                            found = base + l0;
+                            if (lane == 0) {
+                                const unsigned np_ = sel_prefix[j] | ((unsigned)found << shift);
+                                const int nk = kk - before;
+                                for (int r = 0; r < C; r++) { *cluster.map_shared_rank(&sel_prefix[j], r) = np_; *cluster.map_shared_rank(&sel_k[j], r) = nk; }
+                            }
+                        } else carry += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                }
+                // the next pass's first cluster.sync() publishes the new prefixes
+            }
+            cluster.sync();
+            // sel_prefix[j] is now the threshold key T_j, sel_k[j] the number of values == T_j to include
+            for (int i = tid; i < np; i += kBnbThreads)
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const unsigned key = mk[j * per + i];
+                    if (key < sel_prefix[j]) {
+                        const float m = __uint_as_float(key);
+                        acc[j] = __fadd_rn(acc[j], __fmul_rn(m, m));
+                        const float e = __fsub_rn(m, ctrl.tr[6]);
+                        if (e > 0.0f) acc[8 + j] = __fadd_rn(acc[8 + j], __fmul_rn(e, e));
+                    }
+                }
         }
         block_reduce16(acc, red, tot, warp, lane);      // contains a __syncthreads(); tot valid in warp 0
         if (warp == 0 && lane < 16) cluster.map_shared_rank(&partials[0][0], 0)[rank * 16 + lane] = tot[lane];
@@ -327,6 +411,12 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
             for (int j = 0; j < 8; j++) {
                 float ub = 0.0f, lb = 0.0f;                 // fixed-order sum over the cluster's CTAs
                 for (int r = 0; r < C; r++) { ub += partials[r][j]; lb += partials[r][8 + j]; }
+                if (trim) {                                 // the ties at the trimming threshold that still count
+                    const float tv = __uint_as_float(sel_prefix[j]), cnt = (float)sel_k[j];
+                    ub += cnt * (tv * tv);
+                    const float e = __fsub_rn(tv, ctrl.tr[6]);
+                    if (e > 0.0f) lb += cnt * (e * e);
+                }
                 if (ub < opt_t) {
                     opt_t = ub;
                     own.best[0] = __fadd_rn(px, (j & 1) ? cw : 0.0f);
@@ -486,35 +576,42 @@ cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int
     return cudaGetLastError();
 }
 // Opts the kernels into the full shared-memory carve-out; returns the dynamic bytes one CTA may use.
+template <bool P, bool T>
+static cudaError_t configure_one(int smem_optin, int* stat_out)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, inner_bnb_kernel<P, T>);
+    if (e != cudaSuccess) return e;
+    *stat_out = (int)a.sharedSizeBytes;
+    e = cudaFuncSetAttribute(inner_bnb_kernel<P, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(inner_bnb_kernel<P, T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
+// Opts the kernels into the full shared-memory carve-out; returns the dynamic bytes one CTA may use.
 cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
 {
-    cudaFuncAttributes a0, a1;
-    cudaError_t e = cudaFuncGetAttributes(&a0, inner_bnb_kernel<true>);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncGetAttributes(&a1, inner_bnb_kernel<false>);
-    if (e != cudaSuccess) return e;
-    const int stat = (int)(a0.sharedSizeBytes > a1.sharedSizeBytes ? a0.sharedSizeBytes : a1.sharedSizeBytes);
-    const int dyn = smem_optin - stat;
-    e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(inner_bnb_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(inner_bnb_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
+    int st[4] = {0, 0, 0, 0};
+    cudaError_t e;
+    if ((e = configure_one<true, false>(smem_optin, &st[0])) != cudaSuccess) return e;
+    if ((e = configure_one<false, false>(smem_optin, &st[1])) != cudaSuccess) return e;
+    if ((e = configure_one<true, true>(smem_optin, &st[2])) != cudaSuccess) return e;
+    if ((e = configure_one<false, true>(smem_optin, &st[3])) != cudaSuccess) return e;
+    int stat = 0;
+    for (int i = 0; i < 4; i++) stat = st[i] > stat ? st[i] : stat;
     e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(dt_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
-    *max_dyn_out = dyn;
+    *max_dyn_out = smem_optin - stat;
     return e;
 }
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
                              bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
+    const bool trim = c.inlier_num < c.nd;
     const int per = (c.nd + cluster - 1) / cluster;
-    size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0);
+    size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0)
+                + (trim ? (size_t)per * 8 * sizeof(unsigned) : 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n * cluster); cfg.blockDim = dim3(kBnbThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -522,8 +619,10 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     BnbConst cc = c;
-    if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
-    return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (!pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
 }
 // out5 = {strict optErrorT, node x, y, z, w}; d_strict: kMaxCand floats; d_scratch: kMaxCand*nd floats (only if nd does not fit in smem)
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,

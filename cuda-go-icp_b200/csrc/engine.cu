@@ -250,7 +250,6 @@ int make_const(goicp_handle* h, BnbConst& c)
 {
     if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "distance transform not built (call goicp_build_dt or goicp_set_dt first)");
     if (!h->initialized) { int rc = initialize(h); if (rc) return rc; }
-    if (h->inlier_num != h->nd) return fail(h, GOICP_ERR_INVALID, "trim_fraction > 0 is not supported by this build of the bound kernels yet");
     c.dt.grid = h->d_dt.p; c.dt.S = h->dt_size; c.dt.S2 = h->dt_size * h->dt_size;
     c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3]; c.dt.inv_scale = 1.0 / h->dt_meta[3];
     c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
@@ -274,9 +273,12 @@ InnerPlan plan_inner(const goicp_handle* h)
     // two CTAs per SM: each may take half of the SM's shared memory minus its static part and the 1 KB the driver reserves per CTA
     const size_t stat = (size_t)(h->max_smem_optin - h->inner_dyn_smem);
     const size_t per_cta = (size_t)h->max_smem_optin / 2 - stat - 2048;
-    const size_t pts = (size_t)((h->nd + cl - 1) / cl) * sizeof(float4);
-    p.pts_smem = pts + 16 * 1024 <= per_cta;
-    size_t heap_bytes = per_cta - (p.pts_smem ? pts : 0);
+    const size_t per = (size_t)((h->nd + cl - 1) / cl);
+    const size_t pts = per * sizeof(float4);
+    const bool trim = h->initialized && h->inlier_num < h->nd;
+    const size_t keys = trim ? per * 8 * sizeof(unsigned) : 0;          // residual keys of the radix select
+    p.pts_smem = pts + keys + 16 * 1024 <= per_cta;
+    size_t heap_bytes = per_cta - keys - (p.pts_smem ? pts : 0);
     p.heap_cap_sm = (int)std::min<size_t>(heap_bytes / sizeof(HeapEntry), 4096);
     return p;
 }
@@ -600,6 +602,7 @@ int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_
     if (!h || npairs < 0 || !R9 || !level || !tcube || !ub_out || !lb_out) return fail(h, GOICP_ERR_INVALID, "eval_bounds: bad arguments");
     if (npairs == 0) return GOICP_OK;
     BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    if (c.inlier_num < c.nd) return fail(h, GOICP_ERR_INVALID, "eval_bounds: trimmed bounds are evaluated by goicp_inner_bnb / goicp_register");
     std::vector<PairTask> tasks(npairs);
     for (int k = 0; k < npairs; k++) {
         if (level[k] >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "eval_bounds: rotation level >= 20");
@@ -624,6 +627,7 @@ int goicp_expand_bounds(goicp_handle* h, int n, const float* R9, const int32_t* 
     if (!h || n < 0 || !R9 || !level || !tcube || !out16) return fail(h, GOICP_ERR_INVALID, "expand_bounds: bad arguments");
     if (n == 0) return GOICP_OK;
     BnbConst c; int rc = make_const(h, c); if (rc) return rc;
+    if (c.inlier_num < c.nd) return fail(h, GOICP_ERR_INVALID, "expand_bounds: trimmed bounds are evaluated by goicp_inner_bnb / goicp_register");
     std::vector<PairTask> tasks(n);
     for (int k = 0; k < n; k++) {
         if (level[k] >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "expand_bounds: rotation level >= 20");

@@ -111,8 +111,8 @@ __device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane)
 // children: 6 double-precision index computations serve 8 gathers.  The in-grid case (all six
 // indices inside) is the fast path; anything else goes through the reference's clamp +
 // overshoot formula per child.
-__device__ __forceinline__ void accumulate_point8(const DtView& dt, float px, float py, float pz, float gamma,
-                                                  const float* __restrict__ tr, float (&acc)[16])
+__device__ __forceinline__ void point_residuals8(const DtView& dt, float px, float py, float pz, float gamma,
+                                                 const float* __restrict__ tr, float (&m)[8])
 {
     // per axis and axis bit: clamped voxel index and squared overshoot (0 inside the grid);
     // overshoot a = x (x<0) or x-S+1 (x>=S) == raw - clamped (jly_3ddt.cpp:991-1023)
@@ -145,13 +145,23 @@ __device__ __forceinline__ void accumulate_point8(const DtView& dt, float px, fl
             if (s2 != 0.0f) d[j] = __double2float_rn(__dadd_rn(__dmul_rn((double)__fsqrt_rn(s2), dt.inv_scale), (double)d[j]));
         }
     }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float v = __fsub_rn(d[j], gamma);
+        m[j] = v < 0.0f ? 0.0f : v;
+    }
+}
+
+__device__ __forceinline__ void accumulate_point8(const DtView& dt, float px, float py, float pz, float gamma,
+                                                  const float* __restrict__ tr, float (&acc)[16])
+{
+    float m[8];
+    point_residuals8(dt, px, py, pz, gamma, tr, m);
     const float gt = tr[6];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        float m = __fsub_rn(d[j], gamma);
-        m = m < 0.0f ? 0.0f : m;
-        acc[j] = __fadd_rn(acc[j], __fmul_rn(m, m));
-        const float e = __fsub_rn(m, gt);
+        acc[j] = __fadd_rn(acc[j], __fmul_rn(m[j], m[j]));
+        const float e = __fsub_rn(m[j], gt);
         if (e > 0.0f) acc[8 + j] = __fadd_rn(acc[8 + j], __fmul_rn(e, e));
     }
 }

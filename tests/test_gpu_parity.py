@@ -199,3 +199,37 @@ def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
     _check_run(res, runs["bunny_s0.1_mse1e-3"])
     text = out.read_text()
     assert "exit_path = \"early_sse_below_thresh\"" in text and "rotation_nodes = 206" in text
+
+
+def test_trimmed_inner_bnb_and_register(pkg, runs, bunny, restated, small):
+    """trimFraction = 0.1 (the reference's outlier-robust variant, jly_goicp.cpp:293-315): inner BnBs
+    against the oracle on a coarse DT, then the full S=300 bunny run against the reference's own."""
+    data = bunny["data_s"][::2].copy()
+    o = restated.create(bunny["model_s"], data, 1e-3, 0.1, 64)
+    restated.L.go_set_dt(o, restated.dt_wrap(small["inner_grid"], 64, small["inner_meta"]))
+    restated.L.go_initialize(o)
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model_s"], data
+    g.trimFraction = 0.1
+    g.dt.SIZE = 64
+    g.SetDT(small["inner_grid"], small["inner_meta"])
+    cases = small["inner_cases"][:24]
+    out = g.InnerBnB(cases[:, :9], cases[:, 9].astype(np.int32), cases[:, 10].astype(np.float32))
+    for row, got in zip(cases, out):
+        want = restated.inner(o, row[:9].astype(np.float32), int(row[9]), float(np.float32(row[10])))
+        if int(row[9]) < 0:
+            assert np.float32(got["value"]) == np.float32(want["value"])
+            if want["value"] < row[10]:
+                assert np.array_equal(got["node"], want["node"])
+        else:
+            assert got["value"] == pytest.approx(want["value"], rel=1e-5, abs=1e-6)
+        assert _close_counts(got["pops"], want["pops"])
+    g.close()
+    gold = runs["bunny_s0.1_mse1e-3_trim0.1"]
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.trimFraction = 0.1
+    g.BuildDT()
+    g.Register()
+    _check_run(g.result, gold)
+    g.close()
