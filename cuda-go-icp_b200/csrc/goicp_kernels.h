@@ -43,7 +43,8 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
     float* q;               // 3*nd transformed data points
     int32_t* nn;            // nd nearest model indices
     float* d2;              // nd squared distances
-    unsigned long long* keys;   // next_pow2(nd) sort keys (d2 bits << 32 | point index)
+    unsigned long long* keys;   // nd sort keys (d2 bits << 32 | point index)
+    int32_t* order;         // nd: order[rank] = point index, ranks by key
     float* stage;           // 8*nd: correspondences in sorted order
 };
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);

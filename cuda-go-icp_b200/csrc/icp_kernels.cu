@@ -351,24 +351,20 @@ __device__ void icp_update(IcpState* st, const float* H)
 // ------------------------------------------------------------------------------------------
 constexpr int kIcpChunk = 384;
 
-__device__ void bitonic_sort_block(unsigned long long* a, int n_pow2)
-{
-    const int half = n_pow2 >> 1;
-    for (int k = 2; k <= n_pow2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int p = threadIdx.x; p < half; p += blockDim.x) {          // one compare-exchange per pair
-                const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                const int ixj = i + j;
-                const unsigned long long x = a[i], y = a[ixj];
-                const bool up = (i & k) == 0;
-                if (up ? (x > y) : (x < y)) { a[i] = y; a[ixj] = x; }
-            }
-            __syncthreads();
-        }
-}
-
 // dynamic shared memory plan of the ICP kernel (decided on the host)
-struct IcpSmemPlan { int tree_nodes; int tree_bytes; int sort_bytes; int stage_bytes; };
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; };
+
+// ------------------------------------------------------------------------------------------
+// Nearest neighbour of up to 32 queries per pass (one per lane), all 16 warps of the CTA scanning
+// 1/16 of the model each.  A linear scan has no divergence, unlike the kd-tree descent where every
+// lane walks its own path; for the model sizes of this path it is an order of magnitude faster.
+// It is still the REFERENCE's answer: the scan also tracks the second-smallest distance, and
+// whenever that is within 1e-5 (relative) of the smallest -- exact ties included -- the query is
+// re-run through the reference-ordered kd-tree search.  Outside that margin the kd-tree cannot
+// return anything else: its pruning test would have to be wrong by 1e-5, more than an order of
+// magnitude above the float rounding of its bound (a handful of ulps).
+// ------------------------------------------------------------------------------------------
+struct NnPartial { float d1[kIcpThreads / 32][32]; float d2[kIcpThreads / 32][32]; int i1[kIcpThreads / 32][32]; };
 
 __global__ void __launch_bounds__(kIcpThreads)
 icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
@@ -379,11 +375,12 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     __shared__ float sh_H[9];
     __shared__ float sh_acc[8];
     __shared__ __align__(16) float chunk[kIcpChunk * 8];
+    __shared__ NnPartial part;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int npad = 1; while (npad < nd) npad <<= 1;
+    constexpr int kWarps = kIcpThreads / 32;
     const volatile IcpState* vst = st;
 
-    // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [sort keys] [staged rows]
+    // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [staged rows]
     const KdNode* nodes = kd.nodes; const float4* leaf = kd.pts_leaf;
     unsigned char* sp = icp_smem;
     if (plan.tree_bytes) {
@@ -393,12 +390,8 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
         nodes = sn; leaf = sl; sp += plan.tree_bytes;
     }
-    unsigned long long* skeys = plan.sort_bytes ? reinterpret_cast<unsigned long long*>(sp) : nullptr;
-    sp += plan.sort_bytes;
     float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
     __syncthreads();
-
-    for (int i = nd + blockIdx.x * blockDim.x + threadIdx.x; i < npad; i += gridDim.x * blockDim.x) wk.keys[i] = ~0ull;
 
     long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
@@ -408,39 +401,97 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         for (int i = 0; i < 9; i++) R[i] = vst->R[i];
 #pragma unroll
         for (int i = 0; i < 3; i++) t[i] = vst->t[i];
-        // queries interleaved over CTAs so that every SM of the grid searches
-        for (int i = threadIdx.x * gridDim.x + blockIdx.x; i < nd; i += gridDim.x * blockDim.x) {
-            const float4 p = __ldg(data + i);
-            // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
-            const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
-            const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
-            const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-            float d2;
-            const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
-            wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
-            wk.nn[i] = id; wk.d2[i] = d2;
-            wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+        // ---- phase A: transform + nearest neighbour; queries interleaved over the CTAs ----------
+        if (plan.brute_force) {
+            const int mchunk = (kd.nm + kWarps - 1) / kWarps;
+            const int m0 = min(warp * mchunk, kd.nm), m1 = min(m0 + mchunk, kd.nm);
+            for (int qpass = 0; (qpass * 32) * (int)gridDim.x + (int)blockIdx.x < nd; qpass++) {
+                const int i = (qpass * 32 + lane) * gridDim.x + blockIdx.x;
+                const bool valid = i < nd;
+                float qx = 0.0f, qy = 0.0f, qz = 0.0f;
+                if (valid) {
+                    const float4 p = __ldg(data + i);
+                    // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
+                    qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                }
+                float d1 = 3.402823466e+38f, d2 = 3.402823466e+38f; int i1 = 0;
+                for (int m = m0; m < m1; m++) {
+                    const float4 pm = leaf[m];                      // same address in every lane: broadcast
+                    const float e0 = qx - pm.x, e1 = qy - pm.y, e2 = qz - pm.z;
+                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;  // kdtree_distance (jly_icp3d.hpp:48-54)
+                    if (dist < d1) { d2 = d1; d1 = dist; i1 = __float_as_int(pm.w); }
+                    else if (dist < d2) d2 = dist;
+                }
+                part.d1[warp][lane] = d1; part.d2[warp][lane] = d2; part.i1[warp][lane] = i1;
+                __syncthreads();
+                if (warp == 0) {
+                    float D1 = 3.402823466e+38f, D2 = 3.402823466e+38f; int I1 = 0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; w++) {
+                        const float a = part.d1[w][lane], b = part.d2[w][lane];
+                        if (a < D1) { D2 = fminf(D1, b); D1 = a; I1 = part.i1[w][lane]; }
+                        else D2 = fminf(D2, a);
+                        D2 = fminf(D2, b);
+                    }
+                    if (valid) {
+                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1);   // near tie: reference traversal order decides
+                        wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
+                        wk.nn[i] = I1; wk.d2[i] = D1;
+                        wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int i = threadIdx.x * gridDim.x + blockIdx.x; i < nd; i += gridDim.x * blockDim.x) {
+                const float4 p = __ldg(data + i);
+                const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                float d2;
+                const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
+                wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
+                wk.nn[i] = id; wk.d2[i] = d2;
+                wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+            }
         }
         long long c1 = clock64(); c_nn += c1 - c0;
         grid.sync();
         c0 = clock64(); c_wait += c0 - c1;
-        if (blockIdx.x == 0) {
-            // ---- sort by (distance, index)
-            unsigned long long* keys = wk.keys;
-            if (skeys) {
-                for (int i = threadIdx.x; i < npad; i += blockDim.x) skeys[i] = __ldcg(wk.keys + i);
+        // ---- phase B: the reference's qsort by distance (stable for ties) as a distributed rank
+        // count: rank(i) = #{j : key_j < key_i}, keys = (d^2 bits, index) are unique.  Every CTA ranks
+        // its own queries against all keys; order[rank] = i.
+        {
+            const unsigned long long* keys = wk.keys;
+            const bool keys_in_smem = sstage != nullptr && (size_t)plan.stage_bytes >= (size_t)nd * sizeof(unsigned long long);
+            if (keys_in_smem) {                      // the staging area is idle until phase C
+                unsigned long long* sk = reinterpret_cast<unsigned long long*>(sstage);
+                for (int j = threadIdx.x; j < nd; j += blockDim.x) sk[j] = __ldcg(wk.keys + j);
                 __syncthreads();
-                bitonic_sort_block(skeys, npad);
-                keys = skeys;
-            } else {
-                __syncthreads();
-                bitonic_sort_block(wk.keys, npad);
+                keys = sk;
             }
-            c1 = clock64(); c_sort += c1 - c0; c0 = c1;
-            // ---- reference-order accumulations: correspondences (model point, query, d^2) are laid
-            // out in sorted order -- all of them in shared memory when they fit, else in chunks of
-            // kIcpChunk rows (kept in wk.stage for the second pass); one lane per accumulator then
-            // adds them up strictly sequentially.
+            for (int qq = warp; qq * (int)gridDim.x + (int)blockIdx.x < nd; qq += kWarps) {
+                const int i = qq * gridDim.x + blockIdx.x;
+                const unsigned long long ki = keys[i];
+                int cnt = 0;
+                if (keys_in_smem) { for (int j = lane; j < nd; j += 32) cnt += keys[j] < ki; }
+                else              { for (int j = lane; j < nd; j += 32) cnt += __ldcg(keys + j) < ki; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (lane == 0) wk.order[cnt] = i;
+            }
+            if (keys_in_smem) __syncthreads();       // block 0 overwrites the area in phase C
+        }
+        c1 = clock64(); c_sort += c1 - c0;
+        grid.sync();
+        c0 = clock64(); c_wait += c0 - c1;
+        if (blockIdx.x == 0) {
+            // ---- phase C: reference-order accumulations: correspondences (model point, query, d^2)
+            // are laid out in sorted order -- all of them in shared memory when they fit, else in
+            // chunks of kIcpChunk rows (kept in wk.stage for the second pass); one lane per
+            // accumulator then adds them up strictly sequentially.
             float acc = 0.0f;
             if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
             const int step = sstage ? num : kIcpChunk;
@@ -448,7 +499,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 const int cnt = min(step, num - base);
                 float* rows = sstage ? sstage : chunk;
                 for (int rr = threadIdx.x; rr < cnt; rr += blockDim.x) {
-                    const int i = (int)(keys[base + rr] & 0xffffffffu);
+                    const int i = __ldcg(wk.order + base + rr);
                     const int id = __ldcg(wk.nn + i);
                     float4 lo = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), __ldcg(wk.q + 3 * i));
                     float4 hi = make_float4(__ldcg(wk.q + 3 * i + 1), __ldcg(wk.q + 3 * i + 2), __ldcg(wk.d2 + i), 0.0f);
@@ -457,14 +508,20 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 }
                 __syncthreads();
                 if (warp == 0 && lane < 7) {
+                    // err_new += dis is float += double in the reference (:254); the double sum of two
+                    // floats is exact (or differs from either by < 2^-29), so rounding it to float
+                    // equals the float sum -- one add per element, like the other accumulators
+                    // operands are fetched 16 at a time ahead of the dependent chain of adds
                     const float* sg = rows + lane;
-                    if (lane < 6) {
-#pragma unroll 8
-                        for (int rr = 0; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
-                    } else {
-#pragma unroll 8
-                        for (int rr = 0; rr < cnt; rr++) acc = (float)((double)acc + (double)sg[8 * rr]);      // float += double (:254)
+                    int rr = 0;
+                    for (; rr + 16 <= cnt; rr += 16) {
+                        float v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) v[u] = sg[8 * (rr + u)];
+#pragma unroll
+                        for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
                     }
+                    for (; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
                 }
                 __syncthreads();
             }
@@ -498,8 +555,16 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                         __syncthreads();
                     }
                     if (warp == 0 && lane < 9) {
-#pragma unroll 8
-                        for (int rr = 0; rr < cnt; rr++)
+                        // products are formed 16 at a time (independent), then added in order
+                        int rr = 0;
+                        for (; rr + 16 <= cnt; rr += 16) {
+                            float pr[16];
+#pragma unroll
+                            for (int u = 0; u < 16; u++) pr[u] = __fmul_rn(__fsub_rn(rows[8 * (rr + u) + 3 + a], mud), __fsub_rn(rows[8 * (rr + u) + b], mum));
+#pragma unroll
+                            for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, pr[u]);
+                        }
+                        for (; rr < cnt; rr++)
                             acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(rows[8 * rr + 3 + a], mud), __fsub_rn(rows[8 * rr + b], mum)));
                     }
                     if (!sstage) __syncthreads();
@@ -530,13 +595,12 @@ static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int 
 {
     IcpSmemPlan p = {0, 0, 0, 0};
     int left = smem_limit;
-    size_t npad = 1; while (npad < (size_t)nd) npad <<= 1;
     const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
-    const size_t sort = npad * sizeof(unsigned long long);
     const size_t stage = (size_t)num * 8 * sizeof(float);
-    if (sort <= (size_t)left) { p.sort_bytes = (int)sort; left -= (int)sort; }
-    if (stage <= (size_t)left) { p.stage_bytes = (int)stage; left -= (int)stage; }
     if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
+    if (stage <= (size_t)left) { p.stage_bytes = (int)stage; left -= (int)stage; }
+    // linear scan while it beats the (divergent) tree descent: model resident in shared memory, or moderate size
+    p.brute_force = (p.tree_bytes != 0 || kd.nm <= 16384) ? 1 : 0;
     return p;
 }
 int icp_threads() { return kIcpThreads; }
@@ -548,7 +612,7 @@ int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int n
     cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.sort_bytes + p.stage_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
@@ -564,7 +628,7 @@ cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int 
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
                     (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&plan};
     return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args,
-                                       (size_t)plan.tree_bytes + plan.sort_bytes + plan.stage_bytes, s);
+                                       (size_t)plan.tree_bytes + plan.stage_bytes, s);
 }
 
 } // namespace goicp
