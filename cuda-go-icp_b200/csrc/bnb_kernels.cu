@@ -9,6 +9,7 @@
 #include "goicp_kernels.h"
 #include "strict_sum.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace goicp {
 
@@ -167,6 +168,88 @@ __device__ __forceinline__ HeapEntry heap_pop(Heap& h)
         hole = child - 1;
     }
     heap_sift_up(h, hole, v);
+    return top;
+}
+
+// Warp-cooperative versions (all 32 lanes call with identical arguments; same resulting array as
+// the sequential routines above).  push: every ancestor of the new slot is loaded by its own lane,
+// a ballot finds how far the new entry rises, the displaced ancestors move down in one step.
+// pop: lane 0 walks the preferred-child path to a leaf (keys only), then the entries on the path
+// and the re-inserted last element are placed in parallel.
+// Entries move as 16-byte vectors; comparisons need only the first 8 bytes (lb, level).  While the
+// queue fits the shared-memory part (the common case) no address-space select is involved.
+__device__ __forceinline__ uint4 he_pack(const HeapEntry& e) { return make_uint4(__float_as_uint(e.lb), e.level, e.path_lo, e.path_hi); }
+__device__ __forceinline__ HeapEntry he_unpack(const uint4& u) { HeapEntry e; e.lb = __uint_as_float(u.x); e.level = u.y; e.path_lo = u.z; e.path_hi = u.w; return e; }
+__device__ __forceinline__ bool key_less(float lb_a, uint32_t lv_a, float lb_b, uint32_t lv_b) { return lb_a != lb_b ? lb_a > lb_b : lv_a > lv_b; }
+
+__device__ __forceinline__ bool wheap_push(Heap& h, const HeapEntry& v, int lane)
+{
+    if (h.n >= h.cap_total) return false;
+    const int n = h.n;
+    const int depth = 31 - __clz(n + 1);                 // number of ancestors of slot n
+    uint4* A = reinterpret_cast<uint4*>(h.sm);
+    const bool in_sm = n < h.cap_sm;
+    uint4 e = he_pack(v); bool pred = false;
+    if (lane >= 1 && lane <= depth) {
+        const int a = ((n + 1) >> lane) - 1;
+        e = in_sm ? A[a] : he_pack(h.get(a));
+        pred = key_less(__uint_as_float(e.x), e.y, v.lb, v.level);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, pred) >> 1;
+    const int m = __ffs(~b) - 1;                         // ancestors 1..m are displaced
+    if (lane >= 1 && lane <= m) { const int d = ((n + 1) >> (lane - 1)) - 1; if (in_sm) A[d] = e; else h.set(d, he_unpack(e)); }
+    if (lane == 0) { const int d = ((n + 1) >> m) - 1; if (in_sm) A[d] = e; else h.set(d, v); }
+    h.n = n + 1;
+    __syncwarp();
+    return true;
+}
+__device__ __forceinline__ HeapEntry wheap_pop(Heap& h, int lane, int* path /* shared, >= 34 ints */)
+{
+    uint4* A = reinterpret_cast<uint4*>(h.sm);
+    const bool in_sm = h.n <= h.cap_sm;
+    const HeapEntry top = in_sm ? he_unpack(A[0]) : h.get(0);
+    const int len = h.n - 1;
+    h.n = len;
+    if (len == 0) return top;
+    const uint4 v = in_sm ? A[len] : he_pack(h.get(len));
+    if (lane == 0) {
+        int t = 0, child = 0;
+        path[0] = 0;
+        const int last_parent = (len - 1) / 2;
+        if (in_sm) {
+            const uint2* K = reinterpret_cast<const uint2*>(h.sm);          // first 8 bytes of entry i at K[2*i]
+            while (child < last_parent) {
+                child = 2 * (child + 1);
+                const uint2 a = K[2 * child], b = K[2 * (child - 1)];
+                if (key_less(__uint_as_float(a.x), a.y, __uint_as_float(b.x), b.y)) child--;
+                path[++t] = child;
+            }
+        } else {
+            while (child < last_parent) {
+                child = 2 * (child + 1);
+                const HeapEntry a = h.get(child), b = h.get(child - 1);
+                if (node_less(a, b)) child--;
+                path[++t] = child;
+            }
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); path[++t] = child - 1; }
+        path[33] = t;
+    }
+    __syncwarp();
+    const int t = path[33];
+    uint4 e = v; bool pred = false; int pos = 0;
+    if (lane >= 1 && lane <= t) {
+        pos = path[lane];
+        e = in_sm ? A[pos] : he_pack(h.get(pos));
+        pred = key_less(__uint_as_float(e.x), e.y, __uint_as_float(v.x), v.y);
+    }
+    // the last element climbs from the leaf while the entry above it (path entry i, now one level up) is lower
+    const unsigned b = __ballot_sync(0xffffffffu, pred);  // bit i = entry i is lower than v
+    int j = t;
+    while (j > 0 && ((b >> j) & 1u)) j--;
+    if (lane >= 1 && lane <= j) { const int d = path[lane - 1]; if (in_sm) A[d] = e; else h.set(d, he_unpack(e)); }
+    if (lane == 0) { const int d = path[j]; if (in_sm) A[d] = v; else h.set(d, he_unpack(v)); }
+    __syncwarp();
     return top;
 }
 
@@ -480,6 +563,267 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
 }
 
 // ------------------------------------------------------------------------------------------
+// Pipelined variant (no trimming): warp 0 of every CTA is the OWNER warp and does not gather; in
+// the leader CTA it runs the priority queue.  The cluster barrier is split into arrive / wait so
+// that the leader's queue maintenance (8 pushes + 1 pop in libstdc++ order) happens in the SHADOW
+// of the cluster's gathers for the next cube:
+//     owner:    decide next cube -> write ctrl to all CTAs -> arrive(A) ; queue maintenance ; wait(A) ;
+//               arrive(B) ; wait(B) -> partial sums are in -> decide ...
+//     gatherers:            arrive(A) ; wait(A) ; gather + reduce + send partials ; arrive(B) ; wait(B)
+// "Decide" picks the node the queue WILL pop next -- the better of the current top and the children
+// about to be pushed -- which is unambiguous unless two candidates tie on (lb, level); on a tie the
+// maintenance runs first (the tie is then resolved by the heap exactly like in the reference).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// arrival that publishes nothing (no fence needed on the arriving side)
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+constexpr int kGatherThreads = kBnbThreads - 32;
+constexpr int kGatherWarps = kBnbWarps - 1;
+
+template <bool PTS_SMEM>
+__global__ void __launch_bounds__(kBnbThreads, 2)
+inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
+                           int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int task_id = blockIdx.x / C;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float red[kGatherWarps][16];
+    __shared__ InnerCtrl ctrl;                       // written by the leader into every CTA of the cluster
+    __shared__ float partials[kMaxCluster][16];      // leader: one row per CTA
+    __shared__ float4 cand_node[kMaxCand];
+    __shared__ float cand_ub[kMaxCand];
+
+    HeapEntry* hsm = reinterpret_cast<HeapEntry*>(smem_raw);
+    float4* pts = reinterpret_cast<float4*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry));
+
+    const long long t_begin = clock64();
+    const InnerTask& task = tasks[task_id];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool leader = rank == 0;
+    const bool ub_pass = task.level < 0;
+    const float cand_eps = fminf(1e-2f, 2.0f * (float)c.nd * 5.9604645e-8f) + 1e-6f;
+    const int per = (c.nd + C - 1) / C;
+    const int p_begin = min(rank * per, c.nd), p_end = min(p_begin + per, c.nd);
+    const int np = p_end - p_begin;
+
+    if (PTS_SMEM) {
+        const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+        for (int i = tid; i < np; i += kBnbThreads) {
+            float4 p = __ldg(c.data + p_begin + i);
+            pts[i] = make_float4(dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                 dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w));
+        }
+    }
+    __syncthreads();
+
+    if (warp != 0) {
+        // ================================ gather warps ======================================
+        const int gt = tid - 32;
+        for (;;) {
+            cluster_arrive_relaxed(); cluster_wait();               // (A) next cube published
+            if (ctrl.done) break;
+            float acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+            if (PTS_SMEM) {
+                for (int i = gt; i < np; i += kGatherThreads) {
+                    const float4 p = pts[i];
+                    accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+                }
+            } else {
+                const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+                for (int i = p_begin + gt; i < p_end; i += kGatherThreads) {
+                    const float4 p = __ldg(c.data + i);
+                    accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                      dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
+                }
+            }
+            warp_reduce16(acc, lane);
+            if ((lane & 1) == 0) red[warp - 1][(lane >> 1) & 15] = acc[0];
+            asm volatile("bar.sync 1, %0;" :: "r"(kGatherThreads) : "memory");
+            if (warp == 1 && lane < 16) {
+                float s = 0.0f;
+#pragma unroll
+                for (int w = 0; w < kGatherWarps; w++) s += red[w][lane];
+                cluster.map_shared_rank(&partials[0][0], 0)[rank * 16 + lane] = s;
+            }
+            cluster_arrive(); cluster_wait();                       // (B) partial sums delivered
+        }
+        return;
+    }
+    if (!leader) {
+        // ============================ idle owner warp of a helper CTA ========================
+        for (;;) {
+            cluster_arrive_relaxed(); cluster_wait();
+            if (ctrl.done) break;
+            cluster_arrive_relaxed(); cluster_wait();
+        }
+        return;
+    }
+
+    // ===================================== leader's owner warp =============================
+    // All 32 lanes run the same scalar bookkeeping redundantly (no divergence); the lanes share the
+    // work where there is any: summing the CTAs' partials, heap operations, the ctrl broadcast.
+    __shared__ float tot16[16];
+    __shared__ int pop_path[34];
+    Heap heap; heap.sm = hsm; heap.gl = spill + (size_t)task_id * spill_cap; heap.cap_sm = heap_cap_sm; heap.cap_total = heap_cap_sm + spill_cap; heap.n = 0;
+    float opt_t = task.opt_error;
+    float best[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t pops = 0, evals = 0, max_heap = 0, flags = 0; int status = 0, n_cand = 0;
+    float px = c.tx, py = c.ty, pz = c.tz, cw = c.tw / 2;              // cube being expanded
+    uint32_t plevel = 0; unsigned long long ppath = 0ull;
+    HeapEntry pend[8]; int n_pend = 0; bool need_pop = false;           // pushes deferred into the shadow of the gathers
+    HeapEntry expect; expect.lb = 0.0f; expect.level = 0; expect.path_lo = expect.path_hi = 0;
+    bool done = false;
+
+    auto publish = [&](bool fin) {                                       // lane r writes the control block of CTA r
+        if (lane < C) {
+            InnerCtrl next; next.done = fin ? 1 : 0;
+            const float half = cw / 2;
+#pragma unroll
+            for (int b = 0; b < 2; b++) {
+                next.tr[b] = __fadd_rn(__fadd_rn(px, b ? cw : 0.0f), half);
+                next.tr[2 + b] = __fadd_rn(__fadd_rn(py, b ? cw : 0.0f), half);
+                next.tr[4 + b] = __fadd_rn(__fadd_rn(pz, b ? cw : 0.0f), half);
+            }
+            next.tr[6] = max_trans_dis(cw); next.tr[7] = 0.0f;
+            *cluster.map_shared_rank(&ctrl, lane) = next;
+        }
+    };
+    // adopt `e` as the cube to expand next (the reference's pop, :246-262), or finish
+    auto adopt = [&](const HeapEntry& e) {
+        pops++;                                                               // tNodeCount++ (:248)
+        if (__fsub_rn(opt_t, e.lb) < c.sse_thresh) { done = true; return; }  // :257
+        if (e.level >= (uint32_t)kMaxTransLevel) { done = true; status = 4; return; }
+        // corner: replay the reference's float additions parent.x + (j&1)*w down the octant path (:267-269)
+        float x = c.tx, y = c.ty, z = c.tz, w = c.tw;
+        const unsigned long long path = ((unsigned long long)e.path_hi << 32) | e.path_lo;
+        for (uint32_t l = 0; l < e.level; l++) {
+            w = w / 2;
+            const unsigned b = (unsigned)(path >> (3 * l)) & 7u;
+            x = __fadd_rn(x, (b & 1) ? w : 0.0f); y = __fadd_rn(y, (b & 2) ? w : 0.0f); z = __fadd_rn(z, (b & 4) ? w : 0.0f);
+        }
+        px = x; py = y; pz = z; cw = w / 2; plevel = e.level; ppath = path;
+    };
+    auto flush_pending = [&]() {
+        for (int k = 0; k < n_pend && !status; k++) if (!wheap_push(heap, pend[k], lane)) status = 3;
+        n_pend = 0;
+        if ((uint32_t)heap.n > max_heap) max_heap = heap.n;
+    };
+
+    {   // push + pop of initNodeTrans (:241-247)
+        HeapEntry root; root.lb = 0.0f; root.level = 0; root.path_lo = root.path_hi = 0;
+        adopt(root);
+        publish(done);
+    }
+    for (;;) {
+        __syncwarp();
+        cluster_arrive();                                                     // (A) cube published
+        if (!done) {
+            // ---- queue maintenance in the shadow of the gathers --------------------------
+            flush_pending();
+            if (need_pop && !status) {
+                const HeapEntry e = wheap_pop(heap, lane, pop_path);
+                if (e.lb != expect.lb || e.level != expect.level || e.path_lo != expect.path_lo || e.path_hi != expect.path_hi) status = 5;   // cannot happen: the prediction was unambiguous
+                need_pop = false;
+            }
+        }
+        cluster_wait();
+        if (done) break;
+        cluster_arrive_relaxed(); cluster_wait();                             // (B) partial sums are in
+        // ---- fixed-order sum over the cluster's CTAs, one lane per value ------------------------
+        if (lane < 16) { float sacc = 0.0f; for (int r = 0; r < C; r++) sacc += partials[r][lane]; tot16[lane] = sacc; }
+        __syncwarp();
+        // ---- sequential bookkeeping of the 8 children (jly_goicp.cpp:317-336) -------------------
+        evals += 8;
+        n_pend = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const float ub = tot16[j], lb = tot16[8 + j];
+            if (ub < opt_t) {
+                opt_t = ub;
+                best[0] = __fadd_rn(px, (j & 1) ? cw : 0.0f); best[1] = __fadd_rn(py, (j & 2) ? cw : 0.0f);
+                best[2] = __fadd_rn(pz, (j & 4) ? cw : 0.0f); best[3] = cw;
+            }
+            if (ub_pass && ub <= opt_t * (1.0f + cand_eps)) {
+                if (n_cand == kMaxCand) {
+                    int k = 0;
+                    for (int q = 0; q < n_cand; q++)
+                        if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { if (lane == 0) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; } k++; }
+                    n_cand = k;
+                    __syncwarp();
+                }
+                if (n_cand < kMaxCand) {
+                    if (lane == 0) {
+                        cand_node[n_cand] = make_float4(__fadd_rn(px, (j & 1) ? cw : 0.0f), __fadd_rn(py, (j & 2) ? cw : 0.0f),
+                                                        __fadd_rn(pz, (j & 4) ? cw : 0.0f), cw);
+                        cand_ub[n_cand] = ub;
+                    }
+                    n_cand++;
+                    __syncwarp();
+                } else flags |= 1u;
+            }
+            if (lb >= opt_t) continue;
+            HeapEntry e; e.lb = lb; e.level = plevel + 1;
+            const unsigned long long path = ppath | ((unsigned long long)j << (3 * plevel));
+            e.path_lo = (uint32_t)path; e.path_hi = (uint32_t)(path >> 32);
+            pend[n_pend++] = e;
+        }
+        // ---- which node will the queue pop next? ------------------------------------------------
+        if (status) { done = true; publish(true); }
+        else if (heap.n == 0 && n_pend == 0) { done = true; publish(true); }          // queue empty (:243-244)
+        else {
+            // best candidate among the current top and the pending children; ties on (lb, level) are left to the heap
+            HeapEntry b; bool tie = false; int k0 = 0;
+            if (heap.n > 0) b = heap.get(0); else { b = pend[0]; k0 = 1; }
+            for (int k = k0; k < n_pend; k++) {
+                const HeapEntry& e = pend[k];
+                if (node_less(b, e)) { b = e; tie = false; }                   // e has strictly higher priority
+                else if (!node_less(e, b)) tie = true;                         // same (lb, level)
+            }
+            if (tie) {
+                flush_pending();                                               // the heap's own arrangement decides
+                if (status) { done = true; publish(true); }
+                else { const HeapEntry e = wheap_pop(heap, lane, pop_path); adopt(e); publish(done); }
+            } else {
+                expect = b; need_pop = true;
+                adopt(b);
+                publish(done);
+            }
+        }
+    }
+
+    // ---- results (see inner_bnb_kernel) ---------------------------------------------------------
+    if (ub_pass) {
+        __syncwarp();
+        {
+            int k = 0;
+            for (int q = 0; q < n_cand; q++)
+                if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { if (lane == 0) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; } k++; }
+            n_cand = k;
+            __syncwarp();
+        }
+        CandList& cl = cands[task_id];
+        for (int q = lane; q < n_cand; q += 32) { cl.node[q] = cand_node[q]; cl.ub[q] = cand_ub[q]; }
+        if (lane == 0) { cl.n = n_cand; cl.flags = flags; cl.final_fast = opt_t; cl.eps = cand_eps; }
+    }
+    if (lane == 0) {
+        InnerResult r;
+        r.value = opt_t; r.node[0] = best[0]; r.node[1] = best[1]; r.node[2] = best[2]; r.node[3] = best[3];
+        r.pops = pops; r.evals = evals; r.status = status == 5 ? 3 : status; r.max_heap = max_heap;
+        r.pad[0] = flags | (status == 5 ? 0x100u : 0u); r.pad[1] = ub_pass ? (uint32_t)n_cand : 0u;
+        r.kcycles = (uint32_t)((clock64() - t_begin) >> 10);
+        results[task_id] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Strict resolution of one upper-bound pass (on demand, when the pass may improve the optimum).
 // One CTA per contender: gathers in parallel into shared memory, then one thread applies the
 // reference's intro_select + sequential float sum.  strict_pick_kernel replays the reference's
@@ -598,6 +942,17 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     if ((e = configure_one<false, true>(smem_optin, &st[3])) != cudaSuccess) return e;
     int stat = 0;
     for (int i = 0; i < 4; i++) stat = st[i] > stat ? st[i] : stat;
+    {
+        cudaFuncAttributes a;
+        if ((e = cudaFuncGetAttributes(&a, inner_bnb_pipelined_kernel<true>)) != cudaSuccess) return e;
+        stat = (int)a.sharedSizeBytes > stat ? (int)a.sharedSizeBytes : stat;
+        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&a, inner_bnb_pipelined_kernel<false>)) != cudaSuccess) return e;
+        stat = (int)a.sharedSizeBytes > stat ? (int)a.sharedSizeBytes : stat;
+        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(dt_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
@@ -619,6 +974,9 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     BnbConst cc = c;
+    static const bool legacy = getenv("GOICP_NO_PIPELINE") != nullptr;     // A/B switch for profiling
+    if (pts_in_smem && !trim && !legacy) return cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (!pts_in_smem && !trim && !legacy) return cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     if (pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     if (!pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);

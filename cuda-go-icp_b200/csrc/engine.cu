@@ -455,7 +455,7 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     for (int i = 0; i < 3; i++) out->t[i] = st.t[i];
     out->err = st.err_new; out->iterations = st.iter;
     if (getenv("GOICP_ICP_STATS"))
-        fprintf(stderr, "[icp] iters %d blocks %d cycles: nn %lld wait %lld sort %lld pass1 %lld pass2 %lld total %lld\n", st.iter, blocks,
+        fprintf(stderr, "[icp] iters %d blocks %d cycles: nn %lld wait %lld sort %lld pass1 %lld pass2 %lld acc1 %lld\n", st.iter, blocks,
                 st.dbg[0], st.dbg[1], st.dbg[2], st.dbg[3], st.dbg[4], st.dbg[5]);
     return GOICP_OK;
 }

@@ -393,7 +393,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
     __syncthreads();
 
-    long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0; const long long c_begin = clock64();
+    long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
         long long c0 = clock64();
         float R[9], t[3];
@@ -507,6 +507,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     if (!sstage) { reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi; }
                 }
                 __syncthreads();
+                const long long ca0 = clock64();
                 if (warp == 0 && lane < 7) {
                     // err_new += dis is float += double in the reference (:254); the double sum of two
                     // floats is exact (or differs from either by < 2^-29), so rounding it to float
@@ -523,6 +524,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     }
                     for (; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
                 }
+                c_acc1 += clock64() - ca0;
                 __syncthreads();
             }
             if (warp == 0) {
@@ -582,7 +584,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         if (vst->converged) break;
         if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = clock64() - c_begin; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; }
 }
 
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s)
