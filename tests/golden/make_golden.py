@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference and `make -C oracle ref`)
     python tests/golden/make_golden.py clouds      # deterministic bunny subsamples (seeds 1234/1235)
     python tests/golden/make_golden.py runs        # 5 full reference Go-ICP runs, S=300 (~13 min CPU)
     python tests/golden/make_golden.py small       # small-S DT grids / NN / ICP / inner-BnB vectors (seconds)
+    python tests/golden/make_golden.py config2     # full-size bun045/bun000 clouds + reference NN indices + ICP result
 
 The committed fixtures were produced by exactly these commands; the GPU box never runs this.
 """
@@ -121,6 +122,22 @@ def small():
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in g.items()})
 
 
+def config2():
+    """BASELINE config 2 (test/bunny_icp.toml: bun045.ply target, bun000.ply source, resize 15, subsample 1.0):
+    full-size clouds, reference NN indices at the identity pose and the reference ICP3D::Run result."""
+    import importlib
+    from oracle.oracle import Reference
+    pkg = importlib.import_module("cuda-go-icp_b200")
+    rf = Reference()
+    model = pkg.load_cloud(f"{REFDATA}/bunny/bun045.ply", 1.0, 15.0, 1)
+    data = pkg.load_cloud(f"{REFDATA}/bunny/bun000.ply", 1.0, 15.0, 1)
+    icp = rf.icp_build(model)
+    idx, d2 = rf.icp_nn(icp, data)
+    e, R, t = rf.icp_run(icp, data, np.eye(3), np.zeros(3), 10000, 1e-9, 0.0, True)
+    np.savez_compressed(os.path.join(HERE, "bun_icp_config2.npz"), model=model, data=data, nn_idx=idx, nn_d2=d2,
+                        icp_err=np.float32(e), icp_R=R, icp_t=t)
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "clouds":
@@ -129,3 +146,5 @@ if __name__ == "__main__":
         runs(sys.argv[2] if len(sys.argv) > 2 else None)
     elif cmd == "small":
         small()
+    elif cmd == "config2":
+        config2()

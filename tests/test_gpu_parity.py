@@ -233,3 +233,20 @@ def test_trimmed_inner_bnb_and_register(pkg, runs, bunny, restated, small):
     g.Register()
     _check_run(g.result, gold)
     g.close()
+
+
+def test_config2_full_size_nn_and_icp_on_gpu(pkg):
+    """BASELINE config 2 (bunny ICP only) at full size: 40256 nearest-neighbour indices bit-exact with the
+    reference kd-tree (incl. its 53 exact-tie queries), and ICP3D::Run reproduced bit for bit."""
+    import os
+    from conftest import GOLDEN
+    gold = dict(np.load(os.path.join(GOLDEN, "bun_icp_config2.npz")))
+    g = pkg.GoICP(1e-5)
+    g.pModel, g.pData = gold["model"], gold["data"]
+    idx, d2 = g.NN(gold["data"])
+    assert np.array_equal(idx, gold["nn_idx"])
+    assert np.array_equal(d2.view(np.uint32), gold["nn_d2"].view(np.uint32))
+    err, R, t, iters = g.ICP(np.eye(3), np.zeros(3), 10000, 1e-9)
+    assert np.float32(err) == gold["icp_err"]
+    assert np.array_equal(R, gold["icp_R"]) and np.array_equal(t, gold["icp_t"])
+    g.close()

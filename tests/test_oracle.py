@@ -115,3 +115,19 @@ def test_golden_runs_file_is_the_survey_known_answers(runs):
     assert r["sse"] == pytest.approx(2.29739285, abs=1e-7) and r["select_calls"] - 3 == 235552
     assert runs["bunny_s0.1_mse5e-4"]["exit_lb"] == pytest.approx(0.796166, abs=1e-6)
     assert runs["bunny_s0.1_mse1e-3_trim0.1"]["sse"] == pytest.approx(1.65017891, abs=1e-7)
+
+
+def test_config2_full_size_nn_and_icp(restated):
+    """BASELINE config 2 at full size (40097 x 40256 points): the survey's known answers -- sum d^2 =
+    4733.98282, FNV-1a-64 of the indices dcfe927c373eaf21, 53 exact-tie queries -- and the ICP result."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "bun_icp_config2.npz")))
+    assert "%016x" % restated.fnv(g["nn_idx"].astype(np.uint32)) == "dcfe927c373eaf21"
+    assert float(g["nn_d2"].astype(np.float64).sum()) == pytest.approx(4733.98282, abs=1e-4)
+    assert float(g["icp_err"]) == pytest.approx(86.54953, abs=1e-4)
+    kd = restated.kd_build(g["model"])
+    idx, d2 = restated.kd_nn(kd, g["data"])
+    assert np.array_equal(idx, g["nn_idx"]) and np.array_equal(bits(d2), bits(g["nn_d2"]))
+    e, R, t, iters, _ = restated.icp_run(kd, g["data"], np.eye(3), np.zeros(3), 10000, 1e-9, 0.0)
+    assert np.float32(e) == g["icp_err"] and np.array_equal(R, g["icp_R"]) and np.array_equal(t, g["icp_t"])
