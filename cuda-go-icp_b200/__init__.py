@@ -269,8 +269,9 @@ class GoICP:
     def Register(self):
         """GoICP::Register (jly_goicp.cpp:569-585); returns optError, fills optR/optT."""
         res = Result()
-        self._check(self.L.goicp_register(self._handle(), C.byref(res)))
-        self.result = res.as_dict()
+        rc = self.L.goicp_register(self._handle(), C.byref(res))
+        self.result = res.as_dict()          # filled even when the call was cancelled
+        self._check(rc)
         self.optR, self.optT, self.optError = self.result["R"], self.result["t"], self.result["sse"]
         self.finished = True
         return self.optError
@@ -342,6 +343,9 @@ class GoICP:
             t = _f32(t).reshape(3)
             self._check(self.L.goicp_dt_score(self._handle(), R.ctypes.data, t.ctypes.data, C.byref(out)))
         return out.value
+
+    def last_result(self):
+        return self.result
 
     def Poll(self):
         s = Snapshot()

@@ -25,10 +25,18 @@ RUNS = {  # name: (model fixture, data fixture, mse, trim)
     "bunny_s0.1_mse5e-4": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "5e-4", "0"),
     "bunny_s0.033_mse1e-3": ("bunny_model_s0.033_seed1234.f32", "bunny_data_s0.033_seed1235.f32", "1e-3", "0"),
     "bunny_s0.1_mse1e-3_trim0.1": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "1e-3", "0.1"),
+    # BASELINE config 4 substitute: rotated_model_spanner -> noisy_flipped_model_spanner, x0.02, subsample 0.02,
+    # fgoicp's translation domain [-1,1]^3 (extra CLI args: S tx ty tz tw)
+    "spanner_s0.02_mse1e-3": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
+    "spanner_s0.02_mse1e-3_trim0.1": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0.1", "300", "-1", "-1", "-1", "2"),
 }
 
 
 def clouds():
+    import importlib
+    pkg = importlib.import_module("cuda-go-icp_b200")     # host loader only (binary PLY); seeded like the TXT fixtures
+    pkg.load_cloud(f"{REFDATA}/artec3d/noisy_flipped_model_spanner.ply", 0.02, 0.02, 1234).tofile(os.path.join(HERE, "spanner_model_noisy_flipped_s0.02_seed1234.f32"))
+    pkg.load_cloud(f"{REFDATA}/artec3d/rotated_model_spanner.ply", 0.02, 0.02, 1235).tofile(os.path.join(HERE, "spanner_data_rotated_s0.02_seed1235.f32"))
     for sub in ("0.1", "0.033"):
         for kind, seed in (("model", 1234), ("data", 1235)):
             out = os.path.join(HERE, f"bunny_{kind}_s{sub}_seed{seed}.f32")
@@ -51,14 +59,16 @@ def parse_run(text):
 
 def runs(from_logs=None):
     out = {}
-    for name, (m, d, mse, trim) in RUNS.items():
+    for name, (m, d, mse, trim, *extra) in RUNS.items():
         if from_logs and os.path.exists(os.path.join(from_logs, name + ".log")):
             text = open(os.path.join(from_logs, name + ".log")).read()
         else:
-            text = subprocess.run([REFBIN, "goicp", os.path.join(HERE, m), os.path.join(HERE, d), mse, trim],
+            text = subprocess.run([REFBIN, "goicp", os.path.join(HERE, m), os.path.join(HERE, d), mse, trim] + list(extra),
                                   check=True, capture_output=True, text=True).stdout
         out[name] = parse_run(text)
         out[name]["model"], out[name]["data"] = m, d
+        if extra:
+            out[name]["trans_cube"] = [float(v) for v in extra[1:5]]
         print(name, out[name]["sse"], out[name]["rot_pops"], out[name]["trans_pops"])
     json.dump(out, open(os.path.join(HERE, "goicp_runs.json"), "w"), indent=1)
 

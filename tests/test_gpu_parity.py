@@ -250,3 +250,19 @@ def test_config2_full_size_nn_and_icp_on_gpu(pkg):
     assert np.float32(err) == gold["icp_err"]
     assert np.array_equal(R, gold["icp_R"]) and np.array_equal(t, gold["icp_t"])
     g.close()
+
+
+@pytest.mark.parametrize("name", ["spanner_s0.02_mse1e-3", "spanner_s0.02_mse1e-3_trim0.1"])
+def test_spanner_noisy_scan_with_and_without_trimming(pkg, runs, name):
+    """BASELINE config 4 substitute: Artec spanner scans (binary PLY, noisy target), fgoicp's translation
+    domain [-1,1]^3, with and without trimming; the reference certifies right after the first ICP."""
+    from conftest import load_cloud
+    gold = runs[name]
+    g = pkg.GoICP(gold["mse"])
+    g.pModel, g.pData = load_cloud(gold["model"]), load_cloud(gold["data"])
+    g.trimFraction = gold["trim"]
+    g.initNodeTrans = gold["trans_cube"]
+    g.BuildDT()
+    g.Register()
+    _check_run(g.result, gold)
+    g.close()
