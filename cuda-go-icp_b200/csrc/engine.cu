@@ -432,7 +432,7 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     rc = ensure_kdtree(h); if (rc) return rc;
     const int num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;     // jly_icp3d.hpp:189-196
     size_t npad = 1; while (npad < (size_t)h->nd) npad <<= 1;
-    CUDA_TRY(h, h->d_icp_q.reserve((size_t)3 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd));
+    CUDA_TRY(h, h->d_icp_q.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd));
     CUDA_TRY(h, h->d_icp_keys.reserve(npad)); CUDA_TRY(h, h->d_icp_stage.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_order.reserve(h->nd));
     IcpWork wk; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p; wk.order = h->d_icp_order.p;
     IcpState st; std::memset(&st, 0, sizeof st);
@@ -455,8 +455,8 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     for (int i = 0; i < 3; i++) out->t[i] = st.t[i];
     out->err = st.err_new; out->iterations = st.iter;
     if (getenv("GOICP_ICP_STATS"))
-        fprintf(stderr, "[icp] iters %d blocks %d cycles: nn %lld wait %lld sort %lld pass1 %lld pass2 %lld acc1 %lld\n", st.iter, blocks,
-                st.dbg[0], st.dbg[1], st.dbg[2], st.dbg[3], st.dbg[4], st.dbg[5]);
+        fprintf(stderr, "[icp] iters %d blocks %d cycles: nn %lld wait %lld sort %lld pass1 %lld pass2 %lld acc1 %lld svd+compose %lld\n", st.iter, blocks,
+                st.dbg[0] & 0xffffffffll, st.dbg[1], st.dbg[2], st.dbg[3], st.dbg[4], st.dbg[5], st.dbg[0] >> 32);
     return GOICP_OK;
 }
 

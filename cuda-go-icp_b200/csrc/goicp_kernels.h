@@ -40,7 +40,7 @@ struct IcpState {           // lives in device memory; written by block 0 of the
     long long dbg[6];       // cycles spent by CTA 0 in: NN, wait, sort, pass 1, pass 2 + SVD, total
 };
 struct IcpWork {            // per-iteration device scratch of the ICP kernel
-    float* q;               // 3*nd transformed data points
+    float* q;               // 8*nd: correspondence rows in query order (model xyz, query xyz, d^2, pad)
     int32_t* nn;            // nd nearest model indices
     float* d2;              // nd squared distances
     unsigned long long* keys;   // nd sort keys (d2 bits << 32 | point index)

@@ -393,7 +393,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
     __syncthreads();
 
-    long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0; const long long c_begin = clock64();
+    long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0, c_svd = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
         long long c0 = clock64();
         float R[9], t[3];
@@ -437,9 +437,12 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     }
                     if (valid) {
                         if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1);   // near tie: reference traversal order decides
-                        wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
                         wk.nn[i] = I1; wk.d2[i] = D1;
                         wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
+                        // correspondence row (model point, query, d^2) in query order
+                        float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                        row[0] = make_float4(__ldg(kd.model + 3 * I1), __ldg(kd.model + 3 * I1 + 1), __ldg(kd.model + 3 * I1 + 2), qx);
+                        row[1] = make_float4(qy, qz, D1, 0.0f);
                     }
                 }
                 __syncthreads();
@@ -452,9 +455,11 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
                 float d2;
                 const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
-                wk.q[3 * i] = qx; wk.q[3 * i + 1] = qy; wk.q[3 * i + 2] = qz;
                 wk.nn[i] = id; wk.d2[i] = d2;
                 wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+                float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                row[0] = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), qx);
+                row[1] = make_float4(qy, qz, d2, 0.0f);
             }
         }
         long long c1 = clock64(); c_nn += c1 - c0;
@@ -498,13 +503,24 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             for (int base = 0; base < num; base += step) {
                 const int cnt = min(step, num - base);
                 float* rows = sstage ? sstage : chunk;
-                for (int rr = threadIdx.x; rr < cnt; rr += blockDim.x) {
-                    const int i = __ldcg(wk.order + base + rr);
-                    const int id = __ldcg(wk.nn + i);
-                    float4 lo = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), __ldcg(wk.q + 3 * i));
-                    float4 hi = make_float4(__ldcg(wk.q + 3 * i + 1), __ldcg(wk.q + 3 * i + 2), __ldcg(wk.d2 + i), 0.0f);
-                    reinterpret_cast<float4*>(rows)[2 * rr] = lo; reinterpret_cast<float4*>(rows)[2 * rr + 1] = hi;
-                    if (!sstage) { reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi; }
+                // two dependent round trips (order -> row), issued 8 rows at a time per thread
+                for (int r0 = threadIdx.x; r0 < cnt; r0 += 8 * blockDim.x) {
+                    int ii[8]; float4 lo[8], hi[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { const int rr = r0 + u * blockDim.x; ii[u] = rr < cnt ? __ldcg(wk.order + base + rr) : 0; }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float4* row = reinterpret_cast<const float4*>(wk.q) + 2 * (size_t)ii[u];
+                        lo[u] = __ldcg(row); hi[u] = __ldcg(row + 1);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int rr = r0 + u * blockDim.x;
+                        if (rr < cnt) {
+                            reinterpret_cast<float4*>(rows)[2 * rr] = lo[u]; reinterpret_cast<float4*>(rows)[2 * rr + 1] = hi[u];
+                            if (!sstage) { reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo[u]; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi[u]; }
+                        }
+                    }
                 }
                 __syncthreads();
                 const long long ca0 = clock64();
@@ -557,24 +573,34 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                         __syncthreads();
                     }
                     if (warp == 0 && lane < 9) {
-                        // products are formed 16 at a time (independent), then added in order
+                        // the products of the next 8 rows are formed in the shadow of the dependent adds of these 8
+                        const float* ra = rows + 3 + a; const float* rb = rows + b;
+                        float pr[8];
                         int rr = 0;
-                        for (; rr + 16 <= cnt; rr += 16) {
-                            float pr[16];
+                        if (cnt >= 8) {
 #pragma unroll
-                            for (int u = 0; u < 16; u++) pr[u] = __fmul_rn(__fsub_rn(rows[8 * (rr + u) + 3 + a], mud), __fsub_rn(rows[8 * (rr + u) + b], mum));
+                            for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(__fsub_rn(ra[8 * u], mud), __fsub_rn(rb[8 * u], mum));
+                            for (rr = 8; rr + 8 <= cnt; rr += 8) {
+                                float nx[8];
 #pragma unroll
-                            for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, pr[u]);
+                                for (int u = 0; u < 8; u++) {
+                                    nx[u] = __fmul_rn(__fsub_rn(ra[8 * (rr + u)], mud), __fsub_rn(rb[8 * (rr + u)], mum));
+                                    acc = __fadd_rn(acc, pr[u]);
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; u++) pr[u] = nx[u];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, pr[u]);
                         }
-                        for (; rr < cnt; rr++)
-                            acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(rows[8 * rr + 3 + a], mud), __fsub_rn(rows[8 * rr + b], mum)));
+                        for (; rr < cnt; rr++) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(ra[8 * rr], mud), __fsub_rn(rb[8 * rr], mum)));
                     }
                     if (!sstage) __syncthreads();
                 }
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;
                     __syncwarp();
-                    if (lane == 0) icp_update(st, sh_H);
+                    if (lane == 0) { const long long cu0 = clock64(); icp_update(st, sh_H); c_wait += 0; c_svd += clock64() - cu0; }
                 }
             }
             c1 = clock64(); c_p2 += c1 - c0;
@@ -584,7 +610,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         if (vst->converged) break;
         if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; st->dbg[0] = c_nn + (c_svd << 32); }
 }
 
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s)
