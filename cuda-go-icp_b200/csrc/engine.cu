@@ -267,7 +267,9 @@ InnerPlan plan_inner(const goicp_handle* h)
     // Cluster size: one expansion step costs 8*Nd scattered lookups and an SM retires ~1 per clock,
     // so split each inner BnB over as many SMs as keeps a slice worth a CTA (>= ~256 points).
     int cl = h->p.cluster_size;
-    if (cl <= 0) { cl = 1; while (cl < 8 && h->nd / (cl * 2) >= 192) cl *= 2; }
+    // (measured on the bunny config, Nd = 3019: clusters of 4 beat 8 and 16 -- beyond ~750 points per CTA the
+    // extra barrier/DSMEM traffic costs more than the shorter gather saves)
+    if (cl <= 0) { cl = 1; while (cl < 16 && h->nd / (cl * 2) >= 512) cl *= 2; }
     if (cl > 16) cl = 16;
     p.cluster = cl;
     // two CTAs per SM: each may take half of the SM's shared memory minus its static part and the 1 KB the driver reserves per CTA
@@ -298,9 +300,9 @@ int ensure_task_buffers(goicp_handle* h, size_t n)
         h->h_results_n = cap; h->h_tasks_n = cap;
     }
     // spill region: one slab per concurrently launched CTA (grid == n)
-    const int spill_cap = 1 << 16;        // 65536 entries (1 MiB) per task beyond the shared-memory part
+    const int spill_cap = 1 << 16;        // 65536 entries (1 MiB) per task beyond the ~4000 kept in shared memory; overflow is reported, not hidden
     if ((size_t)h->spill_slots < n || h->spill_cap != spill_cap) {
-        size_t slots = std::max<size_t>(n, 512);
+        size_t slots = std::max<size_t>(n, 640);
         CUDA_TRY(h, h->d_spill.reserve(slots * (size_t)spill_cap));
         h->spill_slots = (int)slots; h->spill_cap = spill_cap;
     }
@@ -791,7 +793,8 @@ int goicp_register(goicp_handle* h, goicp_result* out)
 
     std::unordered_map<CubeKey, CubeEval, CubeKeyHash> cache;
     long epoch = 0;
-    int spec = h->p.spec_cubes > 0 ? h->p.spec_cubes : std::max(1, (2 * h->sm_count) / 16);
+    // default speculation width: ~4 SMs' worth of clusters per cube (36 cubes = 576 inner BnBs per round on 148 SMs)
+    int spec = h->p.spec_cubes > 0 ? h->p.spec_cubes : std::max(1, h->sm_count / 4);
     if (h->xchg && h->p.world_size > 1) spec *= h->p.world_size;
 
     // Evaluate `first` (must be evaluated) plus the best not-yet-evaluated queue entries.
