@@ -85,9 +85,10 @@ __device__ __forceinline__ Vox v4_to(const V4& a) { Vox r; r.v = (short)a.v; r.h
 template <int IV, int IH, int ID>
 __device__ __forceinline__ void consider(V4& best, const V4 s)
 {
-    if (s.n >= kInf) return;                        // unset source: scores ~56755 > 32767 in the reference, never chosen
+    // unset source (n == kInf): scores ~56755 > 32767 in the reference and is never chosen; kInf + increments stays > any real norm
     const int n = s.n + 2 * (IV * s.v + IH * s.h + ID * s.d) + (IV + IH + ID);
-    if (n < best.n) { best.n = n; best.v = s.v + IV; best.h = s.h + IH; best.d = s.d + ID; }
+    const bool take = (s.n < kInf) & (n < best.n);
+    best.n = take ? n : best.n; best.v = take ? s.v + IV : best.v; best.h = take ? s.h + IH : best.h; best.d = take ? s.d + ID : best.d;
 }
 
 // Row-scan kinds (mask functions of jly_3ddt.cpp and where the running-scan entry sits in the
@@ -98,13 +99,23 @@ __device__ __forceinline__ void consider(V4& best, const V4 s)
 // voxel with a strictly smaller increment; they are omitted.
 enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 
+// All row buffers live in one dynamic shared array; the layout is a set of byte offsets so that
+// every access is derived from the __shared__ symbol (LDS/STS, not generic loads).
+extern __shared__ __align__(16) unsigned char dt_smem[];
 struct RowSmem {
-    V4* xs[3];           // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
-    V4* prev;            // final previous row of the current slice in this pass, padded
-    V4* own[2];          // per scan position k: the voxel's own (recurrence-free) result; double-buffered across the two scans of a row
-    int* T[2];           // the squared norm the recurrence must beat at k
-    short* run_start; short* run_end; unsigned char* accept;
-    unsigned* wmask;
+    int o_xs[3];         // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
+    int o_prev;          // final previous row of the current slice in this pass, padded
+    int o_own[2];        // per scan position k: the voxel's own (recurrence-free) result; double-buffered across the two scans of a row
+    int o_T[2];          // the squared norm the recurrence must beat at k
+    int o_run_start, o_run_end, o_accept, o_wmask;
+    __device__ __forceinline__ V4* xs(int r) const { return reinterpret_cast<V4*>(dt_smem + o_xs[r]); }
+    __device__ __forceinline__ V4* prev() const { return reinterpret_cast<V4*>(dt_smem + o_prev); }
+    __device__ __forceinline__ V4* own(int b) const { return reinterpret_cast<V4*>(dt_smem + o_own[b]); }
+    __device__ __forceinline__ int* T(int b) const { return reinterpret_cast<int*>(dt_smem + o_T[b]); }
+    __device__ __forceinline__ short* run_start() const { return reinterpret_cast<short*>(dt_smem + o_run_start); }
+    __device__ __forceinline__ short* run_end() const { return reinterpret_cast<short*>(dt_smem + o_run_end); }
+    __device__ __forceinline__ unsigned char* accept() const { return dt_smem + o_accept; }
+    __device__ __forceinline__ unsigned* wmask() const { return reinterpret_cast<unsigned*>(dt_smem + o_wmask); }
 };
 
 #ifdef GOICP_DT_INSTRUMENT
@@ -126,26 +137,26 @@ __device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4
     const bool active = z < S;
     constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;     // +1: recurrence reads z-1
     const int k = dir > 0 ? z : S - 1 - z;                                      // position in scan order
-    V4* own = sh.own[buf]; int* T = sh.T[buf];
+    V4* own = sh.own(buf); int* T = sh.T(buf);
     V4 P = v4_unset(), Q = v4_unset();
     V4 out = P; int Tk = kInf;
     if (active) {
         const int zp = z + 1;                                                    // padded index
         if (KIND == F1 || KIND == B1) {
-            const V4* r0 = sh.xs[(y - 1 + 3) % 3]; const V4* r1 = sh.xs[(y + 3) % 3]; const V4* r2 = sh.xs[(y + 1 + 3) % 3];
+            const V4* r0 = sh.xs((y - 1 + 3) % 3); const V4* r1 = sh.xs((y + 3) % 3); const V4* r2 = sh.xs((y + 1 + 3) % 3);
             consider<1, 1, 1>(P, r0[zp - 1]); consider<1, 1, 0>(P, r0[zp]); consider<1, 1, 1>(P, r0[zp + 1]);
             consider<1, 0, 1>(P, r1[zp - 1]); consider<1, 0, 0>(P, r1[zp]); consider<1, 0, 1>(P, r1[zp + 1]);
             consider<1, 1, 1>(P, r2[zp - 1]); consider<1, 1, 0>(P, r2[zp]); consider<1, 1, 1>(P, r2[zp + 1]);
         }
         if (KIND == F1 || KIND == B3) {              // previous row y-1, then self; recurrence comes last
-            consider<0, 1, 1>(P, sh.prev[zp - 1]);
-            consider<0, 1, 0>(P, sh.prev[zp]);
-            consider<0, 1, 1>(P, sh.prev[zp + 1]);
+            consider<0, 1, 1>(P, sh.prev()[zp - 1]);
+            consider<0, 1, 0>(P, sh.prev()[zp]);
+            consider<0, 1, 1>(P, sh.prev()[zp + 1]);
             consider<0, 0, 0>(P, self);
         } else if (KIND == F3 || KIND == B1) {       // recurrence first, then (z,y+1), self, (z-1,y+1)
-            consider<0, 1, 0>(Q, sh.prev[zp]);
+            consider<0, 1, 0>(Q, sh.prev()[zp]);
             consider<0, 0, 0>(Q, self);
-            consider<0, 1, 1>(Q, sh.prev[zp - 1]);
+            consider<0, 1, 1>(Q, sh.prev()[zp - 1]);
         } else {                                     // pure chains: recurrence first, then self
             consider<0, 0, 0>(Q, self);
         }
@@ -169,13 +180,13 @@ __device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4
         }
     }
     const unsigned ballot = __ballot_sync(0xffffffffu, win);
-    if ((threadIdx.x & 31) == 0) sh.wmask[threadIdx.x >> 5] = ballot;
-    if (last_of_row && active) sh.prev[z + 1] = out;         // optimistic: valid unless a run covers z
+    if ((threadIdx.x & 31) == 0) sh.wmask()[threadIdx.x >> 5] = ballot;
+    if (last_of_row && active) sh.prev()[z + 1] = out;       // optimistic: valid unless a run covers z
     const int any = __syncthreads_or(win);
     DT_STAT(0, threadIdx.x == 0); DT_STAT(1, threadIdx.x == 0 && any);
     had_runs = any != 0;
     if (any) {
-        if (active) sh.run_start[k] = -1;
+        if (active) sh.run_start()[k] = -1;
         if (win) {                                   // extent of the run that starts at k-1
             int n = nc, d = o.d + 1, pos = k + 1;
             while (pos < S) {
@@ -185,7 +196,7 @@ __device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4
                 if (n == w.n && w.v == o.v && w.h == o.h && w.d == d) break;
                 pos++;
             }
-            sh.run_end[k] = (short)pos;
+            sh.run_end()[k] = (short)pos;
             DT_STAT(2, 1); DT_STAT(3, pos - k);
         }
         __syncthreads();
@@ -195,28 +206,28 @@ __device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4
             const int nw = (S + 31) / 32;
             if (dir > 0) {
                 for (int w = 0; w < nw; w++) {
-                    unsigned m = sh.wmask[w];
+                    unsigned m = sh.wmask()[w];
                     while (m) { const int b = __ffs(m) - 1; m &= m - 1; const int kk = w * 32 + b;      // kk == z
-                        const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
+                        const bool ok = kk - 1 >= last_end; sh.accept()[kk] = ok; if (ok) last_end = sh.run_end()[kk]; }
                 }
             } else {
                 for (int w = nw - 1; w >= 0; w--) {
-                    unsigned m = sh.wmask[w];
+                    unsigned m = sh.wmask()[w];
                     while (m) { const int b = 31 - __clz(m); m &= ~(1u << b); const int kk = S - 1 - (w * 32 + b);   // thread z -> k
-                        const bool ok = kk - 1 >= last_end; sh.accept[kk] = ok; if (ok) last_end = sh.run_end[kk]; }
+                        const bool ok = kk - 1 >= last_end; sh.accept()[kk] = ok; if (ok) last_end = sh.run_end()[kk]; }
                 }
             }
         }
         __syncthreads();
-        if (win && sh.accept[k]) { const int e = sh.run_end[k]; for (int pos = k; pos < e; pos++) sh.run_start[pos] = (short)(k - 1); }
+        if (win && sh.accept()[k]) { const int e = sh.run_end()[k]; for (int pos = k; pos < e; pos++) sh.run_start()[pos] = (short)(k - 1); }
         __syncthreads();
         if (active) {
-            const int rs = sh.run_start[k];
+            const int rs = sh.run_start()[k];
             if (rs >= 0) {
                 const V4 s0 = own[rs];
                 const int m = k - rs;
                 out.v = s0.v; out.h = s0.h; out.d = s0.d + m; out.n = s0.n + 2 * s0.d * m + m * m;
-                if (last_of_row) sh.prev[z + 1] = out;
+                if (last_of_row) sh.prev()[z + 1] = out;
             }
         }
     }
@@ -235,8 +246,8 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem
     auto gload = [&](int xx, int yy) -> Vox { return (active && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset_g; };
     // prime the shared rows: adjacent-slice rows y0-1, y0, y0+1 ; previous row of this slice = outside
     if (active) {
-        for (int r = -1; r <= 1; r++) sh.xs[(y0 + r + 3) % 3][z + 1] = use_xs ? v4_from(gload(xs, y0 + r)) : v4_unset();
-        sh.prev[z + 1] = v4_unset();
+        for (int r = -1; r <= 1; r++) sh.xs((y0 + r + 3) % 3)[z + 1] = use_xs ? v4_from(gload(xs, y0 + r)) : v4_unset();
+        sh.prev()[z + 1] = v4_unset();
     }
     Vox self_next = gload(x, y0);
     Vox xs_next = use_xs ? gload(xs, y0 + 2 * ydir) : unset_g;
@@ -257,7 +268,7 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem
         V4 v = row_scan<K1>(sh, S, y, self, 0, false, runs1);
         // the adjacent-slice row that leaves the 3-row window is replaced by the incoming one; nobody
         // reads that slot again in this row, and the next row's reads come after >= 2 barriers
-        if ((K1 == F1 || K1 == B1) && active) sh.xs[(y + 2 * ydir + 3 + 3) % 3][z + 1] = xs_row;
+        if ((K1 == F1 || K1 == B1) && active) sh.xs((y + 2 * ydir + 3 + 3) % 3)[z + 1] = xs_row;
         v = row_scan<K2>(sh, S, y, v, 1, true, runs2);
         if (active) G[((size_t)x * S + y) * S + z] = v4_to(v);
         if (runs2) __syncthreads();                         // prev[] was patched after the deciding barrier
@@ -268,25 +279,24 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem
 __global__ void __launch_bounds__(kMaxS)
 dt_propagate_kernel(Vox* G, int S)
 {
-    extern __shared__ __align__(16) unsigned char dt_smem[];
     RowSmem sh;
     {
-        unsigned char* p = dt_smem;
-        const size_t row = (size_t)(S + 2) * sizeof(V4);
-        for (int r = 0; r < 3; r++) { sh.xs[r] = reinterpret_cast<V4*>(p); p += row; }
-        sh.prev = reinterpret_cast<V4*>(p); p += row;
-        for (int b = 0; b < 2; b++) { sh.own[b] = reinterpret_cast<V4*>(p); p += (size_t)S * sizeof(V4); }
-        for (int b = 0; b < 2; b++) { sh.T[b] = reinterpret_cast<int*>(p); p += (size_t)S * sizeof(int); }
-        sh.wmask = reinterpret_cast<unsigned*>(p); p += 32 * sizeof(unsigned);
-        sh.run_start = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
-        sh.run_end = reinterpret_cast<short*>(p); p += (size_t)(S + 2) / 2 * 2 * sizeof(short);
-        sh.accept = p;
+        int p = 0;
+        const int row = (S + 2) * (int)sizeof(V4);
+        for (int r = 0; r < 3; r++) { sh.o_xs[r] = p; p += row; }
+        sh.o_prev = p; p += row;
+        for (int b = 0; b < 2; b++) { sh.o_own[b] = p; p += S * (int)sizeof(V4); }
+        for (int b = 0; b < 2; b++) { sh.o_T[b] = p; p += S * (int)sizeof(int); }
+        sh.o_wmask = p; p += 32 * (int)sizeof(unsigned);
+        sh.o_run_start = p; p += (S + 2) / 2 * 2 * (int)sizeof(short);
+        sh.o_run_end = p; p += (S + 2) / 2 * 2 * (int)sizeof(short);
+        sh.o_accept = p;
     }
     // pads of the shared rows stay "unset" for the whole kernel
     if (threadIdx.x == 0) {
         const V4 u = v4_unset();
-        for (int r = 0; r < 3; r++) { sh.xs[r][0] = u; sh.xs[r][S + 1] = u; }
-        sh.prev[0] = u; sh.prev[S + 1] = u;
+        for (int r = 0; r < 3; r++) { sh.xs(r)[0] = u; sh.xs(r)[S + 1] = u; }
+        sh.prev()[0] = u; sh.prev()[S + 1] = u;
     }
     __syncthreads();
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
