@@ -59,36 +59,61 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
 }
 
 // ---- the sequential propagation ------------------------------------------------------------
-// One persistent CTA, thread z owns column z of every row it visits.  Shared memory holds the
-// three relevant rows of the adjacent slice and the previous row of the current slice (padded
-// with "unset" voxels so that the reference's bounds tests need no branches); every global
-// access is a thread's own column, prefetched one row ahead, so HBM/L2 latency stays off the
-// critical path.  A row scan is resolved as
-//   own_z   = first minimum (mask order) of all candidates that do not depend on the scan,
-//   T_z     = the squared norm the running-scan candidate must beat at z (ties by mask order),
-//   chain   = runs: a run starts at s when (own_s + (0,0,1)) beats T_{s+1} and lives while
-//             own_s + (0,0,k) beats T_{s+k}; where it dies the voxel falls back to own.
-// Runs are found in parallel (one thread per possible run head, first wins are exactly the
-// "static" wins against the neighbour's own value), then the few heads are filtered in scan
-// order so that a head inside an earlier run is ignored -- the sequential semantics exactly.
+// One persistent CTA.  A row scan of the reference is the recurrence
+//   state_k = (state_{k-1} + (0,0,1) beats T_k) ? state_{k-1} + (0,0,1) : own_k
+// where own_k is the first minimum (mask order) of all candidates that do not depend on the
+// running scan and T_k the squared norm the running-scan candidate must beat at k (ties by mask
+// order).  own/T of a whole row are computed in parallel; the recurrence has a unique solution,
+// so any fixed point of the parallel update "every voxel re-evaluates the rule against its
+// predecessor's current state" IS the sequential result, and starting from state = own that
+// iteration converges in (longest run + 1) steps -- runs are short (1.3 voxels on average on the
+// bunny), most rows have none.
+// Mapping: each warp owns 30 consecutive voxels of the row; lanes 0 and 31 shadow the boundary
+// voxels of the neighbouring warps, so a warp resolves both scans of a row with shuffles only,
+// speculating that no run crosses into it.  The owner of a boundary voxel knows whether that
+// held (its state differs from its own value); the flags are OR-ed by the single barrier of the
+// row, which also publishes the row to the neighbours.  Rows where the speculation failed are
+// redone by the same fixed-point iteration across the CTA through shared memory.
+// State the row recurrence needs lives in registers: the final previous row at z-1, z, z+1 and
+// the folded candidates of the adjacent slice (three rows x three z-neighbours, folded per row
+// into A (row offset +-1) and B (same row) when a row enters the window, one row ahead of its
+// use).  Every global access is a thread's own column, prefetched one row ahead.
 // Working representation on chip: 32-bit components plus the squared norm, 16 bytes per voxel
 // (one LDS.128), so that a candidate costs a handful of integer instructions:
 //   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1}.
 // Global memory keeps the compact 8-byte (short) form.
 struct __align__(16) V4 { int v, h, d, n; };
+constexpr int kOwned = 30;             // voxels owned per warp
+constexpr int kMaxRefS = 32 * kOwned;  // 1024 threads
+constexpr int kDepth = 4;              // rows of global-load lookahead held in registers
 
 __device__ __forceinline__ V4 v4_unset() { V4 u; u.v = u.h = u.d = 32767; u.n = kInf; return u; }
 __device__ __forceinline__ V4 v4_from(const Vox& a) { V4 r; r.v = a.v; r.h = a.h; r.d = a.d; r.n = vox_unset(a) ? kInf : vox_norm2(a); return r; }
 __device__ __forceinline__ Vox v4_to(const V4& a) { Vox r; r.v = (short)a.v; r.h = (short)a.h; r.d = (short)a.d; r.pad = 0; return r; }
+__device__ __forceinline__ bool v4_differs(const V4& a, const V4& b) { return (a.v != b.v) | (a.h != b.h) | (a.d != b.d); }
 
 // candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order
 template <int IV, int IH, int ID>
 __device__ __forceinline__ void consider(V4& best, const V4 s)
 {
-    // unset source (n == kInf): scores ~56755 > 32767 in the reference and is never chosen; kInf + increments stays > any real norm
+    // unset source (n == kInf): scores ~56755 > 32767 in the reference and is never chosen
     const int n = s.n + 2 * (IV * s.v + IH * s.h + ID * s.d) + (IV + IH + ID);
     const bool take = (s.n < kInf) & (n < best.n);
     best.n = take ? n : best.n; best.v = take ? s.v + IV : best.v; best.h = take ? s.h + IH : best.h; best.d = take ? s.d + ID : best.d;
+}
+// fold an already-incremented candidate (first minimum in order)
+__device__ __forceinline__ void fold(V4& best, const V4 c)
+{
+    const bool take = c.n < best.n;
+    best.n = take ? c.n : best.n; best.v = take ? c.v : best.v; best.h = take ? c.h : best.h; best.d = take ? c.d : best.d;
+}
+// the recurrence rule at one voxel: predecessor state o, own result, threshold T
+__device__ __forceinline__ V4 chain_rule(const V4 o, const V4 own, int T)
+{
+    const int nc = o.n + 2 * o.d + 1;
+    const bool take = (o.n < kInf) & (nc < T);
+    V4 r; r.v = take ? o.v : own.v; r.h = take ? o.h : own.h; r.d = take ? o.d + 1 : own.d; r.n = take ? nc : own.n;
+    return r;
 }
 
 // Row-scan kinds (mask functions of jly_3ddt.cpp and where the running-scan entry sits in the
@@ -99,24 +124,17 @@ __device__ __forceinline__ void consider(V4& best, const V4 s)
 // voxel with a strictly smaller increment; they are omitted.
 enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 
-// All row buffers live in one dynamic shared array; the layout is a set of byte offsets so that
-// every access is derived from the __shared__ symbol (LDS/STS, not generic loads).
+// Row buffers: voxel z sits at index z+2, two "unset" pads on each side (a shadow lane reads the
+// neighbour of a voxel one outside the row).  `fin` and `xrow` alternate by row parity: a row is
+// written before the row's barrier and read after it, the next row writes the other copy.
 extern __shared__ __align__(16) unsigned char dt_smem[];
 struct RowSmem {
-    int o_xs[3];         // rows (y-1, y, y+1) % 3 of the adjacent slice, padded: index z+1
-    int o_prev;          // final previous row of the current slice in this pass, padded
-    int o_own[2];        // per scan position k: the voxel's own (recurrence-free) result; double-buffered across the two scans of a row
-    int o_T[2];          // the squared norm the recurrence must beat at k
-    int o_run_start, o_run_end, o_accept, o_wmask;
-    __device__ __forceinline__ V4* xs(int r) const { return reinterpret_cast<V4*>(dt_smem + o_xs[r]); }
-    __device__ __forceinline__ V4* prev() const { return reinterpret_cast<V4*>(dt_smem + o_prev); }
-    __device__ __forceinline__ V4* own(int b) const { return reinterpret_cast<V4*>(dt_smem + o_own[b]); }
-    __device__ __forceinline__ int* T(int b) const { return reinterpret_cast<int*>(dt_smem + o_T[b]); }
-    __device__ __forceinline__ short* run_start() const { return reinterpret_cast<short*>(dt_smem + o_run_start); }
-    __device__ __forceinline__ short* run_end() const { return reinterpret_cast<short*>(dt_smem + o_run_end); }
-    __device__ __forceinline__ unsigned char* accept() const { return dt_smem + o_accept; }
-    __device__ __forceinline__ unsigned* wmask() const { return reinterpret_cast<unsigned*>(dt_smem + o_wmask); }
+    int stride;          // bytes of one padded row
+    __device__ __forceinline__ V4* fin(int par) const { return reinterpret_cast<V4*>(dt_smem + par * stride); }
+    __device__ __forceinline__ V4* xrow(int par) const { return reinterpret_cast<V4*>(dt_smem + (2 + par) * stride); }
+    __device__ __forceinline__ V4* xchg() const { return reinterpret_cast<V4*>(dt_smem + 4 * stride); }
 };
+static size_t dt_propagate_smem(int S) { return 5 * (size_t)(S + 4) * sizeof(V4); }
 
 #ifdef GOICP_DT_INSTRUMENT
 __device__ unsigned long long g_dt_stats_buf[8];
@@ -125,194 +143,415 @@ __device__ unsigned long long g_dt_stats_buf[8];
 #define DT_STAT(i, v) ((void)0)
 #endif
 
-// One row scan.  `buf` selects the record buffer (0 for the first scan of a row, 1 for the second)
-// so that the second scan may start writing its records while slow threads still read the first's.
-// If last_of_row the result is also stored as the row's entry of sh.prev -- optimistically BEFORE
-// the barrier that decides whether any run exists, so the common run-free row needs no extra
-// barrier; rows with runs rewrite it afterwards.
-template <int KIND>
-__device__ __forceinline__ V4 row_scan(const RowSmem& sh, int S, int y, const V4 self, int buf, bool last_of_row, bool& had_runs)
+// One scan resolved inside a warp (DIR = +1: the predecessor is lane-1).  The lane at the upstream
+// end has no predecessor in the warp and keeps its own value -- the speculation.
+template <int DIR>
+__device__ __forceinline__ V4 warp_resolve(const V4 own, const int T, const int lane)
 {
-    const int z = threadIdx.x;
-    const bool active = z < S;
-    constexpr int dir = (KIND == F1 || KIND == B3 || KIND == C_UP) ? +1 : -1;     // +1: recurrence reads z-1
-    const int k = dir > 0 ? z : S - 1 - z;                                      // position in scan order
-    V4* own = sh.own(buf); int* T = sh.T(buf);
-    V4 P = v4_unset(), Q = v4_unset();
-    V4 out = P; int Tk = kInf;
-    if (active) {
-        const int zp = z + 1;                                                    // padded index
-        if (KIND == F1 || KIND == B1) {
-            const V4* r0 = sh.xs((y - 1 + 3) % 3); const V4* r1 = sh.xs((y + 3) % 3); const V4* r2 = sh.xs((y + 1 + 3) % 3);
-            consider<1, 1, 1>(P, r0[zp - 1]); consider<1, 1, 0>(P, r0[zp]); consider<1, 1, 1>(P, r0[zp + 1]);
-            consider<1, 0, 1>(P, r1[zp - 1]); consider<1, 0, 0>(P, r1[zp]); consider<1, 0, 1>(P, r1[zp + 1]);
-            consider<1, 1, 1>(P, r2[zp - 1]); consider<1, 1, 0>(P, r2[zp]); consider<1, 1, 1>(P, r2[zp + 1]);
-        }
-        if (KIND == F1 || KIND == B3) {              // previous row y-1, then self; recurrence comes last
-            consider<0, 1, 1>(P, sh.prev()[zp - 1]);
-            consider<0, 1, 0>(P, sh.prev()[zp]);
-            consider<0, 1, 1>(P, sh.prev()[zp + 1]);
-            consider<0, 0, 0>(P, self);
-        } else if (KIND == F3 || KIND == B1) {       // recurrence first, then (z,y+1), self, (z-1,y+1)
-            consider<0, 1, 0>(Q, sh.prev()[zp]);
-            consider<0, 0, 0>(Q, self);
-            consider<0, 1, 1>(Q, sh.prev()[zp - 1]);
-        } else {                                     // pure chains: recurrence first, then self
-            consider<0, 0, 0>(Q, self);
-        }
-        out = P.n <= Q.n ? P : Q;
-        Tk = min(P.n, Q.n + 1);                      // recurrence wins iff nc < nP and nc <= nQ
-        own[k] = out; T[k] = Tk;
+    const unsigned full = 0xffffffffu;
+    const bool has_pred = DIR > 0 ? lane > 0 : lane < 31;
+    V4 st = own;
+    while (true) {
+        // v,h,d < 2^15: two shuffles carry the state, the norm is recomputed
+        const unsigned p0 = (unsigned)st.v | ((unsigned)st.h << 16);
+        const unsigned q0 = DIR > 0 ? __shfl_up_sync(full, p0, 1) : __shfl_down_sync(full, p0, 1);
+        const int od = DIR > 0 ? __shfl_up_sync(full, st.d, 1) : __shfl_down_sync(full, st.d, 1);
+        const int ov = (int)(q0 & 0xffffu), oh = (int)(q0 >> 16);
+        const int nc = ov * ov + oh * oh + (od + 1) * (od + 1);
+        const bool take = has_pred & (ov != 32767) & (nc < T);
+        V4 nw; nw.v = take ? ov : own.v; nw.h = take ? oh : own.h; nw.d = take ? od + 1 : own.d; nw.n = take ? nc : own.n;
+        const bool changed = v4_differs(nw, st);
+        st = nw;
+        if (!__any_sync(full, changed)) break;
     }
-    __syncthreads();
-    // A run can only begin with a win against the neighbour's OWN value.  A "win" whose vector is
-    // identical to the voxel's own result changes nothing (state == own either way) and is not a
-    // head; likewise a run that arrives at a voxel carrying exactly the vector the voxel would
-    // hold anyway simply ends there.  Most recurrence wins are such ties (the chain entry precedes
-    // `self` in four of the six masks), so real heads are few and runs short.
-    int win = 0, nc = 0;
-    V4 o = out;
-    if (active && k >= 1) {
-        o = own[k - 1];
-        if (o.n < kInf) {
-            nc = o.n + 2 * o.d + 1;
-            win = (nc < Tk) && !(o.v == out.v && o.h == out.h && o.d + 1 == out.d);
-        }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, win);
-    if ((threadIdx.x & 31) == 0) sh.wmask()[threadIdx.x >> 5] = ballot;
-    if (last_of_row && active) sh.prev()[z + 1] = out;       // optimistic: valid unless a run covers z
-    const int any = __syncthreads_or(win);
-    DT_STAT(0, threadIdx.x == 0); DT_STAT(1, threadIdx.x == 0 && any);
-    had_runs = any != 0;
-    if (any) {
-        if (active) sh.run_start()[k] = -1;
-        if (win) {                                   // extent of the run that starts at k-1
-            int n = nc, d = o.d + 1, pos = k + 1;
-            while (pos < S) {
-                n += 2 * d + 1; d++;
-                if (!(n < T[pos])) break;
-                const V4 w = own[pos];
-                if (n == w.n && w.v == o.v && w.h == o.h && w.d == d) break;
-                pos++;
-            }
-            sh.run_end()[k] = (short)pos;
-            DT_STAT(2, 1); DT_STAT(3, pos - k);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // heads in scan order; a head whose start lies inside an accepted run is void
-            int last_end = -1;
-            const int nw = (S + 31) / 32;
-            if (dir > 0) {
-                for (int w = 0; w < nw; w++) {
-                    unsigned m = sh.wmask()[w];
-                    while (m) { const int b = __ffs(m) - 1; m &= m - 1; const int kk = w * 32 + b;      // kk == z
-                        const bool ok = kk - 1 >= last_end; sh.accept()[kk] = ok; if (ok) last_end = sh.run_end()[kk]; }
-                }
-            } else {
-                for (int w = nw - 1; w >= 0; w--) {
-                    unsigned m = sh.wmask()[w];
-                    while (m) { const int b = 31 - __clz(m); m &= ~(1u << b); const int kk = S - 1 - (w * 32 + b);   // thread z -> k
-                        const bool ok = kk - 1 >= last_end; sh.accept()[kk] = ok; if (ok) last_end = sh.run_end()[kk]; }
-                }
-            }
-        }
-        __syncthreads();
-        if (win && sh.accept()[k]) { const int e = sh.run_end()[k]; for (int pos = k; pos < e; pos++) sh.run_start()[pos] = (short)(k - 1); }
-        __syncthreads();
-        if (active) {
-            const int rs = sh.run_start()[k];
-            if (rs >= 0) {
-                const V4 s0 = own[rs];
-                const int m = k - rs;
-                out.v = s0.v; out.h = s0.h; out.d = s0.d + m; out.n = s0.n + 2 * s0.d * m + m * m;
-                if (last_of_row) sh.prev()[z + 1] = out;
-            }
-        }
-    }
-    return out;
+    return st;
 }
 
-// one pass over the rows of slice x: K1 then K2 on every row, rows in direction ydir
-template <int K1, int K2>
-__device__ void slice_pass(Vox* G, int S, int x, int xs, int ydir, const RowSmem& sh)
+// The same fixed-point iteration across the whole row through shared memory (collective).
+template <int DIR>
+__device__ __noinline__ V4 block_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z)
 {
-    const int z = threadIdx.x;
-    const bool active = z < S;
-    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
-    const bool use_xs = (K1 == F1 || K1 == B1) && xs >= 0 && xs < S;
-    const int y0 = ydir > 0 ? 0 : S - 1;
-    auto gload = [&](int xx, int yy) -> Vox { return (active && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset_g; };
-    // prime the shared rows: adjacent-slice rows y0-1, y0, y0+1 ; previous row of this slice = outside
-    if (active) {
-        for (int r = -1; r <= 1; r++) sh.xs((y0 + r + 3) % 3)[z + 1] = use_xs ? v4_from(gload(xs, y0 + r)) : v4_unset();
-        sh.prev()[z + 1] = v4_unset();
+    while (true) {
+        if (owned) xchg[z + 2] = st;
+        __syncthreads();
+        bool changed = false;
+        if (owned) {
+            const V4 nw = chain_rule(xchg[z + 2 - DIR], own, T);
+            changed = v4_differs(nw, st);
+            st = nw;
+        }
+        if (!__syncthreads_or(changed)) break;
     }
-    Vox self_next = gload(x, y0);
-    Vox xs_next = use_xs ? gload(xs, y0 + 2 * ydir) : unset_g;
-    __syncthreads();
-    for (int i = 0, y = y0; i < S; i++, y += ydir) {
-        const V4 self = v4_from(self_next);
-        const V4 xs_row = v4_from(xs_next);                 // adjacent-slice row y + 2*ydir: needed from the next row on
-        self_next = gload(x, y + ydir);                     // prefetch: own column only
-        xs_next = use_xs ? gload(xs, y + 3 * ydir) : unset_g;
-        {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed a few iterations from now into L2
-            const int yf = y + 8 * ydir;
-            if (active && (z & 15) == 0 && yf >= 0 && yf < S) {
+    return st;
+}
+
+// one pass over the rows of slice x: scan K1 then chain scan K2 on every row, rows in direction YDIR
+template <int K1, int K2, int YDIR>
+__device__ void slice_pass(Vox* G, int S, int x, int xs, const RowSmem& sh)
+{
+    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;                       // +1: recurrence reads z-1
+    constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
+    static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int z = warp * kOwned + lane - 1;
+    const bool valid = z >= 0 && z < S;                       // a voxel of the row (owned or shadow)
+    const bool owned = valid && lane >= 1 && lane <= kOwned;
+    const bool reads = z >= -1 && z <= S;                     // may index the padded buffers at z+1 .. z+3
+    // the owner of a warp's downstream boundary voxel validates the neighbour warp's speculation
+    const bool check1 = owned && (DIR1 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
+    const bool check2 = owned && (DIR2 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
+    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
+    const bool use_xs = HAS_XS && xs >= 0 && xs < S;
+    const int y0 = YDIR > 0 ? 0 : S - 1;
+    auto gload = [&](int xx, int yy) -> Vox { return (valid && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset_g; };
+    // folded candidates of one adjacent-slice row for column z: A = row offset +-1, B = same row
+    auto fold_xrow = [&](const V4* xr, V4& A, V4& B) {
+        A = v4_unset(); B = v4_unset();
+        if (valid) {
+            const V4 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
+            consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
+            consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
+        }
+    };
+    // adjacent-slice window: rows y-YDIR ("behind", outside the grid at the first row), y, y+YDIR
+    V4 A_behind = v4_unset(), A_cur = v4_unset(), B_cur = v4_unset(), A_ahead = v4_unset(), B_ahead = v4_unset();
+    if (use_xs) {
+        if (owned) { sh.xrow(0)[z + 2] = v4_from(gload(xs, y0)); sh.xrow(1)[z + 2] = v4_from(gload(xs, y0 + YDIR)); }
+        __syncthreads();
+        fold_xrow(sh.xrow(0), A_cur, B_cur);
+        fold_xrow(sh.xrow(1), A_ahead, B_ahead);
+        __syncthreads();
+    }
+    // register queues of global loads, kDepth rows ahead: an L2 hit costs more than one row of work
+    Vox self_q[kDepth], xs_q[kDepth];
+#pragma unroll
+    for (int d = 0; d < kDepth; d++) {
+        self_q[d] = gload(x, y0 + d * YDIR);
+        xs_q[d] = (use_xs && owned) ? gload(xs, y0 + (2 + d) * YDIR) : unset_g;
+    }
+    V4 pL = v4_unset(), pC = v4_unset(), pR = v4_unset();    // final previous row of this pass at z-1, z, z+1
+    for (int i = 0, y = y0; i < S; i++, y += YDIR) {
+        const int par = i & 1;
+        const V4 self = v4_from(self_q[0]);
+        const V4 xs_new = v4_from(xs_q[0]);                 // adjacent-slice row y + 2*YDIR: enters the window at the next row
+#pragma unroll
+        for (int d = 0; d + 1 < kDepth; d++) { self_q[d] = self_q[d + 1]; xs_q[d] = xs_q[d + 1]; }
+        self_q[kDepth - 1] = gload(x, y + kDepth * YDIR);   // own column only
+        xs_q[kDepth - 1] = (use_xs && owned) ? gload(xs, y + (2 + kDepth) * YDIR) : unset_g;
+        {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed some iterations from now into L2
+            const int yf = y + 24 * YDIR;
+            if (owned && (z & 15) == 0 && yf >= 0 && yf < S) {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + yf) * S + z));
                 if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + yf) * S + z));
             }
         }
-        bool runs1, runs2;
-        V4 v = row_scan<K1>(sh, S, y, self, 0, false, runs1);
-        // the adjacent-slice row that leaves the 3-row window is replaced by the incoming one; nobody
-        // reads that slot again in this row, and the next row's reads come after >= 2 barriers
-        if ((K1 == F1 || K1 == B1) && active) sh.xs((y + 2 * ydir + 3 + 3) % 3)[z + 1] = xs_row;
-        v = row_scan<K2>(sh, S, y, v, 1, true, runs2);
-        if (active) G[((size_t)x * S + y) * S + z] = v4_to(v);
-        if (runs2) __syncthreads();                         // prev[] was patched after the deciding barrier
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_row0 = clock64();
+#endif
+        // scan K1: own result and threshold
+        V4 P = v4_unset(), Q = v4_unset();
+        if (HAS_XS) {                                       // mask order: row y-1, row y, row y+1 of the adjacent slice
+            if (YDIR > 0) { fold(P, A_behind); fold(P, B_cur); fold(P, A_ahead); }
+            else          { fold(P, A_ahead); fold(P, B_cur); fold(P, A_behind); }
+        }
+        if (K1 == F1 || K1 == B3) {                  // previous row, then self; recurrence comes last
+            consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC); consider<0, 1, 1>(P, pR); consider<0, 0, 0>(P, self);
+        } else {                                     // recurrence first, then (z,y+-1), self, (z-1,y+-1)
+            consider<0, 1, 0>(Q, pC); consider<0, 0, 0>(Q, self); consider<0, 1, 1>(Q, pL);
+        }
+        V4 own1 = P.n <= Q.n ? P : Q;
+        int T1 = min(P.n, Q.n + 1);                  // recurrence wins iff nc < nP and nc <= nQ
+        if (!valid) { own1 = v4_unset(); T1 = -1; }  // nothing propagates through a lane outside the row
+        const V4 st1w = warp_resolve<DIR1>(own1, T1, lane);
+        // chain scan K2: its input is the state after K1, its only other candidate the voxel itself
+        const V4 fin_w = warp_resolve<DIR2>(st1w, valid ? min(kInf, st1w.n + 1) : -1, lane);
+        const bool bad = (check1 && v4_differs(st1w, own1)) || (check2 && v4_differs(fin_w, st1w));
+        V4* fin_row = sh.fin(par);
+        if (owned) { fin_row[z + 2] = fin_w; if (use_xs) sh.xrow(par)[z + 2] = xs_new; }
+        const int any = __syncthreads_or(bad);
+        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
+        V4 fin = fin_w;
+        if (any) {                                   // a run crossed a warp boundary: resolve across the CTA
+            const V4 st1 = block_resolve<DIR1>(sh.xchg(), own1, T1, st1w, owned, z);
+            fin = block_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, owned, z);
+            if (owned) fin_row[z + 2] = fin;
+            __syncthreads();
+        }
+        if (owned) G[((size_t)x * S + y) * S + z] = v4_to(fin);
+        pL = pC = pR = v4_unset();
+        if (reads) { pL = fin_row[z + 1]; pC = fin_row[z + 2]; pR = fin_row[z + 3]; }
+#ifdef GOICP_DT_INSTRUMENT
+        if (threadIdx.x == 0) DT_STAT(any ? 7 : 6, clock64() - c_row0);
+#endif
+        if (HAS_XS) {                                // slide the adjacent-slice window
+            A_behind = A_cur; A_cur = A_ahead; B_cur = B_ahead;
+            if (use_xs) fold_xrow(sh.xrow(par), A_ahead, B_ahead); else { A_ahead = v4_unset(); B_ahead = v4_unset(); }
+        }
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kMaxS)
+__global__ void __launch_bounds__(1024)
 dt_propagate_kernel(Vox* G, int S)
 {
     RowSmem sh;
-    {
-        int p = 0;
-        const int row = (S + 2) * (int)sizeof(V4);
-        for (int r = 0; r < 3; r++) { sh.o_xs[r] = p; p += row; }
-        sh.o_prev = p; p += row;
-        for (int b = 0; b < 2; b++) { sh.o_own[b] = p; p += S * (int)sizeof(V4); }
-        for (int b = 0; b < 2; b++) { sh.o_T[b] = p; p += S * (int)sizeof(int); }
-        sh.o_wmask = p; p += 32 * (int)sizeof(unsigned);
-        sh.o_run_start = p; p += (S + 2) / 2 * 2 * (int)sizeof(short);
-        sh.o_run_end = p; p += (S + 2) / 2 * 2 * (int)sizeof(short);
-        sh.o_accept = p;
-    }
-    // pads of the shared rows stay "unset" for the whole kernel
-    if (threadIdx.x == 0) {
-        const V4 u = v4_unset();
-        for (int r = 0; r < 3; r++) { sh.xs(r)[0] = u; sh.xs(r)[S + 1] = u; }
-        sh.prev()[0] = u; sh.prev()[S + 1] = u;
-    }
+    sh.stride = (S + 4) * (int)sizeof(V4);
+    // pads of the row buffers stay "unset" for the whole kernel
+    for (int i = threadIdx.x; i < 5 * (S + 4); i += blockDim.x) reinterpret_cast<V4*>(dt_smem)[i] = v4_unset();
     __syncthreads();
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
-        slice_pass<F1, C_DN>(G, S, x, x - 1, +1, sh);
-        slice_pass<F3, C_UP>(G, S, x, -1, -1, sh);
+        slice_pass<F1, C_DN, +1>(G, S, x, x - 1, sh);
+        slice_pass<F3, C_UP, -1>(G, S, x, -1, sh);
     }
     for (int x = S - 1; x >= 0; x--) {                              // :729-739
-        slice_pass<B1, C_UP>(G, S, x, x + 1, -1, sh);
-        slice_pass<B3, C_DN>(G, S, x, -1, +1, sh);
+        slice_pass<B1, C_UP, -1>(G, S, x, x + 1, sh);
+        slice_pass<B3, C_DN, +1>(G, S, x, -1, sh);
     }
 }
 
-static size_t dt_propagate_smem(int S)
+// ---- the same propagation, warp-specialised ------------------------------------------------
+// Everything that does not depend on the row recurrence is taken off its critical path: the CTA
+// is split into CONSUMER warps (own/T from the previous row, the two scans, the speculation
+// check -- the recurrence proper, ~1/3 of the instructions) and PRODUCER warps, which run one row
+// ahead and do all global traffic and all adjacent-slice work: load and unpack the rows, fold the
+// 3x3 candidates of the adjacent slice into one candidate per voxel (p9), hand p9 and the voxel's
+// current value over through shared memory, and write final rows back two rows behind.  One
+// CTA-wide barrier per row step is the only synchronisation; redoing a row across the CTA uses a
+// named barrier among the consumer warps only.  A producer thread only ever touches its own
+// columns of G, so global memory needs no ordering beyond program order.
+constexpr int kSplitMaxS = 640;        // 32 warps must hold ceil(S/30) consumer warps and S/(32*VPT) producer warps
+constexpr int kLook = 2;               // producer global-load lookahead (row steps)
+
+struct SplitSmem {
+    int stride;          // V4 elements of one padded row (S + 4), voxel z at index z+2
+    __device__ __forceinline__ V4* base() const { return reinterpret_cast<V4*>(dt_smem); }
+    __device__ __forceinline__ V4* fin(int k) const { return base() + k * stride; }            // final rows, ring of 4
+    __device__ __forceinline__ V4* p9(int k) const { return base() + (4 + k) * stride; }       // folded adjacent-slice candidate, by row parity
+    __device__ __forceinline__ V4* selfv(int k) const { return base() + (6 + k) * stride; }    // the voxel's value before this pass, by row parity
+    __device__ __forceinline__ V4* xrow(int k) const { return base() + (8 + k) * stride; }     // adjacent-slice row being folded (producers only)
+    __device__ __forceinline__ V4* xchg() const { return base() + 10 * stride; }               // CTA-wide resolution (consumers only)
+    __device__ __forceinline__ volatile int* flag() const { return reinterpret_cast<volatile int*>(base() + 11 * stride); }
+};
+static size_t dt_split_smem(int S) { return 11 * (size_t)(S + 4) * sizeof(V4) + 16; }
+
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_consumers(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
+__device__ __forceinline__ bool bar_consumers_or(int n, bool pred)
 {
-    return 4 * (size_t)(S + 2) * 16 + 2 * (size_t)S * 16 + 2 * (size_t)S * sizeof(int) + 32 * sizeof(unsigned)
-         + 2 * (size_t)(S + 2) * sizeof(short) + (size_t)S + 64;
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"((unsigned)pred), "r"(n) : "memory");
+    return r != 0;
+}
+
+// one scan inside a warp, state carried packed through three shuffles
+template <int DIR>
+__device__ __forceinline__ V4 warp_resolve3(const V4 own, const int T, const int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const bool has_pred = DIR > 0 ? lane > 0 : lane < 31;
+    const unsigned own_p = (unsigned)own.v | ((unsigned)own.h << 16);
+    unsigned p = own_p; int d = own.d, n = own.n;
+    while (true) {
+        const unsigned q = DIR > 0 ? __shfl_up_sync(full, p, 1) : __shfl_down_sync(full, p, 1);
+        const int od = DIR > 0 ? __shfl_up_sync(full, d, 1) : __shfl_down_sync(full, d, 1);
+        const int on = DIR > 0 ? __shfl_up_sync(full, n, 1) : __shfl_down_sync(full, n, 1);
+        const int nc = on + 2 * od + 1;                      // an unset predecessor gives nc > kInf >= T
+        const bool take = has_pred & (nc < T);
+        const unsigned np = take ? q : own_p; const int nd = take ? od + 1 : own.d;
+        const bool changed = (np != p) | (nd != d);
+        p = np; d = nd; n = take ? nc : own.n;
+        if (!__any_sync(full, changed)) break;
+    }
+    V4 r; r.v = (int)(p & 0xffffu); r.h = (int)(p >> 16); r.d = d; r.n = n;
+    return r;
+}
+
+template <int DIR>
+__device__ __noinline__ V4 consumers_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z, const int nthreads)
+{
+    while (true) {
+        if (owned) xchg[z + 2] = st;
+        bar_consumers(nthreads);
+        bool changed = false;
+        if (owned) {
+            const V4 nw = chain_rule(xchg[z + 2 - DIR], own, T);
+            changed = v4_differs(nw, st);
+            st = nw;
+        }
+        if (!bar_consumers_or(nthreads, changed)) break;
+    }
+    return st;
+}
+
+// Row steps s = -3 .. S+1 of one pass: the consumers work on row s, the producers emit p9/self of
+// row s+1, fold adjacent-slice row s+2, stage row s+3 and store final row s-2 (rows outside [0,S)
+// are "unset" / skipped).  Row index i maps to y = y0 + i*YDIR.
+template <int K1, int K2, int YDIR>
+__device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const int ncons_threads, const int serial)
+{
+    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;
+    constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
+    static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int z = warp * kOwned + lane - 1;
+    const bool valid = z >= 0 && z < S;
+    const bool owned = valid && lane >= 1 && lane <= kOwned;
+    const int zc = min(max(z, -1), S) + 2;                   // lanes outside the row read the pads
+    const bool check1 = owned && (DIR1 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
+    const bool check2 = owned && (DIR2 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
+    if (owned) sh.fin(3)[z + 2] = v4_unset();                // "row -1" of this pass
+    for (int s = -3; s < S + 2; s++) {
+        const bool act = s >= 0 && s < S;
+        V4 own1 = v4_unset(), st1w = own1, fin_w = own1; int T1 = 0;
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_w0 = clock64();
+#endif
+        if (act) {
+            const V4* prev = sh.fin((s - 1) & 3);
+            const V4 pL = prev[zc - 1], pC = prev[zc], pR = prev[zc + 1];
+            const V4 self = sh.selfv(s & 1)[zc];
+            V4 P = v4_unset(), Q = v4_unset();
+            if (HAS_XS) P = sh.p9(s & 1)[zc];
+            if (K1 == F1 || K1 == B3) {              // previous row, then self; recurrence comes last
+                V4 P2 = v4_unset();
+                consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC);
+                consider<0, 1, 1>(P2, pR); consider<0, 0, 0>(P2, self);
+                fold(P, P2);
+            } else {                                 // recurrence first, then (z,y+-1), self, (z-1,y+-1)
+                consider<0, 1, 0>(Q, pC); consider<0, 0, 0>(Q, self); consider<0, 1, 1>(Q, pL);
+            }
+            own1 = P.n <= Q.n ? P : Q;
+            T1 = valid ? min(P.n, Q.n + 1) : 0;      // recurrence wins iff nc < nP and nc <= nQ; nothing passes a lane outside the row
+            st1w = warp_resolve3<DIR1>(own1, T1, lane);
+            fin_w = warp_resolve3<DIR2>(st1w, valid ? min(kInf, st1w.n + 1) : 0, lane);
+            const bool bad = (check1 && v4_differs(st1w, own1)) || (check2 && v4_differs(fin_w, st1w));
+            if (owned) sh.fin(s & 3)[z + 2] = fin_w;
+            if (bad) sh.flag()[s & 1] = serial + s;
+        }
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_w1 = clock64();
+        bar_all();
+        if (threadIdx.x == 0 && act) { DT_STAT(6, c_w1 - c_w0); DT_STAT(7, clock64() - c_w1); }
+#else
+        bar_all();
+#endif
+        if (act) {
+            const bool any = sh.flag()[s & 1] == serial + s;
+            DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
+            if (any) {                               // a run crossed a warp boundary: resolve across the consumers
+                const V4 st1 = consumers_resolve<DIR1>(sh.xchg(), own1, T1, st1w, owned, z, ncons_threads);
+                const V4 fin = consumers_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, owned, z, ncons_threads);
+                if (owned) sh.fin(s & 3)[z + 2] = fin;
+                bar_consumers(ncons_threads);
+            }
+        }
+    }
+}
+
+template <int K1, int YDIR, int VPT>
+__device__ __forceinline__ void producer_pass(Vox* G, int S, int x, int xs, const SplitSmem& sh, const int ptid, const int nprod_threads)
+{
+    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    const bool use_xs = HAS_XS && xs >= 0 && xs < S;
+    const int y0 = YDIR > 0 ? 0 : S - 1;
+    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
+    int zs[VPT]; bool zok[VPT];
+    V4 A_prev[VPT], X_prev[VPT];
+    Vox self_q[VPT][kLook], xs_q[VPT][kLook];
+#pragma unroll
+    for (int j = 0; j < VPT; j++) { zs[j] = ptid + j * nprod_threads; zok[j] = zs[j] < S; }
+    auto gload = [&](int xx, int i, int j) -> Vox {          // row index i of slice xx, this thread's column j
+        return (zok[j] && i >= 0 && i < S) ? G[((size_t)xx * S + (y0 + i * YDIR)) * S + zs[j]] : unset_g;
+    };
+#pragma unroll
+    for (int j = 0; j < VPT; j++) {
+        A_prev[j] = v4_unset(); X_prev[j] = v4_unset();
+#pragma unroll
+        for (int d = 0; d < kLook; d++) {                    // at step s the heads are self row s+1 and adjacent row s+3
+            self_q[j][d] = gload(x, -3 + 1 + d, j);
+            xs_q[j][d] = use_xs ? gload(xs, -3 + 3 + d, j) : unset_g;
+        }
+    }
+    for (int s = -3; s < S + 2; s++) {
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_p0 = clock64();
+#endif
+#pragma unroll
+        for (int j = 0; j < VPT; j++) {
+            const int z = zs[j];
+            const Vox sv = self_q[j][0], xv = xs_q[j][0];
+#pragma unroll
+            for (int d = 0; d + 1 < kLook; d++) { self_q[j][d] = self_q[j][d + 1]; xs_q[j][d] = xs_q[j][d + 1]; }
+            self_q[j][kLook - 1] = gload(x, s + 1 + kLook, j);
+            xs_q[j][kLook - 1] = use_xs ? gload(xs, s + 3 + kLook, j) : unset_g;
+            if (zok[j]) {
+                {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed some steps from now into L2
+                    const int ifar = s + 24;
+                    if ((z & 15) == 0 && ifar >= 0 && ifar < S) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + (y0 + ifar * YDIR)) * S + z));
+                        if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + (y0 + ifar * YDIR)) * S + z));
+                    }
+                }
+                if (HAS_XS) {
+                    sh.xrow(s & 1)[z + 2] = v4_from(xv);                      // stage adjacent row s+3 (unset outside the grid)
+                    if (s >= -2) {                                            // fold adjacent row s+2, staged at the previous step
+                        const V4* xr = sh.xrow((s - 1) & 1);
+                        const V4 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
+                        V4 A = v4_unset(), B = v4_unset();
+                        consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
+                        consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
+                        // mask order of row s+1: adjacent rows y-1, y, y+1 = (s, s+1, s+2) for YDIR>0, reversed otherwise
+                        V4 p9, X;
+                        if (YDIR > 0) { p9 = X_prev[j]; fold(p9, A); X = A_prev[j]; fold(X, B); }
+                        else          { p9 = A; fold(p9, X_prev[j]); X = B; fold(X, A_prev[j]); }
+                        if (s + 1 >= 0 && s + 1 < S) sh.p9((s + 1) & 1)[z + 2] = p9;
+                        X_prev[j] = X; A_prev[j] = A;
+                    }
+                }
+                if (s + 1 >= 0 && s + 1 < S) sh.selfv((s + 1) & 1)[z + 2] = v4_from(sv);
+                if (s - 2 >= 0 && s - 2 < S) G[((size_t)x * S + (y0 + (s - 2) * YDIR)) * S + z] = v4_to(sh.fin((s - 2) & 3)[z + 2]);
+            }
+        }
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_p1 = clock64();
+        bar_all();
+        if (ptid == 0 && s >= 0 && s < S) { DT_STAT(2, c_p1 - c_p0); DT_STAT(3, clock64() - c_p1); }
+#else
+        bar_all();
+#endif
+    }
+}
+
+template <int VPT>
+__global__ void __launch_bounds__(1024)
+dt_propagate_split_kernel(Vox* G, int S, int ncons_warps)
+{
+    SplitSmem sh;
+    sh.stride = S + 4;
+    // pads of the row buffers stay "unset" for the whole kernel
+    for (int i = threadIdx.x; i < 11 * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
+    if (threadIdx.x < 4) sh.flag()[threadIdx.x] = -1;
+    __syncthreads();
+    const bool consumer = (int)(threadIdx.x >> 5) < ncons_warps;
+    const int nct = ncons_warps * 32;
+    const int ptid = (int)threadIdx.x - nct, npt = (int)blockDim.x - nct;
+    int serial = 0;                                                // row steps get unique ids across passes
+#define DT_PASS(K1, K2, YD, XX, XS) do { \
+        if (consumer) consumer_pass<K1, K2, YD>(S, sh, nct, serial); \
+        else producer_pass<K1, YD, VPT>(G, S, XX, XS, sh, ptid, npt); \
+        serial += 2048; } while (0)
+    for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
+        DT_PASS(F1, C_DN, +1, x, x - 1);
+        DT_PASS(F3, C_UP, -1, x, -1);
+    }
+    for (int x = S - 1; x >= 0; x--) {                              // :729-739
+        DT_PASS(B1, C_UP, -1, x, x + 1);
+        DT_PASS(B3, C_DN, +1, x, -1);
+    }
+#undef DT_PASS
 }
 
 // distance = float( double(float(sqrt(double(n2)))) / scale ), clamped at 0 (jly_3ddt.cpp:970-978);
@@ -406,6 +645,7 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
 {
     cudaError_t e;
     if (S > kMaxS) { msg = "dt_size > 1024"; return cudaErrorInvalidValue; }
+    if (mode == 0 && S > kMaxRefS) { msg = "dt_size > 960 in reference-order mode (use the exact EDT mode)"; return cudaErrorInvalidValue; }
     dt_frame_host(model, nm, S, expand, meta);
     const size_t n3 = (size_t)S * S * S;
     Vox* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
@@ -419,17 +659,40 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
     DT_TRY(cudaGetLastError());
     if (mode == 0) {
-        const int threads = ((S + 31) / 32) * 32;
-        const size_t smem = dt_propagate_smem(S);
-        DT_TRY(cudaFuncSetAttribute(dt_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dt_propagate_kernel<<<1, threads, smem, stream>>>(G, S);
+        const bool timing = getenv("GOICP_DT_TIMING") != nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (timing) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, stream); }
+        const int ncons = (S + kOwned - 1) / kOwned;
+        if (S <= kSplitMaxS && getenv("GOICP_DT_UNSPLIT") == nullptr) {
+            // producer warps: one voxel per thread while 32 warps suffice, else two
+            int nprod = (S + 31) / 32, vpt = 1;
+            if (ncons + nprod > 32) { nprod = 32 - ncons; vpt = 2; }
+            const size_t smem = dt_split_smem(S);
+            if (vpt == 1) {
+                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dt_propagate_split_kernel<1><<<1, (ncons + nprod) * 32, smem, stream>>>(G, S, ncons);
+            } else {
+                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dt_propagate_split_kernel<2><<<1, (ncons + nprod) * 32, smem, stream>>>(G, S, ncons);
+            }
+        } else {
+            const size_t smem = dt_propagate_smem(S);
+            DT_TRY(cudaFuncSetAttribute(dt_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dt_propagate_kernel<<<1, ncons * 32, smem, stream>>>(G, S);
+        }
         DT_TRY(cudaGetLastError());
+        if (timing) {
+            cudaEventRecord(ev1, stream); cudaEventSynchronize(ev1);
+            float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+            fprintf(stderr, "[dt timing] S=%d propagate kernel %.3f ms\n", S, ms);
+            cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+        }
 #ifdef GOICP_DT_INSTRUMENT
         {
             unsigned long long hs[8];
             DT_TRY(cudaStreamSynchronize(stream));
             DT_TRY(cudaMemcpyFromSymbol(hs, g_dt_stats_buf, sizeof hs));
-            fprintf(stderr, "[dt stats] row scans %llu, with runs %llu, run heads %llu, total run length %llu\n", hs[0], hs[1], hs[2], hs[3]);
+            fprintf(stderr, "[dt stats] rows %llu, resolved across the CTA %llu; per row: consumer work %.0f wait %.0f, producer work %.0f wait %.0f cycles\n", hs[4], hs[5], (double)hs[6] / hs[4], (double)hs[7] / hs[4], (double)hs[2] / hs[4], (double)hs[3] / hs[4]);
         }
 #endif
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);
