@@ -6,11 +6,11 @@
 // rows forward then backward, each row along z forward then backward, and the whole volume in
 // +x then -x.  Its output depends on that order (it is not the exact EDT), so the order is
 // kept: one persistent CTA walks slices and rows in the reference order; within a row all the
-// candidates that do not depend on the running scan are evaluated in parallel (one thread per
-// voxel) and only the true recurrence -- "previous voxel of this scan + (0,0,1)" -- is resolved
-// serially, and only for rows where it can matter.  Comparisons use the integer squared norm:
-// the reference compares float(sqrt(v^2+h^2+d^2)), a strictly increasing function of that
-// integer for grids up to 1024^3, with strict '<' in mask order (first minimum wins).
+// candidates that do not depend on the running scan are evaluated in parallel and only the true
+// recurrence -- "previous voxel of this scan + (0,0,1)" -- is resolved, as a fixed point.
+// Comparisons use the integer squared norm: the reference compares float(sqrt(v^2+h^2+d^2)), a
+// strictly increasing function of that integer for grids up to 1024^3, with strict '<' in mask
+// order (first minimum wins).
 //
 // GOICP_DT_EXACT_EDT is the separable exact squared-Euclidean transform (three 1-D lower-envelope
 // passes over integer squared distances), fully parallel.
@@ -28,25 +28,29 @@ namespace {
 constexpr int kInf = 0x3fffffff;       // "no candidate" squared norm
 constexpr int kMaxS = 1024;
 
-struct __align__(8) Vox { short v, h, d, pad; };
+// Working voxel, in HBM and on chip alike: the vector to the nearest seed found so far (component
+// magnitudes) and its squared norm; one 16-byte access.  "unset" = no seed seen yet.  A candidate
+// costs a handful of integer instructions:
+//   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1}.
+struct __align__(16) V4 { int v, h, d, n; };
 
-__device__ __forceinline__ int vox_norm2(const Vox& a) { return (int)a.v * a.v + (int)a.h * a.h + (int)a.d * a.d; }
-__device__ __forceinline__ bool vox_unset(const Vox& a) { return a.v == 32767; }
+__device__ __forceinline__ V4 v4_unset() { V4 u; u.v = u.h = u.d = 32767; u.n = kInf; return u; }
+__device__ __forceinline__ bool v4_differs(const V4& a, const V4& b) { return (a.v != b.v) | (a.h != b.h) | (a.d != b.d); }
 
-__global__ void dt_init_kernel(Vox* G, size_t n3)
+__global__ void dt_init_kernel(V4* G, size_t n3, int corner_seed)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n3) return;
-    Vox u; u.v = u.h = u.d = 32767; u.pad = 0;
+    V4 u = v4_unset();
     // As compiled (g++ 13.3 -O2) the reference's mask function returns (0,0,0) for the very first
     // voxel it visits, where no candidate qualifies and its result struct is uninitialised
     // (jly_3ddt.cpp:469-470): voxel (0,0,0) acts as one extra seed.  Pinned against oracle/_ref.
-    if (i == 0) u.v = u.h = u.d = 0;
+    if (i == 0 && corner_seed) u.v = u.h = u.d = u.n = 0;
     G[i] = u;
 }
 
 // seeds: ROUND((p - min)*scale) in double, points outside the grid skipped (jly_3ddt.cpp:952-966)
-__global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, int nm, double xmin, double ymin, double zmin, double scale)
+__global__ void dt_seed_kernel(V4* G, int S, const float* __restrict__ model, int nm, double xmin, double ymin, double zmin, double scale)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nm) return;
@@ -54,12 +58,12 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
     int y = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 1], ymin), scale), 0.5));
     int z = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 2], zmin), scale), 0.5));
     if (x < 0 || x >= S || y < 0 || y >= S || z < 0 || z >= S) return;
-    Vox s; s.v = s.h = s.d = 0; s.pad = 0;
+    V4 s; s.v = s.h = s.d = s.n = 0;
     G[((size_t)x * S + y) * S + z] = s;
 }
 
 // ---- the sequential propagation ------------------------------------------------------------
-// One persistent CTA.  A row scan of the reference is the recurrence
+// A row scan of the reference is the recurrence
 //   state_k = (state_{k-1} + (0,0,1) beats T_k) ? state_{k-1} + (0,0,1) : own_k
 // where own_k is the first minimum (mask order) of all candidates that do not depend on the
 // running scan and T_k the squared norm the running-scan candidate must beat at k (ties by mask
@@ -71,34 +75,19 @@ __global__ void dt_seed_kernel(Vox* G, int S, const float* __restrict__ model, i
 // Mapping: each warp owns 30 consecutive voxels of the row; lanes 0 and 31 shadow the boundary
 // voxels of the neighbouring warps, so a warp resolves both scans of a row with shuffles only,
 // speculating that no run crosses into it.  The owner of a boundary voxel knows whether that
-// held (its state differs from its own value); the flags are OR-ed by the single barrier of the
-// row, which also publishes the row to the neighbours.  Rows where the speculation failed are
-// redone by the same fixed-point iteration across the CTA through shared memory.
-// State the row recurrence needs lives in registers: the final previous row at z-1, z, z+1 and
-// the folded candidates of the adjacent slice (three rows x three z-neighbours, folded per row
-// into A (row offset +-1) and B (same row) when a row enters the window, one row ahead of its
-// use).  Every global access is a thread's own column, prefetched one row ahead.
-// Working representation on chip: 32-bit components plus the squared norm, 16 bytes per voxel
-// (one LDS.128), so that a candidate costs a handful of integer instructions:
-//   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1}.
-// Global memory keeps the compact 8-byte (short) form.
-struct __align__(16) V4 { int v, h, d, n; };
+// held (its state differs from its own value); the flags are gathered by the single barrier of
+// the row, which also publishes the row to the neighbours.  Rows where the speculation failed
+// (3 %) are redone by the same fixed-point iteration across the CTA through shared memory.
 constexpr int kOwned = 30;             // voxels owned per warp
 constexpr int kMaxRefS = 32 * kOwned;  // 1024 threads
-constexpr int kDepth = 4;              // rows of global-load lookahead held in registers
 
-__device__ __forceinline__ V4 v4_unset() { V4 u; u.v = u.h = u.d = 32767; u.n = kInf; return u; }
-__device__ __forceinline__ V4 v4_from(const Vox& a) { V4 r; r.v = a.v; r.h = a.h; r.d = a.d; r.n = vox_unset(a) ? kInf : vox_norm2(a); return r; }
-__device__ __forceinline__ Vox v4_to(const V4& a) { Vox r; r.v = (short)a.v; r.h = (short)a.h; r.d = (short)a.d; r.pad = 0; return r; }
-__device__ __forceinline__ bool v4_differs(const V4& a, const V4& b) { return (a.v != b.v) | (a.h != b.h) | (a.d != b.d); }
-
-// candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order
+// candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order.  An unset
+// source (n = kInf) scores above kInf and never wins (the reference scores it ~56755 > 32767).
 template <int IV, int IH, int ID>
 __device__ __forceinline__ void consider(V4& best, const V4 s)
 {
-    // unset source (n == kInf): scores ~56755 > 32767 in the reference and is never chosen
     const int n = s.n + 2 * (IV * s.v + IH * s.h + ID * s.d) + (IV + IH + ID);
-    const bool take = (s.n < kInf) & (n < best.n);
+    const bool take = n < best.n;
     best.n = take ? n : best.n; best.v = take ? s.v + IV : best.v; best.h = take ? s.h + IH : best.h; best.d = take ? s.d + ID : best.d;
 }
 // fold an already-incremented candidate (first minimum in order)
@@ -110,8 +99,8 @@ __device__ __forceinline__ void fold(V4& best, const V4 c)
 // the recurrence rule at one voxel: predecessor state o, own result, threshold T
 __device__ __forceinline__ V4 chain_rule(const V4 o, const V4 own, int T)
 {
-    const int nc = o.n + 2 * o.d + 1;
-    const bool take = (o.n < kInf) & (nc < T);
+    const int nc = o.n + 2 * o.d + 1;            // an unset predecessor gives nc > kInf >= T
+    const bool take = nc < T;
     V4 r; r.v = take ? o.v : own.v; r.h = take ? o.h : own.h; r.d = take ? o.d + 1 : own.d; r.n = take ? nc : own.n;
     return r;
 }
@@ -124,17 +113,7 @@ __device__ __forceinline__ V4 chain_rule(const V4 o, const V4 own, int T)
 // voxel with a strictly smaller increment; they are omitted.
 enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 
-// Row buffers: voxel z sits at index z+2, two "unset" pads on each side (a shadow lane reads the
-// neighbour of a voxel one outside the row).  `fin` and `xrow` alternate by row parity: a row is
-// written before the row's barrier and read after it, the next row writes the other copy.
 extern __shared__ __align__(16) unsigned char dt_smem[];
-struct RowSmem {
-    int stride;          // bytes of one padded row
-    __device__ __forceinline__ V4* fin(int par) const { return reinterpret_cast<V4*>(dt_smem + par * stride); }
-    __device__ __forceinline__ V4* xrow(int par) const { return reinterpret_cast<V4*>(dt_smem + (2 + par) * stride); }
-    __device__ __forceinline__ V4* xchg() const { return reinterpret_cast<V4*>(dt_smem + 4 * stride); }
-};
-static size_t dt_propagate_smem(int S) { return 5 * (size_t)(S + 4) * sizeof(V4); }
 
 #ifdef GOICP_DT_INSTRUMENT
 __device__ unsigned long long g_dt_stats_buf[8];
@@ -143,147 +122,183 @@ __device__ unsigned long long g_dt_stats_buf[8];
 #define DT_STAT(i, v) ((void)0)
 #endif
 
-// One scan resolved inside a warp (DIR = +1: the predecessor is lane-1).  The lane at the upstream
-// end has no predecessor in the warp and keeps its own value -- the speculation.
+// One scan resolved inside a warp (DIR = +1: the predecessor is lane-1), state carried through
+// three shuffles (v,h < 2^15 share a word).  The lane at the upstream end has no predecessor in
+// the warp and keeps its own value -- the speculation.
 template <int DIR>
 __device__ __forceinline__ V4 warp_resolve(const V4 own, const int T, const int lane)
 {
     const unsigned full = 0xffffffffu;
     const bool has_pred = DIR > 0 ? lane > 0 : lane < 31;
-    V4 st = own;
+    const unsigned own_p = (unsigned)own.v | ((unsigned)own.h << 16);
+    unsigned p = own_p; int d = own.d, n = own.n;
     while (true) {
-        // v,h,d < 2^15: two shuffles carry the state, the norm is recomputed
-        const unsigned p0 = (unsigned)st.v | ((unsigned)st.h << 16);
-        const unsigned q0 = DIR > 0 ? __shfl_up_sync(full, p0, 1) : __shfl_down_sync(full, p0, 1);
-        const int od = DIR > 0 ? __shfl_up_sync(full, st.d, 1) : __shfl_down_sync(full, st.d, 1);
-        const int ov = (int)(q0 & 0xffffu), oh = (int)(q0 >> 16);
-        const int nc = ov * ov + oh * oh + (od + 1) * (od + 1);
-        const bool take = has_pred & (ov != 32767) & (nc < T);
-        V4 nw; nw.v = take ? ov : own.v; nw.h = take ? oh : own.h; nw.d = take ? od + 1 : own.d; nw.n = take ? nc : own.n;
-        const bool changed = v4_differs(nw, st);
-        st = nw;
+        const unsigned q = DIR > 0 ? __shfl_up_sync(full, p, 1) : __shfl_down_sync(full, p, 1);
+        const int od = DIR > 0 ? __shfl_up_sync(full, d, 1) : __shfl_down_sync(full, d, 1);
+        const int on = DIR > 0 ? __shfl_up_sync(full, n, 1) : __shfl_down_sync(full, n, 1);
+        const int nc = on + 2 * od + 1;
+        const bool take = has_pred & (nc < T);
+        const unsigned np = take ? q : own_p; const int nd = take ? od + 1 : own.d;
+        const bool changed = (np != p) | (nd != d);
+        p = np; d = nd; n = take ? nc : own.n;
         if (!__any_sync(full, changed)) break;
     }
-    return st;
+    V4 r; r.v = (int)(p & 0xffffu); r.h = (int)(p >> 16); r.d = d; r.n = n;
+    return r;
 }
 
-// The same fixed-point iteration across the whole row through shared memory (collective).
+// lane / voxel bookkeeping of a row-recurrence thread
+struct Lane {
+    int lane, z, zc;
+    bool valid, owned, check_up, check_dn;
+    __device__ __forceinline__ Lane(int warp, int lane_, int S) : lane(lane_)
+    {
+        z = warp * kOwned + lane - 1;
+        valid = z >= 0 && z < S;                              // a voxel of the row (owned or shadow)
+        owned = valid && lane >= 1 && lane <= kOwned;
+        zc = min(max(z, -1), S) + 2;                          // padded index; lanes outside the row read the pads
+        // the owner of a warp's downstream boundary voxel validates the neighbour warp's speculation
+        check_up = owned && lane == kOwned && z + 1 < S;      // scans with DIR = +1
+        check_dn = owned && lane == 1 && z > 0;               // scans with DIR = -1
+    }
+};
+
+// Both scans of one row for this lane's voxel, warp-local.  pL/pC/pR = final previous row of the
+// pass at z-1, z, z+1; p9 = folded candidates of the adjacent slice; self = the voxel's value so far.
+template <int K1, int K2>
+__device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, const V4 pC, const V4 pR, const V4 p9, const V4 self,
+                                               V4& own1, int& T1, V4& st1, V4& fin, bool& bad)
+{
+    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;                       // +1: recurrence reads z-1
+    constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
+    static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
+    V4 P = v4_unset(), Q = v4_unset();
+    if (HAS_XS) P = p9;
+    if (K1 == F1 || K1 == B3) {                  // previous row, then self; recurrence comes last
+        V4 P2 = v4_unset();
+        consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC);
+        consider<0, 1, 1>(P2, pR); consider<0, 0, 0>(P2, self);
+        fold(P, P2);
+    } else {                                     // recurrence first, then (z,y+-1), self, (z-1,y+-1)
+        consider<0, 1, 0>(Q, pC); consider<0, 0, 0>(Q, self); consider<0, 1, 1>(Q, pL);
+    }
+    own1 = P.n <= Q.n ? P : Q;
+    T1 = ln.valid ? min(P.n, Q.n + 1) : 0;       // recurrence wins iff nc < nP and nc <= nQ; nothing passes a lane outside the row
+    st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
+    // chain scan K2: its input is the state after K1, its only other candidate the voxel itself
+    fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
+    bad = ((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) || ((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1));
+}
+
+// ---- variant 1: every warp does everything (any S <= 960) -------------------------------------
+// State the row recurrence needs lives in registers: the final previous row at z-1, z, z+1 and
+// the folded candidates of the adjacent slice (three rows x three z-neighbours, folded per row
+// into A (row offset +-1) and B (same row) when a row enters the window, one row ahead of its
+// use).  Every global access is a thread's own column, prefetched one row ahead.
+// Row buffers: voxel z sits at index z+2, two "unset" pads on each side (a shadow lane reads the
+// neighbour of a voxel one outside the row).  `fin` and `xrow` alternate by row parity: a row is
+// written before the row's barrier and read after it, the next row writes the other copy.
+struct RowSmem {
+    int stride;          // V4 elements of one padded row
+    __device__ __forceinline__ V4* base() const { return reinterpret_cast<V4*>(dt_smem); }
+    __device__ __forceinline__ V4* fin(int par) const { return base() + par * stride; }
+    __device__ __forceinline__ V4* xrow(int par) const { return base() + (2 + par) * stride; }
+    __device__ __forceinline__ V4* xchg() const { return base() + 4 * stride; }
+};
+size_t dt_propagate_smem(int S) { return 5 * (size_t)(S + 4) * sizeof(V4); }
+
+// The fixed-point iteration across the whole row through shared memory (collective over `nthreads`
+// threads on named barrier 1; with nthreads == blockDim.x that is the whole CTA).
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_group(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
+__device__ __forceinline__ bool bar_group_or(int n, bool pred)
+{
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"((unsigned)pred), "r"(n) : "memory");
+    return r != 0;
+}
 template <int DIR>
-__device__ __noinline__ V4 block_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z)
+__device__ __noinline__ V4 group_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z, const int nthreads)
 {
     while (true) {
         if (owned) xchg[z + 2] = st;
-        __syncthreads();
+        bar_group(nthreads);
         bool changed = false;
         if (owned) {
             const V4 nw = chain_rule(xchg[z + 2 - DIR], own, T);
             changed = v4_differs(nw, st);
             st = nw;
         }
-        if (!__syncthreads_or(changed)) break;
+        if (!bar_group_or(nthreads, changed)) break;
     }
     return st;
 }
 
 // one pass over the rows of slice x: scan K1 then chain scan K2 on every row, rows in direction YDIR
 template <int K1, int K2, int YDIR>
-__device__ void slice_pass(Vox* G, int S, int x, int xs, const RowSmem& sh)
+__device__ void slice_pass(V4* G, int S, int x, int xs, const RowSmem& sh)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
-    constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;                       // +1: recurrence reads z-1
-    constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
-    static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int z = warp * kOwned + lane - 1;
-    const bool valid = z >= 0 && z < S;                       // a voxel of the row (owned or shadow)
-    const bool owned = valid && lane >= 1 && lane <= kOwned;
-    const bool reads = z >= -1 && z <= S;                     // may index the padded buffers at z+1 .. z+3
-    // the owner of a warp's downstream boundary voxel validates the neighbour warp's speculation
-    const bool check1 = owned && (DIR1 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
-    const bool check2 = owned && (DIR2 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
-    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
+    constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;
+    constexpr int DIR2 = -DIR1;
+    const Lane ln(threadIdx.x >> 5, threadIdx.x & 31, S);
+    const int z = ln.z;
     const bool use_xs = HAS_XS && xs >= 0 && xs < S;
     const int y0 = YDIR > 0 ? 0 : S - 1;
-    auto gload = [&](int xx, int yy) -> Vox { return (valid && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : unset_g; };
+    auto gload = [&](int xx, int yy) -> V4 { return (ln.valid && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : v4_unset(); };
     // folded candidates of one adjacent-slice row for column z: A = row offset +-1, B = same row
     auto fold_xrow = [&](const V4* xr, V4& A, V4& B) {
         A = v4_unset(); B = v4_unset();
-        if (valid) {
-            const V4 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
-            consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
-            consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
-        }
+        const V4 l = xr[ln.zc - 1], c = xr[ln.zc], r = xr[ln.zc + 1];
+        consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
+        consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
     };
     // adjacent-slice window: rows y-YDIR ("behind", outside the grid at the first row), y, y+YDIR
     V4 A_behind = v4_unset(), A_cur = v4_unset(), B_cur = v4_unset(), A_ahead = v4_unset(), B_ahead = v4_unset();
     if (use_xs) {
-        if (owned) { sh.xrow(0)[z + 2] = v4_from(gload(xs, y0)); sh.xrow(1)[z + 2] = v4_from(gload(xs, y0 + YDIR)); }
+        if (ln.owned) { sh.xrow(0)[z + 2] = gload(xs, y0); sh.xrow(1)[z + 2] = gload(xs, y0 + YDIR); }
         __syncthreads();
         fold_xrow(sh.xrow(0), A_cur, B_cur);
         fold_xrow(sh.xrow(1), A_ahead, B_ahead);
         __syncthreads();
     }
-    // register queues of global loads, kDepth rows ahead: an L2 hit costs more than one row of work
-    Vox self_q[kDepth], xs_q[kDepth];
-#pragma unroll
-    for (int d = 0; d < kDepth; d++) {
-        self_q[d] = gload(x, y0 + d * YDIR);
-        xs_q[d] = (use_xs && owned) ? gload(xs, y0 + (2 + d) * YDIR) : unset_g;
-    }
+    V4 self_next = gload(x, y0);
+    V4 xs_next = (use_xs && ln.owned) ? gload(xs, y0 + 2 * YDIR) : v4_unset();
     V4 pL = v4_unset(), pC = v4_unset(), pR = v4_unset();    // final previous row of this pass at z-1, z, z+1
     for (int i = 0, y = y0; i < S; i++, y += YDIR) {
         const int par = i & 1;
-        const V4 self = v4_from(self_q[0]);
-        const V4 xs_new = v4_from(xs_q[0]);                 // adjacent-slice row y + 2*YDIR: enters the window at the next row
-#pragma unroll
-        for (int d = 0; d + 1 < kDepth; d++) { self_q[d] = self_q[d + 1]; xs_q[d] = xs_q[d + 1]; }
-        self_q[kDepth - 1] = gload(x, y + kDepth * YDIR);   // own column only
-        xs_q[kDepth - 1] = (use_xs && owned) ? gload(xs, y + (2 + kDepth) * YDIR) : unset_g;
-        {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed some iterations from now into L2
-            const int yf = y + 24 * YDIR;
-            if (owned && (z & 15) == 0 && yf >= 0 && yf < S) {
+        const V4 self = self_next;
+        const V4 xs_new = xs_next;                          // adjacent-slice row y + 2*YDIR: enters the window at the next row
+        self_next = gload(x, y + YDIR);                     // own column only
+        xs_next = (use_xs && ln.owned) ? gload(xs, y + 3 * YDIR) : v4_unset();
+        {   // the volume exceeds L2 at S=300: pull the rows needed some iterations from now into L2
+            const int yf = y + 16 * YDIR;
+            if (ln.owned && (z & 7) == 0 && yf >= 0 && yf < S) {
                 asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + yf) * S + z));
                 if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + yf) * S + z));
             }
         }
-#ifdef GOICP_DT_INSTRUMENT
-        const long long c_row0 = clock64();
-#endif
-        // scan K1: own result and threshold
-        V4 P = v4_unset(), Q = v4_unset();
+        V4 p9 = v4_unset();
         if (HAS_XS) {                                       // mask order: row y-1, row y, row y+1 of the adjacent slice
-            if (YDIR > 0) { fold(P, A_behind); fold(P, B_cur); fold(P, A_ahead); }
-            else          { fold(P, A_ahead); fold(P, B_cur); fold(P, A_behind); }
+            if (YDIR > 0) { fold(p9, A_behind); fold(p9, B_cur); fold(p9, A_ahead); }
+            else          { fold(p9, A_ahead); fold(p9, B_cur); fold(p9, A_behind); }
         }
-        if (K1 == F1 || K1 == B3) {                  // previous row, then self; recurrence comes last
-            consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC); consider<0, 1, 1>(P, pR); consider<0, 0, 0>(P, self);
-        } else {                                     // recurrence first, then (z,y+-1), self, (z-1,y+-1)
-            consider<0, 1, 0>(Q, pC); consider<0, 0, 0>(Q, self); consider<0, 1, 1>(Q, pL);
-        }
-        V4 own1 = P.n <= Q.n ? P : Q;
-        int T1 = min(P.n, Q.n + 1);                  // recurrence wins iff nc < nP and nc <= nQ
-        if (!valid) { own1 = v4_unset(); T1 = -1; }  // nothing propagates through a lane outside the row
-        const V4 st1w = warp_resolve<DIR1>(own1, T1, lane);
-        // chain scan K2: its input is the state after K1, its only other candidate the voxel itself
-        const V4 fin_w = warp_resolve<DIR2>(st1w, valid ? min(kInf, st1w.n + 1) : -1, lane);
-        const bool bad = (check1 && v4_differs(st1w, own1)) || (check2 && v4_differs(fin_w, st1w));
+        V4 own1, st1w, fin; int T1; bool bad;
+        row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin, bad);
         V4* fin_row = sh.fin(par);
-        if (owned) { fin_row[z + 2] = fin_w; if (use_xs) sh.xrow(par)[z + 2] = xs_new; }
+        if (ln.owned) { fin_row[z + 2] = fin; if (use_xs) sh.xrow(par)[z + 2] = xs_new; }
         const int any = __syncthreads_or(bad);
         DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
-        V4 fin = fin_w;
         if (any) {                                   // a run crossed a warp boundary: resolve across the CTA
-            const V4 st1 = block_resolve<DIR1>(sh.xchg(), own1, T1, st1w, owned, z);
-            fin = block_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, owned, z);
-            if (owned) fin_row[z + 2] = fin;
+            const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, blockDim.x);
+            fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, blockDim.x);
+            if (ln.owned) fin_row[z + 2] = fin;
             __syncthreads();
         }
-        if (owned) G[((size_t)x * S + y) * S + z] = v4_to(fin);
-        pL = pC = pR = v4_unset();
-        if (reads) { pL = fin_row[z + 1]; pC = fin_row[z + 2]; pR = fin_row[z + 3]; }
-#ifdef GOICP_DT_INSTRUMENT
-        if (threadIdx.x == 0) DT_STAT(any ? 7 : 6, clock64() - c_row0);
-#endif
+        if (ln.owned) G[((size_t)x * S + y) * S + z] = fin;
+        pL = fin_row[ln.zc - 1]; pC = fin_row[ln.zc]; pR = fin_row[ln.zc + 1];
         if (HAS_XS) {                                // slide the adjacent-slice window
             A_behind = A_cur; A_cur = A_ahead; B_cur = B_ahead;
             if (use_xs) fold_xrow(sh.xrow(par), A_ahead, B_ahead); else { A_ahead = v4_unset(); B_ahead = v4_unset(); }
@@ -293,12 +308,12 @@ __device__ void slice_pass(Vox* G, int S, int x, int xs, const RowSmem& sh)
 }
 
 __global__ void __launch_bounds__(1024)
-dt_propagate_kernel(Vox* G, int S)
+dt_propagate_kernel(V4* G, int S)
 {
     RowSmem sh;
-    sh.stride = (S + 4) * (int)sizeof(V4);
+    sh.stride = S + 4;
     // pads of the row buffers stay "unset" for the whole kernel
-    for (int i = threadIdx.x; i < 5 * (S + 4); i += blockDim.x) reinterpret_cast<V4*>(dt_smem)[i] = v4_unset();
+    for (int i = threadIdx.x; i < 5 * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
     __syncthreads();
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
         slice_pass<F1, C_DN, +1>(G, S, x, x - 1, sh);
@@ -310,100 +325,69 @@ dt_propagate_kernel(Vox* G, int S)
     }
 }
 
-// ---- the same propagation, warp-specialised ------------------------------------------------
-// Everything that does not depend on the row recurrence is taken off its critical path: the CTA
-// is split into CONSUMER warps (own/T from the previous row, the two scans, the speculation
-// check -- the recurrence proper, ~1/3 of the instructions) and PRODUCER warps, which run one row
-// ahead and do all global traffic and all adjacent-slice work: load and unpack the rows, fold the
-// 3x3 candidates of the adjacent slice into one candidate per voxel (p9), hand p9 and the voxel's
-// current value over through shared memory, and write final rows back two rows behind.  One
-// CTA-wide barrier per row step is the only synchronisation; redoing a row across the CTA uses a
-// named barrier among the consumer warps only.  A producer thread only ever touches its own
-// columns of G, so global memory needs no ordering beyond program order.
-constexpr int kSplitMaxS = 640;        // 32 warps must hold ceil(S/30) consumer warps and S/(32*VPT) producer warps
-constexpr int kLook = 2;               // producer global-load lookahead (row steps)
+// ---- variant 2: warp-specialised, rows moved by the TMA (S <= 640) ----------------------------
+// Everything that does not depend on the row recurrence is taken off its critical path.  The CTA
+// is split into
+//   CONSUMER warps   the recurrence proper: own/T from the previous row, the two scans, the
+//                    speculation check;
+//   PRODUCER warps   one row ahead: fold the 3x3 candidates of the adjacent slice into one
+//                    candidate per voxel (p9), and write final rows back to HBM two rows behind;
+//   one COPY warp    a single lane streams rows HBM -> shared memory with 1-D bulk copies
+//                    (cp.async.bulk + mbarrier complete_tx) into two rings, R rows deep: the rows
+//                    of the slice being updated (read by the consumers as "self") and the rows of
+//                    the adjacent slice (read by the producers).  Nobody computes a global address
+//                    or converts a format per voxel; the copy lane absorbs all HBM/L2 latency.
+// One CTA-wide barrier per row step is the only synchronisation (the copy lane waits for the bulk
+// copies a step before their rows are used, the barrier publishes them); redoing a row across the
+// CTA uses a named barrier among the consumer warps only.
+constexpr int kSplitMaxS = 640;
 
 struct SplitSmem {
     int stride;          // V4 elements of one padded row (S + 4), voxel z at index z+2
+    int R;               // ring depth (power of two)
     __device__ __forceinline__ V4* base() const { return reinterpret_cast<V4*>(dt_smem); }
-    __device__ __forceinline__ V4* fin(int k) const { return base() + k * stride; }            // final rows, ring of 4
-    __device__ __forceinline__ V4* p9(int k) const { return base() + (4 + k) * stride; }       // folded adjacent-slice candidate, by row parity
-    __device__ __forceinline__ V4* selfv(int k) const { return base() + (6 + k) * stride; }    // the voxel's value before this pass, by row parity
-    __device__ __forceinline__ V4* xrow(int k) const { return base() + (8 + k) * stride; }     // adjacent-slice row being folded (producers only)
-    __device__ __forceinline__ V4* xchg() const { return base() + 10 * stride; }               // CTA-wide resolution (consumers only)
-    __device__ __forceinline__ volatile int* flag() const { return reinterpret_cast<volatile int*>(base() + 11 * stride); }
+    __device__ __forceinline__ V4* fin(int k) const { return base() + k * stride; }                // final rows, ring of 4
+    __device__ __forceinline__ V4* p9(int k) const { return base() + (4 + k) * stride; }           // folded adjacent-slice candidate, by row parity
+    __device__ __forceinline__ V4* xchg() const { return base() + 6 * stride; }                    // CTA-wide resolution (consumers only)
+    __device__ __forceinline__ V4* selfv(int k) const { return base() + (7 + k) * stride; }        // ring: rows of the slice before this pass
+    __device__ __forceinline__ V4* xrow(int k) const { return base() + (7 + R + k) * stride; }     // ring: rows of the adjacent slice
+    __device__ __forceinline__ unsigned char* tail() const { return reinterpret_cast<unsigned char*>(base() + (7 + 2 * R) * stride); }
+    __device__ __forceinline__ volatile int* flag() const { return reinterpret_cast<volatile int*>(tail()); }
+    __device__ __forceinline__ unsigned full_s(int k) const { return (unsigned)__cvta_generic_to_shared(tail() + 16 + 8 * k); }
+    __device__ __forceinline__ unsigned full_x(int k) const { return (unsigned)__cvta_generic_to_shared(tail() + 16 + 8 * (R + k)); }
 };
-static size_t dt_split_smem(int S) { return 11 * (size_t)(S + 4) * sizeof(V4) + 16; }
+size_t dt_split_smem(int S, int R) { return (size_t)(7 + 2 * R) * (S + 4) * sizeof(V4) + 16 + 16 * (size_t)R; }
 
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
-__device__ __forceinline__ void bar_consumers(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
-__device__ __forceinline__ bool bar_consumers_or(int n, bool pred)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
-    unsigned r;
-    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(r) : "r"((unsigned)pred), "r"(n) : "memory");
-    return r != 0;
+    asm volatile("{\n.reg .pred P1;\nDT_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DT_DONE;\nbra DT_WAIT;\nDT_DONE:\n}"
+                 :: "r"(bar), "r"(parity) : "memory");
 }
-
-// one scan inside a warp, state carried packed through three shuffles
-template <int DIR>
-__device__ __forceinline__ V4 warp_resolve3(const V4 own, const int T, const int lane)
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar)
 {
-    const unsigned full = 0xffffffffu;
-    const bool has_pred = DIR > 0 ? lane > 0 : lane < 31;
-    const unsigned own_p = (unsigned)own.v | ((unsigned)own.h << 16);
-    unsigned p = own_p; int d = own.d, n = own.n;
-    while (true) {
-        const unsigned q = DIR > 0 ? __shfl_up_sync(full, p, 1) : __shfl_down_sync(full, p, 1);
-        const int od = DIR > 0 ? __shfl_up_sync(full, d, 1) : __shfl_down_sync(full, d, 1);
-        const int on = DIR > 0 ? __shfl_up_sync(full, n, 1) : __shfl_down_sync(full, n, 1);
-        const int nc = on + 2 * od + 1;                      // an unset predecessor gives nc > kInf >= T
-        const bool take = has_pred & (nc < T);
-        const unsigned np = take ? q : own_p; const int nd = take ? od + 1 : own.d;
-        const bool changed = (np != p) | (nd != d);
-        p = np; d = nd; n = take ? nc : own.n;
-        if (!__any_sync(full, changed)) break;
-    }
-    V4 r; r.v = (int)(p & 0xffffu); r.h = (int)(p >> 16); r.d = d; r.n = n;
-    return r;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int DIR>
-__device__ __noinline__ V4 consumers_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z, const int nthreads)
-{
-    while (true) {
-        if (owned) xchg[z + 2] = st;
-        bar_consumers(nthreads);
-        bool changed = false;
-        if (owned) {
-            const V4 nw = chain_rule(xchg[z + 2 - DIR], own, T);
-            changed = v4_differs(nw, st);
-            st = nw;
-        }
-        if (!bar_consumers_or(nthreads, changed)) break;
-    }
-    return st;
-}
-
-// Row steps s = -3 .. S+1 of one pass: the consumers work on row s, the producers emit p9/self of
-// row s+1, fold adjacent-slice row s+2, stage row s+3 and store final row s-2 (rows outside [0,S)
-// are "unset" / skipped).  Row index i maps to y = y0 + i*YDIR.
+// Row steps s = -2 .. S+1 of one pass (rows indexed along the pass: y = y0 + i*YDIR; rows outside
+// [0,S) are "unset" / skipped).  At step s
+//   consumers  resolve row s                      (reads self row s, p9 of row s, final row s-1)
+//   producers  fold adjacent row s+2 -> p9 of row s+1; store final row s-2
+//   copy lane  refills the ring slots freed at step s-1, then waits for self row s+1 and adjacent
+//              row s+3, which are first read at step s+1.
 template <int K1, int K2, int YDIR>
 __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const int ncons_threads, const int serial)
 {
-    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;
-    constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
-    static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int z = warp * kOwned + lane - 1;
-    const bool valid = z >= 0 && z < S;
-    const bool owned = valid && lane >= 1 && lane <= kOwned;
-    const int zc = min(max(z, -1), S) + 2;                   // lanes outside the row read the pads
-    const bool check1 = owned && (DIR1 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
-    const bool check2 = owned && (DIR2 > 0 ? (lane == kOwned && z + 1 < S) : (lane == 1 && z > 0));
-    if (owned) sh.fin(3)[z + 2] = v4_unset();                // "row -1" of this pass
-    for (int s = -3; s < S + 2; s++) {
+    constexpr int DIR2 = -DIR1;
+    const Lane ln(threadIdx.x >> 5, threadIdx.x & 31, S);
+    const int z = ln.z, Rm = sh.R - 1;
+    if (ln.owned) sh.fin(3)[z + 2] = v4_unset();             // "row -1" of this pass
+    bar_all();
+    for (int s = -2; s < S + 2; s++) {
         const bool act = s >= 0 && s < S;
         V4 own1 = v4_unset(), st1w = own1, fin_w = own1; int T1 = 0;
 #ifdef GOICP_DT_INSTRUMENT
@@ -411,24 +395,12 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 #endif
         if (act) {
             const V4* prev = sh.fin((s - 1) & 3);
-            const V4 pL = prev[zc - 1], pC = prev[zc], pR = prev[zc + 1];
-            const V4 self = sh.selfv(s & 1)[zc];
-            V4 P = v4_unset(), Q = v4_unset();
-            if (HAS_XS) P = sh.p9(s & 1)[zc];
-            if (K1 == F1 || K1 == B3) {              // previous row, then self; recurrence comes last
-                V4 P2 = v4_unset();
-                consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC);
-                consider<0, 1, 1>(P2, pR); consider<0, 0, 0>(P2, self);
-                fold(P, P2);
-            } else {                                 // recurrence first, then (z,y+-1), self, (z-1,y+-1)
-                consider<0, 1, 0>(Q, pC); consider<0, 0, 0>(Q, self); consider<0, 1, 1>(Q, pL);
-            }
-            own1 = P.n <= Q.n ? P : Q;
-            T1 = valid ? min(P.n, Q.n + 1) : 0;      // recurrence wins iff nc < nP and nc <= nQ; nothing passes a lane outside the row
-            st1w = warp_resolve3<DIR1>(own1, T1, lane);
-            fin_w = warp_resolve3<DIR2>(st1w, valid ? min(kInf, st1w.n + 1) : 0, lane);
-            const bool bad = (check1 && v4_differs(st1w, own1)) || (check2 && v4_differs(fin_w, st1w));
-            if (owned) sh.fin(s & 3)[z + 2] = fin_w;
+            const V4 pL = prev[ln.zc - 1], pC = prev[ln.zc], pR = prev[ln.zc + 1];
+            const V4 self = sh.selfv(s & Rm)[ln.zc];
+            const V4 p9 = sh.p9(s & 1)[ln.zc];
+            bool bad;
+            row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
+            if (ln.owned) sh.fin(s & 3)[z + 2] = fin_w;
             if (bad) sh.flag()[s & 1] = serial + s;
         }
 #ifdef GOICP_DT_INSTRUMENT
@@ -442,79 +414,57 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
             const bool any = sh.flag()[s & 1] == serial + s;
             DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
             if (any) {                               // a run crossed a warp boundary: resolve across the consumers
-                const V4 st1 = consumers_resolve<DIR1>(sh.xchg(), own1, T1, st1w, owned, z, ncons_threads);
-                const V4 fin = consumers_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, owned, z, ncons_threads);
-                if (owned) sh.fin(s & 3)[z + 2] = fin;
-                bar_consumers(ncons_threads);
+                const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, ncons_threads);
+                const V4 fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, ncons_threads);
+                if (ln.owned) sh.fin(s & 3)[z + 2] = fin;
+                bar_group(ncons_threads);
             }
         }
     }
 }
 
 template <int K1, int YDIR, int VPT>
-__device__ __forceinline__ void producer_pass(Vox* G, int S, int x, int xs, const SplitSmem& sh, const int ptid, const int nprod_threads)
+__device__ __forceinline__ void producer_pass(V4* G, int S, int x, int xs, const SplitSmem& sh, const int ptid, const int nprod_threads)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     const bool use_xs = HAS_XS && xs >= 0 && xs < S;
     const int y0 = YDIR > 0 ? 0 : S - 1;
-    Vox unset_g; unset_g.v = unset_g.h = unset_g.d = 32767; unset_g.pad = 0;
-    int zs[VPT]; bool zok[VPT];
+    const int Rm = sh.R - 1;
     V4 A_prev[VPT], X_prev[VPT];
-    Vox self_q[VPT][kLook], xs_q[VPT][kLook];
-#pragma unroll
-    for (int j = 0; j < VPT; j++) { zs[j] = ptid + j * nprod_threads; zok[j] = zs[j] < S; }
-    auto gload = [&](int xx, int i, int j) -> Vox {          // row index i of slice xx, this thread's column j
-        return (zok[j] && i >= 0 && i < S) ? G[((size_t)xx * S + (y0 + i * YDIR)) * S + zs[j]] : unset_g;
-    };
 #pragma unroll
     for (int j = 0; j < VPT; j++) {
         A_prev[j] = v4_unset(); X_prev[j] = v4_unset();
-#pragma unroll
-        for (int d = 0; d < kLook; d++) {                    // at step s the heads are self row s+1 and adjacent row s+3
-            self_q[j][d] = gload(x, -3 + 1 + d, j);
-            xs_q[j][d] = use_xs ? gload(xs, -3 + 3 + d, j) : unset_g;
-        }
+        const int z = ptid + j * nprod_threads;
+        if (HAS_XS && !use_xs && z < S) { sh.p9(0)[z + 2] = v4_unset(); sh.p9(1)[z + 2] = v4_unset(); }   // no adjacent slice: nothing to fold
     }
-    for (int s = -3; s < S + 2; s++) {
+    bar_all();
+    for (int s = -2; s < S + 2; s++) {
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_p0 = clock64();
 #endif
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
-            const int z = zs[j];
-            const Vox sv = self_q[j][0], xv = xs_q[j][0];
-#pragma unroll
-            for (int d = 0; d + 1 < kLook; d++) { self_q[j][d] = self_q[j][d + 1]; xs_q[j][d] = xs_q[j][d + 1]; }
-            self_q[j][kLook - 1] = gload(x, s + 1 + kLook, j);
-            xs_q[j][kLook - 1] = use_xs ? gload(xs, s + 3 + kLook, j) : unset_g;
-            if (zok[j]) {
-                {   // the volume (8 B/voxel) exceeds L2 at S=300: pull the rows needed some steps from now into L2
-                    const int ifar = s + 24;
-                    if ((z & 15) == 0 && ifar >= 0 && ifar < S) {
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + (y0 + ifar * YDIR)) * S + z));
-                        if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + (y0 + ifar * YDIR)) * S + z));
-                    }
-                }
-                if (HAS_XS) {
-                    sh.xrow(s & 1)[z + 2] = v4_from(xv);                      // stage adjacent row s+3 (unset outside the grid)
-                    if (s >= -2) {                                            // fold adjacent row s+2, staged at the previous step
-                        const V4* xr = sh.xrow((s - 1) & 1);
+            const int z = ptid + j * nprod_threads;
+            if (z < S) {
+                if (use_xs && s + 1 < S) {
+                    V4 A = v4_unset(), B = v4_unset();
+                    if (s + 2 < S) {                                              // row S is outside the grid
+                        const V4* xr = sh.xrow((s + 2) & Rm);
                         const V4 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
-                        V4 A = v4_unset(), B = v4_unset();
                         consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
                         consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
-                        // mask order of row s+1: adjacent rows y-1, y, y+1 = (s, s+1, s+2) for YDIR>0, reversed otherwise
-                        V4 p9, X;
-                        if (YDIR > 0) { p9 = X_prev[j]; fold(p9, A); X = A_prev[j]; fold(X, B); }
-                        else          { p9 = A; fold(p9, X_prev[j]); X = B; fold(X, A_prev[j]); }
-                        if (s + 1 >= 0 && s + 1 < S) sh.p9((s + 1) & 1)[z + 2] = p9;
-                        X_prev[j] = X; A_prev[j] = A;
                     }
+                    // mask order of row s+1: adjacent rows y-1, y, y+1 = (s, s+1, s+2) for YDIR>0, reversed otherwise
+                    V4 p9, X;
+                    if (YDIR > 0) { p9 = X_prev[j]; fold(p9, A); X = A_prev[j]; fold(X, B); }
+                    else          { p9 = A; fold(p9, X_prev[j]); X = B; fold(X, A_prev[j]); }
+                    if (s + 1 >= 0) sh.p9((s + 1) & 1)[z + 2] = p9;
+                    X_prev[j] = X; A_prev[j] = A;
                 }
-                if (s + 1 >= 0 && s + 1 < S) sh.selfv((s + 1) & 1)[z + 2] = v4_from(sv);
-                if (s - 2 >= 0 && s - 2 < S) G[((size_t)x * S + (y0 + (s - 2) * YDIR)) * S + z] = v4_to(sh.fin((s - 2) & 3)[z + 2]);
+                if (s - 2 >= 0 && s - 2 < S) G[((size_t)x * S + (y0 + (s - 2) * YDIR)) * S + z] = sh.fin((s - 2) & 3)[z + 2];
             }
         }
+        if (s == S + 1) fence_async_proxy();         // the rows just written are bulk-read by the next pass
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_p1 = clock64();
         bar_all();
@@ -525,23 +475,78 @@ __device__ __forceinline__ void producer_pass(Vox* G, int S, int x, int xs, cons
     }
 }
 
+template <int K1, int YDIR>
+__device__ __forceinline__ void copy_pass(const V4* G, int S, int x, int xs, const SplitSmem& sh, unsigned& ph_s, unsigned& ph_x)
+{
+    constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    const bool use_xs = HAS_XS && xs >= 0 && xs < S;
+    const int y0 = YDIR > 0 ? 0 : S - 1;
+    const int R = sh.R, Rm = R - 1;
+    const unsigned row_bytes = (unsigned)S * (unsigned)sizeof(V4);
+    const bool lead = (threadIdx.x & 31) == 0;
+    auto issue_self = [&](int r) {
+        if (r < 0 || r >= S) return;
+        const unsigned bar = sh.full_s(r & Rm);
+        mbar_expect_tx(bar, row_bytes);
+        bulk_load((unsigned)__cvta_generic_to_shared(sh.selfv(r & Rm) + 2), G + ((size_t)x * S + (y0 + r * YDIR)) * S, row_bytes, bar);
+    };
+    auto issue_x = [&](int r) {
+        if (!use_xs || r < 0 || r >= S) return;
+        const unsigned bar = sh.full_x(r & Rm);
+        mbar_expect_tx(bar, row_bytes);
+        bulk_load((unsigned)__cvta_generic_to_shared(sh.xrow(r & Rm) + 2), G + ((size_t)xs * S + (y0 + r * YDIR)) * S, row_bytes, bar);
+    };
+    auto wait_self = [&](int r) {
+        if (r < 0 || r >= S) return;
+        mbar_wait(sh.full_s(r & Rm), (ph_s >> (r & Rm)) & 1u); ph_s ^= 1u << (r & Rm);
+    };
+    auto wait_x = [&](int r) {
+        if (!use_xs || r < 0 || r >= S) return;
+        mbar_wait(sh.full_x(r & Rm), (ph_x >> (r & Rm)) & 1u); ph_x ^= 1u << (r & Rm);
+    };
+    if (lead) {
+        fence_async_proxy();
+        for (int r = 0; r <= R - 4; r++) issue_self(r);      // step s issues self row s-1+R and adjacent row s+1+R
+        for (int r = 0; r <= R - 2; r++) issue_x(r);
+        wait_x(0);                                           // folded at step -2
+    }
+    __syncwarp();
+    bar_all();
+    for (int s = -2; s < S + 2; s++) {
+        if (lead) {
+            issue_self(s - 1 + R); issue_x(s + 1 + R);
+            wait_self(s + 1); wait_x(s + 3);
+        }
+        __syncwarp();
+        bar_all();
+    }
+}
+
 template <int VPT>
 __global__ void __launch_bounds__(1024)
-dt_propagate_split_kernel(Vox* G, int S, int ncons_warps)
+dt_propagate_split_kernel(V4* G, int S, int ncons_warps, int nprod_warps, int R)
 {
     SplitSmem sh;
-    sh.stride = S + 4;
+    sh.stride = S + 4; sh.R = R;
     // pads of the row buffers stay "unset" for the whole kernel
-    for (int i = threadIdx.x; i < 11 * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
+    for (int i = threadIdx.x; i < (7 + 2 * R) * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
     if (threadIdx.x < 4) sh.flag()[threadIdx.x] = -1;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < R; k++) { mbar_init(sh.full_s(k), 1); mbar_init(sh.full_x(k), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_proxy();
+    }
     __syncthreads();
-    const bool consumer = (int)(threadIdx.x >> 5) < ncons_warps;
+    const int warp = threadIdx.x >> 5;
+    const int role = warp < ncons_warps ? 0 : (warp < ncons_warps + nprod_warps ? 1 : 2);
     const int nct = ncons_warps * 32;
-    const int ptid = (int)threadIdx.x - nct, npt = (int)blockDim.x - nct;
+    const int ptid = (int)threadIdx.x - nct, npt = nprod_warps * 32;
     int serial = 0;                                                // row steps get unique ids across passes
+    unsigned ph_s = 0, ph_x = 0;                                   // mbarrier phase bits per ring slot (copy lane)
 #define DT_PASS(K1, K2, YD, XX, XS) do { \
-        if (consumer) consumer_pass<K1, K2, YD>(S, sh, nct, serial); \
-        else producer_pass<K1, YD, VPT>(G, S, XX, XS, sh, ptid, npt); \
+        if (role == 0) consumer_pass<K1, K2, YD>(S, sh, nct, serial); \
+        else if (role == 1) producer_pass<K1, YD, VPT>(G, S, XX, XS, sh, ptid, npt); \
+        else copy_pass<K1, YD>(G, S, XX, XS, sh, ph_s, ph_x); \
         serial += 2048; } while (0)
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
         DT_PASS(F1, C_DN, +1, x, x - 1);
@@ -556,7 +561,7 @@ dt_propagate_split_kernel(Vox* G, int S, int ncons_warps)
 
 // distance = float( double(float(sqrt(double(n2)))) / scale ), clamped at 0 (jly_3ddt.cpp:970-978);
 // also transposes the working [x][y][z] layout into the reference's [z][y][x].
-__global__ void dt_finalize_kernel(const Vox* __restrict__ G, int S, double scale, float* __restrict__ out)
+__global__ void dt_finalize_kernel(const V4* __restrict__ G, int S, double scale, float* __restrict__ out)
 {
     __shared__ float tile[32][33];
     const int y = blockIdx.z;
@@ -564,8 +569,8 @@ __global__ void dt_finalize_kernel(const Vox* __restrict__ G, int S, double scal
     {
         const int x = x0 + threadIdx.y, z = z0 + threadIdx.x;
         if (x < S && z < S) {
-            const Vox a = G[((size_t)x * S + y) * S + z];
-            const double n2 = (double)a.v * (double)a.v + (double)((int)a.h * a.h) + (double)((int)a.d * a.d);
+            const V4 a = G[((size_t)x * S + y) * S + z];
+            const double n2 = (double)a.v * (double)a.v + (double)(a.h * a.h) + (double)(a.d * a.d);
             float dv = __double2float_rn(sqrt(n2));
             float r = __double2float_rn(__ddiv_rn((double)dv, scale));
             tile[threadIdx.y][threadIdx.x] = r < 0.0f ? 0.0f : r;
@@ -580,16 +585,16 @@ __global__ void dt_finalize_kernel(const Vox* __restrict__ G, int S, double scal
 
 // ---- exact EDT (separable, integer squared distances) ----------------------------------------
 // pass along z per (x,y) column: squared distance to the nearest seed in the column
-__global__ void edt_pass_z(const Vox* __restrict__ G, int S, int* __restrict__ D)
+__global__ void edt_pass_z(const V4* __restrict__ G, int S, int* __restrict__ D)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;      // x*S + y
     if (col >= S * S) return;
-    const Vox* g = G + (size_t)col * S;
+    const V4* g = G + (size_t)col * S;
     int* d = D + (size_t)col * S;
     int last = -kMaxS * 4;
-    for (int z = 0; z < S; z++) { if (g[z].v == 0 && g[z].h == 0 && g[z].d == 0) last = z; int k = z - last; d[z] = k > 4 * kMaxS - 1 ? kInf : k * k; }
+    for (int z = 0; z < S; z++) { if (g[z].n == 0) last = z; int k = z - last; d[z] = k > 4 * kMaxS - 1 ? kInf : k * k; }
     last = kMaxS * 8;
-    for (int z = S - 1; z >= 0; z--) { if (g[z].v == 0 && g[z].h == 0 && g[z].d == 0) last = z; int k = last - z; int v = k > 4 * kMaxS - 1 ? kInf : k * k; if (v < d[z]) d[z] = v; }
+    for (int z = S - 1; z >= 0; z--) { if (g[z].n == 0) last = z; int k = last - z; int v = k > 4 * kMaxS - 1 ? kInf : k * k; if (v < d[z]) d[z] = v; }
 }
 // generic 1-D min-plus pass along a strided line: out[i] = min_j in[j] + (i-j)^2
 __global__ void edt_pass_line(const int* __restrict__ in, int* __restrict__ out, int S, size_t line_stride_a, size_t line_stride_b, size_t elem_stride)
@@ -648,13 +653,14 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     if (mode == 0 && S > kMaxRefS) { msg = "dt_size > 960 in reference-order mode (use the exact EDT mode)"; return cudaErrorInvalidValue; }
     dt_frame_host(model, nm, S, expand, meta);
     const size_t n3 = (size_t)S * S * S;
-    Vox* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
+    V4* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
     auto cleanup = [&]() { if (G) cudaFree(G); if (d_model) cudaFree(d_model); if (D0) cudaFree(D0); if (D1) cudaFree(D1); };
 #define DT_TRY(expr) do { e = (expr); if (e != cudaSuccess) { msg = #expr; cleanup(); return e; } } while (0)
-    DT_TRY(cudaMalloc((void**)&G, n3 * sizeof(Vox)));
+    DT_TRY(cudaMalloc((void**)&G, n3 * sizeof(V4)));
     DT_TRY(cudaMalloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
     DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
-    dt_init_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, stream>>>(G, n3);
+    // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
+    dt_init_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, stream>>>(G, n3, mode == 0 ? 1 : 0);
     DT_TRY(cudaGetLastError());
     dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
     DT_TRY(cudaGetLastError());
@@ -664,16 +670,23 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         if (timing) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, stream); }
         const int ncons = (S + kOwned - 1) / kOwned;
         if (S <= kSplitMaxS && getenv("GOICP_DT_UNSPLIT") == nullptr) {
-            // producer warps: one voxel per thread while 32 warps suffice, else two
-            int nprod = (S + 31) / 32, vpt = 1;
-            if (ncons + nprod > 32) { nprod = 32 - ncons; vpt = 2; }
-            const size_t smem = dt_split_smem(S);
+            // producer warps: one voxel per thread while 32 warps suffice, else up to three; one copy warp
+            int nprod = (S + 31) / 32;
+            if (ncons + nprod + 1 > 32) nprod = 32 - 1 - ncons;
+            const int vpt = (S + nprod * 32 - 1) / (nprod * 32);                // <= 3 for S <= kSplitMaxS
+            int R = 8;
+            if (dt_split_smem(S, R) > 227 * 1024) R = 4;
+            const size_t smem = dt_split_smem(S, R);
+            const int threads = (ncons + nprod + 1) * 32;
             if (vpt == 1) {
                 DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dt_propagate_split_kernel<1><<<1, (ncons + nprod) * 32, smem, stream>>>(G, S, ncons);
-            } else {
+                dt_propagate_split_kernel<1><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
+            } else if (vpt == 2) {
                 DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dt_propagate_split_kernel<2><<<1, (ncons + nprod) * 32, smem, stream>>>(G, S, ncons);
+                dt_propagate_split_kernel<2><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
+            } else {
+                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dt_propagate_split_kernel<3><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
             }
         } else {
             const size_t smem = dt_propagate_smem(S);
@@ -699,10 +712,6 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, meta[3], d_out);
         DT_TRY(cudaGetLastError());
     } else {
-        // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
-        Vox unset; unset.v = unset.h = unset.d = 32767; unset.pad = 0;
-        DT_TRY(cudaMemcpyAsync(G, &unset, sizeof(Vox), cudaMemcpyHostToDevice, stream));
-        dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
         DT_TRY(cudaMalloc((void**)&D0, n3 * sizeof(int)));
         DT_TRY(cudaMalloc((void**)&D1, n3 * sizeof(int)));
         edt_pass_z<<<(S * S + 127) / 128, 128, 0, stream>>>(G, S, D0);
