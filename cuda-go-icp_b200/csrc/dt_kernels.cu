@@ -185,10 +185,28 @@ __device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, cons
     }
     own1 = P.n <= Q.n ? P : Q;
     T1 = ln.valid ? min(P.n, Q.n + 1) : 0;       // recurrence wins iff nc < nP and nc <= nQ; nothing passes a lane outside the row
-    st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
-    // chain scan K2: its input is the state after K1, its only other candidate the voxel itself
-    fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
-    bad = ((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) || ((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1));
+    // chain scan K2: its input is the state after K1, its only other candidate the voxel itself.
+    // First step of both scans at once, K2 under the assumption that K1 changes nothing: if no voxel
+    // of the warp takes its predecessor's candidate in either scan, the row keeps its own values.
+    {
+        const unsigned full = 0xffffffffu;
+        const unsigned own_p = (unsigned)own1.v | ((unsigned)own1.h << 16);
+        const unsigned up_p = __shfl_up_sync(full, own_p, 1), dn_p = __shfl_down_sync(full, own_p, 1);
+        const int up_d = __shfl_up_sync(full, own1.d, 1), dn_d = __shfl_down_sync(full, own1.d, 1);
+        const int up_n = __shfl_up_sync(full, own1.n, 1), dn_n = __shfl_down_sync(full, own1.n, 1);
+        const int T2 = ln.valid ? min(kInf, own1.n + 1) : 0;
+        const int nc_up = up_n + 2 * up_d + 1, nc_dn = dn_n + 2 * dn_d + 1;
+        const bool ch_up = (ln.lane > 0) & (nc_up < (DIR1 > 0 ? T1 : T2)) & ((up_p != own_p) | (up_d + 1 != own1.d));
+        const bool ch_dn = (ln.lane < 31) & (nc_dn < (DIR1 > 0 ? T2 : T1)) & ((dn_p != own_p) | (dn_d + 1 != own1.d));
+        const bool any1 = __any_sync(full, DIR1 > 0 ? ch_up : ch_dn);
+        const bool any2 = __any_sync(full, DIR1 > 0 ? ch_dn : ch_up);
+        st1 = own1; fin = own1; bad = false;
+        if (any1 | any2) {
+            if (any1) st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
+            fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
+            bad = ((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) || ((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1));
+        }
+    }
 }
 
 // ---- variant 1: every warp does everything (any S <= 960) -------------------------------------
@@ -386,41 +404,42 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
     const Lane ln(threadIdx.x >> 5, threadIdx.x & 31, S);
     const int z = ln.z, Rm = sh.R - 1;
     if (ln.owned) sh.fin(3)[z + 2] = v4_unset();             // "row -1" of this pass
-    bar_all();
-    for (int s = -2; s < S + 2; s++) {
-        const bool act = s >= 0 && s < S;
-        V4 own1 = v4_unset(), st1w = own1, fin_w = own1; int T1 = 0;
+    bar_all();                                               // prologue
+    bar_all(); bar_all();                                    // steps -2, -1: the producers and the copy lane fill the pipeline
+    // inputs of the coming step, loaded right after the barrier that publishes them
+    V4 pL = v4_unset(), pC = pL, pR = pL;
+    V4 self = sh.selfv(0)[ln.zc], p9 = sh.p9(0)[ln.zc];
+    for (int s = 0; s < S; s++) {
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w0 = clock64();
 #endif
-        if (act) {
-            const V4* prev = sh.fin((s - 1) & 3);
-            const V4 pL = prev[ln.zc - 1], pC = prev[ln.zc], pR = prev[ln.zc + 1];
-            const V4 self = sh.selfv(s & Rm)[ln.zc];
-            const V4 p9 = sh.p9(s & 1)[ln.zc];
-            bool bad;
-            row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
-            if (ln.owned) sh.fin(s & 3)[z + 2] = fin_w;
-            if (bad) sh.flag()[s & 1] = serial + s;
-        }
+        V4 own1, st1w, fin_w; int T1; bool bad;
+        row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
+        V4* cur = sh.fin(s & 3);
+        if (ln.owned) cur[z + 2] = fin_w;
+        if (bad) sh.flag()[s & 1] = serial + s;
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w1 = clock64();
         bar_all();
-        if (threadIdx.x == 0 && act) { DT_STAT(6, c_w1 - c_w0); DT_STAT(7, clock64() - c_w1); }
+        if (threadIdx.x == 0) { DT_STAT(6, c_w1 - c_w0); DT_STAT(7, clock64() - c_w1); }
 #else
         bar_all();
 #endif
-        if (act) {
-            const bool any = sh.flag()[s & 1] == serial + s;
-            DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
-            if (any) {                               // a run crossed a warp boundary: resolve across the consumers
-                const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, ncons_threads);
-                const V4 fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, ncons_threads);
-                if (ln.owned) sh.fin(s & 3)[z + 2] = fin;
-                bar_group(ncons_threads);
-            }
+        const int flagv = sh.flag()[s & 1];
+        pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
+        self = sh.selfv((s + 1) & Rm)[ln.zc];
+        p9 = sh.p9((s + 1) & 1)[ln.zc];
+        const bool any = flagv == serial + s;
+        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
+        if (any) {                                   // a run crossed a warp boundary: resolve across the consumers
+            const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, ncons_threads);
+            const V4 fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, ncons_threads);
+            if (ln.owned) cur[z + 2] = fin;
+            bar_group(ncons_threads);
+            pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
         }
     }
+    bar_all(); bar_all();                                    // steps S, S+1: the producers store the last rows
 }
 
 template <int K1, int YDIR, int VPT>
@@ -522,8 +541,8 @@ __device__ __forceinline__ void copy_pass(const V4* G, int S, int x, int xs, con
     }
 }
 
-template <int VPT>
-__global__ void __launch_bounds__(1024)
+template <int VPT, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 dt_propagate_split_kernel(V4* G, int S, int ncons_warps, int nprod_warps, int R)
 {
     SplitSmem sh;
@@ -678,16 +697,14 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
             if (dt_split_smem(S, R) > 227 * 1024) R = 4;
             const size_t smem = dt_split_smem(S, R);
             const int threads = (ncons + nprod + 1) * 32;
-            if (vpt == 1) {
-                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dt_propagate_split_kernel<1><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
-            } else if (vpt == 2) {
-                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dt_propagate_split_kernel<2><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
-            } else {
-                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dt_propagate_split_kernel<3><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R);
-            }
+#define DT_LAUNCH_SPLIT(VPT, MAXT) do { \
+                DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<VPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                dt_propagate_split_kernel<VPT, MAXT><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R); } while (0)
+            if (vpt == 1 && threads <= 704) DT_LAUNCH_SPLIT(1, 704);            // S <= 320: more registers per thread
+            else if (vpt == 1) DT_LAUNCH_SPLIT(1, 1024);
+            else if (vpt == 2) DT_LAUNCH_SPLIT(2, 1024);
+            else DT_LAUNCH_SPLIT(3, 1024);
+#undef DT_LAUNCH_SPLIT
         } else {
             const size_t smem = dt_propagate_smem(S);
             DT_TRY(cudaFuncSetAttribute(dt_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
