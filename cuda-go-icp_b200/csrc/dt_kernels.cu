@@ -167,7 +167,7 @@ struct Lane {
 // pass at z-1, z, z+1; p9 = folded candidates of the adjacent slice; self = the voxel's value so far.
 template <int K1, int K2>
 __device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, const V4 pC, const V4 pR, const V4 p9, const V4 self,
-                                               V4& own1, int& T1, V4& st1, V4& fin, bool& bad)
+                                               V4& own1, int& T1, V4& st1, V4& fin, int& bad)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;                       // +1: recurrence reads z-1
@@ -200,11 +200,11 @@ __device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, cons
         const bool ch_dn = (ln.lane < 31) & (nc_dn < (DIR1 > 0 ? T2 : T1)) & ((dn_p != own_p) | (dn_d + 1 != own1.d));
         const bool any1 = __any_sync(full, DIR1 > 0 ? ch_up : ch_dn);
         const bool any2 = __any_sync(full, DIR1 > 0 ? ch_dn : ch_up);
-        st1 = own1; fin = own1; bad = false;
+        st1 = own1; fin = own1; bad = 0;
         if (any1 | any2) {
             if (any1) st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
             fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
-            bad = ((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) || ((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1));
+            bad = (((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) ? 1 : 0) | (((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1)) ? 2 : 0);
         }
     }
 }
@@ -250,6 +250,26 @@ __device__ __noinline__ V4 group_resolve(V4* xchg, const V4 own, const int T, V4
             st = nw;
         }
         if (!bar_group_or(nthreads, changed)) break;
+    }
+    return st;
+}
+
+// The cheaper way to redo a row: exchange the states of the warps' downstream boundary voxels and
+// re-resolve inside the warps with the upstream shadow lane pinned to its voxel's true state, until
+// no boundary state moves (one round per warp boundary a run crosses).  Collective over `nthreads`.
+template <int DIR>
+__device__ __noinline__ V4 boundary_resolve(V4* xchg, const Lane& ln, const V4 own, const int T, V4 st, const int nthreads)
+{
+    const bool is_out = ln.owned && (DIR > 0 ? ln.lane == kOwned : ln.lane == 1);
+    const bool is_in = ln.valid && (DIR > 0 ? ln.lane == 0 : ln.lane == 31);
+    V4 in_state = own;                                       // what the warp assumed about its upstream shadow
+    while (true) {
+        if (is_out) xchg[ln.z + 2] = st;
+        bar_group(nthreads);
+        bool changed = false;
+        if (is_in) { const V4 t = xchg[ln.z + 2]; changed = v4_differs(t, in_state); in_state = t; }
+        if (!bar_group_or(nthreads, changed)) break;
+        st = warp_resolve<DIR>(is_in ? in_state : own, T, ln.lane);
     }
     return st;
 }
@@ -303,11 +323,11 @@ __device__ void slice_pass(V4* G, int S, int x, int xs, const RowSmem& sh)
             if (YDIR > 0) { fold(p9, A_behind); fold(p9, B_cur); fold(p9, A_ahead); }
             else          { fold(p9, A_ahead); fold(p9, B_cur); fold(p9, A_behind); }
         }
-        V4 own1, st1w, fin; int T1; bool bad;
+        V4 own1, st1w, fin; int T1, bad;
         row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin, bad);
         V4* fin_row = sh.fin(par);
         if (ln.owned) { fin_row[z + 2] = fin; if (use_xs) sh.xrow(par)[z + 2] = xs_new; }
-        const int any = __syncthreads_or(bad);
+        const int any = __syncthreads_or(bad != 0);
         DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
         if (any) {                                   // a run crossed a warp boundary: resolve across the CTA
             const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, blockDim.x);
@@ -413,11 +433,11 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w0 = clock64();
 #endif
-        V4 own1, st1w, fin_w; int T1; bool bad;
+        V4 own1, st1w, fin_w; int T1, bad;
         row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
         V4* cur = sh.fin(s & 3);
         if (ln.owned) cur[z + 2] = fin_w;
-        if (bad) sh.flag()[s & 1] = serial + s;
+        if (bad) { if (bad & 1) sh.flag()[s & 1] = serial + s; else sh.flag()[2 + (s & 1)] = serial + s; }
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w1 = clock64();
         bar_all();
@@ -425,15 +445,24 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 #else
         bar_all();
 #endif
-        const int flagv = sh.flag()[s & 1];
+        const int flag1 = sh.flag()[s & 1], flag2 = sh.flag()[2 + (s & 1)];
         pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
         self = sh.selfv((s + 1) & Rm)[ln.zc];
         p9 = sh.p9((s + 1) & 1)[ln.zc];
-        const bool any = flagv == serial + s;
-        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
-        if (any) {                                   // a run crossed a warp boundary: resolve across the consumers
-            const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, ncons_threads);
-            const V4 fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, ncons_threads);
+        const bool any1 = flag1 == serial + s, any2 = flag2 == serial + s;
+        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && (any1 || any2));
+        if (any1 | any2) {                           // a run crossed a warp boundary: settle the boundaries among the consumers
+            V4 st1 = st1w, fin = fin_w;
+            if (any1) {
+                st1 = boundary_resolve<DIR1>(sh.xchg(), ln, own1, T1, st1w, ncons_threads);
+                // the shadow lanes' copies of the neighbours' scan-1 states feed scan 2: refresh them
+                if (ln.owned) sh.xchg()[z + 2] = st1;
+                bar_group(ncons_threads);
+                if (ln.valid) st1 = sh.xchg()[z + 2];
+                bar_group(ncons_threads);
+                fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
+            }
+            fin = boundary_resolve<DIR2>(sh.xchg(), ln, st1, ln.valid ? min(kInf, st1.n + 1) : 0, fin, ncons_threads);
             if (ln.owned) cur[z + 2] = fin;
             bar_group(ncons_threads);
             pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
