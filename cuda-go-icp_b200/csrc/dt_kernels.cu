@@ -28,29 +28,33 @@ namespace {
 constexpr int kInf = 0x3fffffff;       // "no candidate" squared norm
 constexpr int kMaxS = 1024;
 
-// Working voxel, in HBM and on chip alike: the vector to the nearest seed found so far (component
-// magnitudes) and its squared norm; one 16-byte access.  "unset" = no seed seen yet.  A candidate
-// costs a handful of integer instructions:
-//   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1}.
-struct __align__(16) V4 { int v, h, d, n; };
+// Working voxel, in HBM and on chip alike, 8 bytes: the vector to the nearest seed found so far
+// (component magnitudes, 10 bits each: w = v | h<<10 | d<<20) and its squared norm n.  "unset"
+// (no seed seen yet) = all-ones components with n = kInf.  Shared-memory bandwidth and warp
+// shuffles are what the propagation kernel runs out of first, so the record is as small as the
+// arithmetic allows; a candidate still costs a handful of integer instructions:
+//   |(v+a, h+b, d+c)|^2 = n + 2(a v + b h + c d) + (a+b+c)   for a,b,c in {0,1},
+// and adding (a,b,c) to the vector is one add on w.
+struct __align__(8) V2 { unsigned w; int n; };
+constexpr unsigned kUnsetW = 0x3fffffffu;
 
-__device__ __forceinline__ V4 v4_unset() { V4 u; u.v = u.h = u.d = 32767; u.n = kInf; return u; }
-__device__ __forceinline__ bool v4_differs(const V4& a, const V4& b) { return (a.v != b.v) | (a.h != b.h) | (a.d != b.d); }
+__device__ __forceinline__ V2 v2_unset() { V2 u; u.w = kUnsetW; u.n = kInf; return u; }
+__device__ __forceinline__ int pitch_of(int S) { return (S + 1) & ~1; }       // rows of G are 16-byte aligned for the bulk copies
 
-__global__ void dt_init_kernel(V4* G, size_t n3, int corner_seed)
+__global__ void dt_init_kernel(V2* G, size_t n, int corner_seed)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n3) return;
-    V4 u = v4_unset();
+    if (i >= n) return;
+    V2 u = v2_unset();
     // As compiled (g++ 13.3 -O2) the reference's mask function returns (0,0,0) for the very first
     // voxel it visits, where no candidate qualifies and its result struct is uninitialised
     // (jly_3ddt.cpp:469-470): voxel (0,0,0) acts as one extra seed.  Pinned against oracle/_ref.
-    if (i == 0 && corner_seed) u.v = u.h = u.d = u.n = 0;
+    if (i == 0 && corner_seed) { u.w = 0; u.n = 0; }
     G[i] = u;
 }
 
 // seeds: ROUND((p - min)*scale) in double, points outside the grid skipped (jly_3ddt.cpp:952-966)
-__global__ void dt_seed_kernel(V4* G, int S, const float* __restrict__ model, int nm, double xmin, double ymin, double zmin, double scale)
+__global__ void dt_seed_kernel(V2* G, int S, int P, const float* __restrict__ model, int nm, double xmin, double ymin, double zmin, double scale)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nm) return;
@@ -58,8 +62,8 @@ __global__ void dt_seed_kernel(V4* G, int S, const float* __restrict__ model, in
     int y = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 1], ymin), scale), 0.5));
     int z = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 2], zmin), scale), 0.5));
     if (x < 0 || x >= S || y < 0 || y >= S || z < 0 || z >= S) return;
-    V4 s; s.v = s.h = s.d = s.n = 0;
-    G[((size_t)x * S + y) * S + z] = s;
+    V2 s; s.w = 0; s.n = 0;
+    G[((size_t)x * S + y) * P + z] = s;
 }
 
 // ---- the sequential propagation ------------------------------------------------------------
@@ -77,32 +81,38 @@ __global__ void dt_seed_kernel(V4* G, int S, const float* __restrict__ model, in
 // speculating that no run crosses into it.  The owner of a boundary voxel knows whether that
 // held (its state differs from its own value); the flags are gathered by the single barrier of
 // the row, which also publishes the row to the neighbours.  Rows where the speculation failed
-// (3 %) are redone by the same fixed-point iteration across the CTA through shared memory.
+// (3 %) exchange the warps' boundary states through shared memory and re-resolve.
 constexpr int kOwned = 30;             // voxels owned per warp
-constexpr int kMaxRefS = 32 * kOwned;  // 1024 threads
+constexpr int kMaxRefS = 32 * kOwned;  // 1024 threads; also keeps every component below the 10-bit unset marker
 
-// candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order.  An unset
-// source (n = kInf) scores above kInf and never wins (the reference scores it ~56755 > 32767).
+// IV*v + IH*h + ID*d out of the packed vector
 template <int IV, int IH, int ID>
-__device__ __forceinline__ void consider(V4& best, const V4 s)
+__device__ __forceinline__ int vec_dot(unsigned w)
 {
-    const int n = s.n + 2 * (IV * s.v + IH * s.h + ID * s.d) + (IV + IH + ID);
+    if (IV && IH && ID) return (int)((w & 1023u) + ((w >> 10) & 1023u) + (w >> 20));
+    if (IV && IH) { const unsigned y = w & 0xfffffu; return (int)((y & 1023u) + (y >> 10)); }
+    if (IV && ID) return (int)((w & 1023u) + (w >> 20));
+    if (IH && ID) { const unsigned x = w >> 10; return (int)((x & 1023u) + (x >> 10)); }
+    if (IV) return (int)(w & 1023u);
+    if (IH) return (int)((w >> 10) & 1023u);
+    if (ID) return (int)(w >> 20);
+    return 0;
+}
+// candidate = source + (IV,IH,ID); strict '<' keeps the first minimum in mask order.  An unset
+// source (n = kInf) scores above kInf and never wins (the reference scores it ~56755 > 32767);
+// its components overflow their fields harmlessly.
+template <int IV, int IH, int ID>
+__device__ __forceinline__ void consider(V2& best, const V2 s)
+{
+    const int n = s.n + 2 * vec_dot<IV, IH, ID>(s.w) + (IV + IH + ID);
     const bool take = n < best.n;
-    best.n = take ? n : best.n; best.v = take ? s.v + IV : best.v; best.h = take ? s.h + IH : best.h; best.d = take ? s.d + ID : best.d;
+    best.n = take ? n : best.n; best.w = take ? s.w + (unsigned)(IV | (IH << 10) | (ID << 20)) : best.w;
 }
 // fold an already-incremented candidate (first minimum in order)
-__device__ __forceinline__ void fold(V4& best, const V4 c)
+__device__ __forceinline__ void fold(V2& best, const V2 c)
 {
     const bool take = c.n < best.n;
-    best.n = take ? c.n : best.n; best.v = take ? c.v : best.v; best.h = take ? c.h : best.h; best.d = take ? c.d : best.d;
-}
-// the recurrence rule at one voxel: predecessor state o, own result, threshold T
-__device__ __forceinline__ V4 chain_rule(const V4 o, const V4 own, int T)
-{
-    const int nc = o.n + 2 * o.d + 1;            // an unset predecessor gives nc > kInf >= T
-    const bool take = nc < T;
-    V4 r; r.v = take ? o.v : own.v; r.h = take ? o.h : own.h; r.d = take ? o.d + 1 : own.d; r.n = take ? nc : own.n;
-    return r;
+    best.n = take ? c.n : best.n; best.w = take ? c.w : best.w;
 }
 
 // Row-scan kinds (mask functions of jly_3ddt.cpp and where the running-scan entry sits in the
@@ -122,29 +132,26 @@ __device__ unsigned long long g_dt_stats_buf[8];
 #define DT_STAT(i, v) ((void)0)
 #endif
 
-// One scan resolved inside a warp (DIR = +1: the predecessor is lane-1), state carried through
-// three shuffles (v,h < 2^15 share a word).  The lane at the upstream end has no predecessor in
-// the warp and keeps its own value -- the speculation.
+// One scan resolved inside a warp (DIR = +1: the predecessor is lane-1), state carried through two
+// shuffles.  The lane at the upstream end has no predecessor in the warp and keeps its own value
+// -- the speculation.
 template <int DIR>
-__device__ __forceinline__ V4 warp_resolve(const V4 own, const int T, const int lane)
+__device__ __forceinline__ V2 warp_resolve(const V2 own, const int T, const int lane)
 {
     const unsigned full = 0xffffffffu;
     const bool has_pred = DIR > 0 ? lane > 0 : lane < 31;
-    const unsigned own_p = (unsigned)own.v | ((unsigned)own.h << 16);
-    unsigned p = own_p; int d = own.d, n = own.n;
+    V2 st = own;
     while (true) {
-        const unsigned q = DIR > 0 ? __shfl_up_sync(full, p, 1) : __shfl_down_sync(full, p, 1);
-        const int od = DIR > 0 ? __shfl_up_sync(full, d, 1) : __shfl_down_sync(full, d, 1);
-        const int on = DIR > 0 ? __shfl_up_sync(full, n, 1) : __shfl_down_sync(full, n, 1);
-        const int nc = on + 2 * od + 1;
+        const unsigned ow = DIR > 0 ? __shfl_up_sync(full, st.w, 1) : __shfl_down_sync(full, st.w, 1);
+        const int on = DIR > 0 ? __shfl_up_sync(full, st.n, 1) : __shfl_down_sync(full, st.n, 1);
+        const int nc = on + 2 * (int)(ow >> 20) + 1;         // an unset predecessor gives nc > kInf >= T
         const bool take = has_pred & (nc < T);
-        const unsigned np = take ? q : own_p; const int nd = take ? od + 1 : own.d;
-        const bool changed = (np != p) | (nd != d);
-        p = np; d = nd; n = take ? nc : own.n;
+        const unsigned nw = take ? ow + (1u << 20) : own.w;
+        const bool changed = nw != st.w;
+        st.w = nw; st.n = take ? nc : own.n;
         if (!__any_sync(full, changed)) break;
     }
-    V4 r; r.v = (int)(p & 0xffffu); r.h = (int)(p >> 16); r.d = d; r.n = n;
-    return r;
+    return st;
 }
 
 // lane / voxel bookkeeping of a row-recurrence thread
@@ -165,18 +172,19 @@ struct Lane {
 
 // Both scans of one row for this lane's voxel, warp-local.  pL/pC/pR = final previous row of the
 // pass at z-1, z, z+1; p9 = folded candidates of the adjacent slice; self = the voxel's value so far.
+// bad: bit 0 = the speculation of scan K1 failed at this (boundary) voxel, bit 1 = that of scan K2.
 template <int K1, int K2>
-__device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, const V4 pC, const V4 pR, const V4 p9, const V4 self,
-                                               V4& own1, int& T1, V4& st1, V4& fin, int& bad)
+__device__ __forceinline__ void row_recurrence(const Lane& ln, const V2 pL, const V2 pC, const V2 pR, const V2 p9, const V2 self,
+                                               V2& own1, int& T1, V2& st1, V2& fin, int& bad)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;                       // +1: recurrence reads z-1
     constexpr int DIR2 = (K2 == C_UP) ? +1 : -1;
     static_assert(DIR1 == -DIR2, "the two scans of a row run in opposite directions");
-    V4 P = v4_unset(), Q = v4_unset();
+    V2 P = v2_unset(), Q = v2_unset();
     if (HAS_XS) P = p9;
     if (K1 == F1 || K1 == B3) {                  // previous row, then self; recurrence comes last
-        V4 P2 = v4_unset();
+        V2 P2 = v2_unset();
         consider<0, 1, 1>(P, pL); consider<0, 1, 0>(P, pC);
         consider<0, 1, 1>(P2, pR); consider<0, 0, 0>(P2, self);
         fold(P, P2);
@@ -188,25 +196,68 @@ __device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, cons
     // chain scan K2: its input is the state after K1, its only other candidate the voxel itself.
     // First step of both scans at once, K2 under the assumption that K1 changes nothing: if no voxel
     // of the warp takes its predecessor's candidate in either scan, the row keeps its own values.
-    {
-        const unsigned full = 0xffffffffu;
-        const unsigned own_p = (unsigned)own1.v | ((unsigned)own1.h << 16);
-        const unsigned up_p = __shfl_up_sync(full, own_p, 1), dn_p = __shfl_down_sync(full, own_p, 1);
-        const int up_d = __shfl_up_sync(full, own1.d, 1), dn_d = __shfl_down_sync(full, own1.d, 1);
-        const int up_n = __shfl_up_sync(full, own1.n, 1), dn_n = __shfl_down_sync(full, own1.n, 1);
-        const int T2 = ln.valid ? min(kInf, own1.n + 1) : 0;
-        const int nc_up = up_n + 2 * up_d + 1, nc_dn = dn_n + 2 * dn_d + 1;
-        const bool ch_up = (ln.lane > 0) & (nc_up < (DIR1 > 0 ? T1 : T2)) & ((up_p != own_p) | (up_d + 1 != own1.d));
-        const bool ch_dn = (ln.lane < 31) & (nc_dn < (DIR1 > 0 ? T2 : T1)) & ((dn_p != own_p) | (dn_d + 1 != own1.d));
-        const bool any1 = __any_sync(full, DIR1 > 0 ? ch_up : ch_dn);
-        const bool any2 = __any_sync(full, DIR1 > 0 ? ch_dn : ch_up);
-        st1 = own1; fin = own1; bad = 0;
-        if (any1 | any2) {
-            if (any1) st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
-            fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
-            bad = (((DIR1 > 0 ? ln.check_up : ln.check_dn) && v4_differs(st1, own1)) ? 1 : 0) | (((DIR2 > 0 ? ln.check_up : ln.check_dn) && v4_differs(fin, st1)) ? 2 : 0);
-        }
+    const unsigned full = 0xffffffffu;
+    const unsigned up_w = __shfl_up_sync(full, own1.w, 1), dn_w = __shfl_down_sync(full, own1.w, 1);
+    const int up_n = __shfl_up_sync(full, own1.n, 1), dn_n = __shfl_down_sync(full, own1.n, 1);
+    const int T2 = ln.valid ? min(kInf, own1.n + 1) : 0;
+    const int nc_up = up_n + 2 * (int)(up_w >> 20) + 1, nc_dn = dn_n + 2 * (int)(dn_w >> 20) + 1;
+    const bool ch_up = (ln.lane > 0) & (nc_up < (DIR1 > 0 ? T1 : T2)) & (up_w + (1u << 20) != own1.w);
+    const bool ch_dn = (ln.lane < 31) & (nc_dn < (DIR1 > 0 ? T2 : T1)) & (dn_w + (1u << 20) != own1.w);
+    const bool any1 = __any_sync(full, DIR1 > 0 ? ch_up : ch_dn);
+    const bool any2 = __any_sync(full, DIR1 > 0 ? ch_dn : ch_up);
+    st1 = own1; fin = own1; bad = 0;
+    if (any1 | any2) {
+        if (any1) st1 = warp_resolve<DIR1>(own1, T1, ln.lane);
+        fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
+        bad = (((DIR1 > 0 ? ln.check_up : ln.check_dn) && st1.w != own1.w) ? 1 : 0) | (((DIR2 > 0 ? ln.check_up : ln.check_dn) && fin.w != st1.w) ? 2 : 0);
     }
+}
+
+__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_group(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
+__device__ __forceinline__ bool bar_group_or(int n, bool pred)
+{
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(r) : "r"((unsigned)pred), "r"(n) : "memory");
+    return r != 0;
+}
+
+// Redo one scan of a row whose speculation failed: exchange the states of the warps' downstream
+// boundary voxels and re-resolve inside the warps with the upstream shadow lane pinned to its
+// voxel's true state, until no boundary state moves (one round per warp boundary a run crosses).
+// Collective over `nthreads` threads on named barrier 1.
+template <int DIR>
+__device__ __noinline__ V2 boundary_resolve(V2* xchg, const Lane& ln, const V2 own, const int T, V2 st, const int nthreads)
+{
+    const bool is_out = ln.owned && (DIR > 0 ? ln.lane == kOwned : ln.lane == 1);
+    const bool is_in = ln.valid && (DIR > 0 ? ln.lane == 0 : ln.lane == 31);
+    V2 in_state = own;                                       // what the warp assumed about its upstream shadow
+    while (true) {
+        if (is_out) xchg[ln.z + 2] = st;
+        bar_group(nthreads);
+        bool changed = false;
+        if (is_in) { const V2 t = xchg[ln.z + 2]; changed = t.w != in_state.w; in_state = t; }
+        if (!bar_group_or(nthreads, changed)) break;
+        st = warp_resolve<DIR>(is_in ? in_state : own, T, ln.lane);
+    }
+    return st;
+}
+// both scans redone; `which`: bit 0 = scan K1 failed somewhere, bit 1 = scan K2 failed somewhere
+template <int DIR1>
+__device__ __forceinline__ V2 settle_row(V2* xchg, const Lane& ln, const int which, const V2 own1, const int T1, const V2 st1w, const V2 fin_w, const int nthreads)
+{
+    V2 st1 = st1w, fin = fin_w;
+    if (which & 1) {
+        st1 = boundary_resolve<DIR1>(xchg, ln, own1, T1, st1w, nthreads);
+        // the shadow lanes' copies of the neighbours' scan-K1 states feed scan K2: refresh them
+        if (ln.owned) xchg[ln.z + 2] = st1;
+        bar_group(nthreads);
+        if (ln.valid) st1 = xchg[ln.z + 2];
+        bar_group(nthreads);
+        fin = warp_resolve<-DIR1>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
+    }
+    return boundary_resolve<-DIR1>(xchg, ln, st1, ln.valid ? min(kInf, st1.n + 1) : 0, fin, nthreads);
 }
 
 // ---- variant 1: every warp does everything (any S <= 960) -------------------------------------
@@ -218,83 +269,35 @@ __device__ __forceinline__ void row_recurrence(const Lane& ln, const V4 pL, cons
 // neighbour of a voxel one outside the row).  `fin` and `xrow` alternate by row parity: a row is
 // written before the row's barrier and read after it, the next row writes the other copy.
 struct RowSmem {
-    int stride;          // V4 elements of one padded row
-    __device__ __forceinline__ V4* base() const { return reinterpret_cast<V4*>(dt_smem); }
-    __device__ __forceinline__ V4* fin(int par) const { return base() + par * stride; }
-    __device__ __forceinline__ V4* xrow(int par) const { return base() + (2 + par) * stride; }
-    __device__ __forceinline__ V4* xchg() const { return base() + 4 * stride; }
+    int stride;          // voxels of one padded row
+    __device__ __forceinline__ V2* base() const { return reinterpret_cast<V2*>(dt_smem); }
+    __device__ __forceinline__ V2* fin(int par) const { return base() + par * stride; }
+    __device__ __forceinline__ V2* xrow(int par) const { return base() + (2 + par) * stride; }
+    __device__ __forceinline__ V2* xchg() const { return base() + 4 * stride; }
+    __device__ __forceinline__ volatile int* flag() const { return reinterpret_cast<volatile int*>(base() + 5 * stride); }
 };
-size_t dt_propagate_smem(int S) { return 5 * (size_t)(S + 4) * sizeof(V4); }
-
-// The fixed-point iteration across the whole row through shared memory (collective over `nthreads`
-// threads on named barrier 1; with nthreads == blockDim.x that is the whole CTA).
-__device__ __forceinline__ void bar_all() { asm volatile("bar.sync 0;" ::: "memory"); }
-__device__ __forceinline__ void bar_group(int n) { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
-__device__ __forceinline__ bool bar_group_or(int n, bool pred)
-{
-    unsigned r;
-    asm volatile("{ .reg .pred p, q; setp.ne.u32 q, %1, 0; bar.red.or.pred p, 1, %2, q; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(r) : "r"((unsigned)pred), "r"(n) : "memory");
-    return r != 0;
-}
-template <int DIR>
-__device__ __noinline__ V4 group_resolve(V4* xchg, const V4 own, const int T, V4 st, const bool owned, const int z, const int nthreads)
-{
-    while (true) {
-        if (owned) xchg[z + 2] = st;
-        bar_group(nthreads);
-        bool changed = false;
-        if (owned) {
-            const V4 nw = chain_rule(xchg[z + 2 - DIR], own, T);
-            changed = v4_differs(nw, st);
-            st = nw;
-        }
-        if (!bar_group_or(nthreads, changed)) break;
-    }
-    return st;
-}
-
-// The cheaper way to redo a row: exchange the states of the warps' downstream boundary voxels and
-// re-resolve inside the warps with the upstream shadow lane pinned to its voxel's true state, until
-// no boundary state moves (one round per warp boundary a run crosses).  Collective over `nthreads`.
-template <int DIR>
-__device__ __noinline__ V4 boundary_resolve(V4* xchg, const Lane& ln, const V4 own, const int T, V4 st, const int nthreads)
-{
-    const bool is_out = ln.owned && (DIR > 0 ? ln.lane == kOwned : ln.lane == 1);
-    const bool is_in = ln.valid && (DIR > 0 ? ln.lane == 0 : ln.lane == 31);
-    V4 in_state = own;                                       // what the warp assumed about its upstream shadow
-    while (true) {
-        if (is_out) xchg[ln.z + 2] = st;
-        bar_group(nthreads);
-        bool changed = false;
-        if (is_in) { const V4 t = xchg[ln.z + 2]; changed = v4_differs(t, in_state); in_state = t; }
-        if (!bar_group_or(nthreads, changed)) break;
-        st = warp_resolve<DIR>(is_in ? in_state : own, T, ln.lane);
-    }
-    return st;
-}
+size_t dt_propagate_smem(int S) { return 5 * (size_t)(S + 6) * sizeof(V2) + 16; }
 
 // one pass over the rows of slice x: scan K1 then chain scan K2 on every row, rows in direction YDIR
 template <int K1, int K2, int YDIR>
-__device__ void slice_pass(V4* G, int S, int x, int xs, const RowSmem& sh)
+__device__ void slice_pass(V2* G, int S, int x, int xs, const RowSmem& sh, const int serial)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;
-    constexpr int DIR2 = -DIR1;
     const Lane ln(threadIdx.x >> 5, threadIdx.x & 31, S);
-    const int z = ln.z;
+    const int z = ln.z, P = pitch_of(S);
     const bool use_xs = HAS_XS && xs >= 0 && xs < S;
     const int y0 = YDIR > 0 ? 0 : S - 1;
-    auto gload = [&](int xx, int yy) -> V4 { return (ln.valid && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * S + z] : v4_unset(); };
+    auto gload = [&](int xx, int yy) -> V2 { return (ln.valid && yy >= 0 && yy < S) ? G[((size_t)xx * S + yy) * P + z] : v2_unset(); };
     // folded candidates of one adjacent-slice row for column z: A = row offset +-1, B = same row
-    auto fold_xrow = [&](const V4* xr, V4& A, V4& B) {
-        A = v4_unset(); B = v4_unset();
-        const V4 l = xr[ln.zc - 1], c = xr[ln.zc], r = xr[ln.zc + 1];
+    auto fold_xrow = [&](const V2* xr, V2& A, V2& B) {
+        A = v2_unset(); B = v2_unset();
+        const V2 l = xr[ln.zc - 1], c = xr[ln.zc], r = xr[ln.zc + 1];
         consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
         consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
     };
     // adjacent-slice window: rows y-YDIR ("behind", outside the grid at the first row), y, y+YDIR
-    V4 A_behind = v4_unset(), A_cur = v4_unset(), B_cur = v4_unset(), A_ahead = v4_unset(), B_ahead = v4_unset();
+    V2 A_behind = v2_unset(), A_cur = v2_unset(), B_cur = v2_unset(), A_ahead = v2_unset(), B_ahead = v2_unset();
     if (use_xs) {
         if (ln.owned) { sh.xrow(0)[z + 2] = gload(xs, y0); sh.xrow(1)[z + 2] = gload(xs, y0 + YDIR); }
         __syncthreads();
@@ -302,64 +305,67 @@ __device__ void slice_pass(V4* G, int S, int x, int xs, const RowSmem& sh)
         fold_xrow(sh.xrow(1), A_ahead, B_ahead);
         __syncthreads();
     }
-    V4 self_next = gload(x, y0);
-    V4 xs_next = (use_xs && ln.owned) ? gload(xs, y0 + 2 * YDIR) : v4_unset();
-    V4 pL = v4_unset(), pC = v4_unset(), pR = v4_unset();    // final previous row of this pass at z-1, z, z+1
+    V2 self_next = gload(x, y0);
+    V2 xs_next = (use_xs && ln.owned) ? gload(xs, y0 + 2 * YDIR) : v2_unset();
+    V2 pL = v2_unset(), pC = v2_unset(), pR = v2_unset();    // final previous row of this pass at z-1, z, z+1
     for (int i = 0, y = y0; i < S; i++, y += YDIR) {
         const int par = i & 1;
-        const V4 self = self_next;
-        const V4 xs_new = xs_next;                          // adjacent-slice row y + 2*YDIR: enters the window at the next row
+        const V2 self = self_next;
+        const V2 xs_new = xs_next;                          // adjacent-slice row y + 2*YDIR: enters the window at the next row
         self_next = gload(x, y + YDIR);                     // own column only
-        xs_next = (use_xs && ln.owned) ? gload(xs, y + 3 * YDIR) : v4_unset();
+        xs_next = (use_xs && ln.owned) ? gload(xs, y + 3 * YDIR) : v2_unset();
         {   // the volume exceeds L2 at S=300: pull the rows needed some iterations from now into L2
             const int yf = y + 16 * YDIR;
-            if (ln.owned && (z & 7) == 0 && yf >= 0 && yf < S) {
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + yf) * S + z));
-                if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + yf) * S + z));
+            if (ln.owned && (z & 15) == 0 && yf >= 0 && yf < S) {
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)x * S + yf) * P + z));
+                if (use_xs) asm volatile("prefetch.global.L2 [%0];" :: "l"(G + ((size_t)xs * S + yf) * P + z));
             }
         }
-        V4 p9 = v4_unset();
+        V2 p9 = v2_unset();
         if (HAS_XS) {                                       // mask order: row y-1, row y, row y+1 of the adjacent slice
             if (YDIR > 0) { fold(p9, A_behind); fold(p9, B_cur); fold(p9, A_ahead); }
             else          { fold(p9, A_ahead); fold(p9, B_cur); fold(p9, A_behind); }
         }
-        V4 own1, st1w, fin; int T1, bad;
+        V2 own1, st1w, fin; int T1, bad;
         row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin, bad);
-        V4* fin_row = sh.fin(par);
+        V2* fin_row = sh.fin(par);
         if (ln.owned) { fin_row[z + 2] = fin; if (use_xs) sh.xrow(par)[z + 2] = xs_new; }
-        const int any = __syncthreads_or(bad != 0);
-        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && any);
-        if (any) {                                   // a run crossed a warp boundary: resolve across the CTA
-            const V4 st1 = group_resolve<DIR1>(sh.xchg(), own1, T1, st1w, ln.owned, z, blockDim.x);
-            fin = group_resolve<DIR2>(sh.xchg(), st1, min(kInf, st1.n + 1), st1, ln.owned, z, blockDim.x);
+        if (bad) { if (bad & 1) sh.flag()[par] = serial + i; else sh.flag()[2 + par] = serial + i; }
+        __syncthreads();
+        const int which = (sh.flag()[par] == serial + i ? 1 : 0) | (sh.flag()[2 + par] == serial + i ? 2 : 0);
+        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && which);
+        if (which) {                                 // a run crossed a warp boundary: settle the boundaries across the CTA
+            fin = settle_row<DIR1>(sh.xchg(), ln, which, own1, T1, st1w, fin, blockDim.x);
             if (ln.owned) fin_row[z + 2] = fin;
             __syncthreads();
         }
-        if (ln.owned) G[((size_t)x * S + y) * S + z] = fin;
+        if (ln.owned) G[((size_t)x * S + y) * P + z] = fin;
         pL = fin_row[ln.zc - 1]; pC = fin_row[ln.zc]; pR = fin_row[ln.zc + 1];
         if (HAS_XS) {                                // slide the adjacent-slice window
             A_behind = A_cur; A_cur = A_ahead; B_cur = B_ahead;
-            if (use_xs) fold_xrow(sh.xrow(par), A_ahead, B_ahead); else { A_ahead = v4_unset(); B_ahead = v4_unset(); }
+            if (use_xs) fold_xrow(sh.xrow(par), A_ahead, B_ahead); else { A_ahead = v2_unset(); B_ahead = v2_unset(); }
         }
     }
     __syncthreads();
 }
 
 __global__ void __launch_bounds__(1024)
-dt_propagate_kernel(V4* G, int S)
+dt_propagate_kernel(V2* G, int S)
 {
     RowSmem sh;
-    sh.stride = S + 4;
+    sh.stride = S + 6;
     // pads of the row buffers stay "unset" for the whole kernel
-    for (int i = threadIdx.x; i < 5 * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
+    for (int i = threadIdx.x; i < 5 * (S + 6); i += blockDim.x) sh.base()[i] = v2_unset();
+    if (threadIdx.x < 4) sh.flag()[threadIdx.x] = -1;
     __syncthreads();
+    int serial = 0;                                                 // rows get unique ids across passes
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
-        slice_pass<F1, C_DN, +1>(G, S, x, x - 1, sh);
-        slice_pass<F3, C_UP, -1>(G, S, x, -1, sh);
+        slice_pass<F1, C_DN, +1>(G, S, x, x - 1, sh, serial); serial += 1024;
+        slice_pass<F3, C_UP, -1>(G, S, x, -1, sh, serial); serial += 1024;
     }
     for (int x = S - 1; x >= 0; x--) {                              // :729-739
-        slice_pass<B1, C_UP, -1>(G, S, x, x + 1, sh);
-        slice_pass<B3, C_DN, +1>(G, S, x, -1, sh);
+        slice_pass<B1, C_UP, -1>(G, S, x, x + 1, sh, serial); serial += 1024;
+        slice_pass<B3, C_DN, +1>(G, S, x, -1, sh, serial); serial += 1024;
     }
 }
 
@@ -376,25 +382,25 @@ dt_propagate_kernel(V4* G, int S)
 //                    the adjacent slice (read by the producers).  Nobody computes a global address
 //                    or converts a format per voxel; the copy lane absorbs all HBM/L2 latency.
 // One CTA-wide barrier per row step is the only synchronisation (the copy lane waits for the bulk
-// copies a step before their rows are used, the barrier publishes them); redoing a row across the
-// CTA uses a named barrier among the consumer warps only.
+// copies a step before their rows are used, the barrier publishes them); settling a row whose
+// speculation failed uses a named barrier among the consumer warps only.
 constexpr int kSplitMaxS = 640;
+constexpr int kRing = 8;               // rows of lookahead of the bulk copies
 
 struct SplitSmem {
-    int stride;          // V4 elements of one padded row (S + 4), voxel z at index z+2
-    int R;               // ring depth (power of two)
-    __device__ __forceinline__ V4* base() const { return reinterpret_cast<V4*>(dt_smem); }
-    __device__ __forceinline__ V4* fin(int k) const { return base() + k * stride; }                // final rows, ring of 4
-    __device__ __forceinline__ V4* p9(int k) const { return base() + (4 + k) * stride; }           // folded adjacent-slice candidate, by row parity
-    __device__ __forceinline__ V4* xchg() const { return base() + 6 * stride; }                    // CTA-wide resolution (consumers only)
-    __device__ __forceinline__ V4* selfv(int k) const { return base() + (7 + k) * stride; }        // ring: rows of the slice before this pass
-    __device__ __forceinline__ V4* xrow(int k) const { return base() + (7 + R + k) * stride; }     // ring: rows of the adjacent slice
-    __device__ __forceinline__ unsigned char* tail() const { return reinterpret_cast<unsigned char*>(base() + (7 + 2 * R) * stride); }
+    int stride;          // voxels of one padded row (pitch + 4), voxel z at index z+2; rows are 16-byte aligned
+    __device__ __forceinline__ V2* base() const { return reinterpret_cast<V2*>(dt_smem); }
+    __device__ __forceinline__ V2* fin(int k) const { return base() + k * stride; }                // final rows, ring of 4
+    __device__ __forceinline__ V2* p9(int k) const { return base() + (4 + k) * stride; }           // folded adjacent-slice candidate, by row parity
+    __device__ __forceinline__ V2* xchg() const { return base() + 6 * stride; }                    // boundary exchange (consumers only)
+    __device__ __forceinline__ V2* selfv(int k) const { return base() + (7 + k) * stride; }        // ring: rows of the slice before this pass
+    __device__ __forceinline__ V2* xrow(int k) const { return base() + (7 + kRing + k) * stride; } // ring: rows of the adjacent slice
+    __device__ __forceinline__ unsigned char* tail() const { return reinterpret_cast<unsigned char*>(base() + (7 + 2 * kRing) * stride); }
     __device__ __forceinline__ volatile int* flag() const { return reinterpret_cast<volatile int*>(tail()); }
     __device__ __forceinline__ unsigned full_s(int k) const { return (unsigned)__cvta_generic_to_shared(tail() + 16 + 8 * k); }
-    __device__ __forceinline__ unsigned full_x(int k) const { return (unsigned)__cvta_generic_to_shared(tail() + 16 + 8 * (R + k)); }
+    __device__ __forceinline__ unsigned full_x(int k) const { return (unsigned)__cvta_generic_to_shared(tail() + 16 + 8 * (kRing + k)); }
 };
-size_t dt_split_smem(int S, int R) { return (size_t)(7 + 2 * R) * (S + 4) * sizeof(V4) + 16 + 16 * (size_t)R; }
+size_t dt_split_smem(int S) { return (size_t)(7 + 2 * kRing) * (((S + 1) & ~1) + 4) * sizeof(V2) + 16 + 16 * (size_t)kRing; }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
@@ -420,22 +426,21 @@ template <int K1, int K2, int YDIR>
 __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const int ncons_threads, const int serial)
 {
     constexpr int DIR1 = (K1 == F1 || K1 == B3) ? +1 : -1;
-    constexpr int DIR2 = -DIR1;
     const Lane ln(threadIdx.x >> 5, threadIdx.x & 31, S);
-    const int z = ln.z, Rm = sh.R - 1;
-    if (ln.owned) sh.fin(3)[z + 2] = v4_unset();             // "row -1" of this pass
+    const int z = ln.z;
+    if (ln.owned) sh.fin(3)[z + 2] = v2_unset();             // "row -1" of this pass
     bar_all();                                               // prologue
     bar_all(); bar_all();                                    // steps -2, -1: the producers and the copy lane fill the pipeline
     // inputs of the coming step, loaded right after the barrier that publishes them
-    V4 pL = v4_unset(), pC = pL, pR = pL;
-    V4 self = sh.selfv(0)[ln.zc], p9 = sh.p9(0)[ln.zc];
+    V2 pL = v2_unset(), pC = pL, pR = pL;
+    V2 self = sh.selfv(0)[ln.zc], p9 = sh.p9(0)[ln.zc];
     for (int s = 0; s < S; s++) {
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w0 = clock64();
 #endif
-        V4 own1, st1w, fin_w; int T1, bad;
+        V2 own1, st1w, fin_w; int T1, bad;
         row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
-        V4* cur = sh.fin(s & 3);
+        V2* cur = sh.fin(s & 3);
         if (ln.owned) cur[z + 2] = fin_w;
         if (bad) { if (bad & 1) sh.flag()[s & 1] = serial + s; else sh.flag()[2 + (s & 1)] = serial + s; }
 #ifdef GOICP_DT_INSTRUMENT
@@ -447,22 +452,12 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 #endif
         const int flag1 = sh.flag()[s & 1], flag2 = sh.flag()[2 + (s & 1)];
         pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
-        self = sh.selfv((s + 1) & Rm)[ln.zc];
+        self = sh.selfv((s + 1) & (kRing - 1))[ln.zc];
         p9 = sh.p9((s + 1) & 1)[ln.zc];
-        const bool any1 = flag1 == serial + s, any2 = flag2 == serial + s;
-        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && (any1 || any2));
-        if (any1 | any2) {                           // a run crossed a warp boundary: settle the boundaries among the consumers
-            V4 st1 = st1w, fin = fin_w;
-            if (any1) {
-                st1 = boundary_resolve<DIR1>(sh.xchg(), ln, own1, T1, st1w, ncons_threads);
-                // the shadow lanes' copies of the neighbours' scan-1 states feed scan 2: refresh them
-                if (ln.owned) sh.xchg()[z + 2] = st1;
-                bar_group(ncons_threads);
-                if (ln.valid) st1 = sh.xchg()[z + 2];
-                bar_group(ncons_threads);
-                fin = warp_resolve<DIR2>(st1, ln.valid ? min(kInf, st1.n + 1) : 0, ln.lane);
-            }
-            fin = boundary_resolve<DIR2>(sh.xchg(), ln, st1, ln.valid ? min(kInf, st1.n + 1) : 0, fin, ncons_threads);
+        const int which = (flag1 == serial + s ? 1 : 0) | (flag2 == serial + s ? 2 : 0);
+        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && which);
+        if (which) {                                 // a run crossed a warp boundary: settle the boundaries among the consumers
+            const V2 fin = settle_row<DIR1>(sh.xchg(), ln, which, own1, T1, st1w, fin_w, ncons_threads);
             if (ln.owned) cur[z + 2] = fin;
             bar_group(ncons_threads);
             pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
@@ -472,18 +467,17 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 }
 
 template <int K1, int YDIR, int VPT>
-__device__ __forceinline__ void producer_pass(V4* G, int S, int x, int xs, const SplitSmem& sh, const int ptid, const int nprod_threads)
+__device__ __forceinline__ void producer_pass(V2* G, int S, int x, int xs, const SplitSmem& sh, const int ptid, const int nprod_threads)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
     const bool use_xs = HAS_XS && xs >= 0 && xs < S;
-    const int y0 = YDIR > 0 ? 0 : S - 1;
-    const int Rm = sh.R - 1;
-    V4 A_prev[VPT], X_prev[VPT];
+    const int y0 = YDIR > 0 ? 0 : S - 1, P = pitch_of(S);
+    V2 A_prev[VPT], X_prev[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; j++) {
-        A_prev[j] = v4_unset(); X_prev[j] = v4_unset();
+        A_prev[j] = v2_unset(); X_prev[j] = v2_unset();
         const int z = ptid + j * nprod_threads;
-        if (HAS_XS && !use_xs && z < S) { sh.p9(0)[z + 2] = v4_unset(); sh.p9(1)[z + 2] = v4_unset(); }   // no adjacent slice: nothing to fold
+        if (HAS_XS && !use_xs && z < S) { sh.p9(0)[z + 2] = v2_unset(); sh.p9(1)[z + 2] = v2_unset(); }   // no adjacent slice: nothing to fold
     }
     bar_all();
     for (int s = -2; s < S + 2; s++) {
@@ -495,21 +489,21 @@ __device__ __forceinline__ void producer_pass(V4* G, int S, int x, int xs, const
             const int z = ptid + j * nprod_threads;
             if (z < S) {
                 if (use_xs && s + 1 < S) {
-                    V4 A = v4_unset(), B = v4_unset();
+                    V2 A = v2_unset(), B = v2_unset();
                     if (s + 2 < S) {                                              // row S is outside the grid
-                        const V4* xr = sh.xrow((s + 2) & Rm);
-                        const V4 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
+                        const V2* xr = sh.xrow((s + 2) & (kRing - 1));
+                        const V2 l = xr[z + 1], c = xr[z + 2], r = xr[z + 3];
                         consider<1, 1, 1>(A, l); consider<1, 1, 0>(A, c); consider<1, 1, 1>(A, r);
                         consider<1, 0, 1>(B, l); consider<1, 0, 0>(B, c); consider<1, 0, 1>(B, r);
                     }
                     // mask order of row s+1: adjacent rows y-1, y, y+1 = (s, s+1, s+2) for YDIR>0, reversed otherwise
-                    V4 p9, X;
+                    V2 p9, X;
                     if (YDIR > 0) { p9 = X_prev[j]; fold(p9, A); X = A_prev[j]; fold(X, B); }
                     else          { p9 = A; fold(p9, X_prev[j]); X = B; fold(X, A_prev[j]); }
                     if (s + 1 >= 0) sh.p9((s + 1) & 1)[z + 2] = p9;
                     X_prev[j] = X; A_prev[j] = A;
                 }
-                if (s - 2 >= 0 && s - 2 < S) G[((size_t)x * S + (y0 + (s - 2) * YDIR)) * S + z] = sh.fin((s - 2) & 3)[z + 2];
+                if (s - 2 >= 0 && s - 2 < S) G[((size_t)x * S + (y0 + (s - 2) * YDIR)) * P + z] = sh.fin((s - 2) & 3)[z + 2];
             }
         }
         if (s == S + 1) fence_async_proxy();         // the rows just written are bulk-read by the next pass
@@ -524,25 +518,25 @@ __device__ __forceinline__ void producer_pass(V4* G, int S, int x, int xs, const
 }
 
 template <int K1, int YDIR>
-__device__ __forceinline__ void copy_pass(const V4* G, int S, int x, int xs, const SplitSmem& sh, unsigned& ph_s, unsigned& ph_x)
+__device__ __forceinline__ void copy_pass(const V2* G, int S, int x, int xs, const SplitSmem& sh, unsigned& ph_s, unsigned& ph_x)
 {
     constexpr bool HAS_XS = (K1 == F1 || K1 == B1);
+    constexpr int R = kRing, Rm = kRing - 1;
     const bool use_xs = HAS_XS && xs >= 0 && xs < S;
-    const int y0 = YDIR > 0 ? 0 : S - 1;
-    const int R = sh.R, Rm = R - 1;
-    const unsigned row_bytes = (unsigned)S * (unsigned)sizeof(V4);
+    const int y0 = YDIR > 0 ? 0 : S - 1, P = pitch_of(S);
+    const unsigned row_bytes = (unsigned)P * (unsigned)sizeof(V2);           // the pad voxel of an odd row is "unset" and lands on a pad
     const bool lead = (threadIdx.x & 31) == 0;
     auto issue_self = [&](int r) {
         if (r < 0 || r >= S) return;
         const unsigned bar = sh.full_s(r & Rm);
         mbar_expect_tx(bar, row_bytes);
-        bulk_load((unsigned)__cvta_generic_to_shared(sh.selfv(r & Rm) + 2), G + ((size_t)x * S + (y0 + r * YDIR)) * S, row_bytes, bar);
+        bulk_load((unsigned)__cvta_generic_to_shared(sh.selfv(r & Rm) + 2), G + ((size_t)x * S + (y0 + r * YDIR)) * P, row_bytes, bar);
     };
     auto issue_x = [&](int r) {
         if (!use_xs || r < 0 || r >= S) return;
         const unsigned bar = sh.full_x(r & Rm);
         mbar_expect_tx(bar, row_bytes);
-        bulk_load((unsigned)__cvta_generic_to_shared(sh.xrow(r & Rm) + 2), G + ((size_t)xs * S + (y0 + r * YDIR)) * S, row_bytes, bar);
+        bulk_load((unsigned)__cvta_generic_to_shared(sh.xrow(r & Rm) + 2), G + ((size_t)xs * S + (y0 + r * YDIR)) * P, row_bytes, bar);
     };
     auto wait_self = [&](int r) {
         if (r < 0 || r >= S) return;
@@ -572,15 +566,15 @@ __device__ __forceinline__ void copy_pass(const V4* G, int S, int x, int xs, con
 
 template <int VPT, int MAXT>
 __global__ void __launch_bounds__(MAXT)
-dt_propagate_split_kernel(V4* G, int S, int ncons_warps, int nprod_warps, int R)
+dt_propagate_split_kernel(V2* G, int S, int ncons_warps, int nprod_warps)
 {
     SplitSmem sh;
-    sh.stride = S + 4; sh.R = R;
+    sh.stride = pitch_of(S) + 4;
     // pads of the row buffers stay "unset" for the whole kernel
-    for (int i = threadIdx.x; i < (7 + 2 * R) * (S + 4); i += blockDim.x) sh.base()[i] = v4_unset();
+    for (int i = threadIdx.x; i < (7 + 2 * kRing) * sh.stride; i += blockDim.x) sh.base()[i] = v2_unset();
     if (threadIdx.x < 4) sh.flag()[threadIdx.x] = -1;
     if (threadIdx.x == 0) {
-        for (int k = 0; k < R; k++) { mbar_init(sh.full_s(k), 1); mbar_init(sh.full_x(k), 1); }
+        for (int k = 0; k < kRing; k++) { mbar_init(sh.full_s(k), 1); mbar_init(sh.full_x(k), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_async_proxy();
     }
@@ -595,7 +589,7 @@ dt_propagate_split_kernel(V4* G, int S, int ncons_warps, int nprod_warps, int R)
         if (role == 0) consumer_pass<K1, K2, YD>(S, sh, nct, serial); \
         else if (role == 1) producer_pass<K1, YD, VPT>(G, S, XX, XS, sh, ptid, npt); \
         else copy_pass<K1, YD>(G, S, XX, XS, sh, ph_s, ph_x); \
-        serial += 2048; } while (0)
+        serial += 1024; } while (0)
     for (int x = 0; x < S; x++) {                                   // jly_3ddt.cpp:719-728
         DT_PASS(F1, C_DN, +1, x, x - 1);
         DT_PASS(F3, C_UP, -1, x, -1);
@@ -609,7 +603,7 @@ dt_propagate_split_kernel(V4* G, int S, int ncons_warps, int nprod_warps, int R)
 
 // distance = float( double(float(sqrt(double(n2)))) / scale ), clamped at 0 (jly_3ddt.cpp:970-978);
 // also transposes the working [x][y][z] layout into the reference's [z][y][x].
-__global__ void dt_finalize_kernel(const V4* __restrict__ G, int S, double scale, float* __restrict__ out)
+__global__ void dt_finalize_kernel(const V2* __restrict__ G, int S, int P, double scale, float* __restrict__ out)
 {
     __shared__ float tile[32][33];
     const int y = blockIdx.z;
@@ -617,8 +611,8 @@ __global__ void dt_finalize_kernel(const V4* __restrict__ G, int S, double scale
     {
         const int x = x0 + threadIdx.y, z = z0 + threadIdx.x;
         if (x < S && z < S) {
-            const V4 a = G[((size_t)x * S + y) * S + z];
-            const double n2 = (double)a.v * (double)a.v + (double)(a.h * a.h) + (double)(a.d * a.d);
+            const V2 a = G[((size_t)x * S + y) * P + z];
+            const double n2 = (double)a.n;                   // = v^2 + h^2 + d^2 exactly, as the reference's double sum
             float dv = __double2float_rn(sqrt(n2));
             float r = __double2float_rn(__ddiv_rn((double)dv, scale));
             tile[threadIdx.y][threadIdx.x] = r < 0.0f ? 0.0f : r;
@@ -633,11 +627,11 @@ __global__ void dt_finalize_kernel(const V4* __restrict__ G, int S, double scale
 
 // ---- exact EDT (separable, integer squared distances) ----------------------------------------
 // pass along z per (x,y) column: squared distance to the nearest seed in the column
-__global__ void edt_pass_z(const V4* __restrict__ G, int S, int* __restrict__ D)
+__global__ void edt_pass_z(const V2* __restrict__ G, int S, int P, int* __restrict__ D)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;      // x*S + y
     if (col >= S * S) return;
-    const V4* g = G + (size_t)col * S;
+    const V2* g = G + (size_t)col * P;
     int* d = D + (size_t)col * S;
     int last = -kMaxS * 4;
     for (int z = 0; z < S; z++) { if (g[z].n == 0) last = z; int k = z - last; d[z] = k > 4 * kMaxS - 1 ? kInf : k * k; }
@@ -701,16 +695,18 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     if (mode == 0 && S > kMaxRefS) { msg = "dt_size > 960 in reference-order mode (use the exact EDT mode)"; return cudaErrorInvalidValue; }
     dt_frame_host(model, nm, S, expand, meta);
     const size_t n3 = (size_t)S * S * S;
-    V4* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
+    const int P = (S + 1) & ~1;
+    const size_t ng = (size_t)S * S * P;
+    V2* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
     auto cleanup = [&]() { if (G) cudaFree(G); if (d_model) cudaFree(d_model); if (D0) cudaFree(D0); if (D1) cudaFree(D1); };
 #define DT_TRY(expr) do { e = (expr); if (e != cudaSuccess) { msg = #expr; cleanup(); return e; } } while (0)
-    DT_TRY(cudaMalloc((void**)&G, n3 * sizeof(V4)));
+    DT_TRY(cudaMalloc((void**)&G, ng * sizeof(V2)));
     DT_TRY(cudaMalloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
     DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
     // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
-    dt_init_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, stream>>>(G, n3, mode == 0 ? 1 : 0);
+    dt_init_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(G, ng, mode == 0 ? 1 : 0);
     DT_TRY(cudaGetLastError());
-    dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
+    dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, P, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
     DT_TRY(cudaGetLastError());
     if (mode == 0) {
         const bool timing = getenv("GOICP_DT_TIMING") != nullptr;
@@ -722,13 +718,11 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
             int nprod = (S + 31) / 32;
             if (ncons + nprod + 1 > 32) nprod = 32 - 1 - ncons;
             const int vpt = (S + nprod * 32 - 1) / (nprod * 32);                // <= 3 for S <= kSplitMaxS
-            int R = 8;
-            if (dt_split_smem(S, R) > 227 * 1024) R = 4;
-            const size_t smem = dt_split_smem(S, R);
+            const size_t smem = dt_split_smem(S);
             const int threads = (ncons + nprod + 1) * 32;
 #define DT_LAUNCH_SPLIT(VPT, MAXT) do { \
                 DT_TRY(cudaFuncSetAttribute(dt_propagate_split_kernel<VPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                dt_propagate_split_kernel<VPT, MAXT><<<1, threads, smem, stream>>>(G, S, ncons, nprod, R); } while (0)
+                dt_propagate_split_kernel<VPT, MAXT><<<1, threads, smem, stream>>>(G, S, ncons, nprod); } while (0)
             if (vpt == 1 && threads <= 704) DT_LAUNCH_SPLIT(1, 704);            // S <= 320: more registers per thread
             else if (vpt == 1) DT_LAUNCH_SPLIT(1, 1024);
             else if (vpt == 2) DT_LAUNCH_SPLIT(2, 1024);
@@ -751,16 +745,16 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
             unsigned long long hs[8];
             DT_TRY(cudaStreamSynchronize(stream));
             DT_TRY(cudaMemcpyFromSymbol(hs, g_dt_stats_buf, sizeof hs));
-            fprintf(stderr, "[dt stats] rows %llu, resolved across the CTA %llu; per row: consumer work %.0f wait %.0f, producer work %.0f wait %.0f cycles\n", hs[4], hs[5], (double)hs[6] / hs[4], (double)hs[7] / hs[4], (double)hs[2] / hs[4], (double)hs[3] / hs[4]);
+            fprintf(stderr, "[dt stats] rows %llu, settled across warps %llu; per row: consumer work %.0f wait %.0f, producer work %.0f wait %.0f cycles\n", hs[4], hs[5], (double)hs[6] / hs[4], (double)hs[7] / hs[4], (double)hs[2] / hs[4], (double)hs[3] / hs[4]);
         }
 #endif
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);
-        dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, meta[3], d_out);
+        dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, P, meta[3], d_out);
         DT_TRY(cudaGetLastError());
     } else {
         DT_TRY(cudaMalloc((void**)&D0, n3 * sizeof(int)));
         DT_TRY(cudaMalloc((void**)&D1, n3 * sizeof(int)));
-        edt_pass_z<<<(S * S + 127) / 128, 128, 0, stream>>>(G, S, D0);
+        edt_pass_z<<<(S * S + 127) / 128, 128, 0, stream>>>(G, S, P, D0);
         DT_TRY(cudaGetLastError());
         // along y: lines indexed by (x, z): base = x*S*S + z, element stride S
         edt_pass_line<<<dim3(S, S), 128, S * sizeof(int), stream>>>(D0, D1, S, (size_t)S * S, 1, (size_t)S);

@@ -134,6 +134,25 @@ def test_dt_build_reference_mode_bit_exact_small(pkg, small, bunny, S):
     g.close()
 
 
+@pytest.mark.parametrize("S,unsplit", [(31, False), (61, False), (61, True), (100, True), (95, False)])
+def test_dt_build_reference_mode_vs_oracle_odd_sizes_and_both_kernels(pkg, restated, bunny, S, unsplit, monkeypatch):
+    """Odd grid sizes (padded row pitch), several warps with ragged tails, and both propagation
+    kernels (warp-specialised / single-role) against the restated DT3D::Build, bit for bit."""
+    if unsplit:
+        monkeypatch.setenv("GOICP_DT_UNSPLIT", "1")
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = bunny["model_s"], bunny["data_s"]
+    g.dt.SIZE = S
+    g.BuildDT()
+    grid, meta = g.GetDT()
+    g.close()
+    dt = restated.dt_build(bunny["model_s"], S)
+    want = restated.dt_grid(dt, S)
+    restated.dt_free(dt)
+    assert np.array_equal(meta, restated.dt_frame(bunny["model_s"], S))
+    assert np.array_equal(grid.view(np.uint32), want.view(np.uint32))
+
+
 def test_dt_build_exact_edt_mode(pkg, small, bunny):
     from scipy import ndimage
     g = pkg.GoICP(1e-3)
