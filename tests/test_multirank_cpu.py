@@ -33,7 +33,8 @@ WORKER = textwrap.dedent('''
     ub = torch.tensor([3.5 - rank], dtype=torch.float32)
     dist.all_reduce(ub, op=dist.ReduceOp.MIN)
     assert ub.item() == 3.5 - (world - 1)
-    print("RANK", rank, "mismatches", bad_total)
+    sys.stdout.write("RANK {} mismatches {}\\n".format(rank, bad_total))   # one write: ranks must not interleave
+    sys.stdout.flush()
     dist.destroy_process_group()
 ''')
 
