@@ -52,6 +52,10 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1b_ncu_full_selected.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.5e6}
+
+
 def load(name):
     return np.fromfile(os.path.join(GOLDEN, name), np.float32).reshape(-1, 3)
 
@@ -135,6 +139,38 @@ def cpu_reference_sample(wl, seconds):
             "dt_build_s": dt_s}
 
 
+def cpu_reference_job(wl):
+    """One whole job of the reference CPU Go-ICP on this workload: DT build + full Register, timed
+    separately (oracle/_ref when built, else the C restatement)."""
+    from oracle import oracle as orc
+    model, data = load(wl["model"]), load(wl["data"])
+    if orc.Reference.available():
+        rf = orc.Reference()
+        g = rf.create(model, data, wl["mse"], 0.0, wl["S"])
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        sys.stdout.flush()
+        os.dup2(devnull, 1)                     # the reference narrates on stdout
+        try:
+            dt_s = rf.build_dt(g)
+            counter = ctypes.c_longlong.in_dll(rf.L, "ref_select_calls")
+            c0, t0 = counter.value, time.perf_counter()
+            rf.register(g)
+            c1, t1 = counter.value, time.perf_counter()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(devnull)
+        return {"kind": "reference", "dt_build_s": dt_s, "register_s": t1 - t0, "job_s": dt_s + (t1 - t0),
+                "register_rate": wl["ref_evals"] / (t1 - t0), "select_calls": c1 - c0}
+    rs = orc.Restated()
+    g = rs.create(model, data, wl["mse"], 0.0, wl["S"])
+    t0 = time.perf_counter(); rs.L.go_build_dt(g); dt_s = time.perf_counter() - t0
+    r = rs.register(g)
+    return {"kind": "port", "dt_build_s": dt_s, "register_s": r["register_s"], "job_s": dt_s + r["register_s"],
+            "register_rate": r["bound_evals"] / r["register_s"], "select_calls": r["bound_evals"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,18 +192,42 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = []
-        for _ in range(max(1, args.steps)):
-            steps.append(cpu_reference_sample(wl, args.cpu_seconds))
-        v = float(np.mean([s["value"] for s in steps]))
-        base = steps[-1]
-        base["value"] = v
+        # One step = the whole job the GPU arm's e2e times: DT build + Register of the workload, by the
+        # reference's own CPU code (1 thread: src/goicp has no threading).  A full bunny job is ~30 s
+        # on the B200 host, so steps are capped to a ~200 s budget (at least one); a workload whose
+        # full job does not fit (the certified one, ~6 min) is sampled for --cpu-seconds of Register
+        # and the whole-job figure is derived from its known evaluation count (flagged).
         config.update(Nd=len(load(wl["data"])), Nm=len(load(wl["model"])))
+        budget_s, steps, t_begin = 200.0, [], time.perf_counter()
+        full = wl["ref_register_s"] < 120.0
+        while len(steps) < max(1, args.steps):
+            st = cpu_reference_job(wl) if full else cpu_reference_sample(wl, args.cpu_seconds)
+            steps.append(st)
+            spent = time.perf_counter() - t_begin
+            if spent + spent / len(steps) > budget_s:
+                break
+        if full:
+            job_s = float(np.mean([s["job_s"] for s in steps]))
+            v = wl["ref_evals"] / job_s
+            reg_rate = float(np.mean([s["register_rate"] for s in steps]))
+            sample = (f"{len(steps)} full job(s): DT build {np.mean([s['dt_build_s'] for s in steps]):.1f} s + GoICP::Register "
+                      f"{np.mean([s['register_s'] for s in steps]):.1f} s, {wl['ref_evals']} bound evaluations each")
+            span = "measured"
+        else:
+            reg_rate = float(np.mean([s["value"] for s in steps]))
+            dt_s = float(np.mean([s["dt_build_s"] for s in steps]))
+            job_s = dt_s + wl["ref_evals"] / reg_rate
+            v = wl["ref_evals"] / job_s
+            sample = steps[-1]["sample"] + f"; whole job derived: DT {dt_s:.1f} s + {wl['ref_evals']} evals / measured rate"
+            span = "derived from a bounded sample"
+        base = {"value": v, "unit": "bound-evals/s", "cores": 1, "kind": steps[-1]["kind"], "sample": sample,
+                "span": "DT build + Register (the span of the GPU arm's e2e), " + span,
+                "register_only_bound_evals_per_s": reg_rate, "job_seconds": job_s}
         print(json.dumps({"impl": "reference", "metric": "goicp_bound_evals_per_sec", "value": v, "unit": "bound-evals/s",
-                          "n_gpus": 0, "steps": len(steps), "warmup": 0, "ms_per_step": 1e3 * args.cpu_seconds,
+                          "n_gpus": 0, "steps": len(steps), "warmup": 0, "ms_per_step": 1e3 * job_s,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                           "data": "reference bunny scans, deterministic subsample (committed fixtures)", "config": config,
-                          "cpu_baseline": base,
+                          "time_to_optimum_s": job_s, "cpu_baseline": base,
                           "e2e": {"value": v, "unit": "bound-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -282,7 +342,8 @@ def main():
     lookups = executed * len(data)
     achieved = lookups * 32 / kern_s / 1e9
     roofline = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1b_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
+                "algorithmic_bytes_per_launch": lookups * 32 / max(1, sum(r["rounds"] for r in results)), "peak_source": peak_src,
                 "basis": "32 B sector per DT lookup (SURVEY 8d); lookups = executed bound evals * Nd; 300^3 fp32 DT (108 MB) is L2-resident",
                 "launches": int(sum(r["rounds"] for r in results)), "avg_launch_ms": 1e3 * kern_s / max(1, sum(r["rounds"] for r in results)),
                 "gather": gather}
