@@ -133,7 +133,7 @@ struct goicp_handle {
     DevBuf<CandList> d_cands; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
     int64_t strict_resolves = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
-    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_order; DevBuf<unsigned long long> d_icp_keys; int icp_blocks = 0;
+    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
     InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
 
@@ -436,7 +436,10 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     size_t npad = 1; while (npad < (size_t)h->nd) npad <<= 1;
     CUDA_TRY(h, h->d_icp_q.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd));
     CUDA_TRY(h, h->d_icp_keys.reserve(npad)); CUDA_TRY(h, h->d_icp_stage.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_order.reserve(h->nd));
-    IcpWork wk; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p; wk.order = h->d_icp_order.p;
+    // radix-sort scratch of the large-cloud path: second key buffer, digit-major histogram (256 x warps of the grid) + 1024 chunk totals
+    const size_t hist_n = (size_t)256 * icp_max_blocks_supported() * (icp_threads() / 32);
+    CUDA_TRY(h, h->d_icp_keys2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_hist.reserve(hist_n + 1024));
+    IcpWork wk; wk.keys2 = h->d_icp_keys2.p; wk.hist = h->d_icp_hist.p; wk.blocksum = h->d_icp_hist.p + hist_n; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p; wk.order = h->d_icp_order.p;
     IcpState st; std::memset(&st, 0, sizeof st);
     for (int i = 0; i < 9; i++) st.R[i] = R0[i];
     for (int i = 0; i < 3; i++) st.t[i] = t0[i];
@@ -447,7 +450,7 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     // queries are interleaved over the CTAs, 32 per CTA and pass: use every SM the cooperative launch allows
-    const int blocks = std::max(1, std::min(max_blocks, (h->nd + 31) / 32));
+    const int blocks = std::max(1, std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32));
     CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->max_smem_optin, h->stream));
     h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
@@ -517,7 +520,7 @@ int goicp_destroy(goicp_handle* h)
         cudaSetDevice(h->p.device);
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
-        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_order.release();
+        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
         if (h->h_results) cudaFreeHost(h->h_results);
         if (h->h_tasks) cudaFreeHost(h->h_tasks);
         if (h->ev0) cudaEventDestroy(h->ev0);

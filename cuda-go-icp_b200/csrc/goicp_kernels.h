@@ -46,12 +46,16 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
     unsigned long long* keys;   // nd sort keys (d2 bits << 32 | point index)
     int32_t* order;         // nd: order[rank] = point index, ranks by key
     float* stage;           // 8*nd: correspondences in sorted order
+    unsigned long long* keys2;  // nd: second key buffer of the radix sort (large clouds)
+    unsigned* hist;         // 256 * (warps of the grid): digit-major histogram / scanned bases of the radix sort
+    unsigned* blocksum;     // 1024: per-CTA chunk totals of that scan
 };
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s);
 int icp_threads();
+int icp_max_blocks_supported();   // CTAs the in-kernel radix sort's scan supports
 int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin);
 
 } // namespace goicp

@@ -5,6 +5,7 @@
 // Replaces ICP3D<float>::Run (jly_icp3d.hpp:180-295), KDTreeSingleIndexAdaptor::searchLevel
 // (nanoflann_goicp.hpp:1136-1184) and Matrix::svd (matrix.cpp:602-830) for the GPU.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include "goicp_kernels.h"
 
 namespace cg = cooperative_groups;
@@ -352,7 +353,112 @@ __device__ void icp_update(IcpState* st, const float* H)
 constexpr int kIcpChunk = 384;
 
 // dynamic shared memory plan of the ICP kernel (decided on the host)
-struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; };
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; };
+
+// ------------------------------------------------------------------------------------------
+// Phase B for clouds too large to rank by counting (the keys no longer fit in shared memory and
+// the O(nd^2) count would stream them through L2 nd times): a grid-wide, STABLE least-significant
+// -digit radix sort of the 64-bit keys over the 32 distance bits, 8 bits per pass.  The keys enter
+// in point order, so stability reproduces the (d^2, index) order the counting version produces.
+// Every warp of the grid owns one contiguous slice of the array:
+//   1. per-warp digit histogram (shared-memory atomics)           -> hist[digit][warp]   grid.sync
+//   2. exclusive scan of that digit-major table, one chunk per CTA -> + chunk totals      grid.sync
+//   3. each warp re-walks its slice in order, 32 keys at a time: match_any groups equal digits,
+//      rank within the group = earlier lanes, destination = scanned base + running count  grid.sync
+// ------------------------------------------------------------------------------------------
+constexpr int kRadixBlockOffs = 1024;          // max CTAs of the cooperative grid the scan supports
+constexpr int kRadixSmemBytes = (kIcpThreads / 32 * 256 + 96 + kRadixBlockOffs) * 4;
+
+__device__ void icp_radix_sort(cg::grid_group& grid, const IcpWork& wk, int nd, unsigned* sm)
+{
+    constexpr int kWarps = kIcpThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int NW = (int)gridDim.x * kWarps, gw = (int)blockIdx.x * kWarps + warp;
+    int per = (nd + NW - 1) / NW; per = (per + 31) & ~31;
+    const int r0 = (int)min((long long)gw * per, (long long)nd), r1 = min(r0 + per, nd);
+    unsigned* wh = sm + warp * 256;                     // this warp's histogram, then its running bases
+    unsigned* sscan = sm + kWarps * 256;                // [0..31] warp totals, [32..63] exclusive, [64] block total
+    unsigned* boff = sscan + 96;                        // exclusive scan of the chunk totals
+    const int M = 256 * NW;
+    const int chunk = (M + (int)gridDim.x - 1) / (int)gridDim.x;
+    unsigned long long* src = wk.keys; unsigned long long* dst = wk.keys2;
+    for (int pass = 0; pass < 4; pass++) {
+        const int shift = 32 + 8 * pass;
+        // ---- 1. histogram of this warp's slice
+        for (int d = lane; d < 256; d += 32) wh[d] = 0u;
+        __syncwarp();
+        for (int i = r0 + lane; i < r1; i += 32) atomicAdd(&wh[(unsigned)(__ldcg(src + i) >> shift) & 255u], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) wk.hist[(size_t)d * NW + gw] = wh[d];
+        grid.sync();
+        // ---- 2. chunk-local exclusive scan (in place) + chunk total
+        {
+            const int e0 = min((int)blockIdx.x * chunk, M), e1 = min(e0 + chunk, M);
+            const int ept = (chunk + kIcpThreads - 1) / kIcpThreads;
+            const int t0 = min(e0 + (int)threadIdx.x * ept, e1), t1 = min(t0 + ept, e1);
+            unsigned s = 0;
+            for (int e = t0; e < t1; e++) s += __ldcg(wk.hist + e);
+            unsigned incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            if (lane == 31) sscan[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const unsigned v = lane < kWarps ? sscan[lane] : 0u;
+                unsigned iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+                sscan[32 + lane] = iv - v;
+                if (lane == 31) sscan[64] = iv;
+            }
+            __syncthreads();
+            unsigned run = sscan[32 + warp] + incl - s;
+            for (int e = t0; e < t1; e++) { const unsigned v = __ldcg(wk.hist + e); wk.hist[e] = run; run += v; }
+            if (threadIdx.x == 0) wk.blocksum[blockIdx.x] = sscan[64];
+        }
+        grid.sync();
+        // ---- 3. stable scatter
+        if (warp == 0) {
+            unsigned carry = 0;
+            for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32) {
+                const unsigned v = b0 + lane < (int)gridDim.x ? __ldcg(wk.blocksum + b0 + lane) : 0u;
+                unsigned iv = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+                if (b0 + lane < (int)gridDim.x) boff[b0 + lane] = carry + iv - v;
+                carry += __shfl_sync(0xffffffffu, iv, 31);
+            }
+        }
+        __syncthreads();
+        for (int d = lane; d < 256; d += 32) { const int e = d * NW + gw; wh[d] = __ldcg(wk.hist + e) + boff[e / chunk]; }
+        __syncwarp();
+        for (int i0 = r0; i0 < r1; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < r1;
+            const unsigned long long k = valid ? __ldcg(src + i) : 0ull;
+            const unsigned dg = valid ? ((unsigned)(k >> shift) & 255u) : (256u + (unsigned)lane);
+            const unsigned m = __match_any_sync(0xffffffffu, dg);
+            const unsigned rank = __popc(m & ((1u << lane) - 1u));
+            const unsigned pos = valid ? wh[dg] + rank : 0u;
+            __syncwarp();
+            if (valid) {
+                dst[pos] = k;
+                if (pass == 3) {                              // final position: publish the index and the correspondence row
+                    const unsigned i = (unsigned)k;
+                    wk.order[pos] = (int)i;
+                    const float4* row = reinterpret_cast<const float4*>(wk.q) + 2 * (size_t)i;
+                    const float4 lo = __ldcg(row), hi = __ldcg(row + 1);
+                    reinterpret_cast<float4*>(wk.stage)[2 * (size_t)pos] = lo; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)pos + 1] = hi;
+                }
+                if (rank == 0) wh[dg] += __popc(m);
+            }
+            __syncwarp();
+        }
+        __syncthreads();                                 // boff / sscan are rewritten by the next pass
+        grid.sync();
+        unsigned long long* tmp = src; src = dst; dst = tmp;
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Nearest neighbour of up to 32 queries per pass (one per lane), all 16 warps of the CTA scanning
@@ -374,7 +480,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     extern __shared__ __align__(16) unsigned char icp_smem[];
     __shared__ float sh_H[9];
     __shared__ float sh_acc[8];
-    __shared__ __align__(16) float chunk[kIcpChunk * 8];
+    __shared__ __align__(16) float chunk[2][kIcpChunk * 8];      // double buffer of the streamed (large-cloud) accumulation
     __shared__ NnPartial part;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIcpThreads / 32;
@@ -391,6 +497,8 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         nodes = sn; leaf = sl; sp += plan.tree_bytes;
     }
     float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
+    sp += plan.stage_bytes;
+    unsigned* sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr;
     __syncthreads();
 
     long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0, c_svd = 0; const long long c_begin = clock64();
@@ -468,7 +576,9 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         // ---- phase B: the reference's qsort by distance (stable for ties) as a distributed rank
         // count: rank(i) = #{j : key_j < key_i}, keys = (d^2 bits, index) are unique.  Every CTA ranks
         // its own queries against all keys; order[rank] = i.
-        {
+        if (sradix) {
+            icp_radix_sort(grid, wk, nd, sradix);        // large clouds: stable LSD radix sort (ends with a grid.sync)
+        } else {
             const unsigned long long* keys = wk.keys;
             const bool keys_in_smem = sstage != nullptr && (size_t)plan.stage_bytes >= (size_t)nd * sizeof(unsigned long long);
             if (keys_in_smem) {                      // the staging area is idle until phase C
@@ -486,62 +596,61 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
                 if (lane == 0) wk.order[cnt] = i;
+                if (lane < 2) reinterpret_cast<float4*>(wk.stage)[2 * (size_t)cnt + lane] = __ldcg(reinterpret_cast<const float4*>(wk.q) + 2 * (size_t)i + lane);
             }
             if (keys_in_smem) __syncthreads();       // block 0 overwrites the area in phase C
         }
         c1 = clock64(); c_sort += c1 - c0;
-        grid.sync();
+        if (!sradix) grid.sync();
         c0 = clock64(); c_wait += c0 - c1;
         if (blockIdx.x == 0) {
-            // ---- phase C: reference-order accumulations: correspondences (model point, query, d^2)
-            // are laid out in sorted order -- all of them in shared memory when they fit, else in
-            // chunks of kIcpChunk rows (kept in wk.stage for the second pass); one lane per
-            // accumulator then adds them up strictly sequentially.
+            // ---- phase C: reference-order accumulations.  The sort left the correspondences (model
+            // point, query, d^2) in wk.stage in sorted order; they are read into shared memory -- all at
+            // once when they fit, else streamed in double-buffered chunks of kIcpChunk rows that warps
+            // 1.. fetch while warp 0 adds the previous chunk -- and one lane per accumulator adds them
+            // up strictly sequentially.
             float acc = 0.0f;
             if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
-            const int step = sstage ? num : kIcpChunk;
-            for (int base = 0; base < num; base += step) {
-                const int cnt = min(step, num - base);
-                float* rows = sstage ? sstage : chunk;
-                // two dependent round trips (order -> row), issued 8 rows at a time per thread
-                for (int r0 = threadIdx.x; r0 < cnt; r0 += 8 * blockDim.x) {
-                    int ii[8]; float4 lo[8], hi[8];
+            const float4* srows = reinterpret_cast<const float4*>(wk.stage);
+            // err_new += dis is float += double in the reference (:254); the double sum of two floats is
+            // exact (or differs from either by < 2^-29), so rounding it to float equals the float sum --
+            // one add per element, like the other accumulators; operands are fetched 16 at a time ahead
+            // of the dependent chain of adds
+            auto add_rows = [&](const float* rows, int cnt) {
+                const float* sg = rows + lane;
+                int rr = 0;
+                for (; rr + 16 <= cnt; rr += 16) {
+                    float v[16];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) { const int rr = r0 + u * blockDim.x; ii[u] = rr < cnt ? __ldcg(wk.order + base + rr) : 0; }
+                    for (int u = 0; u < 16; u++) v[u] = sg[8 * (rr + u)];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const float4* row = reinterpret_cast<const float4*>(wk.q) + 2 * (size_t)ii[u];
-                        lo[u] = __ldcg(row); hi[u] = __ldcg(row + 1);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int rr = r0 + u * blockDim.x;
-                        if (rr < cnt) {
-                            reinterpret_cast<float4*>(rows)[2 * rr] = lo[u]; reinterpret_cast<float4*>(rows)[2 * rr + 1] = hi[u];
-                            if (!sstage) { reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr)] = lo[u]; reinterpret_cast<float4*>(wk.stage)[2 * (size_t)(base + rr) + 1] = hi[u]; }
-                        }
-                    }
+                    for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
                 }
+                for (; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
+            };
+            if (sstage) {
+                for (int v = threadIdx.x; v < 2 * num; v += blockDim.x) reinterpret_cast<float4*>(sstage)[v] = __ldcg(srows + v);
                 __syncthreads();
                 const long long ca0 = clock64();
-                if (warp == 0 && lane < 7) {
-                    // err_new += dis is float += double in the reference (:254); the double sum of two
-                    // floats is exact (or differs from either by < 2^-29), so rounding it to float
-                    // equals the float sum -- one add per element, like the other accumulators
-                    // operands are fetched 16 at a time ahead of the dependent chain of adds
-                    const float* sg = rows + lane;
-                    int rr = 0;
-                    for (; rr + 16 <= cnt; rr += 16) {
-                        float v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; u++) v[u] = sg[8 * (rr + u)];
-#pragma unroll
-                        for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
-                    }
-                    for (; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
-                }
+                if (warp == 0 && lane < 7) add_rows(sstage, num);
                 c_acc1 += clock64() - ca0;
                 __syncthreads();
+            } else {
+                const int nchunks = (num + kIcpChunk - 1) / kIcpChunk;
+                for (int v = threadIdx.x; v < 2 * min(kIcpChunk, num); v += blockDim.x) reinterpret_cast<float4*>(chunk[0])[v] = __ldcg(srows + v);
+                __syncthreads();
+                const long long ca0 = clock64();
+                for (int k = 0; k < nchunks; k++) {
+                    const int cnt = min(kIcpChunk, num - k * kIcpChunk);
+                    if (warp == 0) { if (lane < 7) add_rows(chunk[k & 1], cnt); }
+                    else if (k + 1 < nchunks) {
+                        const int ncnt = min(kIcpChunk, num - (k + 1) * kIcpChunk);
+                        for (int v = threadIdx.x - 32; v < 2 * ncnt; v += blockDim.x - 32)
+                            reinterpret_cast<float4*>(chunk[(k + 1) & 1])[v] = __ldcg(srows + 2 * (size_t)(k + 1) * kIcpChunk + v);
+                    }
+                    __syncthreads();
+                }
+                c_acc1 += clock64() - ca0;
             }
             if (warp == 0) {
                 if (lane < 7) sh_acc[lane] = acc;
@@ -564,38 +673,45 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 float mud = 0.0f, mum = 0.0f; int a = 0, b = 0;
                 if (warp == 0 && lane < 9) { a = lane / 3; b = lane % 3; mud = vst->mu_d[a]; mum = vst->mu_m[b]; }
                 acc = 0.0f;
-                for (int base = 0; base < num; base += step) {
-                    const int cnt = min(step, num - base);
-                    const float* rows = sstage ? sstage : chunk;
-                    if (!sstage) {
-                        for (int v = threadIdx.x; v < 2 * cnt; v += blockDim.x)
-                            reinterpret_cast<float4*>(chunk)[v] = reinterpret_cast<const float4*>(wk.stage)[2 * (size_t)base + v];
-                        __syncthreads();
-                    }
-                    if (warp == 0 && lane < 9) {
-                        // the products of the next 8 rows are formed in the shadow of the dependent adds of these 8
-                        const float* ra = rows + 3 + a; const float* rb = rows + b;
-                        float pr[8];
-                        int rr = 0;
-                        if (cnt >= 8) {
+                // the products of the next 8 rows are formed in the shadow of the dependent adds of these 8
+                auto add_products = [&](const float* rows, int cnt) {
+                    const float* ra = rows + 3 + a; const float* rb = rows + b;
+                    float pr[8];
+                    int rr = 0;
+                    if (cnt >= 8) {
 #pragma unroll
-                            for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(__fsub_rn(ra[8 * u], mud), __fsub_rn(rb[8 * u], mum));
-                            for (rr = 8; rr + 8 <= cnt; rr += 8) {
-                                float nx[8];
+                        for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(__fsub_rn(ra[8 * u], mud), __fsub_rn(rb[8 * u], mum));
+                        for (rr = 8; rr + 8 <= cnt; rr += 8) {
+                            float nx[8];
 #pragma unroll
-                                for (int u = 0; u < 8; u++) {
-                                    nx[u] = __fmul_rn(__fsub_rn(ra[8 * (rr + u)], mud), __fsub_rn(rb[8 * (rr + u)], mum));
-                                    acc = __fadd_rn(acc, pr[u]);
-                                }
-#pragma unroll
-                                for (int u = 0; u < 8; u++) pr[u] = nx[u];
+                            for (int u = 0; u < 8; u++) {
+                                nx[u] = __fmul_rn(__fsub_rn(ra[8 * (rr + u)], mud), __fsub_rn(rb[8 * (rr + u)], mum));
+                                acc = __fadd_rn(acc, pr[u]);
                             }
 #pragma unroll
-                            for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, pr[u]);
+                            for (int u = 0; u < 8; u++) pr[u] = nx[u];
                         }
-                        for (; rr < cnt; rr++) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(ra[8 * rr], mud), __fsub_rn(rb[8 * rr], mum)));
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, pr[u]);
                     }
-                    if (!sstage) __syncthreads();
+                    for (; rr < cnt; rr++) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(ra[8 * rr], mud), __fsub_rn(rb[8 * rr], mum)));
+                };
+                if (sstage) {
+                    if (warp == 0 && lane < 9) add_products(sstage, num);
+                } else {
+                    const int nchunks = (num + kIcpChunk - 1) / kIcpChunk;
+                    for (int v = threadIdx.x; v < 2 * min(kIcpChunk, num); v += blockDim.x) reinterpret_cast<float4*>(chunk[0])[v] = __ldcg(srows + v);
+                    __syncthreads();
+                    for (int k = 0; k < nchunks; k++) {
+                        const int cnt = min(kIcpChunk, num - k * kIcpChunk);
+                        if (warp == 0) { if (lane < 9) add_products(chunk[k & 1], cnt); }
+                        else if (k + 1 < nchunks) {
+                            const int ncnt = min(kIcpChunk, num - (k + 1) * kIcpChunk);
+                            for (int v = threadIdx.x - 32; v < 2 * ncnt; v += blockDim.x - 32)
+                                reinterpret_cast<float4*>(chunk[(k + 1) & 1])[v] = __ldcg(srows + 2 * (size_t)(k + 1) * kIcpChunk + v);
+                        }
+                        __syncthreads();
+                    }
                 }
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;
@@ -621,17 +737,26 @@ cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx,
 }
 static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int smem_limit)
 {
-    IcpSmemPlan p = {0, 0, 0, 0};
+    IcpSmemPlan p = {0, 0, 0, 0, 0};
     int left = smem_limit;
     const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
     const size_t stage = (size_t)num * 8 * sizeof(float);
     if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
     if (stage <= (size_t)left) { p.stage_bytes = (int)stage; left -= (int)stage; }
+    // sort: rank by counting while the keys can sit in shared memory next to the staged rows, radix sort beyond
+    // (GOICP_ICP_RADIX=1/0 forces the choice -- used by the parity tests to cover both on the same input)
+    bool radix = p.stage_bytes == 0;
+    if (const char* f = getenv("GOICP_ICP_RADIX")) radix = f[0] == '1';
+    if (radix && kRadixSmemBytes > left) {       // make room: the tree goes back to global memory
+        left += p.tree_bytes; p.tree_nodes = 0; p.tree_bytes = 0;
+    }
+    if (radix) { p.radix_bytes = kRadixSmemBytes; left -= kRadixSmemBytes; }
     // linear scan while it beats the (divergent) tree descent: model resident in shared memory, or moderate size
     p.brute_force = (p.tree_bytes != 0 || kd.nm <= 16384) ? 1 : 0;
     return p;
 }
 int icp_threads() { return kIcpThreads; }
+int icp_max_blocks_supported() { return kRadixBlockOffs; }
 int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin)
 {
     cudaFuncAttributes a;
@@ -640,7 +765,7 @@ int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int n
     cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
@@ -656,7 +781,7 @@ cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int 
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
                     (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&plan};
     return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args,
-                                       (size_t)plan.tree_bytes + plan.stage_bytes, s);
+                                       (size_t)plan.tree_bytes + plan.stage_bytes + plan.radix_bytes, s);
 }
 
 } // namespace goicp

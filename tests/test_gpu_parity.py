@@ -105,7 +105,10 @@ def test_nn_indices_bit_exact(pkg, small, bunny):
     g.close()
 
 
-def test_icp_matches_reference(pkg, small, bunny):
+@pytest.mark.parametrize("sort", ["count", "radix"])
+def test_icp_matches_reference(pkg, small, bunny, sort, monkeypatch):
+    # both sorts of the ICP kernel (rank by counting / grid-wide stable radix sort) on the same input
+    monkeypatch.setenv("GOICP_ICP_RADIX", "1" if sort == "radix" else "0")
     g = pkg.GoICP(1e-3)
     g.pModel, g.pData = bunny["model"], bunny["data"]
     err, R, t, iters = g.ICP(np.eye(3), np.zeros(3), 10000, 1e-7)
@@ -255,10 +258,13 @@ def test_trimmed_inner_bnb_and_register(pkg, runs, bunny, restated, small):
     g.close()
 
 
-def test_config2_full_size_nn_and_icp_on_gpu(pkg):
+@pytest.mark.parametrize("sort", ["radix", "count"])
+def test_config2_full_size_nn_and_icp_on_gpu(pkg, sort, monkeypatch):
     """BASELINE config 2 (bunny ICP only) at full size: 40256 nearest-neighbour indices bit-exact with the
-    reference kd-tree (incl. its 53 exact-tie queries), and ICP3D::Run reproduced bit for bit."""
+    reference kd-tree (incl. its 53 exact-tie queries), and ICP3D::Run reproduced bit for bit -- with the
+    radix sort this size selects by itself and with the counting sort of the small clouds forced."""
     import os
+    monkeypatch.setenv("GOICP_ICP_RADIX", "1" if sort == "radix" else "0")
     from conftest import GOLDEN
     gold = dict(np.load(os.path.join(GOLDEN, "bun_icp_config2.npz")))
     g = pkg.GoICP(1e-5)
