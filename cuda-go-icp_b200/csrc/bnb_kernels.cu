@@ -625,9 +625,12 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     if (warp != 0) {
         // ================================ gather warps ======================================
         const int gt = tid - 32;
+        long long g_waitA = 0, g_gather = 0, g_reduce = 0, g_waitB = 0;      // cycle breakdown (reported when c.dbg is set)
         for (;;) {
+            long long g0 = clock64();
             cluster_arrive_relaxed(); cluster_wait();               // (A) next cube published
             if (ctrl.done) break;
+            long long g1 = clock64(); g_waitA += g1 - g0;
             float acc[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) acc[k] = 0.0f;
@@ -644,6 +647,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                                       dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
                 }
             }
+            g0 = clock64(); g_gather += g0 - g1;
             warp_reduce16(acc, lane);
             if ((lane & 1) == 0) red[warp - 1][(lane >> 1) & 15] = acc[0];
             asm volatile("bar.sync 1, %0;" :: "r"(kGatherThreads) : "memory");
@@ -653,7 +657,13 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                 for (int w = 0; w < kGatherWarps; w++) s += red[w][lane];
                 cluster.map_shared_rank(&partials[0][0], 0)[rank * 16 + lane] = s;
             }
+            g1 = clock64(); g_reduce += g1 - g0;
             cluster_arrive(); cluster_wait();                       // (B) partial sums delivered
+            g_waitB += clock64() - g1;
+        }
+        if (c.dbg && leader && warp == 1 && lane == 0) {
+            unsigned long long* d = c.dbg + (size_t)task_id * 8;
+            d[4] = g_waitA; d[5] = g_gather; d[6] = g_reduce; d[7] = g_waitB;
         }
         return;
     }
@@ -678,7 +688,9 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     uint32_t pops = 0, evals = 0, max_heap = 0, flags = 0; int status = 0, n_cand = 0;
     float px = c.tx, py = c.ty, pz = c.tz, cw = c.tw / 2;              // cube being expanded
     uint32_t plevel = 0; unsigned long long ppath = 0ull;
-    HeapEntry pend[8]; int n_pend = 0; bool need_pop = false;           // pushes deferred into the shadow of the gathers
+    // pushes deferred into the shadow of the gathers: children pmask of one parent; their lower bounds stay in
+    // tot16[8..15] (not rewritten before the flush), level and path are rebuilt from the parent's -- no local array
+    uint32_t pmask = 0, pend_level = 0; unsigned long long pend_base = 0ull; int pend_shift = 0; bool need_pop = false;
     HeapEntry expect; expect.lb = 0.0f; expect.level = 0; expect.path_lo = expect.path_hi = 0;
     bool done = false;
 
@@ -711,9 +723,15 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         }
         px = x; py = y; pz = z; cw = w / 2; plevel = e.level; ppath = path;
     };
+    auto pend_entry = [&](int j) {
+        HeapEntry e; e.lb = tot16[8 + j]; e.level = pend_level;
+        const unsigned long long path = pend_base | ((unsigned long long)j << pend_shift);
+        e.path_lo = (uint32_t)path; e.path_hi = (uint32_t)(path >> 32);
+        return e;
+    };
     auto flush_pending = [&]() {
-        for (int k = 0; k < n_pend && !status; k++) if (!wheap_push(heap, pend[k], lane)) status = 3;
-        n_pend = 0;
+        for (uint32_t m = pmask; m && !status; m &= m - 1) if (!wheap_push(heap, pend_entry(__ffs(m) - 1), lane)) status = 3;
+        pmask = 0;
         if ((uint32_t)heap.n > max_heap) max_heap = heap.n;
     };
 
@@ -722,8 +740,10 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         adopt(root);
         publish(done);
     }
+    long long o_maint = 0, o_waitA = 0, o_waitB = 0, o_book = 0;
     for (;;) {
         __syncwarp();
+        long long o0 = clock64();
         cluster_arrive();                                                     // (A) cube published
         if (!done) {
             // ---- queue maintenance in the shadow of the gathers --------------------------
@@ -734,15 +754,18 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                 need_pop = false;
             }
         }
+        long long o1 = clock64(); o_maint += o1 - o0;
         cluster_wait();
         if (done) break;
+        o0 = clock64(); o_waitA += o0 - o1;
         cluster_arrive_relaxed(); cluster_wait();                             // (B) partial sums are in
+        o1 = clock64(); o_waitB += o1 - o0;
         // ---- fixed-order sum over the cluster's CTAs, one lane per value ------------------------
         if (lane < 16) { float sacc = 0.0f; for (int r = 0; r < C; r++) sacc += partials[r][lane]; tot16[lane] = sacc; }
         __syncwarp();
         // ---- sequential bookkeeping of the 8 children (jly_goicp.cpp:317-336) -------------------
         evals += 8;
-        n_pend = 0;
+        pmask = 0; pend_level = plevel + 1; pend_base = ppath; pend_shift = 3 * (int)plevel;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const float ub = tot16[j], lb = tot16[8 + j];
@@ -770,20 +793,17 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                 } else flags |= 1u;
             }
             if (lb >= opt_t) continue;
-            HeapEntry e; e.lb = lb; e.level = plevel + 1;
-            const unsigned long long path = ppath | ((unsigned long long)j << (3 * plevel));
-            e.path_lo = (uint32_t)path; e.path_hi = (uint32_t)(path >> 32);
-            pend[n_pend++] = e;
+            pmask |= 1u << j;
         }
         // ---- which node will the queue pop next? ------------------------------------------------
         if (status) { done = true; publish(true); }
-        else if (heap.n == 0 && n_pend == 0) { done = true; publish(true); }          // queue empty (:243-244)
+        else if (heap.n == 0 && pmask == 0) { done = true; publish(true); }          // queue empty (:243-244)
         else {
             // best candidate among the current top and the pending children; ties on (lb, level) are left to the heap
-            HeapEntry b; bool tie = false; int k0 = 0;
-            if (heap.n > 0) b = heap.get(0); else { b = pend[0]; k0 = 1; }
-            for (int k = k0; k < n_pend; k++) {
-                const HeapEntry& e = pend[k];
+            HeapEntry b; bool tie = false; uint32_t m = pmask;
+            if (heap.n > 0) b = heap.get(0); else { b = pend_entry(__ffs(m) - 1); m &= m - 1; }
+            for (; m; m &= m - 1) {
+                const HeapEntry e = pend_entry(__ffs(m) - 1);
                 if (node_less(b, e)) { b = e; tie = false; }                   // e has strictly higher priority
                 else if (!node_less(e, b)) tie = true;                         // same (lb, level)
             }
@@ -797,6 +817,11 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                 publish(done);
             }
         }
+        o_book += clock64() - o1;
+    }
+    if (c.dbg && lane == 0) {
+        unsigned long long* d = c.dbg + (size_t)task_id * 8;
+        d[0] = o_maint; d[1] = o_waitA; d[2] = o_waitB; d[3] = o_book;
     }
 
     // ---- results (see inner_bnb_kernel) ---------------------------------------------------------

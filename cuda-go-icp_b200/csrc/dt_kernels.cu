@@ -15,6 +15,7 @@
 // GOICP_DT_EXACT_EDT is the separable exact squared-Euclidean transform (three 1-D lower-envelope
 // passes over integer squared distances), fully parallel.
 #include "dt_kernels.h"
+#include "mem_pool.h"
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -698,10 +699,10 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     const int P = (S + 1) & ~1;
     const size_t ng = (size_t)S * S * P;
     V2* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
-    auto cleanup = [&]() { if (G) cudaFree(G); if (d_model) cudaFree(d_model); if (D0) cudaFree(D0); if (D1) cudaFree(D1); };
+    auto cleanup = [&]() { cudaStreamSynchronize(stream);      /* blocks go back to a shared pool: nothing may still use them */ pool_free(G); pool_free(d_model); pool_free(D0); pool_free(D1); };
 #define DT_TRY(expr) do { e = (expr); if (e != cudaSuccess) { msg = #expr; cleanup(); return e; } } while (0)
-    DT_TRY(cudaMalloc((void**)&G, ng * sizeof(V2)));
-    DT_TRY(cudaMalloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
+    DT_TRY(pool_alloc((void**)&G, ng * sizeof(V2)));
+    DT_TRY(pool_alloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
     DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
     // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
     dt_init_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(G, ng, mode == 0 ? 1 : 0);
@@ -752,8 +753,8 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, P, meta[3], d_out);
         DT_TRY(cudaGetLastError());
     } else {
-        DT_TRY(cudaMalloc((void**)&D0, n3 * sizeof(int)));
-        DT_TRY(cudaMalloc((void**)&D1, n3 * sizeof(int)));
+        DT_TRY(pool_alloc((void**)&D0, n3 * sizeof(int)));
+        DT_TRY(pool_alloc((void**)&D1, n3 * sizeof(int)));
         edt_pass_z<<<(S * S + 127) / 128, 128, 0, stream>>>(G, S, P, D0);
         DT_TRY(cudaGetLastError());
         // along y: lines indexed by (x, z): base = x*S*S + z, element stride S

@@ -31,6 +31,7 @@
 #include "goicp_kernels.h"
 #include "kdtree_host.h"
 #include "dt_kernels.h"
+#include "mem_pool.h"
 
 using namespace goicp;
 
@@ -100,13 +101,13 @@ struct DevBuf {
     cudaError_t reserve(size_t count)
     {
         if (count <= n) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr; n = 0;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = pool_alloc((void**)&p, count * sizeof(T));
         if (e == cudaSuccess) n = count;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) pool_free(p); p = nullptr; n = 0; }
 };
 
 } // namespace
@@ -130,7 +131,7 @@ struct goicp_handle {
     bool kd_ready = false;
     // scratch
     DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
-    DevBuf<CandList> d_cands; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
+    DevBuf<CandList> d_cands; DevBuf<unsigned long long> d_dbg; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
     int64_t strict_resolves = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
     DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
@@ -255,6 +256,7 @@ int make_const(goicp_handle* h, BnbConst& c)
     c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
     c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
     for (int i = 0; i < kMaxRotLevel; i++) c.cgamma[i] = h->cgamma[i];
+    c.dbg = nullptr;
     return GOICP_OK;
 }
 
@@ -291,12 +293,12 @@ int ensure_task_buffers(goicp_handle* h, size_t n)
     CUDA_TRY(h, h->d_results.reserve(n));
     CUDA_TRY(h, h->d_cands.reserve(n + 1));
     if (h->h_results_n < n) {
-        if (h->h_results) cudaFreeHost(h->h_results);
-        if (h->h_tasks) cudaFreeHost(h->h_tasks);
+        if (h->h_results) pool_free_host(h->h_results);
+        if (h->h_tasks) pool_free_host(h->h_tasks);
         h->h_results = nullptr; h->h_tasks = nullptr;
         size_t cap = std::max<size_t>(n, 1024);
-        CUDA_TRY(h, cudaMallocHost((void**)&h->h_results, cap * sizeof(InnerResult)));
-        CUDA_TRY(h, cudaMallocHost((void**)&h->h_tasks, cap * sizeof(InnerTask)));
+        CUDA_TRY(h, pool_alloc_host((void**)&h->h_results, cap * sizeof(InnerResult)));
+        CUDA_TRY(h, pool_alloc_host((void**)&h->h_tasks, cap * sizeof(InnerTask)));
         h->h_results_n = cap; h->h_tasks_n = cap;
     }
     // spill region: one slab per concurrently launched CTA (grid == n)
@@ -343,10 +345,13 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         mine = (int)local.size();
         src = local.data();
     } else mine = n;
+    const bool stats = getenv("GOICP_ROUND_STATS") != nullptr;
+    BnbConst cdbg = c;
+    if (stats) { CUDA_TRY(h, h->d_dbg.reserve((size_t)8 * (n + 64))); CUDA_TRY(h, cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned long long) * 8 * n, h->stream)); cdbg.dbg = h->d_dbg.p; }
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     if (mine > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, launch_inner_bnb(c, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->stream));
+        CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->stream));
         h->launches++;
     }
     if (W == 1) {
@@ -367,6 +372,13 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         for (int t = 0; t < n; t++) { const InnerResult& q = h->h_results[t]; sumc += q.kcycles; sump += q.pops; if (q.kcycles > maxc) { maxc = q.kcycles; arg = t; } if (q.pops > maxp) maxp = q.pops; if (q.max_heap > maxh) maxh = q.max_heap; if (q.pad[1]) flagged++; }
         fprintf(stderr, "[round] tasks %d kernel %.3f ms; slowest task %.3f Mcyc (pops %u, level %d); max pops %u; total pops %u; sum task cycles %.1f Mcyc; max heap %u; tasks with contenders %d\n",
                 n, ms, maxc * 1024e-6, h->h_results[arg].pops, h->h_tasks[arg].level, maxp, sump, sumc * 1024e-6, maxh, flagged);
+        if (W == 1) {
+            unsigned long long d[8];
+            cudaMemcpy(d, h->d_dbg.p + (size_t)8 * arg, sizeof d, cudaMemcpyDeviceToHost);
+            const double steps = std::max(1u, h->h_results[arg].evals / 8);
+            fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
+                    plan.cluster, d[0] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
+        }
     }
     if (lists) {
         // contender lists of the upper-bound passes that have any (local tasks only; a rank that
@@ -519,10 +531,10 @@ int goicp_destroy(goicp_handle* h)
     if (h->cuda_ready) {
         cudaSetDevice(h->p.device);
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
-        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
+        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
-        if (h->h_results) cudaFreeHost(h->h_results);
-        if (h->h_tasks) cudaFreeHost(h->h_tasks);
+        if (h->h_results) pool_free_host(h->h_results);
+        if (h->h_tasks) pool_free_host(h->h_tasks);
         if (h->ev0) cudaEventDestroy(h->ev0);
         if (h->ev1) cudaEventDestroy(h->ev1);
         if (h->stream) cudaStreamDestroy(h->stream);
@@ -748,6 +760,8 @@ int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void
     *mismatches = bad;
     return GOICP_OK;
 }
+
+int goicp_trim_memory(void) { pool_trim(); return GOICP_OK; }
 
 int goicp_cancel(goicp_handle* h) { if (!h) return GOICP_ERR_INVALID; h->cancel_flag.store(1); return GOICP_OK; }
 int goicp_poll(goicp_handle* h, goicp_snapshot* out)

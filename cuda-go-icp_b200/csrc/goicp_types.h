@@ -21,6 +21,7 @@ struct BnbConst {
     float sse_thresh;                   // SSEThresh (jly_goicp.cpp:208)
     float tx, ty, tz, tw;               // initNodeTrans (jly_goicp.cpp:50-53)
     float cgamma[kMaxRotLevel];         // 2*sinf(maxAngle_l/2): maxRotDis[l][i] = cgamma[l]*||p_i|| (jly_goicp.cpp:150-160)
+    unsigned long long* dbg;            // optional (GOICP_ROUND_STATS): 8 cycle counters per task of the pipelined inner BnB, else nullptr
 };
 
 // One inner (translation) BnB to run: a rotation-cube child and a pass.

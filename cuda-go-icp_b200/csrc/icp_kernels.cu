@@ -101,6 +101,68 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
     return best;
 }
 
+// ------------------------------------------------------------------------------------------
+// Warm-started exact nearest neighbour for ICP iterations >= 1: the previous iteration's
+// correspondent of the query bounds the search radius, so the descent prunes almost everything.
+// Any exact search returns the reference's index unless two model points are (nearly) equally
+// close, so the search also tracks the second-smallest distance within a 2e-5 relative margin
+// and the caller re-runs near-ties through the reference-ordered traversal (kd_nearest).
+// Far-side bound of a split = squared distance to the far child's slab along the split axis
+// (divlow / divhigh are the extreme coordinates of the two children, nanoflann_goicp.hpp:1013-1045).
+// Returns -1 if the explicit stack overflowed (caller falls back to kd_nearest).
+// ------------------------------------------------------------------------------------------
+constexpr int kSeedStack = 40;
+__device__ int kd_seeded(const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, const float* __restrict__ model,
+                         float qx, float qy, float qz, int seed, float& d1_out, float& d2_out)
+{
+    float d1, d2 = 3.402823466e+38f; int i1 = seed;
+    {
+        const float e0 = qx - __ldg(model + 3 * seed), e1 = qy - __ldg(model + 3 * seed + 1), e2 = qz - __ldg(model + 3 * seed + 2);
+        d1 = e0 * e0 + e1 * e1 + e2 * e2;
+    }
+    int st_node[kSeedStack]; float st_bound[kSeedStack];
+    int sp = 0, cur = 0;
+    float cur_bound = 0.0f;
+    for (;;) {
+        for (;;) {
+            const uint4 a = reinterpret_cast<const uint4*>(nodes + cur)[0];
+            if ((int)a.x < 0 && (int)a.y < 0) {
+                for (int i = (int)a.z; i < (int)a.w; i++) {
+                    const float4 p = leaf[i];
+                    const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
+                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;     // kdtree_distance (jly_icp3d.hpp:48-54)
+                    const int id = __float_as_int(p.w);
+                    if (id == i1) continue;
+                    if (dist < d1) { d2 = d1; d1 = dist; i1 = id; }
+                    else if (dist < d2) d2 = dist;
+                }
+                break;
+            }
+            const uint4 b = reinterpret_cast<const uint4*>(nodes + cur)[1];
+            const int idx = (int)b.x;
+            const float divlow = __uint_as_float(b.y), divhigh = __uint_as_float(b.z);
+            const float val = sel3(qx, qy, qz, idx);
+            int bestc, otherc; float cut;
+            if (((val - divlow) + (val - divhigh)) < 0) { bestc = (int)a.x; otherc = (int)a.y; cut = (val - divhigh) * (val - divhigh); }
+            else                                        { bestc = (int)a.y; otherc = (int)a.x; cut = (val - divlow) * (val - divlow); }
+            const float fb = fmaxf(cur_bound, cut);
+            if (fb <= d1 * 1.00002f) {
+                if (sp == kSeedStack) return -1;
+                st_node[sp] = otherc; st_bound[sp] = fb; sp++;
+            }
+            cur = bestc;
+        }
+        bool more = false;
+        while (sp > 0) {
+            sp--;
+            if (st_bound[sp] <= d1 * 1.00002f) { cur = st_node[sp]; cur_bound = st_bound[sp]; more = true; break; }
+        }
+        if (!more) break;
+    }
+    d1_out = d1; d2_out = d2;
+    return i1;
+}
+
 __global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t* __restrict__ idx, float* __restrict__ d2)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -460,6 +522,31 @@ __device__ void icp_radix_sort(cg::grid_group& grid, const IcpWork& wk, int nd, 
     }
 }
 
+// acc += x[0], x[stride], x[2*stride], ... (cnt terms) strictly in order; the operands of the next 16
+// adds are fetched while the dependent chain of the current 16 retires.
+__device__ __forceinline__ float seq_add_strided(float acc, const float* x, int stride, int cnt)
+{
+    int rr = 0;
+    if (cnt >= 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) v[u] = x[stride * u];
+        for (rr = 16; rr + 16 <= cnt; rr += 16) {
+            float nx[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) nx[u] = x[stride * (rr + u)];
+#pragma unroll
+            for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = nx[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
+    }
+    for (; rr < cnt; rr++) acc = __fadd_rn(acc, x[stride * rr]);
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------
 // Nearest neighbour of up to 32 queries per pass (one per lane), all 16 warps of the CTA scanning
 // 1/16 of the model each.  A linear scan has no divergence, unlike the kd-tree descent where every
@@ -561,8 +648,13 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
                 const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
                 const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-                float d2;
-                const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
+                float d2; int id = -1;
+                if (iter > 0) {           // warm start from the previous correspondent; near ties go to the reference traversal
+                    float dsecond;
+                    id = kd_seeded(nodes, leaf, kd.model, qx, qy, qz, __ldcg(wk.nn + i), d2, dsecond);
+                    if (id >= 0 && dsecond <= d2 * 1.00001f) id = -1;
+                }
+                if (id < 0) id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
                 wk.nn[i] = id; wk.d2[i] = d2;
                 wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
                 float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
@@ -616,18 +708,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             // exact (or differs from either by < 2^-29), so rounding it to float equals the float sum --
             // one add per element, like the other accumulators; operands are fetched 16 at a time ahead
             // of the dependent chain of adds
-            auto add_rows = [&](const float* rows, int cnt) {
-                const float* sg = rows + lane;
-                int rr = 0;
-                for (; rr + 16 <= cnt; rr += 16) {
-                    float v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; u++) v[u] = sg[8 * (rr + u)];
-#pragma unroll
-                    for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
-                }
-                for (; rr < cnt; rr++) acc = __fadd_rn(acc, sg[8 * rr]);
-            };
+            auto add_rows = [&](const float* rows, int cnt) { acc = seq_add_strided(acc, rows + lane, 8, cnt); };
             if (sstage) {
                 for (int v = threadIdx.x; v < 2 * num; v += blockDim.x) reinterpret_cast<float4*>(sstage)[v] = __ldcg(srows + v);
                 __syncthreads();
@@ -670,48 +751,40 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             __syncthreads();
             c1 = clock64(); c_p1 += c1 - c0; c0 = c1;
             if (!vst->converged) {
-                float mud = 0.0f, mum = 0.0f; int a = 0, b = 0;
-                if (warp == 0 && lane < 9) { a = lane / 3; b = lane % 3; mud = vst->mu_d[a]; mum = vst->mu_m[b]; }
+                // H = sum over the sorted rows of (q - mu_d)(m - mu_m)^T, each of its 9 entries a strictly
+                // sequential float sum (:268).  Warps 1.. form the products of block k+1 into a
+                // shared-memory ring while lanes 0..8 of warp 0 add block k: the dependent chain of adds
+                // is all that is left on the critical path.
                 acc = 0.0f;
-                // the products of the next 8 rows are formed in the shadow of the dependent adds of these 8
-                auto add_products = [&](const float* rows, int cnt) {
-                    const float* ra = rows + 3 + a; const float* rb = rows + b;
-                    float pr[8];
-                    int rr = 0;
-                    if (cnt >= 8) {
-#pragma unroll
-                        for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(__fsub_rn(ra[8 * u], mud), __fsub_rn(rb[8 * u], mum));
-                        for (rr = 8; rr + 8 <= cnt; rr += 8) {
-                            float nx[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                nx[u] = __fmul_rn(__fsub_rn(ra[8 * (rr + u)], mud), __fsub_rn(rb[8 * (rr + u)], mum));
-                                acc = __fadd_rn(acc, pr[u]);
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; u++) pr[u] = nx[u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 8; u++) acc = __fadd_rn(acc, pr[u]);
+                constexpr int kProd = 336;                           // rows per ring half: 2 * 336 * 9 floats fit `chunk`
+                float* ring = &chunk[0][0];
+                const int nblk = (num + kProd - 1) / kProd;
+                const float md0 = vst->mu_d[0], md1 = vst->mu_d[1], md2 = vst->mu_d[2], mm0 = vst->mu_m[0], mm1 = vst->mu_m[1], mm2 = vst->mu_m[2];
+                auto produce = [&](int k) {
+                    const int base = k * kProd, cnt = min(kProd, num - base);
+                    float* dst = ring + (k & 1) * (kProd * 9);
+                    for (int r = threadIdx.x - 32; r < cnt; r += blockDim.x - 32) {
+                        float4 lo, hi;
+                        if (sstage) { lo = reinterpret_cast<const float4*>(sstage)[2 * (base + r)]; hi = reinterpret_cast<const float4*>(sstage)[2 * (base + r) + 1]; }
+                        else { lo = __ldcg(srows + 2 * (size_t)(base + r)); hi = __ldcg(srows + 2 * (size_t)(base + r) + 1); }
+                        const float q0 = __fsub_rn(lo.w, md0), q1 = __fsub_rn(hi.x, md1), q2 = __fsub_rn(hi.y, md2);
+                        const float m0 = __fsub_rn(lo.x, mm0), m1 = __fsub_rn(lo.y, mm1), m2 = __fsub_rn(lo.z, mm2);
+                        float* d = dst + 9 * r;
+                        d[0] = __fmul_rn(q0, m0); d[1] = __fmul_rn(q0, m1); d[2] = __fmul_rn(q0, m2);
+                        d[3] = __fmul_rn(q1, m0); d[4] = __fmul_rn(q1, m1); d[5] = __fmul_rn(q1, m2);
+                        d[6] = __fmul_rn(q2, m0); d[7] = __fmul_rn(q2, m1); d[8] = __fmul_rn(q2, m2);
                     }
-                    for (; rr < cnt; rr++) acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(ra[8 * rr], mud), __fsub_rn(rb[8 * rr], mum)));
                 };
-                if (sstage) {
-                    if (warp == 0 && lane < 9) add_products(sstage, num);
-                } else {
-                    const int nchunks = (num + kIcpChunk - 1) / kIcpChunk;
-                    for (int v = threadIdx.x; v < 2 * min(kIcpChunk, num); v += blockDim.x) reinterpret_cast<float4*>(chunk[0])[v] = __ldcg(srows + v);
-                    __syncthreads();
-                    for (int k = 0; k < nchunks; k++) {
-                        const int cnt = min(kIcpChunk, num - k * kIcpChunk);
-                        if (warp == 0) { if (lane < 9) add_products(chunk[k & 1], cnt); }
-                        else if (k + 1 < nchunks) {
-                            const int ncnt = min(kIcpChunk, num - (k + 1) * kIcpChunk);
-                            for (int v = threadIdx.x - 32; v < 2 * ncnt; v += blockDim.x - 32)
-                                reinterpret_cast<float4*>(chunk[(k + 1) & 1])[v] = __ldcg(srows + 2 * (size_t)(k + 1) * kIcpChunk + v);
+                if (warp != 0) produce(0);
+                __syncthreads();
+                for (int k = 0; k < nblk; k++) {
+                    if (warp == 0) {
+                        if (lane < 9) {
+                            const int cnt = min(kProd, num - k * kProd);
+                            acc = seq_add_strided(acc, ring + (k & 1) * (kProd * 9) + lane, 9, cnt);
                         }
-                        __syncthreads();
-                    }
+                    } else if (k + 1 < nblk) produce(k + 1);
+                    __syncthreads();
                 }
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;

@@ -173,6 +173,11 @@ int goicp_register(goicp_handle* h, goicp_result* out);
 int goicp_poll(goicp_handle* h, goicp_snapshot* out);
 int goicp_cancel(goicp_handle* h);
 
+/* Device and pinned buffers of destroyed handles are cached process-wide and reused by the next
+ * handle (the reference new/deletes its 324 MB grid per GoICP object, jly_3ddt.cpp:932-935; here a
+ * cudaMalloc costs a driver lock).  This returns the cached blocks to the driver. */
+int goicp_trim_memory(void);
+
 /* Multi-GPU: every rank evaluates its slice of each round's cubes; `exchange` must all-gather
  * `bytes_per_rank` bytes from every rank into recv (rank-major).  The Python driver implements it
  * with torch.distributed (NCCL on device buffers is_device=1, gloo on host buffers). */
