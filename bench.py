@@ -250,11 +250,21 @@ def main():
     model, data = load(wl["model"]), load(wl["data"])
     config.update(Nd=len(data), Nm=len(model))
 
+    nccl_id = None
+    if world > 1:                                       # rank 0's ncclUniqueId travels over torch.distributed (plumbing only)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
     def make_engine():
         g = pkg.GoICP(wl["mse"], device=local_rank)
         g.pModel, g.pData = model, data
         g.dt.SIZE = wl["S"]
-        if world > 1:
+        if world > 1 and os.environ.get("GOICP_EXCHANGE", "nccl") == "nccl":
+            g.init_nccl(nccl_id, rank, world)          # native: ncclAllGather on the engine's stream (include/goicp_b200.h)
+        elif world > 1:
             send_t = {}
 
             def allgather(send):
@@ -370,7 +380,7 @@ def main():
            "bound_evals_per_step": evals // args.steps, "bound_evals_executed_per_step": executed // args.steps,
            "rot_pops": res["rot_pops"], "trans_pops": res["trans_pops"], "rounds_per_step": res["rounds"],
            "dt_build_s": dt_build_s, "seconds_icp_per_step": float(np.mean([r["seconds_icp"] for r in results])),
-           "seconds_bnb_kernels_per_step": kern_s / args.steps,
+           "seconds_bnb_kernels_per_step": kern_s / args.steps, "exchange": (os.environ.get("GOICP_EXCHANGE", "nccl") if world > 1 else None),
            "reference_cpu_published_here": {"register_s": wl["ref_register_s"], "bound_evals": wl["ref_evals"],
                                             "note": "oracle/_ref in the build container, 1 core (tests/golden/goicp_runs.json)"}}
     eng.close()

@@ -73,7 +73,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
                "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
-               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_set_exchange", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
+               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 
 def build(verbose: bool = False) -> str:
@@ -120,6 +120,8 @@ def lib():
         L.goicp_poll.argtypes = [C.c_void_p, C.POINTER(Snapshot)]
         L.goicp_cancel.argtypes = [C.c_void_p]
         L.goicp_set_exchange.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p, C.c_int]
+        L.goicp_nccl_unique_id.argtypes = [C.c_void_p]
+        L.goicp_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.goicp_selftest_shard.argtypes = [C.c_int, C.c_int, C.c_int, ALLGATHER_FN, C.c_void_p, C.POINTER(C.c_int)]
         L.goicp_load_cloud.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_uint, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int)]
         L.goicp_free_cloud.argtypes = [C.POINTER(C.c_float)]
@@ -127,6 +129,15 @@ def lib():
         L.goicp_run_toml.argtypes = [C.c_char_p, C.c_uint, C.c_uint, C.POINTER(Result)]
         _lib = L
     return _lib
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte ncclUniqueId (call on rank 0, broadcast to the other ranks, pass to GoICP.init_nccl)."""
+    buf = np.zeros(128, np.uint8)
+    rc = lib().goicp_nccl_unique_id(buf.ctypes.data)
+    if rc != 0:
+        raise GoicpError(rc, "ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+    return buf.tobytes()
 
 
 def _f32(a, cols=None):
@@ -173,6 +184,7 @@ class GoICP:
         self._keep = []
         self.rank, self.world_size = 0, 1
         self._exchange = None
+        self._nccl_id = None
 
     # -- handle management ---------------------------------------------------------------------
     def _check(self, rc):
@@ -208,6 +220,8 @@ class GoICP:
                 self._check(self.L.goicp_set_data(self._h, d.ctypes.data, len(d)))
             if self._exchange is not None:
                 self._check(self.L.goicp_set_exchange(self._h, self._exchange, None, 0))
+            if self._nccl_id is not None:
+                self._check(self.L.goicp_nccl_init(self._h, self._nccl_id.ctypes.data, self.rank, self.world_size))
         return self._h
 
     def close(self):
@@ -228,6 +242,12 @@ class GoICP:
     @property
     def Nd(self):
         return 0 if self.pData is None else len(_f32(self.pData, 3))
+
+    def init_nccl(self, unique_id, rank, world_size):
+        """Native multi-GPU exchange: `unique_id` = the 128 bytes of nccl_unique_id() from rank 0 (collective at handle creation)."""
+        self._nccl_id = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert self._nccl_id.size == 128
+        self.rank, self.world_size = rank, world_size
 
     def set_exchange(self, fn, rank, world_size):
         """fn(send: bytes-like np.uint8 array, world) -> np.uint8 array of world*len(send) (rank-major)."""

@@ -203,6 +203,52 @@ __device__ __forceinline__ bool wheap_push(Heap& h, const HeapEntry& v, int lane
     __syncwarp();
     return true;
 }
+// Up to NB pushes in one shared-memory round trip (entries e[0..k-1] pushed in that order; same
+// resulting array as k wheap_push calls).  Lane l holds, for every new slot, the slot's ancestor at
+// tree level l -- all loaded up front.  The pushes are then resolved one after the other in
+// registers: a ballot finds how far the new entry rises, every displaced ancestor moves one level
+// down its path (one shuffle), and a lane that rewrites an index patches its copies of that index
+// held for the later pushes (an index lives at one level, hence in one lane).  Requires the heap to
+// stay in shared memory and n >= 7 (then no new slot is an ancestor of another new slot).
+template <int NB>
+__device__ __forceinline__ void wheap_push_batch(Heap& h, const HeapEntry* e, int k, int lane)
+{
+    const unsigned full = 0xffffffffu;
+    uint4* A = reinterpret_cast<uint4*>(h.sm);
+    const int n0 = h.n;
+    uint4 anc[NB]; int aidx[NB];
+#pragma unroll
+    for (int p = 0; p < NB; p++) {
+        aidx[p] = -1; anc[p] = make_uint4(0u, 0u, 0u, 0u);
+        if (p < k) {
+            const int s = n0 + p, D = 31 - __clz(s + 1);
+            if (lane < D) { aidx[p] = ((s + 1) >> (D - lane)) - 1; anc[p] = A[aidx[p]]; }
+            else if (lane == D) aidx[p] = s;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NB; p++) {
+        if (p < k) {
+            const uint4 vv = he_pack(e[p]);
+            const int s = n0 + p, D = 31 - __clz(s + 1);
+            const bool pred = lane < D && key_less(__uint_as_float(anc[p].x), anc[p].y, e[p].lb, e[p].level);
+            const unsigned bits = __ballot_sync(full, pred);
+            const int rise = __clz(~(bits << (32 - D)));          // displaced ancestors, counted from the parent upwards
+            const int top = D - rise;                              // level the new entry lands on
+            uint4 up;
+            up.x = __shfl_up_sync(full, anc[p].x, 1); up.y = __shfl_up_sync(full, anc[p].y, 1);
+            up.z = __shfl_up_sync(full, anc[p].z, 1); up.w = __shfl_up_sync(full, anc[p].w, 1);
+            if (lane >= top && lane <= D) {
+                const uint4 w = lane == top ? vv : up;
+                A[aidx[p]] = w;
+#pragma unroll
+                for (int q = p + 1; q < NB; q++) if (aidx[q] == aidx[p]) anc[q] = w;
+            }
+        }
+    }
+    h.n = n0 + k;
+    __syncwarp();
+}
 __device__ __forceinline__ HeapEntry wheap_pop(Heap& h, int lane, int* path /* shared, >= 34 ints */)
 {
     uint4* A = reinterpret_cast<uint4*>(h.sm);
@@ -581,8 +627,11 @@ __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier
 constexpr int kGatherThreads = kBnbThreads - 32;
 constexpr int kGatherWarps = kBnbWarps - 1;
 
+// Small clouds (rotated points resident in shared memory) are latency-bound on the owner warp: that variant trades
+// the second resident CTA for 128 registers, so that the batched queue maintenance stays out of local memory (local
+// traffic would queue behind the gathers in L1TEX).  Measured: one CTA per SM loses nothing at these sizes.
 template <bool PTS_SMEM>
-__global__ void __launch_bounds__(kBnbThreads, 2)
+__global__ void __launch_bounds__(kBnbThreads, PTS_SMEM ? 1 : 2)
 inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
                            int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
 {
@@ -662,7 +711,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
             g_waitB += clock64() - g1;
         }
         if (c.dbg && leader && warp == 1 && lane == 0) {
-            unsigned long long* d = c.dbg + (size_t)task_id * 8;
+            unsigned long long* d = c.dbg + (size_t)task_id * 12;
             d[4] = g_waitA; d[5] = g_gather; d[6] = g_reduce; d[7] = g_waitB;
         }
         return;
@@ -730,7 +779,15 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         return e;
     };
     auto flush_pending = [&]() {
-        for (uint32_t m = pmask; m && !status; m &= m - 1) if (!wheap_push(heap, pend_entry(__ffs(m) - 1), lane)) status = 3;
+        uint32_t m = pmask;
+        // common case: the queue stays in shared memory -> the pushes go four at a time, one shared-memory round trip each
+        while (PTS_SMEM && m && !status && heap.n >= 7 && heap.n + 4 <= heap.cap_sm) {
+            HeapEntry e4[4]; int k = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (m) { e4[u] = pend_entry(__ffs(m) - 1); m &= m - 1; k = u + 1; }
+            wheap_push_batch<4>(heap, e4, k, lane);
+        }
+        for (; m && !status; m &= m - 1) if (!wheap_push(heap, pend_entry(__ffs(m) - 1), lane)) status = 3;
         pmask = 0;
         if ((uint32_t)heap.n > max_heap) max_heap = heap.n;
     };
@@ -740,14 +797,16 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         adopt(root);
         publish(done);
     }
-    long long o_maint = 0, o_waitA = 0, o_waitB = 0, o_book = 0;
+    long long o_maint = 0, o_waitA = 0, o_waitB = 0, o_book = 0, o_arrive = 0, o_push = 0;
     for (;;) {
         __syncwarp();
         long long o0 = clock64();
         cluster_arrive();                                                     // (A) cube published
+        const long long oa = clock64(); o_arrive += oa - o0;
         if (!done) {
             // ---- queue maintenance in the shadow of the gathers --------------------------
             flush_pending();
+            o_push += clock64() - oa;
             if (need_pop && !status) {
                 const HeapEntry e = wheap_pop(heap, lane, pop_path);
                 if (e.lb != expect.lb || e.level != expect.level || e.path_lo != expect.path_lo || e.path_hi != expect.path_hi) status = 5;   // cannot happen: the prediction was unambiguous
@@ -820,8 +879,8 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         o_book += clock64() - o1;
     }
     if (c.dbg && lane == 0) {
-        unsigned long long* d = c.dbg + (size_t)task_id * 8;
-        d[0] = o_maint; d[1] = o_waitA; d[2] = o_waitB; d[3] = o_book;
+        unsigned long long* d = c.dbg + (size_t)task_id * 12;
+        d[0] = o_maint; d[1] = o_waitA; d[2] = o_waitB; d[3] = o_book; d[8] = o_arrive; d[9] = o_push;
     }
 
     // ---- results (see inner_bnb_kernel) ---------------------------------------------------------
@@ -992,6 +1051,9 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     const int per = (c.nd + cluster - 1) / cluster;
     size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0)
                 + (trim ? (size_t)per * 8 * sizeof(unsigned) : 0);
+    // GOICP_BNB_MIN_SMEM_KB (experiment): pad the request so that fewer CTAs share an SM (and its L1TEX pipe)
+    static const size_t min_smem = getenv("GOICP_BNB_MIN_SMEM_KB") ? (size_t)atoi(getenv("GOICP_BNB_MIN_SMEM_KB")) << 10 : 0;
+    if (smem < min_smem) smem = min_smem;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n * cluster); cfg.blockDim = dim3(kBnbThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];

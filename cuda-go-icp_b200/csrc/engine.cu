@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -112,6 +113,43 @@ struct DevBuf {
 
 } // namespace
 
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen): a single-GPU user needs no NCCL at all, and inside a
+// torch.distributed process the already-loaded libnccl.so.2 is picked up by soname.  Only the
+// stable C ABI is used: ncclGetUniqueId / ncclCommInitRank / ncclAllGather / ncclCommDestroy.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclUniqueId { char internal[128]; };             // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128)
+typedef struct ncclComm* NcclComm;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (!api.lib) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(api.lib, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(api.lib, "ncclAllGather");
+        api.CommDestroy = (int (*)(NcclComm))dlsym(api.lib, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(api.lib, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) api.err = "libnccl is missing a required symbol";
+    });
+    return &api;
+}
+constexpr int kNcclUint8 = 1;                            // ncclUint8
+} // namespace
+
 struct goicp_handle {
     goicp_params p;
     std::string err;
@@ -146,6 +184,7 @@ struct goicp_handle {
 
     // multi-GPU exchange
     goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
+    NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather;      // native exchange: all-gather of the round's result records on the stream
 
     // timing
     double t_kernels = 0, t_icp = 0;
@@ -333,7 +372,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     if (n <= 0) return GOICP_OK;
     int rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
     const InnerPlan plan = plan_inner(h);
-    const int W = (h->xchg && h->p.world_size > 1) ? h->p.world_size : 1;
+    const int W = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
     const int r = W > 1 ? h->p.rank : 0;
     const int per_rank = (n + W - 1) / W;
     int mine = 0;
@@ -347,7 +386,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     } else mine = n;
     const bool stats = getenv("GOICP_ROUND_STATS") != nullptr;
     BnbConst cdbg = c;
-    if (stats) { CUDA_TRY(h, h->d_dbg.reserve((size_t)8 * (n + 64))); CUDA_TRY(h, cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned long long) * 8 * n, h->stream)); cdbg.dbg = h->d_dbg.p; }
+    if (stats) { CUDA_TRY(h, h->d_dbg.reserve((size_t)12 * (n + 64))); CUDA_TRY(h, cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned long long) * 12 * n, h->stream)); cdbg.dbg = h->d_dbg.p; }
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     if (mine > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
@@ -358,6 +397,20 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results.p, sizeof(InnerResult) * n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else if (h->nccl) {
+        // native exchange: the per-rank result blocks (padded to per_rank records) are all-gathered by NCCL on the
+        // engine's stream right behind the kernel; one D2H copy brings every rank's results back.  This all-gather of
+        // 48-byte records is the round's best-bound exchange: every rank commits the same results in the same order.
+        CUDA_TRY(h, h->d_gather.reserve((size_t)per_rank * W));
+        CUDA_TRY(h, h->d_results.reserve((size_t)per_rank));
+        if (mine < per_rank) CUDA_TRY(h, cudaMemsetAsync(h->d_results.p + mine, 0, sizeof(InnerResult) * (per_rank - mine), h->stream));
+        const int nrc = nccl_api()->AllGather(h->d_results.p, h->d_gather.p, sizeof(InnerResult) * per_rank, kNcclUint8, h->nccl, h->stream);
+        if (nrc != 0) return fail(h, GOICP_ERR_CUDA, std::string("ncclAllGather: ") + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(nrc) : "error"));
+        std::vector<InnerResult> recv((size_t)per_rank * W);
+        CUDA_TRY(h, cudaMemcpyAsync(recv.data(), h->d_gather.p, sizeof(InnerResult) * per_rank * W, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int t = 0; t < n; t++) h->h_results[t] = recv[(size_t)(t % W) * per_rank + t / W];
     } else {
         std::vector<InnerResult> mine_res(std::max(mine, 1));
         if (mine > 0) CUDA_TRY(h, cudaMemcpyAsync(mine_res.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
@@ -373,11 +426,11 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         fprintf(stderr, "[round] tasks %d kernel %.3f ms; slowest task %.3f Mcyc (pops %u, level %d); max pops %u; total pops %u; sum task cycles %.1f Mcyc; max heap %u; tasks with contenders %d\n",
                 n, ms, maxc * 1024e-6, h->h_results[arg].pops, h->h_tasks[arg].level, maxp, sump, sumc * 1024e-6, maxh, flagged);
         if (W == 1) {
-            unsigned long long d[8];
-            cudaMemcpy(d, h->d_dbg.p + (size_t)8 * arg, sizeof d, cudaMemcpyDeviceToHost);
+            unsigned long long d[12];
+            cudaMemcpy(d, h->d_dbg.p + (size_t)12 * arg, sizeof d, cudaMemcpyDeviceToHost);
             const double steps = std::max(1u, h->h_results[arg].evals / 8);
-            fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
-                    plan.cluster, d[0] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
+            fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f (arrive %.0f, pushes %.0f) waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
+                    plan.cluster, d[0] / steps, d[8] / steps, d[9] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
         }
     }
     if (lists) {
@@ -530,6 +583,8 @@ int goicp_destroy(goicp_handle* h)
     if (!h) return GOICP_OK;
     if (h->cuda_ready) {
         cudaSetDevice(h->p.device);
+        h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
+        h->d_gather.release();
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
@@ -684,9 +739,10 @@ int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* leve
         h->h_tasks[k].level = level[k]; h->h_tasks[k].opt_error = opt_error[k]; h->h_tasks[k].pad = 0;
     }
     goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;       // this entry point is single-GPU
+    NcclComm saved_nccl = h->nccl; h->nccl = nullptr;
     std::vector<std::shared_ptr<CandList>> lists;
     rc = run_inner_batch(h, c, n, nullptr, &lists);
-    h->xchg = saved;
+    h->xchg = saved; h->nccl = saved_nccl;
     if (rc) return rc;
     std::vector<InnerTask> tasks(h->h_tasks, h->h_tasks + n);
     std::vector<InnerResult> results(h->h_results, h->h_results + n);
@@ -737,6 +793,42 @@ int goicp_icp_dt(goicp_handle* h, float R[9], float t[3], float* dt_error_out)
     if (!h || !R || !t || !dt_error_out) return fail(h, GOICP_ERR_INVALID, "icp_dt: bad arguments");
     BnbConst c; int rc = make_const(h, c); if (rc) return rc;
     return icp_then_dt(h, c, R, t, dt_error_out);
+}
+
+int goicp_nccl_unique_id(void* id128_out)
+{
+    if (!id128_out) return GOICP_ERR_INVALID;
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return GOICP_ERR_CUDA;
+    NcclUniqueId id;
+    if (a->GetUniqueId(&id) != 0) return GOICP_ERR_CUDA;
+    std::memcpy(id128_out, &id, sizeof id);
+    return GOICP_OK;
+}
+
+int goicp_nccl_init(goicp_handle* h, const void* id128, int rank, int world_size)
+{
+    if (!h || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return fail(h, GOICP_ERR_INVALID, "nccl_init: bad arguments");
+    NcclApi* a = nccl_api();
+    if (!a->err.empty()) return fail(h, GOICP_ERR_CUDA, a->err);
+    int rc = ensure_cuda(h); if (rc) return rc;
+    // communicators are process-wide, keyed by the unique id: creating one is a collective costing ~0.1 s, and the
+    // handles of one process (one GPU) share it -- calls on them are serialised by the caller anyway
+    static std::mutex comm_mtx;
+    static std::unordered_map<std::string, NcclComm> comms;
+    NcclUniqueId id; std::memcpy(&id, id128, sizeof id);
+    const std::string key(id.internal, sizeof id.internal);
+    std::lock_guard<std::mutex> lk(comm_mtx);
+    auto it = comms.find(key);
+    if (it == comms.end()) {
+        NcclComm comm = nullptr;
+        const int nrc = a->CommInitRank(&comm, world_size, id, rank);
+        if (nrc != 0) return fail(h, GOICP_ERR_CUDA, std::string("ncclCommInitRank: ") + (a->GetErrorString ? a->GetErrorString(nrc) : "error"));
+        it = comms.emplace(key, comm).first;
+    }
+    h->nccl = it->second;
+    h->p.rank = rank; h->p.world_size = world_size;
+    return GOICP_OK;
 }
 
 int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int use_device_buffers)
@@ -812,7 +904,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     long epoch = 0;
     // default speculation width: ~4 SMs' worth of clusters per cube (36 cubes = 576 inner BnBs per round on 148 SMs)
     int spec = h->p.spec_cubes > 0 ? h->p.spec_cubes : std::max(1, h->sm_count / 4);
-    if (h->xchg && h->p.world_size > 1) spec *= h->p.world_size;
+    if ((h->xchg || h->nccl) && h->p.world_size > 1) spec *= h->p.world_size;
 
     // Evaluate `first` (must be evaluated) plus the best not-yet-evaluated queue entries.
     auto evaluate_round = [&](const RotNode& first) -> int {
@@ -910,9 +1002,10 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                         if (!cl) {      // evaluated on another rank: re-derive the contender list here (deterministic)
                             h->h_tasks[0] = task;
                             goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;
+                            NcclComm saved_nccl = h->nccl; h->nccl = nullptr;
                             std::vector<std::shared_ptr<CandList>> one;
                             rc = run_inner_batch(h, c, 1, nullptr, &one);
-                            h->xchg = saved;
+                            h->xchg = saved; h->nccl = saved_nccl;
                             if (rc) return rc;
                             cl = one[0];
                         }

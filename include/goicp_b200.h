@@ -184,6 +184,16 @@ int goicp_trim_memory(void);
 typedef int (*goicp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank, int is_device);
 int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int use_device_buffers);
 
+/* Native exchange over NCCL (NVLink / NVSwitch): rank 0 obtains a 128-byte ncclUniqueId, hands it to the
+ * other ranks by any means (torch.distributed broadcast, MPI, a file), then every rank calls goicp_nccl_init
+ * (collective).  From then on goicp_register shards each round's inner BnBs over the ranks and all-gathers
+ * the 48-byte result records with ncclAllGather on the engine's own stream, right behind the kernel; every
+ * rank commits the same results in the same order, so the best upper bound (the prune threshold), the
+ * rotation queue and the certificate stay replicated -- this is the per-round best-bound exchange of
+ * SURVEY.md section 8e.  libnccl.so.2 is loaded on demand; single-GPU use never touches it. */
+int goicp_nccl_unique_id(void* id128_out);
+int goicp_nccl_init(goicp_handle* h, const void* id128, int rank, int world_size);
+
 /* Host-only self test of the sharding + exchange plumbing used by multi-GPU rounds (no GPU needed). */
 int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void* user, int* mismatches);
 
