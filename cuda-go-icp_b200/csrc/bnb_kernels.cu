@@ -627,11 +627,12 @@ __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier
 constexpr int kGatherThreads = kBnbThreads - 32;
 constexpr int kGatherWarps = kBnbWarps - 1;
 
-// Small clouds (rotated points resident in shared memory) are latency-bound on the owner warp: that variant trades
-// the second resident CTA for 128 registers, so that the batched queue maintenance stays out of local memory (local
-// traffic would queue behind the gathers in L1TEX).  Measured: one CTA per SM loses nothing at these sizes.
-template <bool PTS_SMEM>
-__global__ void __launch_bounds__(kBnbThreads, PTS_SMEM ? 1 : 2)
+// LOWLAT: for rounds bound by their longest inner BnB (not by throughput) the kernel trades the second resident CTA
+// for 128 registers, so that the batched queue maintenance of the owner warp stays out of local memory (local traffic
+// would queue behind the gathers in L1TEX).  Measured on the bunny config: the longest task of a round gets 1.4x
+// faster, the sum of all task cycles 1.5x smaller, with half the resident clusters; the engine picks per round.
+template <bool PTS_SMEM, bool LOWLAT>
+__global__ void __launch_bounds__(kBnbThreads, LOWLAT ? 1 : 2)
 inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
                            int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
 {
@@ -781,7 +782,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     auto flush_pending = [&]() {
         uint32_t m = pmask;
         // common case: the queue stays in shared memory -> the pushes go four at a time, one shared-memory round trip each
-        while (PTS_SMEM && m && !status && heap.n >= 7 && heap.n + 4 <= heap.cap_sm) {
+        while (LOWLAT && m && !status && heap.n >= 7 && heap.n + 4 <= heap.cap_sm) {
             HeapEntry e4[4]; int k = 0;
 #pragma unroll
             for (int u = 0; u < 4; u++) if (m) { e4[u] = pend_entry(__ffs(m) - 1); m &= m - 1; k = u + 1; }
@@ -1028,14 +1029,17 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     for (int i = 0; i < 4; i++) stat = st[i] > stat ? st[i] : stat;
     {
         cudaFuncAttributes a;
-        if ((e = cudaFuncGetAttributes(&a, inner_bnb_pipelined_kernel<true>)) != cudaSuccess) return e;
-        stat = (int)a.sharedSizeBytes > stat ? (int)a.sharedSizeBytes : stat;
-        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
-        if ((e = cudaFuncGetAttributes(&a, inner_bnb_pipelined_kernel<false>)) != cudaSuccess) return e;
-        stat = (int)a.sharedSizeBytes > stat ? (int)a.sharedSizeBytes : stat;
-        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(inner_bnb_pipelined_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) != cudaSuccess) return e;
+        auto conf = [&](auto kern) -> cudaError_t {
+            cudaError_t e2 = cudaFuncGetAttributes(&a, kern);
+            if (e2 != cudaSuccess) return e2;
+            stat = (int)a.sharedSizeBytes > stat ? (int)a.sharedSizeBytes : stat;
+            if ((e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - (int)a.sharedSizeBytes)) != cudaSuccess) return e2;
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        };
+        if ((e = conf(inner_bnb_pipelined_kernel<true, false>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<true, true>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<false, false>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<false, true>)) != cudaSuccess) return e;
     }
     e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
     if (e != cudaSuccess) return e;
@@ -1044,7 +1048,7 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     return e;
 }
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, cudaStream_t s)
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const bool trim = c.inlier_num < c.nd;
@@ -1062,8 +1066,12 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     cfg.attrs = attr; cfg.numAttrs = 1;
     BnbConst cc = c;
     static const bool legacy = getenv("GOICP_NO_PIPELINE") != nullptr;     // A/B switch for profiling
-    if (pts_in_smem && !trim && !legacy) return cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
-    if (!pts_in_smem && !trim && !legacy) return cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (!trim && !legacy) {
+        if (pts_in_smem) return low_latency ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
+                                            : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+        return low_latency ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
+                           : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    }
     if (pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     if (!pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);

@@ -184,6 +184,7 @@ struct goicp_handle {
 
     // multi-GPU exchange
     goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
+    bool low_latency = true;             // inner-BnB kernel variant of the next round (see run_inner_batch)
     NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather;      // native exchange: all-gather of the round's result records on the stream
 
     // timing
@@ -390,7 +391,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     if (mine > 0) {
         CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->stream));
+        CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->low_latency, h->stream));
         h->launches++;
     }
     if (W == 1) {
@@ -432,6 +433,19 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f (arrive %.0f, pushes %.0f) waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
                     plan.cluster, d[0] / steps, d[8] / steps, d[9] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
         }
+    }
+    {
+        // Variant for the next round, from this round's task cycle counts (all ranks' tasks).  In low-latency units
+        // (measured ratios on the bunny config: a task is 1.43x slower, the sum of task cycles 1.54x larger in the
+        // two-CTAs-per-SM variant) a round costs about max(longest task, sum / resident clusters) in either variant.
+        static const char* force = getenv("GOICP_BNB_VARIANT");       // "lat" / "thr": pin the variant (experiments)
+        double maxc = 0, sumc = 0;
+        for (int t = 0; t < n; t++) { const double k = h->h_results[t].kcycles; sumc += k; if (k > maxc) maxc = k; }
+        if (!h->low_latency) { maxc /= 1.43; sumc /= 1.54; }
+        const double per_rank_sum = sumc / W;
+        const double res_lat = std::max(1, h->sm_count / plan.cluster), res_thr = std::max(1, 2 * h->sm_count / plan.cluster);
+        const double t_lat = std::max(maxc, per_rank_sum / res_lat), t_thr = std::max(1.43 * maxc, 1.54 * per_rank_sum / res_thr);
+        h->low_latency = force ? force[0] == 'l' : t_lat <= t_thr;
     }
     if (lists) {
         // contender lists of the upper-bound passes that have any (local tasks only; a rank that
@@ -870,7 +884,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
-    h->t_kernels = 0; h->t_icp = 0; h->launches = 0;
+    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true;
     const double t_begin = now_s();
     h->initialized = false;
     int rc = initialize(h); if (rc) return rc;

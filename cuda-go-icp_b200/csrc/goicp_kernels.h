@@ -10,7 +10,7 @@ cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n
 cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
 cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, cudaStream_t s);
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, cudaStream_t s);
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
                                   float* d_out5, int smem_limit, cudaStream_t s);
 cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, cudaStream_t s);
