@@ -4,7 +4,7 @@
 Run in the build container only (needs /root/reference and `make -C oracle ref`):
 
     python tests/golden/make_golden.py clouds      # deterministic bunny subsamples (seeds 1234/1235)
-    python tests/golden/make_golden.py runs        # 5 full reference Go-ICP runs, S=300 (~13 min CPU)
+    python tests/golden/make_golden.py runs        # 9 full reference Go-ICP runs, S=300 (~20 min CPU)
     python tests/golden/make_golden.py small       # small-S DT grids / NN / ICP / inner-BnB vectors (seconds)
     python tests/golden/make_golden.py config2     # full-size bun045/bun000 clouds + reference NN indices + ICP result
 
@@ -29,7 +29,22 @@ RUNS = {  # name: (model fixture, data fixture, mse, trim)
     # fgoicp's translation domain [-1,1]^3 (extra CLI args: S tx ty tz tw)
     "spanner_s0.02_mse1e-3": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
     "spanner_s0.02_mse1e-3_trim0.1": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0.1", "300", "-1", "-1", "-1", "2"),
+    # BASELINE config 3 substitute (the Artec targets are missing): target = the scan itself moved by a seeded rigid
+    # motion (150 deg / 110 deg about a random axis, |t| <= 0.25) and subsampled with another seed, translation domain [-1,1]^3.
+    # Unlike the spanner pair the first ICP does not solve these: 23 / 250 rotation cubes are expanded.
+    "skull_s0.03_mse1e-3": ("skull_model_moved_s0.03_seed1234.f32", "skull_data_s0.03_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
+    "face_s0.025_mse1e-3": ("face_model_moved_s0.025_seed1234.f32", "face_data_s0.025_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
 }
+
+
+def artec_pose(seed, deg, tmax):
+    """seeded rigid motion: rotation by `deg` about a random axis, translation uniform in [-tmax, tmax]^3"""
+    r = np.random.default_rng(seed)
+    ax = r.normal(size=3); ax /= np.linalg.norm(ax)
+    a = np.deg2rad(deg)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+    return R.astype(np.float32), r.uniform(-tmax, tmax, 3).astype(np.float32)
 
 
 def clouds():
@@ -37,6 +52,13 @@ def clouds():
     pkg = importlib.import_module("cuda-go-icp_b200")     # host loader only (binary PLY); seeded like the TXT fixtures
     pkg.load_cloud(f"{REFDATA}/artec3d/noisy_flipped_model_spanner.ply", 0.02, 0.02, 1234).tofile(os.path.join(HERE, "spanner_model_noisy_flipped_s0.02_seed1234.f32"))
     pkg.load_cloud(f"{REFDATA}/artec3d/rotated_model_spanner.ply", 0.02, 0.02, 1235).tofile(os.path.join(HERE, "spanner_data_rotated_s0.02_seed1235.f32"))
+    for name, f, resize, sub, seed, deg in (("skull", "data_skull.ply", 0.01, 0.03, 7, 150.0), ("face", "data_face_left.ply", 0.007, 0.025, 11, 110.0)):
+        src_m = pkg.load_cloud(f"{REFDATA}/artec3d/{f}", sub, resize, 1234)
+        src_d = pkg.load_cloud(f"{REFDATA}/artec3d/{f}", sub, resize, 1235)
+        R, t = artec_pose(seed, deg, 0.25)
+        (src_m @ R.T + t).astype(np.float32).tofile(os.path.join(HERE, f"{name}_model_moved_s{sub}_seed1234.f32"))
+        src_d.astype(np.float32).tofile(os.path.join(HERE, f"{name}_data_s{sub}_seed1235.f32"))
+        np.savez(os.path.join(HERE, f"{name}_pose_gt.npz"), R=R, t=t)
     for sub in ("0.1", "0.033"):
         for kind, seed in (("model", 1234), ("data", 1235)):
             out = os.path.join(HERE, f"bunny_{kind}_s{sub}_seed{seed}.f32")

@@ -292,3 +292,23 @@ def test_spanner_noisy_scan_with_and_without_trimming(pkg, runs, name):
     g.Register()
     _check_run(g.result, gold)
     g.close()
+
+
+@pytest.mark.parametrize("name", ["skull_s0.03_mse1e-3", "face_s0.025_mse1e-3"])
+def test_artec_skull_and_face_scans(pkg, runs, name):
+    """BASELINE config 3 substitute: Artec skull / face scans (binary PLY, CRLF headers, RGB payload) against a
+    rigidly moved copy of themselves (150 / 110 degrees: ICP alone does not solve it), fgoicp's translation
+    domain [-1,1]^3.  Same pose, SSE, exit path and search counters as the reference; the pose is also the
+    ground-truth motion the target was generated with."""
+    import os
+    from conftest import GOLDEN, load_cloud
+    gold = runs[name]
+    g = pkg.GoICP(gold["mse"])
+    g.pModel, g.pData = load_cloud(gold["model"]), load_cloud(gold["data"])
+    g.initNodeTrans = gold["trans_cube"]
+    g.BuildDT()
+    g.Register()
+    _check_run(g.result, gold)
+    gt = np.load(os.path.join(GOLDEN, name.split("_")[0] + "_pose_gt.npz"))
+    assert rot_angle(g.result["R"], gt["R"]) < 2e-2 and np.abs(g.result["t"] - gt["t"]).max() < 2e-2
+    g.close()

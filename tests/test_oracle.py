@@ -131,3 +131,17 @@ def test_config2_full_size_nn_and_icp(restated):
     assert np.array_equal(idx, g["nn_idx"]) and np.array_equal(bits(d2), bits(g["nn_d2"]))
     e, R, t, iters, _ = restated.icp_run(kd, g["data"], np.eye(3), np.zeros(3), 10000, 1e-9, 0.0)
     assert np.float32(e) == g["icp_err"] and np.array_equal(R, g["icp_R"]) and np.array_equal(t, g["icp_t"])
+
+
+def test_restatement_reproduces_the_skull_golden_run(restated, runs):
+    """Artec skull scan vs its moved copy (BASELINE config 3 substitute, S=300, [-1,1]^3 translation domain): the C
+    restatement follows the unmodified reference's run -- same pose, SSE, pops and evaluation count (about 50 s)."""
+    from conftest import load_cloud
+    gold = runs["skull_s0.03_mse1e-3"]
+    g = restated.create(load_cloud(gold["model"]), load_cloud(gold["data"]), gold["mse"], 0.0, 300, trans_cube=gold["trans_cube"])
+    restated.L.go_build_dt(g)
+    r = restated.register(g)
+    assert (r["rot_pops"], r["trans_pops"], r["exit_path"]) == (gold["rot_pops"], gold["trans_pops"], gold["exit_path"])
+    assert r["bound_evals"] + r["icp_calls"] == gold["bound_evals_plus_icp"]
+    assert np.float32(r["sse"]) == np.float32(gold["sse"])
+    assert np.allclose(r["R"].reshape(-1), gold["R"], atol=2e-7) and np.allclose(r["t"], gold["t"], atol=2e-7)
