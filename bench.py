@@ -342,7 +342,7 @@ def main():
            "d2h_bytes_per_step": int(res["rounds"] * 48 * 288 + 256),
            "seconds_per_step": e2e_med, "seconds_per_step_samples": [round(x, 4) for x in e2e_s], "statistic": "median",
            "seconds_create_h2d_dt_build": float(np.median([p[0] for p in e2e_parts])),
-           "seconds_register_and_readback": float(np.median([p[1] for p in e2e_parts])), "includes": "create + H2D clouds + GPU DT build (reference-exact mode) + Register + result D2H"}
+           "seconds_register_and_readback": float(np.median([p[1] for p in e2e_parts])), "includes": "create + H2D clouds + GPU DT build (reference-exact mode; Register's first ICP runs next to it on the idle SMs) + Register + result D2H"}
 
     # DT-gather kernel alone at full occupancy (roofline of the gather itself)
     peaks = {}

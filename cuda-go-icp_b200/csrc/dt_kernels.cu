@@ -14,6 +14,7 @@
 //
 // GOICP_DT_EXACT_EDT is the separable exact squared-Euclidean transform (three 1-D lower-envelope
 // passes over integer squared distances), fully parallel.
+#include <ctime>
 #include "dt_kernels.h"
 #include "mem_pool.h"
 #include <cmath>
@@ -692,6 +693,10 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
                             float* d_out, double* meta, cudaStream_t stream, std::string& msg)
 {
     cudaError_t e;
+    const bool trace = getenv("GOICP_TRACE_DT") != nullptr;
+    auto tnow = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    double tprev = tnow();
+    auto mark = [&](const char* what) { if (trace) { const double t = tnow(); fprintf(stderr, "[dt trace] %-28s %.3f ms\n", what, 1e3 * (t - tprev)); tprev = t; } };
     if (S > kMaxS) { msg = "dt_size > 1024"; return cudaErrorInvalidValue; }
     if (mode == 0 && S > kMaxRefS) { msg = "dt_size > 960 in reference-order mode (use the exact EDT mode)"; return cudaErrorInvalidValue; }
     dt_frame_host(model, nm, S, expand, meta);
@@ -703,12 +708,14 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
 #define DT_TRY(expr) do { e = (expr); if (e != cudaSuccess) { msg = #expr; cleanup(); return e; } } while (0)
     DT_TRY(pool_alloc((void**)&G, ng * sizeof(V2)));
     DT_TRY(pool_alloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
+    mark("frame + pool_alloc");
     DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
     // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
     dt_init_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(G, ng, mode == 0 ? 1 : 0);
     DT_TRY(cudaGetLastError());
     dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, P, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
     DT_TRY(cudaGetLastError());
+    mark("memcpy + init + seed launch");
     if (mode == 0) {
         const bool timing = getenv("GOICP_DT_TIMING") != nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -735,6 +742,7 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
             dt_propagate_kernel<<<1, ncons * 32, smem, stream>>>(G, S);
         }
         DT_TRY(cudaGetLastError());
+        mark("propagate launch");
         if (timing) {
             cudaEventRecord(ev1, stream); cudaEventSynchronize(ev1);
             float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
@@ -766,9 +774,12 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         edt_finalize_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, stream>>>(D0, S, meta[3], d_out);
         DT_TRY(cudaGetLastError());
     }
+    mark("finalize launch");
     DT_TRY(cudaStreamSynchronize(stream));
+    mark("stream sync");
 #undef DT_TRY
     cleanup();
+    mark("cleanup");
     return cudaSuccess;
 }
 

@@ -25,6 +25,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -46,7 +47,10 @@ double now_s()
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-struct RotNode { float a, b, c, w, ub, lb; int l; };                  // ROTNODE, jly_goicp.h:44-58
+struct RotNode {                                                       // ROTNODE, jly_goicp.h:44-58
+    float a, b, c, w, ub, lb; int l;
+    uint32_t pops_ub = 0, pops_lb = 0;   // not in the reference: translation pops of this cube's own two passes, a cost hint for its children's
+};
 struct RotLower {                                                      // its operator<
     bool operator()(const RotNode& n1, const RotNode& n2) const { return n1.lb != n2.lb ? n1.lb > n2.lb : n1.w < n2.w; }
 };
@@ -165,7 +169,7 @@ struct goicp_handle {
     // data cloud on device (x,y,z,norm)
     DevBuf<float4> d_data; bool data_uploaded = false;
     // kd-tree
-    HostKdTree kd_host; DevBuf<KdNode> d_kd_nodes; DevBuf<int32_t> d_kd_vind; DevBuf<float4> d_kd_leaf; DevBuf<float> d_model;
+    HostKdTree kd_host; DevBuf<KdNode> d_kd_nodes; DevBuf<float4> d_kd_boxes; DevBuf<int32_t> d_kd_vind; DevBuf<float4> d_kd_leaf; DevBuf<float> d_model;
     bool kd_ready = false;
     // scratch
     DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
@@ -189,6 +193,9 @@ struct goicp_handle {
 
     // timing
     double t_kernels = 0, t_icp = 0;
+    // ICP from the identity pose, run by goicp_build_dt next to the distance-transform build (it needs no DT) and
+    // consumed by the first goicp_register after it
+    cudaStream_t stream_dt = nullptr; bool icp0_valid = false; goicp_icp_result icp0;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -200,23 +207,48 @@ int fail(goicp_handle* h, int code, const std::string& msg) { if (h) h->err = ms
     do { cudaError_t _e = (expr);                                                                 \
          if (_e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
 
+// Per-device facts and launch configuration are looked up once per process, and the streams / events of destroyed
+// handles are kept for the next one: cudaGetDeviceProperties, cudaFuncSetAttribute and stream creation take the
+// driver's global lock, and a registration through a fresh handle spent 3-110 ms here (measured; whenever a
+// monitoring process happened to hold that lock) before any work started.
+struct DeviceFacts { bool ready = false; int sm_count = 0, max_smem_optin = 0, inner_dyn_smem = 0; };
+struct StreamSet { cudaStream_t stream = nullptr, stream_dt = nullptr; cudaEvent_t ev0 = nullptr, ev1 = nullptr; };
+std::mutex g_dev_mtx;
+std::unordered_map<int, DeviceFacts> g_dev_facts;
+std::unordered_map<int, std::vector<StreamSet>> g_stream_sets;
+
 int ensure_cuda(goicp_handle* h)
 {
     if (h->cuda_ready) return GOICP_OK;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(h, GOICP_ERR_CUDA, std::string("no CUDA device available (this engine has no CPU fallback): ") + cudaGetErrorString(e));
-    CUDA_TRY(h, cudaSetDevice(h->p.device));
-    cudaDeviceProp prop;
-    CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->p.device));
-    if (prop.major < 10) return fail(h, GOICP_ERR_CUDA, "device is not sm_100-class; this library ships sm_100a code only");
-    h->sm_count = prop.multiProcessorCount;
-    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUDA_TRY(h, cudaEventCreate(&h->ev0));
-    CUDA_TRY(h, cudaEventCreate(&h->ev1));
-    CUDA_TRY(h, inner_bnb_configure(h->max_smem_optin, &h->inner_dyn_smem));
+    std::lock_guard<std::mutex> lk(g_dev_mtx);
+    DeviceFacts& f = g_dev_facts[h->p.device];
+    if (!f.ready) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return fail(h, GOICP_ERR_CUDA, std::string("no CUDA device available (this engine has no CPU fallback): ") + cudaGetErrorString(e));
+        CUDA_TRY(h, cudaSetDevice(h->p.device));
+        int major = 0;
+        CUDA_TRY(h, cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, h->p.device));
+        if (major < 10) return fail(h, GOICP_ERR_CUDA, "device is not sm_100-class; this library ships sm_100a code only");
+        CUDA_TRY(h, cudaDeviceGetAttribute(&f.sm_count, cudaDevAttrMultiProcessorCount, h->p.device));
+        CUDA_TRY(h, cudaDeviceGetAttribute(&f.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->p.device));
+        CUDA_TRY(h, inner_bnb_configure(f.max_smem_optin, &f.inner_dyn_smem));
+        f.ready = true;
+    } else {
+        CUDA_TRY(h, cudaSetDevice(h->p.device));
+    }
+    h->sm_count = f.sm_count; h->max_smem_optin = f.max_smem_optin; h->inner_dyn_smem = f.inner_dyn_smem;
+    std::vector<StreamSet>& spare = g_stream_sets[h->p.device];
+    if (!spare.empty()) {
+        const StreamSet ss = spare.back(); spare.pop_back();
+        h->stream = ss.stream; h->stream_dt = ss.stream_dt; h->ev0 = ss.ev0; h->ev1 = ss.ev1;
+    } else {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream_dt, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreate(&h->ev0));
+        CUDA_TRY(h, cudaEventCreate(&h->ev1));
+    }
     h->cuda_ready = true;
     return GOICP_OK;
 }
@@ -249,10 +281,12 @@ int ensure_kdtree(goicp_handle* h)
         leaf[i] = make_float4(h->model[3 * id], h->model[3 * id + 1], h->model[3 * id + 2], w);
     }
     CUDA_TRY(h, h->d_kd_nodes.reserve(h->kd_host.nodes.size()));
+    CUDA_TRY(h, h->d_kd_boxes.reserve(2 * h->kd_host.nodes.size()));
     CUDA_TRY(h, h->d_kd_vind.reserve(h->nm));
     CUDA_TRY(h, h->d_kd_leaf.reserve(h->nm));
     CUDA_TRY(h, h->d_model.reserve((size_t)3 * h->nm));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_nodes.p, h->kd_host.nodes.data(), sizeof(KdNode) * h->kd_host.nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_boxes.p, h->kd_host.boxes.data(), sizeof(float) * h->kd_host.boxes.size(), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_vind.p, h->kd_host.vind.data(), sizeof(int32_t) * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
@@ -265,7 +299,7 @@ int ensure_kdtree(goicp_handle* h)
 KdView kd_view(const goicp_handle* h)
 {
     KdView v;
-    v.nodes = h->d_kd_nodes.p; v.vind = h->d_kd_vind.p; v.pts_leaf = h->d_kd_leaf.p; v.model = h->d_model.p; v.nm = h->nm;
+    v.nodes = h->d_kd_nodes.p; v.boxes = h->d_kd_boxes.p; v.vind = h->d_kd_vind.p; v.pts_leaf = h->d_kd_leaf.p; v.model = h->d_model.p; v.nm = h->nm;
     for (int i = 0; i < 3; i++) { v.bb_lo[i] = h->kd_host.bb_lo[i]; v.bb_hi[i] = h->kd_host.bb_hi[i]; }
     return v;
 }
@@ -506,7 +540,7 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     return GOICP_OK;
 }
 
-int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, float err_diff, goicp_icp_result* out)
+int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, float err_diff, goicp_icp_result* out, int blocks_cap = 1 << 30)
 {
     int rc = ensure_cuda(h); if (rc) return rc;
     rc = upload_data(h); if (rc) return rc;
@@ -529,7 +563,7 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     // queries are interleaved over the CTAs, 32 per CTA and pass: use every SM the cooperative launch allows
-    const int blocks = std::max(1, std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32));
+    const int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32), blocks_cap));
     CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->max_smem_optin, h->stream));
     h->launches++;
     CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
@@ -545,11 +579,14 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
 }
 
 // GoICP::ICP (jly_goicp.cpp:93-132)
-int icp_then_dt(goicp_handle* h, const BnbConst& c, float* R, float* t, float* err)
+int icp_then_dt(goicp_handle* h, const BnbConst& c, float* R, float* t, float* err, const goicp_icp_result* done = nullptr)
 {
     goicp_icp_result r;
-    int rc = run_icp(h, R, t, h->p.icp_max_iter, h->p.mse_threshold / 10000, &r);      // err_diff_def = MSEThresh/10000 (jly_goicp.cpp:186)
-    if (rc) return rc;
+    if (done) r = *done;
+    else {
+        int rc = run_icp(h, R, t, h->p.icp_max_iter, h->p.mse_threshold / 10000, &r);  // err_diff_def = MSEThresh/10000 (jly_goicp.cpp:186)
+        if (rc) return rc;
+    }
     std::memcpy(R, r.R, sizeof r.R); std::memcpy(t, r.t, sizeof r.t);
     return score_pose(h, c, R, t, err);
 }
@@ -599,14 +636,23 @@ int goicp_destroy(goicp_handle* h)
         cudaSetDevice(h->p.device);
         h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
         h->d_gather.release();
-        h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
+        h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
         if (h->h_results) pool_free_host(h->h_results);
         if (h->h_tasks) pool_free_host(h->h_tasks);
-        if (h->ev0) cudaEventDestroy(h->ev0);
-        if (h->ev1) cudaEventDestroy(h->ev1);
-        if (h->stream) cudaStreamDestroy(h->stream);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->stream_dt) cudaStreamSynchronize(h->stream_dt);
+        if (h->stream && h->stream_dt && h->ev0 && h->ev1) {       // kept for the next handle on this device (ensure_cuda)
+            std::lock_guard<std::mutex> lk(g_dev_mtx);
+            StreamSet ss; ss.stream = h->stream; ss.stream_dt = h->stream_dt; ss.ev0 = h->ev0; ss.ev1 = h->ev1;
+            g_stream_sets[h->p.device].push_back(ss);
+        } else {
+            if (h->ev0) cudaEventDestroy(h->ev0);
+            if (h->ev1) cudaEventDestroy(h->ev1);
+            if (h->stream) cudaStreamDestroy(h->stream);
+            if (h->stream_dt) cudaStreamDestroy(h->stream_dt);
+        }
     }
     delete h;
     return GOICP_OK;
@@ -617,13 +663,13 @@ const char* goicp_last_error(const goicp_handle* h) { return h ? h->err.c_str() 
 int goicp_set_model(goicp_handle* h, const float* xyz, int n)
 {
     if (!h || !xyz || n <= 0) return fail(h, GOICP_ERR_INVALID, "set_model: bad arguments");
-    h->model.assign(xyz, xyz + 3 * (size_t)n); h->nm = n; h->kd_ready = false;
+    h->model.assign(xyz, xyz + 3 * (size_t)n); h->nm = n; h->kd_ready = false; h->icp0_valid = false;
     return GOICP_OK;
 }
 int goicp_set_data(goicp_handle* h, const float* xyz, int n)
 {
     if (!h || !xyz || n <= 0) return fail(h, GOICP_ERR_INVALID, "set_data: bad arguments");
-    h->data.assign(xyz, xyz + 3 * (size_t)n); h->nd = n; h->data_uploaded = false; h->initialized = false;
+    h->data.assign(xyz, xyz + 3 * (size_t)n); h->nd = n; h->data_uploaded = false; h->initialized = false; h->icp0_valid = false;
     return GOICP_OK;
 }
 
@@ -653,15 +699,41 @@ int goicp_dt_size(const goicp_handle* h) { return h && h->have_dt ? h->dt_size :
 int goicp_build_dt(goicp_handle* h)
 {
     if (!h || h->nm <= 0) return fail(h, GOICP_ERR_INVALID, "build_dt: no model cloud set");
+    const bool trace = getenv("GOICP_TRACE_DT") != nullptr;
+    const double tr0 = now_s();
     int rc = ensure_cuda(h); if (rc) return rc;
+    if (trace) fprintf(stderr, "[dt trace] ensure_cuda %.3f ms\n", 1e3 * (now_s() - tr0));
     const int S = h->p.dt_size;
     if (S < 2 || S > 1024) return fail(h, GOICP_ERR_INVALID, "build_dt: dt_size out of range [2,1024]");
     const size_t n3 = (size_t)S * S * S;
     CUDA_TRY(h, h->d_dt.reserve(n3));
     std::string msg;
-    cudaError_t e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
-    if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, "dt_build_device: " + msg + ": " + cudaGetErrorString(e));
+    cudaError_t e = cudaSuccess;
+    h->icp0_valid = false;
+    const bool no_overlap = getenv("GOICP_NO_PREFETCH") != nullptr;
+    if (h->nd > 0 && !no_overlap) {
+        // GoICP::Register starts with an ICP from the identity pose (jly_goicp.cpp:378-391) that reads the clouds and
+        // the kd-tree but not the DT.  The reference-order DT propagation is one CTA on one SM for most of the build
+        // (DESIGN.md section 5), so that refinement runs here, on the other SMs, while the DT is being built: the DT
+        // build goes to its own stream on a helper thread, this thread builds the kd-tree and drives the ICP kernel
+        // (capped to the SMs the DT leaves free, so that the cooperative launch can be resident next to it).
+        std::thread worker([&]() {
+            cudaSetDevice(h->p.device);
+            e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream_dt, msg);
+        });
+        const float R0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0, 0, 0};
+        const double tr1 = now_s();
+        const int rc_icp = run_icp(h, R0, t0, h->p.icp_max_iter, h->p.mse_threshold / 10000, &h->icp0, std::max(1, h->sm_count - 1));
+        if (trace) fprintf(stderr, "[dt trace] overlapped ICP (upload + kd-tree + kernel) %.3f ms\n", 1e3 * (now_s() - tr1));
+        worker.join();
+        if (rc_icp) return rc_icp;
+        h->icp0_valid = true;
+    } else {
+        e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
+    }
+    if (e != cudaSuccess) { h->icp0_valid = false; return fail(h, GOICP_ERR_CUDA, "dt_build_device: " + msg + ": " + cudaGetErrorString(e)); }
     h->dt_size = S; h->have_dt = true;
+    if (trace) fprintf(stderr, "[dt trace] goicp_build_dt total %.3f ms\n", 1e3 * (now_s() - tr0));
     return GOICP_OK;
 }
 
@@ -902,7 +974,9 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     {
         float R_icp[9], t_icp[3], error;
         std::memcpy(R_icp, optR, sizeof optR); std::memcpy(t_icp, optT, sizeof optT);
-        rc = icp_then_dt(h, c, R_icp, t_icp, &error); if (rc) return rc;
+        // goicp_build_dt may already have run exactly this refinement next to the DT build (one use only)
+        const bool pre = h->icp0_valid; h->icp0_valid = false;
+        rc = icp_then_dt(h, c, R_icp, t_icp, &error, pre ? &h->icp0 : nullptr); if (rc) return rc;
         res.icp_calls++;
         if (error < E) { E = error; std::memcpy(optR, R_icp, sizeof optR); std::memcpy(optT, t_icp, sizeof optT); }
     }
@@ -964,6 +1038,20 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                     slots.push_back(Slot{ci, j, pass});
                 }
             }
+        }
+        // Launch order = longest expected first.  Clusters are dispatched in task order and a round lasts until its
+        // last task retires; an inner BnB of a child costs about what the same pass cost on its parent (same
+        // neighbourhood of rotation space, half the uncertainty radius), so sorting by the parent's pop counts keeps
+        // the long searches out of the tail.  Results are per task, so the order changes no value; every rank
+        // derives the same permutation from replicated data.
+        {
+            std::vector<int> ord(n);
+            for (int t = 0; t < n; t++) ord[t] = t;
+            auto cost = [&](int t) { const RotNode& P = cubes[slots[t].cube]; return slots[t].pass == 0 ? P.pops_ub : P.pops_lb; };
+            std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return cost(x) > cost(y); });
+            std::vector<InnerTask> tk(n); std::vector<Slot> sl(n);
+            for (int t = 0; t < n; t++) { tk[t] = h->h_tasks[ord[t]]; sl[t] = slots[ord[t]]; }
+            std::memcpy(h->h_tasks, tk.data(), sizeof(InnerTask) * n); slots.swap(sl);
         }
         std::vector<std::shared_ptr<CandList>> lists;
         rcl = run_inner_batch(h, c, n, &res.bound_evals_executed, &lists); if (rcl) return rcl;
@@ -1055,7 +1143,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 const float lb = ce.lb.value;                                              // :551
                 res.trans_pops += ce.lb.pops; res.bound_evals += ce.lb.evals;
                 if (lb >= E) continue;                                                    // :554
-                nd.ub = ub; nd.lb = lb;
+                nd.ub = ub; nd.lb = lb; nd.pops_ub = ce.ub.pops; nd.pops_lb = ce.lb.pops;
                 heap.push_back(nd); std::push_heap(heap.begin(), heap.end(), lower);      // :560-562
             }
             if (!restart) break;

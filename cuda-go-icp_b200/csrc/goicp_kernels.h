@@ -29,6 +29,7 @@ struct KdView {
     const int32_t* __restrict__ vind;
     const float4* __restrict__ pts_leaf;   // model points permuted into leaf order: x,y,z,(original index as int bits)
     const float* __restrict__ model;       // original xyz triples
+    const float4* __restrict__ boxes;      // 2 per node: tight box of the subtree's points {lo xyz, 0}, {hi xyz, 0}; may be null
     int nm;
     float bb_lo[3], bb_hi[3];
 };

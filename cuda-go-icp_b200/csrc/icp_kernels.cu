@@ -21,12 +21,33 @@ constexpr int kKdStack = 64;
 // is unrolled onto an explicit stack; leaves are scanned in ascending vind order and a point is
 // accepted only if strictly closer than the incumbent, so the first-visited of several
 // exactly-equidistant model points wins, as in the reference (nanoflann_goicp.hpp:95-116,1143-1150).
+//
+// Subtree skipping.  The reference prunes with slab distances only (divlow/divhigh along the split
+// axes of the path), so a query at distance r from the surface walks every cell under the ball's
+// shadow -- O(r^2 * density) leaves, none of which can hold a closer point.  Each node also carries
+// the tight box of its points (kdtree_host.cpp); a subtree whose box is farther than the incumbent
+// (with a 1e-5 relative margin, two orders above the float rounding of either side) cannot change
+// (worst, best): every `dist < worst` test below it fails and the reference restores its per-axis
+// offsets on the way out.  Skipping it leaves the traversal's state -- hence the returned index,
+// ties included -- exactly the reference's.
+//
+// `cap` (optional, FLT_MAX = none) is any known upper bound of the nearest distance -- the distance to
+// some model point, e.g. the previous iteration's correspondent.  Subtrees whose box is farther than
+// min(worst, cap) are skipped as well.  That no longer mirrors the reference's intermediate `worst`
+// (ours stays >= its value at every point of the common depth-first order, so we prune a subset of
+// what it prunes by the slab test), but the RESULT is the same: both traversals end at the smallest
+// float distance d*, no skipped subtree holds a point at d* (all of its points are > cap >= d*), the
+// extra subtrees we enter hold only points the reference had already beaten, and a point replaces the
+// incumbent only if strictly closer -- so both return the first point at d* in that common order.
+// (Only a query whose runner-up is within float rounding, 6e-7 relative, of d* AND whose offset to
+// the winner is parallel to the cut axes could make the reference's rounded slab bound skip the
+// winner itself; the caller's margin for treating a result as a tie is above that.)
 // ------------------------------------------------------------------------------------------
 struct KdFrame { int32_t other; float m2; int32_t idx; float cut; float dst; int32_t state; };
 
 __device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
 
-__device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, float qx, float qy, float qz, float& d2_out)
+__device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, float qx, float qy, float qz, float cap, float& d2_out)
 {
     float worst = 3.402823466e+38f;     // KNNResultSet::init (nanoflann_goicp.hpp:79)
     int best = 0;
@@ -54,6 +75,13 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
                 const uint4 a = reinterpret_cast<const uint4*>(nodes + cur)[0], b = reinterpret_cast<const uint4*>(nodes + cur)[1];
                 nd.child1 = (int)a.x; nd.child2 = (int)a.y; nd.left = (int)a.z; nd.right = (int)a.w;
                 nd.divfeat = (int)b.x; nd.divlow = __uint_as_float(b.y); nd.divhigh = __uint_as_float(b.z); nd.pad = 0;
+            }
+            if (kd.boxes != nullptr && (worst < 3.0e+38f || cap < 3.0e+38f)) {
+                const float4 lo = __ldg(kd.boxes + 2 * (size_t)cur), hi = __ldg(kd.boxes + 2 * (size_t)cur + 1);
+                const float bx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+                const float by = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+                const float bz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+                if (bx * bx + by * by + bz * bz > fminf(worst, cap) * 1.00001f) break;      // nothing below can be the answer
             }
             if (nd.child1 < 0 && nd.child2 < 0) {
                 const float worst_at_entry = worst;          // cached once per leaf (:1143)
@@ -101,74 +129,12 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
     return best;
 }
 
-// ------------------------------------------------------------------------------------------
-// Warm-started exact nearest neighbour for ICP iterations >= 1: the previous iteration's
-// correspondent of the query bounds the search radius, so the descent prunes almost everything.
-// Any exact search returns the reference's index unless two model points are (nearly) equally
-// close, so the search also tracks the second-smallest distance within a 2e-5 relative margin
-// and the caller re-runs near-ties through the reference-ordered traversal (kd_nearest).
-// Far-side bound of a split = squared distance to the far child's slab along the split axis
-// (divlow / divhigh are the extreme coordinates of the two children, nanoflann_goicp.hpp:1013-1045).
-// Returns -1 if the explicit stack overflowed (caller falls back to kd_nearest).
-// ------------------------------------------------------------------------------------------
-constexpr int kSeedStack = 40;
-__device__ int kd_seeded(const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, const float* __restrict__ model,
-                         float qx, float qy, float qz, int seed, float& d1_out, float& d2_out)
-{
-    float d1, d2 = 3.402823466e+38f; int i1 = seed;
-    {
-        const float e0 = qx - __ldg(model + 3 * seed), e1 = qy - __ldg(model + 3 * seed + 1), e2 = qz - __ldg(model + 3 * seed + 2);
-        d1 = e0 * e0 + e1 * e1 + e2 * e2;
-    }
-    int st_node[kSeedStack]; float st_bound[kSeedStack];
-    int sp = 0, cur = 0;
-    float cur_bound = 0.0f;
-    for (;;) {
-        for (;;) {
-            const uint4 a = reinterpret_cast<const uint4*>(nodes + cur)[0];
-            if ((int)a.x < 0 && (int)a.y < 0) {
-                for (int i = (int)a.z; i < (int)a.w; i++) {
-                    const float4 p = leaf[i];
-                    const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
-                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;     // kdtree_distance (jly_icp3d.hpp:48-54)
-                    const int id = __float_as_int(p.w);
-                    if (id == i1) continue;
-                    if (dist < d1) { d2 = d1; d1 = dist; i1 = id; }
-                    else if (dist < d2) d2 = dist;
-                }
-                break;
-            }
-            const uint4 b = reinterpret_cast<const uint4*>(nodes + cur)[1];
-            const int idx = (int)b.x;
-            const float divlow = __uint_as_float(b.y), divhigh = __uint_as_float(b.z);
-            const float val = sel3(qx, qy, qz, idx);
-            int bestc, otherc; float cut;
-            if (((val - divlow) + (val - divhigh)) < 0) { bestc = (int)a.x; otherc = (int)a.y; cut = (val - divhigh) * (val - divhigh); }
-            else                                        { bestc = (int)a.y; otherc = (int)a.x; cut = (val - divlow) * (val - divlow); }
-            const float fb = fmaxf(cur_bound, cut);
-            if (fb <= d1 * 1.00002f) {
-                if (sp == kSeedStack) return -1;
-                st_node[sp] = otherc; st_bound[sp] = fb; sp++;
-            }
-            cur = bestc;
-        }
-        bool more = false;
-        while (sp > 0) {
-            sp--;
-            if (st_bound[sp] <= d1 * 1.00002f) { cur = st_node[sp]; cur_bound = st_bound[sp]; more = true; break; }
-        }
-        if (!more) break;
-    }
-    d1_out = d1; d2_out = d2;
-    return i1;
-}
-
 __global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t* __restrict__ idx, float* __restrict__ d2)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float d;
-    idx[i] = kd_nearest(kd, kd.nodes, kd.pts_leaf, q[3 * i], q[3 * i + 1], q[3 * i + 2], d);
+    idx[i] = kd_nearest(kd, kd.nodes, kd.pts_leaf, q[3 * i], q[3 * i + 1], q[3 * i + 2], 3.402823466e+38f, d);
     d2[i] = d;
 }
 
@@ -631,7 +597,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                         D2 = fminf(D2, b);
                     }
                     if (valid) {
-                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1);   // near tie: reference traversal order decides
+                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1, D1);   // near tie: reference traversal order decides
                         wk.nn[i] = I1; wk.d2[i] = D1;
                         wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
                         // correspondence row (model point, query, d^2) in query order
@@ -648,13 +614,15 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
                 const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
                 const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-                float d2; int id = -1;
-                if (iter > 0) {           // warm start from the previous correspondent; near ties go to the reference traversal
-                    float dsecond;
-                    id = kd_seeded(nodes, leaf, kd.model, qx, qy, qz, __ldcg(wk.nn + i), d2, dsecond);
-                    if (id >= 0 && dsecond <= d2 * 1.00001f) id = -1;
+                // reference traversal with subtree skipping, capped by the distance to the point's last correspondent
+                // (any model point bounds the nearest distance from above; a stale or never-written index is just a loose cap)
+                float d2, cap;
+                {
+                    const unsigned seed = (unsigned)__ldcg(wk.nn + i) < (unsigned)kd.nm ? (unsigned)__ldcg(wk.nn + i) : 0u;
+                    const float e0 = qx - __ldg(kd.model + 3 * seed), e1 = qy - __ldg(kd.model + 3 * seed + 1), e2 = qz - __ldg(kd.model + 3 * seed + 2);
+                    cap = e0 * e0 + e1 * e1 + e2 * e2;
                 }
-                if (id < 0) id = kd_nearest(kd, nodes, leaf, qx, qy, qz, d2);
+                const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, cap, d2);
                 wk.nn[i] = id; wk.d2[i] = d2;
                 wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
                 float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;

@@ -51,6 +51,10 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
 {
     const int id = (int)nodes.size();
     nodes.push_back(KdNode{});
+    boxes.resize(boxes.size() + 8, 0.0f);
+    // on return lo/hi hold the tight box of the points below this node (the reference tightens them the same
+    // way, :939-946,:965-968); the device search uses it to skip subtrees that cannot hold a closer point
+    auto keep_box = [&]() { for (int a = 0; a < 3; ++a) { boxes[8 * (size_t)id + a] = lo[a]; boxes[8 * (size_t)id + 4 + a] = hi[a]; } };
     if (right - left <= leaf_max) {                                  // leaf (:932-947)
         KdNode& n = nodes[id];
         n.child1 = n.child2 = -1; n.left = left; n.right = right; n.divfeat = 0; n.divlow = n.divhigh = 0.0f; n.pad = 0;
@@ -61,6 +65,7 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
                 if (lo[a] > v) lo[a] = v;
                 if (hi[a] < v) hi[a] = v;
             }
+        keep_box();
         return id;
     }
     // ---- split selection (middleSplit_, :1033-1072) ----
@@ -95,6 +100,7 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
     n.child1 = c1; n.child2 = c2; n.left = n.right = 0; n.divfeat = axis; n.pad = 0;
     n.divlow = lhi[axis]; n.divhigh = rlo[axis];                     // tightened child boxes (:962-963)
     for (int a = 0; a < 3; ++a) { lo[a] = std::min(llo[a], rlo[a]); hi[a] = std::max(lhi[a], rhi[a]); }
+    keep_box();
     return id;
 }
 
@@ -102,6 +108,7 @@ void HostKdTree::build(const float* xyz, int n, int leaf_max)
 {
     pts_ = xyz;
     nodes.clear();
+    boxes.clear();
     vind.resize(n);
     for (int i = 0; i < n; ++i) vind[i] = i;
     for (int a = 0; a < 3; ++a) bb_lo[a] = bb_hi[a] = xyz[a];        // computeBoundingBox (:895-917)

@@ -123,7 +123,10 @@ const char* goicp_last_error(const goicp_handle* h);
 int goicp_set_model(goicp_handle* h, const float* xyz, int n);
 int goicp_set_data(goicp_handle* h, const float* xyz, int n);
 
-/* GoICP::BuildDT (jly_goicp.cpp:75-90) on the GPU. */
+/* GoICP::BuildDT (jly_goicp.cpp:75-90) on the GPU.  When the data cloud is already set (the order of main.cpp:47-57)
+ * the ICP from the identity pose that GoICP::Register begins with (jly_goicp.cpp:378-391; it reads no DT) runs on the
+ * SMs the single-CTA DT propagation leaves idle; the first goicp_register after this call picks its result up.  Setting
+ * either cloud again discards it.  GOICP_NO_PREFETCH=1 in the environment turns the overlap off. */
 int goicp_build_dt(goicp_handle* h);
 /* Install / read back a distance grid ([z][y][x] floats + {xMin,yMin,zMin,scale}); lets a caller
  * cache the model-only precompute across runs (the reference cannot). */

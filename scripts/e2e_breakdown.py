@@ -6,7 +6,7 @@ pkg = importlib.import_module("cuda-go-icp_b200")
 G = os.path.join(ROOT, "tests", "golden")
 model = np.fromfile(os.path.join(G, "bunny_model_s0.1_seed1234.f32"), np.float32).reshape(-1, 3)
 data = np.fromfile(os.path.join(G, "bunny_data_s0.1_seed1235.f32"), np.float32).reshape(-1, 3)
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', '3'))):
     t0 = time.perf_counter()
     g = pkg.GoICP(1e-3); g.pModel, g.pData = model, data
     g._handle(); t1 = time.perf_counter()

@@ -5,6 +5,11 @@ after --budget seconds); prints one JSON line per case with executed bound evalu
 DT look-ups per second and the L1TEX-sector roofline fraction.
 
     python scripts/sweep.py --cases 1000:100000:300 10000:100000:300 100000:1000000:512 --budget 10
+
+Multi-GPU: launch under torchrun (one rank per GPU); every rank builds the same clouds and DT, the
+rotation frontier of each registration is sharded across the ranks (ncclAllGather per round, see
+DESIGN.md section 7) and rank 0 prints.  The time box is off in that mode (a cancel that reaches the
+ranks in different rounds would leave a collective unmatched) -- wrap the run in `timeout` instead.
 """
 import argparse, importlib, json, os, sys, threading, time
 import numpy as np
@@ -43,17 +48,37 @@ def main():
     ap.add_argument("--mse", type=float, default=1e-4)
     ap.add_argument("--dt-mode", type=int, default=1, help="0 reference-exact propagation, 1 exact EDT (default for the sweep)")
     args = ap.parse_args()
+    # goicp_build_dt would run Register's first ICP next to the DT build (include/goicp_b200.h); the sweep reports the
+    # registration by itself, so that overlap is off here and `seconds` holds every ICP call
+    os.environ["GOICP_NO_PREFETCH"] = "1"
     pkg = importlib.import_module("cuda-go-icp_b200")
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    nccl_id = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)                      # plumbing only: the 128-byte ncclUniqueId
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
     for case in args.cases:
         nd, nm, S = (int(v) for v in case.split(":"))
         model, data, Rgt, tgt = synth(nm, nd)
-        g = pkg.GoICP(args.mse)
+        g = pkg.GoICP(args.mse, device=local_rank)
         g.pModel, g.pData = model, data
         g.dt.SIZE = S
         g.dt_mode = args.dt_mode
+        if world > 1:
+            g.init_nccl(nccl_id, rank, world)
         t0 = time.perf_counter(); g.BuildDT(); dt_s = time.perf_counter() - t0
         timer = threading.Timer(args.budget, g.Cancel)
-        timer.start()
+        if world > 1:
+            dist.barrier()
+        else:
+            timer.start()
         t0 = time.perf_counter()
         try:
             g.Register()
@@ -66,14 +91,23 @@ def main():
         timer.cancel()
         ang = float(np.linalg.norm(res["R"] - Rgt) / np.sqrt(2))
         lookups = res["bound_evals_executed"] * nd
-        out = {"case": case, "Nd": nd, "Nm": nm, "S": S, "dt_mode": args.dt_mode, "dt_build_s": dt_s, "seconds": el, "exit_path": res["exit_path"],
+        if world > 1:
+            tt = torch.tensor([el], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            el = float(tt.item())
+        out = {"case": case, "n_gpus": world, "Nd": nd, "Nm": nm, "S": S, "dt_mode": args.dt_mode, "bound_evals_committed": res["bound_evals"],
+               "rot_pops": res["rot_pops"], "icp_calls": res.get("icp_calls"), "dt_build_s": dt_s, "seconds": el, "exit_path": res["exit_path"],
                "sse": res["sse"], "sse_thresh": res["sse_thresh"], "rot_err_rad_vs_truth": ang, "t_err_vs_truth": float(np.abs(res["t"] - tgt).max()),
                "bound_evals_executed": res["bound_evals_executed"], "bound_evals_per_s": res["bound_evals_executed"] / el,
                "dt_lookups_per_s": lookups / el, "bnb_kernel_s": res["seconds_bnb_kernels"], "icp_s": res["seconds_icp"], "rounds": res["rounds"],
                "lookups_per_s_in_bnb_kernels": lookups / max(res["seconds_bnb_kernels"], 1e-9),
-               "l1tex_sector_roofline_frac": lookups / max(res["seconds_bnb_kernels"], 1e-9) / (148 * 1.965e9)}
-        print(json.dumps(out), flush=True)
+               "l1tex_sector_roofline_frac": lookups / max(res["seconds_bnb_kernels"], 1e-9) / (148 * 1.965e9 * world)}
+        if rank == 0:
+            print(json.dumps(out), flush=True)
         g.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -105,6 +105,59 @@ def test_nn_indices_bit_exact(pkg, small, bunny):
     g.close()
 
 
+def _bumpy_surface(n, seed):
+    rng = np.random.default_rng(seed)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    k = rng.normal(size=(4, 3)); ph = rng.uniform(0, 2 * np.pi, 4)
+    r = 0.33 + sum(0.04 * np.sin(3 * (u @ kk) + p) for kk, p in zip(k, ph))
+    return (u * r[:, None]).astype(np.float32)
+
+
+def test_nn_far_queries_large_model_vs_oracle(pkg, restated):
+    """kd-tree search with subtree skipping (tight boxes) against the oracle's plain reference traversal:
+    a model large enough for the tree path (60k surface points + a lattice block with duplicated points),
+    queries far from the surface (where the reference walks thousands of leaves), near it, on model points,
+    and at half-integer lattice positions (exact ties: the traversal ORDER decides the index)."""
+    rng = np.random.default_rng(11)
+    surf = _bumpy_surface(60000, 5)
+    ax = np.arange(8, dtype=np.float32) * 0.0625 + 0.55
+    lat = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+    model = np.concatenate([surf, lat, lat[::3]]).astype(np.float32)
+    q = np.concatenate([rng.uniform(-1.2, 1.2, (6000, 3)),                                   # far
+                        surf[rng.choice(len(surf), 4000)] + rng.normal(scale=2e-3, size=(4000, 3)),  # near
+                        model[rng.choice(len(model), 1000)],                                 # on model points (d = 0, duplicates)
+                        lat[rng.choice(len(lat), 1000)] + np.float32(0.03125),               # cell centres: 8-way exact ties
+                        np.zeros((1, 3))]).astype(np.float32)                                 # centre of the surface: near-ties all around
+    kd = restated.kd_build(model)
+    ref_idx, ref_d2 = restated.kd_nn(kd, q)
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = model, q
+    idx, d2 = g.NN(q)
+    g.close()
+    assert np.array_equal(d2.view(np.uint32), ref_d2.view(np.uint32))
+    assert np.array_equal(idx, ref_idx)
+
+
+def test_icp_large_model_tree_path_vs_oracle(pkg, restated):
+    """ICP3D::Run through the tree-search branch of the ICP kernel (model > 16384 points) from a pose
+    40 mrad / 0.05 off: every iteration's correspondences, sort and sequential sums follow the oracle,
+    so R, t and the error agree bit for bit."""
+    model = _bumpy_surface(50000, 7)
+    rng = np.random.default_rng(3)
+    data = (model[rng.choice(len(model), 6000, replace=False)] + rng.normal(scale=1e-3, size=(6000, 3))).astype(np.float32)
+    a = 0.04
+    R0 = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    t0 = np.array([0.05, -0.03, 0.02], np.float32)
+    kd = restated.kd_build(model)
+    e_ref, R_ref, t_ref, it_ref, _ = restated.icp_run(kd, data, R0, t0, 10000, 1e-7)
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = model, data
+    err, R, t, iters = g.ICP(R0, t0, 10000, 1e-7)
+    g.close()
+    assert np.array_equal(R, R_ref) and np.array_equal(t, t_ref)
+    assert np.float32(err) == np.float32(e_ref)
+
+
 @pytest.mark.parametrize("sort", ["count", "radix"])
 def test_icp_matches_reference(pkg, small, bunny, sort, monkeypatch):
     # both sorts of the ICP kernel (rank by counting / grid-wide stable radix sort) on the same input
@@ -205,6 +258,33 @@ def test_register_bunny_full_size_reference_dt_on_gpu(pkg, runs, bunny, restated
         _check_run(g2.result, gold)
         g2.close()
     g.close()
+
+
+def test_icp_overlapped_with_dt_build_changes_nothing(pkg, bunny, monkeypatch):
+    """goicp_build_dt runs Register's first ICP (from the identity, no DT needed) next to the DT build; the
+    registration that follows must be the one obtained without the overlap, field for field -- and a second
+    Register on the same handle (which has to run that ICP itself) as well."""
+    def run(no_prefetch):
+        if no_prefetch:
+            monkeypatch.setenv("GOICP_NO_PREFETCH", "1")
+        else:
+            monkeypatch.delenv("GOICP_NO_PREFETCH", raising=False)
+        g = pkg.GoICP(1e-3)
+        g.pModel, g.pData = bunny["model_s"], bunny["data_s"]
+        g.dt.SIZE = 100
+        g.BuildDT()
+        g.Register(); a = dict(g.result)
+        g.Register(); b = dict(g.result)
+        grid, meta = g.GetDT()
+        g.close()
+        return a, b, grid, meta
+    a0, b0, grid0, meta0 = run(True)
+    a1, b1, grid1, meta1 = run(False)
+    assert np.array_equal(grid0, grid1) and np.array_equal(meta0, meta1)
+    for x in (a1, b1, b0):
+        for k in ("sse", "rot_pops", "trans_pops", "bound_evals", "icp_calls", "exit_path"):
+            assert x[k] == a0[k], k
+        assert np.array_equal(x["R"], a0["R"]) and np.array_equal(x["t"], a0["t"])
 
 
 def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
