@@ -52,8 +52,8 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1b_ncu_full_selected.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.5e6}
+# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1d_ncu_full_selected.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.3e6}
 
 
 def load(name):
@@ -338,7 +338,7 @@ def main():
     # catches the GPU re-ramping its clocks after the idle gap (all samples are reported)
     e2e_med = float(np.median(e2e_s))
     e2e = {"value": e2e_evals / e2e_med, "unit": "bound-evals/s",
-           "h2d_bytes_per_step": int(model.nbytes + data.nbytes + 16 * len(data) + 44 * len(model)),
+           "h2d_bytes_per_step": int(model.nbytes + data.nbytes + 16 * len(data) + 56 * len(model)),
            "d2h_bytes_per_step": int(res["rounds"] * 48 * 288 + 256),
            "seconds_per_step": e2e_med, "seconds_per_step_samples": [round(x, 4) for x in e2e_s], "statistic": "median",
            "seconds_create_h2d_dt_build": float(np.median([p[0] for p in e2e_parts])),
@@ -365,17 +365,25 @@ def main():
     lookups = executed * len(data)
     achieved = lookups * 32 / kern_s / 1e9
     roofline = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1b_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1d_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
                 "algorithmic_bytes_per_launch": lookups * 32 / max(1, sum(r["rounds"] for r in results)), "peak_source": peak_src,
                 "basis": "32 B sector per DT lookup (SURVEY 8d); lookups = executed bound evals * Nd; 300^3 fp32 DT (108 MB) is L2-resident",
                 "launches": int(sum(r["rounds"] for r in results)), "avg_launch_ms": 1e3 * kern_s / max(1, sum(r["rounds"] for r in results)),
                 "gather": gather}
 
+    # the reference-order DT propagation (87 % of an end-to-end pass): 4 sweeps read and write every 8-byte working voxel,
+    # the two sweeps that look at the adjacent slice read it once more
+    S = wl["S"]
+    dt_bytes = (4 * 2 + 2) * 8.0 * S ** 3
+    dt_kernel = {"kernel": "dt_propagate_split_kernel", "seconds_build_dt_call": e2e["seconds_create_h2d_dt_build"],
+                 "algorithmic_bytes": dt_bytes, "achieved": dt_bytes / e2e["seconds_create_h2d_dt_build"] / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": dt_bytes / e2e["seconds_create_h2d_dt_build"] / 1e9 / peak,
+                 "bound": "latency: 4*S^2 row steps, each after the previous one, on ONE CTA (DESIGN.md section 5); not a bandwidth kernel"}
     out = {"metric": "goicp_bound_evals_per_sec", "value": value, "unit": "bound-evals/s", "n_gpus": world, "steps": args.steps,
            "warmup": max(3, args.warmup), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
            "data": "reference bunny scans, deterministic subsample (committed fixtures tests/golden/*.f32)",
-           "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+           "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "dt_kernel": dt_kernel,
            "time_to_optimum_s": total_s / args.steps, "exit_path": res["exit_path"], "sse": res["sse"],
            "bound_evals_per_step": evals // args.steps, "bound_evals_executed_per_step": executed // args.steps,
            "rot_pops": res["rot_pops"], "trans_pops": res["trans_pops"], "rounds_per_step": res["rounds"],
