@@ -64,6 +64,14 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)                      # plumbing only: the 128-byte ncclUniqueId
         nccl_id = bytes(idt.cpu().numpy().tobytes())
+    if world > 1:                                   # first collective of a communicator sets up its connections (~1 s): not a case's time
+        m0, d0, _, _ = synth(20000, 500)
+        g = pkg.GoICP(1e-3, device=local_rank)
+        g.pModel, g.pData = m0, d0
+        g.dt.SIZE = 64
+        g.dt_mode = 1
+        g.init_nccl(nccl_id, rank, world)
+        g.BuildDT(); g.Register(); g.close()
     for case in args.cases:
         nd, nm, S = (int(v) for v in case.split(":"))
         model, data, Rgt, tgt = synth(nm, nd)
