@@ -19,7 +19,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoicp_b200.so")
+LIB_PATH = os.environ.get("GOICP_LIB_PATH") or os.path.join(_HERE, "libgoicp_b200.so")    # override: instrumented builds (profiling only)
 
 EXIT_PATHS = {0: "none", 1: "certified", 2: "early_sse_below_thresh", 3: "queue_empty", 4: "cancelled"}
 

@@ -128,7 +128,7 @@ enum ScanKind { F1 = 0, F3 = 1, B1 = 2, B3 = 3, C_UP = 4, C_DN = 5 };
 extern __shared__ __align__(16) unsigned char dt_smem[];
 
 #ifdef GOICP_DT_INSTRUMENT
-__device__ unsigned long long g_dt_stats_buf[8];
+__device__ unsigned long long g_dt_stats_buf[16];
 #define DT_STAT(i, v) atomicAdd(&g_dt_stats_buf[i], (unsigned long long)(v))
 #else
 #define DT_STAT(i, v) ((void)0)
@@ -436,9 +436,12 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
     // inputs of the coming step, loaded right after the barrier that publishes them
     V2 pL = v2_unset(), pC = pL, pR = pL;
     V2 self = sh.selfv(0)[ln.zc], p9 = sh.p9(0)[ln.zc];
+#ifdef GOICP_DT_INSTRUMENT
+    long long a_work = 0, a_bar = 0, a_post = 0, a_rows = 0, a_settled = 0; long long c_prev = clock64();
+#endif
     for (int s = 0; s < S; s++) {
 #ifdef GOICP_DT_INSTRUMENT
-        const long long c_w0 = clock64();
+        const long long c_w0 = clock64(); a_post += c_w0 - c_prev;
 #endif
         V2 own1, st1w, fin_w; int T1, bad;
         row_recurrence<K1, K2>(ln, pL, pC, pR, p9, self, own1, T1, st1w, fin_w, bad);
@@ -448,7 +451,7 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_w1 = clock64();
         bar_all();
-        if (threadIdx.x == 0) { DT_STAT(6, c_w1 - c_w0); DT_STAT(7, clock64() - c_w1); }
+        c_prev = clock64(); a_work += c_w1 - c_w0; a_bar += c_prev - c_w1;
 #else
         bar_all();
 #endif
@@ -457,7 +460,9 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
         self = sh.selfv((s + 1) & (kRing - 1))[ln.zc];
         p9 = sh.p9((s + 1) & 1)[ln.zc];
         const int which = (flag1 == serial + s ? 1 : 0) | (flag2 == serial + s ? 2 : 0);
-        DT_STAT(4, threadIdx.x == 0); DT_STAT(5, threadIdx.x == 0 && which);
+#ifdef GOICP_DT_INSTRUMENT
+        a_rows++; a_settled += which ? 1 : 0;
+#endif
         if (which) {                                 // a run crossed a warp boundary: settle the boundaries among the consumers
             const V2 fin = settle_row<DIR1>(sh.xchg(), ln, which, own1, T1, st1w, fin_w, ncons_threads);
             if (ln.owned) cur[z + 2] = fin;
@@ -465,6 +470,9 @@ __device__ __forceinline__ void consumer_pass(int S, const SplitSmem& sh, const 
             pL = cur[ln.zc - 1]; pC = cur[ln.zc]; pR = cur[ln.zc + 1];
         }
     }
+#ifdef GOICP_DT_INSTRUMENT
+    if (threadIdx.x == 0) { DT_STAT(4, a_rows); DT_STAT(5, a_settled); DT_STAT(6, a_work); DT_STAT(7, a_bar); DT_STAT(8, a_post); }
+#endif
     bar_all(); bar_all();                                    // steps S, S+1: the producers store the last rows
 }
 
@@ -482,6 +490,9 @@ __device__ __forceinline__ void producer_pass(V2* G, int S, int x, int xs, const
         if (HAS_XS && !use_xs && z < S) { sh.p9(0)[z + 2] = v2_unset(); sh.p9(1)[z + 2] = v2_unset(); }   // no adjacent slice: nothing to fold
     }
     bar_all();
+#ifdef GOICP_DT_INSTRUMENT
+    long long b_work = 0, b_bar = 0;
+#endif
     for (int s = -2; s < S + 2; s++) {
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_p0 = clock64();
@@ -512,11 +523,14 @@ __device__ __forceinline__ void producer_pass(V2* G, int S, int x, int xs, const
 #ifdef GOICP_DT_INSTRUMENT
         const long long c_p1 = clock64();
         bar_all();
-        if (ptid == 0 && s >= 0 && s < S) { DT_STAT(2, c_p1 - c_p0); DT_STAT(3, clock64() - c_p1); }
+        if (s >= 0 && s < S) { b_work += c_p1 - c_p0; b_bar += clock64() - c_p1; }
 #else
         bar_all();
 #endif
     }
+#ifdef GOICP_DT_INSTRUMENT
+    if (ptid == 0) { DT_STAT(2, b_work); DT_STAT(3, b_bar); }
+#endif
 }
 
 template <int K1, int YDIR>
@@ -556,14 +570,29 @@ __device__ __forceinline__ void copy_pass(const V2* G, int S, int x, int xs, con
     }
     __syncwarp();
     bar_all();
+#ifdef GOICP_DT_INSTRUMENT
+    long long k_work = 0, k_bar = 0;
+#endif
     for (int s = -2; s < S + 2; s++) {
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_k0 = clock64();
+#endif
         if (lead) {
             issue_self(s - 1 + R); issue_x(s + 1 + R);
             wait_self(s + 1); wait_x(s + 3);
         }
         __syncwarp();
+#ifdef GOICP_DT_INSTRUMENT
+        const long long c_k1 = clock64();
         bar_all();
+        if (s >= 0 && s < S) { k_work += c_k1 - c_k0; k_bar += clock64() - c_k1; }
+#else
+        bar_all();
+#endif
     }
+#ifdef GOICP_DT_INSTRUMENT
+    if (lead) { DT_STAT(9, k_work); DT_STAT(10, k_bar); }
+#endif
 }
 
 template <int VPT, int MAXT>
@@ -751,10 +780,10 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         }
 #ifdef GOICP_DT_INSTRUMENT
         {
-            unsigned long long hs[8];
+            unsigned long long hs[16];
             DT_TRY(cudaStreamSynchronize(stream));
             DT_TRY(cudaMemcpyFromSymbol(hs, g_dt_stats_buf, sizeof hs));
-            fprintf(stderr, "[dt stats] rows %llu, settled across warps %llu; per row: consumer work %.0f wait %.0f, producer work %.0f wait %.0f cycles\n", hs[4], hs[5], (double)hs[6] / hs[4], (double)hs[7] / hs[4], (double)hs[2] / hs[4], (double)hs[3] / hs[4]);
+            fprintf(stderr, "[dt stats] rows %llu, settled across warps %llu; per row: consumer work %.0f barrier %.0f post-barrier %.0f | producer work %.0f barrier %.0f | copy lane issue+wait %.0f barrier %.0f cycles\n", hs[4], hs[5], (double)hs[6] / hs[4], (double)hs[7] / hs[4], (double)hs[8] / hs[4], (double)hs[2] / hs[4], (double)hs[3] / hs[4], (double)hs[9] / hs[4], (double)hs[10] / hs[4]);
         }
 #endif
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);

@@ -176,7 +176,7 @@ struct goicp_handle {
     DevBuf<CandList> d_cands; DevBuf<unsigned long long> d_dbg; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
     int64_t strict_resolves = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
-    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
+    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_pos, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
     InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
 
@@ -192,7 +192,7 @@ struct goicp_handle {
     NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather;      // native exchange: all-gather of the round's result records on the stream
 
     // timing
-    double t_kernels = 0, t_icp = 0;
+    double t_kernels = 0, t_icp = 0, t_score = 0, t_strict = 0, t_setup = 0;     // t_score.. only for GOICP_ROUND_STATS
     // ICP from the identity pose, run by goicp_build_dt next to the distance-transform build (it needs no DT) and
     // consumed by the first goicp_register after it
     cudaStream_t stream_dt = nullptr; bool icp0_valid = false; goicp_icp_result icp0;
@@ -507,6 +507,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
 // (strict_sum.cuh).  `list` are the contenders the search kernel reported for that task.
 int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, const CandList& list, float* value, float* node4)
 {
+    struct Acc { double& a; double t0; ~Acc() { a += now_s() - t0; } } acc{h->t_strict, now_s()};
     const size_t scratch = (size_t)h->nd * sizeof(float) <= (size_t)(h->max_smem_optin - 2048) ? 0 : (size_t)kMaxCand * h->nd;
     CUDA_TRY(h, h->d_strict.reserve(256 + scratch));
     CUDA_TRY(h, h->d_tasks.reserve(1)); CUDA_TRY(h, h->d_cands.reserve(1));
@@ -525,6 +526,8 @@ int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, co
 
 int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* t, float* out)
 {
+    const double t_begin = now_s();
+    struct Acc { double& a; double t0; ~Acc() { a += now_s() - t0; } } acc{h->t_score, t_begin};
     float Rt[12]; int use = R ? 1 : 0;
     for (int i = 0; i < 9; i++) Rt[i] = R ? R[i] : 0.0f;
     for (int i = 0; i < 3; i++) Rt[9 + i] = R ? t[i] : 0.0f;
@@ -547,12 +550,13 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     rc = ensure_kdtree(h); if (rc) return rc;
     const int num = h->p.do_trim ? (int)((float)h->nd * (1 - h->p.trim_fraction)) : h->nd;     // jly_icp3d.hpp:189-196
     size_t npad = 1; while (npad < (size_t)h->nd) npad <<= 1;
-    CUDA_TRY(h, h->d_icp_q.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd));
-    CUDA_TRY(h, h->d_icp_keys.reserve(npad)); CUDA_TRY(h, h->d_icp_stage.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_order.reserve(h->nd));
+    CUDA_TRY(h, h->d_icp_q.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_d2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_nn.reserve(h->nd)); CUDA_TRY(h, h->d_icp_pos.reserve(h->nd));
+    CUDA_TRY(h, h->d_icp_keys.reserve(npad)); CUDA_TRY(h, h->d_icp_stage.reserve((size_t)8 * h->nd)); CUDA_TRY(h, h->d_icp_order.reserve((size_t)h->nd + 2048));     // + slack: doubles as the per-CTA lists of deferred queries
     // radix-sort scratch of the large-cloud path: second key buffer, digit-major histogram (256 x warps of the grid) + 1024 chunk totals
     const size_t hist_n = (size_t)256 * icp_max_blocks_supported() * (icp_threads() / 32);
-    CUDA_TRY(h, h->d_icp_keys2.reserve(h->nd)); CUDA_TRY(h, h->d_icp_hist.reserve(hist_n + 1024));
-    IcpWork wk; wk.keys2 = h->d_icp_keys2.p; wk.hist = h->d_icp_hist.p; wk.blocksum = h->d_icp_hist.p + hist_n; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p; wk.order = h->d_icp_order.p;
+    CUDA_TRY(h, h->d_icp_keys2.reserve((size_t)h->nd + 2048));     // + slack: doubles as the per-CTA lists of unsettled queries
+    CUDA_TRY(h, h->d_icp_hist.reserve(hist_n + 1024));
+    IcpWork wk; wk.keys2 = h->d_icp_keys2.p; wk.hist = h->d_icp_hist.p; wk.blocksum = h->d_icp_hist.p + hist_n; wk.q = h->d_icp_q.p; wk.nn = h->d_icp_nn.p; wk.pos = h->d_icp_pos.p; wk.d2 = h->d_icp_d2.p; wk.keys = h->d_icp_keys.p; wk.stage = h->d_icp_stage.p; wk.order = h->d_icp_order.p;
     IcpState st; std::memset(&st, 0, sizeof st);
     for (int i = 0; i < 9; i++) st.R[i] = R0[i];
     for (int i = 0; i < 3; i++) st.t[i] = t0[i];
@@ -638,7 +642,7 @@ int goicp_destroy(goicp_handle* h)
         h->d_gather.release();
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
-        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
+        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
         if (h->h_results) pool_free_host(h->h_results);
         if (h->h_tasks) pool_free_host(h->h_tasks);
         if (h->stream) cudaStreamSynchronize(h->stream);
@@ -852,7 +856,7 @@ int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float
     CUDA_TRY(h, h->d_f32b.reserve(n));
     CUDA_TRY(h, h->d_i32.reserve((size_t)n + 16));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, launch_nn(kd_view(h), h->d_q.p, n, h->d_i32.p, h->d_f32b.p, h->stream));
+    CUDA_TRY(h, launch_nn(kd_view(h), h->d_q.p, n, h->d_i32.p, h->d_f32b.p, getenv("GOICP_NN_COOP") != nullptr, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(idx_out, h->d_i32.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(d2_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -956,12 +960,13 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
-    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true;
+    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->t_score = h->t_strict = 0;
     const double t_begin = now_s();
     h->initialized = false;
     int rc = initialize(h); if (rc) return rc;
     BnbConst c; rc = make_const(h, c); if (rc) return rc;
     rc = ensure_kdtree(h); if (rc) return rc;
+    h->t_setup = now_s() - t_begin;
 
     goicp_result res; std::memset(&res, 0, sizeof res);
     res.sse_thresh = h->sse_thresh;
@@ -1155,6 +1160,10 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     res.exit_path = exit_path; res.best_lb = exit_lb;
     res.kernel_launches = h->launches;
     res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp;
+    if (getenv("GOICP_ROUND_STATS"))
+        fprintf(stderr, "[register] total %.3f s: setup (upload, gamma table, kd-tree) %.3f, BnB kernels + exchange %.3f, ICP %.3f, DT scoring %.3f, strict resolves %.3f (%lld), rest (host commit, copies) %.3f\n",
+                res.seconds_total, h->t_setup, h->t_kernels, h->t_icp, h->t_score, h->t_strict, (long long)h->strict_resolves,
+                res.seconds_total - h->t_setup - h->t_kernels - h->t_icp - h->t_score - h->t_strict);
     publish(h, res, 1);
     *out = res;
     return exit_path == GOICP_EXIT_CANCELLED ? GOICP_ERR_CANCELLED : GOICP_OK;

@@ -29,7 +29,8 @@ struct KdView {
     const int32_t* __restrict__ vind;
     const float4* __restrict__ pts_leaf;   // model points permuted into leaf order: x,y,z,(original index as int bits)
     const float* __restrict__ model;       // original xyz triples
-    const float4* __restrict__ boxes;      // 2 per node: tight box of the subtree's points {lo xyz, 0}, {hi xyz, 0}; may be null
+    const float4* __restrict__ boxes;      // 2 per node: tight box of the subtree's points {lo xyz, m}, {hi xyz, 0}; interior nodes: m = int bits of
+                                           // the first leaf-order position of child2's points (kdtree_host.cpp); may be null
     int nm;
     float bb_lo[3], bb_hi[3];
 };
@@ -43,6 +44,7 @@ struct IcpState {           // lives in device memory; written by block 0 of the
 struct IcpWork {            // per-iteration device scratch of the ICP kernel
     float* q;               // 8*nd: correspondence rows in query order (model xyz, query xyz, d^2, pad)
     int32_t* nn;            // nd nearest model indices
+    int32_t* pos;           // nd leaf-order positions of those points (seed of the next iteration's search)
     float* d2;              // nd squared distances
     unsigned long long* keys;   // nd sort keys (d2 bits << 32 | point index)
     int32_t* order;         // nd: order[rank] = point index, ranks by key
@@ -51,7 +53,7 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
     unsigned* hist;         // 256 * (warps of the grid): digit-major histogram / scanned bases of the radix sort
     unsigned* blocksum;     // 1024: per-CTA chunk totals of that scan
 };
-cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s);
+cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s);

@@ -43,12 +43,36 @@ constexpr int kKdStack = 64;
 // the winner is parallel to the cut axes could make the reference's rounded slab bound skip the
 // winner itself; the caller's margin for treating a result as a tie is above that.)
 // ------------------------------------------------------------------------------------------
-struct KdFrame { int32_t other; float m2; int32_t idx; float cut; float dst; int32_t state; };
+// One pending far-side branch of the walk, 16 bytes so that a push or a pop is ONE local-memory access: x = far child |
+// split axis << 28 | visited << 30, y/z/w = float bits of its bound, of the axis offset inside it and of the offset to
+// restore afterwards.  (As six scalars a frame cost six scattered 4-byte accesses per lane; with 512 walks per SM the
+// stacks do not fit L1 and that traffic, not the tree, was what the walk waited for.)
+typedef uint4 KdFrame;
+
+// Visit the points [left,right) of a leaf in order.  The loads of five points are issued together: a leaf (<= 10
+// points, jly_icp3d.hpp:151) costs two round trips to L2 instead of one per point -- the compiler does not batch
+// the loads of a loop whose trip count it does not know.
+template <typename F>
+__device__ __forceinline__ void for_leaf_points(const float4* __restrict__ leaf, int left, int right, F f)
+{
+    for (int base = left; base < right; base += 5) {
+        float4 p[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (base + k < right) p[k] = leaf[base + k];
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (base + k < right) f(base + k, p[k]);
+    }
+}
 
 __device__ __forceinline__ float sel3(float a, float b, float c, int i) { return i == 0 ? a : (i == 1 ? b : c); }
 
-__device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, float qx, float qy, float qz, float cap, float& d2_out)
+// `budget` bounds the node visits (<= 0: unlimited): a walk that exceeds it returns -1 and the caller hands the
+// query to the warp-cooperative search below.  pos_out = leaf-order position of the returned point.
+__device__ __forceinline__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, const float4* __restrict__ leaf, float qx, float qy, float qz, float cap,
+                          float& d2_out, int budget = 0, int* pos_out = nullptr)
 {
+    int best_pos = 0;
+    if (budget <= 0) budget = 0x7fffffff;
     float worst = 3.402823466e+38f;     // KNNResultSet::init (nanoflann_goicp.hpp:79)
     int best = 0;
     float ds0 = 0.0f, ds1 = 0.0f, ds2 = 0.0f;
@@ -70,6 +94,7 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
     for (;;) {
         // descend along the preferred children
         for (;;) {
+            if (--budget < 0) return -1;
             KdNode nd;
             {
                 const uint4 a = reinterpret_cast<const uint4*>(nodes + cur)[0], b = reinterpret_cast<const uint4*>(nodes + cur)[1];
@@ -89,7 +114,7 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
                     const float4 p = leaf[i];
                     const float d0 = qx - p.x, d1 = qy - p.y, d2 = qz - p.z;
                     const float dist = d0 * d0 + d1 * d1 + d2 * d2;     // kdtree_distance (jly_icp3d.hpp:48-54)
-                    if (dist < worst_at_entry && worst > dist) { worst = dist; best = __float_as_int(p.w); }
+                    if (dist < worst_at_entry && worst > dist) { worst = dist; best = __float_as_int(p.w); best_pos = i; }
                 }
                 break;
             }
@@ -100,33 +125,160 @@ __device__ int kd_nearest(const KdView& kd, const KdNode* __restrict__ nodes, co
             if ((diff1 + diff2) < 0) { bestc = nd.child1; otherc = nd.child2; cut = (val - nd.divhigh) * (val - nd.divhigh); }
             else                     { bestc = nd.child2; otherc = nd.child1; cut = (val - nd.divlow) * (val - nd.divlow); }
             const float dst = sel3(ds0, ds1, ds2, idx);
-            if (sp < kKdStack) {
-                KdFrame& f = stack[sp++];
-                f.other = otherc; f.m2 = cur_min + cut - dst; f.idx = idx; f.cut = cut; f.dst = dst; f.state = 0;
-            }
+            if (sp < kKdStack)
+                stack[sp++] = make_uint4((unsigned)otherc | ((unsigned)idx << 28), __float_as_uint(cur_min + cut - dst), __float_as_uint(cut), __float_as_uint(dst));
             cur = bestc;
         }
         // unwind
         bool descend = false;
         while (sp > 0) {
-            KdFrame& f = stack[sp - 1];
-            if (f.state == 0) {
-                if (f.m2 * 1.0f <= worst) {       // epsError = 1 (:809, :1178)
-                    f.state = 1;
-                    if (f.idx == 0) ds0 = f.cut; else if (f.idx == 1) ds1 = f.cut; else ds2 = f.cut;
-                    cur = f.other; cur_min = f.m2; descend = true;
+            const KdFrame f = stack[sp - 1];
+            const int fidx = (int)((f.x >> 28) & 3u);
+            if ((f.x >> 30) == 0u) {
+                const float m2 = __uint_as_float(f.y);
+                if (m2 * 1.0f <= worst) {         // epsError = 1 (:809, :1178)
+                    stack[sp - 1].x = f.x | (1u << 30);
+                    const float fcut = __uint_as_float(f.z);
+                    if (fidx == 0) ds0 = fcut; else if (fidx == 1) ds1 = fcut; else ds2 = fcut;
+                    cur = (int)(f.x & 0x0fffffffu); cur_min = m2; descend = true;
                     break;
                 }
                 sp--;
             } else {
-                if (f.idx == 0) ds0 = f.dst; else if (f.idx == 1) ds1 = f.dst; else ds2 = f.dst;
+                const float fdst = __uint_as_float(f.w);
+                if (fidx == 0) ds0 = fdst; else if (fidx == 1) ds1 = fdst; else ds2 = fdst;
                 sp--;
             }
         }
         if (!descend) break;
     }
     d2_out = worst;
+    if (pos_out) *pos_out = best_pos;
     return best;
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative search for the queries whose walk is long (far from the surface: hundreds of
+// dependent node visits).  Same answer as kd_nearest, found differently:
+//  1. the minimum distance D1, its point and the runner-up distance D2 by a breadth-first frontier
+//     expansion -- 32 nodes per round trip to L2 instead of one; a node is dropped when its tight box
+//     is farther than the best distance so far (1e-5 relative margin), so every point within that
+//     margin of D1 is scanned and D2 is exact whenever it matters;
+//  2. D2 > D1 (1 + 1e-5): the point at D1 is what the reference returns -- its walk ends at the smallest
+//     float distance, and its slab bound, a lower bound of every distance below a node up to ~2e-6 of
+//     rounding, cannot have excluded that point against an incumbent >= D2;
+//  3. D1 < D2 <= D1 (1 + 1e-5): replay the reference's slab bound along the winner's root path (the
+//     bound depends on the path only): if every far-side step has bound <= D2 <= the incumbent at that
+//     moment, the reference does reach the winner's leaf, and the strictly smallest distance wins;
+//  4. exact ties (D2 == D1), a failed replay or a frontier that outgrows its queue: returns -1 and the best
+//     bound found in d2_out; the caller runs the reference walk itself (kd_nearest) capped by it.
+// q: this warp's queue in shared memory (kCoopQ ints).  seed_pos: leaf-order position of any model
+// point (an upper bound of D1), or -1.  All lanes return the same values.
+// ------------------------------------------------------------------------------------------
+constexpr int kCoopQ = 384;
+__device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float qx, float qy, float qz, int seed_pos, int lane, float& d2_out, int& pos_out)
+{
+    const unsigned full = 0xffffffffu;
+    const float kInfF = 3.402823466e+38f;
+    const KdNode* __restrict__ nodes = kd.nodes; const float4* __restrict__ leaf = kd.pts_leaf;
+    float bd1 = kInfF, bd2 = kInfF, lim = kInfF; int bpos = -1;
+    if (seed_pos >= 0) {
+        const float4 p = __ldg(leaf + seed_pos);
+        const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
+        lim = e0 * e0 + e1 * e1 + e2 * e2;
+        if (lane == 0) { bd1 = lim; bpos = seed_pos; }
+    }
+    int head = 0, tail = 1, live = 1;                  // ring positions in [0, kCoopQ); live = entries queued
+    if (lane == 0) q[0] = 0;
+    __syncwarp();
+    bool overflow = false;
+    while (live > 0) {
+        const int n = min(32, live);
+        int node = -1;
+        if (lane < n) { int at = head + lane; if (at >= kCoopQ) at -= kCoopQ; node = q[at]; }
+        head += n; if (head >= kCoopQ) head -= kCoopQ;
+        live -= n;
+        int c1 = -1, c2 = -1;
+        if (node >= 0) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + node));
+            const float4 lo = __ldg(kd.boxes + 2 * (size_t)node), hi = __ldg(kd.boxes + 2 * (size_t)node + 1);
+            const float bx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
+            const float by = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
+            const float bz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
+            if (bx * bx + by * by + bz * bz <= lim * 1.00001f) {
+                if ((int)a.x < 0 && (int)a.y < 0) {
+                    for_leaf_points(leaf, (int)a.z, (int)a.w, [&](int i, const float4& p) {
+                        if (i == seed_pos) return;                     // already lane 0's candidate
+                        const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
+                        const float dist = e0 * e0 + e1 * e1 + e2 * e2; // kdtree_distance (jly_icp3d.hpp:48-54)
+                        if (dist < bd1) { bd2 = bd1; bd1 = dist; bpos = i; }
+                        else if (dist < bd2) bd2 = dist;
+                    });
+                } else { c1 = (int)a.x; c2 = (int)a.y; }
+            }
+        }
+        // distances are non-negative floats: their bit patterns order like the values
+        lim = fminf(lim, __uint_as_float(__reduce_min_sync(full, __float_as_uint(bd1))));
+        const unsigned pm = __ballot_sync(full, c1 >= 0);
+        const int total = 2 * __popc(pm);
+        if (live + total > kCoopQ) { overflow = true; break; }
+        if (c1 >= 0) {
+            int at = tail + 2 * __popc(pm & ((1u << lane) - 1u));
+            if (at >= kCoopQ) at -= kCoopQ;
+            q[at] = c1;
+            at++; if (at >= kCoopQ) at -= kCoopQ;
+            q[at] = c2;
+        }
+        tail += total; if (tail >= kCoopQ) tail -= kCoopQ;
+        live += total;
+        __syncwarp();
+    }
+    float D1 = kInfF, D2 = kInfF; int p1 = 0; bool settled = false;
+    if (!overflow) {
+        D1 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(bd1)));
+        const int win = __ffs(__ballot_sync(full, bd1 == D1)) - 1;
+        D2 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(lane == win ? bd2 : bd1)));
+        p1 = __shfl_sync(full, bpos, win);
+        if (D2 > D1 * 1.00001f) settled = true;
+        else if (D2 > D1) {
+            // replay of the reference's bound along the root path of p1 (computeInitialDistances + searchLevel,
+            // nanoflann_goicp.hpp:1113-1184); every lane walks the same path
+            float ds0 = 0.0f, ds1 = 0.0f, ds2 = 0.0f, cur_min = 0.0f;
+            {
+                const float qq[3] = {qx, qy, qz};
+                float ds[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    if (qq[i] < kd.bb_lo[i]) { float d = qq[i] - kd.bb_lo[i]; ds[i] = d * d; cur_min += ds[i]; }
+                    if (qq[i] > kd.bb_hi[i]) { float d = qq[i] - kd.bb_hi[i]; ds[i] = d * d; cur_min += ds[i]; }
+                }
+                ds0 = ds[0]; ds1 = ds[1]; ds2 = ds[2];
+            }
+            int cur = 0; settled = true;
+            for (;;) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + cur)), b = __ldg(reinterpret_cast<const uint4*>(nodes + cur) + 1);
+                if ((int)a.x < 0 && (int)a.y < 0) break;
+                const int mid = __float_as_int(__ldg(kd.boxes + 2 * (size_t)cur).w);
+                const int idx = (int)b.x; const float divlow = __uint_as_float(b.y), divhigh = __uint_as_float(b.z);
+                const float val = sel3(qx, qy, qz, idx);
+                const float diff1 = val - divlow, diff2 = val - divhigh;
+                int bestc, otherc; float cut;
+                if ((diff1 + diff2) < 0) { bestc = (int)a.x; otherc = (int)a.y; cut = (val - divhigh) * (val - divhigh); }
+                else                     { bestc = (int)a.y; otherc = (int)a.x; cut = (val - divlow) * (val - divlow); }
+                const int target = p1 < mid ? (int)a.x : (int)a.y;
+                if (target == bestc) { cur = bestc; continue; }       // the preferred child is always searched
+                const float dst = sel3(ds0, ds1, ds2, idx);
+                const float m2 = cur_min + cut - dst;
+                if (!(m2 <= D2)) { settled = false; break; }           // cannot prove the reference gets here
+                if (idx == 0) ds0 = cut; else if (idx == 1) ds1 = cut; else ds2 = cut;
+                cur_min = m2; cur = otherc;
+            }
+        }
+    }
+    if (settled) { d2_out = D1; pos_out = p1; return __float_as_int(__ldg(leaf + p1).w); }
+    d2_out = overflow ? lim : D1;          // not settled here: the caller runs the reference walk, capped by this bound
+    pos_out = 0;
+    return -1;
 }
 
 __global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t* __restrict__ idx, float* __restrict__ d2)
@@ -136,6 +288,19 @@ __global__ void nn_kernel(KdView kd, const float* __restrict__ q, int n, int32_t
     float d;
     idx[i] = kd_nearest(kd, kd.nodes, kd.pts_leaf, q[3 * i], q[3 * i + 1], q[3 * i + 2], 3.402823466e+38f, d);
     d2[i] = d;
+}
+// the same answers through the warp-cooperative search, one query per warp at a time (parity tests: GOICP_NN_COOP=1)
+__global__ void __launch_bounds__(128) nn_coop_kernel(KdView kd, const float* __restrict__ q, int n, int32_t* __restrict__ idx, float* __restrict__ d2)
+{
+    __shared__ int queue[4][kCoopQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = blockIdx.x * 4 + warp; i < n; i += gridDim.x * 4) {
+        float d; int pos;
+        int id = kd_coop_nearest(kd, queue[warp], q[3 * i], q[3 * i + 1], q[3 * i + 2], -1, lane, d, pos);
+        if (id < 0) id = kd_nearest(kd, kd.nodes, kd.pts_leaf, q[3 * i], q[3 * i + 1], q[3 * i + 2], d, d);      // every lane the same walk
+        if (lane == 0) { idx[i] = id; d2[i] = d; }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -381,7 +546,7 @@ __device__ void icp_update(IcpState* st, const float* H)
 constexpr int kIcpChunk = 384;
 
 // dynamic shared memory plan of the ICP kernel (decided on the host)
-struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; };
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; int nn_budget; };
 
 // ------------------------------------------------------------------------------------------
 // Phase B for clouds too large to rank by counting (the keys no longer fit in shared memory and
@@ -535,6 +700,8 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     __shared__ float sh_acc[8];
     __shared__ __align__(16) float chunk[2][kIcpChunk * 8];      // double buffer of the streamed (large-cloud) accumulation
     __shared__ NnPartial part;
+    __shared__ int n_deferred, n_unsettled;
+    static_assert(sizeof(chunk) >= (size_t)(kIcpThreads / 32) * kCoopQ * sizeof(int), "the cooperative search's queues alias `chunk`");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIcpThreads / 32;
     const volatile IcpState* vst = st;
@@ -609,26 +776,67 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 __syncthreads();
             }
         } else {
-            for (int i = threadIdx.x * gridDim.x + blockIdx.x; i < nd; i += gridDim.x * blockDim.x) {
-                const float4 p = __ldg(data + i);
-                const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
-                const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
-                const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-                // reference traversal with subtree skipping, capped by the distance to the point's last correspondent
-                // (any model point bounds the nearest distance from above; a stale or never-written index is just a loose cap)
-                float d2, cap;
-                {
-                    const unsigned seed = (unsigned)__ldcg(wk.nn + i) < (unsigned)kd.nm ? (unsigned)__ldcg(wk.nn + i) : 0u;
-                    const float e0 = qx - __ldg(kd.model + 3 * seed), e1 = qy - __ldg(kd.model + 3 * seed + 1), e2 = qz - __ldg(kd.model + 3 * seed + 2);
-                    cap = e0 * e0 + e1 * e1 + e2 * e2;
-                }
-                const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, cap, d2);
-                wk.nn[i] = id; wk.d2[i] = d2;
+            // Tree search.  With a visit budget > 1 every thread first walks the reference's traversal for its own queries
+            // (subtree skipping, capped by the distance to the point's last correspondent; any model point bounds the
+            // nearest distance from above, a stale or never-written position is just a loose cap) and a walk that exceeds
+            // plan.nn_budget node visits is put on the CTA's list; the listed queries (by default: all of them) are
+            // answered by the warp-cooperative search, one query per warp at a time.
+            int* deferred = wk.order + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);   // wk.order is idle until the sort
+            if (threadIdx.x == 0) { n_deferred = 0; n_unsettled = 0; }
+            __syncthreads();
+            auto emit = [&](int i, int id, int pos, float d2, float qx, float qy, float qz) {
+                wk.nn[i] = id; wk.pos[i] = pos; wk.d2[i] = d2;
                 wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
                 float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
                 row[0] = make_float4(__ldg(kd.model + 3 * id), __ldg(kd.model + 3 * id + 1), __ldg(kd.model + 3 * id + 2), qx);
                 row[1] = make_float4(qy, qz, d2, 0.0f);
+            };
+            // pass 0: every thread its own queries, within the visit budget; then the cooperative search of the deferred
+            // ones; pass 1: the few it could not settle (exact ties, ...) walk the reference traversal to the end.
+            unsigned long long* unsettled = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);   // idle until the sort
+            for (int pass = 0; pass < 2; pass++) {
+                const int count = pass == 0 ? nd : n_unsettled;
+                for (int g = pass == 0 ? threadIdx.x * gridDim.x + blockIdx.x : threadIdx.x; g < count; g += (pass == 0 ? gridDim.x : 1) * blockDim.x) {
+                    const unsigned long long rec = pass == 0 ? 0ull : unsettled[g];
+                    const int i = pass == 0 ? g : (int)(unsigned)rec;
+                    if (pass == 0 && plan.nn_budget == 1) { deferred[atomicAdd(&n_deferred, 1)] = i; continue; }   // everything goes to the cooperative search
+                    const float4 p = __ldg(data + i);
+                    const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                    float d2, cap; int pos;
+                    if (pass == 0) {
+                        const unsigned sp = (unsigned)__ldcg(wk.pos + i) < (unsigned)kd.nm ? (unsigned)__ldcg(wk.pos + i) : 0u;
+                        const float4 m = __ldg(leaf + sp);
+                        const float e0 = qx - m.x, e1 = qy - m.y, e2 = qz - m.z;
+                        cap = e0 * e0 + e1 * e1 + e2 * e2;
+                    } else cap = __uint_as_float((unsigned)(rec >> 32));
+                    const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, cap, d2, pass == 0 ? plan.nn_budget : 0, &pos);
+                    if (id < 0) { deferred[atomicAdd(&n_deferred, 1)] = i; continue; }
+                    emit(i, id, pos, d2, qx, qy, qz);
+                }
+                if (pass == 1) break;
+                __syncthreads();
+                const int ndef = n_deferred;
+                int* queue = reinterpret_cast<int*>(&chunk[0][0]) + warp * kCoopQ;   // `chunk` is idle until phase C
+                for (int k = warp; k < ndef; k += kWarps) {
+                    const int i = deferred[k];
+                    const float4 p = __ldg(data + i);
+                    const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                    const int sp = (unsigned)__ldcg(wk.pos + i) < (unsigned)kd.nm ? __ldcg(wk.pos + i) : 0;
+                    float d2; int pos;
+                    const int id = kd_coop_nearest(kd, queue, qx, qy, qz, sp, lane, d2, pos);
+                    if (lane == 0) {
+                        if (id >= 0) emit(i, id, pos, d2, qx, qy, qz);
+                        else unsettled[atomicAdd(&n_unsettled, 1)] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
             }
+            __syncthreads();                                                         // the lists live in wk.order, the queues in `chunk`
         }
         long long c1 = clock64(); c_nn += c1 - c0;
         grid.sync();
@@ -770,15 +978,22 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; st->dbg[0] = c_nn + (c_svd << 32); }
 }
 
-cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, cudaStream_t s)
+cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    nn_kernel<<<(n + 127) / 128, 128, 0, s>>>(kd, d_q, n, d_idx, d_d2);
+    if (cooperative) nn_coop_kernel<<<min((n + 3) / 4, 148 * 16), 128, 0, s>>>(kd, d_q, n, d_idx, d_d2);
+    else nn_kernel<<<(n + 127) / 128, 128, 0, s>>>(kd, d_q, n, d_idx, d_d2);
     return cudaGetLastError();
 }
 static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int smem_limit)
 {
-    IcpSmemPlan p = {0, 0, 0, 0, 0};
+    // node visits a thread spends on one query before the warp-cooperative search takes it over; 0 = walk to the end, 1 = do
+    // not try at all.  Measured (ICP seconds, budgets 0 / 96 / 1): 10 k x 100 k 0.36 / 0.24 / 0.066, 100 k x 1 M 3.1 / 1.8 / 1.2,
+    // 1 M x 1 M - / 26.3 / 16.2, bunny 40 k x 40 k 0.034 / 0.031 / 0.026: with 32 divergent walks per warp there is nearly
+    // always a lane in a leaf scan or an unwind, so the warp pays the longest branch at every step; the cooperative search
+    // keeps the lanes in lock step on one query.  GOICP_NN_BUDGET overrides (the parity tests force each path).
+    IcpSmemPlan p = {0, 0, 0, 0, 0, 1};
+    if (const char* f = getenv("GOICP_NN_BUDGET")) p.nn_budget = atoi(f);
     int left = smem_limit;
     const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
     const size_t stage = (size_t)num * 8 * sizeof(float);

@@ -101,6 +101,8 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
     n.divlow = lhi[axis]; n.divhigh = rlo[axis];                     // tightened child boxes (:962-963)
     for (int a = 0; a < 3; ++a) { lo[a] = std::min(llo[a], rlo[a]); hi[a] = std::max(lhi[a], rhi[a]); }
     keep_box();
+    const int32_t mid_pos = left + split;                            // first leaf-order position of child2's points
+    std::memcpy(&boxes[8 * (size_t)id + 3], &mid_pos, sizeof mid_pos);
     return id;
 }
 

@@ -16,7 +16,7 @@ namespace goicp {
 struct HostKdTree {
     std::vector<KdNode> nodes;
     std::vector<int32_t> vind;          // permutation of model indices; leaves own [left,right)
-    std::vector<float> boxes;           // 8 floats per node: tight bounding box of the subtree's points {lo xyz, 0, hi xyz, 0}
+    std::vector<float> boxes;           // 8 floats per node: tight bounding box of the subtree's points {lo xyz, m, hi xyz, 0}; interior nodes: m = int bits of the first leaf-order position of child2
     float bb_lo[3], bb_hi[3];           // root bounding box after the build tightened it
     void build(const float* xyz, int n, int leaf_max = 10);
 private:

@@ -113,8 +113,10 @@ def _bumpy_surface(n, seed):
     return (u * r[:, None]).astype(np.float32)
 
 
-def test_nn_far_queries_large_model_vs_oracle(pkg, restated):
-    """kd-tree search with subtree skipping (tight boxes) against the oracle's plain reference traversal:
+@pytest.mark.parametrize("search", ["walk", "cooperative"])
+def test_nn_far_queries_large_model_vs_oracle(pkg, restated, search, monkeypatch):
+    """Both device searches -- the per-thread reference walk with subtree skipping, and the warp-cooperative
+    frontier search with its tie rules (GOICP_NN_COOP=1) -- against the oracle's plain reference traversal:
     a model large enough for the tree path (60k surface points + a lattice block with duplicated points),
     queries far from the surface (where the reference walks thousands of leaves), near it, on model points,
     and at half-integer lattice positions (exact ties: the traversal ORDER decides the index)."""
@@ -128,6 +130,10 @@ def test_nn_far_queries_large_model_vs_oracle(pkg, restated):
                         model[rng.choice(len(model), 1000)],                                 # on model points (d = 0, duplicates)
                         lat[rng.choice(len(lat), 1000)] + np.float32(0.03125),               # cell centres: 8-way exact ties
                         np.zeros((1, 3))]).astype(np.float32)                                 # centre of the surface: near-ties all around
+    if search == "cooperative":
+        monkeypatch.setenv("GOICP_NN_COOP", "1")
+    else:
+        monkeypatch.delenv("GOICP_NN_COOP", raising=False)
     kd = restated.kd_build(model)
     ref_idx, ref_d2 = restated.kd_nn(kd, q)
     g = pkg.GoICP(1e-3)
@@ -138,10 +144,13 @@ def test_nn_far_queries_large_model_vs_oracle(pkg, restated):
     assert np.array_equal(idx, ref_idx)
 
 
-def test_icp_large_model_tree_path_vs_oracle(pkg, restated):
+@pytest.mark.parametrize("budget", ["1", "0", "96", "12"])
+def test_icp_large_model_tree_path_vs_oracle(pkg, restated, budget, monkeypatch):
     """ICP3D::Run through the tree-search branch of the ICP kernel (model > 16384 points) from a pose
     40 mrad / 0.05 off: every iteration's correspondences, sort and sequential sums follow the oracle,
-    so R, t and the error agree bit for bit."""
+    so R, t and the error agree bit for bit -- with every query answered by the warp-cooperative search (1, the
+    default), with the per-thread walk only (0 = unlimited), and with mixes (96, 12)."""
+    monkeypatch.setenv("GOICP_NN_BUDGET", budget)
     model = _bumpy_surface(50000, 7)
     rng = np.random.default_rng(3)
     data = (model[rng.choice(len(model), 6000, replace=False)] + rng.normal(scale=1e-3, size=(6000, 3))).astype(np.float32)
