@@ -296,6 +296,35 @@ def test_icp_overlapped_with_dt_build_changes_nothing(pkg, bunny, monkeypatch):
         assert np.array_equal(x["R"], a0["R"]) and np.array_equal(x["t"], a0["t"])
 
 
+@pytest.mark.parametrize("nm,nd,S,mse,tcube", [(12, 5, 24, 5e-3, None), (700, 1, 32, 5e-3, None), (40, 33, 32, 2e-2, None),
+                                              (1186, 257, 40, 3e-3, None), (300, 100, 31, 1e-2, (-1.0, -1.0, -1.0, 2.0))])
+def test_tiny_and_ragged_clouds_vs_oracle(pkg, restated, bunny, nm, nd, S, mse, tcube):
+    """Edge sizes: fewer points than a warp, a single data point, counts that are no multiple of anything, odd
+    grid sizes, the [-1,1]^3 translation domain of the Artec TOMLs -- whole registrations (several ICP calls,
+    certified exits after thousands of rotation pops) against the oracle on the same inputs."""
+    rng = np.random.default_rng(nm * 1000 + nd)
+    m = bunny["model_s"][rng.choice(len(bunny["model_s"]), nm, replace=False)].copy()
+    d = bunny["data_s"][rng.choice(len(bunny["data_s"]), nd, replace=False)].copy()
+    o = restated.create(m, d, mse, 0.0, S, 2.0, tcube)
+    restated.L.go_build_dt(o)
+    ref = restated.register(o)
+    g = pkg.GoICP(mse)
+    g.pModel, g.pData = m, d
+    g.dt.SIZE = S
+    if tcube is not None:
+        g.initNodeTrans = tcube
+    g.BuildDT()
+    grid, _ = g.GetDT()
+    assert np.array_equal(restated.dt_grid(restated.L.go_get_dt(o), S), grid)
+    g.Register()
+    r = g.result
+    g.close()
+    assert r["exit_path"] == ref["exit_path"]
+    assert r["sse"] == pytest.approx(ref["sse"], rel=1e-5, abs=1e-7)
+    assert rot_angle(r["R"], ref["R"]) < 1e-4 and np.abs(r["t"] - ref["t"]).max() < 1e-4
+    assert r["icp_calls"] == ref["icp_calls"] and _close_counts(r["rot_pops"], ref["rot_pops"])
+
+
 def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
     """the reference's own workflow: TOML -> load clouds -> DT -> Go-ICP -> output file, on the GPU"""
     for name, arr in (("model.txt", bunny["model"]), ("data.txt", bunny["data"])):
