@@ -189,7 +189,7 @@ struct goicp_handle {
     // multi-GPU exchange
     goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
     bool low_latency = true;             // inner-BnB kernel variant of the next round (see run_inner_batch)
-    NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather;      // native exchange: all-gather of the round's result records on the stream
+    NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather; DevBuf<unsigned char> d_share;      // native exchange: all-gather of the round's result records on the stream
 
     // timing
     double t_kernels = 0, t_icp = 0, t_score = 0, t_strict = 0, t_setup = 0;     // t_score.. only for GOICP_ROUND_STATS
@@ -503,6 +503,33 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     return GOICP_OK;
 }
 
+// All ranks hold the same result records but only the rank that ran an upper-bound pass holds its contender list.
+// When the commit needs that list (same moment on every rank: the decision depends on replicated data only), the
+// holder's copy is handed round with one small all-gather over the handle's exchange -- instead of every other rank
+// re-running the whole inner BnB just to re-derive it (as long as the round's longest task at Nd = 1e5).
+int share_cand_list(goicp_handle* h, std::shared_ptr<CandList>& cl)
+{
+    const int W = h->p.world_size;
+    struct Block { int32_t have; int32_t pad; CandList list; };
+    std::vector<Block> recv((size_t)W);
+    Block mine; std::memset(&mine, 0, sizeof mine);
+    if (cl) { mine.have = 1; mine.list = *cl; }
+    if (h->nccl) {
+        CUDA_TRY(h, h->d_share.reserve((size_t)(W + 1) * sizeof(Block)));
+        CUDA_TRY(h, cudaMemcpyAsync(h->d_share.p, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+        const int nrc = nccl_api()->AllGather(h->d_share.p, h->d_share.p + sizeof(Block), sizeof(Block), kNcclUint8, h->nccl, h->stream);
+        if (nrc != 0) return fail(h, GOICP_ERR_CUDA, "ncclAllGather (contender list) failed");
+        CUDA_TRY(h, cudaMemcpyAsync(recv.data(), h->d_share.p + sizeof(Block), sizeof(Block) * W, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    } else if (h->xchg) {
+        if (h->xchg(h->xchg_user, &mine, recv.data(), sizeof(Block), 0) != 0) return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
+    } else return GOICP_OK;
+    if (!cl)
+        for (int r = 0; r < W; r++)
+            if (recv[r].have) { cl = std::make_shared<CandList>(recv[r].list); break; }
+    return GOICP_OK;
+}
+
 // Settles value and arg-min cube of one upper-bound pass in the reference's summation order
 // (strict_sum.cuh).  `list` are the contenders the search kernel reported for that task.
 int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, const CandList& list, float* value, float* node4)
@@ -639,7 +666,7 @@ int goicp_destroy(goicp_handle* h)
     if (h->cuda_ready) {
         cudaSetDevice(h->p.device);
         h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
-        h->d_gather.release();
+        h->d_gather.release(); h->d_share.release();
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
@@ -1106,16 +1133,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                         // reference's summation order before deciding (strict_sum.cuh)
                         InnerTask task; std::memcpy(task.R, ce.R, sizeof ce.R); task.level = -1; task.opt_error = ce.ub_opt_error; task.pad = 0;
                         std::shared_ptr<CandList> cl = ce.cands;
-                        if (!cl) {      // evaluated on another rank: re-derive the contender list here (deterministic)
-                            h->h_tasks[0] = task;
-                            goicp_allgather_fn saved = h->xchg; h->xchg = nullptr;
-                            NcclComm saved_nccl = h->nccl; h->nccl = nullptr;
-                            std::vector<std::shared_ptr<CandList>> one;
-                            rc = run_inner_batch(h, c, 1, nullptr, &one);
-                            h->xchg = saved; h->nccl = saved_nccl;
-                            if (rc) return rc;
-                            cl = one[0];
-                        }
+                        if ((h->xchg || h->nccl) && h->p.world_size > 1) { rc = share_cand_list(h, cl); if (rc) return rc; }   // collective: every rank is here
                         if (cl) { rc = resolve_strict(h, c, task, *cl, &ub, ub_node); if (rc) return rc; }
                     }
                     if (ub < E) {                                                          // :495-544

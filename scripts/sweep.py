@@ -65,10 +65,11 @@ def main():
         dist.broadcast(idt, 0)                      # plumbing only: the 128-byte ncclUniqueId
         nccl_id = bytes(idt.cpu().numpy().tobytes())
     if world > 1:                                   # first collective of a communicator sets up its connections (~1 s): not a case's time
-        m0, d0, _, _ = synth(20000, 500)
-        g = pkg.GoICP(1e-3, device=local_rank)
-        g.pModel, g.pData = m0, d0
-        g.dt.SIZE = 64
+        gold = os.path.join(ROOT, "tests", "golden")    # a registration that does go through BnB rounds (926 rotation pops)
+        g = pkg.GoICP(2e-3, device=local_rank)
+        g.pModel = np.fromfile(os.path.join(gold, "bunny_model_s0.033_seed1234.f32"), np.float32).reshape(-1, 3)
+        g.pData = np.fromfile(os.path.join(gold, "bunny_data_s0.033_seed1235.f32"), np.float32).reshape(-1, 3)[::4].copy()
+        g.dt.SIZE = 50
         g.dt_mode = 1
         g.init_nccl(nccl_id, rank, world)
         g.BuildDT(); g.Register(); g.close()
