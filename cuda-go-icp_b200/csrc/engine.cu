@@ -757,8 +757,8 @@ int goicp_build_dt(goicp_handle* h)
         const int rc_icp = run_icp(h, R0, t0, h->p.icp_max_iter, h->p.mse_threshold / 10000, &h->icp0, std::max(1, h->sm_count - 1));
         if (trace) fprintf(stderr, "[dt trace] overlapped ICP (upload + kd-tree + kernel) %.3f ms\n", 1e3 * (now_s() - tr1));
         worker.join();
-        if (rc_icp) return rc_icp;
-        h->icp0_valid = true;
+        h->icp0_valid = rc_icp == GOICP_OK;           // a failed head start is not a failed DT build: Register runs that ICP itself
+        if (rc_icp) h->err.clear();
     } else {
         e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
     }
