@@ -72,8 +72,21 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
-               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
                "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
+
+
+def kdtree_host(model):
+    """ICP3D::Build's kd-tree layout as the library builds it on the host (no device needed): nodes (n_nodes, 7) int32
+    {child1, child2, left, right, divfeat, divlow bits, divhigh bits}, vind, root box (6 floats)."""
+    m = np.ascontiguousarray(model, np.float32).reshape(-1, 3)
+    L = lib()
+    nn = L.goicp_kdtree_host(m.ctypes.data, len(m), None, 0, None, None)
+    if nn < 0:
+        raise GoicpError(-nn, "goicp_kdtree_host")
+    nodes = np.zeros((nn, 7), np.int32); vind = np.zeros(len(m), np.int32); bbox = np.zeros(6, np.float32)
+    L.goicp_kdtree_host(m.ctypes.data, len(m), nodes.ctypes.data, nn, vind.ctypes.data, bbox.ctypes.data)
+    return nodes, vind, bbox
 
 
 def build(verbose: bool = False) -> str:
@@ -113,6 +126,7 @@ def lib():
         L.goicp_expand_bounds.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.goicp_inner_bnb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.goicp_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.goicp_kdtree_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.POINTER(IcpResult)]
         L.goicp_icp_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
         L.goicp_dt_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]

@@ -890,6 +890,24 @@ int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float
     return GOICP_OK;
 }
 
+int goicp_kdtree_host(const float* model_xyz, int n, int32_t* nodes7_out, int capacity_nodes, int32_t* vind_out, float* bbox6_out)
+{
+    if (!model_xyz || n <= 0) return -GOICP_ERR_INVALID;
+    HostKdTree t;
+    t.build(model_xyz, n, 10);
+    const int nn = (int)t.nodes.size();
+    if (nn > capacity_nodes || !nodes7_out || !vind_out || !bbox6_out) return nn;
+    for (int i = 0; i < nn; i++) {
+        const KdNode& k = t.nodes[i];
+        int32_t* o = nodes7_out + 7 * (size_t)i;
+        o[0] = k.child1; o[1] = k.child2; o[2] = k.left; o[3] = k.right; o[4] = k.divfeat;
+        std::memcpy(&o[5], &k.divlow, 4); std::memcpy(&o[6], &k.divhigh, 4);
+    }
+    std::memcpy(vind_out, t.vind.data(), sizeof(int32_t) * (size_t)n);
+    for (int a = 0; a < 3; a++) { bbox6_out[a] = t.bb_lo[a]; bbox6_out[3 + a] = t.bb_hi[a]; }
+    return nn;
+}
+
 int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff, goicp_icp_result* out)
 {
     if (!h || !R0 || !t0 || !out) return fail(h, GOICP_ERR_INVALID, "icp: bad arguments");

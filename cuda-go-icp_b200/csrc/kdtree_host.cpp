@@ -2,6 +2,7 @@
 #include "kdtree_host.h"
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 namespace goicp {
 
@@ -45,10 +46,19 @@ void plane_split(const float* pts, int32_t* ind, int count, int axis, float cut,
     lim2 = (int)lo;
 }
 
-} // namespace
+// One builder = one contiguous block of nodes in pre-order (a node, its whole left subtree, its whole right subtree).
+// Large right subtrees are built by another builder on its own thread and spliced in behind the left one: same node
+// numbering as a sequential build (child1 == parent + 1), a 1 M-point model in 0.58 s -> a fraction of that on the
+// host cores a registration otherwise leaves idle.
+struct Builder {
+    const float* pts; int32_t* vind;                 // vind: the shared permutation; builders own disjoint ranges of it
+    std::vector<KdNode> nodes; std::vector<float> boxes;
+    int divide(int left, int right, float* lo, float* hi, int leaf_max, int depth);
+};
 
-int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
+int Builder::divide(int left, int right, float* lo, float* hi, int leaf_max, int depth)
 {
+    const float* pts_ = pts;
     const int id = (int)nodes.size();
     nodes.push_back(KdNode{});
     boxes.resize(boxes.size() + 8, 0.0f);
@@ -69,7 +79,7 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
         return id;
     }
     // ---- split selection (middleSplit_, :1033-1072) ----
-    int32_t* ind = vind.data() + left;
+    int32_t* ind = vind + left;
     const int count = right - left;
     const float eps = (float)0.00001;
     float widest = hi[0] - lo[0];
@@ -93,9 +103,24 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
 
     float llo[3], lhi[3], rlo[3], rhi[3];
     std::memcpy(llo, lo, sizeof llo); std::memcpy(lhi, hi, sizeof lhi); lhi[axis] = cut;
-    const int c1 = divide(left, left + split, llo, lhi, leaf_max);
     std::memcpy(rlo, lo, sizeof rlo); std::memcpy(rhi, hi, sizeof rhi); rlo[axis] = cut;
-    const int c2 = divide(left + split, right, rlo, rhi, leaf_max);
+    int c1, c2;
+    if (depth < 3 && count - split >= 16384) {
+        Builder right_b{pts, vind, {}, {}};
+        std::thread worker([&]() { right_b.divide(left + split, right, rlo, rhi, leaf_max, depth + 1); });
+        c1 = divide(left, left + split, llo, lhi, leaf_max, depth + 1);
+        worker.join();
+        c2 = (int)nodes.size();                                      // splice: the right block follows the left one
+        for (KdNode k : right_b.nodes) {
+            if (k.child1 >= 0) k.child1 += c2;
+            if (k.child2 >= 0) k.child2 += c2;
+            nodes.push_back(k);
+        }
+        boxes.insert(boxes.end(), right_b.boxes.begin(), right_b.boxes.end());
+    } else {
+        c1 = divide(left, left + split, llo, lhi, leaf_max, depth + 1);
+        c2 = divide(left + split, right, rlo, rhi, leaf_max, depth + 1);
+    }
     KdNode& n = nodes[id];
     n.child1 = c1; n.child2 = c2; n.left = n.right = 0; n.divfeat = axis; n.pad = 0;
     n.divlow = lhi[axis]; n.divhigh = rlo[axis];                     // tightened child boxes (:962-963)
@@ -106,11 +131,11 @@ int HostKdTree::divide(int left, int right, float* lo, float* hi, int leaf_max)
     return id;
 }
 
+} // namespace
+
 void HostKdTree::build(const float* xyz, int n, int leaf_max)
 {
     pts_ = xyz;
-    nodes.clear();
-    boxes.clear();
     vind.resize(n);
     for (int i = 0; i < n; ++i) vind[i] = i;
     for (int a = 0; a < 3; ++a) bb_lo[a] = bb_hi[a] = xyz[a];        // computeBoundingBox (:895-917)
@@ -120,7 +145,10 @@ void HostKdTree::build(const float* xyz, int n, int leaf_max)
             if (v < bb_lo[a]) bb_lo[a] = v;
             if (v > bb_hi[a]) bb_hi[a] = v;
         }
-    divide(0, n, bb_lo, bb_hi, leaf_max);                             // root box is tightened in place (:761)
+    Builder b{xyz, vind.data(), {}, {}};
+    b.divide(0, n, bb_lo, bb_hi, leaf_max, 0);                        // root box is tightened in place (:761)
+    nodes.swap(b.nodes);
+    boxes.swap(b.boxes);
 }
 
 } // namespace goicp

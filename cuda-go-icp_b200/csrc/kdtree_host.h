@@ -21,7 +21,6 @@ struct HostKdTree {
     void build(const float* xyz, int n, int leaf_max = 10);
 private:
     const float* pts_ = nullptr;
-    int divide(int left, int right, float* lo, float* hi, int leaf_max);
 };
 
 } // namespace goicp

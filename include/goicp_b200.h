@@ -162,6 +162,14 @@ int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* leve
  * KDTreeSingleIndexAdaptor::knnSearch(k=1) (nanoflann_goicp.hpp:821-826). */
 int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float* d2_out);
 
+/* The model kd-tree exactly as ICP3D::Build lays it out (jly_icp3d.hpp:129-154; divideTree / middleSplit_ / planeSplit,
+ * nanoflann_goicp.hpp:927-1111, leaf size 10): built on the host, no device needed -- the layout decides which of several
+ * equidistant points goicp_nn returns, so it is exposed for parity checks.  nodes7_out: 7 int32 per node {child1, child2,
+ * left, right, divfeat, float bits of divlow, float bits of divhigh} (children -1/-1 and [left,right) into vind for a leaf),
+ * node 0 = root, capacity_nodes entries available; vind_out: n indices; bbox6_out: root box lo xyz, hi xyz.
+ * Returns the number of nodes (the tree is not written if that exceeds capacity_nodes), or a negative goicp status. */
+int goicp_kdtree_host(const float* model_xyz, int n, int32_t* nodes7_out, int capacity_nodes, int32_t* vind_out, float* bbox6_out);
+
 /* ICP3D<float>::Run (jly_icp3d.hpp:180-295) from (R0,t0). err_diff<0 -> mse_threshold/10000
  * (jly_goicp.cpp:186); max_iter<=0 -> params.icp_max_iter. */
 int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff,

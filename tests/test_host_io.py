@@ -93,3 +93,49 @@ def test_run_toml_reports_bad_config_and_needs_a_gpu(pkg, tmp_path, bunny):
         with pytest.raises(pkg.GoicpError) as e:
             pkg.run_toml(str(cfg))
         assert "no CUDA device" in str(e.value)
+
+
+def _same_tree(a_nodes, b_nodes, ia=0, ib=0):
+    """structural equality of two flattened kd-trees whose node numbering may differ"""
+    stack = [(ia, ib)]
+    while stack:
+        x, y = stack.pop()
+        a, b = a_nodes[x], b_nodes[y]
+        leaf_a, leaf_b = a[0] < 0 and a[1] < 0, b[0] < 0 and b[1] < 0
+        if leaf_a != leaf_b:
+            return False
+        if leaf_a:
+            if a[2] != b[2] or a[3] != b[3]:
+                return False
+        else:
+            if a[4] != b[4] or a[5] != b[5] or a[6] != b[6]:        # split axis and the bit patterns of divlow / divhigh
+                return False
+            stack.append((a[0], b[0])); stack.append((a[1], b[1]))
+    return True
+
+
+@pytest.mark.parametrize("case", ["bunny", "lattice_with_duplicates", "random_50k", "planar", "tiny"])
+def test_host_kdtree_layout_is_the_reference_layout(pkg, restated, bunny, case):
+    """The library's host kd-tree builder (no device involved) against the oracle's ICP3D::Build restatement, itself
+    pinned to the unmodified reference: same splits (bit patterns), same leaf ranges, same permutation -- the layout
+    that decides which of several equidistant model points a nearest-neighbour query returns."""
+    rng = np.random.default_rng(5)
+    if case == "bunny":
+        m = bunny["model"]
+    elif case == "lattice_with_duplicates":
+        ax = np.arange(9, dtype=np.float32) * 0.125
+        lat = np.stack(np.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)
+        m = np.concatenate([lat, lat[::2], lat[::7]]).astype(np.float32)
+    elif case == "random_50k":
+        m = rng.uniform(-1, 1, (50000, 3)).astype(np.float32)
+    elif case == "planar":
+        m = np.concatenate([rng.uniform(-1, 1, (3000, 2)), np.full((3000, 1), 0.25)], 1).astype(np.float32)   # zero spread on one axis
+    else:
+        m = rng.uniform(-1, 1, (7, 3)).astype(np.float32)                                                     # a single leaf
+    nodes, vind, bbox = pkg.kdtree_host(m)
+    kd = restated.kd_build(m)
+    ref_nodes, ref_vind, ref_bbox = restated.kd_export(kd, len(m))
+    assert len(nodes) == len(ref_nodes)
+    assert np.array_equal(vind, ref_vind)
+    assert np.array_equal(bbox.view(np.uint32), ref_bbox.view(np.uint32))
+    assert _same_tree(nodes, ref_nodes)
