@@ -544,6 +544,7 @@ __device__ void icp_update(IcpState* st, const float* H)
 // point, so its end point depends on the exact path.
 // ------------------------------------------------------------------------------------------
 constexpr int kIcpChunk = 384;
+constexpr int kColPitch = kIcpChunk + 4;       // column pitch of a transposed chunk: 7 columns fit the 8 * kIcpChunk floats, lanes read distinct banks
 
 // dynamic shared memory plan of the ICP kernel (decided on the host)
 struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; int nn_budget; };
@@ -653,28 +654,29 @@ __device__ void icp_radix_sort(cg::grid_group& grid, const IcpWork& wk, int nd, 
     }
 }
 
-// acc += x[0], x[stride], x[2*stride], ... (cnt terms) strictly in order; the operands of the next 16
-// adds are fetched while the dependent chain of the current 16 retires.
-__device__ __forceinline__ float seq_add_strided(float acc, const float* x, int stride, int cnt)
+// acc += x[0], x[1], ... (cnt terms, x 16-byte aligned) strictly in order.  The accumulation buffers are laid out one
+// COLUMN per adding lane, so a lane fetches four operands per shared-memory instruction; 16 operands are in flight
+// ahead of the dependent chain of adds, which is then all that is left: ~4 cycles per term.
+__device__ __forceinline__ float seq_add_contig(float acc, const float* x, int cnt)
 {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
     int rr = 0;
     if (cnt >= 16) {
-        float v[16];
-#pragma unroll
-        for (int u = 0; u < 16; u++) v[u] = x[stride * u];
+        float4 a0 = x4[0], a1 = x4[1], a2 = x4[2], a3 = x4[3];
         for (rr = 16; rr + 16 <= cnt; rr += 16) {
-            float nx[16];
-#pragma unroll
-            for (int u = 0; u < 16; u++) nx[u] = x[stride * (rr + u)];
-#pragma unroll
-            for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
-#pragma unroll
-            for (int u = 0; u < 16; u++) v[u] = nx[u];
+            const float4 b0 = x4[rr / 4], b1 = x4[rr / 4 + 1], b2 = x4[rr / 4 + 2], b3 = x4[rr / 4 + 3];
+            acc = __fadd_rn(acc, a0.x); acc = __fadd_rn(acc, a0.y); acc = __fadd_rn(acc, a0.z); acc = __fadd_rn(acc, a0.w);
+            acc = __fadd_rn(acc, a1.x); acc = __fadd_rn(acc, a1.y); acc = __fadd_rn(acc, a1.z); acc = __fadd_rn(acc, a1.w);
+            acc = __fadd_rn(acc, a2.x); acc = __fadd_rn(acc, a2.y); acc = __fadd_rn(acc, a2.z); acc = __fadd_rn(acc, a2.w);
+            acc = __fadd_rn(acc, a3.x); acc = __fadd_rn(acc, a3.y); acc = __fadd_rn(acc, a3.z); acc = __fadd_rn(acc, a3.w);
+            a0 = b0; a1 = b1; a2 = b2; a3 = b3;
         }
-#pragma unroll
-        for (int u = 0; u < 16; u++) acc = __fadd_rn(acc, v[u]);
+        acc = __fadd_rn(acc, a0.x); acc = __fadd_rn(acc, a0.y); acc = __fadd_rn(acc, a0.z); acc = __fadd_rn(acc, a0.w);
+        acc = __fadd_rn(acc, a1.x); acc = __fadd_rn(acc, a1.y); acc = __fadd_rn(acc, a1.z); acc = __fadd_rn(acc, a1.w);
+        acc = __fadd_rn(acc, a2.x); acc = __fadd_rn(acc, a2.y); acc = __fadd_rn(acc, a2.z); acc = __fadd_rn(acc, a2.w);
+        acc = __fadd_rn(acc, a3.x); acc = __fadd_rn(acc, a3.y); acc = __fadd_rn(acc, a3.z); acc = __fadd_rn(acc, a3.w);
     }
-    for (; rr < cnt; rr++) acc = __fadd_rn(acc, x[stride * rr]);
+    for (; rr < cnt; rr++) acc = __fadd_rn(acc, x[rr]);
     return acc;
 }
 
@@ -884,27 +886,33 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             // exact (or differs from either by < 2^-29), so rounding it to float equals the float sum --
             // one add per element, like the other accumulators; operands are fetched 16 at a time ahead
             // of the dependent chain of adds
-            auto add_rows = [&](const float* rows, int cnt) { acc = seq_add_strided(acc, rows + lane, 8, cnt); };
+            // Rows are handed to the adding lanes in chunks of kIcpChunk, TRANSPOSED: column c of the chunk (model x,y,z, query
+            // x,y,z, d^2) is contiguous at chunk[buf] + c * kColPitch, so lane c reads four terms per instruction.  Warps 1..
+            // fill chunk k+1 (from the staged rows in shared memory, or from global memory for large clouds) while warp 0
+            // adds chunk k.
             if (sstage) {
                 for (int v = threadIdx.x; v < 2 * num; v += blockDim.x) reinterpret_cast<float4*>(sstage)[v] = __ldcg(srows + v);
                 __syncthreads();
-                const long long ca0 = clock64();
-                if (warp == 0 && lane < 7) add_rows(sstage, num);
-                c_acc1 += clock64() - ca0;
-                __syncthreads();
-            } else {
+            }
+            auto fill = [&](int k, int first, int nthr) {
+                const int base = k * kIcpChunk, cnt = min(kIcpChunk, num - base);
+                float* cb = chunk[k & 1];
+                for (int r = first; r < cnt; r += nthr) {
+                    float4 lo, hi;
+                    if (sstage) { lo = reinterpret_cast<const float4*>(sstage)[2 * (base + r)]; hi = reinterpret_cast<const float4*>(sstage)[2 * (base + r) + 1]; }
+                    else { lo = __ldcg(srows + 2 * (size_t)(base + r)); hi = __ldcg(srows + 2 * (size_t)(base + r) + 1); }
+                    cb[r] = lo.x; cb[kColPitch + r] = lo.y; cb[2 * kColPitch + r] = lo.z; cb[3 * kColPitch + r] = lo.w;
+                    cb[4 * kColPitch + r] = hi.x; cb[5 * kColPitch + r] = hi.y; cb[6 * kColPitch + r] = hi.z;
+                }
+            };
+            {
                 const int nchunks = (num + kIcpChunk - 1) / kIcpChunk;
-                for (int v = threadIdx.x; v < 2 * min(kIcpChunk, num); v += blockDim.x) reinterpret_cast<float4*>(chunk[0])[v] = __ldcg(srows + v);
+                fill(0, threadIdx.x, blockDim.x);
                 __syncthreads();
                 const long long ca0 = clock64();
                 for (int k = 0; k < nchunks; k++) {
-                    const int cnt = min(kIcpChunk, num - k * kIcpChunk);
-                    if (warp == 0) { if (lane < 7) add_rows(chunk[k & 1], cnt); }
-                    else if (k + 1 < nchunks) {
-                        const int ncnt = min(kIcpChunk, num - (k + 1) * kIcpChunk);
-                        for (int v = threadIdx.x - 32; v < 2 * ncnt; v += blockDim.x - 32)
-                            reinterpret_cast<float4*>(chunk[(k + 1) & 1])[v] = __ldcg(srows + 2 * (size_t)(k + 1) * kIcpChunk + v);
-                    }
+                    if (warp == 0) { if (lane < 7) acc = seq_add_contig(acc, chunk[k & 1] + lane * kColPitch, min(kIcpChunk, num - k * kIcpChunk)); }
+                    else if (k + 1 < nchunks) fill(k + 1, threadIdx.x - 32, blockDim.x - 32);
                     __syncthreads();
                 }
                 c_acc1 += clock64() - ca0;
@@ -932,23 +940,24 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 // shared-memory ring while lanes 0..8 of warp 0 add block k: the dependent chain of adds
                 // is all that is left on the critical path.
                 acc = 0.0f;
-                constexpr int kProd = 336;                           // rows per ring half: 2 * 336 * 9 floats fit `chunk`
+                constexpr int kProd = 336, kProdPitch = kProd + 4;   // rows per ring half; 2 * 9 columns of 340 floats fit `chunk`; the pitch keeps the lanes' float4 reads on distinct banks
+                static_assert(2 * 9 * kProdPitch <= 2 * kIcpChunk * 8, "product ring exceeds `chunk`");
                 float* ring = &chunk[0][0];
                 const int nblk = (num + kProd - 1) / kProd;
                 const float md0 = vst->mu_d[0], md1 = vst->mu_d[1], md2 = vst->mu_d[2], mm0 = vst->mu_m[0], mm1 = vst->mu_m[1], mm2 = vst->mu_m[2];
                 auto produce = [&](int k) {
                     const int base = k * kProd, cnt = min(kProd, num - base);
-                    float* dst = ring + (k & 1) * (kProd * 9);
+                    float* dst = ring + (k & 1) * (kProdPitch * 9);
                     for (int r = threadIdx.x - 32; r < cnt; r += blockDim.x - 32) {
                         float4 lo, hi;
                         if (sstage) { lo = reinterpret_cast<const float4*>(sstage)[2 * (base + r)]; hi = reinterpret_cast<const float4*>(sstage)[2 * (base + r) + 1]; }
                         else { lo = __ldcg(srows + 2 * (size_t)(base + r)); hi = __ldcg(srows + 2 * (size_t)(base + r) + 1); }
                         const float q0 = __fsub_rn(lo.w, md0), q1 = __fsub_rn(hi.x, md1), q2 = __fsub_rn(hi.y, md2);
                         const float m0 = __fsub_rn(lo.x, mm0), m1 = __fsub_rn(lo.y, mm1), m2 = __fsub_rn(lo.z, mm2);
-                        float* d = dst + 9 * r;
-                        d[0] = __fmul_rn(q0, m0); d[1] = __fmul_rn(q0, m1); d[2] = __fmul_rn(q0, m2);
-                        d[3] = __fmul_rn(q1, m0); d[4] = __fmul_rn(q1, m1); d[5] = __fmul_rn(q1, m2);
-                        d[6] = __fmul_rn(q2, m0); d[7] = __fmul_rn(q2, m1); d[8] = __fmul_rn(q2, m2);
+                        float* d = dst + r;                                 // entry e of H: column e of the ring half
+                        d[0] = __fmul_rn(q0, m0); d[kProdPitch] = __fmul_rn(q0, m1); d[2 * kProdPitch] = __fmul_rn(q0, m2);
+                        d[3 * kProdPitch] = __fmul_rn(q1, m0); d[4 * kProdPitch] = __fmul_rn(q1, m1); d[5 * kProdPitch] = __fmul_rn(q1, m2);
+                        d[6 * kProdPitch] = __fmul_rn(q2, m0); d[7 * kProdPitch] = __fmul_rn(q2, m1); d[8 * kProdPitch] = __fmul_rn(q2, m2);
                     }
                 };
                 if (warp != 0) produce(0);
@@ -957,7 +966,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     if (warp == 0) {
                         if (lane < 9) {
                             const int cnt = min(kProd, num - k * kProd);
-                            acc = seq_add_strided(acc, ring + (k & 1) * (kProd * 9) + lane, 9, cnt);
+                            acc = seq_add_contig(acc, ring + (k & 1) * (kProdPitch * 9) + lane * kProdPitch, cnt);
                         }
                     } else if (k + 1 < nblk) produce(k + 1);
                     __syncthreads();
