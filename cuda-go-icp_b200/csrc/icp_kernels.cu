@@ -170,23 +170,26 @@ __device__ __forceinline__ int kd_nearest(const KdView& kd, const KdNode* __rest
 //  3. D1 < D2 <= D1 (1 + 1e-5): replay the reference's slab bound along the winner's root path (the
 //     bound depends on the path only): if every far-side step has bound <= D2 <= the incumbent at that
 //     moment, the reference does reach the winner's leaf, and the strictly smallest distance wins;
-//  4. exact ties (D2 == D1), a failed replay or a frontier that outgrows its queue: returns -1 and the best
-//     bound found in d2_out; the caller runs the reference walk itself (kd_nearest) capped by it.
+//  4. two points at exactly D1 (0.1 % of far queries on a 1 M-point model): the same replay, following both root paths
+//     until they part -- the point under the preferred child (same leaf: the lower position) is met first and keeps
+//     the title -- with the incumbent >= D1 until then;
+//  5. three or more exact ties, a failed replay or a frontier that outgrows its queue: returns -1 and the best bound
+//     found in d2_out; the caller runs the reference walk itself (kd_nearest) capped by it.
 // q: this warp's queue in shared memory (kCoopQ ints).  seed_pos: leaf-order position of any model
 // point (an upper bound of D1), or -1.  All lanes return the same values.
 // ------------------------------------------------------------------------------------------
-constexpr int kCoopQ = 384;
+constexpr int kCoopQ = 1024;        // ring entries per warp; frontiers of far queries on a 1 M-point model reach ~430
 __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float qx, float qy, float qz, int seed_pos, int lane, float& d2_out, int& pos_out)
 {
     const unsigned full = 0xffffffffu;
     const float kInfF = 3.402823466e+38f;
     const KdNode* __restrict__ nodes = kd.nodes; const float4* __restrict__ leaf = kd.pts_leaf;
-    float bd1 = kInfF, bd2 = kInfF, lim = kInfF; int bpos = -1;
+    float bd1 = kInfF, bd2 = kInfF, lim = kInfF; int bpos = -1, bpos2 = -1, ntie = 0;     // ntie: points at exactly bd1 seen by this lane
     if (seed_pos >= 0) {
         const float4 p = __ldg(leaf + seed_pos);
         const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
         lim = e0 * e0 + e1 * e1 + e2 * e2;
-        if (lane == 0) { bd1 = lim; bpos = seed_pos; }
+        if (lane == 0) { bd1 = lim; bpos = seed_pos; ntie = 1; }
     }
     int head = 0, tail = 1, live = 1;                  // ring positions in [0, kCoopQ); live = entries queued
     if (lane == 0) q[0] = 0;
@@ -211,7 +214,8 @@ __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float q
                         if (i == seed_pos) return;                     // already lane 0's candidate
                         const float e0 = qx - p.x, e1 = qy - p.y, e2 = qz - p.z;
                         const float dist = e0 * e0 + e1 * e1 + e2 * e2; // kdtree_distance (jly_icp3d.hpp:48-54)
-                        if (dist < bd1) { bd2 = bd1; bd1 = dist; bpos = i; }
+                        if (dist < bd1) { bd2 = bd1; bd1 = dist; bpos = i; ntie = 1; }
+                        else if (dist == bd1) { bd2 = dist; bpos2 = i; ntie++; }
                         else if (dist < bd2) bd2 = dist;
                     });
                 } else { c1 = (int)a.x; c2 = (int)a.y; }
@@ -236,13 +240,25 @@ __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float q
     float D1 = kInfF, D2 = kInfF; int p1 = 0; bool settled = false;
     if (!overflow) {
         D1 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(bd1)));
-        const int win = __ffs(__ballot_sync(full, bd1 == D1)) - 1;
+        const unsigned at_min = __ballot_sync(full, bd1 == D1);
+        const int win = __ffs(at_min) - 1;
         D2 = __uint_as_float(__reduce_min_sync(full, __float_as_uint(lane == win ? bd2 : bd1)));
         p1 = __shfl_sync(full, bpos, win);
+        const int ties = __reduce_add_sync(full, bd1 == D1 ? ntie : 0);            // points at exactly D1
+        int p2 = -1;                                                                  // the other one of a two-way exact tie
+        if (ties == 2) {
+            const int win_n = __shfl_sync(full, ntie, win);
+            const int other = win_n == 2 ? win : __ffs(at_min & (at_min - 1)) - 1;
+            p2 = __shfl_sync(full, win_n == 2 ? bpos2 : bpos, other);
+        }
         if (D2 > D1 * 1.00001f) settled = true;
-        else if (D2 > D1) {
-            // replay of the reference's bound along the root path of p1 (computeInitialDistances + searchLevel,
-            // nanoflann_goicp.hpp:1113-1184); every lane walks the same path
+        else if (D2 > D1 || ties == 2) {
+            // Replay of the reference's bound along the root path (computeInitialDistances + searchLevel,
+            // nanoflann_goicp.hpp:1113-1184); every lane walks the same path.  With a unique minimum the incumbent the
+            // reference holds when it tests a far-side step is >= D2; with two points at exactly D1 the walk follows both
+            // until their paths part -- the one under the preferred child is visited first and, strict '<', keeps the
+            // title (same leaf: the lower position) -- and the incumbent is >= D1 until that point is reached.
+            const float bound_ok = ties == 2 ? D1 : D2;
             float ds0 = 0.0f, ds1 = 0.0f, ds2 = 0.0f, cur_min = 0.0f;
             {
                 const float qq[3] = {qx, qy, qz};
@@ -257,7 +273,7 @@ __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float q
             int cur = 0; settled = true;
             for (;;) {
                 const uint4 a = __ldg(reinterpret_cast<const uint4*>(nodes + cur)), b = __ldg(reinterpret_cast<const uint4*>(nodes + cur) + 1);
-                if ((int)a.x < 0 && (int)a.y < 0) break;
+                if ((int)a.x < 0 && (int)a.y < 0) { if (p2 >= 0) p1 = min(p1, p2); break; }     // leaves are scanned in ascending position
                 const int mid = __float_as_int(__ldg(kd.boxes + 2 * (size_t)cur).w);
                 const int idx = (int)b.x; const float divlow = __uint_as_float(b.y), divhigh = __uint_as_float(b.z);
                 const float val = sel3(qx, qy, qz, idx);
@@ -265,11 +281,18 @@ __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float q
                 int bestc, otherc; float cut;
                 if ((diff1 + diff2) < 0) { bestc = (int)a.x; otherc = (int)a.y; cut = (val - divhigh) * (val - divhigh); }
                 else                     { bestc = (int)a.y; otherc = (int)a.x; cut = (val - divlow) * (val - divlow); }
-                const int target = p1 < mid ? (int)a.x : (int)a.y;
+                int target = p1 < mid ? (int)a.x : (int)a.y;
+                if (p2 >= 0) {
+                    const int target2 = p2 < mid ? (int)a.x : (int)a.y;
+                    if (target2 != target) {                             // the paths part here: the preferred child's point comes first
+                        if (target2 == bestc) { p1 = p2; target = target2; }
+                        p2 = -1;
+                    }
+                }
                 if (target == bestc) { cur = bestc; continue; }       // the preferred child is always searched
                 const float dst = sel3(ds0, ds1, ds2, idx);
                 const float m2 = cur_min + cut - dst;
-                if (!(m2 <= D2)) { settled = false; break; }           // cannot prove the reference gets here
+                if (!(m2 <= bound_ok)) { settled = false; break; }     // cannot prove the reference gets here
                 if (idx == 0) ds0 = cut; else if (idx == 1) ds1 = cut; else ds2 = cut;
                 cur_min = m2; cur = otherc;
             }
@@ -547,7 +570,7 @@ constexpr int kIcpChunk = 384;
 constexpr int kColPitch = kIcpChunk + 4;       // column pitch of a transposed chunk: 7 columns fit the 8 * kIcpChunk floats, lanes read distinct banks
 
 // dynamic shared memory plan of the ICP kernel (decided on the host)
-struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; int nn_budget; };
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; int nn_budget; int queue_bytes; };
 
 // ------------------------------------------------------------------------------------------
 // Phase B for clouds too large to rank by counting (the keys no longer fit in shared memory and
@@ -703,7 +726,6 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     __shared__ __align__(16) float chunk[2][kIcpChunk * 8];      // double buffer of the streamed (large-cloud) accumulation
     __shared__ NnPartial part;
     __shared__ int n_deferred, n_unsettled;
-    static_assert(sizeof(chunk) >= (size_t)(kIcpThreads / 32) * kCoopQ * sizeof(int), "the cooperative search's queues alias `chunk`");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIcpThreads / 32;
     const volatile IcpState* vst = st;
@@ -721,6 +743,8 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
     sp += plan.stage_bytes;
     unsigned* sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr;
+    sp += plan.radix_bytes;
+    int* squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr;             // per-warp rings of the cooperative search
     __syncthreads();
 
     long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0, c_svd = 0; const long long c_begin = clock64();
@@ -820,7 +844,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 if (pass == 1) break;
                 __syncthreads();
                 const int ndef = n_deferred;
-                int* queue = reinterpret_cast<int*>(&chunk[0][0]) + warp * kCoopQ;   // `chunk` is idle until phase C
+                int* queue = squeue + warp * kCoopQ;
                 for (int k = warp; k < ndef; k += kWarps) {
                     const int i = deferred[k];
                     const float4 p = __ldg(data + i);
@@ -838,7 +862,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 }
                 __syncthreads();
             }
-            __syncthreads();                                                         // the lists live in wk.order, the queues in `chunk`
+            __syncthreads();                                                         // the lists live in wk.order / wk.keys2
         }
         long long c1 = clock64(); c_nn += c1 - c0;
         grid.sync();
@@ -1001,9 +1025,12 @@ static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int 
     // 1 M x 1 M - / 26.3 / 16.2, bunny 40 k x 40 k 0.034 / 0.031 / 0.026: with 32 divergent walks per warp there is nearly
     // always a lane in a leaf scan or an unwind, so the warp pays the longest branch at every step; the cooperative search
     // keeps the lanes in lock step on one query.  GOICP_NN_BUDGET overrides (the parity tests force each path).
-    IcpSmemPlan p = {0, 0, 0, 0, 0, 1};
+    IcpSmemPlan p = {0, 0, 0, 0, 0, 1, 0};
     if (const char* f = getenv("GOICP_NN_BUDGET")) p.nn_budget = atoi(f);
     int left = smem_limit;
+    // models beyond the brute-force range are searched through the tree (it cannot fit in shared memory at that size):
+    // the cooperative search's per-warp rings come first
+    if (kd.nm > 16384) { p.queue_bytes = (kIcpThreads / 32) * kCoopQ * (int)sizeof(int); left -= p.queue_bytes; }
     const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
     const size_t stage = (size_t)num * 8 * sizeof(float);
     if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
@@ -1030,7 +1057,7 @@ int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int n
     cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
@@ -1046,7 +1073,7 @@ cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int 
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
                     (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&plan};
     return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args,
-                                       (size_t)plan.tree_bytes + plan.stage_bytes + plan.radix_bytes, s);
+                                       (size_t)plan.tree_bytes + plan.stage_bytes + plan.radix_bytes + plan.queue_bytes, s);
 }
 
 } // namespace goicp
