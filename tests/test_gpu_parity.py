@@ -325,6 +325,40 @@ def test_tiny_and_ragged_clouds_vs_oracle(pkg, restated, bunny, nm, nd, S, mse, 
     assert r["icp_calls"] == ref["icp_calls"] and _close_counts(r["rot_pops"], ref["rot_pops"])
 
 
+@pytest.mark.parametrize("nd,trim", [(130000, 0.0), (130000, 0.1), (70001, 0.0)])
+def test_dt_score_of_a_large_cloud_in_reference_order(pkg, restated, nd, trim):
+    """GoICP::ICP's DT re-scoring (jly_goicp.cpp:100-131) for a data cloud too large for shared memory: the residuals
+    live in global memory, and the value must still be the reference's -- intro_select's permutation followed by the
+    sequential float sum -- bit for bit.  Oracle = its DT lookups + its intro_select + a sequential float32 sum."""
+    rng = np.random.default_rng(nd)
+    model = _bumpy_surface(30000, 9)
+    data = (model[rng.choice(len(model), nd)] + rng.normal(scale=3e-3, size=(nd, 3))).astype(np.float32)
+    a = 0.05
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+    t = np.array([0.02, -0.01, 0.03], np.float32)
+    S = 64
+    dt = restated.dt_build(model, S)
+    g = pkg.GoICP(1e-3)
+    g.pModel, g.pData = model, data
+    g.dt.SIZE = S
+    g.trimFraction = trim
+    g.SetDT(restated.dt_grid(dt, S), restated.dt_meta(dt))
+    for pose in (None, (R, t)):
+        if pose is None:
+            q = data
+            got = g.DTScore()
+        else:
+            f = np.float32
+            q = np.stack([((R[r, 0] * data[:, 0] + R[r, 1] * data[:, 1]) + R[r, 2] * data[:, 2]) + t[r] for r in range(3)], 1).astype(f)
+            got = g.DTScore(R, t)
+        d = restated.dt_distance(dt, q)
+        num = int(np.float32(nd) * np.float32(1 - np.float32(trim))) if trim > 0 else nd
+        sel = restated.intro_select(d, num - 1)
+        want = np.add.accumulate((sel[:num] * sel[:num]).astype(np.float32), dtype=np.float32)[-1]
+        assert np.float32(got) == want
+    g.close()
+
+
 def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
     """the reference's own workflow: TOML -> load clouds -> DT -> Go-ICP -> output file, on the GPU"""
     for name, arr in (("model.txt", bunny["model"]), ("data.txt", bunny["data"])):
