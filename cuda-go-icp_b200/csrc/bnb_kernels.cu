@@ -5,6 +5,7 @@
 // body (jly_goicp.cpp:265-336) and GoICP::InnerBnB (jly_goicp.cpp:227-340).  Roofline: random
 // 4-byte gathers into the S^3 float grid (L2-resident at S=300, HBM at S=512); no dense
 // contraction anywhere, so no tensor cores (DESIGN.md "Kernels").
+#include <cstdio>
 #include "goicp_types.h"
 #include "goicp_kernels.h"
 #include "strict_sum.cuh"
@@ -914,6 +915,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
 // reference's intro_select + sequential float sum.  strict_pick_kernel replays the reference's
 // `if (ub < optErrorT)` over the contenders in evaluation order.
 // ------------------------------------------------------------------------------------------
+constexpr int kStrictStaticSmem = 2 * kSsWin * (int)sizeof(float) + 512;       // windows of the global-memory select + slack
 __global__ void __launch_bounds__(256)
 strict_eval_kernel(BnbConst c, const InnerTask* __restrict__ task_p, const CandList* __restrict__ cl, float* __restrict__ strict_ub,
                    float* __restrict__ gscratch, int use_smem)
@@ -936,9 +938,10 @@ strict_eval_kernel(BnbConst c, const InnerTask* __restrict__ task_p, const CandL
         m[i] = d < 0.0f ? 0.0f : d;
     }
     __syncthreads();
+    __shared__ float win[2 * kSsWin];                     // fronts of the select when the residuals live in global memory
     if (threadIdx.x == 0) {
         float ub, lb;
-        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb);
+        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb, use_smem ? nullptr : win);
         strict_ub[q] = ub;
     }
 }
@@ -976,9 +979,18 @@ dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restric
         m[i] = dt_distance(c.dt, x, y, z);
     }
     __syncthreads();
+    __shared__ float win[2 * kSsWin];                     // fronts of the select when the residuals live in global memory
     if (threadIdx.x == 0) {
         float ub, lb;
-        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb);
+#ifdef GOICP_SCORE_TRACE
+        const long long t0 = clock64();
+        if (c.do_trim) { if (!use_smem) ss_intro_select_global(m, 0, c.nd - 1, c.inlier_num - 1, win); else ss_intro_select(m, 0, c.nd - 1, c.inlier_num - 1); }
+        const long long t1 = clock64();
+        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, false, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+        printf("[dt_score] nd %d: select %lld cycles, sum %lld cycles\n", c.nd, t1 - t0, clock64() - t1);
+#else
+        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+#endif
         out[blockIdx.x] = ub;
     }
 }
@@ -1041,9 +1053,10 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
         if ((e = conf(inner_bnb_pipelined_kernel<false, false>)) != cudaSuccess) return e;
         if ((e = conf(inner_bnb_pipelined_kernel<false, true>)) != cudaSuccess) return e;
     }
-    e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
+    // both carry the select's two global-memory windows as static shared memory (strict_sum.cuh)
+    e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024 - kStrictStaticSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dt_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
+    e = cudaFuncSetAttribute(dt_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024 - kStrictStaticSmem);
     *max_dyn_out = smem_optin - stat;
     return e;
 }
@@ -1082,7 +1095,7 @@ cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, co
                                   float* d_out5, int smem_limit, cudaStream_t s)
 {
     const size_t need = (size_t)c.nd * sizeof(float);
-    const int use_smem = need <= (size_t)smem_limit ? 1 : 0;
+    const int use_smem = need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0;
     strict_eval_kernel<<<kMaxCand, 256, use_smem ? need : 0, s>>>(c, d_task, d_list, d_strict, d_scratch, use_smem);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1093,7 +1106,7 @@ cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d
 {
     if (nposes <= 0) return cudaSuccess;
     const size_t need = (size_t)c.nd * sizeof(float);
-    const int use_smem = need <= (size_t)smem_limit ? 1 : 0;
+    const int use_smem = need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0;
     dt_score_kernel<<<nposes, kBnbThreads, use_smem ? need : 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out, use_smem);
     return cudaGetLastError();
 }

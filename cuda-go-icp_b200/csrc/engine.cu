@@ -535,7 +535,7 @@ int share_cand_list(goicp_handle* h, std::shared_ptr<CandList>& cl)
 int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, const CandList& list, float* value, float* node4)
 {
     struct Acc { double& a; double t0; ~Acc() { a += now_s() - t0; } } acc{h->t_strict, now_s()};
-    const size_t scratch = (size_t)h->nd * sizeof(float) <= (size_t)(h->max_smem_optin - 2048) ? 0 : (size_t)kMaxCand * h->nd;
+    const size_t scratch = (size_t)h->nd * sizeof(float) + 20480 <= (size_t)(h->max_smem_optin - 2048) ? 0 : (size_t)kMaxCand * h->nd;      // conservative: the kernel decides with its own static size
     CUDA_TRY(h, h->d_strict.reserve(256 + scratch));
     CUDA_TRY(h, h->d_tasks.reserve(1)); CUDA_TRY(h, h->d_cands.reserve(1));
     InnerTask* d_task = h->d_tasks.p + (h->d_tasks.n - 1);          // last slots are reserved for this
