@@ -52,8 +52,8 @@ WORKLOADS = {
 }
 
 
-# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1e_ncu_full_selected.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.7e6}
+# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1h_ncu_full_selected.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.6e6}
 
 
 def load(name):
@@ -365,7 +365,7 @@ def main():
     lookups = executed * len(data)
     achieved = lookups * 32 / kern_s / 1e9
     roofline = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1e_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1h_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
                 "algorithmic_bytes_per_launch": lookups * 32 / max(1, sum(r["rounds"] for r in results)), "peak_source": peak_src,
                 "basis": "32 B sector per DT lookup (SURVEY 8d); lookups = executed bound evals * Nd; 300^3 fp32 DT (108 MB) is L2-resident",
                 "launches": int(sum(r["rounds"] for r in results)), "avg_launch_ms": 1e3 * kern_s / max(1, sum(r["rounds"] for r in results)),
