@@ -984,6 +984,20 @@ int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void
     if (shard_exchange(fn, user, world, n, mine.data(), (int)mine.size(), all.data()) != 0) return GOICP_ERR_INVALID;
     int bad = 0;
     for (int t = 0; t < n; t++) { InnerResult e = fake(t); if (std::memcmp(&e, &all[t], sizeof e) != 0) bad++; }
+    // the hand-round of an upper-bound pass's contender list (share_cand_list): whoever holds it, every rank ends with it
+    {
+        goicp_handle* h = new goicp_handle();
+        h->p.world_size = world; h->p.rank = rank; h->xchg = fn; h->xchg_user = user;
+        auto pattern = [](int owner) { auto cl = std::make_shared<CandList>(); std::memset(cl.get(), 0, sizeof(CandList));
+                                       cl->n = 3 + owner; cl->flags = 0x55u + owner; cl->final_fast = 1.5f * owner; cl->eps = 1e-6f;
+                                       for (int q = 0; q < cl->n; q++) { cl->node[q] = make_float4(0.25f * q, -0.5f * owner, 0.125f, 1.0f / (q + 1)); cl->ub[q] = 10.0f + q + owner; }
+                                       return cl; };
+        for (int owner = 0; owner < world; owner++) {
+            std::shared_ptr<CandList> cl = rank == owner ? pattern(owner) : nullptr;
+            if (share_cand_list(h, cl) != GOICP_OK || !cl || std::memcmp(cl.get(), pattern(owner).get(), sizeof(CandList)) != 0) bad++;
+        }
+        delete h;
+    }
     *mismatches = bad;
     return GOICP_OK;
 }

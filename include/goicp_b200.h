@@ -205,7 +205,8 @@ int goicp_set_exchange(goicp_handle* h, goicp_allgather_fn fn, void* user, int u
 int goicp_nccl_unique_id(void* id128_out);
 int goicp_nccl_init(goicp_handle* h, const void* id128, int rank, int world_size);
 
-/* Host-only self test of the sharding + exchange plumbing used by multi-GPU rounds (no GPU needed). */
+/* Host-only self test of the sharding + exchange plumbing used by multi-GPU rounds (no GPU needed): the round-robin
+ * deal and all-gather of n result records, and the hand-round of a contender list from each rank in turn. */
 int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void* user, int* mismatches);
 
 /* Convenience driver over the reference's TOML keys (src/common.cpp:39-74) and cloud formats

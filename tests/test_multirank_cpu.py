@@ -1,5 +1,6 @@
 """world_size=2 test of the multi-GPU plumbing on CPU (gloo): the round-robin task sharding and the
-all-gather exchange that merges every rank's inner-BnB results."""
+all-gather exchange that merges every rank's inner-BnB results, and the hand-round of a contender list from each
+rank in turn."""
 import os
 import subprocess
 import sys
