@@ -748,17 +748,25 @@ int goicp_build_dt(goicp_handle* h)
         // (DESIGN.md section 5), so that refinement runs here, on the other SMs, while the DT is being built: the DT
         // build goes to its own stream on a helper thread, this thread builds the kd-tree and drives the ICP kernel
         // (capped to the SMs the DT leaves free, so that the cooperative launch can be resident next to it).
-        std::thread worker([&]() {
-            cudaSetDevice(h->p.device);
-            e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream_dt, msg);
-        });
-        const float R0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0, 0, 0};
-        const double tr1 = now_s();
-        const int rc_icp = run_icp(h, R0, t0, h->p.icp_max_iter, h->p.mse_threshold / 10000, &h->icp0, std::max(1, h->sm_count - 1));
-        if (trace) fprintf(stderr, "[dt trace] overlapped ICP (upload + kd-tree + kernel) %.3f ms\n", 1e3 * (now_s() - tr1));
-        worker.join();
-        h->icp0_valid = rc_icp == GOICP_OK;           // a failed head start is not a failed DT build: Register runs that ICP itself
-        if (rc_icp) h->err.clear();
+        std::thread worker;
+        bool threaded = true;
+        try {
+            worker = std::thread([&]() {
+                cudaSetDevice(h->p.device);
+                e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream_dt, msg);
+            });
+        } catch (...) { threaded = false; }                 // no thread to be had: build the DT here, no head start
+        if (threaded) {
+            const float R0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0, 0, 0};
+            const double tr1 = now_s();
+            const int rc_icp = run_icp(h, R0, t0, h->p.icp_max_iter, h->p.mse_threshold / 10000, &h->icp0, std::max(1, h->sm_count - 1));
+            if (trace) fprintf(stderr, "[dt trace] overlapped ICP (upload + kd-tree + kernel) %.3f ms\n", 1e3 * (now_s() - tr1));
+            worker.join();
+            h->icp0_valid = rc_icp == GOICP_OK;           // a failed head start is not a failed DT build: Register runs that ICP itself
+            if (rc_icp) h->err.clear();
+        } else {
+            e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
+        }
     } else {
         e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
     }

@@ -105,9 +105,14 @@ int Builder::divide(int left, int right, float* lo, float* hi, int leaf_max, int
     std::memcpy(llo, lo, sizeof llo); std::memcpy(lhi, hi, sizeof lhi); lhi[axis] = cut;
     std::memcpy(rlo, lo, sizeof rlo); std::memcpy(rhi, hi, sizeof rhi); rlo[axis] = cut;
     int c1, c2;
-    if (depth < 3 && count - split >= 16384) {
-        Builder right_b{pts, vind, {}, {}};
-        std::thread worker([&]() { right_b.divide(left + split, right, rlo, rhi, leaf_max, depth + 1); });
+    std::thread worker;
+    bool threaded = depth < 3 && count - split >= 16384;
+    Builder right_b{pts, vind, {}, {}};
+    if (threaded) {
+        try { worker = std::thread([&]() { right_b.divide(left + split, right, rlo, rhi, leaf_max, depth + 1); }); }
+        catch (...) { threaded = false; }                            // no thread to be had: build it here
+    }
+    if (threaded) {
         c1 = divide(left, left + split, llo, lhi, leaf_max, depth + 1);
         worker.join();
         c2 = (int)nodes.size();                                      // splice: the right block follows the left one
