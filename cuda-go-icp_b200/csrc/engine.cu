@@ -301,6 +301,24 @@ KdView kd_view(const goicp_handle* h)
     KdView v;
     v.nodes = h->d_kd_nodes.p; v.boxes = h->d_kd_boxes.p; v.vind = h->d_kd_vind.p; v.pts_leaf = h->d_kd_leaf.p; v.model = h->d_model.p; v.nm = h->nm;
     for (int i = 0; i < 3; i++) { v.bb_lo[i] = h->kd_host.bb_lo[i]; v.bb_hi[i] = h->kd_host.bb_hi[i]; }
+    // the 32 nodes five levels down, when every node above them is interior: the first five rounds of a breadth-first
+    // search from the root would keep 1, 2, 4, 8, 16 lanes busy
+    v.n_top = 0;
+    {
+        std::vector<int> cur{0};
+        bool ok = !h->kd_host.nodes.empty();
+        for (int d = 0; d < 5 && ok; d++) {
+            std::vector<int> next;
+            for (int n : cur) {
+                const KdNode& k = h->kd_host.nodes[n];
+                if (k.child1 < 0 || k.child2 < 0) { ok = false; break; }
+                next.push_back(k.child1); next.push_back(k.child2);
+            }
+            if (ok) cur.swap(next);
+        }
+        if (ok && cur.size() == 32) { v.n_top = 32; for (int i = 0; i < 32; i++) v.top[i] = cur[i]; }
+        else for (int i = 0; i < 32; i++) v.top[i] = 0;
+    }
     return v;
 }
 

@@ -33,6 +33,7 @@ struct KdView {
                                            // the first leaf-order position of child2's points (kdtree_host.cpp); may be null
     int nm;
     float bb_lo[3], bb_hi[3];
+    int n_top; int top[32];                // the nodes five levels below the root (n_top = 32), or n_top = 0: where the cooperative search's frontier starts
 };
 struct IcpState {           // lives in device memory; written by block 0 of the ICP kernel
     float R[9], t[3];

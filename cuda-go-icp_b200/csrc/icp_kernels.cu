@@ -192,7 +192,8 @@ __device__ __forceinline__ int kd_coop_nearest(const KdView& kd, int* q, float q
         if (lane == 0) { bd1 = lim; bpos = seed_pos; ntie = 1; }
     }
     int head = 0, tail = 1, live = 1;                  // ring positions in [0, kCoopQ); live = entries queued
-    if (lane == 0) q[0] = 0;
+    if (kd.n_top == 32) { q[lane] = kd.top[lane]; tail = live = 32; }     // start five levels down: a full round at once
+    else if (lane == 0) q[0] = 0;
     __syncwarp();
     bool overflow = false;
     while (live > 0) {
