@@ -3,25 +3,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One "step" = one full Go-ICP registration (GoICP::Register: nested rotation/translation
-branch-and-bound + ICP refinements) of the workload's data cloud against its model cloud.
+One "step" = one full Go-ICP registration (GoICP::Register: nested rotation/translation branch-and-bound + ICP
+refinements) of the workload's data cloud against its model cloud.  Every key means what it says:
 
-  value   bound evaluations per second with model/data/DT already resident in HBM when the timed
-          region starts (goicp_register on a warm handle); counts the COMMITTED evaluations, i.e.
-          the ones the sequential reference performs too (speculative extra work is not credited).
-  e2e     same metric through the C ABI from HOST buffers: goicp_create + set_model + set_data
-          (H2D) + build_dt (GPU, reference-exact mode) + register + result read-back, all timed.
-  roofline  dominant kernel = inner_bnb_kernel (persistent translation BnB).  Algorithmic bytes =
-          DT lookups * 32 B sector, lookups = executed evals * Nd; duration = CUDA
-          events around its launches on the launching stream.  `gather` sub-object: the pure
-          DT-gather kernel (expand_bounds) at full occupancy, same accounting.
-  cpu_baseline  the unmodified reference (oracle/_ref) or its C restatement timed on ONE host core
-          (the reference is single-threaded) for a bounded sample of the same workload.
+  value     committed bound evaluations per second of goicp_register on a warm handle -- model, data, kd-tree and DT
+            resident in HBM when the timed region starts.  "Committed" = the evaluations the sequential reference
+            performs too; speculative extra work is not credited.
+  e2e       the same metric through the C ABI from HOST buffers, in the library's default configuration: goicp_create +
+            set_model + set_data (H2D) + build_dt + register + result read-back, all inside the timed region; the byte
+            counts are the library's own (goicp_transfer_bytes).  `e2e_reference_dt` = the same with the reference-order
+            DT propagation (GOICP_DT_REFERENCE) instead of the default exact EDT.
+  certified the same clouds at mse 5e-4, where the search ends through the global-optimality certificate
+            (time-to-CERTIFIED-optimum; the TOML's own 1e-3 ends through `optError < SSEThresh`).
+  roofline  dominant kernel = the persistent translation BnB.  achieved = DT look-ups this GPU executed * 32 B (one
+            sector per scattered 4-byte gather) / the kernel time on the launching stream (CUDA events).
+            peak = the MEASURED random-gather rate over a buffer of the grid's size (goicp_measure_gather: nothing but
+            the loads) when the grid fits L2, MEASURED_PEAKS.json's HBM copy rate otherwise.  `traffic` comes from the
+            committed ncu capture named in `traffic_source`.
+  cpu_baseline  the unmodified reference (oracle/_ref) or its C restatement on ONE host core (the reference is
+            single-threaded) for a bounded sample of the same workload.
 
---impl reference runs only that CPU arm and prints the same JSON shape.
-Multi-GPU (torchrun, N>1): the rotation frontier of ONE registration is sharded across ranks;
-per round every rank runs its slice of the inner BnBs and the results are all-gathered
-(torch.distributed, NCCL) -- strong scaling.
+--impl reference runs only that CPU arm: `value` = its Register-only rate (the span of our `value`), `e2e` = DT build +
+Register (the span of our `e2e`).  Multi-GPU (torchrun, N>1): the rotation frontier of ONE registration is sharded across
+the ranks, results all-gathered by NCCL on the engine stream -- strong scaling; roofline numbers are rank 0's own GPU.
 """
 from __future__ import annotations
 
@@ -45,19 +49,52 @@ WORKLOADS = {
     # BASELINE.json configs[0]: test/bunny_goicp.toml (subsample 0.1, mse 1e-3, S=300, trim 0),
     # clouds = the committed deterministic subsamples (seeds 1234/1235) of the reference's bunny.
     "bunny_goicp_toml": dict(model="bunny_model_s0.1_seed1234.f32", data="bunny_data_s0.1_seed1235.f32", mse=1e-3, S=300,
-                             ref_register_s=47.5, ref_evals=235552),
+                             ref_register_s=47.5, ref_evals=235552, certified_mse=5e-4),
     # same clouds, tighter threshold: exits through the global-optimality certificate
     "bunny_goicp_certified": dict(model="bunny_model_s0.1_seed1234.f32", data="bunny_data_s0.1_seed1235.f32", mse=5e-4, S=300,
                                   ref_register_s=338.6, ref_evals=1696656),
+    # BASELINE.json configs[4]: synthetic sweep point -- throughput-bound regime (one bound evaluation = 1e5 look-ups into a
+    # 537 MB grid that does not fit L2).  Seeds fixed: model 1, data 2, pose 3.
+    "sweep_100k": dict(synth=dict(nm=1_000_000, nd=100_000), mse=1e-4, S=512, ref_register_s=None, ref_evals=None),
+    "sweep_10k": dict(synth=dict(nm=100_000, nd=10_000), mse=1e-4, S=300, ref_register_s=None, ref_evals=None),
 }
+KERNEL_NAMES = {1: "inner_bnb_pipelined_kernel<1,1>", 2: "inner_bnb_pipelined_kernel<1,0>", 4: "inner_bnb_pipelined_kernel<0,1>",
+                8: "inner_bnb_pipelined_kernel<0,0>", 16: "inner_bnb_kernel"}
+L2_BYTES = 126 * 1000 * 1000
 
 
-# DRAM bytes per inner_bnb launch from the committed `ncu --set full` capture (profiles/r1h_ncu_full_selected.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"bunny_goicp_toml": 47.6e6}
+def synth(nm, nd, seed_model=1, seed_data=2, seed_pose=3, sigma=1e-3):
+    """closed star-shaped surface r(u) = 0.33 + low-order bumps, scaled into [-0.5,0.5]^3; data = noisy subset moved by
+    the inverse of a random rigid motion (rotation uniform on SO(3), |t|_inf <= 0.3)  (SURVEY.md 8d, config 5)."""
+    rng = np.random.default_rng(seed_model)
+    u = rng.normal(size=(nm, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    k = rng.normal(size=(6, 3)); ph = rng.uniform(0, 2 * np.pi, 6); amp = rng.uniform(0.02, 0.06, 6)
+    r = 0.33 + sum(a * np.sin(3 * (u @ kk) + p) for a, kk, p in zip(amp, k, ph))
+    model = (u * r[:, None])
+    model *= 0.5 / np.abs(model).max()
+    rd = np.random.default_rng(seed_data)
+    pick = rd.choice(nm, nd, replace=nd > nm)
+    pts = model[pick] + rd.normal(scale=sigma, size=(nd, 3))
+    rp = np.random.default_rng(seed_pose)
+    q = rp.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    t = rp.uniform(-0.3, 0.3, 3)
+    data = (pts - t) @ R            # data = R^T (p - t)  =>  R data + t = p
+    return model.astype(np.float32), data.astype(np.float32), R.astype(np.float32), t.astype(np.float32)
 
 
 def load(name):
     return np.fromfile(os.path.join(GOLDEN, name), np.float32).reshape(-1, 3)
+
+
+def clouds_of(wl):
+    if "synth" in wl:
+        m, d, _, _ = synth(wl["synth"]["nm"], wl["synth"]["nd"])
+        return m, d
+    return load(wl["model"]), load(wl["data"])
 
 
 class ClockSampler(threading.Thread):
@@ -84,8 +121,7 @@ class ClockSampler(threading.Thread):
     def finish(self):
         self.stop_flag = True
         if self.proc:
-            # nvidia-smi polling holds the driver lock now and then: cudaMalloc/cudaFree of the e2e
-            # passes that follow stalled for up to 0.5 s while it was still exiting -- wait for it
+            # nvidia-smi polling holds the driver lock now and then: wait for it to be gone before the e2e passes
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=10)
@@ -103,38 +139,47 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_sample(wl, seconds):
-    """Bound evaluations per second of the reference CPU Go-ICP (1 thread) over ~`seconds` of its
-    Register() on this workload.  Uses oracle/_ref (unmodified reference) when built, else the C
-    restatement.  The DT is built first (timed separately, not part of the rate)."""
+class _Quiet:
+    """the reference narrates on stdout: keep bench.py's single JSON line clean"""
+
+    def __enter__(self):
+        self.devnull = os.open(os.devnull, os.O_WRONLY)
+        self.saved = os.dup(1)
+        sys.stdout.flush()
+        os.dup2(self.devnull, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.devnull)
+
+
+def cpu_reference_sample(wl, seconds, model=None, data=None):
+    """Bound evaluations per second of the reference CPU Go-ICP (1 thread) over ~`seconds` of its Register() on this
+    workload.  Uses oracle/_ref (unmodified reference) when built, else the C restatement.  The DT is built first (timed
+    separately, not part of the rate)."""
     from oracle import oracle as orc
-    model, data = load(wl["model"]), load(wl["data"])
+    if model is None:
+        model, data = clouds_of(wl)
     if orc.Reference.available():
         rf = orc.Reference()
         g = rf.create(model, data, wl["mse"], 0.0, wl["S"])
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(1)
-        sys.stdout.flush()
-        os.dup2(devnull, 1)                     # the reference narrates on stdout
-        try:
+        with _Quiet():
             dt_s = rf.build_dt(g)
             counter = ctypes.c_longlong.in_dll(rf.L, "ref_select_calls")
             stop = ctypes.c_bool.in_dll(rf.L, "goicp_finished")
             stop.value = False
             th = threading.Thread(target=rf.register, args=(g,), daemon=True)
-            c0, t0 = counter.value, time.perf_counter()
             th.start()
+            time.sleep(min(1.0, seconds / 10))           # past Initialize (kd-tree build) and the first ICP
+            c0, t0 = counter.value, time.perf_counter()
             th.join(seconds)
             c1, t1 = counter.value, time.perf_counter()
             stop.value = True                   # the reference's own cooperative exit (jly_goicp.cpp:400)
-            th.join(120)
+            th.join(600)
             stop.value = False
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(devnull)
-        return {"value": (c1 - c0) / (t1 - t0), "unit": "bound-evals/s", "cores": 1, "kind": "reference",
-                "sample": f"first {t1 - t0:.1f} s of GoICP::Register on {wl['data']} (Nd={len(data)}), DT build excluded ({dt_s:.1f} s)",
+        return {"value": (c1 - c0) / max(t1 - t0, 1e-9), "unit": "bound-evals/s", "cores": 1, "kind": "reference",
+                "sample": f"{t1 - t0:.1f} s of GoICP::Register on Nd={len(data)}, Nm={len(model)}, S={wl['S']} (after its first second); DT build excluded ({dt_s:.1f} s)",
                 "dt_build_s": dt_s}
     rs = orc.Restated()
     g = rs.create(model, data, wl["mse"], 0.0, wl["S"])
@@ -142,32 +187,23 @@ def cpu_reference_sample(wl, seconds):
     rs.L.go_set_budget(g, float(seconds))
     r = rs.register(g)
     return {"value": r["bound_evals"] / r["register_s"], "unit": "bound-evals/s", "cores": 1, "kind": "port",
-            "sample": f"first {r['register_s']:.1f} s of the restated Register on {wl['data']} (Nd={len(data)}), DT build excluded ({dt_s:.1f} s)",
+            "sample": f"first {r['register_s']:.1f} s of the restated Register on Nd={len(data)}, Nm={len(model)}, S={wl['S']}; DT build excluded ({dt_s:.1f} s)",
             "dt_build_s": dt_s}
 
 
 def cpu_reference_job(wl):
-    """One whole job of the reference CPU Go-ICP on this workload: DT build + full Register, timed
-    separately (oracle/_ref when built, else the C restatement)."""
+    """One whole job of the reference CPU Go-ICP on this workload: DT build + full Register, timed separately."""
     from oracle import oracle as orc
-    model, data = load(wl["model"]), load(wl["data"])
+    model, data = clouds_of(wl)
     if orc.Reference.available():
         rf = orc.Reference()
         g = rf.create(model, data, wl["mse"], 0.0, wl["S"])
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        saved = os.dup(1)
-        sys.stdout.flush()
-        os.dup2(devnull, 1)                     # the reference narrates on stdout
-        try:
+        with _Quiet():
             dt_s = rf.build_dt(g)
             counter = ctypes.c_longlong.in_dll(rf.L, "ref_select_calls")
             c0, t0 = counter.value, time.perf_counter()
             rf.register(g)
             c1, t1 = counter.value, time.perf_counter()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(devnull)
         return {"kind": "reference", "dt_build_s": dt_s, "register_s": t1 - t0, "job_s": dt_s + (t1 - t0),
                 "register_rate": wl["ref_evals"] / (t1 - t0), "select_calls": c1 - c0}
     rs = orc.Restated()
@@ -176,6 +212,19 @@ def cpu_reference_job(wl):
     r = rs.register(g)
     return {"kind": "port", "dt_build_s": dt_s, "register_s": r["register_s"], "job_s": dt_s + r["register_s"],
             "register_rate": r["bound_evals"] / r["register_s"], "select_calls": r["bound_evals"]}
+
+
+def ncu_traffic(workload, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed summary of an
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by scripts/summarise_profiles.py)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t[workload]
+        if e["kernel"].startswith(kernel_prefix.split("<")[0]):
+            return e["dram_bytes_per_launch"], e["source"]
+    except Exception:
+        pass
+    return None, None
 
 
 def main():
@@ -187,55 +236,65 @@ def main():
     ap.add_argument("--workload", default="bunny_goicp_toml", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the certified / reference-DT / gather side measurements")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": args.workload, "model": wl["model"], "data": wl["data"], "Nd": None, "Nm": None, "dt_size": wl["S"],
-              "mse_threshold": wl["mse"], "trim": 0.0, "l2": "flushed between timed steps (256 MiB write)"}
+    config = {"workload": args.workload, "model": wl.get("model", "synthetic closed surface, seed 1"), "data": wl.get("data", "noisy subset under a random SE(3), seeds 2/3"),
+              "Nd": None, "Nm": None, "dt_size": wl["S"], "mse_threshold": wl["mse"], "trim": 0.0,
+              "dt_mode": "exact EDT + reference corner seed (library default)", "numerics": "strict (reference-order sums, reference ICP arithmetic)",
+              "l2": "flushed between timed steps (256 MiB write)"}
 
     # ------------------------------------------------------------------ reference arm ---------
     if args.impl == "reference":
         if rank != 0:
             return
-        # One step = the whole job the GPU arm's e2e times: DT build + Register of the workload, by the
-        # reference's own CPU code (1 thread: src/goicp has no threading).  A full bunny job is ~30 s
-        # on the B200 host, so steps are capped to a ~200 s budget (at least one); a workload whose
-        # full job does not fit (the certified one, ~6 min) is sampled for --cpu-seconds of Register
-        # and the whole-job figure is derived from its known evaluation count (flagged).
-        config.update(Nd=len(load(wl["data"])), Nm=len(load(wl["model"])))
+        # One step = the whole job the GPU arm's e2e times: DT build + Register of the workload, by the reference's own CPU
+        # code (1 thread: src/goicp has no threading).  A full bunny job is ~30 s on the B200 host, so steps are capped to a
+        # ~200 s budget (at least one); a workload whose full job does not fit is sampled for --cpu-seconds of Register.
+        model, data = clouds_of(wl)
+        config.update(Nd=len(data), Nm=len(model), dt_mode="reference (DT3D::Build)", numerics="reference")
         budget_s, steps, t_begin = 200.0, [], time.perf_counter()
-        full = wl["ref_register_s"] < 120.0
+        full = wl["ref_register_s"] is not None and wl["ref_register_s"] < 120.0
         while len(steps) < max(1, args.steps):
-            st = cpu_reference_job(wl) if full else cpu_reference_sample(wl, args.cpu_seconds)
+            st = cpu_reference_job(wl) if full else cpu_reference_sample(wl, args.cpu_seconds, model, data)
             steps.append(st)
             spent = time.perf_counter() - t_begin
             if spent + spent / len(steps) > budget_s:
                 break
         if full:
             job_s = float(np.mean([s["job_s"] for s in steps]))
-            v = wl["ref_evals"] / job_s
+            reg_s = float(np.mean([s["register_s"] for s in steps]))
             reg_rate = float(np.mean([s["register_rate"] for s in steps]))
+            e2e_v = wl["ref_evals"] / job_s
             sample = (f"{len(steps)} full job(s): DT build {np.mean([s['dt_build_s'] for s in steps]):.1f} s + GoICP::Register "
-                      f"{np.mean([s['register_s'] for s in steps]):.1f} s, {wl['ref_evals']} bound evaluations each")
+                      f"{reg_s:.1f} s, {wl['ref_evals']} bound evaluations each")
             span = "measured"
         else:
             reg_rate = float(np.mean([s["value"] for s in steps]))
             dt_s = float(np.mean([s["dt_build_s"] for s in steps]))
-            job_s = dt_s + wl["ref_evals"] / reg_rate
-            v = wl["ref_evals"] / job_s
-            sample = steps[-1]["sample"] + f"; whole job derived: DT {dt_s:.1f} s + {wl['ref_evals']} evals / measured rate"
-            span = "derived from a bounded sample"
-        base = {"value": v, "unit": "bound-evals/s", "cores": 1, "kind": steps[-1]["kind"], "sample": sample,
-                "span": "DT build + Register (the span of the GPU arm's e2e), " + span,
-                "register_only_bound_evals_per_s": reg_rate, "job_seconds": job_s}
-        print(json.dumps({"impl": "reference", "metric": "goicp_bound_evals_per_sec", "value": v, "unit": "bound-evals/s",
-                          "n_gpus": 0, "steps": len(steps), "warmup": 0, "ms_per_step": 1e3 * job_s,
+            if wl["ref_evals"]:
+                reg_s = wl["ref_evals"] / reg_rate
+                job_s = dt_s + reg_s
+                e2e_v = wl["ref_evals"] / job_s
+                sample = steps[-1]["sample"] + f"; whole job derived: DT {dt_s:.1f} s + {wl['ref_evals']} evals / measured rate"
+                span = "derived from a bounded sample"
+            else:
+                reg_s, job_s, e2e_v = None, None, reg_rate
+                sample = steps[-1]["sample"] + "; the reference cannot finish this workload: rate only"
+                span = "rate of a bounded sample (no whole job)"
+        base = {"value": reg_rate, "unit": "bound-evals/s", "cores": 1, "kind": steps[-1]["kind"], "sample": sample,
+                "span": "GoICP::Register only (the span of the GPU arm's `value`); e2e = DT build + Register, " + span,
+                "register_seconds": reg_s, "job_seconds": job_s}
+        print(json.dumps({"impl": "reference", "metric": "goicp_bound_evals_per_sec", "value": reg_rate, "unit": "bound-evals/s",
+                          "n_gpus": 0, "steps": len(steps), "warmup": 0, "ms_per_step": None if reg_s is None else 1e3 * reg_s,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                          "data": "reference bunny scans, deterministic subsample (committed fixtures)", "config": config,
-                          "time_to_optimum_s": job_s, "cpu_baseline": base,
-                          "e2e": {"value": v, "unit": "bound-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                          "data": "reference bunny scans, deterministic subsample (committed fixtures)" if "synth" not in wl else "synthetic (seeded)",
+                          "config": config, "time_to_optimum_s": reg_s, "cpu_baseline": base,
+                          "e2e": {"value": e2e_v, "unit": "bound-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                  "seconds_per_step": job_s}}))
         return
 
     # ------------------------------------------------------------------ our arm ---------------
@@ -247,7 +306,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl")
     pkg = importlib.import_module("cuda-go-icp_b200")
-    model, data = load(wl["model"]), load(wl["data"])
+    model, data = clouds_of(wl)
     config.update(Nd=len(data), Nm=len(model))
 
     nccl_id = None
@@ -258,10 +317,12 @@ def main():
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().numpy().tobytes())
 
-    def make_engine():
-        g = pkg.GoICP(wl["mse"], device=local_rank)
+    def make_engine(mse=None, dt_mode=None):
+        g = pkg.GoICP(wl["mse"] if mse is None else mse, device=local_rank)
         g.pModel, g.pData = model, data
         g.dt.SIZE = wl["S"]
+        if dt_mode is not None:
+            g.dt_mode = dt_mode
         if world > 1 and os.environ.get("GOICP_EXCHANGE", "nccl") == "nccl":
             g.init_nccl(nccl_id, rank, world)          # native: ncclAllGather on the engine's stream (include/goicp_b200.h)
         elif world > 1:
@@ -280,122 +341,167 @@ def main():
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    # resident engine: DT built once (reference-exact mode), then timed Register() steps
-    eng = make_engine()
-    t0 = time.perf_counter(); eng.BuildDT(); torch.cuda.synchronize(); dt_build_s = time.perf_counter() - t0
-    for _ in range(max(3, args.warmup)):
-        eng.Register()
-    sampler = ClockSampler(local_rank); sampler.start()
-    step_s, results = [], []
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    for _ in range(args.steps):
-        flush.zero_(); torch.cuda.synchronize()
+    def barrier():
         if world > 1:
             dist.barrier()
-        t0 = time.perf_counter()
+
+    def timed_registers(eng, steps, warm):
+        """`steps` timed goicp_register calls on a warm handle, L2 flushed before each; returns (max-over-ranks seconds, results)"""
+        for _ in range(warm):
+            eng.Register()
+        barrier(); torch.cuda.synchronize()
+        secs, results = 0.0, []
+        for _ in range(steps):
+            flush.zero_(); torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            eng.Register()
+            torch.cuda.synchronize()
+            secs += time.perf_counter() - t0
+            results.append(eng.result)
+        t = torch.tensor([secs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), results
+
+    def timed_e2e(n, warm, mse=None, dt_mode=None):
+        """create + H2D + build_dt + register + read-back through the C ABI from host buffers; median seconds, parts, bytes, evals"""
+        samples, parts, nbytes, evals, exit_path = [], [], (0, 0), 0, None
+        for it in range(n + warm):
+            flush.zero_(); torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            g = make_engine(mse, dt_mode)
+            g.BuildDT()
+            t1 = time.perf_counter()
+            g.Register()
+            _ = (g.optR.copy(), g.optT.copy(), g.optError)
+            t2 = time.perf_counter()
+            if it >= warm:
+                samples.append(t2 - t0); parts.append((t1 - t0, t2 - t1))
+            nbytes, evals, exit_path = g.TransferBytes(), g.result["bound_evals"], g.result["exit_path"]
+            g.close()
+        med = float(np.median(samples))
+        return {"value": evals / med, "unit": "bound-evals/s", "h2d_bytes_per_step": int(nbytes[0]), "d2h_bytes_per_step": int(nbytes[1]),
+                "bytes_source": "goicp_transfer_bytes (every copy the library issued for the step)",
+                "seconds_per_step": med, "seconds_per_step_samples": [round(x, 5) for x in samples], "statistic": "median",
+                "seconds_create_h2d_dt_build": float(np.median([p[0] for p in parts])),
+                "seconds_register_and_readback": float(np.median([p[1] for p in parts])), "exit_path": exit_path, "bound_evals": int(evals)}
+
+    # ---- resident engine (library defaults), timed Register() steps
+    eng = make_engine()
+    t0 = time.perf_counter(); eng.BuildDT(); torch.cuda.synchronize(); dt_build_s = time.perf_counter() - t0
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         eng.Register()
-        torch.cuda.synchronize()
-        step_s.append(time.perf_counter() - t0)
-        results.append(eng.result)
+    sampler = ClockSampler(local_rank); sampler.start()
+    total_s, results = timed_registers(eng, args.steps, 0)
     clocks = sampler.finish()
-    t = torch.tensor([sum(step_s)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_s = float(t.item())
     res = results[-1]
     evals = sum(r["bound_evals"] for r in results)
     executed = sum(r["bound_evals_executed"] for r in results)
+    executed_local = sum(r["bound_evals_executed_local"] for r in results)
     kern_s = sum(r["seconds_bnb_kernels"] for r in results)
     launches = sum(r["kernel_launches"] for r in results)
+    rounds = int(sum(r["rounds"] for r in results))
     value = evals / total_s
 
-    # e2e: everything through the C ABI from host buffers, per step (rank 0's clock; all ranks participate)
-    e2e_s = []
-    e2e_parts = []
+    # ---- e2e through the C ABI from host buffers, default configuration
     n_e2e = max(3, min(args.steps, 5))
-    n_e2e_warm = 2                              # untimed passes: the 1-CTA DT kernel only reaches steady speed after ~2 s of activity
-    for it in range(n_e2e + n_e2e_warm):
-        flush.zero_(); torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        g = make_engine()
-        g.BuildDT()
-        t1 = time.perf_counter()
-        g.Register()
-        _ = (g.optR.copy(), g.optT.copy(), g.optError)
-        t2 = time.perf_counter()
-        if os.environ.get("BENCH_DEBUG"):
-            print(f"[e2e {it}] create+dt {t1 - t0:.4f} register {t2 - t1:.4f} internal {g.result['seconds_total']:.4f} bnb {g.result['seconds_bnb_kernels']:.4f} icp {g.result['seconds_icp']:.4f}", file=sys.stderr, flush=True)
-        if it >= n_e2e_warm:
-            e2e_s.append(t2 - t0)
-            e2e_parts.append((t1 - t0, t2 - t1))
-        e2e_evals = g.result["bound_evals"]
-        g.close()
-    # median over the timed passes: the single-CTA DT propagation runs at the SM clock, and an occasional pass
-    # catches the GPU re-ramping its clocks after the idle gap (all samples are reported)
-    e2e_med = float(np.median(e2e_s))
-    e2e = {"value": e2e_evals / e2e_med, "unit": "bound-evals/s",
-           "h2d_bytes_per_step": int(model.nbytes + data.nbytes + 16 * len(data) + 56 * len(model)),
-           "d2h_bytes_per_step": int(res["rounds"] * 48 * 288 + 256),
-           "seconds_per_step": e2e_med, "seconds_per_step_samples": [round(x, 4) for x in e2e_s], "statistic": "median",
-           "seconds_create_h2d_dt_build": float(np.median([p[0] for p in e2e_parts])),
-           "seconds_register_and_readback": float(np.median([p[1] for p in e2e_parts])), "includes": "create + H2D clouds + GPU DT build (reference-exact mode; Register's first ICP runs next to it on the idle SMs) + Register + result D2H"}
+    e2e = timed_e2e(n_e2e, 2)
+    e2e["includes"] = "create + H2D clouds + GPU DT build (library default: exact EDT with the reference's corner seed) + Register + result D2H"
+    out_extra = {}
+    S = wl["S"]
+    if not args.no_extras:
+        if S <= 640:
+            # the reference-order DT propagation (bit-exact DT values; one CTA, 4*S^2 dependent row steps) instead of the exact EDT
+            ed = timed_e2e(3, 2, dt_mode=0)            # untimed passes: the 1-CTA kernel only reaches steady speed after ~2 s of activity
+            ed["includes"] = "as e2e, with dt_mode = GOICP_DT_REFERENCE (Register's first ICP runs next to the 1-CTA propagation)"
+            dt_bytes = (4 * 2 + 2) * 8.0 * S ** 3          # 4 sweeps read+write every 8-byte working voxel, two of them read the adjacent slice once more
+            ed["dt_kernel"] = {"kernel": "dt_propagate_split_kernel", "algorithmic_bytes": dt_bytes,
+                               "achieved_gbs": dt_bytes / ed["seconds_create_h2d_dt_build"] / 1e9,
+                               "bound": "latency: 4*S^2 row steps, each after the previous one, on ONE CTA (DESIGN.md section 5); not a bandwidth kernel"}
+            out_extra["e2e_reference_dt"] = ed
+        if "certified_mse" in wl:
+            ce = make_engine(wl["certified_mse"])
+            ce.SetDT(*eng.GetDT())
+            c_total, c_results = timed_registers(ce, max(2, min(args.steps, 5)), 2)
+            ce.close()
+            cr = c_results[-1]
+            c_e2e = timed_e2e(3, 1, mse=wl["certified_mse"])
+            out_extra["certified"] = {"mse_threshold": wl["certified_mse"], "exit_path": cr["exit_path"], "time_to_certified_optimum_s": c_total / len(c_results),
+                                      "ms_per_step": 1e3 * c_total / len(c_results), "bound_evals": int(cr["bound_evals"]), "bound_evals_executed": int(cr["bound_evals_executed"]),
+                                      "value": sum(r["bound_evals"] for r in c_results) / c_total, "unit": "bound-evals/s", "rot_pops": int(cr["rot_pops"]),
+                                      "trans_pops": int(cr["trans_pops"]), "sse": cr["sse"], "best_lb": cr["best_lb"], "sse_thresh": cr["sse_thresh"],
+                                      "seconds_icp": float(np.mean([r["seconds_icp"] for r in c_results])),
+                                      "seconds_bnb_kernels": float(np.mean([r["seconds_bnb_kernels"] for r in c_results])),
+                                      "e2e_seconds_per_step": c_e2e["seconds_per_step"], "e2e_value": c_e2e["value"],
+                                      "reference_cpu_here": {"register_s": 338.6, "bound_evals": 1696656, "note": "oracle/_ref in the build container (tests/golden/goicp_runs.json)"}}
 
-    # DT-gather kernel alone at full occupancy (roofline of the gather itself)
+    # ---- roofline of the dominant kernel (this rank's GPU only)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    rng = np.random.default_rng(7)
-    npar = 148 * 16
-    Rs = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(npar)]).astype(np.float32)
-    tc = np.concatenate([rng.uniform(-0.5, 0.25, (npar, 3)), np.full((npar, 1), 0.25)], 1).astype(np.float32)
-    _, _, ms = eng.ExpandBounds(Rs.reshape(npar, 9), np.full(npar, -1, np.int32), tc, repeats=20)
-    gather_lookups = npar * 8 * len(data)
-    gather = {"kernel": "expand_bounds_kernel", "lookups_per_launch": gather_lookups, "ms_per_launch": ms,
-              "achieved": gather_lookups * 32 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-              "frac": gather_lookups * 32 / (ms * 1e-3) / 1e9 / peak, "useful_bytes_frac": gather_lookups * 4 / (ms * 1e-3) / 1e9 / peak,
-              "lookups_per_s": gather_lookups / (ms * 1e-3)}
-    lookups = executed * len(data)
-    achieved = lookups * 32 / kern_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "inner_bnb_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload), "traffic_source": "profiles/r1h_ncu_full_selected.csv: mean dram__bytes_read+write.sum over the 8 inner_bnb launches of one registration (cold cache; the gathers themselves are served by L2)",
-                "algorithmic_bytes_per_launch": lookups * 32 / max(1, sum(r["rounds"] for r in results)), "peak_source": peak_src,
-                "basis": "32 B sector per DT lookup (SURVEY 8d); lookups = executed bound evals * Nd; 300^3 fp32 DT (108 MB) is L2-resident",
-                "launches": int(sum(r["rounds"] for r in results)), "avg_launch_ms": 1e3 * kern_s / max(1, sum(r["rounds"] for r in results)),
-                "gather": gather}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    grid_bytes = 4 * S ** 3
+    gather_lps = eng.MeasureGather(grid_bytes, 5)
+    l2_resident = grid_bytes <= L2_BYTES
+    if l2_resident:
+        peak, peak_src = gather_lps * 32 / 1e9, f"measured here: random 4 B gathers over a {grid_bytes / 1e6:.0f} MB buffer (L2-resident), {gather_lps / 1e9:.1f} G look-ups/s x 32 B sector (goicp_measure_gather)"
+    else:
+        peak, peak_src = hbm, hbm_src + f"; the {grid_bytes / 1e6:.0f} MB grid does not fit L2 (measured random-gather rate over such a buffer: {gather_lps / 1e9:.1f} G look-ups/s = {gather_lps * 32 / 1e9:.0f} GB/s of sectors)"
+    mask = 0
+    for r in results:
+        mask |= int(r["bnb_kernel_variants"])
+    kname = " + ".join(v for k, v in KERNEL_NAMES.items() if mask & k) or "inner_bnb_pipelined_kernel"
+    lookups_local = executed_local * len(data)
+    achieved = lookups_local * 32 / kern_s / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload, kname)
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": lookups_local * 32 / max(1, rounds),
+                "peak_source": peak_src, "memory_level": "L2 (grid resident)" if l2_resident else "HBM",
+                "basis": "32 B sector per DT look-up (SURVEY 8d); look-ups = bound evals this GPU executed * Nd; time = CUDA events around the kernel on the engine stream (incl. the result exchange at N>1)",
+                "launches": rounds, "avg_launch_ms": 1e3 * kern_s / max(1, rounds), "lookups_per_s": lookups_local / kern_s,
+                "useful_bytes_frac_of_hbm": lookups_local * 4 / kern_s / 1e9 / hbm, "hbm_peak": hbm}
+    if not args.no_extras:
+        # the gather + bound arithmetic alone at full occupancy (expand_bounds_kernel), same accounting, same ceiling
+        rng = np.random.default_rng(7)
+        npar = 148 * 16 if len(data) <= 20000 else 148 * 2
+        Rs = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(npar)]).astype(np.float32)
+        tc = np.concatenate([rng.uniform(-0.5, 0.25, (npar, 3)), np.full((npar, 1), 0.25)], 1).astype(np.float32)
+        _, _, ms = eng.ExpandBounds(Rs.reshape(npar, 9), np.full(npar, -1, np.int32), tc, repeats=20)
+        gl = npar * 8 * len(data)
+        roofline["gather"] = {"kernel": "expand_bounds_kernel", "lookups_per_launch": gl, "ms_per_launch": ms, "lookups_per_s": gl / (ms * 1e-3),
+                              "achieved": gl * 32 / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": gl * 32 / (ms * 1e-3) / 1e9 / peak}
+        other = 4 * (512 ** 3 if S != 512 else 300 ** 3)
+        roofline["gather_peaks_measured"] = {f"{grid_bytes / 1e6:.0f}MB": gather_lps, f"{other / 1e6:.0f}MB": eng.MeasureGather(other, 5), "unit": "look-ups/s"}
 
-    # the reference-order DT propagation (87 % of an end-to-end pass): 4 sweeps read and write every 8-byte working voxel,
-    # the two sweeps that look at the adjacent slice read it once more
-    S = wl["S"]
-    dt_bytes = (4 * 2 + 2) * 8.0 * S ** 3
-    dt_kernel = {"kernel": "dt_propagate_split_kernel", "seconds_build_dt_call": e2e["seconds_create_h2d_dt_build"],
-                 "algorithmic_bytes": dt_bytes, "achieved": dt_bytes / e2e["seconds_create_h2d_dt_build"] / 1e9, "peak": peak, "unit": "GB/s",
-                 "frac": dt_bytes / e2e["seconds_create_h2d_dt_build"] / 1e9 / peak,
-                 "bound": "latency: 4*S^2 row steps, each after the previous one, on ONE CTA (DESIGN.md section 5); not a bandwidth kernel"}
     out = {"metric": "goicp_bound_evals_per_sec", "value": value, "unit": "bound-evals/s", "n_gpus": world, "steps": args.steps,
-           "warmup": max(3, args.warmup), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+           "warmup": warm, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-           "data": "reference bunny scans, deterministic subsample (committed fixtures tests/golden/*.f32)",
-           "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "dt_kernel": dt_kernel,
+           "data": "reference bunny scans, deterministic subsample (committed fixtures tests/golden/*.f32)" if "synth" not in wl else "synthetic (seeded closed surface + noisy moved subset)",
+           "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
            "time_to_optimum_s": total_s / args.steps, "exit_path": res["exit_path"], "sse": res["sse"],
            "bound_evals_per_step": evals // args.steps, "bound_evals_executed_per_step": executed // args.steps,
-           "rot_pops": res["rot_pops"], "trans_pops": res["trans_pops"], "rounds_per_step": res["rounds"],
-           "dt_build_s": dt_build_s, "seconds_icp_per_step": float(np.mean([r["seconds_icp"] for r in results])),
-           "seconds_bnb_kernels_per_step": kern_s / args.steps, "exchange": (os.environ.get("GOICP_EXCHANGE", "nccl") if world > 1 else None),
-           "reference_cpu_published_here": {"register_s": wl["ref_register_s"], "bound_evals": wl["ref_evals"],
-                                            "note": "oracle/_ref in the build container, 1 core (tests/golden/goicp_runs.json)"}}
+           "bound_evals_executed_this_gpu_per_step": executed_local // args.steps,
+           "rot_pops": res["rot_pops"], "trans_pops": res["trans_pops"], "rounds_per_step": res["rounds"], "icp_calls": res["icp_calls"],
+           "dt_build_s_first_call": dt_build_s, "seconds_icp_per_step": float(np.mean([r["seconds_icp"] for r in results])),
+           "seconds_bnb_kernels_per_step": kern_s / args.steps, "seconds_dt_score_per_step": float(np.mean([r["seconds_dt_score"] for r in results])),
+           "seconds_strict_resolves_per_step": float(np.mean([r["seconds_strict"] for r in results])), "strict_resolves_per_step": int(res["strict_resolves"]),
+           "contender_overflows": int(sum(r["contender_overflows"] for r in results)),
+           "exchange": (os.environ.get("GOICP_EXCHANGE", "nccl") if world > 1 else None)}
+    out.update(out_extra)
+    if wl.get("ref_register_s"):
+        out["reference_cpu_published_here"] = {"register_s": wl["ref_register_s"], "bound_evals": wl["ref_evals"],
+                                               "note": "oracle/_ref in the build container, 1 core (tests/golden/goicp_runs.json)"}
     eng.close()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             try:
-                out["cpu_baseline"] = cpu_reference_sample(wl, args.cpu_seconds)
+                out["cpu_baseline"] = cpu_reference_sample(wl, args.cpu_seconds, model, data)
             except Exception as e:  # the checker missing must not hide the GPU numbers
                 out["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(out))

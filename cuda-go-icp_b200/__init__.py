@@ -35,7 +35,7 @@ class Params(C.Structure):
                 ("dt_size", C.c_int), ("dt_expand", C.c_double),
                 ("rot_cube", C.c_float * 4), ("trans_cube", C.c_float * 4),
                 ("icp_max_iter", C.c_int), ("device", C.c_int), ("spec_cubes", C.c_int), ("cluster_size", C.c_int), ("dt_mode", C.c_int),
-                ("rank", C.c_int), ("world_size", C.c_int)]
+                ("rank", C.c_int), ("world_size", C.c_int), ("numerics", C.c_int)]
 
 
 class Result(C.Structure):
@@ -43,7 +43,9 @@ class Result(C.Structure):
                 ("best_lb", C.c_float), ("exit_path", C.c_int),
                 ("rot_pops", C.c_int64), ("trans_pops", C.c_int64), ("bound_evals", C.c_int64),
                 ("bound_evals_executed", C.c_int64), ("icp_calls", C.c_int64), ("rounds", C.c_int64), ("kernel_launches", C.c_int64),
-                ("seconds_total", C.c_double), ("seconds_bnb_kernels", C.c_double), ("seconds_icp", C.c_double)]
+                ("seconds_total", C.c_double), ("seconds_bnb_kernels", C.c_double), ("seconds_icp", C.c_double),
+                ("bound_evals_executed_local", C.c_int64), ("strict_resolves", C.c_int64), ("contender_overflows", C.c_int64),
+                ("seconds_dt_score", C.c_double), ("seconds_strict", C.c_double), ("seconds_setup", C.c_double), ("bnb_kernel_variants", C.c_int64)]
 
     def as_dict(self):
         return {"R": np.array(self.R, np.float32).reshape(3, 3), "t": np.array(self.t, np.float32),
@@ -51,7 +53,10 @@ class Result(C.Structure):
                 "exit_path": EXIT_PATHS[self.exit_path], "rot_pops": self.rot_pops, "trans_pops": self.trans_pops,
                 "bound_evals": self.bound_evals, "bound_evals_executed": self.bound_evals_executed,
                 "icp_calls": self.icp_calls, "rounds": self.rounds, "kernel_launches": self.kernel_launches, "seconds_total": self.seconds_total,
-                "seconds_bnb_kernels": self.seconds_bnb_kernels, "seconds_icp": self.seconds_icp}
+                "seconds_bnb_kernels": self.seconds_bnb_kernels, "seconds_icp": self.seconds_icp,
+                "bound_evals_executed_local": self.bound_evals_executed_local, "strict_resolves": self.strict_resolves,
+                "contender_overflows": self.contender_overflows, "seconds_dt_score": self.seconds_dt_score,
+                "seconds_strict": self.seconds_strict, "seconds_setup": self.seconds_setup, "bnb_kernel_variants": self.bnb_kernel_variants}
 
 
 class IcpResult(C.Structure):
@@ -73,7 +78,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
                "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
-               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
+               "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_transfer_bytes", "goicp_measure_gather", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 
 def kdtree_host(model):
@@ -133,6 +138,8 @@ def lib():
         L.goicp_register.argtypes = [C.c_void_p, C.POINTER(Result)]
         L.goicp_poll.argtypes = [C.c_void_p, C.POINTER(Snapshot)]
         L.goicp_cancel.argtypes = [C.c_void_p]
+        L.goicp_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.goicp_measure_gather.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         L.goicp_set_exchange.argtypes = [C.c_void_p, ALLGATHER_FN, C.c_void_p, C.c_int]
         L.goicp_nccl_unique_id.argtypes = [C.c_void_p]
         L.goicp_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -182,7 +189,8 @@ class GoICP:
         self.trimFraction = 0.0
         self.doTrim = True
         self.dt = _DT()
-        self.dt_mode = 0
+        self.dt_mode = p.dt_mode          # default: exact EDT with the reference binary's corner seed (include/goicp_b200.h)
+        self.numerics = p.numerics
         self.spec_cubes = 0
         self.cluster_size = 0
         self.initNodeRot = [p.rot_cube[i] for i in range(4)]
@@ -215,6 +223,7 @@ class GoICP:
             p.dt_size = int(self.dt.SIZE)
             p.dt_expand = float(self.dt.expandFactor)
             p.dt_mode = int(self.dt_mode)
+            p.numerics = int(self.numerics)
             p.spec_cubes = int(self.spec_cubes)
             p.cluster_size = int(self.cluster_size)
             p.rank, p.world_size = self.rank, self.world_size
@@ -389,6 +398,18 @@ class GoICP:
 
     def Cancel(self):
         self.L.goicp_cancel(self._handle())
+
+    def TransferBytes(self):
+        """(host->device, device->host) bytes this handle has copied so far."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self.L.goicp_transfer_bytes(self._handle(), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def MeasureGather(self, nbytes, repeats=5):
+        """random 4-byte gather rate (look-ups/s) over an nbytes buffer: the measured ceiling of the DT gathers"""
+        out = C.c_double(0)
+        self._check(self.L.goicp_measure_gather(self._handle(), nbytes, repeats, C.byref(out)))
+        return out.value
 
 
 def load_cloud(path, subsample=1.0, resize=1.0, seed=1234):

@@ -331,7 +331,7 @@ constexpr int kMaxCluster = 16;
 template <bool PTS_SMEM, bool TRIM>
 __global__ void __launch_bounds__(kBnbThreads, 2)
 inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
-                 int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
+                 int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands, unsigned* __restrict__ gkeys)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -367,8 +367,11 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
     const int p_begin = min(rank * per, c.nd), p_end = min(p_begin + per, c.nd);
     const int np = p_end - p_begin;
     constexpr bool trim = TRIM;
-    // residual keys of this CTA's points for the 8 children (trimming only): after the points (if staged)
-    unsigned* mk = reinterpret_cast<unsigned*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry) + (PTS_SMEM ? (size_t)per * sizeof(float4) : 0));
+    // residual keys of this CTA's points for the 8 children (trimming only): in shared memory after the points (if staged),
+    // or -- clouds whose slice of keys does not fit next to the queue -- in this CTA's slab of global memory (L2-resident
+    // between the passes of the select)
+    unsigned* mk = gkeys ? gkeys + (size_t)blockIdx.x * per * 8
+                         : reinterpret_cast<unsigned*>(smem_raw + (size_t)heap_cap_sm * sizeof(HeapEntry) + (PTS_SMEM ? (size_t)per * sizeof(float4) : 0));
 
     if (PTS_SMEM) {
         // rotate once (jly_goicp.cpp:470-476) and keep (R p, gamma) on chip for the whole search
@@ -996,6 +999,105 @@ dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restric
 }
 
 // ------------------------------------------------------------------------------------------
+// The same score with the sums in a fixed parallel order (GOICP_NUM_FAST_SUMS): every thread adds its strided share of
+// the squared residuals, then a warp-shuffle tree and a fixed-order sum over the warps.  With trimming the inlier_num
+// smallest residuals are found by a 4 x 8-bit radix select over their bit patterns (non-negative floats order like
+// their bits); everything strictly below the threshold is summed and the ties at the threshold that still count are
+// added as a product.  One CTA per pose; scratch (nposes * nd floats) is only touched when trimming.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBnbThreads)
+dt_score_fast_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ scratch, float* __restrict__ out)
+{
+    __shared__ float red[kBnbWarps];
+    __shared__ int hist[256];
+    __shared__ unsigned s_prefix; __shared__ int s_k;
+    const float* Rt = Rt12 + 12 * blockIdx.x;
+    const bool pose = use_pose[blockIdx.x] != 0;
+    const bool trim = c.inlier_num < c.nd;
+    float* m = scratch + (size_t)blockIdx.x * c.nd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
+        float4 p = __ldg(c.data + i);
+        float x = p.x, y = p.y, z = p.z;
+        if (pose) {
+            x = __fadd_rn(dot3_ref(Rt[0], Rt[1], Rt[2], p.x, p.y, p.z), Rt[9]);
+            y = __fadd_rn(dot3_ref(Rt[3], Rt[4], Rt[5], p.x, p.y, p.z), Rt[10]);
+            z = __fadd_rn(dot3_ref(Rt[6], Rt[7], Rt[8], p.x, p.y, p.z), Rt[11]);
+        }
+        const float d = dt_distance(c.dt, x, y, z);
+        if (trim) m[i] = d; else acc = __fadd_rn(acc, __fmul_rn(d, d));
+    }
+    float tie_part = 0.0f;
+    if (trim) {
+        if (threadIdx.x == 0) { s_prefix = 0u; s_k = c.inlier_num; }
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            for (int b = threadIdx.x; b < 256; b += kBnbThreads) hist[b] = 0;
+            __syncthreads();
+            const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            const unsigned prefix = s_prefix;
+            for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
+                const unsigned key = __float_as_uint(m[i]);
+                if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int k = s_k, b = 0, before = 0;
+                for (; b < 256; b++) { if (before + hist[b] >= k) break; before += hist[b]; }
+                s_prefix = prefix | ((unsigned)b << shift); s_k = k - before;
+            }
+            __syncthreads();
+        }
+        const unsigned T = s_prefix;
+        for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
+            const float d = m[i];
+            if (__float_as_uint(d) < T) acc = __fadd_rn(acc, __fmul_rn(d, d));
+        }
+        const float tv = __uint_as_float(T);
+        tie_part = (float)s_k * (tv * tv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.0f;
+        for (int w = 0; w < kBnbWarps; w++) s = __fadd_rn(s, red[w]);
+        out[blockIdx.x] = __fadd_rn(s, tie_part);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Roofline denominator of the DT gathers, measured rather than assumed: uniformly random 4-byte loads over a buffer of a
+// given size and NOTHING else -- no voxel-index arithmetic, no reduction.  Eight independent addresses per step from one
+// 32-bit state (multiplicative hashes), so a thread always has eight loads in flight.  goicp_measure_gather().
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+gather_peak_kernel(const float* __restrict__ buf, unsigned n, int iters, float* __restrict__ sink)
+{
+    unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 0x9e3779b9u;
+    float acc = 0.0f;
+    for (int it = 0; it < iters; it++) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned r = (s ^ (0x85ebca6bu * (unsigned)(k + 1))) * (0xc2b2ae35u + 2u * (unsigned)k);
+            v[k] = __ldg(buf + (unsigned)(((unsigned long long)(r ^ (r >> 15)) * n) >> 32));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc += v[k];
+        s = s * 1664525u + 1013904223u;
+    }
+    if (acc == 1.2345678e33f) *sink = acc;               // never true: keeps the loads alive
+}
+cudaError_t launch_gather_peak(const float* d_buf, unsigned n, int iters, int blocks, float* d_sink, cudaStream_t s)
+{
+    gather_peak_kernel<<<blocks, 512, 0, s>>>(d_buf, n, iters, d_sink);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host-callable launchers
 // ------------------------------------------------------------------------------------------
 cudaError_t launch_dt_lookup(const DtView& dt, const float* d_q, int n, float* d_out, int32_t* d_idx, cudaStream_t s)
@@ -1061,13 +1163,13 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     return e;
 }
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, cudaStream_t s)
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, unsigned* d_trim_keys, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     const bool trim = c.inlier_num < c.nd;
     const int per = (c.nd + cluster - 1) / cluster;
     size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0)
-                + (trim ? (size_t)per * 8 * sizeof(unsigned) : 0);
+                + (trim && !d_trim_keys ? (size_t)per * 8 * sizeof(unsigned) : 0);
     // GOICP_BNB_MIN_SMEM_KB (experiment): pad the request so that fewer CTAs share an SM (and its L1TEX pipe)
     static const size_t min_smem = getenv("GOICP_BNB_MIN_SMEM_KB") ? (size_t)atoi(getenv("GOICP_BNB_MIN_SMEM_KB")) << 10 : 0;
     if (smem < min_smem) smem = min_smem;
@@ -1085,10 +1187,10 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
         return low_latency ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
                            : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
     }
-    if (pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
-    if (!pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
-    if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
-    return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+    if (pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
+    if (!pts_in_smem && !trim) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
+    if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
+    return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
 }
 // out5 = {strict optErrorT, node x, y, z, w}; d_strict: kMaxCand floats; d_scratch: kMaxCand*nd floats (only if nd does not fit in smem)
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
@@ -1102,9 +1204,10 @@ cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, co
     strict_pick_kernel<<<1, 1, 0, s>>>(d_task, d_list, d_strict, d_out5);
     return cudaGetLastError();
 }
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, cudaStream_t s)
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, bool fast_sums, cudaStream_t s)
 {
     if (nposes <= 0) return cudaSuccess;
+    if (fast_sums) { dt_score_fast_kernel<<<nposes, kBnbThreads, 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out); return cudaGetLastError(); }
     const size_t need = (size_t)c.nd * sizeof(float);
     const int use_smem = need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0;
     dt_score_kernel<<<nposes, kBnbThreads, use_smem ? need : 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out, use_smem);

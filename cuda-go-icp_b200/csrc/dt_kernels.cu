@@ -17,6 +17,7 @@
 #include <ctime>
 #include "dt_kernels.h"
 #include "mem_pool.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -656,42 +657,96 @@ __global__ void dt_finalize_kernel(const V2* __restrict__ G, int S, int P, doubl
     }
 }
 
-// ---- exact EDT (separable, integer squared distances) ----------------------------------------
-// pass along z per (x,y) column: squared distance to the nearest seed in the column
-__global__ void edt_pass_z(const V2* __restrict__ G, int S, int P, int* __restrict__ D)
+// ---- exact EDT (separable, integer squared distances; Meijster et al.'s two-scan lower envelope) -------------
+// Works IN PLACE on the output grid, in the output's own [z][y][x] layout (x fastest), as int32 squared distances
+// until the last pass converts to the reference's float metric distance -- no working volume, no transposition:
+//   pass x   one warp per (z,y) line: nearest seed to the left / right by ballots                 (contiguous)
+//   pass y   one thread per (z,x) line, threads of a warp = neighbouring x                          (coalesced)
+//   pass z   one thread per (y,x) line, same, and writes float(double(float(sqrt(n2))) / scale)     (coalesced)
+// A line pass is D'(u) = min_i D(i) + (u-i)^2, the lower envelope of S parabolas: the forward scan keeps the
+// parabolas that own a stretch of the line on a stack (s = apex, t = first owned position, gs = D at the apex;
+// integer Sep() = floor of the crossing point, exact), the backward scan evaluates.  O(S) per line, S^2 lines.
+constexpr int kEdtInf = 0x3f3f3f3f;    // "no seed on this line yet"; byte-uniform so that cudaMemset can write it, and
+                                       // kEdtInf + 1023^2 stays far below 2^31
+
+__global__ void edt_seed_kernel(int* __restrict__ D, int S, const float* __restrict__ model, int nm, double xmin, double ymin, double zmin, double scale, int corner_seed)
 {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;      // x*S + y
-    if (col >= S * S) return;
-    const V2* g = G + (size_t)col * P;
-    int* d = D + (size_t)col * S;
-    int last = -kMaxS * 4;
-    for (int z = 0; z < S; z++) { if (g[z].n == 0) last = z; int k = z - last; d[z] = k > 4 * kMaxS - 1 ? kInf : k * k; }
-    last = kMaxS * 8;
-    for (int z = S - 1; z >= 0; z--) { if (g[z].n == 0) last = z; int k = last - z; int v = k > 4 * kMaxS - 1 ? kInf : k * k; if (v < d[z]) d[z] = v; }
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && corner_seed) D[0] = 0;                       // see dt_init_kernel
+    if (i >= nm) return;
+    int x = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i], xmin), scale), 0.5));
+    int y = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 1], ymin), scale), 0.5));
+    int z = __double2int_rz(__dadd_rn(__dmul_rn(__dsub_rn((double)model[3 * i + 2], zmin), scale), 0.5));
+    if (x < 0 || x >= S || y < 0 || y >= S || z < 0 || z >= S) return;
+    D[((size_t)z * S + y) * S + x] = 0;
 }
-// generic 1-D min-plus pass along a strided line: out[i] = min_j in[j] + (i-j)^2
-__global__ void edt_pass_line(const int* __restrict__ in, int* __restrict__ out, int S, size_t line_stride_a, size_t line_stride_b, size_t elem_stride)
+
+__global__ void __launch_bounds__(256) edt_pass_x(int* __restrict__ D, int S)
 {
-    extern __shared__ int line[];
-    const size_t base = (size_t)blockIdx.x * line_stride_a + (size_t)blockIdx.y * line_stride_b;
-    for (int i = threadIdx.x; i < S; i += blockDim.x) line[i] = in[base + (size_t)i * elem_stride];
-    __syncthreads();
-    for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        int best = kInf;
-        for (int j = 0; j < S; j++) { const int v = line[j]; if (v < kInf) { const int c = v + (i - j) * (i - j); if (c < best) best = c; } }
-        out[base + (size_t)i * elem_stride] = best;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    for (int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); line < S * S; line += nw) {
+        int* d = D + (size_t)line * S;
+        const int far = 1 << 20;
+        int last = -far;                                        // nearest seed at or left of x, chunk by chunk
+        for (int x0 = 0; x0 < S; x0 += 32) {
+            const int x = x0 + lane;
+            const bool seed = x < S && d[x] == 0;
+            const unsigned m = __ballot_sync(full, seed);
+            const unsigned upto = m & (0xffffffffu >> (31 - lane));
+            const int left = upto ? x0 + 31 - __clz(upto) : last;
+            if (x < S) d[x] = x - left;                         // >= far when there is none
+            if (m) last = x0 + 31 - __clz(m);
+        }
+        int next = far + far;                                   // nearest seed at or right of x
+        for (int x0 = ((S - 1) >> 5) << 5; x0 >= 0; x0 -= 32) {
+            const int x = x0 + lane;
+            const int dl = x < S ? d[x] : far;
+            const unsigned m = __ballot_sync(full, dl == 0);
+            const unsigned from = m & (0xffffffffu << lane);
+            const int right = from ? x0 + __ffs(from) - 1 : next;
+            if (x < S) { const int k = min(dl, right - x); d[x] = k >= far ? kEdtInf : k * k; }
+            if (m) next = x0 + __ffs(m) - 1;
+        }
     }
 }
-__global__ void edt_finalize_kernel(const int* __restrict__ D, int S, double scale, float* __restrict__ out)
+
+template <int MAXS, bool FINAL>
+__global__ void __launch_bounds__(128) edt_pass_line(int* __restrict__ D, int S, size_t stride_elem, size_t stride_outer, double scale)
 {
-    // D is [x][y][z]; out is [z][y][x]
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t n3 = (size_t)S * S * S;
-    if (i >= n3) return;
-    const int x = (int)(i % S), y = (int)((i / S) % S), z = (int)(i / ((size_t)S * S));
-    const int n2 = D[((size_t)x * S + y) * S + z];
-    float dv = __double2float_rn(sqrt((double)n2));
-    out[i] = __double2float_rn(__ddiv_rn((double)dv, scale));
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= S * S) return;
+    const size_t base = (size_t)(tid / S) * stride_outer + (size_t)(tid % S);
+    short s[MAXS], t[MAXS]; int gs[MAXS];
+    int q = 0;
+    s[0] = 0; t[0] = 0; gs[0] = D[base];
+    int g_next = S > 1 ? D[base + stride_elem] : 0;
+    for (int u = 1; u < S; u++) {
+        const int gu = g_next;
+        if (u + 1 < S) g_next = D[base + (size_t)(u + 1) * stride_elem];          // one element ahead of the dependent chain
+        while (q >= 0) {
+            const int a = t[q] - s[q], b = t[q] - u;
+            if (a * a + gs[q] > b * b + gu) q--; else break;
+        }
+        if (q < 0) { q = 0; s[0] = (short)u; gs[0] = gu; }
+        else {
+            const int i = s[q];
+            const int w = 1 + (u * u - i * i + gu - gs[q]) / (2 * (u - i));      // numerator >= 0 here: the parabola at i owns t[q] >= 0
+            if (w < S) { q++; s[q] = (short)u; t[q] = (short)w; gs[q] = gu; }
+        }
+    }
+    for (int u = S - 1; u >= 0; u--) {
+        const int e = u - s[q];
+        int v = e * e + gs[q];
+        if (v > kEdtInf) v = kEdtInf;
+        if (FINAL) {
+            // distance = float( double(float(sqrt(double(n2)))) / scale ) (jly_3ddt.cpp:970-978)
+            const float dv = __double2float_rn(sqrt((double)v));
+            reinterpret_cast<float*>(D)[base + (size_t)u * stride_elem] = __double2float_rn(__ddiv_rn((double)dv, scale));
+        } else D[base + (size_t)u * stride_elem] = v;
+        if (u == t[q]) q--;
+    }
 }
 
 } // namespace
@@ -732,20 +787,39 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
     const size_t n3 = (size_t)S * S * S;
     const int P = (S + 1) & ~1;
     const size_t ng = (size_t)S * S * P;
-    V2* G = nullptr; float* d_model = nullptr; int* D0 = nullptr; int* D1 = nullptr;
-    auto cleanup = [&]() { cudaStreamSynchronize(stream);      /* blocks go back to a shared pool: nothing may still use them */ pool_free(G); pool_free(d_model); pool_free(D0); pool_free(D1); };
+    V2* G = nullptr; float* d_model = nullptr;
+    auto cleanup = [&]() { cudaStreamSynchronize(stream);      /* blocks go back to a shared pool: nothing may still use them */ pool_free(G); pool_free(d_model); };
 #define DT_TRY(expr) do { e = (expr); if (e != cudaSuccess) { msg = #expr; cleanup(); return e; } } while (0)
+    if (mode != 0) {
+        // exact EDT, in place on the output grid (see edt_pass_line)
+        DT_TRY(pool_alloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
+        mark("frame + pool_alloc");
+        DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
+        int* D = reinterpret_cast<int*>(d_out);
+        DT_TRY(cudaMemsetAsync(D, 0x3f, n3 * sizeof(int), stream));
+        edt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(D, S, d_model, nm, meta[0], meta[1], meta[2], meta[3], mode == 2 ? 1 : 0);
+        DT_TRY(cudaGetLastError());
+        edt_pass_x<<<std::min((S * S + 7) / 8, 148 * 8), 256, 0, stream>>>(D, S);
+        DT_TRY(cudaGetLastError());
+        const unsigned nb = (unsigned)((S * S + 127) / 128);
+#define DT_EDT_PASSES(MAXS) do { \
+            edt_pass_line<MAXS, false><<<nb, 128, 0, stream>>>(D, S, (size_t)S, (size_t)S * S, meta[3]);      /* along y: lines (z, x) */ \
+            DT_TRY(cudaGetLastError()); \
+            edt_pass_line<MAXS, true><<<nb, 128, 0, stream>>>(D, S, (size_t)S * S, (size_t)S, meta[3]);       /* along z: lines (y, x) */ \
+            DT_TRY(cudaGetLastError()); } while (0)
+        if (S <= 320) DT_EDT_PASSES(320); else if (S <= 512) DT_EDT_PASSES(512); else DT_EDT_PASSES(1024);
+#undef DT_EDT_PASSES
+    } else {
     DT_TRY(pool_alloc((void**)&G, ng * sizeof(V2)));
     DT_TRY(pool_alloc((void**)&d_model, (size_t)3 * nm * sizeof(float)));
     mark("frame + pool_alloc");
     DT_TRY(cudaMemcpyAsync(d_model, model, (size_t)3 * nm * sizeof(float), cudaMemcpyHostToDevice, stream));
-    // the extra corner seed is an artefact of the reference binary, not part of an exact EDT
-    dt_init_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(G, ng, mode == 0 ? 1 : 0);
+    dt_init_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, stream>>>(G, ng, 1);
     DT_TRY(cudaGetLastError());
     dt_seed_kernel<<<(nm + 255) / 256, 256, 0, stream>>>(G, S, P, d_model, nm, meta[0], meta[1], meta[2], meta[3]);
     DT_TRY(cudaGetLastError());
     mark("memcpy + init + seed launch");
-    if (mode == 0) {
+    {
         const bool timing = getenv("GOICP_DT_TIMING") != nullptr;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (timing) { cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventRecord(ev0, stream); }
@@ -789,19 +863,7 @@ cudaError_t dt_build_device(const float* model, int nm, int S, double expand, in
         dim3 grid((S + 31) / 32, (S + 31) / 32, S), block(32, 32);
         dt_finalize_kernel<<<grid, block, 0, stream>>>(G, S, P, meta[3], d_out);
         DT_TRY(cudaGetLastError());
-    } else {
-        DT_TRY(pool_alloc((void**)&D0, n3 * sizeof(int)));
-        DT_TRY(pool_alloc((void**)&D1, n3 * sizeof(int)));
-        edt_pass_z<<<(S * S + 127) / 128, 128, 0, stream>>>(G, S, P, D0);
-        DT_TRY(cudaGetLastError());
-        // along y: lines indexed by (x, z): base = x*S*S + z, element stride S
-        edt_pass_line<<<dim3(S, S), 128, S * sizeof(int), stream>>>(D0, D1, S, (size_t)S * S, 1, (size_t)S);
-        DT_TRY(cudaGetLastError());
-        // along x: lines indexed by (y, z): base = y*S + z, element stride S*S
-        edt_pass_line<<<dim3(S, S), 128, S * sizeof(int), stream>>>(D1, D0, S, (size_t)S, 1, (size_t)S * S);
-        DT_TRY(cudaGetLastError());
-        edt_finalize_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, stream>>>(D0, S, meta[3], d_out);
-        DT_TRY(cudaGetLastError());
+    }
     }
     mark("finalize launch");
     DT_TRY(cudaStreamSynchronize(stream));

@@ -173,10 +173,10 @@ struct goicp_handle {
     bool kd_ready = false;
     // scratch
     DevBuf<InnerTask> d_tasks; DevBuf<InnerResult> d_results; DevBuf<HeapEntry> d_spill; int spill_cap = 0; int spill_slots = 0;
-    DevBuf<CandList> d_cands; DevBuf<unsigned long long> d_dbg; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
-    int64_t strict_resolves = 0;
+    DevBuf<CandList> d_cands; DevBuf<unsigned> d_trim_keys; DevBuf<unsigned long long> d_dbg; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
+    int64_t strict_resolves = 0, cand_overflows = 0, bnb_variants = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
-    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage; DevBuf<int32_t> d_icp_nn, d_icp_pos, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
+    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage, d_icp_partials; DevBuf<int32_t> d_icp_nn, d_icp_pos, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
     InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
 
@@ -197,6 +197,7 @@ struct goicp_handle {
     // consumed by the first goicp_register after it
     cudaStream_t stream_dt = nullptr; bool icp0_valid = false; goicp_icp_result icp0;
     int64_t launches = 0;
+    int64_t bytes_h2d = 0, bytes_d2h = 0;      // cumulative over the handle's life (xfer)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -206,6 +207,14 @@ int fail(goicp_handle* h, int code, const std::string& msg) { if (h) h->err = ms
 #define CUDA_TRY(h, expr)                                                                         \
     do { cudaError_t _e = (expr);                                                                 \
          if (_e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } while (0)
+
+// every host<->device copy of a handle goes through here, so that the bytes a call really moved can be reported
+// (goicp_transfer_bytes; bench.py's e2e.h2d_bytes_per_step / d2h_bytes_per_step are read from it, not estimated)
+inline cudaError_t xfer(goicp_handle* h, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s)
+{
+    if (kind == cudaMemcpyHostToDevice) h->bytes_h2d += (int64_t)bytes; else if (kind == cudaMemcpyDeviceToHost) h->bytes_d2h += (int64_t)bytes;
+    return cudaMemcpyAsync(dst, src, bytes, kind, s);
+}
 
 // Per-device facts and launch configuration are looked up once per process, and the streams / events of destroyed
 // handles are kept for the next one: cudaGetDeviceProperties, cudaFuncSetAttribute and stream creation take the
@@ -263,7 +272,7 @@ int upload_data(goicp_handle* h)
         tmp[i] = make_float4(x, y, z, std::sqrt(x * x + y * y + z * z));     // normData (jly_goicp.cpp:143-147)
     }
     CUDA_TRY(h, h->d_data.reserve(h->nd));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_data.p, tmp.data(), sizeof(float4) * h->nd, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_data.p, tmp.data(), sizeof(float4) * h->nd, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->data_uploaded = true;
     return GOICP_OK;
@@ -285,11 +294,11 @@ int ensure_kdtree(goicp_handle* h)
     CUDA_TRY(h, h->d_kd_vind.reserve(h->nm));
     CUDA_TRY(h, h->d_kd_leaf.reserve(h->nm));
     CUDA_TRY(h, h->d_model.reserve((size_t)3 * h->nm));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_nodes.p, h->kd_host.nodes.data(), sizeof(KdNode) * h->kd_host.nodes.size(), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_boxes.p, h->kd_host.boxes.data(), sizeof(float) * h->kd_host.boxes.size(), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_vind.p, h->kd_host.vind.data(), sizeof(int32_t) * h->nm, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_kd_nodes.p, h->kd_host.nodes.data(), sizeof(KdNode) * h->kd_host.nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_kd_boxes.p, h->kd_host.boxes.data(), sizeof(float) * h->kd_host.boxes.size(), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_kd_vind.p, h->kd_host.vind.data(), sizeof(int32_t) * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, h->d_icp_state.reserve(1));
     h->kd_ready = true;
@@ -354,7 +363,7 @@ int make_const(goicp_handle* h, BnbConst& c)
 
 // Shared-memory plan of the persistent inner-BnB kernel: rotated points on chip when two CTAs
 // per SM still fit, the rest of the per-CTA budget goes to the priority queue.
-struct InnerPlan { bool pts_smem; int heap_cap_sm; int cluster; };
+struct InnerPlan { bool pts_smem; bool keys_smem; int heap_cap_sm; int cluster; };
 InnerPlan plan_inner(const goicp_handle* h)
 {
     InnerPlan p;
@@ -366,16 +375,21 @@ InnerPlan plan_inner(const goicp_handle* h)
     if (cl <= 0) { cl = 1; while (cl < 16 && h->nd / (cl * 2) >= 512) cl *= 2; }
     if (cl > 16) cl = 16;
     p.cluster = cl;
-    // two CTAs per SM: each may take half of the SM's shared memory minus its static part and the 1 KB the driver reserves per CTA
-    const size_t stat = (size_t)(h->max_smem_optin - h->inner_dyn_smem);
-    const size_t per_cta = (size_t)h->max_smem_optin / 2 - stat - 2048;
-    const size_t per = (size_t)((h->nd + cl - 1) / cl);
-    const size_t pts = per * sizeof(float4);
+    // two CTAs per SM: each may take half of the SM's shared memory minus its static part and the 1 KB the driver reserves per CTA.
+    // Signed arithmetic: what does not fit next to a 16 KB queue stays in global memory (the trimming keys first claim the
+    // space -- the radix select reads them five times per expansion --, then the rotated points).
+    const long stat = (long)h->max_smem_optin - h->inner_dyn_smem;
+    const long per_cta = (long)h->max_smem_optin / 2 - stat - 2048;
+    const long per = (h->nd + cl - 1) / cl;
+    const long pts = per * (long)sizeof(float4);
     const bool trim = h->initialized && h->inlier_num < h->nd;
-    const size_t keys = trim ? per * 8 * sizeof(unsigned) : 0;          // residual keys of the radix select
-    p.pts_smem = pts + keys + 16 * 1024 <= per_cta;
-    size_t heap_bytes = per_cta - keys - (p.pts_smem ? pts : 0);
-    p.heap_cap_sm = (int)std::min<size_t>(heap_bytes / sizeof(HeapEntry), 4096);
+    const long keys = trim ? per * 8 * (long)sizeof(unsigned) : 0;          // residual keys of the radix select
+    const long min_heap = 16 * 1024;
+    p.keys_smem = trim && keys + min_heap <= per_cta;
+    long left = per_cta - (p.keys_smem ? keys : 0);
+    p.pts_smem = pts + min_heap <= left;
+    if (p.pts_smem) left -= pts;
+    p.heap_cap_sm = (int)std::max<long>(64, std::min<long>(left / (long)sizeof(HeapEntry), 4096));
     return p;
 }
 
@@ -420,7 +434,7 @@ int shard_exchange(goicp_allgather_fn fn, void* user, int W, int n, const InnerR
 // Runs `n` inner BnBs (tasks in h->h_tasks) and leaves the results in h->h_results.
 // With an exchange hook installed, rank r runs tasks r, r+W, r+2W, ... and the per-rank result
 // blocks are all-gathered, so every rank ends up with all n results.
-int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed_evals, std::vector<std::shared_ptr<CandList>>* lists = nullptr)
+int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed_evals, std::vector<std::shared_ptr<CandList>>* lists = nullptr, int64_t* executed_local = nullptr)
 {
     if (n <= 0) return GOICP_OK;
     int rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
@@ -442,12 +456,30 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     if (stats) { CUDA_TRY(h, h->d_dbg.reserve((size_t)12 * (n + 64))); CUDA_TRY(h, cudaMemsetAsync(h->d_dbg.p, 0, sizeof(unsigned long long) * 12 * n, h->stream)); cdbg.dbg = h->d_dbg.p; }
     CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
     if (mine > 0) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
-        CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->low_latency, h->stream));
-        h->launches++;
+        CUDA_TRY(h, xfer(h, h->d_tasks.p, src, sizeof(InnerTask) * mine, cudaMemcpyHostToDevice, h->stream));
+        const bool trim = c.inlier_num < c.nd;
+        {
+            static const bool legacy = getenv("GOICP_NO_PIPELINE") != nullptr;
+            h->bnb_variants |= (trim || legacy) ? 16 : (plan.pts_smem ? (h->low_latency ? 1 : 2) : (h->low_latency ? 4 : 8));
+        }
+        if (trim && !plan.keys_smem) {
+            // trimming a cloud whose keys do not fit in shared memory: per-CTA key slabs in global memory, the round launched
+            // in chunks so that the slabs stay below 1 GiB
+            const size_t per_task = (size_t)plan.cluster * ((h->nd + plan.cluster - 1) / plan.cluster) * 8;
+            const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)mine, ((size_t)1 << 28) / per_task));
+            CUDA_TRY(h, h->d_trim_keys.reserve(per_task * chunk));
+            for (int off = 0; off < mine; off += chunk) {
+                CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p + off, h->d_results.p + off, std::min(chunk, mine - off), plan.cluster, plan.pts_smem, plan.heap_cap_sm,
+                                             h->d_spill.p, h->spill_cap, h->d_cands.p + off, h->low_latency, h->d_trim_keys.p, h->stream));
+                h->launches++;
+            }
+        } else {
+            CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->low_latency, nullptr, h->stream));
+            h->launches++;
+        }
     }
     if (W == 1) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->h_results, h->d_results.p, sizeof(InnerResult) * n, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, xfer(h, h->h_results, h->d_results.p, sizeof(InnerResult) * n, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     } else if (h->nccl) {
@@ -460,13 +492,13 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         const int nrc = nccl_api()->AllGather(h->d_results.p, h->d_gather.p, sizeof(InnerResult) * per_rank, kNcclUint8, h->nccl, h->stream);
         if (nrc != 0) return fail(h, GOICP_ERR_CUDA, std::string("ncclAllGather: ") + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(nrc) : "error"));
         std::vector<InnerResult> recv((size_t)per_rank * W);
-        CUDA_TRY(h, cudaMemcpyAsync(recv.data(), h->d_gather.p, sizeof(InnerResult) * per_rank * W, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, xfer(h, recv.data(), h->d_gather.p, sizeof(InnerResult) * per_rank * W, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         for (int t = 0; t < n; t++) h->h_results[t] = recv[(size_t)(t % W) * per_rank + t / W];
     } else {
         std::vector<InnerResult> mine_res(std::max(mine, 1));
-        if (mine > 0) CUDA_TRY(h, cudaMemcpyAsync(mine_res.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
+        if (mine > 0) CUDA_TRY(h, xfer(h, mine_res.data(), h->d_results.p, sizeof(InnerResult) * mine, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
         if (shard_exchange(h->xchg, h->xchg_user, W, n, mine_res.data(), mine, h->h_results) != 0)
@@ -507,16 +539,18 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             const int t = W > 1 ? r + k * W : k;
             if (h->h_tasks[t].level < 0 && h->h_results[t].pad[1] > 0) {
                 auto cl = std::make_shared<CandList>();
-                CUDA_TRY(h, cudaMemcpyAsync(cl.get(), h->d_cands.p + k, sizeof(CandList), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(h, xfer(h, cl.get(), h->d_cands.p + k, sizeof(CandList), cudaMemcpyDeviceToHost, h->stream));
                 (*lists)[t] = cl;
             }
         }
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
     for (int t = 0; t < n; t++) {
+        if (h->h_results[t].status == 3 && (h->h_results[t].pad[0] & 0x100u)) return fail(h, GOICP_ERR_CUDA, "internal: the pipelined translation search mispredicted a queue pop (please report)");
         if (h->h_results[t].status == 3) return fail(h, GOICP_ERR_CAPACITY, "translation priority queue overflowed its device capacity");
         if (h->h_results[t].status == 4) return fail(h, GOICP_ERR_DEPTH, "translation search exceeded 21 levels");
         if (executed_evals) *executed_evals += h->h_results[t].evals;
+        if (executed_local && t % W == r) *executed_local += h->h_results[t].evals;
     }
     return GOICP_OK;
 }
@@ -534,10 +568,10 @@ int share_cand_list(goicp_handle* h, std::shared_ptr<CandList>& cl)
     if (cl) { mine.have = 1; mine.list = *cl; }
     if (h->nccl) {
         CUDA_TRY(h, h->d_share.reserve((size_t)(W + 1) * sizeof(Block)));
-        CUDA_TRY(h, cudaMemcpyAsync(h->d_share.p, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, xfer(h, h->d_share.p, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
         const int nrc = nccl_api()->AllGather(h->d_share.p, h->d_share.p + sizeof(Block), sizeof(Block), kNcclUint8, h->nccl, h->stream);
         if (nrc != 0) return fail(h, GOICP_ERR_CUDA, "ncclAllGather (contender list) failed");
-        CUDA_TRY(h, cudaMemcpyAsync(recv.data(), h->d_share.p + sizeof(Block), sizeof(Block) * W, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, xfer(h, recv.data(), h->d_share.p + sizeof(Block), sizeof(Block) * W, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     } else if (h->xchg) {
         if (h->xchg(h->xchg_user, &mine, recv.data(), sizeof(Block), 0) != 0) return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
@@ -558,12 +592,12 @@ int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, co
     CUDA_TRY(h, h->d_tasks.reserve(1)); CUDA_TRY(h, h->d_cands.reserve(1));
     InnerTask* d_task = h->d_tasks.p + (h->d_tasks.n - 1);          // last slots are reserved for this
     CandList* d_list = h->d_cands.p + (h->d_cands.n - 1);
-    CUDA_TRY(h, cudaMemcpyAsync(d_task, &task, sizeof task, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d_list, &list, sizeof list, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, d_task, &task, sizeof task, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, d_list, &list, sizeof list, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_strict_resolve(c, d_task, d_list, h->d_strict.p, h->d_strict.p + 256, h->d_strict.p + 128, h->max_smem_optin - 2048, h->stream));
     h->launches += 2; h->strict_resolves++;
     float out5[5];
-    CUDA_TRY(h, cudaMemcpyAsync(out5, h->d_strict.p + 128, sizeof out5, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, out5, h->d_strict.p + 128, sizeof out5, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *value = out5[0]; node4[0] = out5[1]; node4[1] = out5[2]; node4[2] = out5[3]; node4[3] = out5[4];
     return GOICP_OK;
@@ -578,12 +612,12 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     for (int i = 0; i < 3; i++) Rt[9 + i] = R ? t[i] : 0.0f;
     CUDA_TRY(h, h->d_f32a.reserve(64));
     CUDA_TRY(h, h->d_i32.reserve(16));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, h->d_score_scratch.reserve((size_t)h->nd));
-    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->max_smem_optin - 2048, h->stream));
+    CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->max_smem_optin - 2048, (h->p.numerics & GOICP_NUM_FAST_SUMS) != 0, h->stream));
     h->launches++;
-    CUDA_TRY(h, cudaMemcpyAsync(out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }
@@ -607,15 +641,17 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     for (int i = 0; i < 3; i++) st.t[i] = t0[i];
     st.err = -1.0f;
     const double t_begin = now_s();
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
     const int n_nodes = (int)h->kd_host.nodes.size();
-    const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin);
+    const bool fast = (h->p.numerics & GOICP_NUM_FAST_ICP) != 0;
+    const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin, fast);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     // queries are interleaved over the CTAs, 32 per CTA and pass: use every SM the cooperative launch allows
     const int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32), blocks_cap));
-    CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, blocks, h->max_smem_optin, h->stream));
+    if (fast) CUDA_TRY(h, h->d_icp_partials.reserve((size_t)2 * 16 * blocks));
+    CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, (h->p.do_trim ? 1 : 0) | ((h->p.numerics & GOICP_NUM_JACOBI_SVD) ? 2 : 0), blocks, h->max_smem_optin, fast, h->d_icp_partials.p, h->stream));
     h->launches++;
-    CUDA_TRY(h, cudaMemcpyAsync(&st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, &st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->t_icp += now_s() - t_begin;
     for (int i = 0; i < 9; i++) out->R[i] = st.R[i];
@@ -664,8 +700,9 @@ void goicp_default_params(goicp_params* p)
     p->rot_cube[0] = p->rot_cube[1] = p->rot_cube[2] = (float)-kPi; p->rot_cube[3] = (float)(2 * kPi);
     p->trans_cube[0] = p->trans_cube[1] = p->trans_cube[2] = -0.5f; p->trans_cube[3] = 1.0f;
     p->icp_max_iter = 10000;
-    p->device = 0; p->spec_cubes = 0; p->cluster_size = 0; p->dt_mode = GOICP_DT_REFERENCE;
+    p->device = 0; p->spec_cubes = 0; p->cluster_size = 0; p->dt_mode = GOICP_DT_EXACT_EDT_REFSEED;
     p->rank = 0; p->world_size = 1;
+    p->numerics = GOICP_NUM_STRICT;
 }
 
 int goicp_create(const goicp_params* p, goicp_handle** out)
@@ -683,15 +720,16 @@ int goicp_destroy(goicp_handle* h)
     if (!h) return GOICP_OK;
     if (h->cuda_ready) {
         cudaSetDevice(h->p.device);
+        // nothing queued on this handle's streams may still touch a buffer when it goes back to the process-wide pool
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->stream_dt) cudaStreamSynchronize(h->stream_dt);
         h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
         h->d_gather.release(); h->d_share.release();
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
-        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
-        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release();
+        h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_trim_keys.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
+        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release(); h->d_icp_partials.release();
         if (h->h_results) pool_free_host(h->h_results);
         if (h->h_tasks) pool_free_host(h->h_tasks);
-        if (h->stream) cudaStreamSynchronize(h->stream);
-        if (h->stream_dt) cudaStreamSynchronize(h->stream_dt);
         if (h->stream && h->stream_dt && h->ev0 && h->ev1) {       // kept for the next handle on this device (ensure_cuda)
             std::lock_guard<std::mutex> lk(g_dev_mtx);
             StreamSet ss; ss.stream = h->stream; ss.stream_dt = h->stream_dt; ss.ev0 = h->ev0; ss.ev1 = h->ev1;
@@ -728,7 +766,7 @@ int goicp_set_dt(goicp_handle* h, const float* grid, int size, const double meta
     int rc = ensure_cuda(h); if (rc) return rc;
     const size_t n3 = (size_t)size * size * size;
     CUDA_TRY(h, h->d_dt.reserve(n3));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_dt.p, grid, n3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_dt.p, grid, n3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->dt_size = size; std::memcpy(h->dt_meta, meta4, sizeof h->dt_meta); h->have_dt = true;
     return GOICP_OK;
@@ -740,6 +778,7 @@ int goicp_get_dt(goicp_handle* h, float* grid_out, double meta4_out[4])
     if (grid_out) {
         const size_t n3 = (size_t)h->dt_size * h->dt_size * h->dt_size;
         CUDA_TRY(h, cudaMemcpy(grid_out, h->d_dt.p, n3 * sizeof(float), cudaMemcpyDeviceToHost));
+        h->bytes_d2h += (int64_t)(n3 * sizeof(float));
     }
     return GOICP_OK;
 }
@@ -755,12 +794,13 @@ int goicp_build_dt(goicp_handle* h)
     const int S = h->p.dt_size;
     if (S < 2 || S > 1024) return fail(h, GOICP_ERR_INVALID, "build_dt: dt_size out of range [2,1024]");
     const size_t n3 = (size_t)S * S * S;
+    h->have_dt = false;                              // a failed rebuild must not leave a half-written grid in use
     CUDA_TRY(h, h->d_dt.reserve(n3));
     std::string msg;
     cudaError_t e = cudaSuccess;
     h->icp0_valid = false;
     const bool no_overlap = getenv("GOICP_NO_PREFETCH") != nullptr;
-    if (h->nd > 0 && !no_overlap) {
+    if (h->nd > 0 && !no_overlap && h->p.dt_mode == GOICP_DT_REFERENCE) {
         // GoICP::Register starts with an ICP from the identity pose (jly_goicp.cpp:378-391) that reads the clouds and
         // the kd-tree but not the DT.  The reference-order DT propagation is one CTA on one SM for most of the build
         // (DESIGN.md section 5), so that refinement runs here, on the other SMs, while the DT is being built: the DT
@@ -789,6 +829,7 @@ int goicp_build_dt(goicp_handle* h)
         e = dt_build_device(h->model.data(), h->nm, S, h->p.dt_expand, h->p.dt_mode, h->d_dt.p, h->dt_meta, h->stream, msg);
     }
     if (e != cudaSuccess) { h->icp0_valid = false; return fail(h, GOICP_ERR_CUDA, "dt_build_device: " + msg + ": " + cudaGetErrorString(e)); }
+    h->bytes_h2d += (int64_t)sizeof(float) * 3 * h->nm;          // dt_build_device uploads the model cloud itself
     h->dt_size = S; h->have_dt = true;
     if (trace) fprintf(stderr, "[dt trace] goicp_build_dt total %.3f ms\n", 1e3 * (now_s() - tr0));
     return GOICP_OK;
@@ -804,10 +845,10 @@ int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_ou
     CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
     CUDA_TRY(h, h->d_f32b.reserve(n));
     CUDA_TRY(h, h->d_i32.reserve((size_t)3 * n + 16));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_dt_lookup(dt, h->d_q.p, n, h->d_f32b.p, ixyz_out ? h->d_i32.p : nullptr, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(dist_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
-    if (ixyz_out) CUDA_TRY(h, cudaMemcpyAsync(ixyz_out, h->d_i32.p, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, dist_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (ixyz_out) CUDA_TRY(h, xfer(h, ixyz_out, h->d_i32.p, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }
@@ -828,10 +869,10 @@ int goicp_eval_bounds(goicp_handle* h, int npairs, const float* R9, const int32_
     }
     CUDA_TRY(h, h->d_pairs.reserve(npairs));
     CUDA_TRY(h, h->d_f32b.reserve((size_t)2 * npairs));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pairs.p, tasks.data(), sizeof(PairTask) * npairs, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_pairs.p, tasks.data(), sizeof(PairTask) * npairs, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_pair_bounds(c, h->d_pairs.p, npairs, reinterpret_cast<float2*>(h->d_f32b.p), h->stream));
     std::vector<float> out((size_t)2 * npairs);
-    CUDA_TRY(h, cudaMemcpyAsync(out.data(), h->d_f32b.p, sizeof(float) * 2 * npairs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, out.data(), h->d_f32b.p, sizeof(float) * 2 * npairs, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int k = 0; k < npairs; k++) { ub_out[k] = out[2 * k]; lb_out[k] = out[2 * k + 1]; }
     return GOICP_OK;
@@ -853,7 +894,7 @@ int goicp_expand_bounds(goicp_handle* h, int n, const float* R9, const int32_t* 
     }
     CUDA_TRY(h, h->d_pairs.reserve(n));
     CUDA_TRY(h, h->d_f32b.reserve((size_t)16 * n));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pairs.p, tasks.data(), sizeof(PairTask) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_pairs.p, tasks.data(), sizeof(PairTask) * n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_expand_bounds(c, h->d_pairs.p, n, h->d_f32b.p, h->stream));
     if (device_ms) {
         if (repeats < 1) repeats = 1;
@@ -865,7 +906,7 @@ int goicp_expand_bounds(goicp_handle* h, int n, const float* R9, const int32_t* 
         float ms = 0; CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
         *device_ms = ms / repeats;
     }
-    CUDA_TRY(h, cudaMemcpyAsync(out16, h->d_f32b.p, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, out16, h->d_f32b.p, sizeof(float) * 16 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }
@@ -890,7 +931,7 @@ int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* leve
     std::vector<InnerTask> tasks(h->h_tasks, h->h_tasks + n);
     std::vector<InnerResult> results(h->h_results, h->h_results + n);
     for (int k = 0; k < n; k++)
-        if (lists[k]) { rc = resolve_strict(h, c, tasks[k], *lists[k], &results[k].value, results[k].node); if (rc) return rc; }
+        if (lists[k] && !(h->p.numerics & GOICP_NUM_FAST_SUMS)) { rc = resolve_strict(h, c, tasks[k], *lists[k], &results[k].value, results[k].node); if (rc) return rc; }
     std::memcpy(h->h_results, results.data(), sizeof(InnerResult) * n);
     for (int k = 0; k < n; k++) {
         out[k].value = h->h_results[k].value; std::memcpy(out[k].node, h->h_results[k].node, sizeof out[k].node);
@@ -908,10 +949,10 @@ int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float
     CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
     CUDA_TRY(h, h->d_f32b.reserve(n));
     CUDA_TRY(h, h->d_i32.reserve((size_t)n + 16));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, xfer(h, h->d_q.p, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, launch_nn(kd_view(h), h->d_q.p, n, h->d_i32.p, h->d_f32b.p, getenv("GOICP_NN_COOP") != nullptr, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(idx_out, h->d_i32.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaMemcpyAsync(d2_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, idx_out, h->d_i32.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, d2_out, h->d_f32b.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }
@@ -1030,6 +1071,40 @@ int goicp_selftest_shard(int rank, int world, int n, goicp_allgather_fn fn, void
 
 int goicp_trim_memory(void) { pool_trim(); return GOICP_OK; }
 
+// Random 4-byte gather rate over a `bytes`-sized device buffer (the DT gathers' roofline denominator; bnb_kernels.cu)
+int goicp_measure_gather(goicp_handle* h, size_t bytes, int repeats, double* lookups_per_s_out)
+{
+    if (!h || bytes < 4096 || !lookups_per_s_out) return fail(h, GOICP_ERR_INVALID, "measure_gather: bad arguments");
+    int rc = ensure_cuda(h); if (rc) return rc;
+    if (repeats < 1) repeats = 1;
+    float* buf = nullptr;
+    CUDA_TRY(h, pool_alloc((void**)&buf, bytes + 256));
+    const unsigned n = (unsigned)std::min<size_t>(bytes / 4, 0xffffffffu);
+    cudaError_t e = cudaMemsetAsync(buf, 0, bytes, h->stream);
+    const int blocks = h->sm_count * 4, iters = 256;
+    float* sink = buf + bytes / 4;
+    if (e == cudaSuccess) e = launch_gather_peak(buf, n, iters, blocks, sink, h->stream);          // warm-up (fills L2 when the buffer fits)
+    if (e == cudaSuccess) e = launch_gather_peak(buf, n, iters, blocks, sink, h->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
+    for (int r = 0; r < repeats && e == cudaSuccess; r++) e = launch_gather_peak(buf, n, iters, blocks, sink, h->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev1, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    pool_free(buf);
+    if (e != cudaSuccess) return fail(h, GOICP_ERR_CUDA, std::string("measure_gather: ") + cudaGetErrorString(e));
+    *lookups_per_s_out = (double)blocks * 512.0 * 8.0 * iters * repeats / (ms * 1e-3);
+    return GOICP_OK;
+}
+
+int goicp_transfer_bytes(const goicp_handle* h, int64_t* h2d_out, int64_t* d2h_out)
+{
+    if (!h) return GOICP_ERR_INVALID;
+    if (h2d_out) *h2d_out = h->bytes_h2d;
+    if (d2h_out) *d2h_out = h->bytes_d2h;
+    return GOICP_OK;
+}
+
 int goicp_cancel(goicp_handle* h) { if (!h) return GOICP_ERR_INVALID; h->cancel_flag.store(1); return GOICP_OK; }
 int goicp_poll(goicp_handle* h, goicp_snapshot* out)
 {
@@ -1045,7 +1120,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
-    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->t_score = h->t_strict = 0;
+    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->t_score = h->t_strict = 0; h->strict_resolves = 0; h->cand_overflows = 0; h->bnb_variants = 0;
     const double t_begin = now_s();
     h->initialized = false;
     int rc = initialize(h); if (rc) return rc;
@@ -1144,7 +1219,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
             std::memcpy(h->h_tasks, tk.data(), sizeof(InnerTask) * n); slots.swap(sl);
         }
         std::vector<std::shared_ptr<CandList>> lists;
-        rcl = run_inner_batch(h, c, n, &res.bound_evals_executed, &lists); if (rcl) return rcl;
+        rcl = run_inner_batch(h, c, n, &res.bound_evals_executed, &lists, &res.bound_evals_executed_local); if (rcl) return rcl;
         res.rounds++;
         for (int t = 0; t < n; t++) {
             ChildEval& ce = evs[slots[t].cube].ch[slots[t].child];
@@ -1186,13 +1261,16 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 float ub_node[4] = {ce.ub.node[0], ce.ub.node[1], ce.ub.node[2], ce.ub.node[3]};
                 if (!(j == j0 && skip_ub)) {
                     res.trans_pops += ce.ub.pops; res.bound_evals += ce.ub.evals;
-                    if (ce.ub.pad[1] > 0) {
+                    if (ce.ub.pad[1] > 0 && !(h->p.numerics & GOICP_NUM_FAST_SUMS)) {
                         // this pass may improve the optimum: settle value and arg-min cube in the
                         // reference's summation order before deciding (strict_sum.cuh)
                         InnerTask task; std::memcpy(task.R, ce.R, sizeof ce.R); task.level = -1; task.opt_error = ce.ub_opt_error; task.pad = 0;
                         std::shared_ptr<CandList> cl = ce.cands;
                         if ((h->xchg || h->nccl) && h->p.world_size > 1) { rc = share_cand_list(h, cl); if (rc) return rc; }   // collective: every rank is here
-                        if (cl) { rc = resolve_strict(h, c, task, *cl, &ub, ub_node); if (rc) return rc; }
+                        if (cl) {
+                            if (cl->flags & 1u) h->cand_overflows++;          // the list is the first 128 contenders only (goicp_result.contender_overflows)
+                            rc = resolve_strict(h, c, task, *cl, &ub, ub_node); if (rc) return rc;
+                        }
                     }
                     if (ub < E) {                                                          // :495-544
                         E = ub;
@@ -1236,6 +1314,8 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     res.exit_path = exit_path; res.best_lb = exit_lb;
     res.kernel_launches = h->launches;
     res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp;
+    res.strict_resolves = h->strict_resolves; res.contender_overflows = h->cand_overflows; res.bnb_kernel_variants = h->bnb_variants;
+    res.seconds_dt_score = h->t_score; res.seconds_strict = h->t_strict; res.seconds_setup = h->t_setup;
     if (getenv("GOICP_ROUND_STATS"))
         fprintf(stderr, "[register] total %.3f s: setup (upload, gamma table, kd-tree) %.3f, BnB kernels + exchange %.3f, ICP %.3f, DT scoring %.3f, strict resolves %.3f (%lld), rest (host commit, copies) %.3f\n",
                 res.seconds_total, h->t_setup, h->t_kernels, h->t_icp, h->t_score, h->t_strict, (long long)h->strict_resolves,

@@ -10,10 +10,13 @@ cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n
 cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
 cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, cudaStream_t s);
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency,
+                             unsigned* d_trim_keys /* trimming: per-CTA slabs of 8 * ceil(nd/cluster) keys in global memory, or null = shared memory */, cudaStream_t s);
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
                                   float* d_out5, int smem_limit, cudaStream_t s);
-cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, cudaStream_t s);
+cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, bool fast_sums, cudaStream_t s);
+
+cudaError_t launch_gather_peak(const float* d_buf, unsigned n, int iters, int blocks, float* d_sink, cudaStream_t s);
 
 // ---- icp_kernels.cu ---------------------------------------------------------------------
 // Flattened copy of the reference-ordered kd-tree (built on the host by kdtree_host.cpp).
@@ -56,10 +59,12 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
 };
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
+// do_sort = the reference's do_trim (it sorts the correspondences only then, jly_icp3d.hpp:236-239); fast = GOICP_NUM_FAST_ICP
+// (parallel moments + Jacobi Procrustes, d_partials: 2 * grid_blocks * 16 floats).
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
-                       int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s);
+                       int max_iter, float err_diff, int num_inliers, int do_sort, int grid_blocks, int smem_optin, bool fast, float* d_partials, cudaStream_t s);
 int icp_threads();
 int icp_max_blocks_supported();   // CTAs the in-kernel radix sort's scan supports
-int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin);
+int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin, bool fast);
 
 } // namespace goicp

@@ -63,7 +63,9 @@ std::map<std::string, std::string> parse_toml(const std::string& path)
 
 struct Config {                       // common.h:133-176
     std::string description, target, source, output, visualization;
-    int mode = 3; bool trim = true; float subsample = 1.0f, mse_threshold = 1e-3f, resize = 1.0f;
+    // defaults of the reference's Config for keys a TOML omits (common.cpp:11-13, 56-60): mode 1, trim false, mse 1e-5.
+    // (Config::trim is parsed but never applied to GoICP by the reference -- doTrim stays true, jly_goicp.cpp:62 -- nor here.)
+    int mode = 1; bool trim = false; float subsample = 1.0f, mse_threshold = 1e-5f, resize = 1.0f;
 };
 
 Config load_config(const std::string& path)
@@ -75,10 +77,10 @@ Config load_config(const std::string& path)
     c.description = opt("info.description", "");
     c.target = need("io.target"); c.source = need("io.source");
     c.output = opt("io.output", ""); c.visualization = opt("io.visualization", "");
-    c.mode = std::stoi(opt("params.mode", "3"));
-    c.trim = opt("params.trim", "true") == "true";
+    c.mode = std::stoi(opt("params.mode", "1"));
+    c.trim = opt("params.trim", "false") == "true";
     c.subsample = std::stof(opt("params.subsample", "1.0"));
-    c.mse_threshold = std::stof(opt("params.mse_threshold", "1e-3"));
+    c.mse_threshold = std::stof(opt("params.mse_threshold", "1e-5"));
     c.resize = std::stof(opt("params.resize", "1.0"));
     c.subsample = std::min(1.0f, std::max(0.0f, c.subsample));               // common.cpp:62-64
     c.mse_threshold = std::max(1e-10f, c.mse_threshold);

@@ -522,10 +522,19 @@ __device__ void mat3_mul(const float* A, const float* B, float* C)   // accumula
     }
 }
 
+__device__ void procrustes_jacobi(const double* H, float* Rn);
+
 // Procrustes step + SE(3) composition (jly_icp3d.hpp:268-291) from H = q_d^T q_m and the means.
-__device__ void icp_update(IcpState* st, const float* H)
+// jacobi: GOICP_NUM_JACOBI_SVD -- the rotation from the engine's own solver instead of the reference's svdcmp (experiments:
+// with the reference-order sums kept, does the trajectory survive a solver that is merely accurate?  scripts/parity_modes.py)
+__device__ void icp_update(IcpState* st, const float* H, bool jacobi)
 {
     float U[9], W[3], V[9], Ut[9], Rn[9], VT[9], tmp[9];
+    if (jacobi) {
+        double Hd[9];
+        for (int i = 0; i < 9; i++) Hd[i] = (double)H[i];
+        procrustes_jacobi(Hd, Rn);
+    } else {
     svd3_ref(H, U, W, V);
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Ut[3 * j + i] = U[3 * i + j];
     mat3_mul(V, Ut, Rn);                                                     // R_ = V * ~U
@@ -536,6 +545,7 @@ __device__ void icp_update(IcpState* st, const float* H)
     float D[9] = {1, 0, 0, 0, 1, 0, 0, 0, det};
     mat3_mul(V, D, VT);
     mat3_mul(VT, Ut, Rn);                                                    // R_ = V * diag(1,1,det) * ~U
+    }
     float tn[3], tt[3];
     for (int a = 0; a < 3; a++) {                                            // t_ = ~mu_m - R_ * ~mu_d
         float acc = 0.0f;
@@ -718,8 +728,9 @@ struct NnPartial { float d1[kIcpThreads / 32][32]; float d2[kIcpThreads / 32][32
 
 __global__ void __launch_bounds__(kIcpThreads)
 icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
-           int max_iter, float err_diff, int num, IcpSmemPlan plan)
+           int max_iter, float err_diff, int num, int flags /* bit 0: sort (the reference's do_trim), bit 1: Jacobi solver */, IcpSmemPlan plan)
 {
+    const int do_sort = flags & 1;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char icp_smem[];
     __shared__ float sh_H[9];
@@ -871,7 +882,10 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         // ---- phase B: the reference's qsort by distance (stable for ties) as a distributed rank
         // count: rank(i) = #{j : key_j < key_i}, keys = (d^2 bits, index) are unique.  Every CTA ranks
         // its own queries against all keys; order[rank] = i.
-        if (sradix) {
+        // (the reference sorts only when do_trim is set, jly_icp3d.hpp:236-239: without it the accumulations below run in
+        // data order, i.e. straight over the rows phase A wrote)
+        if (!do_sort) {
+        } else if (sradix) {
             icp_radix_sort(grid, wk, nd, sradix);        // large clouds: stable LSD radix sort (ends with a grid.sync)
         } else {
             const unsigned long long* keys = wk.keys;
@@ -896,7 +910,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             if (keys_in_smem) __syncthreads();       // block 0 overwrites the area in phase C
         }
         c1 = clock64(); c_sort += c1 - c0;
-        if (!sradix) grid.sync();
+        if (do_sort && !sradix) grid.sync();
         c0 = clock64(); c_wait += c0 - c1;
         if (blockIdx.x == 0) {
             // ---- phase C: reference-order accumulations.  The sort left the correspondences (model
@@ -906,7 +920,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             // up strictly sequentially.
             float acc = 0.0f;
             if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
-            const float4* srows = reinterpret_cast<const float4*>(wk.stage);
+            const float4* srows = reinterpret_cast<const float4*>(do_sort ? wk.stage : wk.q);
             // err_new += dis is float += double in the reference (:254); the double sum of two floats is
             // exact (or differs from either by < 2^-29), so rounding it to float equals the float sum --
             // one add per element, like the other accumulators; operands are fetched 16 at a time ahead
@@ -999,7 +1013,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;
                     __syncwarp();
-                    if (lane == 0) { const long long cu0 = clock64(); icp_update(st, sh_H); c_wait += 0; c_svd += clock64() - cu0; }
+                    if (lane == 0) { const long long cu0 = clock64(); icp_update(st, sh_H, (flags & 2) != 0); c_wait += 0; c_svd += clock64() - cu0; }
                 }
             }
             c1 = clock64(); c_p2 += c1 - c0;
@@ -1010,6 +1024,327 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; st->dbg[0] = c_nn + (c_svd << 32); }
+}
+
+// ==========================================================================================
+// GOICP_NUM_FAST_ICP: the same iteration -- same queries, same exact nearest neighbours, same convergence test, same
+// stale-mean quirk -- with the sums formed in parallel and an original closed 3x3 solver.
+//
+//  * Moments.  Every CTA adds up, for the queries it answered, 16 numbers: sum m, sum q, sum d^2 and the 9 products
+//    sum (q - c_d)(m - c_m)^T about the previous iteration's means c (so nothing cancels when the clouds sit away from
+//    the origin); float per thread, shuffle tree per warp, then ONE grid barrier, after which every CTA adds the
+//    per-CTA partials of all CTAs in the same fixed order in double and solves for the new pose by itself.  All CTAs
+//    execute the same arithmetic on the same numbers, so they agree bit for bit without a second barrier and without a
+//    broadcast: one grid.sync per iteration instead of three, nothing sequential but a 16 x gridDim reduction.
+//  * Rotation.  R_ = V diag(1,1,det) U^T of H = U W V^T (jly_icp3d.hpp:268-285) is the proper rotation that maximises
+//    tr(R_ H^T)...  computed here as: cyclic Jacobi eigen-decomposition of H^T H in double (V, det +1, eigenvalues
+//    sorted), u1 = H v1 / |H v1|, u2 = H v2 made orthogonal to u1, u3 = u1 x u2 -- which IS the reference's
+//    reflection fix (its third column flips sign exactly when det(V U^T) < 0).
+// With trimming (num < nd) the correspondences are sorted by the existing phase B and the moments run over the first
+// `num` sorted rows; the sort costs its grid barriers, the rest is the same.
+// ==========================================================================================
+__device__ void procrustes_jacobi(const double* H /* 3x3 row-major: rows = data, cols = model */, float* Rn)
+{
+    // A = H^T H (symmetric)
+    double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) A[i][j] = H[0 + i] * H[0 + j] + H[3 + i] * H[3 + j] + H[6 + i] * H[6 + j];
+    for (int sweep = 0; sweep < 12; sweep++) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off <= 1e-30 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2])) || off == 0.0) break;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int p = k == 2 ? 1 : 0, q = k == 0 ? 1 : 2;            // (0,1), (0,2), (1,2)
+            if (A[p][q] == 0.0) continue;
+            const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+            const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+            const int r = 3 - p - q;
+            const double app = A[p][p], aqq = A[q][q], apq = A[p][q], arp = A[r][p], arq = A[r][q];
+            A[p][p] = app - tt * apq; A[q][q] = aqq + tt * apq; A[p][q] = A[q][p] = 0.0;
+            A[r][p] = A[p][r] = c * arp - sn * arq; A[r][q] = A[q][r] = sn * arp + c * arq;
+#pragma unroll
+            for (int i = 0; i < 3; i++) { const double vp = V[i][p], vq = V[i][q]; V[i][p] = c * vp - sn * vq; V[i][q] = sn * vp + c * vq; }
+        }
+    }
+    // eigenvalues descending; an odd permutation is undone by negating a column (keeps det V = +1)
+    int o0 = 0, o1 = 1, o2 = 2; bool odd = false;
+    if (A[o0][o0] < A[o1][o1]) { const int t = o0; o0 = o1; o1 = t; odd = !odd; }
+    if (A[o1][o1] < A[o2][o2]) { const int t = o1; o1 = o2; o2 = t; odd = !odd; }
+    if (A[o0][o0] < A[o1][o1]) { const int t = o0; o0 = o1; o1 = t; odd = !odd; }
+    double v1[3], v2[3], v3[3];
+    for (int i = 0; i < 3; i++) { v1[i] = V[i][o0]; v2[i] = V[i][o1]; v3[i] = odd ? -V[i][o2] : V[i][o2]; }
+    // U: images of v1, v2 under H, orthonormalised; u3 completes a right-handed frame
+    double u1[3], u2[3], u3[3];
+    for (int i = 0; i < 3; i++) { u1[i] = H[3 * i] * v1[0] + H[3 * i + 1] * v1[1] + H[3 * i + 2] * v1[2]; u2[i] = H[3 * i] * v2[0] + H[3 * i + 1] * v2[1] + H[3 * i + 2] * v2[2]; }
+    double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (n1 > 0.0) { u1[0] /= n1; u1[1] /= n1; u1[2] /= n1; } else { u1[0] = 1.0; u1[1] = u1[2] = 0.0; }
+    const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+    for (int i = 0; i < 3; i++) u2[i] -= d12 * u1[i];
+    double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+    if (n2 > 1e-150) { u2[0] /= n2; u2[1] /= n2; u2[2] /= n2; }
+    else {      // rank one: any unit vector orthogonal to u1
+        const int a = fabs(u1[0]) <= fabs(u1[1]) && fabs(u1[0]) <= fabs(u1[2]) ? 0 : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2);
+        double e[3] = {0, 0, 0}; e[a] = 1.0;
+        const double d = u1[a];
+        for (int i = 0; i < 3; i++) u2[i] = e[i] - d * u1[i];
+        n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+        u2[0] /= n2; u2[1] /= n2; u2[2] /= n2;
+    }
+    u3[0] = u1[1] * u2[2] - u1[2] * u2[1]; u3[1] = u1[2] * u2[0] - u1[0] * u2[2]; u3[2] = u1[0] * u2[1] - u1[1] * u2[0];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rn[3 * i + j] = (float)(v1[i] * u1[j] + v2[i] * u2[j] + v3[i] * u3[j]);   // V U^T
+}
+
+struct IcpFastShared { float R[9], t[3], mu_m[3], mu_d[3]; float err, err_new; int iter, converged; };
+
+__global__ void __launch_bounds__(kIcpThreads)
+icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
+                int max_iter, float err_diff, int num, int do_sort, IcpSmemPlan plan, float* __restrict__ partials /* 2 x gridDim.x x 16 */)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char icp_smem[];
+    __shared__ NnPartial part;
+    __shared__ int n_deferred, n_unsettled;
+    __shared__ IcpFastShared cur;
+    __shared__ float red[kIcpThreads / 32][16];
+    __shared__ double tot[16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kIcpThreads / 32;
+    const bool sorting = do_sort && num < nd;          // an untrimmed sum does not depend on the order
+
+    const KdNode* nodes = kd.nodes; const float4* leaf = kd.pts_leaf;
+    unsigned char* sp = icp_smem;
+    if (plan.tree_bytes) {
+        KdNode* sn = reinterpret_cast<KdNode*>(sp);
+        float4* sl = reinterpret_cast<float4*>(sp + (size_t)plan.tree_nodes * sizeof(KdNode));
+        for (int i = threadIdx.x; i < plan.tree_nodes * 2; i += blockDim.x) reinterpret_cast<uint4*>(sn)[i] = reinterpret_cast<const uint4*>(kd.nodes)[i];
+        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
+        nodes = sn; leaf = sl; sp += plan.tree_bytes;
+    }
+    float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
+    sp += plan.stage_bytes;
+    unsigned* sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr;
+    sp += plan.radix_bytes;
+    int* squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 9; i++) cur.R[i] = st->R[i];
+        for (int i = 0; i < 3; i++) { cur.t[i] = st->t[i]; cur.mu_m[i] = st->mu_m[i]; cur.mu_d[i] = st->mu_d[i]; }
+        cur.err = st->err; cur.err_new = st->err_new; cur.iter = 0; cur.converged = 0;
+    }
+    __syncthreads();
+
+    for (int iter = 0; iter < max_iter; iter++) {
+        float R[9], t[3];
+#pragma unroll
+        for (int i = 0; i < 9; i++) R[i] = cur.R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) t[i] = cur.t[i];
+        const float cm0 = cur.mu_m[0], cm1 = cur.mu_m[1], cm2 = cur.mu_m[2], cd0 = cur.mu_d[0], cd1 = cur.mu_d[1], cd2 = cur.mu_d[2];
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+        auto add_row = [&](float mx, float my, float mz, float qx, float qy, float qz, float d2) {
+            acc[0] += mx; acc[1] += my; acc[2] += mz; acc[3] += qx; acc[4] += qy; acc[5] += qz; acc[6] += d2;
+            const float a0 = qx - cd0, a1 = qy - cd1, a2 = qz - cd2, b0 = mx - cm0, b1 = my - cm1, b2 = mz - cm2;
+            acc[7] += a0 * b0; acc[8] += a0 * b1; acc[9] += a0 * b2;
+            acc[10] += a1 * b0; acc[11] += a1 * b1; acc[12] += a1 * b2;
+            acc[13] += a2 * b0; acc[14] += a2 * b1; acc[15] += a2 * b2;
+        };
+        // ---- phase A: transform + exact nearest neighbour (same searches as icp_kernel) ------------------------
+        if (plan.brute_force) {
+            const int mchunk = (kd.nm + kWarps - 1) / kWarps;
+            const int m0 = min(warp * mchunk, kd.nm), m1 = min(m0 + mchunk, kd.nm);
+            for (int qpass = 0; (qpass * 32) * (int)gridDim.x + (int)blockIdx.x < nd; qpass++) {
+                const int i = (qpass * 32 + lane) * gridDim.x + blockIdx.x;
+                const bool valid = i < nd;
+                float qx = 0.0f, qy = 0.0f, qz = 0.0f;
+                if (valid) {
+                    const float4 p = __ldg(data + i);
+                    qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                }
+                float d1 = 3.402823466e+38f, d2 = 3.402823466e+38f; int i1 = 0;
+                for (int m = m0; m < m1; m++) {
+                    const float4 pm = leaf[m];
+                    const float e0 = qx - pm.x, e1 = qy - pm.y, e2 = qz - pm.z;
+                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;
+                    if (dist < d1) { d2 = d1; d1 = dist; i1 = __float_as_int(pm.w); }
+                    else if (dist < d2) d2 = dist;
+                }
+                part.d1[warp][lane] = d1; part.d2[warp][lane] = d2; part.i1[warp][lane] = i1;
+                __syncthreads();
+                if (warp == 0) {
+                    float D1 = 3.402823466e+38f, D2 = 3.402823466e+38f; int I1 = 0;
+#pragma unroll
+                    for (int w = 0; w < kWarps; w++) {
+                        const float a = part.d1[w][lane], b = part.d2[w][lane];
+                        if (a < D1) { D2 = fminf(D1, b); D1 = a; I1 = part.i1[w][lane]; }
+                        else D2 = fminf(D2, a);
+                        D2 = fminf(D2, b);
+                    }
+                    if (valid) {
+                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1, D1);   // near tie: reference traversal order decides
+                        wk.nn[i] = I1; wk.d2[i] = D1;
+                        const float mx = __ldg(kd.model + 3 * I1), my = __ldg(kd.model + 3 * I1 + 1), mz = __ldg(kd.model + 3 * I1 + 2);
+                        if (sorting) {
+                            wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
+                            float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                            row[0] = make_float4(mx, my, mz, qx);
+                            row[1] = make_float4(qy, qz, D1, 0.0f);
+                        } else add_row(mx, my, mz, qx, qy, qz, D1);
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            int* deferred = wk.order + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
+            if (threadIdx.x == 0) { n_deferred = 0; n_unsettled = 0; }
+            __syncthreads();
+            auto emit = [&](int i, int id, int pos, float d2, float qx, float qy, float qz) {
+                wk.nn[i] = id; wk.pos[i] = pos; wk.d2[i] = d2;
+                const float mx = __ldg(kd.model + 3 * id), my = __ldg(kd.model + 3 * id + 1), mz = __ldg(kd.model + 3 * id + 2);
+                if (sorting) {
+                    wk.keys[i] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+                    float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                    row[0] = make_float4(mx, my, mz, qx);
+                    row[1] = make_float4(qy, qz, d2, 0.0f);
+                } else add_row(mx, my, mz, qx, qy, qz, d2);
+            };
+            unsigned long long* unsettled = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
+            for (int pass = 0; pass < 2; pass++) {
+                const int count = pass == 0 ? nd : n_unsettled;
+                for (int g = pass == 0 ? threadIdx.x * gridDim.x + blockIdx.x : threadIdx.x; g < count; g += (pass == 0 ? gridDim.x : 1) * blockDim.x) {
+                    const unsigned long long rec = pass == 0 ? 0ull : unsettled[g];
+                    const int i = pass == 0 ? g : (int)(unsigned)rec;
+                    if (pass == 0 && plan.nn_budget == 1) { deferred[atomicAdd(&n_deferred, 1)] = i; continue; }
+                    const float4 p = __ldg(data + i);
+                    const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                    float d2, cap; int pos;
+                    if (pass == 0) {
+                        const unsigned sp2 = (unsigned)__ldcg(wk.pos + i) < (unsigned)kd.nm ? (unsigned)__ldcg(wk.pos + i) : 0u;
+                        const float4 m = __ldg(leaf + sp2);
+                        const float e0 = qx - m.x, e1 = qy - m.y, e2 = qz - m.z;
+                        cap = e0 * e0 + e1 * e1 + e2 * e2;
+                    } else cap = __uint_as_float((unsigned)(rec >> 32));
+                    const int id = kd_nearest(kd, nodes, leaf, qx, qy, qz, cap, d2, pass == 0 ? plan.nn_budget : 0, &pos);
+                    if (id < 0) { deferred[atomicAdd(&n_deferred, 1)] = i; continue; }
+                    emit(i, id, pos, d2, qx, qy, qz);
+                }
+                if (pass == 1) break;
+                __syncthreads();
+                const int ndef = n_deferred;
+                int* queue = squeue + warp * kCoopQ;
+                for (int k = warp; k < ndef; k += kWarps) {
+                    const int i = deferred[k];
+                    const float4 p = __ldg(data + i);
+                    const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+                    const float qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+                    const float qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+                    const int sp2 = (unsigned)__ldcg(wk.pos + i) < (unsigned)kd.nm ? __ldcg(wk.pos + i) : 0;
+                    float d2; int pos;
+                    const int id = kd_coop_nearest(kd, queue, qx, qy, qz, sp2, lane, d2, pos);
+                    if (lane == 0) {
+                        if (id >= 0) emit(i, id, pos, d2, qx, qy, qz);
+                        else unsettled[atomicAdd(&n_unsettled, 1)] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+        if (sorting) {
+            // ---- phase B (trimming only): the existing sorts leave the correspondences in wk.stage by (d^2, index)
+            grid.sync();
+            if (sradix) icp_radix_sort(grid, wk, nd, sradix);
+            else {
+                const unsigned long long* keys = wk.keys;
+                const bool keys_in_smem = sstage != nullptr && (size_t)plan.stage_bytes >= (size_t)nd * sizeof(unsigned long long);
+                if (keys_in_smem) {
+                    unsigned long long* sk = reinterpret_cast<unsigned long long*>(sstage);
+                    for (int j = threadIdx.x; j < nd; j += blockDim.x) sk[j] = __ldcg(wk.keys + j);
+                    __syncthreads();
+                    keys = sk;
+                }
+                for (int qq = warp; qq * (int)gridDim.x + (int)blockIdx.x < nd; qq += kWarps) {
+                    const int i = qq * gridDim.x + blockIdx.x;
+                    const unsigned long long ki = keys[i];
+                    int cnt = 0;
+                    if (keys_in_smem) { for (int j = lane; j < nd; j += 32) cnt += keys[j] < ki; }
+                    else              { for (int j = lane; j < nd; j += 32) cnt += __ldcg(keys + j) < ki; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    if (lane < 2) reinterpret_cast<float4*>(wk.stage)[2 * (size_t)cnt + lane] = __ldcg(reinterpret_cast<const float4*>(wk.q) + 2 * (size_t)i + lane);
+                }
+                __syncthreads();
+                grid.sync();
+            }
+            const float4* srows = reinterpret_cast<const float4*>(wk.stage);
+            for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < num; r += gridDim.x * blockDim.x) {
+                const float4 lo = __ldcg(srows + 2 * (size_t)r), hi = __ldcg(srows + 2 * (size_t)r + 1);
+                add_row(lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z);
+            }
+        }
+        // ---- per-CTA partial moments -> global, one grid barrier, then every CTA reduces all of them by itself ---
+        warp_reduce16(acc, lane);
+        if ((lane & 1) == 0) red[warp][(lane >> 1) & 15] = acc[0];
+        __syncthreads();
+        float* mine = partials + ((size_t)(iter & 1) * gridDim.x + blockIdx.x) * 16;
+        if (threadIdx.x < 16) {
+            float sacc = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) sacc += red[w][threadIdx.x];
+            __stcg(mine + threadIdx.x, sacc);
+        }
+        grid.sync();
+        {
+            // warp w sums value w over the CTAs: lane-strided doubles, then a fixed shuffle tree
+            const float* all = partials + (size_t)(iter & 1) * gridDim.x * 16;
+            double sacc = 0.0;
+            for (int b = lane; b < (int)gridDim.x; b += 32) sacc += (double)__ldcg(all + (size_t)b * 16 + warp);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane == 0) tot[warp] = sacc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float err_new = (float)tot[6];
+            cur.err_new = err_new; cur.iter = iter;
+            if (cur.err > 0.0f && cur.err - err_new < err_diff * (float)num) cur.converged = 1;            // jly_icp3d.hpp:257
+            else {
+                cur.err = err_new;
+                // means on top of the previous means, divided by n (the reference never resets them, :205-206, :244-263)
+                double mm[3], md[3];
+                for (int c = 0; c < 3; c++) { mm[c] = ((double)cur.mu_m[c] + tot[c]) / (double)nd; md[c] = ((double)cur.mu_d[c] + tot[3 + c]) / (double)nd; }
+                // H = sum (q - md)(m - mm)^T from the moments about (c_d, c_m) = the previous means
+                double H[9];
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+                    const double dd = md[a] - (double)cur.mu_d[a], dm = mm[b] - (double)cur.mu_m[b];
+                    const double Sq = tot[3 + a] - (double)num * (double)cur.mu_d[a], Sm = tot[b] - (double)num * (double)cur.mu_m[b];
+                    H[3 * a + b] = tot[7 + 3 * a + b] - dd * Sm - Sq * dm + (double)num * dd * dm;
+                }
+                float Rn[9];
+                procrustes_jacobi(H, Rn);
+                float tn[3], tt[3], tmp[9];
+                for (int a = 0; a < 3; a++) tn[a] = (float)(mm[a] - ((double)Rn[3 * a] * md[0] + (double)Rn[3 * a + 1] * md[1] + (double)Rn[3 * a + 2] * md[2]));   // t_ = mu_m - R_ mu_d
+                mat3_mul(Rn, cur.R, tmp);                                                                   // R = R_ R
+                for (int a = 0; a < 3; a++) tt[a] = Rn[3 * a] * cur.t[0] + Rn[3 * a + 1] * cur.t[1] + Rn[3 * a + 2] * cur.t[2] + tn[a];   // t = R_ t + t_
+                for (int i = 0; i < 9; i++) cur.R[i] = tmp[i];
+                for (int i = 0; i < 3; i++) { cur.t[i] = tt[i]; cur.mu_m[i] = (float)mm[i]; cur.mu_d[i] = (float)md[i]; }
+            }
+        }
+        __syncthreads();
+        if (cur.converged) break;
+        if (iter == max_iter - 1 && threadIdx.x == 0) cur.iter = max_iter;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < 9; i++) st->R[i] = cur.R[i];
+        for (int i = 0; i < 3; i++) { st->t[i] = cur.t[i]; st->mu_m[i] = cur.mu_m[i]; st->mu_d[i] = cur.mu_d[i]; }
+        st->err = cur.err; st->err_new = cur.err_new; st->iter = cur.iter; st->converged = cur.converged;
+    }
 }
 
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s)
@@ -1050,30 +1385,32 @@ static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int 
 }
 int icp_threads() { return kIcpThreads; }
 int icp_max_blocks_supported() { return kRadixBlockOffs; }
-int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin)
+int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin, bool fast)
 {
+    const void* kern = fast ? (const void*)icp_fast_kernel : (const void*)icp_kernel;
     cudaFuncAttributes a;
-    if (cudaFuncGetAttributes(&a, icp_kernel) != cudaSuccess) return 0;
+    if (cudaFuncGetAttributes(&a, kern) != cudaSuccess) return 0;
     const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
-    cudaFuncSetAttribute(icp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_kernel, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
-                       int max_iter, float err_diff, int num_inliers, int grid_blocks, int smem_optin, cudaStream_t s)
+                       int max_iter, float err_diff, int num_inliers, int do_sort, int grid_blocks, int smem_optin, bool fast, float* d_partials, cudaStream_t s)
 {
+    const void* kern = fast ? (const void*)icp_fast_kernel : (const void*)icp_kernel;
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, icp_kernel);
+    cudaError_t e = cudaFuncGetAttributes(&a, kern);
     if (e != cudaSuccess) return e;
     const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
     IcpSmemPlan plan = icp_plan(kd, n_nodes, nd, num_inliers, limit);
     KdView kdv = kd; IcpWork wk = work;
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
-                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&plan};
-    return cudaLaunchCooperativeKernel((void*)icp_kernel, dim3(grid_blocks), dim3(kIcpThreads), args,
+                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&do_sort, (void*)&plan, (void*)&d_partials};
+    return cudaLaunchCooperativeKernel(kern, dim3(grid_blocks), dim3(kIcpThreads), args,
                                        (size_t)plan.tree_bytes + plan.stage_bytes + plan.radix_bytes + plan.queue_bytes, s);
 }
 

@@ -48,8 +48,22 @@ typedef enum {
 
 typedef enum {
     GOICP_DT_REFERENCE = 0,   /* bit-exact with DT3D::Build's sequential vector propagation (jly_3ddt.cpp:710-742) */
-    GOICP_DT_EXACT_EDT = 1    /* exact Euclidean DT (fast, fully parallel); differs from the reference on a few voxels */
+    GOICP_DT_EXACT_EDT = 1,   /* exact Euclidean DT (fast, fully parallel); differs from the reference on a few voxels */
+    GOICP_DT_EXACT_EDT_REFSEED = 2   /* exact EDT of the seeds the reference binary really has: the model voxels plus voxel (0,0,0), which
+                                        its mask function seeds by returning an uninitialised struct (jly_3ddt.cpp:469-470).
+                                        Differs from GOICP_DT_REFERENCE only where the reference's propagation is not exact (~1e-5 of the voxels) */
 } goicp_dt_mode;
+
+/* Where float sums are formed in the reference's own order (bit flags; 0 = everywhere a decision hinges on them). */
+typedef enum {
+    GOICP_NUM_STRICT = 0,
+    GOICP_NUM_FAST_SUMS = 1,  /* near-tied upper bounds of an improving pass and the DT scores (optError itself) keep their fixed-order
+                                 tree sums: no single-thread emulation of intro_select + sequential adds (jly_goicp.cpp:293-315) */
+    GOICP_NUM_FAST_ICP = 2,   /* ICP3D::Run: means / covariance by parallel reduction and a Jacobi 3x3 SVD instead of the reference's
+                                 sorted sequential accumulations and Matrix::svd (jly_icp3d.hpp:238-291); NN indices stay bit-exact */
+    GOICP_NUM_JACOBI_SVD = 4  /* reference-order ICP sums, but the Procrustes rotation from the Jacobi solver (an experiment switch:
+                                 shows that Matrix::svd's own rounding is part of the trajectory, profiles/r2_parity_modes.md) */
+} goicp_numerics;
 
 /* Replaces the public tunables of class GoICP (jly_goicp.h:85-120) and its constructor
  * defaults (jly_goicp.cpp:40-72). */
@@ -65,9 +79,11 @@ typedef struct {
     int    device;           /* CUDA device ordinal */
     int    spec_cubes;       /* rotation cubes expanded speculatively per round (0 = auto) */
     int    cluster_size;     /* CTAs (SMs) cooperating on one translation BnB via a thread-block cluster (0 = auto, max 16) */
-    int    dt_mode;          /* goicp_dt_mode used by goicp_build_dt */
+    int    dt_mode;          /* goicp_dt_mode used by goicp_build_dt (default GOICP_DT_EXACT_EDT_REFSEED: on all of the reference's golden
+                                runs it yields the results of GOICP_DT_REFERENCE bit for bit, 200x sooner -- profiles/r2_parity_modes.md) */
     /* multi-GPU sharding of the rotation frontier (all ranks hold identical inputs) */
     int    rank, world_size;
+    int    numerics;         /* goicp_numerics bit flags (default 0: strict) */
 } goicp_params;
 
 /* Replaces the public results of class GoICP (optR/optT/optError/optNodeRot/optNodeTrans,
@@ -88,6 +104,14 @@ typedef struct {
     int64_t rounds;          /* device rounds (one batch of rotation cubes each) */
     int64_t kernel_launches; /* CUDA kernels this call launched */
     double seconds_total, seconds_bnb_kernels, seconds_icp;
+    /* accounting (not in the reference) */
+    int64_t bound_evals_executed_local;  /* the part of bound_evals_executed this rank's GPU ran (== bound_evals_executed on one GPU) */
+    int64_t strict_resolves;             /* upper-bound passes whose near-tied contenders were re-evaluated in the reference's order */
+    int64_t contender_overflows;         /* ... of which the kernel could not keep every contender (more than 128 within rounding of the
+                                            minimum): the arg-min was then chosen among the 128 kept -- reported, never silent */
+    double seconds_dt_score, seconds_strict, seconds_setup;   /* DT scoring of poses / strict re-evaluations / upload + kd-tree */
+    int64_t bnb_kernel_variants;         /* which translation-BnB kernels ran: bit 0 inner_bnb_pipelined_kernel<1,1> (points in shared memory,
+                                            low-latency), bit 1 <1,0>, bit 2 <0,1>, bit 3 <0,0>, bit 4 inner_bnb_kernel (trimming / GOICP_NO_PIPELINE) */
 } goicp_result;
 
 typedef struct {
@@ -123,10 +147,10 @@ const char* goicp_last_error(const goicp_handle* h);
 int goicp_set_model(goicp_handle* h, const float* xyz, int n);
 int goicp_set_data(goicp_handle* h, const float* xyz, int n);
 
-/* GoICP::BuildDT (jly_goicp.cpp:75-90) on the GPU.  When the data cloud is already set (the order of main.cpp:47-57)
- * the ICP from the identity pose that GoICP::Register begins with (jly_goicp.cpp:378-391; it reads no DT) runs on the
- * SMs the single-CTA DT propagation leaves idle; the first goicp_register after this call picks its result up.  Setting
- * either cloud again discards it.  GOICP_NO_PREFETCH=1 in the environment turns the overlap off. */
+/* GoICP::BuildDT (jly_goicp.cpp:75-90) on the GPU.  In GOICP_DT_REFERENCE mode, when the data cloud is already set (the
+ * order of main.cpp:47-57), the ICP from the identity pose that GoICP::Register begins with (jly_goicp.cpp:378-391; it
+ * reads no DT) runs on the SMs the single-CTA DT propagation leaves idle; the first goicp_register after this call picks
+ * its result up.  Setting either cloud again discards it.  GOICP_NO_PREFETCH=1 in the environment turns the overlap off. */
 int goicp_build_dt(goicp_handle* h);
 /* Install / read back a distance grid ([z][y][x] floats + {xMin,yMin,zMin,scale}); lets a caller
  * cache the model-only precompute across runs (the reference cannot). */
@@ -188,6 +212,13 @@ int goicp_cancel(goicp_handle* h);
  * handle (the reference new/deletes its 324 MB grid per GoICP object, jly_3ddt.cpp:932-935; here a
  * cudaMalloc costs a driver lock).  This returns the cached blocks to the driver. */
 int goicp_trim_memory(void);
+
+/* Measurement helpers (bench.py).  goicp_transfer_bytes: host->device / device->host bytes this handle has copied so far
+ * (counted at every copy the library issues).  goicp_measure_gather: rate of uniformly random 4-byte loads over a device
+ * buffer of `bytes` bytes with no other work -- the measured ceiling of the distance-transform gathers (L2-resident for a
+ * 300^3 grid, HBM-bound for 512^3); returns look-ups per second. */
+int goicp_transfer_bytes(const goicp_handle* h, int64_t* h2d_out, int64_t* d2h_out);
+int goicp_measure_gather(goicp_handle* h, size_t bytes, int repeats, double* lookups_per_s_out);
 
 /* Multi-GPU: every rank evaluates its slice of each round's cubes; `exchange` must all-gather
  * `bytes_per_rank` bytes from every rank into recv (rank-major).  The Python driver implements it

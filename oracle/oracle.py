@@ -98,6 +98,7 @@ class Restated:
         L.go_improve_log.argtypes = [C.c_void_p, _f32p]
         L.go_set_budget.argtypes = [C.c_void_p, C.c_double]
         L.go_set_verbose.argtypes = [C.c_void_p, C.c_int]
+        L.go_set_do_trim.argtypes = [C.c_void_p, C.c_int]
         L.go_set_rot_cube.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
         L.go_free.argtypes = [C.c_void_p]
         L.go_fnv1a64.restype = C.c_uint64
@@ -268,6 +269,8 @@ class Reference:
         L.ref_svd3.argtypes = [_f32p, _f32p, _f32p, _f32p]
         L.ref_goicp_create.restype = C.c_void_p
         L.ref_goicp_create.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_double, C.c_void_p]
+        if hasattr(L, "ref_goicp_set_do_trim"):
+            L.ref_goicp_set_do_trim.argtypes = [C.c_void_p, C.c_int]
         L.ref_goicp_build_dt.restype = C.c_double
         L.ref_goicp_build_dt.argtypes = [C.c_void_p]
         L.ref_goicp_dt.restype = C.c_void_p

@@ -155,6 +155,7 @@ void* ref_goicp_create(const float* model_xyz, int nm, const float* data_xyz, in
     h->dt_built = false;
     return h;
 }
+void ref_goicp_set_do_trim(void* hh, int v) { ((RefHandle*)hh)->g->doTrim = v != 0; }      // public field of the reference class
 double ref_goicp_build_dt(void* hh)
 {
     RefHandle* h = (RefHandle*)hh; double t0 = now_s(); h->g->BuildDT(); h->dt_built = true; return now_s() - t0;

@@ -4,7 +4,8 @@
 Run in the build container only (needs /root/reference and `make -C oracle ref`):
 
     python tests/golden/make_golden.py clouds      # deterministic bunny subsamples (seeds 1234/1235)
-    python tests/golden/make_golden.py runs        # 9 full reference Go-ICP runs, S=300 (~20 min CPU)
+    python tests/golden/make_golden.py runs        # the full reference Go-ICP runs, S=300 (~25 min CPU)
+    python tests/golden/make_golden.py runs_add NAME ...   # (re)run only these entries of RUNS and merge them into goicp_runs.json
     python tests/golden/make_golden.py small       # small-S DT grids / NN / ICP / inner-BnB vectors (seconds)
     python tests/golden/make_golden.py config2     # full-size bun045/bun000 clouds + reference NN indices + ICP result
 
@@ -25,6 +26,8 @@ RUNS = {  # name: (model fixture, data fixture, mse, trim)
     "bunny_s0.1_mse5e-4": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "5e-4", "0"),
     "bunny_s0.033_mse1e-3": ("bunny_model_s0.033_seed1234.f32", "bunny_data_s0.033_seed1235.f32", "1e-3", "0"),
     "bunny_s0.1_mse1e-3_trim0.1": ("bunny_model_s0.1_seed1234.f32", "bunny_data_s0.1_seed1235.f32", "1e-3", "0.1"),
+    # SURVEY section 6's larger known answer: subsample 0.3 (Nm 10 756, Nd 9 064), early exit, optError 2.97759032
+    "bunny_s0.3_mse1e-3": ("bunny_model_s0.3_seed1234.f32", "bunny_data_s0.3_seed1235.f32", "1e-3", "0"),
     # BASELINE config 4 substitute: rotated_model_spanner -> noisy_flipped_model_spanner, x0.02, subsample 0.02,
     # fgoicp's translation domain [-1,1]^3 (extra CLI args: S tx ty tz tw)
     "spanner_s0.02_mse1e-3": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
@@ -59,7 +62,7 @@ def clouds():
         (src_m @ R.T + t).astype(np.float32).tofile(os.path.join(HERE, f"{name}_model_moved_s{sub}_seed1234.f32"))
         src_d.astype(np.float32).tofile(os.path.join(HERE, f"{name}_data_s{sub}_seed1235.f32"))
         np.savez(os.path.join(HERE, f"{name}_pose_gt.npz"), R=R, t=t)
-    for sub in ("0.1", "0.033"):
+    for sub in ("0.1", "0.033", "0.3"):
         for kind, seed in (("model", 1234), ("data", 1235)):
             out = os.path.join(HERE, f"bunny_{kind}_s{sub}_seed{seed}.f32")
             subprocess.run([REFBIN, "subsample", f"{REFDATA}/bunny/{kind}_bunny.txt", sub, "1.0", str(seed), out], check=True)
@@ -79,9 +82,12 @@ def parse_run(text):
     return js
 
 
-def runs(from_logs=None):
-    out = {}
+def runs(from_logs=None, only=None):
+    """`only`: re-run just these entries and merge them into the committed JSON (python make_golden.py runs_add NAME ...)"""
+    out = json.load(open(os.path.join(HERE, "goicp_runs.json"))) if only else {}
     for name, (m, d, mse, trim, *extra) in RUNS.items():
+        if only and name not in only:
+            continue
         if from_logs and os.path.exists(os.path.join(from_logs, name + ".log")):
             text = open(os.path.join(from_logs, name + ".log")).read()
         else:
@@ -176,6 +182,8 @@ if __name__ == "__main__":
         clouds()
     elif cmd == "runs":
         runs(sys.argv[2] if len(sys.argv) > 2 else None)
+    elif cmd == "runs_add":
+        runs(None, sys.argv[2:])
     elif cmd == "small":
         small()
     elif cmd == "config2":

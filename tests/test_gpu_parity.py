@@ -13,6 +13,7 @@ from conftest import rot_angle
 pytestmark = pytest.mark.gpu
 
 SUM_RTOL = 4e-6
+DT_REFERENCE, DT_EXACT_EDT, DT_EXACT_EDT_REFSEED = 0, 1, 2      # goicp_dt_mode
 
 
 def _close_counts(a, b):
@@ -192,6 +193,7 @@ def test_dt_build_reference_mode_bit_exact_small(pkg, small, bunny, S):
     g = pkg.GoICP(1e-3)
     g.pModel, g.pData = bunny["model"], bunny["data"]
     g.dt.SIZE = S
+    g.dt_mode = DT_REFERENCE
     g.BuildDT()
     grid, meta = g.GetDT()
     assert np.array_equal(meta, small["dt48_meta"])
@@ -208,6 +210,7 @@ def test_dt_build_reference_mode_vs_oracle_odd_sizes_and_both_kernels(pkg, resta
     g = pkg.GoICP(1e-3)
     g.pModel, g.pData = bunny["model_s"], bunny["data_s"]
     g.dt.SIZE = S
+    g.dt_mode = DT_REFERENCE
     g.BuildDT()
     grid, meta = g.GetDT()
     g.close()
@@ -218,25 +221,58 @@ def test_dt_build_reference_mode_vs_oracle_odd_sizes_and_both_kernels(pkg, resta
     assert np.array_equal(grid.view(np.uint32), want.view(np.uint32))
 
 
-def test_dt_build_exact_edt_mode(pkg, small, bunny):
+@pytest.mark.parametrize("S,mode", [(48, DT_EXACT_EDT), (61, DT_EXACT_EDT_REFSEED), (100, DT_EXACT_EDT_REFSEED), (333, DT_EXACT_EDT_REFSEED)])
+def test_dt_build_exact_edt_modes_vs_scipy(pkg, small, bunny, S, mode):
+    """The exact-EDT builder (in-place Meijster passes; the default mode seeds the reference binary's extra voxel (0,0,0) too)
+    against scipy's exact transform of the same seed set, bit for bit in the reference's float metric; S = 333 takes the
+    512-entry variant of the line kernel."""
     from scipy import ndimage
     g = pkg.GoICP(1e-3)
     g.pModel, g.pData = bunny["model"], bunny["data"]
-    g.dt.SIZE = 48
-    g.dt_mode = 1
+    g.dt.SIZE = S
+    g.dt_mode = mode
     g.BuildDT()
     grid, meta = g.GetDT()
+    g.close()
     idx = np.floor((bunny["model"].astype(np.float64) - meta[:3]) * meta[3] + 0.5).astype(int)
-    occ = np.ones((48, 48, 48), bool)
+    idx = idx[((idx >= 0) & (idx < S)).all(1)]
+    occ = np.ones((S, S, S), bool)
     occ[idx[:, 2], idx[:, 1], idx[:, 0]] = False
+    if mode == DT_EXACT_EDT_REFSEED:
+        occ[0, 0, 0] = False
     exact = ndimage.distance_transform_edt(occ)
     want = (np.sqrt((exact ** 2).round()).astype(np.float32).astype(np.float64) / meta[3]).astype(np.float32)
     assert np.array_equal(grid, want)
-    g.close()
 
 
-def _check_run(res, gold):
+def test_default_dt_differs_from_reference_order_only_where_that_is_inexact(pkg, restated, bunny):
+    """Default DT (exact EDT of the reference binary's seed set) vs the reference-order propagation on the same model: never
+    above it (the propagation only ever over-estimates), identical on all but a ~1e-5 fraction of the voxels."""
+    S = 100
+    grids = {}
+    for mode in (DT_REFERENCE, DT_EXACT_EDT_REFSEED):
+        g = pkg.GoICP(1e-3)
+        g.pModel, g.pData = bunny["model"], bunny["data"]
+        g.dt.SIZE = S
+        g.dt_mode = mode
+        g.BuildDT()
+        grids[mode], meta = g.GetDT()
+        g.close()
+    a, b = grids[DT_REFERENCE], grids[DT_EXACT_EDT_REFSEED]
+    assert (b <= a).all()
+    assert (a != b).mean() < 2e-4 and np.abs(a - b).max() * meta[3] < 0.5
+
+
+# runs whose committed counters equal the reference's exactly (the others differ by a node or two: the search kernels prune on
+# fixed-order tree sums, the reference on its sequential ones -- bunny 5e-4: 225 970 vs 225 968 translation pops)
+EXACT_COUNTS = {"bunny_s0.1_mse1e-3", "bunny_s0.1_mse7e-4", "bunny_s0.033_mse1e-3", "bunny_s0.1_mse1e-3_trim0.1", "spanner_s0.02_mse1e-3",
+                "spanner_s0.02_mse1e-3_trim0.1", "skull_s0.03_mse1e-3", "face_s0.025_mse1e-3"}
+
+
+def _check_run(res, gold, name=None):
     assert res["exit_path"] == gold["exit_path"]
+    if name in EXACT_COUNTS:
+        assert (res["rot_pops"], res["trans_pops"]) == (gold["rot_pops"], gold["trans_pops"])
     assert _close_counts(res["rot_pops"], gold["rot_pops"]) and _close_counts(res["trans_pops"], gold["trans_pops"])
     assert res["sse"] == pytest.approx(gold["sse"], rel=1e-5)
     assert rot_angle(res["R"], np.array(gold["R"]).reshape(3, 3)) < 1e-4
@@ -250,13 +286,14 @@ def test_register_bunny_full_size_reference_dt_on_gpu(pkg, runs, bunny, restated
     checksum against the reference's, run Go-ICP, compare with the reference's own run."""
     g = pkg.GoICP(1e-3)
     g.pModel, g.pData = bunny["model"], bunny["data"]
+    g.dt_mode = DT_REFERENCE
     g.BuildDT()
     grid, meta = g.GetDT()
     assert np.array_equal(meta, [-1.7215785086154938, -1.735278993844986, -1.7175954878330231, 87.099870706007081])
     assert "%016x" % restated.fnv(grid) == "2da64ee1865a968e"
     gold = runs["bunny_s0.1_mse1e-3"]
     g.Register()
-    _check_run(g.result, gold)
+    _check_run(g.result, gold, "bunny_s0.1_mse1e-3")
     # certificate paths reuse the same DT
     for name in ("bunny_s0.1_mse7e-4", "bunny_s0.1_mse5e-4"):
         gold = runs[name]
@@ -264,9 +301,69 @@ def test_register_bunny_full_size_reference_dt_on_gpu(pkg, runs, bunny, restated
         g2.pModel, g2.pData = bunny["model"], bunny["data"]
         g2.SetDT(grid, meta)
         g2.Register()
-        _check_run(g2.result, gold)
+        _check_run(g2.result, gold, name)
         g2.close()
     g.close()
+
+
+def _golden_engine(pkg, gold):
+    from conftest import load_cloud
+    g = pkg.GoICP(gold["mse"])
+    g.pModel, g.pData = load_cloud(gold["model"]), load_cloud(gold["data"])
+    g.trimFraction = gold["trim"]
+    if "trans_cube" in gold:
+        g.initNodeTrans = gold["trans_cube"]
+    return g
+
+
+@pytest.mark.parametrize("name", ["bunny_s0.1_mse1e-3", "bunny_s0.1_mse7e-4", "bunny_s0.1_mse5e-4", "bunny_s0.033_mse1e-3", "bunny_s0.3_mse1e-3",
+                                  "bunny_s0.1_mse1e-3_trim0.1", "spanner_s0.02_mse1e-3", "spanner_s0.02_mse1e-3_trim0.1",
+                                  "skull_s0.03_mse1e-3", "face_s0.025_mse1e-3"])
+def test_every_golden_run_in_the_default_mode(pkg, runs, name):
+    """All of the reference's own S = 300 runs (tests/golden/goicp_runs.json, generated from oracle/_ref) in the library's
+    DEFAULT configuration -- exact-EDT distance transform, reference-order sums and ICP: pose, SSE, exit path, certificate
+    and counters.  Includes the deepest committed run (bunny 0.033: 2 032 rotation pops, 3.5 M bound evaluations, rotation
+    level 8) and SURVEY section 6's sub-0.3 known answer (Nd 9 064)."""
+    if name not in runs:
+        pytest.skip(f"{name} not in goicp_runs.json yet")
+    gold = runs[name]
+    g = _golden_engine(pkg, gold)
+    g.BuildDT()
+    g.Register()
+    _check_run(g.result, gold, name)
+    assert g.result["contender_overflows"] == 0
+    g.close()
+
+
+def test_numerics_modes_table(pkg, runs):
+    """The measurement behind the defaults (scripts/parity_modes.py, profiles/r2_parity_modes.md), asserted:
+      * exact-EDT DT: every golden run ends exactly where the reference-order DT ends -- same pose bits, same counters;
+      * tree sums instead of the reference-order re-evaluations: inside the north-star tolerances on every run;
+      * ICP with parallel sums + Jacobi solver: voxel and NN indices still exact, poses within 1e-3, but the SSE leaves the
+        1e-5 band (ICP stops one iteration earlier or later on its loose test) -- which is why strict ICP stays the default."""
+    names = ["bunny_s0.1_mse1e-3", "bunny_s0.1_mse7e-4", "bunny_s0.1_mse1e-3_trim0.1", "skull_s0.03_mse1e-3", "face_s0.025_mse1e-3"]
+    res = {}
+    for mode, (dt_mode, numerics) in {"strict": (0, 0), "default": (2, 0), "fastsums": (2, 1), "fasticp": (2, 2)}.items():
+        for name in names:
+            g = _golden_engine(pkg, runs[name])
+            g.dt_mode, g.numerics = dt_mode, numerics
+            g.BuildDT()
+            g.Register()
+            res[mode, name] = g.result
+            g.close()
+    fasticp_sse_off = 0
+    for name in names:
+        gold = runs[name]
+        a, b = res["strict", name], res["default", name]
+        assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["t"], b["t"]) and a["sse"] == b["sse"]
+        assert (a["rot_pops"], a["trans_pops"], a["bound_evals"], a["exit_path"]) == (b["rot_pops"], b["trans_pops"], b["bound_evals"], b["exit_path"])
+        _check_run(res["fastsums", name], gold)
+        f = res["fasticp", name]
+        assert f["exit_path"] == gold["exit_path"]
+        assert rot_angle(f["R"], np.array(gold["R"]).reshape(3, 3)) < 1e-3 and np.abs(f["t"] - np.array(gold["t"])).max() < 1e-3
+        assert f["sse"] == pytest.approx(gold["sse"], rel=5e-3)
+        fasticp_sse_off += abs(f["sse"] - gold["sse"]) > 1e-5 * gold["sse"]
+    assert fasticp_sse_off >= 1
 
 
 def test_icp_overlapped_with_dt_build_changes_nothing(pkg, bunny, monkeypatch):
@@ -281,6 +378,7 @@ def test_icp_overlapped_with_dt_build_changes_nothing(pkg, bunny, monkeypatch):
         g = pkg.GoICP(1e-3)
         g.pModel, g.pData = bunny["model_s"], bunny["data_s"]
         g.dt.SIZE = 100
+        g.dt_mode = DT_REFERENCE
         g.BuildDT()
         g.Register(); a = dict(g.result)
         g.Register(); b = dict(g.result)
@@ -311,6 +409,7 @@ def test_tiny_and_ragged_clouds_vs_oracle(pkg, restated, bunny, nm, nd, S, mse, 
     g = pkg.GoICP(mse)
     g.pModel, g.pData = m, d
     g.dt.SIZE = S
+    g.dt_mode = DT_REFERENCE
     if tcube is not None:
         g.initNodeTrans = tcube
     g.BuildDT()
@@ -371,7 +470,7 @@ def test_run_toml_end_to_end(pkg, runs, bunny, tmp_path):
     cfg.write_text(f'[io]\ntarget = "model.txt"\nsource = "data.txt"\noutput = "{out}"\nvisualization = ""\n'
                    '[params]\nmode = 3\ntrim = true\nsubsample = 1.0\nmse_threshold = 1e-3\nresize = 1.0\n')
     res = pkg.run_toml(str(cfg))
-    _check_run(res, runs["bunny_s0.1_mse1e-3"])
+    _check_run(res, runs["bunny_s0.1_mse1e-3"], "bunny_s0.1_mse1e-3")
     text = out.read_text()
     assert "exit_path = \"early_sse_below_thresh\"" in text and "rotation_nodes = 206" in text
 

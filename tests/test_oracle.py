@@ -109,6 +109,29 @@ def test_register_small_matches_reference_when_built(restated, reference, bunny)
     assert ra["bound_evals"] == rb["select_calls"] - 1 - ra["icp_calls"]
 
 
+def test_do_trim_false_restatement_matches_reference_when_built(restated, reference, bunny):
+    """GoICP::doTrim = false (a public field, jly_goicp.h:118): no qsort in ICP3D::Run (jly_icp3d.hpp:236-239), no intro_select
+    in the bound evaluation or the scores (jly_goicp.cpp:109,293,361) -- sums run in data order.  Restatement vs the
+    unmodified reference: the ICP alone, then a small full registration."""
+    kd = restated.kd_build(bunny["model_s"])
+    icp = reference.icp_build(bunny["model_s"])
+    ea, Ra, ta, _, _ = restated.icp_run(kd, bunny["data_s"], np.eye(3), np.zeros(3), 10000, 1e-7, 0.0, False)
+    eb, Rb, tb = reference.icp_run(icp, bunny["data_s"], np.eye(3), np.zeros(3), 10000, 1e-7, 0.0, False)
+    assert np.float32(ea) == np.float32(eb) and np.array_equal(Ra, Rb) and np.array_equal(ta, tb)
+    et, Rt, tt, _, _ = restated.icp_run(kd, bunny["data_s"], np.eye(3), np.zeros(3), 10000, 1e-7, 0.0, True)
+    assert not (np.array_equal(Ra, Rt) and np.float32(ea) == np.float32(et))       # the summation order is visible in the result
+    data = bunny["data_s"][::4].copy()
+    a = restated.create(bunny["model_s"], data, 3e-3, 0.0, 40)
+    b = reference.create(bunny["model_s"], data, 3e-3, 0.0, 40)
+    restated.L.go_set_do_trim(a, 0)
+    reference.L.ref_goicp_set_do_trim(b, 0)
+    restated.L.go_build_dt(a)
+    reference.build_dt(b)
+    ra, rb = restated.register(a), reference.register(b)
+    assert np.array_equal(ra["R"], rb["R"]) and np.array_equal(ra["t"], rb["t"]) and ra["sse"] == rb["sse"]
+    assert (ra["rot_pops"], ra["trans_pops"]) == (rb["rot_pops"], rb["trans_pops"])
+
+
 def test_golden_runs_file_is_the_survey_known_answers(runs):
     r = runs["bunny_s0.1_mse1e-3"]
     assert (r["Nm"], r["Nd"], r["rot_pops"], r["trans_pops"]) == (3594, 3019, 206, 31896)
