@@ -32,6 +32,12 @@ RUNS = {  # name: (model fixture, data fixture, mse, trim)
     # fgoicp's translation domain [-1,1]^3 (extra CLI args: S tx ty tz tw)
     "spanner_s0.02_mse1e-3": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0", "300", "-1", "-1", "-1", "2"),
     "spanner_s0.02_mse1e-3_trim0.1": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-3", "0.1", "300", "-1", "-1", "-1", "2"),
+    # the same pair below the scans' noise floor, where the first ICP no longer certifies and the BnB has to search: mse 3e-4
+    # (89 / 218 rotation pops), and the TOML's own mse 1e-4 (test/spanner_goicp.toml:15-20; 5 305 rotation pops, 154 M bound
+    # evaluations -- 3.5 h of the reference on one core; with trimming 0.1 it needs > 7 h and is not committed)
+    "spanner_s0.02_mse3e-4": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "3e-4", "0", "300", "-1", "-1", "-1", "2"),
+    "spanner_s0.02_mse3e-4_trim0.1": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "3e-4", "0.1", "300", "-1", "-1", "-1", "2"),
+    "spanner_s0.02_mse1e-4": ("spanner_model_noisy_flipped_s0.02_seed1234.f32", "spanner_data_rotated_s0.02_seed1235.f32", "1e-4", "0", "300", "-1", "-1", "-1", "2"),
     # BASELINE config 3 substitute (the Artec targets are missing): target = the scan itself moved by a seeded rigid
     # motion (150 deg / 110 deg about a random axis, |t| <= 0.25) and subsampled with another seed, translation domain [-1,1]^3.
     # Unlike the spanner pair the first ICP does not solve these: 23 / 250 rotation cubes are expanded.
