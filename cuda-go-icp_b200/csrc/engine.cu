@@ -647,7 +647,8 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin, fast);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     // queries are interleaved over the CTAs, 32 per CTA and pass: use every SM the cooperative launch allows
-    const int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32), blocks_cap));
+    int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32), blocks_cap));
+    if (const char* e = getenv("GOICP_ICP_BLOCKS")) blocks = std::max(1, std::min(std::min(max_blocks, icp_max_blocks_supported()), std::min(atoi(e), blocks_cap)));   // experiments
     if (fast) CUDA_TRY(h, h->d_icp_partials.reserve((size_t)2 * 16 * blocks));
     CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, (h->p.do_trim ? 1 : 0) | ((h->p.numerics & GOICP_NUM_JACOBI_SVD) ? 2 : 0), blocks, h->max_smem_optin, fast, h->d_icp_partials.p, h->stream));
     h->launches++;
