@@ -77,7 +77,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
-               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_svd3", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
                "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_transfer_bytes", "goicp_measure_gather", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 
@@ -132,6 +132,7 @@ def lib():
         L.goicp_inner_bnb.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.goicp_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_kdtree_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.goicp_svd3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.goicp_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.POINTER(IcpResult)]
         L.goicp_icp_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
         L.goicp_dt_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
@@ -368,6 +369,14 @@ class GoICP:
         d2 = np.zeros(len(q), np.float32)
         self._check(self.L.goicp_nn(self._handle(), q.ctypes.data, len(q), idx.ctypes.data, d2.ctypes.data))
         return idx, d2
+
+    def SVD3(self, H):
+        """Matrix::svd of a batch of 3x3 matrices (matrix.cpp:602-830): returns U (n,3,3), W (n,3), V (n,3,3)."""
+        H = _f32(H).reshape(-1, 9)
+        n = len(H)
+        U = np.zeros((n, 9), np.float32); W = np.zeros((n, 3), np.float32); V = np.zeros((n, 9), np.float32)
+        self._check(self.L.goicp_svd3(self._handle(), H.ctypes.data, n, U.ctypes.data, W.ctypes.data, V.ctypes.data))
+        return U.reshape(n, 3, 3), W, V.reshape(n, 3, 3)
 
     def ICP(self, R0=None, t0=None, max_iter=0, err_diff=-1.0):
         """ICP3D<float>::Run (jly_icp3d.hpp:180-295)."""

@@ -958,6 +958,22 @@ int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float
     return GOICP_OK;
 }
 
+int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3_out, float* V9_out)
+{
+    if (!h || !H9 || n < 0 || !U9_out || !W3_out || !V9_out) return fail(h, GOICP_ERR_INVALID, "svd3: bad arguments");
+    if (n == 0) return GOICP_OK;
+    int rc = ensure_cuda(h); if (rc) return rc;
+    CUDA_TRY(h, h->d_q.reserve((size_t)30 * n));
+    float* dH = h->d_q.p; float* dU = dH + (size_t)9 * n; float* dW = dU + (size_t)9 * n; float* dV = dW + (size_t)3 * n;
+    CUDA_TRY(h, xfer(h, dH, H9, sizeof(float) * 9 * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_svd3(dH, n, dU, dW, dV, h->stream));
+    CUDA_TRY(h, xfer(h, U9_out, dU, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, W3_out, dW, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, xfer(h, V9_out, dV, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
 int goicp_kdtree_host(const float* model_xyz, int n, int32_t* nodes7_out, int capacity_nodes, int32_t* vind_out, float* bbox6_out)
 {
     if (!model_xyz || n <= 0) return -GOICP_ERR_INVALID;

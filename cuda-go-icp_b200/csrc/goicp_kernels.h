@@ -57,6 +57,7 @@ struct IcpWork {            // per-iteration device scratch of the ICP kernel
     unsigned* hist;         // 256 * (warps of the grid): digit-major histogram / scanned bases of the radix sort
     unsigned* blocksum;     // 1024: per-CTA chunk totals of that scan
 };
+cudaError_t launch_svd3(const float* d_H9, int n, float* d_U9, float* d_W3, float* d_V9, cudaStream_t s);
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s);
 // Whole ICP3D::Run as ONE cooperative kernel (grid-synchronous iterations, no host round trips).
 // do_sort = the reference's do_trim (it sorts the correspondences only then, jly_icp3d.hpp:236-239); fast = GOICP_NUM_FAST_ICP

@@ -341,176 +341,267 @@ __device__ float svd_pythag(float a, float b)
 }
 __device__ __forceinline__ float svd_sign(float a, float b) { return b >= 0.0f ? fabsf(a) : -fabsf(a); }
 
+// Register-resident form: every index below is a compile-time constant once the loops are unrolled -- the three passes over
+// k are unrolled and the data-dependent lower end l of a QR sweep is dispatched to a <K, L> instantiation -- so U, V, w and
+// rv1 live in registers instead of local memory (the one-thread solve sat on the critical path of every ICP iteration:
+// 14.7 k cycles with the arrays in local memory).  The floating-point operations and their order are the reference's.
+template <int K, int L>
+__device__ __forceinline__ bool svd_qr_sweep(float (&U)[3][3], float (&V)[3][3], float (&w)[3], float (&rv1)[3], const float anorm, const int flag)
+{
+    constexpr int m = 3, n = 3;
+    float c, f, g, h, s, x, y, z;
+    if (flag) {
+        constexpr int nm = L - 1;                        // flag is only set with L >= 1 (rv1[0] == 0 always ends the search at l = 0 with flag = 0)
+        c = 0.0f; s = 1.0f;
+#pragma unroll
+        for (int i = L; i <= K; i++) {
+            f = s * rv1[i];
+            rv1[i] = c * rv1[i];
+            if ((float)(fabsf(f) + anorm) == anorm) break;
+            g = w[i];
+            h = svd_pythag(f, g);
+            w[i] = h;
+            h = (float)(1.0 / (double)h);
+            c = g * h;
+            s = -f * h;
+#pragma unroll
+            for (int j = 0; j < m; j++) {
+                y = U[j][nm < 0 ? 0 : nm]; z = U[j][i];
+                U[j][nm < 0 ? 0 : nm] = y * c + z * s;
+                U[j][i] = z * c - y * s;
+            }
+        }
+    }
+    z = w[K];
+    if (L == K) {
+        if (z < 0.0f) {
+            w[K] = -z;
+#pragma unroll
+            for (int j = 0; j < n; j++) V[j][K] = -V[j][K];
+        }
+        return true;                                     // converged for this k
+    }
+    constexpr int nm = K - 1 < 0 ? 0 : K - 1;            // (L < K implies K >= 1)
+    x = w[L]; y = w[nm]; g = rv1[nm]; h = rv1[K];
+    f = (float)((double)((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * (double)h * (double)y));
+    g = svd_pythag(f, 1.0f);
+    f = ((x - z) * (x + z) + h * ((y / (f + svd_sign(g, f))) - h)) / x;
+    c = s = 1.0f;
+#pragma unroll
+    for (int j = L; j <= nm; j++) {
+        const int i = j + 1 > 2 ? 2 : j + 1;
+        g = rv1[i]; y = w[i];
+        h = s * g; g = c * g;
+        z = svd_pythag(f, h);
+        rv1[j] = z;
+        c = f / z; s = h / z;
+        f = x * c + g * s;
+        g = g * c - x * s;
+        h = y * s;
+        y *= c;
+#pragma unroll
+        for (int jj = 0; jj < n; jj++) {
+            x = V[jj][j]; z = V[jj][i];
+            V[jj][j] = x * c + z * s;
+            V[jj][i] = z * c - x * s;
+        }
+        z = svd_pythag(f, h);
+        w[j] = z;
+        if (z != 0.0f) { z = (float)(1.0 / (double)z); c = f * z; s = h * z; }
+        f = c * g + s * y;
+        x = c * y - s * g;
+#pragma unroll
+        for (int jj = 0; jj < m; jj++) {
+            y = U[jj][j]; z = U[jj][i];
+            U[jj][j] = y * c + z * s;
+            U[jj][i] = z * c - y * s;
+        }
+    }
+    rv1[L] = 0.0f; rv1[K] = f; w[K] = x;
+    return false;
+}
+
+template <int K>
+__device__ __forceinline__ void svd_qr_k(float (&U)[3][3], float (&V)[3][3], float (&w)[3], float (&rv1)[3], const float anorm)
+{
+    for (int its = 0; its < 30; its++) {
+        // the reference's search for l (:741-749), over constant indices
+        int flag = 1, l = -1;
+#pragma unroll
+        for (int ll = K; ll >= 0; ll--) {
+            if (l < 0) {
+                if ((float)(fabsf(rv1[ll]) + anorm) == anorm) { flag = 0; l = ll; }
+                else if (ll >= 1 && (float)(fabsf(w[ll >= 1 ? ll - 1 : 0]) + anorm) == anorm) l = ll;
+            }
+        }
+        if (l < 0) l = 0;
+        bool done;
+        if (l == 0) done = svd_qr_sweep<K, 0>(U, V, w, rv1, anorm, flag);
+        else if (l == 1) done = svd_qr_sweep<K, (K >= 1 ? 1 : 0)>(U, V, w, rv1, anorm, flag);
+        else done = svd_qr_sweep<K, (K >= 2 ? 2 : 0)>(U, V, w, rv1, anorm, flag);
+        if (done) break;
+    }
+}
+
 __device__ void svd3_ref(const float* A9, float* U9, float* W3, float* V9)
 {
-    const int m = 3, n = 3;
+    constexpr int m = 3, n = 3;
     float U[3][3], V[3][3], w[3], rv1[3];
-    int flag, i, its, j, jj, k, l = 0, nm = 0;
-    float anorm, c, f, g, h, s, scale, x, y, z;
-    for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) { U[i][j] = A9[3 * i + j]; V[i][j] = 0.0f; }
+    float anorm, f, g, h, s, scale;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { U[i][j] = A9[3 * i + j]; V[i][j] = 0.0f; }
     g = scale = anorm = 0.0f;
-    for (i = 0; i < n; i++) {
-        l = i + 1;
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+        const int l = i + 1;
         rv1[i] = scale * g;
         g = s = scale = 0.0f;
-        if (i < m) {
-            for (k = i; k < m; k++) scale += fabsf(U[k][i]);
+        {
+#pragma unroll
+            for (int k = i; k < m; k++) scale += fabsf(U[k][i]);
             if (scale != 0.0f) {
-                for (k = i; k < m; k++) { U[k][i] /= scale; s += U[k][i] * U[k][i]; }
+#pragma unroll
+                for (int k = i; k < m; k++) { U[k][i] /= scale; s += U[k][i] * U[k][i]; }
                 f = U[i][i];
                 g = -svd_sign(sqrtf(s), f);
                 h = f * g - s;
                 U[i][i] = f - g;
-                for (j = l; j < n; j++) {
-                    for (s = 0.0f, k = i; k < m; k++) s += U[k][i] * U[k][j];
+#pragma unroll
+                for (int j = l; j < n; j++) {
+                    s = 0.0f;
+#pragma unroll
+                    for (int k = i; k < m; k++) s += U[k][i] * U[k][j];
                     f = s / h;
-                    for (k = i; k < m; k++) U[k][j] += f * U[k][i];
+#pragma unroll
+                    for (int k = i; k < m; k++) U[k][j] += f * U[k][i];
                 }
-                for (k = i; k < m; k++) U[k][i] *= scale;
+#pragma unroll
+                for (int k = i; k < m; k++) U[k][i] *= scale;
             }
         }
         w[i] = scale * g;
         g = s = scale = 0.0f;
-        if (i < m && i != n - 1) {
-            for (k = l; k < n; k++) scale += fabsf(U[i][k]);
+        if (i != n - 1) {
+#pragma unroll
+            for (int k = l; k < n; k++) scale += fabsf(U[i][k]);
             if (scale != 0.0f) {
-                for (k = l; k < n; k++) { U[i][k] /= scale; s += U[i][k] * U[i][k]; }
-                f = U[i][l];
+#pragma unroll
+                for (int k = l; k < n; k++) { U[i][k] /= scale; s += U[i][k] * U[i][k]; }
+                f = U[i][l < 3 ? l : 2];
                 g = -svd_sign(sqrtf(s), f);
                 h = f * g - s;
-                U[i][l] = f - g;
-                for (k = l; k < n; k++) rv1[k] = U[i][k] / h;
-                for (j = l; j < m; j++) {
-                    for (s = 0.0f, k = l; k < n; k++) s += U[j][k] * U[i][k];
-                    for (k = l; k < n; k++) U[j][k] += s * rv1[k];
+                U[i][l < 3 ? l : 2] = f - g;
+#pragma unroll
+                for (int k = l; k < n; k++) rv1[k] = U[i][k] / h;
+#pragma unroll
+                for (int j = l; j < m; j++) {
+                    s = 0.0f;
+#pragma unroll
+                    for (int k = l; k < n; k++) s += U[j][k] * U[i][k];
+#pragma unroll
+                    for (int k = l; k < n; k++) U[j][k] += s * rv1[k];
                 }
-                for (k = l; k < n; k++) U[i][k] *= scale;
+#pragma unroll
+                for (int k = l; k < n; k++) U[i][k] *= scale;
             }
         }
         { float t2 = fabsf(w[i]) + fabsf(rv1[i]); anorm = anorm > t2 ? anorm : t2; }
     }
-    for (i = n - 1; i >= 0; i--) {
+    // accumulation of the right-hand transformations (:689-706); entering with g = the last value set above, l = n
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+        const int l = i + 1;
         if (i < n - 1) {
             if (g != 0.0f) {
-                for (j = l; j < n; j++) V[j][i] = (U[i][j] / U[i][l]) / g;
-                for (j = l; j < n; j++) {
-                    for (s = 0.0f, k = l; k < n; k++) s += U[i][k] * V[k][j];
-                    for (k = l; k < n; k++) V[k][j] += s * V[k][i];
+#pragma unroll
+                for (int j = l; j < n; j++) V[j][i] = (U[i][j] / U[i][l < 3 ? l : 2]) / g;
+#pragma unroll
+                for (int j = l; j < n; j++) {
+                    s = 0.0f;
+#pragma unroll
+                    for (int k = l; k < n; k++) s += U[i][k] * V[k][j];
+#pragma unroll
+                    for (int k = l; k < n; k++) V[k][j] += s * V[k][i];
                 }
             }
-            for (j = l; j < n; j++) V[i][j] = V[j][i] = 0.0f;
+#pragma unroll
+            for (int j = l; j < n; j++) V[i][j] = V[j][i] = 0.0f;
         }
         V[i][i] = 1.0f;
         g = rv1[i];
-        l = i;
     }
-    for (i = 2; i >= 0; i--) {
-        l = i + 1;
+    // accumulation of the left-hand transformations (:707-726)
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+        const int l = i + 1;
         g = w[i];
-        for (j = l; j < n; j++) U[i][j] = 0.0f;
+#pragma unroll
+        for (int j = l; j < n; j++) U[i][j] = 0.0f;
         if (g != 0.0f) {
             g = (float)(1.0 / (double)g);
-            for (j = l; j < n; j++) {
-                for (s = 0.0f, k = l; k < m; k++) s += U[k][i] * U[k][j];
+#pragma unroll
+            for (int j = l; j < n; j++) {
+                s = 0.0f;
+#pragma unroll
+                for (int k = l; k < m; k++) s += U[k][i] * U[k][j];
                 f = (s / U[i][i]) * g;
-                for (k = i; k < m; k++) U[k][j] += f * U[k][i];
+#pragma unroll
+                for (int k = i; k < m; k++) U[k][j] += f * U[k][i];
             }
-            for (j = i; j < m; j++) U[j][i] *= g;
-        } else for (j = i; j < m; j++) U[j][i] = 0.0f;
+#pragma unroll
+            for (int j = i; j < m; j++) U[j][i] *= g;
+        } else {
+#pragma unroll
+            for (int j = i; j < m; j++) U[j][i] = 0.0f;
+        }
         U[i][i] = U[i][i] + 1.0f;
     }
-    for (k = n - 1; k >= 0; k--) {
-        for (its = 0; its < 30; its++) {
-            flag = 1;
-            for (l = k; l >= 0; l--) {
-                nm = l - 1;
-                if ((float)(fabsf(rv1[l]) + anorm) == anorm) { flag = 0; break; }
-                if (nm >= 0 && (float)(fabsf(w[nm]) + anorm) == anorm) break;
-            }
-            if (l < 0) l = 0;
-            if (flag) {
-                c = 0.0f; s = 1.0f;
-                for (i = l; i <= k; i++) {
-                    f = s * rv1[i];
-                    rv1[i] = c * rv1[i];
-                    if ((float)(fabsf(f) + anorm) == anorm) break;
-                    g = w[i];
-                    h = svd_pythag(f, g);
-                    w[i] = h;
-                    h = (float)(1.0 / (double)h);
-                    c = g * h;
-                    s = -f * h;
-                    for (j = 0; j < m; j++) {
-                        y = U[j][nm]; z = U[j][i];
-                        U[j][nm] = y * c + z * s;
-                        U[j][i] = z * c - y * s;
-                    }
-                }
-            }
-            z = w[k];
-            if (l == k) {
-                if (z < 0.0f) { w[k] = -z; for (j = 0; j < n; j++) V[j][k] = -V[j][k]; }
-                break;
-            }
-            x = w[l]; nm = k - 1; y = w[nm]; g = rv1[nm]; h = rv1[k];
-            f = (float)((double)((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * (double)h * (double)y));
-            g = svd_pythag(f, 1.0f);
-            f = ((x - z) * (x + z) + h * ((y / (f + svd_sign(g, f))) - h)) / x;
-            c = s = 1.0f;
-            for (j = l; j <= nm; j++) {
-                i = j + 1;
-                g = rv1[i]; y = w[i];
-                h = s * g; g = c * g;
-                z = svd_pythag(f, h);
-                rv1[j] = z;
-                c = f / z; s = h / z;
-                f = x * c + g * s;
-                g = g * c - x * s;
-                h = y * s;
-                y *= c;
-                for (jj = 0; jj < n; jj++) {
-                    x = V[jj][j]; z = V[jj][i];
-                    V[jj][j] = x * c + z * s;
-                    V[jj][i] = z * c - x * s;
-                }
-                z = svd_pythag(f, h);
-                w[j] = z;
-                if (z != 0.0f) { z = (float)(1.0 / (double)z); c = f * z; s = h * z; }
-                f = c * g + s * y;
-                x = c * y - s * g;
-                for (jj = 0; jj < m; jj++) {
-                    y = U[jj][j]; z = U[jj][i];
-                    U[jj][j] = y * c + z * s;
-                    U[jj][i] = z * c - y * s;
-                }
-            }
-            rv1[l] = 0.0f; rv1[k] = f; w[k] = x;
+    // diagonalisation of the bidiagonal form (:727-781)
+    svd_qr_k<2>(U, V, w, rv1, anorm);
+    svd_qr_k<1>(U, V, w, rv1, anorm);
+    svd_qr_k<0>(U, V, w, rv1, anorm);
+    // descending sort (insertion with gap 1 for n = 3) + sign normalisation (:783-818)
+    {   // i = 1
+        const float sw = w[1], su0 = U[0][1], su1 = U[1][1], su2 = U[2][1], sv0 = V[0][1], sv1 = V[1][1], sv2 = V[2][1];
+        if (w[0] < sw) {
+            w[1] = w[0]; U[0][1] = U[0][0]; U[1][1] = U[1][0]; U[2][1] = U[2][0]; V[0][1] = V[0][0]; V[1][1] = V[1][0]; V[2][1] = V[2][0];
+            w[0] = sw; U[0][0] = su0; U[1][0] = su1; U[2][0] = su2; V[0][0] = sv0; V[1][0] = sv1; V[2][0] = sv2;
         }
     }
-    // descending sort (insertion with gap 1 for n=3) + sign normalisation (matrix.cpp:783-818)
-    for (i = 1; i < n; i++) {
-        float sw = w[i], su[3], sv[3];
-        for (k = 0; k < 3; k++) { su[k] = U[k][i]; sv[k] = V[k][i]; }
-        j = i;
-        while (w[j - 1] < sw) {
-            w[j] = w[j - 1];
-            for (k = 0; k < 3; k++) { U[k][j] = U[k][j - 1]; V[k][j] = V[k][j - 1]; }
-            j -= 1;
-            if (j < 1) break;
+    {   // i = 2
+        const float sw = w[2], su0 = U[0][2], su1 = U[1][2], su2 = U[2][2], sv0 = V[0][2], sv1 = V[1][2], sv2 = V[2][2];
+        if (w[1] < sw) {
+            w[2] = w[1]; U[0][2] = U[0][1]; U[1][2] = U[1][1]; U[2][2] = U[2][1]; V[0][2] = V[0][1]; V[1][2] = V[1][1]; V[2][2] = V[2][1];
+            if (w[0] < sw) {
+                w[1] = w[0]; U[0][1] = U[0][0]; U[1][1] = U[1][0]; U[2][1] = U[2][0]; V[0][1] = V[0][0]; V[1][1] = V[1][0]; V[2][1] = V[2][0];
+                w[0] = sw; U[0][0] = su0; U[1][0] = su1; U[2][0] = su2; V[0][0] = sv0; V[1][0] = sv1; V[2][0] = sv2;
+            } else {
+                w[1] = sw; U[0][1] = su0; U[1][1] = su1; U[2][1] = su2; V[0][1] = sv0; V[1][1] = sv1; V[2][1] = sv2;
+            }
         }
-        w[j] = sw;
-        for (k = 0; k < 3; k++) { U[k][j] = su[k]; V[k][j] = sv[k]; }
     }
-    for (k = 0; k < n; k++) {
+#pragma unroll
+    for (int k = 0; k < n; k++) {
         int s2 = 0;
-        for (i = 0; i < 3; i++) if (U[i][k] < 0.0f) s2++;
-        for (j = 0; j < 3; j++) if (V[j][k] < 0.0f) s2++;
+#pragma unroll
+        for (int i = 0; i < 3; i++) if (U[i][k] < 0.0f) s2++;
+#pragma unroll
+        for (int j = 0; j < 3; j++) if (V[j][k] < 0.0f) s2++;
         if (s2 > 3) {
-            for (i = 0; i < 3; i++) U[i][k] = -U[i][k];
-            for (j = 0; j < 3; j++) V[j][k] = -V[j][k];
+#pragma unroll
+            for (int i = 0; i < 3; i++) U[i][k] = -U[i][k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) V[j][k] = -V[j][k];
         }
     }
-    for (i = 0; i < 3; i++) { W3[i] = w[i]; for (j = 0; j < 3; j++) { U9[3 * i + j] = U[i][j]; V9[3 * i + j] = V[i][j]; } }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        W3[i] = w[i];
+#pragma unroll
+        for (int j = 0; j < 3; j++) { U9[3 * i + j] = U[i][j]; V9[3 * i + j] = V[i][j]; }
+    }
 }
 
 __device__ void mat3_mul(const float* A, const float* B, float* C)   // accumulate from 0 in k order (matrix.cpp:287-301)
@@ -1345,6 +1436,23 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
         for (int i = 0; i < 3; i++) { st->t[i] = cur.t[i]; st->mu_m[i] = cur.mu_m[i]; st->mu_d[i] = cur.mu_d[i]; }
         st->err = cur.err; st->err_new = cur.err_new; st->iter = cur.iter; st->converged = cur.converged;
     }
+}
+
+__global__ void svd3_kernel(const float* __restrict__ H9, int n, float* __restrict__ U9, float* __restrict__ W3, float* __restrict__ V9)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float H[9], U[9], W[3], V[9];
+    for (int k = 0; k < 9; k++) H[k] = H9[9 * i + k];
+    svd3_ref(H, U, W, V);
+    for (int k = 0; k < 9; k++) { U9[9 * i + k] = U[k]; V9[9 * i + k] = V[k]; }
+    for (int k = 0; k < 3; k++) W3[3 * i + k] = W[k];
+}
+cudaError_t launch_svd3(const float* d_H9, int n, float* d_U9, float* d_W3, float* d_V9, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    svd3_kernel<<<(n + 63) / 64, 64, 0, s>>>(d_H9, n, d_U9, d_W3, d_V9);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx, float* d_d2, bool cooperative, cudaStream_t s)

@@ -194,6 +194,10 @@ int goicp_nn(goicp_handle* h, const float* q_xyz, int n, int32_t* idx_out, float
  * Returns the number of nodes (the tree is not written if that exceeds capacity_nodes), or a negative goicp status. */
 int goicp_kdtree_host(const float* model_xyz, int n, int32_t* nodes7_out, int capacity_nodes, int32_t* vind_out, float* bbox6_out);
 
+/* Matrix::svd (matrix.cpp:602-830) of n 3x3 float matrices (row-major, 9 floats each) exactly as ICP3D::Run uses it: U, singular
+ * values (descending) and V with the reference's float roundings, sort and sign normalisation.  Exposed for parity tests. */
+int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3_out, float* V9_out);
+
 /* ICP3D<float>::Run (jly_icp3d.hpp:180-295) from (R0,t0). err_diff<0 -> mse_threshold/10000
  * (jly_goicp.cpp:186); max_iter<=0 -> params.icp_max_iter. */
 int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff,

@@ -1,5 +1,5 @@
-"""Short single-GPU program for ncu: one bunny Go-ICP registration (fast exact-EDT DT so the
-capture is dominated by the hot path) + one batched DT-gather launch."""
+"""Short single-GPU program for ncu: one bunny Go-ICP registration in the library's default configuration (DT build
+included) + batched DT-gather launches (expand_bounds_kernel) + the uniform random-gather microbenchmark."""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,8 @@ model = np.fromfile(os.path.join(G, "bunny_model_s0.1_seed1234.f32"), np.float32
 data = np.fromfile(os.path.join(G, "bunny_data_s0.1_seed1235.f32"), np.float32).reshape(-1, 3)
 g = pkg.GoICP(1e-3)
 g.pModel, g.pData = model, data
-g.dt_mode = int(os.environ.get("DT_MODE", "1"))
+if "DT_MODE" in os.environ:
+    g.dt_mode = int(os.environ["DT_MODE"])          # default: the library's (exact EDT + reference corner seed)
 g.BuildDT()
 g.Register()
 print({k: v for k, v in g.result.items() if k not in ("R", "t")})
@@ -19,4 +20,5 @@ n = 148 * 16
 Rs = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(n)]).astype(np.float32)
 tc = np.concatenate([rng.uniform(-0.5, 0.25, (n, 3)), np.full((n, 1), 0.25)], 1).astype(np.float32)
 print(g.ExpandBounds(Rs.reshape(n, 9), np.full(n, -1, np.int32), tc, repeats=3)[2])
+print(g.MeasureGather(4 * 300 ** 3, 2))
 g.close()

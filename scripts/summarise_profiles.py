@@ -15,7 +15,13 @@ SELECT = ["launch__cluster_size", "launch__registers_per_thread", "gpu__time_dur
           "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sector_hit_rate.pct",
           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-          "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct", "smsp__inst_executed.sum"]
+          "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct", "smsp__inst_executed.sum",
+          # L2 / L1TEX / DRAM bytes per second (north_star: achieved L2 and HBM GB/s) and issue efficiency
+          "lts__t_sectors.sum.per_second", "lts__t_sectors.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum", "dram__bytes.sum.per_second",
+          "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.per_cycle_active",
+          "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+          "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+          "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 
 
 def short(name):
@@ -60,6 +66,20 @@ def main():
             w.writerow([units[i] for i in base + idx])
             for b in body:
                 w.writerow([short(b[i]) if i == base[0] else b[i] for i in base + idx])
+        # DRAM bytes per launch of the dominant kernel, for bench.py's roofline.traffic (profiles/ncu_traffic.json)
+        wl = os.environ.get("PROFILE_WORKLOAD")
+        if wl and "dram__bytes_read.sum" in hdr and "dram__bytes_write.sum" in hdr:
+            import json
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            vals = [(float(b[ir].replace(",", "")) * unit.get(units[ir], 1.0) + float(b[iw].replace(",", "")) * unit.get(units[iw], 1.0)) for b in body if "inner_bnb" in b[ik]]
+            names = sorted({short(b[ik]) for b in body if "inner_bnb" in b[ik]})
+            if vals:
+                path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+                t = json.load(open(path)) if os.path.exists(path) else {}
+                t[wl] = {"kernel": names[0], "dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals),
+                         "source": f"profiles/{tag}_ncu_full_selected.csv: mean dram__bytes_read.sum + dram__bytes_write.sum over the {len(vals)} {names[0]} launches of one registration (cold cache; the gathers themselves are served by L2)"}
+                json.dump(t, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":
