@@ -169,6 +169,7 @@ struct goicp_handle {
     // data cloud on device (x,y,z,norm)
     DevBuf<float4> d_data; bool data_uploaded = false;
     // kd-tree
+    std::vector<unsigned short> grid_start; int gdim[3] = {0, 0, 0}; float gh = 0; DevBuf<unsigned short> d_grid_start; DevBuf<float4> d_grid_pts;     // NN grid (small models)
     HostKdTree kd_host; DevBuf<KdNode> d_kd_nodes; DevBuf<float4> d_kd_boxes; DevBuf<int32_t> d_kd_vind; DevBuf<float4> d_kd_leaf; DevBuf<float> d_model;
     bool kd_ready = false;
     // scratch
@@ -299,6 +300,44 @@ int ensure_kdtree(goicp_handle* h)
     CUDA_TRY(h, xfer(h, h->d_kd_vind.p, h->kd_host.vind.data(), sizeof(int32_t) * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, xfer(h, h->d_kd_leaf.p, leaf.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, xfer(h, h->d_model.p, h->model.data(), sizeof(float) * 3 * h->nm, cudaMemcpyHostToDevice, h->stream));
+    // NN grid of the linear-scan range (icp_kernels.cu: grid_nn): cells of edge h = longest bounding-box side / G,
+    // G ~ sqrt(nm / 8) (a surface-like cloud then has a few points per occupied cell); points binned with the same float
+    // expression the kernel applies to a query.
+    h->grid_start.clear(); h->gdim[0] = h->gdim[1] = h->gdim[2] = 0;
+    if (h->nm <= 16384 && h->nm >= 64) {
+        int G = (int)std::lround(std::sqrt((double)h->nm / 8.0));
+        if (const char* e = getenv("GOICP_NN_GRID")) G = atoi(e);
+        if (G >= 2) {
+            G = std::min(G, 40);
+            const float* lo = h->kd_host.bb_lo; const float* hi = h->kd_host.bb_hi;
+            float ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+            if (ext > 0) {
+                const float gh = ext / (float)G, inv = 1.0f / gh;
+                for (int a = 0; a < 3; a++) h->gdim[a] = std::max(1, std::min(G, (int)std::floor((hi[a] - lo[a]) * inv) + 1));
+                const int nc = h->gdim[0] * h->gdim[1] * h->gdim[2];
+                std::vector<int> cell(h->nm); std::vector<int> count(nc + 1, 0);
+                for (int i = 0; i < h->nm; i++) {
+                    int c[3];
+                    for (int a = 0; a < 3; a++) c[a] = std::min(std::max((int)std::floor((h->model[3 * i + a] - lo[a]) * inv), 0), h->gdim[a] - 1);
+                    cell[i] = (c[2] * h->gdim[1] + c[1]) * h->gdim[0] + c[0];
+                    count[cell[i] + 1]++;
+                }
+                for (int c = 0; c < nc; c++) count[c + 1] += count[c];
+                h->grid_start.assign(count.begin(), count.end());
+                std::vector<float4> gp(h->nm); std::vector<int> fill(count.begin(), count.end() - 1);
+                for (int i = 0; i < h->nm; i++) {
+                    float w; std::memcpy(&w, &i, 4);
+                    gp[fill[cell[i]]++] = make_float4(h->model[3 * i], h->model[3 * i + 1], h->model[3 * i + 2], w);
+                }
+                h->gh = gh;
+                CUDA_TRY(h, h->d_grid_start.reserve(h->grid_start.size() + 8));
+                CUDA_TRY(h, h->d_grid_pts.reserve(h->nm));
+                CUDA_TRY(h, xfer(h, h->d_grid_start.p, h->grid_start.data(), sizeof(unsigned short) * h->grid_start.size(), cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(h, xfer(h, h->d_grid_pts.p, gp.data(), sizeof(float4) * h->nm, cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            }
+        }
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, h->d_icp_state.reserve(1));
     h->kd_ready = true;
@@ -310,6 +349,13 @@ KdView kd_view(const goicp_handle* h)
     KdView v;
     v.nodes = h->d_kd_nodes.p; v.boxes = h->d_kd_boxes.p; v.vind = h->d_kd_vind.p; v.pts_leaf = h->d_kd_leaf.p; v.model = h->d_model.p; v.nm = h->nm;
     for (int i = 0; i < 3; i++) { v.bb_lo[i] = h->kd_host.bb_lo[i]; v.bb_hi[i] = h->kd_host.bb_hi[i]; }
+    v.grid_start = nullptr; v.grid_pts = nullptr; v.gcells = 0; v.gh = 0; v.ginv_h = 0;
+    for (int i = 0; i < 3; i++) { v.gdim[i] = 0; v.glo[i] = h->kd_host.bb_lo[i]; }
+    if (!h->grid_start.empty()) {
+        v.grid_start = h->d_grid_start.p; v.grid_pts = h->d_grid_pts.p;
+        for (int i = 0; i < 3; i++) v.gdim[i] = h->gdim[i];
+        v.gcells = h->gdim[0] * h->gdim[1] * h->gdim[2]; v.gh = h->gh; v.ginv_h = 1.0f / h->gh;
+    }
     // the 32 nodes five levels down, when every node above them is interior: the first five rounds of a breadth-first
     // search from the root would keep 1, 2, 4, 8, 16 lanes busy
     v.n_top = 0;
@@ -646,8 +692,8 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     const bool fast = (h->p.numerics & GOICP_NUM_FAST_ICP) != 0;
     const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin, fast);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
-    // queries are interleaved over the CTAs, 32 per CTA and pass: use every SM the cooperative launch allows
-    int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 31) / 32), blocks_cap));
+    // queries are interleaved over the CTAs, one per warp and pass (16 per CTA): use every SM the cooperative launch allows
+    int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 15) / 16), blocks_cap));
     if (const char* e = getenv("GOICP_ICP_BLOCKS")) blocks = std::max(1, std::min(std::min(max_blocks, icp_max_blocks_supported()), std::min(atoi(e), blocks_cap)));   // experiments
     if (fast) CUDA_TRY(h, h->d_icp_partials.reserve((size_t)2 * 16 * blocks));
     CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, (h->p.do_trim ? 1 : 0) | ((h->p.numerics & GOICP_NUM_JACOBI_SVD) ? 2 : 0), blocks, h->max_smem_optin, fast, h->d_icp_partials.p, h->stream));
@@ -726,7 +772,7 @@ int goicp_destroy(goicp_handle* h)
         if (h->stream_dt) cudaStreamSynchronize(h->stream_dt);
         h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
         h->d_gather.release(); h->d_share.release();
-        h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release();
+        h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release(); h->d_grid_start.release(); h->d_grid_pts.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_trim_keys.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release(); h->d_icp_partials.release();
         if (h->h_results) pool_free_host(h->h_results);

@@ -37,6 +37,13 @@ struct KdView {
     int nm;
     float bb_lo[3], bb_hi[3];
     int n_top; int top[32];                // the nodes five levels below the root (n_top = 32), or n_top = 0: where the cooperative search's frontier starts
+    // Uniform grid over the model's bounding box (models of the linear-scan range only, else grid_start = null): cell c holds
+    // grid_pts[grid_start[c] .. grid_start[c+1]), cells ordered x fastest.  A query first looks at the 3x3x3 cells around its
+    // own; if the nearest point found there is closer than the edge of that block, no point outside can beat or tie it.
+    const unsigned short* __restrict__ grid_start;
+    const float4* __restrict__ grid_pts;   // model points sorted by cell: x, y, z, (original index as int bits)
+    int gdim[3]; int gcells;
+    float glo[3]; float gh, ginv_h;
 };
 struct IcpState {           // lives in device memory; written by block 0 of the ICP kernel
     float R[9], t[3];

@@ -5,6 +5,7 @@
 // Replaces ICP3D<float>::Run (jly_icp3d.hpp:180-295), KDTreeSingleIndexAdaptor::searchLevel
 // (nanoflann_goicp.hpp:1136-1184) and Matrix::svd (matrix.cpp:602-830) for the GPU.
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 #include "goicp_kernels.h"
 
@@ -671,8 +672,231 @@ __device__ void icp_update(IcpState* st, const float* H, bool jacobi)
 constexpr int kIcpChunk = 384;
 constexpr int kColPitch = kIcpChunk + 4;       // column pitch of a transposed chunk: 7 columns fit the 8 * kIcpChunk floats, lanes read distinct banks
 
+// ------------------------------------------------------------------------------------------
+// Nearest neighbour on small models (the linear-scan range), two stages, both exact:
+//  1. grid_nn -- eight lanes per query look at the (2r+1)^3 grid cells around the query, r chosen from the query's nearest
+//     distance in the previous iteration (it moves little between iterations; any value is only a hint).  The result is
+//     final when the nearest point found is closer than the edge of that block of cells: every point outside the block is
+//     at least `margin` away, so none can beat it, nor come within the 1e-5 near-tie band that sends a query to the
+//     reference-ordered kd-tree walk.  A few dozen points are looked at instead of the whole model.
+//  2. the rest (a wrong hint, or a query so far from the surface that its block would be most of the grid): a linear scan of
+//     the whole model by all the warps of the CTA together, one query after the other, merged through shared memory
+//     (block_nn_scan); the results are parked and emitted in parallel afterwards.
+// Same distances (same float expression), same near-tie rule, hence the same indices as the plain scan.
+// ------------------------------------------------------------------------------------------
+// what a CTA of the ICP kernel has in (or reaches through) shared memory, see icp_carve
+struct IcpSmem { const KdNode* nodes; const float4* leaf; const unsigned short* gstart; const float4* gpts; float* sstage; unsigned* sradix; int* squeue; float4* qpts; float* qhint; };
+constexpr int kGridMaxR = 5;             // beyond 11^3 cells the block-wide scan is cheaper
+__device__ __forceinline__ void nn_merge(float& d1, int& i1, float& d2, int o)
+{
+    const unsigned full = 0xffffffffu;
+    const float od1 = __shfl_xor_sync(full, d1, o), od2 = __shfl_xor_sync(full, d2, o);
+    const int oi1 = __shfl_xor_sync(full, i1, o);
+    const float nd2 = fminf(fmaxf(d1, od1), fminf(d2, od2));         // second smallest of the union (an exact tie of the two minima counts)
+    if (od1 < d1) { d1 = od1; i1 = oi1; }
+    d2 = nd2;
+}
+// One query per warp, one x-run of cells per lane (two or more beyond r = 2); the points of a run are fetched four at a
+// time so that their loads and distance arithmetic overlap -- a one-by-one loop is a chain of ~130 dependent cycles per
+// point.  r < 0: skip (the caller already knows the block would be too large); all 32 lanes must call.
+__device__ __forceinline__ bool grid_nn(const KdView& kd, const unsigned short* gstart, const float4* gpts, float qx, float qy, float qz, int r, int lane,
+                                        float& D1, int& I1, float& D2)
+{
+    const float kInfF = 3.402823466e+38f;
+    const float q[3] = {qx, qy, qz};
+    int c[3]; float margin = kInfF;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float u = fminf(fmaxf((q[a] - kd.glo[a]) * kd.ginv_h, -1.0f), (float)kd.gdim[a]);
+        const int ca = min(max((int)floorf(u), 0), kd.gdim[a] - 1);
+        c[a] = ca;
+        // a side of the block is closed only if a cell lies beyond it: no model point is below cell 0 or above the last cell
+        if (ca - r - 1 >= 0) margin = fminf(margin, q[a] - (kd.glo[a] + (float)(ca - r) * kd.gh));
+        if (ca + r + 1 < kd.gdim[a]) margin = fminf(margin, (kd.glo[a] + (float)(ca + r + 1) * kd.gh) - q[a]);
+    }
+    float d1 = kInfF, d2 = kInfF; int i1 = 0;
+    if (r >= 0) {
+        const int x0 = max(c[0] - r, 0), x1 = min(c[0] + r, kd.gdim[0] - 1);
+        const int side = 2 * r + 1;
+        for (int run = lane; run < side * side; run += 32) {           // x-runs: the cells (x0..x1, cy, cz) are contiguous
+            const int cy = c[1] + (run % side) - r, cz = c[2] + (run / side) - r;
+            if (cy < 0 || cy >= kd.gdim[1] || cz < 0 || cz >= kd.gdim[2]) continue;
+            const int base = (cz * kd.gdim[1] + cy) * kd.gdim[0];
+            const int e = gstart[base + x1 + 1];
+            for (int m = gstart[base + x0]; m < e; m += 4) {
+                float4 pm[4]; float dist[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) pm[u] = gpts[min(m + u, e - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float e0 = qx - pm[u].x, e1 = qy - pm[u].y, e2 = qz - pm[u].z;
+                    dist[u] = m + u < e ? e0 * e0 + e1 * e1 + e2 * e2 : kInfF;    // kdtree_distance (jly_icp3d.hpp:48-54)
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (dist[u] < d1) { d2 = d1; d1 = dist[u]; i1 = m + u; }
+                    else if (dist[u] < d2) d2 = dist[u];
+                }
+            }
+        }
+    }
+    nn_merge(d1, i1, d2, 16); nn_merge(d1, i1, d2, 8); nn_merge(d1, i1, d2, 4); nn_merge(d1, i1, d2, 2); nn_merge(d1, i1, d2, 1);
+    D1 = d1; D2 = d2; I1 = __shfl_sync(0xffffffffu, i1, 0);
+    const float me = margin - 1e-4f * kd.gh;                        // binning and edge arithmetic round at ~1e-6 of a cell
+    return r >= 0 && me > 0.0f && d1 * 1.00001f < me * me;
+}
+// one query, all the warps of the CTA: every thread scans its stride of the model, warps merge by shuffles, the warps'
+// results go through merge[3][16] in shared memory; returns (in warp 0, all lanes) the two smallest distances and lane
+// 0's index.  One block barrier per call; the caller alternates between two merge buffers.
+__device__ __forceinline__ void block_nn_scan(const float4* __restrict__ pts, int nm, float qx, float qy, float qz, float* merge, int lane, int warp,
+                                              float& D1, int& I1, float& D2)
+{
+    const float kInfF = 3.402823466e+38f;
+    float d1 = kInfF, d2 = kInfF; int i1 = 0;
+    for (int m = threadIdx.x; m < nm; m += kIcpThreads) {
+        const float4 pm = pts[m];
+        const float e0 = qx - pm.x, e1 = qy - pm.y, e2 = qz - pm.z;
+        const float dist = e0 * e0 + e1 * e1 + e2 * e2;
+        if (dist < d1) { d2 = d1; d1 = dist; i1 = m; }
+        else if (dist < d2) d2 = dist;
+    }
+    nn_merge(d1, i1, d2, 16); nn_merge(d1, i1, d2, 8); nn_merge(d1, i1, d2, 4); nn_merge(d1, i1, d2, 2); nn_merge(d1, i1, d2, 1);
+    if (lane == 0) { merge[warp] = d1; merge[16 + warp] = d2; merge[32 + warp] = __int_as_float(i1); }
+    __syncthreads();
+    if (warp == 0) {
+        d1 = lane < kIcpThreads / 32 ? merge[lane] : kInfF; d2 = lane < kIcpThreads / 32 ? merge[16 + lane] : kInfF;
+        i1 = lane < kIcpThreads / 32 ? __float_as_int(merge[32 + lane]) : 0;
+        nn_merge(d1, i1, d2, 8); nn_merge(d1, i1, d2, 4); nn_merge(d1, i1, d2, 2); nn_merge(d1, i1, d2, 1);
+        I1 = __shfl_sync(0xffffffffu, i1, 0);
+    }
+    D1 = d1; D2 = d2;
+}
+// The NN phase of one ICP iteration for the queries of this CTA (i = k * gridDim.x + blockIdx.x).
+// emit(i, model index, model xyz, d^2, query xyz) is called by exactly one thread per query: lane 0 of warp k mod 16 when the
+// grid settles it, else thread k mod 512 -- a fixed assignment, so whatever emit accumulates is reproducible from run to run.
+// d2_hint: the queries' squared nearest distances of the previous iteration (any content is safe; sm.qhint caches the first
+// ones on chip, as sm.qpts caches their data points).  park: >= ceil(nd / gridDim.x) 64-bit words of scratch owned by this
+// CTA: 0 = settled by the grid, else bit 63 | d^2 bits << 32 | near-tie << 31 | position of the winner in the scanned array.
+template <typename Emit>
+__device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSmem& sm, int qcache_n, const float4* __restrict__ data, int nd, const float (&R)[9], const float (&t)[3],
+                                                   float* d2_hint, unsigned long long* park, float* merge /* [2][3][16] */, Emit emit)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nq = nd > (int)blockIdx.x ? (nd - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf; const unsigned short* gstart = sm.gstart; const float4* gpts = sm.gpts;
+    const float4* scan = gpts ? gpts : leaf;                 // either way: x, y, z, original index
+    auto query = [&](int k, int i, float& qx, float& qy, float& qz) {
+        const float4 p = k < qcache_n ? sm.qpts[k] : __ldg(data + i);
+        // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (jly_icp3d.hpp:219-221)
+        qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
+        qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
+        qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
+    };
+    // winner at position `pos` of the scanned array, or -- near tie -- whatever the reference-ordered kd-tree walk returns
+    auto finish = [&](int k, int i, int pos, bool tie, float D1, float qx, float qy, float qz) {
+        if (k < qcache_n) sm.qhint[k] = D1; else d2_hint[i] = D1;
+        const float4 w = scan[pos];
+        int I1 = __float_as_int(w.w); float mx = w.x, my = w.y, mz = w.z;
+        if (tie) {
+            I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1, D1);
+            mx = __ldg(kd.model + 3 * I1); my = __ldg(kd.model + 3 * I1 + 1); mz = __ldg(kd.model + 3 * I1 + 2);
+        }
+        emit(i, I1, mx, my, mz, D1, qx, qy, qz);
+    };
+    __shared__ int n_park_sm;
+    if (threadIdx.x == 0) n_park_sm = 0;
+    __syncthreads();
+    if (gstart) {
+        for (int k = warp; k < nq; k += kIcpThreads / 32) {
+            const int i = k * gridDim.x + blockIdx.x;
+            float qx, qy, qz;
+            query(k, i, qx, qy, qz);
+            // radius of the block of cells from last iteration's distance: the block's edge is >= r cells away
+            int r = 1;
+            {
+                const float hint = k < qcache_n ? sm.qhint[k] : __ldcg(d2_hint + i);
+                if (hint >= 0.0f && hint < 1.0e30f) r = (int)(sqrtf(hint) * 1.02f * kd.ginv_h) + 1;
+                if (r > kGridMaxR) r = -1;
+            }
+            float D1, D2; int P1;
+            const bool ok = grid_nn(kd, gstart, gpts, qx, qy, qz, r, lane, D1, P1, D2);
+            if (lane == 0) {
+                park[k] = ok ? 0ull : 1ull;
+                if (ok) finish(k, i, P1, D2 <= D1 * 1.00001f, D1, qx, qy, qz);
+                else atomicAdd(&n_park_sm, 1);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        if (n_park_sm == 0) return;                           // the usual case after the first iteration
+    }
+    int par = 0;
+    for (int k = 0; k < nq; k++) {
+        if (gstart && park[k] == 0ull) continue;              // block-uniform
+        const int i = k * gridDim.x + blockIdx.x;
+        float qx, qy, qz;
+        query(k, i, qx, qy, qz);
+        float D1, D2; int P1;
+        block_nn_scan(scan, kd.nm, qx, qy, qz, merge + par * 48, lane, warp, D1, P1, D2);
+        par ^= 1;
+        if (threadIdx.x == 0)
+            park[k] = (1ull << 63) | ((unsigned long long)__float_as_uint(D1) << 32) | (D2 <= D1 * 1.00001f ? 0x80000000ull : 0ull) | (unsigned)P1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nq; k += kIcpThreads) {
+        const unsigned long long w = park[k];
+        if (!(w >> 63)) continue;
+        const int i = k * gridDim.x + blockIdx.x;
+        float qx, qy, qz;
+        query(k, i, qx, qy, qz);
+        finish(k, i, (int)(w & 0x7fffffffu), (w & 0x80000000ull) != 0, __uint_as_float((unsigned)(w >> 32) & 0x7fffffffu), qx, qy, qz);
+    }
+}
+
 // dynamic shared memory plan of the ICP kernel (decided on the host)
-struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes; int brute_force; int radix_bytes; int nn_budget; int queue_bytes; };
+struct IcpSmemPlan { int tree_nodes; int tree_bytes; int stage_bytes /* keys of the counting sort */; int brute_force; int radix_bytes; int nn_budget; int queue_bytes;
+                     int grid_bytes /* NN grid: cell table + cell-sorted points */; int qcache_n /* this CTA's first data points + distance hints kept on chip */; };
+constexpr int kQCacheEntry = (int)sizeof(float4) + (int)sizeof(float);
+__host__ __device__ inline size_t icp_plan_bytes(const IcpSmemPlan& p)
+{
+    return (size_t)p.grid_bytes + p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes + (((size_t)p.qcache_n * kQCacheEntry + 15) & ~(size_t)15);
+}
+// carve the dynamic shared memory [NN grid][kd-tree][sort keys][radix][search rings][query cache] and fill the read-only parts
+__device__ __forceinline__ IcpSmem icp_carve(const KdView& kd, const IcpSmemPlan& plan, unsigned char* sp, const float4* __restrict__ data, int nd)
+{
+    IcpSmem m;
+    m.nodes = kd.nodes; m.leaf = kd.pts_leaf; m.gstart = kd.grid_start; m.gpts = kd.grid_pts;
+    if (plan.grid_bytes) {
+        unsigned short* sg = reinterpret_cast<unsigned short*>(sp);
+        float4* sl = reinterpret_cast<float4*>(sp + (((size_t)(kd.gcells + 1) * sizeof(unsigned short) + 15) & ~(size_t)15));
+        for (int i = threadIdx.x; i < kd.gcells + 1; i += blockDim.x) sg[i] = kd.grid_start[i];
+        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.grid_pts[i];
+        m.gstart = sg; m.gpts = sl; sp += plan.grid_bytes;
+    }
+    if (plan.tree_bytes) {
+        KdNode* sn = reinterpret_cast<KdNode*>(sp);
+        float4* sl = reinterpret_cast<float4*>(sp + (size_t)plan.tree_nodes * sizeof(KdNode));
+        for (int i = threadIdx.x; i < plan.tree_nodes * 2; i += blockDim.x) reinterpret_cast<uint4*>(sn)[i] = reinterpret_cast<const uint4*>(kd.nodes)[i];
+        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
+        m.nodes = sn; m.leaf = sl; sp += plan.tree_bytes;
+    }
+    m.sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr; sp += plan.stage_bytes;
+    m.sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr; sp += plan.radix_bytes;
+    m.squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr; sp += plan.queue_bytes;
+    m.qpts = nullptr; m.qhint = nullptr;
+    if (plan.qcache_n) {
+        // the queries of this CTA never change (i = k * gridDim.x + blockIdx.x): keep the first qcache_n data points on chip,
+        // next to their nearest distance of the previous iteration (the grid search's radius hint; -1 = none yet)
+        m.qpts = reinterpret_cast<float4*>(sp); m.qhint = reinterpret_cast<float*>(sp + (size_t)plan.qcache_n * sizeof(float4));
+        for (int k = threadIdx.x; k < plan.qcache_n; k += blockDim.x) {
+            const long long i = (long long)k * gridDim.x + blockIdx.x;
+            m.qpts[k] = i < nd ? __ldg(data + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            m.qhint[k] = -1.0f;
+        }
+    }
+    __syncthreads();
+    return m;
+}
 
 // ------------------------------------------------------------------------------------------
 // Phase B for clouds too large to rank by counting (the keys no longer fit in shared memory and
@@ -805,18 +1029,6 @@ __device__ __forceinline__ float seq_add_contig(float acc, const float* x, int c
     return acc;
 }
 
-// ------------------------------------------------------------------------------------------
-// Nearest neighbour of up to 32 queries per pass (one per lane), all 16 warps of the CTA scanning
-// 1/16 of the model each.  A linear scan has no divergence, unlike the kd-tree descent where every
-// lane walks its own path; for the model sizes of this path it is an order of magnitude faster.
-// It is still the REFERENCE's answer: the scan also tracks the second-smallest distance, and
-// whenever that is within 1e-5 (relative) of the smallest -- exact ties included -- the query is
-// re-run through the reference-ordered kd-tree search.  Outside that margin the kd-tree cannot
-// return anything else: its pruning test would have to be wrong by 1e-5, more than an order of
-// magnitude above the float rounding of its bound (a handful of ulps).
-// ------------------------------------------------------------------------------------------
-struct NnPartial { float d1[kIcpThreads / 32][32]; float d2[kIcpThreads / 32][32]; int i1[kIcpThreads / 32][32]; };
-
 __global__ void __launch_bounds__(kIcpThreads)
 icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
            int max_iter, float err_diff, int num, int flags /* bit 0: sort (the reference's do_trim), bit 1: Jacobi solver */, IcpSmemPlan plan)
@@ -827,28 +1039,16 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     __shared__ float sh_H[9];
     __shared__ float sh_acc[8];
     __shared__ __align__(16) float chunk[2][kIcpChunk * 8];      // double buffer of the streamed (large-cloud) accumulation
-    __shared__ NnPartial part;
     __shared__ int n_deferred, n_unsettled;
+    __shared__ float nn_merge_sm[2 * 48];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIcpThreads / 32;
     const volatile IcpState* vst = st;
 
     // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [staged rows]
-    const KdNode* nodes = kd.nodes; const float4* leaf = kd.pts_leaf;
-    unsigned char* sp = icp_smem;
-    if (plan.tree_bytes) {
-        KdNode* sn = reinterpret_cast<KdNode*>(sp);
-        float4* sl = reinterpret_cast<float4*>(sp + (size_t)plan.tree_nodes * sizeof(KdNode));
-        for (int i = threadIdx.x; i < plan.tree_nodes * 2; i += blockDim.x) reinterpret_cast<uint4*>(sn)[i] = reinterpret_cast<const uint4*>(kd.nodes)[i];
-        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
-        nodes = sn; leaf = sl; sp += plan.tree_bytes;
-    }
-    float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
-    sp += plan.stage_bytes;
-    unsigned* sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr;
-    sp += plan.radix_bytes;
-    int* squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr;             // per-warp rings of the cooperative search
-    __syncthreads();
+    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, nd);
+    const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf;
+    float* sstage = sm.sstage; unsigned* sradix = sm.sradix; int* squeue = sm.squeue;
 
     long long c_nn = 0, c_wait = 0, c_sort = 0, c_p1 = 0, c_p2 = 0, c_acc1 = 0, c_svd = 0; const long long c_begin = clock64();
     for (int iter = 0; iter < max_iter; iter++) {
@@ -860,50 +1060,15 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         for (int i = 0; i < 3; i++) t[i] = vst->t[i];
         // ---- phase A: transform + nearest neighbour; queries interleaved over the CTAs ----------
         if (plan.brute_force) {
-            const int mchunk = (kd.nm + kWarps - 1) / kWarps;
-            const int m0 = min(warp * mchunk, kd.nm), m1 = min(m0 + mchunk, kd.nm);
-            for (int qpass = 0; (qpass * 32) * (int)gridDim.x + (int)blockIdx.x < nd; qpass++) {
-                const int i = (qpass * 32 + lane) * gridDim.x + blockIdx.x;
-                const bool valid = i < nd;
-                float qx = 0.0f, qy = 0.0f, qz = 0.0f;
-                if (valid) {
-                    const float4 p = __ldg(data + i);
-                    // query = R p + t, (((r0*x + r1*y) + r2*z) + t) in float (:219-221)
-                    qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
-                    qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
-                    qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-                }
-                float d1 = 3.402823466e+38f, d2 = 3.402823466e+38f; int i1 = 0;
-                for (int m = m0; m < m1; m++) {
-                    const float4 pm = leaf[m];                      // same address in every lane: broadcast
-                    const float e0 = qx - pm.x, e1 = qy - pm.y, e2 = qz - pm.z;
-                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;  // kdtree_distance (jly_icp3d.hpp:48-54)
-                    if (dist < d1) { d2 = d1; d1 = dist; i1 = __float_as_int(pm.w); }
-                    else if (dist < d2) d2 = dist;
-                }
-                part.d1[warp][lane] = d1; part.d2[warp][lane] = d2; part.i1[warp][lane] = i1;
-                __syncthreads();
-                if (warp == 0) {
-                    float D1 = 3.402823466e+38f, D2 = 3.402823466e+38f; int I1 = 0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; w++) {
-                        const float a = part.d1[w][lane], b = part.d2[w][lane];
-                        if (a < D1) { D2 = fminf(D1, b); D1 = a; I1 = part.i1[w][lane]; }
-                        else D2 = fminf(D2, a);
-                        D2 = fminf(D2, b);
-                    }
-                    if (valid) {
-                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1, D1);   // near tie: reference traversal order decides
-                        wk.nn[i] = I1; wk.d2[i] = D1;
-                        wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
-                        // correspondence row (model point, query, d^2) in query order
-                        float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
-                        row[0] = make_float4(__ldg(kd.model + 3 * I1), __ldg(kd.model + 3 * I1 + 1), __ldg(kd.model + 3 * I1 + 2), qx);
-                        row[1] = make_float4(qy, qz, D1, 0.0f);
-                    }
-                }
-                __syncthreads();
-            }
+            unsigned long long* park = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);      // wk.keys2 is idle until the sort
+            icp_nn_small_model(kd, sm, plan.qcache_n, data, nd, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
+                wk.nn[i] = I1;
+                wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
+                // correspondence row (model point, query, d^2) in query order
+                float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                row[0] = make_float4(mx, my, mz, qx);
+                row[1] = make_float4(qy, qz, D1, 0.0f);
+            });
         } else {
             // Tree search.  With a visit budget > 1 every thread first walks the reference's traversal for its own queries
             // (subtree skipping, capped by the distance to the point's last correspondent; any model point bounds the
@@ -1009,6 +1174,11 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             // once when they fit, else streamed in double-buffered chunks of kIcpChunk rows that warps
             // 1.. fetch while warp 0 adds the previous chunk -- and one lane per accumulator adds them
             // up strictly sequentially.
+            // The adding lanes (warp 0) run a chain of dependent FADDs, 4 cycles apart when nothing else wants their issue
+            // port.  Warps 4, 8 and 12 share that port (warp id mod 4 = SM sub-partition), so they stay out of the staging work:
+            // the 12 warps of the other three sub-partitions do it.
+            constexpr int kHelpers = (kWarps - 4) * 32;
+            const int helper = (warp & 3) != 0 ? (warp - 1 - (warp >> 2)) * 32 + lane : -1;
             float acc = 0.0f;
             if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
             const float4* srows = reinterpret_cast<const float4*>(do_sort ? wk.stage : wk.q);
@@ -1020,17 +1190,11 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             // x,y,z, d^2) is contiguous at chunk[buf] + c * kColPitch, so lane c reads four terms per instruction.  Warps 1..
             // fill chunk k+1 (from the staged rows in shared memory, or from global memory for large clouds) while warp 0
             // adds chunk k.
-            if (sstage) {
-                for (int v = threadIdx.x; v < 2 * num; v += blockDim.x) reinterpret_cast<float4*>(sstage)[v] = __ldcg(srows + v);
-                __syncthreads();
-            }
             auto fill = [&](int k, int first, int nthr) {
                 const int base = k * kIcpChunk, cnt = min(kIcpChunk, num - base);
                 float* cb = chunk[k & 1];
                 for (int r = first; r < cnt; r += nthr) {
-                    float4 lo, hi;
-                    if (sstage) { lo = reinterpret_cast<const float4*>(sstage)[2 * (base + r)]; hi = reinterpret_cast<const float4*>(sstage)[2 * (base + r) + 1]; }
-                    else { lo = __ldcg(srows + 2 * (size_t)(base + r)); hi = __ldcg(srows + 2 * (size_t)(base + r) + 1); }
+                    const float4 lo = __ldcg(srows + 2 * (size_t)(base + r)), hi = __ldcg(srows + 2 * (size_t)(base + r) + 1);
                     cb[r] = lo.x; cb[kColPitch + r] = lo.y; cb[2 * kColPitch + r] = lo.z; cb[3 * kColPitch + r] = lo.w;
                     cb[4 * kColPitch + r] = hi.x; cb[5 * kColPitch + r] = hi.y; cb[6 * kColPitch + r] = hi.z;
                 }
@@ -1042,7 +1206,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 const long long ca0 = clock64();
                 for (int k = 0; k < nchunks; k++) {
                     if (warp == 0) { if (lane < 7) acc = seq_add_contig(acc, chunk[k & 1] + lane * kColPitch, min(kIcpChunk, num - k * kIcpChunk)); }
-                    else if (k + 1 < nchunks) fill(k + 1, threadIdx.x - 32, blockDim.x - 32);
+                    else if (k + 1 < nchunks && helper >= 0) fill(k + 1, helper, kHelpers);
                     __syncthreads();
                 }
                 c_acc1 += clock64() - ca0;
@@ -1078,10 +1242,8 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 auto produce = [&](int k) {
                     const int base = k * kProd, cnt = min(kProd, num - base);
                     float* dst = ring + (k & 1) * (kProdPitch * 9);
-                    for (int r = threadIdx.x - 32; r < cnt; r += blockDim.x - 32) {
-                        float4 lo, hi;
-                        if (sstage) { lo = reinterpret_cast<const float4*>(sstage)[2 * (base + r)]; hi = reinterpret_cast<const float4*>(sstage)[2 * (base + r) + 1]; }
-                        else { lo = __ldcg(srows + 2 * (size_t)(base + r)); hi = __ldcg(srows + 2 * (size_t)(base + r) + 1); }
+                    for (int r = helper; r < cnt; r += kHelpers) {
+                        const float4 lo = __ldcg(srows + 2 * (size_t)(base + r)), hi = __ldcg(srows + 2 * (size_t)(base + r) + 1);
                         const float q0 = __fsub_rn(lo.w, md0), q1 = __fsub_rn(hi.x, md1), q2 = __fsub_rn(hi.y, md2);
                         const float m0 = __fsub_rn(lo.x, mm0), m1 = __fsub_rn(lo.y, mm1), m2 = __fsub_rn(lo.z, mm2);
                         float* d = dst + r;                                 // entry e of H: column e of the ring half
@@ -1090,7 +1252,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                         d[6 * kProdPitch] = __fmul_rn(q2, m0); d[7 * kProdPitch] = __fmul_rn(q2, m1); d[8 * kProdPitch] = __fmul_rn(q2, m2);
                     }
                 };
-                if (warp != 0) produce(0);
+                if (helper >= 0) produce(0);
                 __syncthreads();
                 for (int k = 0; k < nblk; k++) {
                     if (warp == 0) {
@@ -1098,7 +1260,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                             const int cnt = min(kProd, num - k * kProd);
                             acc = seq_add_contig(acc, ring + (k & 1) * (kProdPitch * 9) + lane * kProdPitch, cnt);
                         }
-                    } else if (k + 1 < nblk) produce(k + 1);
+                    } else if (k + 1 < nblk && helper >= 0) produce(k + 1);
                     __syncthreads();
                 }
                 if (warp == 0) {
@@ -1193,8 +1355,8 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char icp_smem[];
-    __shared__ NnPartial part;
     __shared__ int n_deferred, n_unsettled;
+    __shared__ float nn_merge_sm[2 * 48];
     __shared__ IcpFastShared cur;
     __shared__ float red[kIcpThreads / 32][16];
     __shared__ double tot[16];
@@ -1202,20 +1364,9 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
     constexpr int kWarps = kIcpThreads / 32;
     const bool sorting = do_sort && num < nd;          // an untrimmed sum does not depend on the order
 
-    const KdNode* nodes = kd.nodes; const float4* leaf = kd.pts_leaf;
-    unsigned char* sp = icp_smem;
-    if (plan.tree_bytes) {
-        KdNode* sn = reinterpret_cast<KdNode*>(sp);
-        float4* sl = reinterpret_cast<float4*>(sp + (size_t)plan.tree_nodes * sizeof(KdNode));
-        for (int i = threadIdx.x; i < plan.tree_nodes * 2; i += blockDim.x) reinterpret_cast<uint4*>(sn)[i] = reinterpret_cast<const uint4*>(kd.nodes)[i];
-        for (int i = threadIdx.x; i < kd.nm; i += blockDim.x) sl[i] = kd.pts_leaf[i];
-        nodes = sn; leaf = sl; sp += plan.tree_bytes;
-    }
-    float* sstage = plan.stage_bytes ? reinterpret_cast<float*>(sp) : nullptr;
-    sp += plan.stage_bytes;
-    unsigned* sradix = plan.radix_bytes ? reinterpret_cast<unsigned*>(sp) : nullptr;
-    sp += plan.radix_bytes;
-    int* squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr;
+    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, nd);
+    const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf;
+    float* sstage = sm.sstage; unsigned* sradix = sm.sradix; int* squeue = sm.squeue;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; i++) cur.R[i] = st->R[i];
         for (int i = 0; i < 3; i++) { cur.t[i] = st->t[i]; cur.mu_m[i] = st->mu_m[i]; cur.mu_d[i] = st->mu_d[i]; }
@@ -1242,51 +1393,16 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
         };
         // ---- phase A: transform + exact nearest neighbour (same searches as icp_kernel) ------------------------
         if (plan.brute_force) {
-            const int mchunk = (kd.nm + kWarps - 1) / kWarps;
-            const int m0 = min(warp * mchunk, kd.nm), m1 = min(m0 + mchunk, kd.nm);
-            for (int qpass = 0; (qpass * 32) * (int)gridDim.x + (int)blockIdx.x < nd; qpass++) {
-                const int i = (qpass * 32 + lane) * gridDim.x + blockIdx.x;
-                const bool valid = i < nd;
-                float qx = 0.0f, qy = 0.0f, qz = 0.0f;
-                if (valid) {
-                    const float4 p = __ldg(data + i);
-                    qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
-                    qy = __fadd_rn(dot3_ref(R[3], R[4], R[5], p.x, p.y, p.z), t[1]);
-                    qz = __fadd_rn(dot3_ref(R[6], R[7], R[8], p.x, p.y, p.z), t[2]);
-                }
-                float d1 = 3.402823466e+38f, d2 = 3.402823466e+38f; int i1 = 0;
-                for (int m = m0; m < m1; m++) {
-                    const float4 pm = leaf[m];
-                    const float e0 = qx - pm.x, e1 = qy - pm.y, e2 = qz - pm.z;
-                    const float dist = e0 * e0 + e1 * e1 + e2 * e2;
-                    if (dist < d1) { d2 = d1; d1 = dist; i1 = __float_as_int(pm.w); }
-                    else if (dist < d2) d2 = dist;
-                }
-                part.d1[warp][lane] = d1; part.d2[warp][lane] = d2; part.i1[warp][lane] = i1;
-                __syncthreads();
-                if (warp == 0) {
-                    float D1 = 3.402823466e+38f, D2 = 3.402823466e+38f; int I1 = 0;
-#pragma unroll
-                    for (int w = 0; w < kWarps; w++) {
-                        const float a = part.d1[w][lane], b = part.d2[w][lane];
-                        if (a < D1) { D2 = fminf(D1, b); D1 = a; I1 = part.i1[w][lane]; }
-                        else D2 = fminf(D2, a);
-                        D2 = fminf(D2, b);
-                    }
-                    if (valid) {
-                        if (D2 <= D1 * 1.00001f) I1 = kd_nearest(kd, nodes, leaf, qx, qy, qz, D1, D1);   // near tie: reference traversal order decides
-                        wk.nn[i] = I1; wk.d2[i] = D1;
-                        const float mx = __ldg(kd.model + 3 * I1), my = __ldg(kd.model + 3 * I1 + 1), mz = __ldg(kd.model + 3 * I1 + 2);
-                        if (sorting) {
-                            wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
-                            float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
-                            row[0] = make_float4(mx, my, mz, qx);
-                            row[1] = make_float4(qy, qz, D1, 0.0f);
-                        } else add_row(mx, my, mz, qx, qy, qz, D1);
-                    }
-                }
-                __syncthreads();
-            }
+            unsigned long long* park = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
+            icp_nn_small_model(kd, sm, plan.qcache_n, data, nd, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
+                wk.nn[i] = I1;
+                if (sorting) {
+                    wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
+                    float4* row = reinterpret_cast<float4*>(wk.q) + 2 * (size_t)i;
+                    row[0] = make_float4(mx, my, mz, qx);
+                    row[1] = make_float4(qy, qz, D1, 0.0f);
+                } else add_row(mx, my, mz, qx, qy, qz, D1);
+            });
         } else {
             int* deferred = wk.order + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
             if (threadIdx.x == 0) { n_deferred = 0; n_unsettled = 0; }
@@ -1469,26 +1585,33 @@ static IcpSmemPlan icp_plan(const KdView& kd, int n_nodes, int nd, int num, int 
     // 1 M x 1 M - / 26.3 / 16.2, bunny 40 k x 40 k 0.034 / 0.031 / 0.026: with 32 divergent walks per warp there is nearly
     // always a lane in a leaf scan or an unwind, so the warp pays the longest branch at every step; the cooperative search
     // keeps the lanes in lock step on one query.  GOICP_NN_BUDGET overrides (the parity tests force each path).
-    IcpSmemPlan p = {0, 0, 0, 0, 0, 1, 0};
+    IcpSmemPlan p = {0, 0, 0, 0, 0, 1, 0, 0, 0};
+    (void)num;
     if (const char* f = getenv("GOICP_NN_BUDGET")) p.nn_budget = atoi(f);
     int left = smem_limit;
-    // models beyond the brute-force range are searched through the tree (it cannot fit in shared memory at that size):
+    // models beyond the linear-scan range are searched through the tree (it cannot fit in shared memory at that size):
     // the cooperative search's per-warp rings come first
     if (kd.nm > 16384) { p.queue_bytes = (kIcpThreads / 32) * kCoopQ * (int)sizeof(int); left -= p.queue_bytes; }
-    const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
-    const size_t stage = (size_t)num * 8 * sizeof(float);
-    if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
-    if (stage <= (size_t)left) { p.stage_bytes = (int)stage; left -= (int)stage; }
-    // sort: rank by counting while the keys can sit in shared memory next to the staged rows, radix sort beyond
+    p.brute_force = kd.nm <= 16384 ? 1 : 0;
+    // sort: rank by counting while the cloud is small and its keys can sit in shared memory, radix sort beyond
     // (GOICP_ICP_RADIX=1/0 forces the choice -- used by the parity tests to cover both on the same input)
-    bool radix = p.stage_bytes == 0;
-    if (const char* f = getenv("GOICP_ICP_RADIX")) radix = f[0] == '1';
-    if (radix && kRadixSmemBytes > left) {       // make room: the tree goes back to global memory
-        left += p.tree_bytes; p.tree_nodes = 0; p.tree_bytes = 0;
-    }
+    const size_t keys = ((size_t)nd * sizeof(unsigned long long) + 15) & ~(size_t)15;
+    bool radix = nd > 6144 || keys + 8192 > (size_t)left;
+    if (const char* f = getenv("GOICP_ICP_RADIX")) radix = f[0] == '1' || keys > (size_t)left;
     if (radix) { p.radix_bytes = kRadixSmemBytes; left -= kRadixSmemBytes; }
-    // linear scan while it beats the (divergent) tree descent: model resident in shared memory, or moderate size
-    p.brute_force = (p.tree_bytes != 0 || kd.nm <= 16384) ? 1 : 0;
+    else { p.stage_bytes = (int)keys; left -= (int)keys; }
+    if (p.brute_force) {
+        // this CTA's data points + distance hints (at most ceil(nd / 128) + 1 queries per CTA matter, 512 kept)
+        p.qcache_n = std::min(512, nd / 128 + 2);
+        left -= (int)(((size_t)p.qcache_n * kQCacheEntry + 15) & ~(size_t)15);
+        if (kd.grid_start) {
+            const size_t grid = (((size_t)(kd.gcells + 1) * sizeof(unsigned short) + 15) & ~(size_t)15) + (size_t)kd.nm * sizeof(float4);
+            if (grid <= (size_t)left) { p.grid_bytes = (int)grid; left -= (int)grid; }
+        }
+        // the kd-tree (walked only by near-tied queries) on chip as well when there is room
+        const size_t tree = (size_t)n_nodes * sizeof(KdNode) + (size_t)kd.nm * sizeof(float4);
+        if (tree <= (size_t)left) { p.tree_nodes = n_nodes; p.tree_bytes = (int)((tree + 15) / 16 * 16); left -= p.tree_bytes; }
+    }
     return p;
 }
 int icp_threads() { return kIcpThreads; }
@@ -1502,7 +1625,7 @@ int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int n
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     const IcpSmemPlan p = icp_plan(kd, n_nodes, nd, num, limit);
     int per_sm = 0, sms = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kIcpThreads, (size_t)p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kIcpThreads, icp_plan_bytes(p));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
@@ -1519,7 +1642,7 @@ cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int 
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
                     (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&do_sort, (void*)&plan, (void*)&d_partials};
     return cudaLaunchCooperativeKernel(kern, dim3(grid_blocks), dim3(kIcpThreads), args,
-                                       (size_t)plan.tree_bytes + plan.stage_bytes + plan.radix_bytes + plan.queue_bytes, s);
+                                       icp_plan_bytes(plan), s);
 }
 
 } // namespace goicp
