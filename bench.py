@@ -440,6 +440,20 @@ def main():
                                       "e2e_seconds_per_step": c_e2e["seconds_per_step"], "e2e_value": c_e2e["value"],
                                       "reference_cpu_here": {"register_s": 338.6, "bound_evals": 1696656, "note": "oracle/_ref in the build container (tests/golden/goicp_runs.json)"}}
 
+        if "certified_mse" in wl:
+            # the reference's OTHER search strategy (its GPU path, src/fgoicp): quaternion cube + relaxed ICP trigger, include/goicp_b200.h
+            fe = make_engine()
+            fe.search_mode = 1
+            fe.SetDT(*eng.GetDT())
+            f_total, f_results = timed_registers(fe, 3, 2)
+            fe.close()
+            fr = f_results[-1]
+            dR = float(2 * np.arcsin(min(1.0, np.linalg.norm(fr["R"].astype(np.float64) - res["R"].astype(np.float64)) / (2 * np.sqrt(2)))))
+            out_extra["fgoicp_style_search"] = {"seconds_per_step": f_total / 3, "exit_path": fr["exit_path"], "rot_pops": int(fr["rot_pops"]), "trans_pops": int(fr["trans_pops"]),
+                                                "bound_evals": int(fr["bound_evals"]), "icp_calls": int(fr["icp_calls"]), "nn_sse": fr["sse"],
+                                                "pose_vs_default_mode": {"dR_rad": dR, "dt": float(np.abs(fr["t"] - res["t"]).max())},
+                                                "note": "strategy of icp::FastGoICP (quaternion cube, span cut-offs 0.1 / 0.12, ub < 2 best => ICP) on this engine's kernels; no executable oracle"}
+
     # ---- roofline of the dominant kernel (this rank's GPU only)
     peaks = {}
     try:
@@ -507,6 +521,8 @@ def main():
            "seconds_bnb_kernels_per_step": kern_s / args.steps, "seconds_dt_score_per_step": float(np.mean([r["seconds_dt_score"] for r in results])),
            "seconds_strict_resolves_per_step": float(np.mean([r["seconds_strict"] for r in results])), "strict_resolves_per_step": int(res["strict_resolves"]),
            "contender_overflows": int(sum(r["contender_overflows"] for r in results)),
+           "seconds_host_frontier_per_step": float(np.mean([r["seconds_host"] for r in results])),
+           "host_frontier_share_of_register": float(np.mean([r["seconds_host"] / r["seconds_total"] for r in results])),
            "exchange": (os.environ.get("GOICP_EXCHANGE", "nccl") if world > 1 else None)}
     out.update(out_extra)
     if wl.get("ref_register_s"):

@@ -35,7 +35,7 @@ class Params(C.Structure):
                 ("dt_size", C.c_int), ("dt_expand", C.c_double),
                 ("rot_cube", C.c_float * 4), ("trans_cube", C.c_float * 4),
                 ("icp_max_iter", C.c_int), ("device", C.c_int), ("spec_cubes", C.c_int), ("cluster_size", C.c_int), ("dt_mode", C.c_int),
-                ("rank", C.c_int), ("world_size", C.c_int), ("numerics", C.c_int)]
+                ("rank", C.c_int), ("world_size", C.c_int), ("numerics", C.c_int), ("search_mode", C.c_int)]
 
 
 class Result(C.Structure):
@@ -45,7 +45,8 @@ class Result(C.Structure):
                 ("bound_evals_executed", C.c_int64), ("icp_calls", C.c_int64), ("rounds", C.c_int64), ("kernel_launches", C.c_int64),
                 ("seconds_total", C.c_double), ("seconds_bnb_kernels", C.c_double), ("seconds_icp", C.c_double),
                 ("bound_evals_executed_local", C.c_int64), ("strict_resolves", C.c_int64), ("contender_overflows", C.c_int64),
-                ("seconds_dt_score", C.c_double), ("seconds_strict", C.c_double), ("seconds_setup", C.c_double), ("bnb_kernel_variants", C.c_int64)]
+                ("seconds_dt_score", C.c_double), ("seconds_strict", C.c_double), ("seconds_setup", C.c_double), ("seconds_host", C.c_double),
+                ("bnb_kernel_variants", C.c_int64)]
 
     def as_dict(self):
         return {"R": np.array(self.R, np.float32).reshape(3, 3), "t": np.array(self.t, np.float32),
@@ -56,7 +57,8 @@ class Result(C.Structure):
                 "seconds_bnb_kernels": self.seconds_bnb_kernels, "seconds_icp": self.seconds_icp,
                 "bound_evals_executed_local": self.bound_evals_executed_local, "strict_resolves": self.strict_resolves,
                 "contender_overflows": self.contender_overflows, "seconds_dt_score": self.seconds_dt_score,
-                "seconds_strict": self.seconds_strict, "seconds_setup": self.seconds_setup, "bnb_kernel_variants": self.bnb_kernel_variants}
+                "seconds_strict": self.seconds_strict, "seconds_setup": self.seconds_setup, "seconds_host": self.seconds_host,
+                "bnb_kernel_variants": self.bnb_kernel_variants}
 
 
 class IcpResult(C.Structure):
@@ -192,6 +194,7 @@ class GoICP:
         self.dt = _DT()
         self.dt_mode = p.dt_mode          # default: exact EDT with the reference binary's corner seed (include/goicp_b200.h)
         self.numerics = p.numerics
+        self.search_mode = 0              # 0: GoICP::Register (reference-identical); 1: fgoicp-style strategy (include/goicp_b200.h)
         self.spec_cubes = 0
         self.cluster_size = 0
         self.initNodeRot = [p.rot_cube[i] for i in range(4)]
@@ -225,6 +228,7 @@ class GoICP:
             p.dt_expand = float(self.dt.expandFactor)
             p.dt_mode = int(self.dt_mode)
             p.numerics = int(self.numerics)
+            p.search_mode = int(self.search_mode)
             p.spec_cubes = int(self.spec_cubes)
             p.cluster_size = int(self.cluster_size)
             p.rank, p.world_size = self.rank, self.world_size

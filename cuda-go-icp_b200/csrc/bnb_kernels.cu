@@ -573,6 +573,7 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
                     own.n_cand = n_cand;
                 }
                 if (lb >= opt_t) continue;
+                if ((int)own.plevel + 1 > c.trans_cutoff_level) continue;          // span cut-off (fgoicp-style search): evaluated, not subdivided
                 HeapEntry e; e.lb = lb; e.level = own.plevel + 1;
                 unsigned long long path = (((unsigned long long)own.ppath_hi << 32) | own.ppath_lo) | ((unsigned long long)j << (3 * own.plevel));
                 e.path_lo = (uint32_t)path; e.path_hi = (uint32_t)(path >> 32);
@@ -857,6 +858,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                 } else flags |= 1u;
             }
             if (lb >= opt_t) continue;
+            if ((int)plevel + 1 > c.trans_cutoff_level) continue;                  // span cut-off (fgoicp-style search): evaluated, not subdivided
             pmask |= 1u << j;
         }
         // ---- which node will the queue pop next? ------------------------------------------------

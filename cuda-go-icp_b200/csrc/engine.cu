@@ -403,6 +403,7 @@ int make_const(goicp_handle* h, BnbConst& c)
     c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
     c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
     for (int i = 0; i < kMaxRotLevel; i++) c.cgamma[i] = h->cgamma[i];
+    c.trans_cutoff_level = kMaxTransLevel;
     c.dbg = nullptr;
     return GOICP_OK;
 }
@@ -668,7 +669,7 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     return GOICP_OK;
 }
 
-int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, float err_diff, goicp_icp_result* out, int blocks_cap = 1 << 30)
+int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, float err_diff, goicp_icp_result* out, int blocks_cap = 1 << 30, bool force_fast = false)
 {
     int rc = ensure_cuda(h); if (rc) return rc;
     rc = upload_data(h); if (rc) return rc;
@@ -689,7 +690,7 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     const double t_begin = now_s();
     CUDA_TRY(h, xfer(h, h->d_icp_state.p, &st, sizeof st, cudaMemcpyHostToDevice, h->stream));
     const int n_nodes = (int)h->kd_host.nodes.size();
-    const bool fast = (h->p.numerics & GOICP_NUM_FAST_ICP) != 0;
+    const bool fast = force_fast || (h->p.numerics & GOICP_NUM_FAST_ICP) != 0;
     const int max_blocks = icp_max_grid_blocks(h->p.device, kd_view(h), n_nodes, h->nd, num, h->max_smem_optin, fast);
     if (max_blocks <= 0) return fail(h, GOICP_ERR_CUDA, "cooperative ICP kernel cannot be resident");
     // queries are interleaved over the CTAs, one per warp and pass (16 per CTA): use every SM the cooperative launch allows
@@ -731,6 +732,142 @@ void publish(goicp_handle* h, const goicp_result& res, int finished)
     h->snap.bound_evals = res.bound_evals; h->snap.finished = finished;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// GOICP_SEARCH_FGOICP: the search strategy of the reference's GPU path, icp::FastGoICP::run (src/fgoicp/fgoicp.cpp:9-181),
+// on this engine's kernels.  Rotation nodes are cubes (centre q, half edge `span`) of the vector part of a unit quaternion
+// in [-1,1]^3 (fgoicp_common.hpp:31-105); the translation domain is [-1,1]^3; a popped rotation node spawns 8 children
+// unless their span falls below 0.1 (:50); a child outside the unit ball is dropped, one whose centre is outside it is
+// queued unevaluated with its parent's bounds (:58-63); otherwise an upper-bound translation BnB (rotation fixed), the
+// relaxed refinement trigger `ub < 2 * best => ICP` (:75-91, 500 iterations, relative stop 1e-3), then a lower-bound
+// translation BnB with the rotation-uncertainty radius of the cube; children with lb >= best are dropped (:97).  The search
+// ends on `best - lb <= sse_threshold` (:44) or when the queue runs dry.  Nodes order by lb, ties by larger span (:88-95).
+// The translation BnB is this library's persistent inner-BnB kernel with fgoicp's span cut-off (translation cubes of half
+// edge < 0.12 are evaluated but not subdivided, :156-157) -- up to 8 queue nodes' children (128 inner BnBs) per device round,
+// committed in queue order.  Deviations, all deliberate: distances come from the distance transform (fgoicp's table only
+// covers [0,1]^3); the rotation-uncertainty radius is 2 |p| sin(min(sqrt3 pi span / 2, pi / 2)) (registration.cu:41-43 uses
+// |p|^2 with a "needs examination" note); the error of a pose is ICP's sum of squared nearest-neighbour distances, as there.
+// ---------------------------------------------------------------------------------------------
+struct QNode { float x, y, z, span, lb, ub; };
+struct QLower { bool operator()(const QNode& a, const QNode& b) const { return a.lb == b.lb ? a.span < b.span : a.lb > b.lb; } };
+
+void quat_rotation(float x, float y, float z, float* R)
+{
+    const float r = x * x + y * y + z * z, ww = 1.0f - r, w = std::sqrt(std::max(ww, 0.0f));
+    const float wx = w * x, xx = x * x, wy = w * y, xy = x * y, yy = y * y, wz = w * z, xz = x * z, yz = y * z, zz = z * z;
+    R[0] = ww + xx - yy - zz; R[1] = 2 * (xy - wz);      R[2] = 2 * (xz + wy);
+    R[3] = 2 * (xy + wz);     R[4] = ww - xx + yy - zz;  R[5] = 2 * (yz - wx);
+    R[6] = 2 * (xz - wy);     R[7] = 2 * (yz + wx);      R[8] = ww - xx - yy + zz;
+}
+
+int register_fgoicp(goicp_handle* h, goicp_result* out)
+{
+    const double t_begin = now_s();
+    h->initialized = false;
+    int rc = initialize(h); if (rc) return rc;
+    BnbConst c; rc = make_const(h, c); if (rc) return rc;
+    rc = ensure_kdtree(h); if (rc) return rc;
+    h->t_setup = now_s() - t_begin;
+    // fgoicp's constants
+    const float kRotSpanMin = 0.1f, kIcpRel = 1e-3f;
+    const int kIcpIter0 = 1000, kIcpIter = 500, kBatch = 8;
+    c.tx = c.ty = c.tz = -1.0f; c.tw = 2.0f;                                   // TransNode(0,0,0, span 1)
+    c.trans_cutoff_level = 3;                                                  // half edges 1, .5, .25, .125 are subdivided; .0625 < 0.12 is not
+    c.inlier_num = h->nd; c.do_trim = 0;
+    const float sse_threshold = (float)h->nd * h->p.mse_threshold;             // fgoicp.hpp:24
+    c.sse_thresh = sse_threshold;
+    for (int d = 0; d < kMaxRotLevel; d++) {                                   // rotation-uncertainty scale of a cube at depth d (half edge 2^-d)
+        const double half_angle = std::min(kSqrt3 * kPi / 2.0 * std::pow(0.5, d), kPi / 2.0);
+        c.cgamma[d] = (float)(2.0 * std::sin(half_angle));
+    }
+    goicp_result res; std::memset(&res, 0, sizeof res);
+    res.sse_thresh = sse_threshold;
+    float best = 1e+10f, optR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, optT[3] = {0, 0, 0};
+    auto sync_res = [&]() { std::memcpy(res.R, optR, sizeof optR); std::memcpy(res.t, optT, sizeof optT); res.sse = best; };
+    {
+        goicp_icp_result r;
+        rc = run_icp(h, optR, optT, kIcpIter0, -kIcpRel, &r, 1 << 30, true); if (rc) return rc;
+        res.icp_calls++;
+        best = r.err; std::memcpy(optR, r.R, sizeof optR); std::memcpy(optT, r.t, sizeof optT);
+    }
+    sync_res(); publish(h, res, 0);
+    int exit_path = GOICP_EXIT_NONE; float exit_lb = 0;
+    if (!(best > sse_threshold)) exit_path = GOICP_EXIT_EARLY_SSE;             // fgoicp.cpp:21: the BnB only runs when the first ICP is not good enough
+    std::vector<QNode> heap; QLower lower;
+    heap.push_back(QNode{0, 0, 0, 1.0f, 0.0f, best}); std::push_heap(heap.begin(), heap.end(), lower);
+    struct Child { int parent; QNode n; bool evaluate; float R[9]; int depth; int task_ub, task_lb; };
+    while (exit_path == GOICP_EXIT_NONE) {
+        if (h->cancel_flag.load()) { exit_path = GOICP_EXIT_CANCELLED; break; }
+        if (heap.empty()) { exit_path = GOICP_EXIT_QUEUE_EMPTY; break; }
+        // pop up to kBatch nodes (the first decides the certificate, :44)
+        std::vector<QNode> popped;
+        while (!heap.empty() && (int)popped.size() < kBatch) {
+            const QNode top = heap.front();
+            if (best - top.lb <= sse_threshold) { if (popped.empty()) { exit_path = GOICP_EXIT_CERTIFIED; exit_lb = top.lb; res.rot_pops++; } break; }
+            std::pop_heap(heap.begin(), heap.end(), lower); heap.pop_back();
+            popped.push_back(top);
+        }
+        if (exit_path != GOICP_EXIT_NONE) break;
+        std::vector<Child> kids;
+        int n_tasks = 0;
+        rc = ensure_task_buffers(h, (size_t)kBatch * 16 + 64); if (rc) return rc;
+        for (size_t pi = 0; pi < popped.size(); pi++) {
+            const QNode& P = popped[pi];
+            const float span = P.span / 2.0f;
+            if (span < kRotSpanMin) continue;
+            int depth = 0; { float sp = 1.0f; while (sp > span * 1.5f && depth < kMaxRotLevel - 1) { sp *= 0.5f; depth++; } }
+            for (int j = 0; j < 8; j++) {
+                Child k; k.parent = (int)pi; k.depth = depth; k.task_ub = k.task_lb = -1;
+                k.n = QNode{P.x - span + (j & 1) * P.span, P.y - span + (j >> 1 & 1) * P.span, P.z - span + (j >> 2 & 1) * P.span, span, P.lb, P.ub};
+                // nearest point of the cube to the origin inside the unit ball?  (overlaps_SO3, fgoicp_common.hpp:103-107, stated geometrically)
+                const float nx = std::max(std::fabs(k.n.x) - span, 0.0f), ny = std::max(std::fabs(k.n.y) - span, 0.0f), nz = std::max(std::fabs(k.n.z) - span, 0.0f);
+                if (nx * nx + ny * ny + nz * nz > 1.0f) continue;
+                k.evaluate = k.n.x * k.n.x + k.n.y * k.n.y + k.n.z * k.n.z <= 1.0f;      // in_SO3
+                if (k.evaluate) {
+                    quat_rotation(k.n.x, k.n.y, k.n.z, k.R);
+                    for (int pass = 0; pass < 2; pass++) {
+                        InnerTask& t = h->h_tasks[n_tasks];
+                        std::memcpy(t.R, k.R, sizeof k.R);
+                        t.level = pass == 0 ? -1 : depth;
+                        t.opt_error = pass == 0 ? 2.0f * best : best;           // the ub pass must report values up to 2 * best (:75)
+                        t.pad = 0;
+                        (pass == 0 ? k.task_ub : k.task_lb) = n_tasks++;
+                    }
+                }
+                kids.push_back(k);
+            }
+        }
+        res.rot_pops += (int64_t)popped.size();
+        if (n_tasks > 0) { rc = run_inner_batch(h, c, n_tasks, &res.bound_evals_executed, nullptr, &res.bound_evals_executed_local); if (rc) return rc; res.rounds++; }
+        const std::vector<InnerResult> results(h->h_results, h->h_results + n_tasks);
+        for (const Child& k : kids) {
+            QNode nd = k.n;
+            if (!k.evaluate) { heap.push_back(nd); std::push_heap(heap.begin(), heap.end(), lower); continue; }
+            const InnerResult& ru = results[k.task_ub]; const InnerResult& rl = results[k.task_lb];
+            res.trans_pops += ru.pops + rl.pops; res.bound_evals += ru.evals + rl.evals;
+            const float ub = ru.value;
+            if (ub < 2.0f * best && ru.node[3] > 0.0f) {
+                float t0[3] = {ru.node[0] + ru.node[3] / 2, ru.node[1] + ru.node[3] / 2, ru.node[2] + ru.node[3] / 2};
+                goicp_icp_result r;
+                rc = run_icp(h, k.R, t0, kIcpIter, -kIcpRel, &r, 1 << 30, true); if (rc) return rc;
+                res.icp_calls++;
+                if (r.err < best) { best = r.err; std::memcpy(optR, r.R, sizeof optR); std::memcpy(optT, r.t, sizeof optT); sync_res(); publish(h, res, 0); }
+            }
+            const float lb = rl.value;
+            if (lb >= best) continue;
+            nd.lb = lb; nd.ub = ub;
+            heap.push_back(nd); std::push_heap(heap.begin(), heap.end(), lower);
+        }
+    }
+    sync_res();
+    res.exit_path = exit_path; res.best_lb = exit_lb; res.kernel_launches = h->launches;
+    res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp; res.seconds_setup = h->t_setup;
+    res.bnb_kernel_variants = h->bnb_variants;
+    publish(h, res, 1);
+    *out = res;
+    return exit_path == GOICP_EXIT_CANCELLED ? GOICP_ERR_CANCELLED : GOICP_OK;
+}
+
 } // namespace
 
 // =============================================================================================
@@ -750,6 +887,7 @@ void goicp_default_params(goicp_params* p)
     p->device = 0; p->spec_cubes = 0; p->cluster_size = 0; p->dt_mode = GOICP_DT_EXACT_EDT_REFSEED;
     p->rank = 0; p->world_size = 1;
     p->numerics = GOICP_NUM_STRICT;
+    p->search_mode = GOICP_SEARCH_GOICP;
 }
 
 int goicp_create(const goicp_params* p, goicp_handle** out)
@@ -1184,6 +1322,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
     h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->t_score = h->t_strict = 0; h->strict_resolves = 0; h->cand_overflows = 0; h->bnb_variants = 0;
+    if (h->p.search_mode == GOICP_SEARCH_FGOICP) return register_fgoicp(h, out);
     const double t_begin = now_s();
     h->initialized = false;
     int rc = initialize(h); if (rc) return rc;
@@ -1379,6 +1518,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     res.seconds_total = now_s() - t_begin; res.seconds_bnb_kernels = h->t_kernels; res.seconds_icp = h->t_icp;
     res.strict_resolves = h->strict_resolves; res.contender_overflows = h->cand_overflows; res.bnb_kernel_variants = h->bnb_variants;
     res.seconds_dt_score = h->t_score; res.seconds_strict = h->t_strict; res.seconds_setup = h->t_setup;
+    res.seconds_host = res.seconds_total - h->t_setup - h->t_kernels - h->t_icp - h->t_score - h->t_strict;
     if (getenv("GOICP_ROUND_STATS"))
         fprintf(stderr, "[register] total %.3f s: setup (upload, gamma table, kd-tree) %.3f, BnB kernels + exchange %.3f, ICP %.3f, DT scoring %.3f, strict resolves %.3f (%lld), rest (host commit, copies) %.3f\n",
                 res.seconds_total, h->t_setup, h->t_kernels, h->t_icp, h->t_score, h->t_strict, (long long)h->strict_resolves,

@@ -21,6 +21,8 @@ struct BnbConst {
     float sse_thresh;                   // SSEThresh (jly_goicp.cpp:208)
     float tx, ty, tz, tw;               // initNodeTrans (jly_goicp.cpp:50-53)
     float cgamma[kMaxRotLevel];         // 2*sinf(maxAngle_l/2): maxRotDis[l][i] = cgamma[l]*||p_i|| (jly_goicp.cpp:150-160)
+    int trans_cutoff_level;             // translation cubes deeper than this are evaluated but not queued (kMaxTransLevel = no cut-off; the
+                                        // fgoicp-style search stops subdividing below a span, fgoicp.cpp:156-157)
     unsigned long long* dbg;            // optional (GOICP_ROUND_STATS): 8 cycle counters per task of the pipelined inner BnB, else nullptr
 };
 

@@ -1519,7 +1519,9 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
         if (threadIdx.x == 0) {
             const float err_new = (float)tot[6];
             cur.err_new = err_new; cur.iter = iter;
-            if (cur.err > 0.0f && cur.err - err_new < err_diff * (float)num) cur.converged = 1;            // jly_icp3d.hpp:257
+            // jly_icp3d.hpp:257; err_diff < 0 selects fgoicp's relative rule instead (icp3d.cu:96: stop when the improvement is
+            // at most |err_diff| of the previous error)
+            if (cur.err > 0.0f && (err_diff >= 0.0f ? cur.err - err_new < err_diff * (float)num : cur.err - err_new <= -err_diff * cur.err)) cur.converged = 1;
             else {
                 cur.err = err_new;
                 // means on top of the previous means, divided by n (the reference never resets them, :205-206, :244-263)

@@ -65,6 +65,18 @@ typedef enum {
                                  shows that Matrix::svd's own rounding is part of the trajectory, profiles/r2_parity_modes.md) */
 } goicp_numerics;
 
+/* Which search goicp_register runs. */
+typedef enum {
+    GOICP_SEARCH_GOICP = 0,   /* GoICP::Register of src/goicp (jly_goicp.cpp:342-585): angle-axis rotation cubes, nested translation BnB,
+                                 results identical to the reference's -- the default, and the only mode with an executable oracle */
+    GOICP_SEARCH_FGOICP = 1   /* the strategy of the reference's own GPU path, icp::FastGoICP (src/fgoicp/fgoicp.cpp:9-181): unit-quaternion
+                                 cube [-1,1]^3 with its SO(3) overlap tests, rotation span cut-off 0.1 and translation span cut-off 0.12,
+                                 translation domain [-1,1]^3, the relaxed trigger "ub < 2 * best => ICP" (500 iterations, relative
+                                 stop 1e-3), error = sum of squared NEAREST-NEIGHBOUR distances.  Bounds come from this library's distance
+                                 transform instead of fgoicp's 300^3 trilinear table over [0,1]^3 (registration.hpp:67, "TODO: needs fix"),
+                                 so it is a compatible strategy, not a bit-compatible restatement */
+} goicp_search_mode;
+
 /* Replaces the public tunables of class GoICP (jly_goicp.h:85-120) and its constructor
  * defaults (jly_goicp.cpp:40-72). */
 typedef struct {
@@ -84,6 +96,7 @@ typedef struct {
     /* multi-GPU sharding of the rotation frontier (all ranks hold identical inputs) */
     int    rank, world_size;
     int    numerics;         /* goicp_numerics bit flags (default 0: strict) */
+    int    search_mode;      /* goicp_search_mode (default GOICP_SEARCH_GOICP) */
 } goicp_params;
 
 /* Replaces the public results of class GoICP (optR/optT/optError/optNodeRot/optNodeTrans,
@@ -110,6 +123,8 @@ typedef struct {
     int64_t contender_overflows;         /* ... of which the kernel could not keep every contender (more than 128 within rounding of the
                                             minimum): the arg-min was then chosen among the 128 kept -- reported, never silent */
     double seconds_dt_score, seconds_strict, seconds_setup;   /* DT scoring of poses / strict re-evaluations / upload + kd-tree */
+    double seconds_host;                 /* the rest of seconds_total: the host side of the rotation frontier (queue, prune, commit in the
+                                            reference's order, task lists) -- the part a device-side frontier would absorb */
     int64_t bnb_kernel_variants;         /* which translation-BnB kernels ran: bit 0 inner_bnb_pipelined_kernel<1,1> (points in shared memory,
                                             low-latency), bit 1 <1,0>, bit 2 <0,1>, bit 3 <0,0>, bit 4 inner_bnb_kernel (trimming / GOICP_NO_PIPELINE) */
 } goicp_result;
