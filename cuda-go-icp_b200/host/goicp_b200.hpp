@@ -40,7 +40,11 @@ public:
     POINT3D* pData = nullptr;
     ROTNODE initNodeRot;
     TRANSNODE initNodeTrans;
-    struct { int SIZE = 300; double expandFactor = 2.0; int mode = GOICP_DT_REFERENCE; } dt;   // DT3D's public knobs (jly_3ddt.h:100-111)
+    // DT3D's public knobs (jly_3ddt.h:100-111); mode: goicp_dt_mode (default: exact EDT of the reference's seed set -- same
+    // registrations as GOICP_DT_REFERENCE, the bit-exact propagation, at 1/200 of its build time)
+    struct { int SIZE = 300; double expandFactor = 2.0; int mode = GOICP_DT_EXACT_EDT_REFSEED; } dt;
+    int numerics = GOICP_NUM_STRICT;                    // goicp_numerics flags
+    int searchMode = GOICP_SEARCH_GOICP;                // goicp_search_mode
     float MSEThresh, SSEThresh = 0, optError = 1e+10f;
     float trimFraction = 0.0f;
     bool doTrim = true;
@@ -80,7 +84,7 @@ private:
         if (!pModel || !pData || Nm <= 0 || Nd <= 0) throw std::runtime_error("GoICP: pModel/Nm/pData/Nd not set");
         goicp_params p; goicp_default_params(&p);
         p.mse_threshold = MSEThresh; p.trim_fraction = trimFraction; p.do_trim = doTrim ? 1 : 0;
-        p.dt_size = dt.SIZE; p.dt_expand = dt.expandFactor; p.dt_mode = dt.mode; p.device = device_;
+        p.dt_size = dt.SIZE; p.dt_expand = dt.expandFactor; p.dt_mode = dt.mode; p.device = device_; p.numerics = numerics; p.search_mode = searchMode;
         p.rot_cube[0] = initNodeRot.a; p.rot_cube[1] = initNodeRot.b; p.rot_cube[2] = initNodeRot.c; p.rot_cube[3] = initNodeRot.w;
         p.trans_cube[0] = initNodeTrans.x; p.trans_cube[1] = initNodeTrans.y; p.trans_cube[2] = initNodeTrans.z; p.trans_cube[3] = initNodeTrans.w;
         if (goicp_create(&p, &h_)) throw std::runtime_error("goicp_create failed");

@@ -284,3 +284,52 @@ def test_fgoicp_style_search_reaches_the_reference_optimum(pkg, runs, name):
     assert a["rot_pops"] <= 585
     assert rot_angle(a["R"], np.array(gold["R"]).reshape(3, 3)) < 2e-2 and np.abs(a["t"] - np.array(gold["t"])).max() < 2e-2
     assert a["sse"] <= e_gold * 1.02
+
+
+def _write_txt(path, arr):
+    with open(path, "w") as f:
+        f.write(f"{len(arr)}\n")
+        for q in arr:
+            f.write("%.9g %.9g %.9g\n" % tuple(q))
+
+
+def test_cli_and_cpp_mirror_binaries(pkg, runs, bunny, tmp_path):
+    """The two host programs the Makefile builds, run as a user would: `goicp_b200_cli <config.toml>` (the reference's
+    `cis5650_fgo_icp <config.toml>` without the window: TOML -> clouds -> DT -> Go-ICP -> output.toml + viz.ply) and
+    `example_mirror` (the C++ mirror of class GoICP with the reference's member names, main.cpp:47-59)."""
+    import json
+    pkg_dir = os.path.join(ROOT, "cuda-go-icp_b200")
+    _write_txt(tmp_path / "model.txt", bunny["model"]); _write_txt(tmp_path / "data.txt", bunny["data"])
+    cfg = tmp_path / "bunny.toml"
+    cfg.write_text('[info]\ndescription = "bunny"\n[io]\ntarget = "model.txt"\nsource = "data.txt"\noutput = "output.toml"\nvisualization = "viz.ply"\n'
+                   '[params]\nmode = 3\ntrim = true\nsubsample = 1.0\nmse_threshold = 1e-3\nresize = 1.0\n')
+    r = subprocess.run([os.path.join(pkg_dir, "goicp_b200_cli"), str(cfg)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r.returncode == 0, r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    gold = runs["bunny_s0.1_mse1e-3"]
+    assert out["exit_path"] == gold["exit_path"] and (out["rot_pops"], out["trans_pops"]) == (gold["rot_pops"], gold["trans_pops"])
+    assert out["sse"] == pytest.approx(gold["sse"], rel=1e-5)
+    assert rot_angle(np.array(out["R"]).reshape(3, 3), np.array(gold["R"]).reshape(3, 3)) < 1e-4
+    text = (tmp_path / "output.toml").read_text()
+    assert "rotation_nodes = 206" in text and "exit_path = \"early_sse_below_thresh\"" in text
+    ply = (tmp_path / "viz.ply").read_text().splitlines()
+    assert ply[0] == "ply" and f"element vertex {len(bunny['model']) + len(bunny['data'])}" in ply[:4]
+    body = ply[ply.index("end_header") + 1:]
+    assert len(body) == len(bunny["model"]) + len(bunny["data"])
+    # the registered source points sit on the target: last vertex = R * last data point + t
+    R, t = np.array(out["R"]).reshape(3, 3), np.array(out["t"])
+    last = np.array([float(x) for x in body[-1].split()[:3]])
+    assert np.abs(last - (R @ bunny["data"][-1].astype(np.float64) + t)).max() < 1e-4
+    # a missing key falls back to the reference's Config defaults (mode 1 = ICP only, mse 1e-5): common.cpp:11-13,56-60
+    cfg2 = tmp_path / "icp_only.toml"
+    cfg2.write_text('[io]\ntarget = "model.txt"\nsource = "data.txt"\n')
+    r2 = subprocess.run([os.path.join(pkg_dir, "goicp_b200_cli"), str(cfg2)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert r2.returncode == 0, r2.stderr
+    o2 = json.loads(r2.stdout.strip().splitlines()[-1])
+    assert o2["rot_pops"] == 0 and o2["exit_path"] == "none" and o2["sse"] > 0
+    # unreadable input: an error message and a non-zero exit code, no crash
+    r3 = subprocess.run([os.path.join(pkg_dir, "goicp_b200_cli"), str(tmp_path / "nope.toml")], capture_output=True, text=True, cwd=tmp_path, timeout=60)
+    assert r3.returncode != 0 and "error" in r3.stderr.lower()
+    # the C++ mirror (subsamples its inputs by 0.1 with the golden seeds: a 359 x 301 point registration)
+    r4 = subprocess.run([os.path.join(pkg_dir, "example_mirror"), str(tmp_path / "model.txt"), str(tmp_path / "data.txt"), "5e-3"], capture_output=True, text=True, timeout=300)
+    assert r4.returncode == 0 and r4.stdout.startswith("optError "), r4.stderr
