@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the certified / reference-DT / gather side measurements")
+    ap.add_argument("--numerics", type=int, default=0, help="goicp_numerics flags of the engine (0 = strict, the library default; 3 = tree sums + parallel ICP moments)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -246,7 +247,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": args.workload, "model": wl.get("model", "synthetic closed surface, seed 1"), "data": wl.get("data", "noisy subset under a random SE(3), seeds 2/3"),
               "Nd": None, "Nm": None, "dt_size": wl["S"], "mse_threshold": wl["mse"], "trim": 0.0,
-              "dt_mode": "exact EDT + reference corner seed (library default)", "numerics": "strict (reference-order sums, reference ICP arithmetic)",
+              "dt_mode": "exact EDT + reference corner seed (library default)",
+              "numerics": "strict (reference-order sums, reference ICP arithmetic)" if args.numerics == 0 else f"goicp_numerics flags {args.numerics} (tolerance mode: see profiles/r2_parity_modes.md)",
               "l2": "flushed between timed steps (256 MiB write)"}
 
     # ------------------------------------------------------------------ reference arm ---------
@@ -323,6 +325,7 @@ def main():
         g = pkg.GoICP(wl["mse"] if mse is None else mse, device=local_rank)
         g.pModel, g.pData = model, data
         g.dt.SIZE = wl["S"]
+        g.numerics = args.numerics
         if dt_mode is not None:
             g.dt_mode = dt_mode
         if world > 1 and os.environ.get("GOICP_EXCHANGE", "nccl") == "nccl":

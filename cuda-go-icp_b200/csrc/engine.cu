@@ -177,7 +177,7 @@ struct goicp_handle {
     DevBuf<CandList> d_cands; DevBuf<unsigned> d_trim_keys; DevBuf<unsigned long long> d_dbg; DevBuf<float> d_strict;   // d_strict: [0..127] strict sums, [128..135] pick result, then optional scratch
     int64_t strict_resolves = 0, cand_overflows = 0, bnb_variants = 0;
     DevBuf<PairTask> d_pairs; DevBuf<float> d_f32a, d_f32b, d_score_scratch; DevBuf<int32_t> d_i32; DevBuf<float> d_q;
-    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage, d_icp_partials; DevBuf<int32_t> d_icp_nn, d_icp_pos, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
+    DevBuf<IcpState> d_icp_state; DevBuf<float> d_icp_q, d_icp_d2, d_icp_stage, d_icp_partials; DevBuf<double> d_icp_xch; DevBuf<int32_t> d_icp_nn, d_icp_pos, d_icp_order; DevBuf<unsigned long long> d_icp_keys, d_icp_keys2; DevBuf<unsigned> d_icp_hist; int icp_blocks = 0;
     InnerResult* h_results = nullptr; size_t h_results_n = 0;       // pinned
     InnerTask* h_tasks = nullptr; size_t h_tasks_n = 0;             // pinned
 
@@ -697,6 +697,43 @@ int run_icp(goicp_handle* h, const float* R0, const float* t0, int max_iter, flo
     int blocks = std::max(1, std::min(std::min(std::min(max_blocks, icp_max_blocks_supported()), (h->nd + 15) / 16), blocks_cap));
     if (const char* e = getenv("GOICP_ICP_BLOCKS")) blocks = std::max(1, std::min(std::min(max_blocks, icp_max_blocks_supported()), std::min(atoi(e), blocks_cap)));   // experiments
     if (fast) CUDA_TRY(h, h->d_icp_partials.reserve((size_t)2 * 16 * blocks));
+    // Multi-GPU, tolerance numerics, large cloud: the nearest-neighbour search -- all that is left of an iteration once the
+    // sums are parallel -- is dealt over the ranks by query range.  Per iteration every rank reduces its queries to 16
+    // moments, the W x 128 bytes are all-gathered (NCCL on the engine stream, or the host hook) and every rank solves for
+    // the same new pose; the host loop reads the convergence flag back each iteration (~50 us, against milliseconds of
+    // search per iteration at these sizes).  Strict ICP is not sharded: its sorted sequential sums need every row on one GPU.
+    const int W = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
+    static const int shard_min = getenv("GOICP_ICP_SHARD_MIN") ? atoi(getenv("GOICP_ICP_SHARD_MIN")) : 20000;
+    if (fast && W > 1 && h->nd >= shard_min && !(h->p.do_trim && num < h->nd)) {
+        const int per = (h->nd + W - 1) / W, q0 = std::min(h->p.rank * per, h->nd), q1 = std::min(q0 + per, h->nd);
+        CUDA_TRY(h, h->d_icp_xch.reserve((size_t)16 * W));
+        std::vector<double> hx((size_t)16 * W);
+        int it = 0;
+        for (; it < max_iter; it++) {
+            CUDA_TRY(h, launch_icp_fast_shard(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, num, blocks, h->max_smem_optin, h->d_icp_partials.p, q0, q1,
+                                              h->d_icp_xch.p + (size_t)16 * h->p.rank, h->stream));
+            if (h->nccl) {
+                const int nrc = nccl_api()->AllGather(h->d_icp_xch.p + (size_t)16 * h->p.rank, h->d_icp_xch.p, 16 * sizeof(double), kNcclUint8, h->nccl, h->stream);
+                if (nrc != 0) return fail(h, GOICP_ERR_CUDA, "ncclAllGather (ICP moments) failed");
+            } else {
+                CUDA_TRY(h, xfer(h, hx.data() + (size_t)16 * h->p.rank, h->d_icp_xch.p + (size_t)16 * h->p.rank, 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+                std::vector<double> mine(hx.begin() + 16 * h->p.rank, hx.begin() + 16 * (h->p.rank + 1));
+                if (h->xchg(h->xchg_user, mine.data(), hx.data(), 16 * sizeof(double), 0) != 0) return fail(h, GOICP_ERR_INVALID, "exchange callback failed");
+                CUDA_TRY(h, xfer(h, h->d_icp_xch.p, hx.data(), sizeof(double) * 16 * W, cudaMemcpyHostToDevice, h->stream));
+            }
+            CUDA_TRY(h, launch_icp_fast_solve(h->d_icp_state.p, h->d_icp_xch.p, W, h->nd, num, err_diff, it, max_iter, h->stream));
+            h->launches += 2;
+            CUDA_TRY(h, xfer(h, &st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if (st.converged) break;
+        }
+        h->t_icp += now_s() - t_begin;
+        for (int i = 0; i < 9; i++) out->R[i] = st.R[i];
+        for (int i = 0; i < 3; i++) out->t[i] = st.t[i];
+        out->err = st.err_new; out->iterations = st.iter;
+        return GOICP_OK;
+    }
     CUDA_TRY(h, launch_icp(kd_view(h), n_nodes, h->d_data.p, h->nd, h->d_icp_state.p, wk, max_iter, err_diff, num, (h->p.do_trim ? 1 : 0) | ((h->p.numerics & GOICP_NUM_JACOBI_SVD) ? 2 : 0), blocks, h->max_smem_optin, fast, h->d_icp_partials.p, h->stream));
     h->launches++;
     CUDA_TRY(h, xfer(h, &st, h->d_icp_state.p, sizeof st, cudaMemcpyDeviceToHost, h->stream));
@@ -912,7 +949,7 @@ int goicp_destroy(goicp_handle* h)
         h->d_gather.release(); h->d_share.release();
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release(); h->d_grid_start.release(); h->d_grid_pts.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_trim_keys.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
-        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release(); h->d_icp_partials.release();
+        h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release(); h->d_icp_partials.release(); h->d_icp_xch.release();
         if (h->h_results) pool_free_host(h->h_results);
         if (h->h_tasks) pool_free_host(h->h_tasks);
         if (h->stream && h->stream_dt && h->ev0 && h->ev1) {       // kept for the next handle on this device (ensure_cuda)

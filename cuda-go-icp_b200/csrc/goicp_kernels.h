@@ -71,6 +71,11 @@ cudaError_t launch_nn(const KdView& kd, const float* d_q, int n, int32_t* d_idx,
 // (parallel moments + Jacobi Procrustes, d_partials: 2 * grid_blocks * 16 floats).
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int do_sort, int grid_blocks, int smem_optin, bool fast, float* d_partials, cudaStream_t s);
+// Sharded fast ICP (one iteration per call): NN + moments of the queries [q_begin, q_end) -> 16 doubles in d_xch_out; after the
+// ranks' blocks have been all-gathered, icp_fast_solve forms the new pose from the W x 16 moments (same result on every rank).
+cudaError_t launch_icp_fast_shard(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
+                                  int num_inliers, int grid_blocks, int smem_optin, float* d_partials, int q_begin, int q_end, double* d_xch_out, cudaStream_t s);
+cudaError_t launch_icp_fast_solve(IcpState* d_state, const double* d_xch_all, int W, int nd, int num, float err_diff, int iter, int max_iter, cudaStream_t s);
 int icp_threads();
 int icp_max_blocks_supported();   // CTAs the in-kernel radix sort's scan supports
 int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int num, int smem_optin, bool fast);

@@ -771,18 +771,18 @@ __device__ __forceinline__ void block_nn_scan(const float4* __restrict__ pts, in
     }
     D1 = d1; D2 = d2;
 }
-// The NN phase of one ICP iteration for the queries of this CTA (i = k * gridDim.x + blockIdx.x).
+// The NN phase of one ICP iteration for the queries of this CTA (i = q_begin + k * gridDim.x + blockIdx.x < q_end).
 // emit(i, model index, model xyz, d^2, query xyz) is called by exactly one thread per query: lane 0 of warp k mod 16 when the
 // grid settles it, else thread k mod 512 -- a fixed assignment, so whatever emit accumulates is reproducible from run to run.
 // d2_hint: the queries' squared nearest distances of the previous iteration (any content is safe; sm.qhint caches the first
 // ones on chip, as sm.qpts caches their data points).  park: >= ceil(nd / gridDim.x) 64-bit words of scratch owned by this
 // CTA: 0 = settled by the grid, else bit 63 | d^2 bits << 32 | near-tie << 31 | position of the winner in the scanned array.
 template <typename Emit>
-__device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSmem& sm, int qcache_n, const float4* __restrict__ data, int nd, const float (&R)[9], const float (&t)[3],
+__device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSmem& sm, int qcache_n, const float4* __restrict__ data, int q_begin, int q_end, const float (&R)[9], const float (&t)[3],
                                                    float* d2_hint, unsigned long long* park, float* merge /* [2][3][16] */, Emit emit)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nq = nd > (int)blockIdx.x ? (nd - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nq = q_end - q_begin > (int)blockIdx.x ? (q_end - q_begin - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf; const unsigned short* gstart = sm.gstart; const float4* gpts = sm.gpts;
     const float4* scan = gpts ? gpts : leaf;                 // either way: x, y, z, original index
     auto query = [&](int k, int i, float& qx, float& qy, float& qz) {
@@ -808,7 +808,7 @@ __device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSm
     __syncthreads();
     if (gstart) {
         for (int k = warp; k < nq; k += kIcpThreads / 32) {
-            const int i = k * gridDim.x + blockIdx.x;
+            const int i = q_begin + k * gridDim.x + blockIdx.x;
             float qx, qy, qz;
             query(k, i, qx, qy, qz);
             // radius of the block of cells from last iteration's distance: the block's edge is >= r cells away
@@ -833,7 +833,7 @@ __device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSm
     int par = 0;
     for (int k = 0; k < nq; k++) {
         if (gstart && park[k] == 0ull) continue;              // block-uniform
-        const int i = k * gridDim.x + blockIdx.x;
+        const int i = q_begin + k * gridDim.x + blockIdx.x;
         float qx, qy, qz;
         query(k, i, qx, qy, qz);
         float D1, D2; int P1;
@@ -846,7 +846,7 @@ __device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSm
     for (int k = threadIdx.x; k < nq; k += kIcpThreads) {
         const unsigned long long w = park[k];
         if (!(w >> 63)) continue;
-        const int i = k * gridDim.x + blockIdx.x;
+        const int i = q_begin + k * gridDim.x + blockIdx.x;
         float qx, qy, qz;
         query(k, i, qx, qy, qz);
         finish(k, i, (int)(w & 0x7fffffffu), (w & 0x80000000ull) != 0, __uint_as_float((unsigned)(w >> 32) & 0x7fffffffu), qx, qy, qz);
@@ -862,7 +862,7 @@ __host__ __device__ inline size_t icp_plan_bytes(const IcpSmemPlan& p)
     return (size_t)p.grid_bytes + p.tree_bytes + p.stage_bytes + p.radix_bytes + p.queue_bytes + (((size_t)p.qcache_n * kQCacheEntry + 15) & ~(size_t)15);
 }
 // carve the dynamic shared memory [NN grid][kd-tree][sort keys][radix][search rings][query cache] and fill the read-only parts
-__device__ __forceinline__ IcpSmem icp_carve(const KdView& kd, const IcpSmemPlan& plan, unsigned char* sp, const float4* __restrict__ data, int nd)
+__device__ __forceinline__ IcpSmem icp_carve(const KdView& kd, const IcpSmemPlan& plan, unsigned char* sp, const float4* __restrict__ data, int q_begin, int q_end)
 {
     IcpSmem m;
     m.nodes = kd.nodes; m.leaf = kd.pts_leaf; m.gstart = kd.grid_start; m.gpts = kd.grid_pts;
@@ -885,12 +885,12 @@ __device__ __forceinline__ IcpSmem icp_carve(const KdView& kd, const IcpSmemPlan
     m.squeue = plan.queue_bytes ? reinterpret_cast<int*>(sp) : nullptr; sp += plan.queue_bytes;
     m.qpts = nullptr; m.qhint = nullptr;
     if (plan.qcache_n) {
-        // the queries of this CTA never change (i = k * gridDim.x + blockIdx.x): keep the first qcache_n data points on chip,
+        // the queries of this CTA never change (i = q_begin + k * gridDim.x + blockIdx.x): keep the first qcache_n data points on chip,
         // next to their nearest distance of the previous iteration (the grid search's radius hint; -1 = none yet)
         m.qpts = reinterpret_cast<float4*>(sp); m.qhint = reinterpret_cast<float*>(sp + (size_t)plan.qcache_n * sizeof(float4));
         for (int k = threadIdx.x; k < plan.qcache_n; k += blockDim.x) {
-            const long long i = (long long)k * gridDim.x + blockIdx.x;
-            m.qpts[k] = i < nd ? __ldg(data + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const long long i = (long long)q_begin + (long long)k * gridDim.x + blockIdx.x;
+            m.qpts[k] = i < q_end ? __ldg(data + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             m.qhint[k] = -1.0f;
         }
     }
@@ -1046,7 +1046,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     const volatile IcpState* vst = st;
 
     // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [staged rows]
-    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, nd);
+    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, 0, nd);
     const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf;
     float* sstage = sm.sstage; unsigned* sradix = sm.sradix; int* squeue = sm.squeue;
 
@@ -1061,7 +1061,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
         // ---- phase A: transform + nearest neighbour; queries interleaved over the CTAs ----------
         if (plan.brute_force) {
             unsigned long long* park = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);      // wk.keys2 is idle until the sort
-            icp_nn_small_model(kd, sm, plan.qcache_n, data, nd, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
+            icp_nn_small_model(kd, sm, plan.qcache_n, data, 0, nd, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
                 wk.nn[i] = I1;
                 wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
                 // correspondence row (model point, query, d^2) in query order
@@ -1349,9 +1349,56 @@ __device__ void procrustes_jacobi(const double* H /* 3x3 row-major: rows = data,
 
 struct IcpFastShared { float R[9], t[3], mu_m[3], mu_d[3]; float err, err_new; int iter, converged; };
 
+// New pose from the 16 moments of one iteration (see icp_fast_kernel); thread-serial, identical on every CTA / rank.
+__device__ void icp_fast_solve(IcpFastShared& cur, const double* tot, int nd, int num, float err_diff, int iter)
+{
+    const float err_new = (float)tot[6];
+    cur.err_new = err_new; cur.iter = iter;
+    // jly_icp3d.hpp:257; err_diff < 0 selects fgoicp's relative rule instead (icp3d.cu:96: stop when the improvement is
+    // at most |err_diff| of the previous error)
+    if (cur.err > 0.0f && (err_diff >= 0.0f ? cur.err - err_new < err_diff * (float)num : cur.err - err_new <= -err_diff * cur.err)) { cur.converged = 1; return; }
+    cur.err = err_new;
+    // means on top of the previous means, divided by n (the reference never resets them, :205-206, :244-263)
+    double mm[3], md[3];
+    for (int c = 0; c < 3; c++) { mm[c] = ((double)cur.mu_m[c] + tot[c]) / (double)nd; md[c] = ((double)cur.mu_d[c] + tot[3 + c]) / (double)nd; }
+    // H = sum (q - md)(m - mm)^T from the moments about (c_d, c_m) = the previous means
+    double H[9];
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
+        const double dd = md[a] - (double)cur.mu_d[a], dm = mm[b] - (double)cur.mu_m[b];
+        const double Sq = tot[3 + a] - (double)num * (double)cur.mu_d[a], Sm = tot[b] - (double)num * (double)cur.mu_m[b];
+        H[3 * a + b] = tot[7 + 3 * a + b] - dd * Sm - Sq * dm + (double)num * dd * dm;
+    }
+    float Rn[9];
+    procrustes_jacobi(H, Rn);
+    float tn[3], tt[3], tmp[9];
+    for (int a = 0; a < 3; a++) tn[a] = (float)(mm[a] - ((double)Rn[3 * a] * md[0] + (double)Rn[3 * a + 1] * md[1] + (double)Rn[3 * a + 2] * md[2]));   // t_ = mu_m - R_ mu_d
+    mat3_mul(Rn, cur.R, tmp);                                                                   // R = R_ R
+    for (int a = 0; a < 3; a++) tt[a] = Rn[3 * a] * cur.t[0] + Rn[3 * a + 1] * cur.t[1] + Rn[3 * a + 2] * cur.t[2] + tn[a];   // t = R_ t + t_
+    for (int i = 0; i < 9; i++) cur.R[i] = tmp[i];
+    for (int i = 0; i < 3; i++) { cur.t[i] = tt[i]; cur.mu_m[i] = (float)mm[i]; cur.mu_d[i] = (float)md[i]; }
+}
+// Sharded ICP (the queries of an iteration dealt over W GPUs): every rank runs this on the all-gathered W x 16 moments, added
+// in rank order -- the same arithmetic on the same numbers everywhere, so the ranks' poses stay bit-identical.
+__global__ void icp_fast_solve_kernel(IcpState* st, const double* __restrict__ xch_all, int W, int nd, int num, float err_diff, int iter, int max_iter)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    IcpFastShared cur;
+    for (int i = 0; i < 9; i++) cur.R[i] = st->R[i];
+    for (int i = 0; i < 3; i++) { cur.t[i] = st->t[i]; cur.mu_m[i] = st->mu_m[i]; cur.mu_d[i] = st->mu_d[i]; }
+    cur.err = st->err; cur.err_new = st->err_new; cur.iter = st->iter; cur.converged = 0;
+    double tot[16];
+    for (int v = 0; v < 16; v++) { double a = 0.0; for (int r = 0; r < W; r++) a += xch_all[(size_t)r * 16 + v]; tot[v] = a; }
+    icp_fast_solve(cur, tot, nd, num, err_diff, iter);
+    if (!cur.converged && iter == max_iter - 1) cur.iter = max_iter;
+    for (int i = 0; i < 9; i++) st->R[i] = cur.R[i];
+    for (int i = 0; i < 3; i++) { st->t[i] = cur.t[i]; st->mu_m[i] = cur.mu_m[i]; st->mu_d[i] = cur.mu_d[i]; }
+    st->err = cur.err; st->err_new = cur.err_new; st->iter = cur.iter; st->converged = cur.converged;
+}
+
 __global__ void __launch_bounds__(kIcpThreads)
 icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, IcpWork wk,
-                int max_iter, float err_diff, int num, int do_sort, IcpSmemPlan plan, float* __restrict__ partials /* 2 x gridDim.x x 16 */)
+                int max_iter, float err_diff, int num, int do_sort, IcpSmemPlan plan, float* __restrict__ partials /* 2 x gridDim.x x 16 */,
+                int q_begin, int q_end, double* __restrict__ xch_out /* shard mode: one NN pass over [q_begin, q_end), its 16 moments go here */)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char icp_smem[];
@@ -1364,7 +1411,7 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
     constexpr int kWarps = kIcpThreads / 32;
     const bool sorting = do_sort && num < nd;          // an untrimmed sum does not depend on the order
 
-    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, nd);
+    const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, q_begin, q_end);
     const KdNode* nodes = sm.nodes; const float4* leaf = sm.leaf;
     float* sstage = sm.sstage; unsigned* sradix = sm.sradix; int* squeue = sm.squeue;
     if (threadIdx.x == 0) {
@@ -1394,7 +1441,7 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
         // ---- phase A: transform + exact nearest neighbour (same searches as icp_kernel) ------------------------
         if (plan.brute_force) {
             unsigned long long* park = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
-            icp_nn_small_model(kd, sm, plan.qcache_n, data, nd, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
+            icp_nn_small_model(kd, sm, plan.qcache_n, data, q_begin, q_end, R, t, wk.d2, park, nn_merge_sm, [&](int i, int I1, float mx, float my, float mz, float D1, float qx, float qy, float qz) {
                 wk.nn[i] = I1;
                 if (sorting) {
                     wk.keys[i] = ((unsigned long long)__float_as_uint(D1) << 32) | (unsigned)i;
@@ -1419,10 +1466,10 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
             };
             unsigned long long* unsettled = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);
             for (int pass = 0; pass < 2; pass++) {
-                const int count = pass == 0 ? nd : n_unsettled;
+                const int count = pass == 0 ? q_end - q_begin : n_unsettled;
                 for (int g = pass == 0 ? threadIdx.x * gridDim.x + blockIdx.x : threadIdx.x; g < count; g += (pass == 0 ? gridDim.x : 1) * blockDim.x) {
                     const unsigned long long rec = pass == 0 ? 0ull : unsettled[g];
-                    const int i = pass == 0 ? g : (int)(unsigned)rec;
+                    const int i = pass == 0 ? q_begin + g : (int)(unsigned)rec;
                     if (pass == 0 && plan.nn_budget == 1) { deferred[atomicAdd(&n_deferred, 1)] = i; continue; }
                     const float4 p = __ldg(data + i);
                     const float qx = __fadd_rn(dot3_ref(R[0], R[1], R[2], p.x, p.y, p.z), t[0]);
@@ -1506,6 +1553,7 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
             __stcg(mine + threadIdx.x, sacc);
         }
         grid.sync();
+        if (xch_out && blockIdx.x != 0) return;                 // shard mode: CTA 0 adds this GPU's partials up and hands them to the exchange
         {
             // warp w sums value w over the CTAs: lane-strided doubles, then a fixed shuffle tree
             const float* all = partials + (size_t)(iter & 1) * gridDim.x * 16;
@@ -1514,36 +1562,10 @@ icp_fast_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
             if (lane == 0) tot[warp] = sacc;
+            if (xch_out) { if (lane == 0) xch_out[warp] = sacc; return; }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const float err_new = (float)tot[6];
-            cur.err_new = err_new; cur.iter = iter;
-            // jly_icp3d.hpp:257; err_diff < 0 selects fgoicp's relative rule instead (icp3d.cu:96: stop when the improvement is
-            // at most |err_diff| of the previous error)
-            if (cur.err > 0.0f && (err_diff >= 0.0f ? cur.err - err_new < err_diff * (float)num : cur.err - err_new <= -err_diff * cur.err)) cur.converged = 1;
-            else {
-                cur.err = err_new;
-                // means on top of the previous means, divided by n (the reference never resets them, :205-206, :244-263)
-                double mm[3], md[3];
-                for (int c = 0; c < 3; c++) { mm[c] = ((double)cur.mu_m[c] + tot[c]) / (double)nd; md[c] = ((double)cur.mu_d[c] + tot[3 + c]) / (double)nd; }
-                // H = sum (q - md)(m - mm)^T from the moments about (c_d, c_m) = the previous means
-                double H[9];
-                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) {
-                    const double dd = md[a] - (double)cur.mu_d[a], dm = mm[b] - (double)cur.mu_m[b];
-                    const double Sq = tot[3 + a] - (double)num * (double)cur.mu_d[a], Sm = tot[b] - (double)num * (double)cur.mu_m[b];
-                    H[3 * a + b] = tot[7 + 3 * a + b] - dd * Sm - Sq * dm + (double)num * dd * dm;
-                }
-                float Rn[9];
-                procrustes_jacobi(H, Rn);
-                float tn[3], tt[3], tmp[9];
-                for (int a = 0; a < 3; a++) tn[a] = (float)(mm[a] - ((double)Rn[3 * a] * md[0] + (double)Rn[3 * a + 1] * md[1] + (double)Rn[3 * a + 2] * md[2]));   // t_ = mu_m - R_ mu_d
-                mat3_mul(Rn, cur.R, tmp);                                                                   // R = R_ R
-                for (int a = 0; a < 3; a++) tt[a] = Rn[3 * a] * cur.t[0] + Rn[3 * a + 1] * cur.t[1] + Rn[3 * a + 2] * cur.t[2] + tn[a];   // t = R_ t + t_
-                for (int i = 0; i < 9; i++) cur.R[i] = tmp[i];
-                for (int i = 0; i < 3; i++) { cur.t[i] = tt[i]; cur.mu_m[i] = (float)mm[i]; cur.mu_d[i] = (float)md[i]; }
-            }
-        }
+        if (threadIdx.x == 0) icp_fast_solve(cur, tot, nd, num, err_diff, iter);
         __syncthreads();
         if (cur.converged) break;
         if (iter == max_iter - 1 && threadIdx.x == 0) cur.iter = max_iter;
@@ -1631,6 +1653,27 @@ int icp_max_grid_blocks(int device, const KdView& kd, int n_nodes, int nd, int n
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     return per_sm * sms;
 }
+// one iteration's NN pass of the fast ICP over the queries [q_begin, q_end) (this rank's share); the 16 moments land in d_xch_out
+cudaError_t launch_icp_fast_shard(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
+                                  int num_inliers, int grid_blocks, int smem_optin, float* d_partials, int q_begin, int q_end, double* d_xch_out, cudaStream_t s)
+{
+    const void* kern = (const void*)icp_fast_kernel;
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kern);
+    if (e != cudaSuccess) return e;
+    const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
+    IcpSmemPlan plan = icp_plan(kd, n_nodes, nd, num_inliers, limit);
+    KdView kdv = kd; IcpWork wk = work;
+    int max_iter = 1, do_sort = 0; float err_diff = 0.0f;
+    void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk, (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&do_sort,
+                    (void*)&plan, (void*)&d_partials, (void*)&q_begin, (void*)&q_end, (void*)&d_xch_out};
+    return cudaLaunchCooperativeKernel(kern, dim3(grid_blocks), dim3(kIcpThreads), args, icp_plan_bytes(plan), s);
+}
+cudaError_t launch_icp_fast_solve(IcpState* d_state, const double* d_xch_all, int W, int nd, int num, float err_diff, int iter, int max_iter, cudaStream_t s)
+{
+    icp_fast_solve_kernel<<<1, 32, 0, s>>>(d_state, d_xch_all, W, nd, num, err_diff, iter, max_iter);
+    return cudaGetLastError();
+}
 cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int nd, IcpState* d_state, const IcpWork& work,
                        int max_iter, float err_diff, int num_inliers, int do_sort, int grid_blocks, int smem_optin, bool fast, float* d_partials, cudaStream_t s)
 {
@@ -1641,8 +1684,9 @@ cudaError_t launch_icp(const KdView& kd, int n_nodes, const float4* d_data, int 
     const int limit = smem_optin - (int)a.sharedSizeBytes - 1024;
     IcpSmemPlan plan = icp_plan(kd, n_nodes, nd, num_inliers, limit);
     KdView kdv = kd; IcpWork wk = work;
+    int q_begin = 0, q_end = nd; double* d_xch = nullptr;               // (the last three only exist in icp_fast_kernel's signature)
     void* args[] = {(void*)&kdv, (void*)&d_data, (void*)&nd, (void*)&d_state, (void*)&wk,
-                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&do_sort, (void*)&plan, (void*)&d_partials};
+                    (void*)&max_iter, (void*)&err_diff, (void*)&num_inliers, (void*)&do_sort, (void*)&plan, (void*)&d_partials, (void*)&q_begin, (void*)&q_end, (void*)&d_xch};
     return cudaLaunchCooperativeKernel(kern, dim3(grid_blocks), dim3(kIcpThreads), args,
                                        icp_plan_bytes(plan), s);
 }

@@ -219,6 +219,13 @@ def test_two_rank_nccl_registration_vs_golden(pkg, runs):
     import json
     res = json.load(open(out))
     os.remove(out)
+    shard = res.pop("_icp_shard"); gt = res.pop("_icp_shard_gt")
+    # sharded ICP: both ranks end with the same pose bit for bit, and it is the single-GPU pose up to summation order
+    assert shard[0]["sharded"] == shard[1]["sharded"]
+    a, b = shard[0]["sharded"], shard[0]["single"]
+    assert abs(a["iterations"] - b["iterations"]) <= 2 and a["err"] == pytest.approx(b["err"], rel=2e-3)
+    assert rot_angle(np.array(a["R"]).reshape(3, 3), np.array(b["R"]).reshape(3, 3)) < 2e-4 and np.abs(np.array(a["t"]) - np.array(b["t"])).max() < 2e-4
+    assert rot_angle(np.array(a["R"]).reshape(3, 3), np.array(gt["R"]).reshape(3, 3)) < 5e-3
     for name, per_rank in res.items():
         gold = runs[name]
         for r in per_rank:
@@ -333,3 +340,35 @@ def test_cli_and_cpp_mirror_binaries(pkg, runs, bunny, tmp_path):
     # the C++ mirror (subsamples its inputs by 0.1 with the golden seeds: a 359 x 301 point registration)
     r4 = subprocess.run([os.path.join(pkg_dir, "example_mirror"), str(tmp_path / "model.txt"), str(tmp_path / "data.txt"), "5e-3"], capture_output=True, text=True, timeout=300)
     assert r4.returncode == 0 and r4.stdout.startswith("optError "), r4.stderr
+
+
+@pytest.mark.parametrize("nm,nd,S,mse,seed_pose", [(50000, 2000, 100, 3e-4, 3), (30000, 1500, 80, 3e-4, 11)])
+def test_synthetic_sweep_cases_vs_oracle(pkg, restated, nm, nd, S, mse, seed_pose):
+    """BASELINE config 5 (synthetic closed surface, noisy subset under a random SE(3)) at sizes the oracle finishes in
+    seconds: whole registrations -- model beyond the linear-scan range (tree NN path), BnB with several ICP refinements --
+    against the oracle on the same clouds, in the reference-order DT mode (grid bit-exact) and in the default mode; and the
+    recovered pose is the ground-truth motion the data was generated with."""
+    sys.path.insert(0, ROOT)
+    from bench import synth
+    model, data, R_gt, t_gt = synth(nm, nd, seed_pose=seed_pose)
+    o = restated.create(model, data, mse, 0.0, S)
+    restated.L.go_build_dt(o)
+    ref = restated.register(o)
+    for dt_mode in (DT_REFERENCE, None):
+        g = pkg.GoICP(mse)
+        g.pModel, g.pData = model, data
+        g.dt.SIZE = S
+        if dt_mode is not None:
+            g.dt_mode = dt_mode
+        g.BuildDT()
+        if dt_mode == DT_REFERENCE:
+            assert np.array_equal(restated.dt_grid(restated.L.go_get_dt(o), S), g.GetDT()[0])
+        g.Register()
+        r = g.result
+        g.close()
+        assert r["exit_path"] == ref["exit_path"] and r["icp_calls"] == ref["icp_calls"]
+        assert r["sse"] == pytest.approx(ref["sse"], rel=1e-5, abs=1e-7)
+        assert rot_angle(r["R"], ref["R"]) < 1e-4 and np.abs(r["t"] - ref["t"]).max() < 1e-4
+        assert _close_counts(r["rot_pops"], ref["rot_pops"]) and _close_counts(r["trans_pops"], ref["trans_pops"])
+    if ref["exit_path"] != "certified" or ref["rot_pops"] > 1:
+        assert rot_angle(ref["R"], R_gt) < 5e-3 and np.abs(ref["t"] - t_gt).max() < 5e-3
