@@ -803,7 +803,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         adopt(root);
         publish(done);
     }
-    long long o_maint = 0, o_waitA = 0, o_waitB = 0, o_book = 0, o_arrive = 0, o_push = 0;
+    long long o_maint = 0, o_waitA = 0, o_waitB = 0, o_book = 0, o_arrive = 0, o_push = 0, o_npush = 0, o_pop = 0;
     for (;;) {
         __syncwarp();
         long long o0 = clock64();
@@ -811,10 +811,13 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         const long long oa = clock64(); o_arrive += oa - o0;
         if (!done) {
             // ---- queue maintenance in the shadow of the gathers --------------------------
+            o_npush += __popc(pmask);
             flush_pending();
-            o_push += clock64() - oa;
+            const long long ob = clock64();
+            o_push += ob - oa;
             if (need_pop && !status) {
                 const HeapEntry e = wheap_pop(heap, lane, pop_path);
+                o_pop += clock64() - ob;
                 if (e.lb != expect.lb || e.level != expect.level || e.path_lo != expect.path_lo || e.path_hi != expect.path_hi) status = 5;   // cannot happen: the prediction was unambiguous
                 need_pop = false;
             }
@@ -826,60 +829,105 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         cluster_arrive_relaxed(); cluster_wait();                             // (B) partial sums are in
         o1 = clock64(); o_waitB += o1 - o0;
         // ---- fixed-order sum over the cluster's CTAs, one lane per value ------------------------
-        if (lane < 16) { float sacc = 0.0f; for (int r = 0; r < C; r++) sacc += partials[r][lane]; tot16[lane] = sacc; }
-        __syncwarp();
-        // ---- sequential bookkeeping of the 8 children (jly_goicp.cpp:317-336) -------------------
-        evals += 8;
-        pmask = 0; pend_level = plevel + 1; pend_base = ppath; pend_shift = 3 * (int)plevel;
+        float sacc = 0.0f;
+        if (lane < 16) { for (int r = 0; r < C; r++) sacc += partials[r][lane]; tot16[lane] = sacc; }   // tot16[8..15]: lbs of the deferred pushes
+        // ---- bookkeeping of the 8 children (jly_goicp.cpp:317-336), one lane per child -----------
+        // The reference walks j = 0..7 with a running optErrorT; lane j needs that running value right after child j's
+        // own update = min(optErrorT, ub_0..ub_j): an 8-wide prefix minimum.  Everything else is a ballot.
+        constexpr unsigned kFull = 0xffffffffu;
+        const int cj = lane & 7;
+        const float ub = __shfl_sync(kFull, sacc, cj), lb = __shfl_sync(kFull, sacc, 8 + cj);
+        float run = ub;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float ub = tot16[j], lb = tot16[8 + j];
-            if (ub < opt_t) {
-                opt_t = ub;
-                best[0] = __fadd_rn(px, (j & 1) ? cw : 0.0f); best[1] = __fadd_rn(py, (j & 2) ? cw : 0.0f);
-                best[2] = __fadd_rn(pz, (j & 4) ? cw : 0.0f); best[3] = cw;
+        for (int d = 1; d < 8; d <<= 1) { const float o = __shfl_up_sync(kFull, run, d, 8); if (cj >= d && o < run) run = o; }
+        if (opt_t < run) run = opt_t;                                                // optErrorT after child cj was looked at
+        evals += 8;
+        {
+            const float fin = __shfl_sync(kFull, run, 7);
+            if (fin < opt_t) {                                                       // taken by the first child that reaches the final value
+                const int jb = __ffs(__ballot_sync(kFull, lane < 8 && ub == fin)) - 1;
+                opt_t = fin;
+                best[0] = __fadd_rn(px, (jb & 1) ? cw : 0.0f); best[1] = __fadd_rn(py, (jb & 2) ? cw : 0.0f);
+                best[2] = __fadd_rn(pz, (jb & 4) ? cw : 0.0f); best[3] = cw;
             }
-            if (ub_pass && ub <= opt_t * (1.0f + cand_eps)) {
-                if (n_cand == kMaxCand) {
-                    int k = 0;
-                    for (int q = 0; q < n_cand; q++)
-                        if (cand_ub[q] <= opt_t * (1.0f + cand_eps)) { if (lane == 0) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; } k++; }
-                    n_cand = k;
-                    __syncwarp();
-                }
-                if (n_cand < kMaxCand) {
-                    if (lane == 0) {
-                        cand_node[n_cand] = make_float4(__fadd_rn(px, (j & 1) ? cw : 0.0f), __fadd_rn(py, (j & 2) ? cw : 0.0f),
-                                                        __fadd_rn(pz, (j & 4) ? cw : 0.0f), cw);
-                        cand_ub[n_cand] = ub;
-                    }
-                    n_cand++;
-                    __syncwarp();
-                } else flags |= 1u;
-            }
-            if (lb >= opt_t) continue;
-            if ((int)plevel + 1 > c.trans_cutoff_level) continue;                  // span cut-off (fgoicp-style search): evaluated, not subdivided
-            pmask |= 1u << j;
         }
+        if (ub_pass) {
+            const float lim = run * (1.0f + cand_eps);
+            const unsigned cm = __ballot_sync(kFull, lane < 8 && ub <= lim);
+            if (n_cand + __popc(cm) <= kMaxCand) {
+                if ((cm >> lane) & 1u) {
+                    const int q = n_cand + __popc(cm & ((1u << lane) - 1u));
+                    cand_node[q] = make_float4(__fadd_rn(px, (lane & 1) ? cw : 0.0f), __fadd_rn(py, (lane & 2) ? cw : 0.0f), __fadd_rn(pz, (lane & 4) ? cw : 0.0f), cw);
+                    cand_ub[q] = ub;
+                }
+                n_cand += __popc(cm);
+                __syncwarp();
+            } else {
+                // the list is (nearly) full: the sequential form, which purges entries the running optimum has left behind
+                for (int j = 0; j < 8; j++) {
+                    const float uj = __shfl_sync(kFull, ub, j), oj = __shfl_sync(kFull, run, j);
+                    if (!(uj <= oj * (1.0f + cand_eps))) continue;
+                    if (n_cand == kMaxCand) {
+                        int k = 0;
+                        for (int q = 0; q < n_cand; q++)
+                            if (cand_ub[q] <= oj * (1.0f + cand_eps)) { if (lane == 0) { cand_node[k] = cand_node[q]; cand_ub[k] = cand_ub[q]; } k++; }
+                        n_cand = k;
+                        __syncwarp();
+                    }
+                    if (n_cand < kMaxCand) {
+                        if (lane == 0) {
+                            cand_node[n_cand] = make_float4(__fadd_rn(px, (j & 1) ? cw : 0.0f), __fadd_rn(py, (j & 2) ? cw : 0.0f), __fadd_rn(pz, (j & 4) ? cw : 0.0f), cw);
+                            cand_ub[n_cand] = uj;
+                        }
+                        n_cand++;
+                        __syncwarp();
+                    } else flags |= 1u;
+                }
+            }
+        }
+        // children that go into the queue (`if (lb >= optErrorT) continue;`, and the span cut-off of the fgoicp-style search)
+        pmask = __ballot_sync(kFull, lane < 8 && !(lb >= run) && (int)plevel + 1 <= c.trans_cutoff_level);
+        pend_level = plevel + 1; pend_base = ppath; pend_shift = 3 * (int)plevel;
+        __syncwarp();                                                                // tot16 is read by the deferred pushes
         // ---- which node will the queue pop next? ------------------------------------------------
         if (status) { done = true; publish(true); }
         else if (heap.n == 0 && pmask == 0) { done = true; publish(true); }          // queue empty (:243-244)
         else {
-            // best candidate among the current top and the pending children; ties on (lb, level) are left to the heap
-            HeapEntry b; bool tie = false; uint32_t m = pmask;
-            if (heap.n > 0) b = heap.get(0); else { b = pend_entry(__ffs(m) - 1); m &= m - 1; }
-            for (; m; m &= m - 1) {
-                const HeapEntry e = pend_entry(__ffs(m) - 1);
-                if (node_less(b, e)) { b = e; tie = false; }                   // e has strictly higher priority
-                else if (!node_less(e, b)) tie = true;                         // same (lb, level)
+            // best candidate among the current top (lane 8) and the pending children (lanes 0..7): smallest lb, then smallest
+            // level; two candidates with the same (lb, level) are left to the heap's own arrangement
+            HeapEntry top; top.lb = 0.0f; top.level = 0; top.path_lo = top.path_hi = 0;
+            if (heap.n > 0) top = heap.get(0);
+            const bool valid = lane < 8 ? ((pmask >> lane) & 1u) != 0 : (lane == 8 && heap.n > 0);
+            const float klb = lane == 8 ? top.lb : lb;
+            const uint32_t klv = lane == 8 ? top.level : pend_level;
+            bool in = valid;
+            {   // lower bounds are sums of squares (>= +0): their bit patterns order like the values
+                const unsigned kb = in ? __float_as_uint(klb) : 0xffffffffu;
+                const unsigned kb_min = __reduce_min_sync(kFull, kb);              // (not inside an `&&`: every lane takes part)
+                in = in && kb == kb_min;
+                const unsigned kl = in ? klv : 0xffffffffu;
+                const unsigned kl_min = __reduce_min_sync(kFull, kl);
+                in = in && kl == kl_min;
             }
-            if (tie) {
+            const unsigned win = __ballot_sync(kFull, in);
+            if (__popc(win) > 1) {
                 flush_pending();                                               // the heap's own arrangement decides
                 if (status) { done = true; publish(true); }
                 else { const HeapEntry e = wheap_pop(heap, lane, pop_path); adopt(e); publish(done); }
             } else {
-                expect = b; need_pop = true;
-                adopt(b);
+                const int wl = __ffs(win) - 1;
+                if (wl == 8) { expect = top; need_pop = true; adopt(top); }
+                else {
+                    // a child of the cube just expanded: its corner is one more step of the reference's additions (:267-269)
+                    expect = pend_entry(wl); need_pop = true;
+                    pops++;                                                               // tNodeCount++ (:248)
+                    if (__fsub_rn(opt_t, expect.lb) < c.sse_thresh) done = true;         // :257
+                    else if (expect.level >= (uint32_t)kMaxTransLevel) { done = true; status = 4; }
+                    else {
+                        px = __fadd_rn(px, (wl & 1) ? cw : 0.0f); py = __fadd_rn(py, (wl & 2) ? cw : 0.0f); pz = __fadd_rn(pz, (wl & 4) ? cw : 0.0f);
+                        cw = cw / 2; plevel = expect.level; ppath = ((unsigned long long)expect.path_hi << 32) | expect.path_lo;
+                    }
+                }
                 publish(done);
             }
         }
@@ -887,7 +935,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     }
     if (c.dbg && lane == 0) {
         unsigned long long* d = c.dbg + (size_t)task_id * 12;
-        d[0] = o_maint; d[1] = o_waitA; d[2] = o_waitB; d[3] = o_book; d[8] = o_arrive; d[9] = o_push;
+        d[0] = o_maint; d[1] = o_waitA; d[2] = o_waitB; d[3] = o_book; d[8] = o_arrive; d[9] = o_push; d[10] = o_npush; d[11] = o_pop;
     }
 
     // ---- results (see inner_bnb_kernel) ---------------------------------------------------------

@@ -561,8 +561,8 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             unsigned long long d[12];
             cudaMemcpy(d, h->d_dbg.p + (size_t)12 * arg, sizeof d, cudaMemcpyDeviceToHost);
             const double steps = std::max(1u, h->h_results[arg].evals / 8);
-            fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f (arrive %.0f, pushes %.0f) waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
-                    plan.cluster, d[0] / steps, d[8] / steps, d[9] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
+            fprintf(stderr, "        slowest task, cycles per expansion (cluster %d): owner maint %.0f (arrive %.0f, pushes %.0f = %.1f entries, pop %.0f) waitA %.0f waitB %.0f bookkeeping %.0f | gather warp waitA %.0f gather %.0f reduce %.0f waitB %.0f\n",
+                    plan.cluster, d[0] / steps, d[8] / steps, d[9] / steps, d[10] / steps, d[11] / steps, d[1] / steps, d[2] / steps, d[3] / steps, d[4] / steps, d[5] / steps, d[6] / steps, d[7] / steps);
         }
     }
     {
