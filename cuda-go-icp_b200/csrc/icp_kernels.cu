@@ -7,6 +7,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstddef>
 #include "goicp_kernels.h"
 
 namespace cg = cooperative_groups;
@@ -619,7 +620,7 @@ __device__ void procrustes_jacobi(const double* H, float* Rn);
 // Procrustes step + SE(3) composition (jly_icp3d.hpp:268-291) from H = q_d^T q_m and the means.
 // jacobi: GOICP_NUM_JACOBI_SVD -- the rotation from the engine's own solver instead of the reference's svdcmp (experiments:
 // with the reference-order sums kept, does the trajectory survive a solver that is merely accurate?  scripts/parity_modes.py)
-__device__ void icp_update(IcpState* st, const float* H, bool jacobi)
+__device__ void icp_update(IcpState* st, const float* H, bool jacobi, const float* Rc /* current R */, const float* tc /* current t */, const float* mu /* mu_m, mu_d */)
 {
     float U[9], W[3], V[9], Ut[9], Rn[9], VT[9], tmp[9];
     if (jacobi) {
@@ -641,13 +642,13 @@ __device__ void icp_update(IcpState* st, const float* H, bool jacobi)
     float tn[3], tt[3];
     for (int a = 0; a < 3; a++) {                                            // t_ = ~mu_m - R_ * ~mu_d
         float acc = 0.0f;
-        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->mu_d[k];
-        tn[a] = st->mu_m[a] - acc;
+        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * mu[3 + k];
+        tn[a] = mu[a] - acc;
     }
-    mat3_mul(Rn, st->R, tmp);                                                // R = R_ * R
+    mat3_mul(Rn, Rc, tmp);                                                   // R = R_ * R
     for (int a = 0; a < 3; a++) {                                            // t = R_ * t + t_
         float acc = 0.0f;
-        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * st->t[k];
+        for (int k = 0; k < 3; k++) acc += Rn[3 * a + k] * tc[k];
         tt[a] = acc + tn[a];
     }
     for (int i = 0; i < 9; i++) st->R[i] = tmp[i];
@@ -699,7 +700,9 @@ __device__ __forceinline__ void nn_merge(float& d1, int& i1, float& d2, int o)
 // One query per warp, one x-run of cells per lane (two or more beyond r = 2); the points of a run are fetched four at a
 // time so that their loads and distance arithmetic overlap -- a one-by-one loop is a chain of ~130 dependent cycles per
 // point.  r < 0: skip (the caller already knows the block would be too large); all 32 lanes must call.
-__device__ __forceinline__ bool grid_nn(const KdView& kd, const unsigned short* gstart, const float4* gpts, float qx, float qy, float qz, int r, int lane,
+// gl = lanes per query: 32 (the whole warp) or 16 (two queries side by side, lanes 0-15 and 16-31 -- a block of 3^3 cells has nine x-runs,
+// so half a warp is enough for the usual radius).
+__device__ __forceinline__ bool grid_nn(const KdView& kd, const unsigned short* gstart, const float4* gpts, float qx, float qy, float qz, int r, int lane, int gl,
                                         float& D1, int& I1, float& D2)
 {
     const float kInfF = 3.402823466e+38f;
@@ -718,7 +721,7 @@ __device__ __forceinline__ bool grid_nn(const KdView& kd, const unsigned short* 
     if (r >= 0) {
         const int x0 = max(c[0] - r, 0), x1 = min(c[0] + r, kd.gdim[0] - 1);
         const int side = 2 * r + 1;
-        for (int run = lane; run < side * side; run += 32) {           // x-runs: the cells (x0..x1, cy, cz) are contiguous
+        for (int run = lane & (gl - 1); run < side * side; run += gl) {  // x-runs: the cells (x0..x1, cy, cz) are contiguous
             const int cy = c[1] + (run % side) - r, cz = c[2] + (run / side) - r;
             if (cy < 0 || cy >= kd.gdim[1] || cz < 0 || cz >= kd.gdim[2]) continue;
             const int base = (cz * kd.gdim[1] + cy) * kd.gdim[0];
@@ -740,8 +743,9 @@ __device__ __forceinline__ bool grid_nn(const KdView& kd, const unsigned short* 
             }
         }
     }
-    nn_merge(d1, i1, d2, 16); nn_merge(d1, i1, d2, 8); nn_merge(d1, i1, d2, 4); nn_merge(d1, i1, d2, 2); nn_merge(d1, i1, d2, 1);
-    D1 = d1; D2 = d2; I1 = __shfl_sync(0xffffffffu, i1, 0);
+    if (gl == 32) nn_merge(d1, i1, d2, 16);
+    nn_merge(d1, i1, d2, 8); nn_merge(d1, i1, d2, 4); nn_merge(d1, i1, d2, 2); nn_merge(d1, i1, d2, 1);
+    D1 = d1; D2 = d2; I1 = __shfl_sync(0xffffffffu, i1, lane & ~(gl - 1));
     const float me = margin - 1e-4f * kd.gh;                        // binning and edge arithmetic round at ~1e-6 of a cell
     return r >= 0 && me > 0.0f && d1 * 1.00001f < me * me;
 }
@@ -807,20 +811,25 @@ __device__ __forceinline__ void icp_nn_small_model(const KdView& kd, const IcpSm
     if (threadIdx.x == 0) n_park_sm = 0;
     __syncthreads();
     if (gstart) {
-        for (int k = warp; k < nq; k += kIcpThreads / 32) {
+        // one query per warp while there are warps enough, else two per warp (half a warp each)
+        const int gl = nq > kIcpThreads / 32 ? 16 : 32, per_warp = 32 / gl, sub = lane / gl;
+        for (int kb = warp * per_warp; kb < nq; kb += per_warp * (kIcpThreads / 32)) {
+            const int k = kb + sub;
+            const bool valid = k < nq;
             const int i = q_begin + k * gridDim.x + blockIdx.x;
-            float qx, qy, qz;
-            query(k, i, qx, qy, qz);
+            float qx = 0.0f, qy = 0.0f, qz = 0.0f;
             // radius of the block of cells from last iteration's distance: the block's edge is >= r cells away
-            int r = 1;
-            {
+            int r = -1;
+            if (valid) {
+                query(k, i, qx, qy, qz);
+                r = 1;
                 const float hint = k < qcache_n ? sm.qhint[k] : __ldcg(d2_hint + i);
                 if (hint >= 0.0f && hint < 1.0e30f) r = (int)(sqrtf(hint) * 1.02f * kd.ginv_h) + 1;
                 if (r > kGridMaxR) r = -1;
             }
             float D1, D2; int P1;
-            const bool ok = grid_nn(kd, gstart, gpts, qx, qy, qz, r, lane, D1, P1, D2);
-            if (lane == 0) {
+            const bool ok = grid_nn(kd, gstart, gpts, qx, qy, qz, r, lane, gl, D1, P1, D2);
+            if ((lane & (gl - 1)) == 0 && valid) {
                 park[k] = ok ? 0ull : 1ull;
                 if (ok) finish(k, i, P1, D2 <= D1 * 1.00001f, D1, qx, qy, qz);
                 else atomicAdd(&n_park_sm, 1);
@@ -1038,12 +1047,16 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     extern __shared__ __align__(16) unsigned char icp_smem[];
     __shared__ float sh_H[9];
     __shared__ float sh_acc[8];
+    __shared__ float sh_mu[6];                                   // block 0: mu_m, mu_d of this iteration
+    __shared__ int sh_conv;                                      // block 0: converged in this iteration
+    __shared__ float sh_err;                                     // block 0: err of the previous iteration
     __shared__ __align__(16) float chunk[2][kIcpChunk * 8];      // double buffer of the streamed (large-cloud) accumulation
     __shared__ int n_deferred, n_unsettled;
     __shared__ float nn_merge_sm[2 * 48];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kWarps = kIcpThreads / 32;
-    const volatile IcpState* vst = st;
+    if (threadIdx.x == 0) { sh_conv = 0; sh_err = st->err; }
+    if (threadIdx.x < 6) sh_mu[threadIdx.x] = threadIdx.x < 3 ? st->mu_m[threadIdx.x] : st->mu_d[threadIdx.x - 3];
 
     // ---- carve dynamic shared memory: [kd-tree nodes | leaf points] [staged rows]
     const IcpSmem sm = icp_carve(kd, plan, icp_smem, data, 0, nd);
@@ -1054,10 +1067,16 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
     for (int iter = 0; iter < max_iter; iter++) {
         long long c0 = clock64();
         float R[9], t[3];
-#pragma unroll
-        for (int i = 0; i < 9; i++) R[i] = vst->R[i];
-#pragma unroll
-        for (int i = 0; i < 3; i++) t[i] = vst->t[i];
+        {   // the pose (and, from the second iteration on, the convergence flag) block 0 wrote before the grid barrier: four
+            // 16-byte L2 loads in flight together (volatile scalar loads are issued one after the other -- thirteen L2 round
+            // trips, ~10 k cycles per iteration)
+            const float4* sp4 = reinterpret_cast<const float4*>(st);
+            const float4 s0 = __ldcg(sp4), s1 = __ldcg(sp4 + 1), s2 = __ldcg(sp4 + 2);
+            static_assert(offsetof(IcpState, converged) == 84 && offsetof(IcpState, R) == 0 && offsetof(IcpState, t) == 36, "IcpState layout");
+            if (iter > 0 && __float_as_int(__ldcg(sp4 + 5).y)) break;
+            R[0] = s0.x; R[1] = s0.y; R[2] = s0.z; R[3] = s0.w; R[4] = s1.x; R[5] = s1.y; R[6] = s1.z; R[7] = s1.w; R[8] = s2.x;
+            t[0] = s2.y; t[1] = s2.z; t[2] = s2.w;
+        }
         // ---- phase A: transform + nearest neighbour; queries interleaved over the CTAs ----------
         if (plan.brute_force) {
             unsigned long long* park = wk.keys2 + (size_t)blockIdx.x * ((nd + gridDim.x - 1) / gridDim.x);      // wk.keys2 is idle until the sort
@@ -1180,7 +1199,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
             constexpr int kHelpers = (kWarps - 4) * 32;
             const int helper = (warp & 3) != 0 ? (warp - 1 - (warp >> 2)) * 32 + lane : -1;
             float acc = 0.0f;
-            if (warp == 0 && lane < 7) acc = lane < 3 ? st->mu_m[lane] : (lane < 6 ? st->mu_d[lane - 3] : 0.0f);
+            if (warp == 0 && lane < 7) acc = lane < 6 ? sh_mu[lane] : 0.0f;                // never reset between iterations (:205-206)
             const float4* srows = reinterpret_cast<const float4*>(do_sort ? wk.stage : wk.q);
             // err_new += dis is float += double in the reference (:254); the double sum of two floats is
             // exact (or differs from either by < 2^-29), so rounding it to float equals the float sum --
@@ -1218,17 +1237,17 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                     const float err_new = sh_acc[6];
                     st->err_new = err_new;
                     st->iter = iter;
-                    if (st->err > 0.0f && st->err - err_new < err_diff * (float)num) st->converged = 1;          // :257
+                    if (sh_err > 0.0f && sh_err - err_new < err_diff * (float)num) { st->converged = 1; sh_conv = 1; }          // :257
                     else {
-                        st->err = err_new;
-                        for (int c = 0; c < 3; c++) { st->mu_m[c] = sh_acc[c] / (float)nd; st->mu_d[c] = sh_acc[3 + c] / (float)nd; }   // :262-263
+                        st->err = sh_err = err_new;
+                        for (int c = 0; c < 3; c++) { sh_mu[c] = st->mu_m[c] = sh_acc[c] / (float)nd; sh_mu[3 + c] = st->mu_d[c] = sh_acc[3 + c] / (float)nd; }   // :262-263
                     }
                     __threadfence_block();
                 }
             }
             __syncthreads();
             c1 = clock64(); c_p1 += c1 - c0; c0 = c1;
-            if (!vst->converged) {
+            if (!sh_conv) {
                 // H = sum over the sorted rows of (q - mu_d)(m - mu_m)^T, each of its 9 entries a strictly
                 // sequential float sum (:268).  Warps 1.. form the products of block k+1 into a
                 // shared-memory ring while lanes 0..8 of warp 0 add block k: the dependent chain of adds
@@ -1238,7 +1257,7 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 static_assert(2 * 9 * kProdPitch <= 2 * kIcpChunk * 8, "product ring exceeds `chunk`");
                 float* ring = &chunk[0][0];
                 const int nblk = (num + kProd - 1) / kProd;
-                const float md0 = vst->mu_d[0], md1 = vst->mu_d[1], md2 = vst->mu_d[2], mm0 = vst->mu_m[0], mm1 = vst->mu_m[1], mm2 = vst->mu_m[2];
+                const float md0 = sh_mu[3], md1 = sh_mu[4], md2 = sh_mu[5], mm0 = sh_mu[0], mm1 = sh_mu[1], mm2 = sh_mu[2];   // the means just formed (:262-263)
                 auto produce = [&](int k) {
                     const int base = k * kProd, cnt = min(kProd, num - base);
                     float* dst = ring + (k & 1) * (kProdPitch * 9);
@@ -1266,15 +1285,14 @@ icp_kernel(KdView kd, const float4* __restrict__ data, int nd, IcpState* st, Icp
                 if (warp == 0) {
                     if (lane < 9) sh_H[lane] = acc;
                     __syncwarp();
-                    if (lane == 0) { const long long cu0 = clock64(); icp_update(st, sh_H, (flags & 2) != 0); c_wait += 0; c_svd += clock64() - cu0; }
+                    if (lane == 0) { const long long cu0 = clock64(); icp_update(st, sh_H, (flags & 2) != 0, R, t, sh_mu); c_wait += 0; c_svd += clock64() - cu0; }
                 }
             }
             c1 = clock64(); c_p2 += c1 - c0;
             if (threadIdx.x == 0) __threadfence();
         }
         grid.sync();
-        if (vst->converged) break;
-        if (iter == max_iter - 1 && blockIdx.x == 0 && threadIdx.x == 0) st->iter = max_iter;
+        if (iter == max_iter - 1) { if (blockIdx.x == 0 && threadIdx.x == 0 && !sh_conv) st->iter = max_iter; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { st->dbg[0] = c_nn; st->dbg[1] = c_wait; st->dbg[2] = c_sort; st->dbg[3] = c_p1; st->dbg[4] = c_p2; st->dbg[5] = c_acc1; st->dbg[0] = c_nn + (c_svd << 32); }
 }
