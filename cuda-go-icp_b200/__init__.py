@@ -79,7 +79,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
-               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_svd3", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_svd3", "goicp_intro_select", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
                "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_transfer_bytes", "goicp_measure_gather", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 
@@ -135,6 +135,7 @@ def lib():
         L.goicp_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_kdtree_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.goicp_svd3.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.goicp_intro_select.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.goicp_icp.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.POINTER(IcpResult)]
         L.goicp_icp_dt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
         L.goicp_dt_score.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, f32p]
@@ -381,6 +382,12 @@ class GoICP:
         U = np.zeros((n, 9), np.float32); W = np.zeros((n, 3), np.float32); V = np.zeros((n, 9), np.float32)
         self._check(self.L.goicp_svd3(self._handle(), H.ctypes.data, n, U.ctypes.data, W.ctypes.data, V.ctypes.data))
         return U.reshape(n, 3, 3), W, V.reshape(n, 3, 3)
+
+    def IntroSelect(self, a, k, threads=512, in_global=False):
+        """intro_select (jly_sorting.hpp:228-313) of a copy of `a` for position k by the strict kernels' block-wide select."""
+        a = np.array(a, np.float32).reshape(-1).copy()
+        self._check(self.L.goicp_intro_select(self._handle(), a.ctypes.data, len(a), int(k), int(threads), 1 if in_global else 0))
+        return a
 
     def ICP(self, R0=None, t0=None, max_iter=0, err_diff=-1.0):
         """ICP3D<float>::Run (jly_icp3d.hpp:180-295)."""

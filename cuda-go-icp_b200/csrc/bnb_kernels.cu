@@ -968,17 +968,19 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
 // reference's intro_select + sequential float sum.  strict_pick_kernel replays the reference's
 // `if (ub < optErrorT)` over the contenders in evaluation order.
 // ------------------------------------------------------------------------------------------
-constexpr int kStrictStaticSmem = 2 * kSsWin * (int)sizeof(float) + 512;       // windows of the global-memory select + slack
+constexpr int kStrictStaticSmem = 2 * kSsWin * (int)sizeof(float) + 1024;       // windows of the global-memory select + slack
 __global__ void __launch_bounds__(256)
 strict_eval_kernel(BnbConst c, const InnerTask* __restrict__ task_p, const CandList* __restrict__ cl, float* __restrict__ strict_ub,
-                   float* __restrict__ gscratch, int use_smem)
+                   float* __restrict__ gscratch, int use_smem /* 2: residuals + the select's position lists in shared memory, 1: residuals only, 0: neither */)
 {
     extern __shared__ float m_sm[];
+    __shared__ unsigned long long sel_sh[40];
     const int q = blockIdx.x;
     if (q >= cl->n) return;
     if (!(cl->ub[q] <= cl->final_fast * (1.0f + cl->eps))) { if (threadIdx.x == 0) strict_ub[q] = 3.402823466e+38f; return; }
     const InnerTask& task = *task_p;
-    float* m = use_smem ? m_sm : gscratch + (size_t)q * c.nd;
+    float* m = use_smem ? m_sm : gscratch + (size_t)q * 3 * c.nd;
+    int* sel_idx = use_smem == 2 ? reinterpret_cast<int*>(m_sm + c.nd) : reinterpret_cast<int*>(gscratch + (size_t)q * 3 * c.nd + c.nd);
     const float4 nd4 = cl->node[q];
     const float half = nd4.w / 2;
     const float tx = __fadd_rn(nd4.x, half), ty = __fadd_rn(nd4.y, half), tz = __fadd_rn(nd4.z, half);   // :270-272
@@ -991,10 +993,11 @@ strict_eval_kernel(BnbConst c, const InnerTask* __restrict__ task_p, const CandL
         m[i] = d < 0.0f ? 0.0f : d;
     }
     __syncthreads();
-    __shared__ float win[2 * kSsWin];                     // fronts of the select when the residuals live in global memory
+    __shared__ float win[2 * kSsWin];                     // staging of the sequential sum when the residuals live in global memory
+    if (c.do_trim) ss_intro_select_cta(m, 0, c.nd - 1, c.inlier_num - 1, sel_idx, sel_sh);
     if (threadIdx.x == 0) {
         float ub, lb;
-        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+        ss_sum_selected(m, c.do_trim ? c.inlier_num : c.nd, 0.0f, false, ub, lb, use_smem ? nullptr : win);
         strict_ub[q] = ub;
     }
 }
@@ -1018,9 +1021,11 @@ __global__ void __launch_bounds__(kBnbThreads)
 dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restrict__ use_pose, float* __restrict__ scratch, float* __restrict__ out, int use_smem)
 {
     extern __shared__ float m_sm[];
+    __shared__ unsigned long long sel_sh[40];
     const float* Rt = Rt12 + 12 * blockIdx.x;
     const bool pose = use_pose[blockIdx.x] != 0;
-    float* m = use_smem ? m_sm : scratch + (size_t)blockIdx.x * c.nd;
+    float* m = use_smem ? m_sm : scratch + (size_t)blockIdx.x * 3 * c.nd;
+    int* sel_idx = use_smem == 2 ? reinterpret_cast<int*>(m_sm + c.nd) : reinterpret_cast<int*>(scratch + (size_t)blockIdx.x * 3 * c.nd + c.nd);
     for (int i = threadIdx.x; i < c.nd; i += kBnbThreads) {
         float4 p = __ldg(c.data + i);
         float x = p.x, y = p.y, z = p.z;
@@ -1032,17 +1037,17 @@ dt_score_kernel(BnbConst c, const float* __restrict__ Rt12, const int* __restric
         m[i] = dt_distance(c.dt, x, y, z);
     }
     __syncthreads();
-    __shared__ float win[2 * kSsWin];                     // fronts of the select when the residuals live in global memory
+    __shared__ float win[2 * kSsWin];                     // staging of the sequential sum when the residuals live in global memory
+    const long long t0 = clock64();
+    if (c.do_trim) ss_intro_select_cta(m, 0, c.nd - 1, c.inlier_num - 1, sel_idx, sel_sh);
     if (threadIdx.x == 0) {
         float ub, lb;
-#ifdef GOICP_SCORE_TRACE
-        const long long t0 = clock64();
-        if (c.do_trim) { if (!use_smem) ss_intro_select_global(m, 0, c.nd - 1, c.inlier_num - 1, win); else ss_intro_select(m, 0, c.nd - 1, c.inlier_num - 1); }
         const long long t1 = clock64();
-        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, false, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+        ss_sum_selected(m, c.do_trim ? c.inlier_num : c.nd, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+#ifdef GOICP_SCORE_TRACE
         printf("[dt_score] nd %d: select %lld cycles, sum %lld cycles\n", c.nd, t1 - t0, clock64() - t1);
 #else
-        ss_select_and_sum(m, c.nd, c.do_trim ? c.inlier_num : c.nd, c.do_trim != 0, 0.0f, false, ub, lb, use_smem ? nullptr : win);
+        (void)t0; (void)t1;
 #endif
         out[blockIdx.x] = ub;
     }
@@ -1242,13 +1247,40 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     if (pts_in_smem) return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
     return cudaLaunchKernelEx(&cfg, inner_bnb_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands, d_trim_keys);
 }
+// intro_select on a caller's array (parity hook, goicp_intro_select): the CTA-wide select of the strict kernels on its own.
+// in_smem: the array and the position lists are staged in dynamic shared memory (3 * n floats), else they stay in global memory.
+__global__ void __launch_bounds__(1024)
+select_test_kernel(float* __restrict__ a, int n, int k, int* __restrict__ idx, int in_smem)
+{
+    extern __shared__ float m_sm[];
+    __shared__ unsigned long long sel_sh[40];
+    float* m = in_smem ? m_sm : a;
+    if (in_smem) { for (int i = threadIdx.x; i < n; i += blockDim.x) m[i] = a[i]; __syncthreads(); }
+    ss_intro_select_cta(m, 0, n - 1, k, in_smem ? reinterpret_cast<int*>(m_sm + n) : idx, sel_sh);
+    if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = m[i];
+}
+cudaError_t launch_select_test(float* d_a, int n, int k, int* d_idx, int threads, int smem_limit, bool allow_smem, cudaStream_t s)
+{
+    const size_t need = 3 * (size_t)n * sizeof(float);
+    const int in_smem = allow_smem && need + 1024 <= (size_t)smem_limit ? 1 : 0;
+    if (in_smem) { cudaError_t e = cudaFuncSetAttribute(select_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need); if (e != cudaSuccess) return e; }
+    select_test_kernel<<<1, threads, in_smem ? need : 0, s>>>(d_a, n, k, d_idx, in_smem);
+    return cudaGetLastError();
+}
+// where the residuals (nd floats) and the position lists of the CTA-wide select (2 * nd ints) of one strict evaluation live:
+// 2 = all in shared memory, 1 = residuals in shared memory, 0 = all in the caller's scratch (3 * nd floats per evaluation)
+int strict_smem_mode(int nd, int smem_limit)
+{
+    const size_t need = (size_t)nd * sizeof(float);
+    return 3 * need + kStrictStaticSmem <= (size_t)smem_limit ? 2 : (need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0);
+}
 // out5 = {strict optErrorT, node x, y, z, w}; d_strict: kMaxCand floats; d_scratch: kMaxCand*nd floats (only if nd does not fit in smem)
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
                                   float* d_out5, int smem_limit, cudaStream_t s)
 {
     const size_t need = (size_t)c.nd * sizeof(float);
-    const int use_smem = need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0;
-    strict_eval_kernel<<<kMaxCand, 256, use_smem ? need : 0, s>>>(c, d_task, d_list, d_strict, d_scratch, use_smem);
+    const int use_smem = strict_smem_mode(c.nd, smem_limit);
+    strict_eval_kernel<<<kMaxCand, 256, use_smem == 2 ? 3 * need : (use_smem == 1 ? need : 0), s>>>(c, d_task, d_list, d_strict, d_scratch, use_smem);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     strict_pick_kernel<<<1, 1, 0, s>>>(d_task, d_list, d_strict, d_out5);
@@ -1259,8 +1291,8 @@ cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d
     if (nposes <= 0) return cudaSuccess;
     if (fast_sums) { dt_score_fast_kernel<<<nposes, kBnbThreads, 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out); return cudaGetLastError(); }
     const size_t need = (size_t)c.nd * sizeof(float);
-    const int use_smem = need + kStrictStaticSmem <= (size_t)smem_limit ? 1 : 0;
-    dt_score_kernel<<<nposes, kBnbThreads, use_smem ? need : 0, s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out, use_smem);
+    const int use_smem = strict_smem_mode(c.nd, smem_limit);
+    dt_score_kernel<<<nposes, kBnbThreads, use_smem == 2 ? 3 * need : (use_smem == 1 ? need : 0), s>>>(c, d_Rt12, d_use_pose, d_scratch, d_out, use_smem);
     return cudaGetLastError();
 }
 

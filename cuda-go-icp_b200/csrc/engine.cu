@@ -634,7 +634,7 @@ int share_cand_list(goicp_handle* h, std::shared_ptr<CandList>& cl)
 int resolve_strict(goicp_handle* h, const BnbConst& c, const InnerTask& task, const CandList& list, float* value, float* node4)
 {
     struct Acc { double& a; double t0; ~Acc() { a += now_s() - t0; } } acc{h->t_strict, now_s()};
-    const size_t scratch = (size_t)h->nd * sizeof(float) + 20480 <= (size_t)(h->max_smem_optin - 2048) ? 0 : (size_t)kMaxCand * h->nd;      // conservative: the kernel decides with its own static size
+    const size_t scratch = strict_smem_mode(h->nd, h->max_smem_optin - 2048) == 2 ? 0 : (size_t)kMaxCand * 3 * h->nd;      // residuals + the select's position lists
     CUDA_TRY(h, h->d_strict.reserve(256 + scratch));
     CUDA_TRY(h, h->d_tasks.reserve(1)); CUDA_TRY(h, h->d_cands.reserve(1));
     InnerTask* d_task = h->d_tasks.p + (h->d_tasks.n - 1);          // last slots are reserved for this
@@ -661,7 +661,7 @@ int score_pose(goicp_handle* h, const BnbConst& c, const float* R, const float* 
     CUDA_TRY(h, h->d_i32.reserve(16));
     CUDA_TRY(h, xfer(h, h->d_f32a.p, Rt, sizeof Rt, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, xfer(h, h->d_i32.p, &use, sizeof use, cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, h->d_score_scratch.reserve((size_t)h->nd));
+    CUDA_TRY(h, h->d_score_scratch.reserve((size_t)3 * h->nd));                     // residuals + the select's position lists (strict_smem_mode < 2)
     CUDA_TRY(h, launch_dt_score(c, h->d_f32a.p, h->d_i32.p, 1, h->d_score_scratch.p, h->d_f32a.p + 16, h->max_smem_optin - 2048, (h->p.numerics & GOICP_NUM_FAST_SUMS) != 0, h->stream));
     h->launches++;
     CUDA_TRY(h, xfer(h, out, h->d_f32a.p + 16, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1191,6 +1191,19 @@ int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3
     CUDA_TRY(h, xfer(h, U9_out, dU, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, xfer(h, W3_out, dW, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, xfer(h, V9_out, dV, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return GOICP_OK;
+}
+
+int goicp_intro_select(goicp_handle* h, float* a, int n, int k, int threads, int in_global)
+{
+    if (!h || !a || n <= 0 || k < 0 || k >= n || threads < 32 || threads > 1024 || (threads & 31)) return fail(h, GOICP_ERR_INVALID, "intro_select: bad arguments");
+    int rc = ensure_cuda(h); if (rc) return rc;
+    CUDA_TRY(h, h->d_q.reserve((size_t)n));
+    CUDA_TRY(h, h->d_i32.reserve((size_t)2 * n));
+    CUDA_TRY(h, xfer(h, h->d_q.p, a, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, launch_select_test(h->d_q.p, n, k, h->d_i32.p, threads, h->max_smem_optin - 2048, !in_global, h->stream));
+    CUDA_TRY(h, xfer(h, a, h->d_q.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return GOICP_OK;
 }

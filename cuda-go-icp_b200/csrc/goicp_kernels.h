@@ -12,6 +12,8 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
                              bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency,
                              unsigned* d_trim_keys /* trimming: per-CTA slabs of 8 * ceil(nd/cluster) keys in global memory, or null = shared memory */, cudaStream_t s);
+cudaError_t launch_select_test(float* d_a, int n, int k, int* d_idx, int threads, int smem_limit, bool allow_smem, cudaStream_t s);
+int strict_smem_mode(int nd, int smem_limit);        // 2 / 1 / 0: see bnb_kernels.cu
 cudaError_t launch_strict_resolve(const BnbConst& c, const InnerTask* d_task, const CandList* d_list, float* d_strict, float* d_scratch,
                                   float* d_out5, int smem_limit, cudaStream_t s);
 cudaError_t launch_dt_score(const BnbConst& c, const float* d_Rt12, const int* d_use_pose, int nposes, float* d_scratch, float* d_out, int smem_limit, bool fast_sums, cudaStream_t s);

@@ -3,9 +3,11 @@
 // SEQUENTIALLY in float (jly_goicp.cpp:293-315).  The float result therefore depends on that
 // permutation.  Wherever a decision of the search hinges on which of two nearly equal sums is
 // smaller (the arg-min translation cube of an improving upper-bound pass, the error after an ICP
-// refinement), the engine re-evaluates the few contenders with this single-thread emulation so
-// the decision -- and hence the refinement the search performs next -- is the reference's.
-// One thread per array; arrays of Nd floats in shared or global memory.
+// refinement), the engine re-evaluates the few contenders in that order so the decision -- and
+// hence the refinement the search performs next -- is the reference's.
+// The selection runs block-wide (ss_intro_select_cta: each partition sweep as two ranked position
+// lists and K independent exchanges); what is inherently serial -- pivot rule, ranges of a few
+// dozen elements, the final sum -- stays with one thread.  Arrays of Nd floats in shared or global memory.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -57,11 +59,10 @@ __device__ inline int ss_mom(float* a, int st, int en)                         /
         return st;
     }
 }
-// intro_select (:228-313)
-__device__ inline void ss_intro_select(float* a, int st, int en, int k)
+// intro_select (:228-313); l_pre / tries / quick: the state of its pivot-rule switch (the CTA-wide form below hands the tail of a
+// selection to one thread in mid-flight)
+__device__ inline void ss_intro_select_from(float* a, int st, int en, int k, int l_pre, int tries, bool quick)
 {
-    int l_pre = en - st + 1, tries = 0;
-    bool quick = true;
     for (;;) {
         if (st >= en) break;
         if (en - st <= 5) {                                                     // insertion_sort (:212-224)
@@ -91,13 +92,119 @@ __device__ inline void ss_intro_select(float* a, int st, int en, int k)
         if (s < k) st = s + 1; else if (s > k) en = s - 1; else break;
     }
 }
+__device__ inline void ss_intro_select(float* a, int st, int en, int k) { ss_intro_select_from(a, st, en, k, en - st + 1, 0, true); }
 
-// ---- the same for an array in GLOBAL memory (clouds beyond ~55 k points) ------------------------
-// One thread walking a global array pays an L2 round trip per element (the accesses depend on the
-// comparisons), 75x a CPU core.  The Hoare sweep only ever touches two fronts, so the thread stages
-// them through two shared-memory windows with plain copy loops (independent loads: they pipeline)
-// and runs the reference's loop on the windows; a range of <= 2 windows is staged whole.  Same
-// comparisons, same swaps, same order -- only where the operands sit differs.
+// ---- the same selection by a whole CTA ---------------------------------------------------------------------------
+// What the reference's partition sweep (:283-296) does to the array, said without its two walking indices: the sweep stops
+// its left index on elements > pivot and its right index on elements < pivot (elements equal to the pivot stop neither), and
+// swaps the pair it stopped on.  A swapped-in element lies behind the index that passes it, so the stops are those of the
+// ORIGINAL array: the sweep exchanges the k-th element > pivot counted from the left with the k-th element < pivot counted
+// from the right, for k = 1, 2, ... as long as the former lies left of the latter (K exchanges), and its indices meet on the
+// (K+1)-th element > pivot if that lies left of the K-th partner (of the range's end for K = 0), else on that partner.
+// Two ranked position lists (warp ballots + one scan over the warps' counts), K independent exchanges, one thread for the
+// meeting point: same array, same pivot position, for any input including ties and all-equal ranges
+// (tests/test_gpu_gaps.py::test_cta_select_matches_reference_permutation).  Pivot choice, the placing of the pivot, ranges
+// below kSsSeqBelow elements and the median-of-medians fallback stay with thread 0 (the routines above).
+// Every thread of the CTA calls with the same arguments.  a: shared or global memory.  idx: 2 * (en - st + 1) ints, shared or
+// global.  sh: 40 64-bit words of shared memory.
+constexpr int kSsSeqBelow = 64;
+__device__ inline int ss_partition_cta(float* a, int lo, int hi, float pivot, int* idx, unsigned long long* sh)
+{
+    const unsigned full = 0xffffffffu;
+    const int n = hi - lo + 1, T = (int)blockDim.x, t = (int)threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
+    const int cw = (((n + nw - 1) / nw) + 31) & ~31;                      // elements per warp, whole 32-element rows
+    const int wb = min(lo + warp * cw, hi + 1), we = min(wb + cw, hi + 1);
+    const unsigned lt = (1u << lane) - 1u;
+    int nl = 0, nr = 0;                                                      // stops in this warp's stretch (warp-uniform)
+    for (int p0 = wb; p0 < we; p0 += 128) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int p = p0 + 32 * u + lane; v[u] = p < we ? a[p] : pivot; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { nl += __popc(__ballot_sync(full, v[u] > pivot)); nr += __popc(__ballot_sync(full, v[u] < pivot)); }
+    }
+    if (lane == 0) sh[warp] = (unsigned long long)(unsigned)nl | ((unsigned long long)(unsigned)nr << 32);
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = lane < nw ? sh[lane] : 0ull; unsigned long long inc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(full, inc, o); if (lane >= o) inc += y; }
+        sh[lane] = inc - w;                                                  // stops in the warps to the left
+        if (lane == 31) sh[32] = inc;
+    }
+    __syncthreads();
+    const unsigned long long before = sh[warp], tot = sh[32];
+    const int NL = (int)(unsigned)tot, NR = (int)(tot >> 32);
+    int* lpos = idx; int* rpos = idx + n;                                    // k-th stop from the left / from the right
+    int il = (int)(unsigned)before, ir = (int)(before >> 32);
+    for (int p0 = wb; p0 < we; p0 += 128) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const int p = p0 + 32 * u + lane; v[u] = p < we ? a[p] : pivot; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned bl = __ballot_sync(full, v[u] > pivot), br = __ballot_sync(full, v[u] < pivot);
+            const int p = p0 + 32 * u + lane;
+            if (v[u] > pivot) lpos[il + __popc(bl & lt)] = p;
+            else if (v[u] < pivot) rpos[NR - 1 - (ir + __popc(br & lt))] = p;
+            il += __popc(bl); ir += __popc(br);
+        }
+    }
+    __syncthreads();
+    const int m = min(NL, NR);
+    int fail = m;                                                            // first k whose pair has crossed (the lists are monotone)
+    for (int k = t; k < m; k += T) {
+        const int p = lpos[k], q = rpos[k];
+        if (p < q) { const float vp = a[p]; a[p] = a[q]; a[q] = vp; } else { fail = k; break; }
+    }
+    fail = __reduce_min_sync(full, (unsigned)fail);
+    if (lane == 0) sh[warp] = (unsigned long long)(unsigned)fail;
+    __syncthreads();
+    if (t == 0) {
+        int K = m;
+        for (int w = 0; w < nw; w++) K = min(K, (int)(unsigned)sh[w]);
+        const int rK = K > 0 ? rpos[K - 1] : hi;
+        sh[33] = (unsigned long long)(unsigned)((K < NL && lpos[K] < rK) ? lpos[K] : rK);
+    }
+    __syncthreads();
+    return (int)(unsigned)sh[33];
+}
+__device__ inline void ss_intro_select_cta(float* a, int st, int en, int k, int* idx, unsigned long long* sh)
+{
+    int l_pre = en - st + 1, tries = 0;
+    bool quick = true;
+    for (;;) {
+        if (st >= en) break;
+        if (en - st < kSsSeqBelow) { if (threadIdx.x == 0) ss_intro_select_from(a, st, en, k, l_pre, tries, quick); break; }
+        if (quick && tries++ == 5) {
+            const int l = en - st + 1;
+            if (l * 2 > l_pre) quick = false;
+            l_pre = l; tries = 0;
+        }
+        if (threadIdx.x == 0) {
+            const int med = quick ? ss_med_ends(a, st, en) : ss_mom(a, st, en);
+            if (med != st) { const float t = a[st]; a[st] = a[med]; a[med] = t; }
+            sh[34] = (unsigned long long)__float_as_uint(a[st]);
+        }
+        __syncthreads();
+        const float pivot = __uint_as_float((unsigned)sh[34]);
+        const int left = ss_partition_cta(a, st + 1, en, pivot, idx, sh);
+        if (threadIdx.x == 0) {
+            int s = left - 1;
+            if (a[left] < pivot) s = left;
+            a[st] = a[s]; a[s] = pivot;
+            sh[35] = (unsigned long long)(unsigned)s;
+        }
+        __syncthreads();
+        const int s = (int)(unsigned)sh[35];
+        if (s < k) st = s + 1; else if (s > k) en = s - 1; else break;
+    }
+    __syncthreads();
+}
+
+// ---- reading an array in GLOBAL memory from one thread -----------------------------------------------------------
+// One thread walking a global array pays an L2 round trip per element; the sequential sum below therefore stages the
+// residuals through a shared-memory window with plain copy loops (independent loads: they pipeline).
 constexpr int kSsWin = 2048;                 // floats per window; callers provide 2 * kSsWin floats of shared memory
 
 // One thread moving a window: what it needs is loads in flight, so the bulk goes as 16 independent 16-byte accesses
@@ -124,79 +231,11 @@ __device__ inline void ss_copy(float* dst, const float* src, int n, bool src_is_
     }
     for (; i < n; i++) dst[i] = src[i];
 }
-// the partition sweep of intro_select (:283-296) on a[left..right]; returns with left/right where the reference's
-// `for (;;)` leaves them
-__device__ inline void ss_partition_global(float* a, int& left, int& right, const float pivot, float* buf)
-{
-    for (;;) {
-        const int n = right - left + 1;
-        if (n <= 2 * kSsWin) {                                   // the rest fits: the reference's loop verbatim, on the staged copy
-            if (n <= 0) return;
-            ss_copy(buf, a + left, n);
-            int l = 0, r = n - 1;
-            for (;;) {
-                while (l < r && pivot >= buf[l]) ++l;
-                while (l < r && pivot <= buf[r]) --r;
-                if (l >= r) break;
-                const float t = buf[l]; buf[l] = buf[r]; buf[r] = t;
-            }
-            ss_copy(a + left, buf, n, false);
-            right = left + r; left += l;
-            return;
-        }
-        // two disjoint fronts (left < right holds throughout): L = a[left, left+W), R = a(right-W, right]
-        float* L = buf; float* R = buf + kSsWin;
-        ss_copy(L, a + left, kSsWin);
-        ss_copy(R, a + right - kSsWin + 1, kSsWin);
-        int l = 0, r = kSsWin - 1;
-        for (;;) {
-            while (l < kSsWin && pivot >= L[l]) ++l;
-            if (l == kSsWin) break;                               // left front leaves its window in the middle of its scan
-            while (r >= 0 && pivot <= R[r]) --r;
-            if (r < 0) break;                                     // right front leaves its window; the left one rests on a[left] > pivot
-            const float t = L[l]; L[l] = R[r]; R[r] = t;
-        }
-        ss_copy(a + left, L, kSsWin, false);
-        ss_copy(a + right - kSsWin + 1, R, kSsWin, false);
-        left += l; right -= kSsWin - 1 - r;                       // resuming with the left scan is what the reference does in both cases
-    }
-}
-__device__ inline void ss_intro_select_global(float* a, int st, int en, int k, float* buf)
-{
-    int l_pre = en - st + 1, tries = 0;
-    bool quick = true;
-    for (;;) {
-        if (st >= en) break;
-        if (en - st <= 5) {                                                     // insertion_sort (:212-224)
-            for (int i = st + 1; i <= en; i++)
-                for (int j = i; j > st && a[j - 1] > a[j]; j--) { float t = a[j - 1]; a[j - 1] = a[j]; a[j] = t; }
-            return;
-        }
-        if (quick && tries++ == 5) {
-            const int l = en - st + 1;
-            if (l * 2 > l_pre) quick = false;
-            l_pre = l; tries = 0;
-        }
-        const int med = quick ? ss_med_ends(a, st, en) : ss_mom(a, st, en);
-        float t;
-        if (med != st) { t = a[st]; a[st] = a[med]; a[med] = t; }
-        int left = st + 1, right = en;
-        const float pivot = a[st];
-        ss_partition_global(a, left, right, pivot, buf);
-        int s = left - 1;
-        if (a[left] < pivot) s = left;
-        a[st] = a[s]; a[s] = pivot;
-        if (s < k) st = s + 1; else if (s > k) en = s - 1; else break;
-    }
-}
-
 // The reference's (trimmed) sums over the selected residuals: ub (jly_goicp.cpp:302-306) and,
 // when want_lb, lb with the translation radius gt (:308-315).
 // win: 2 * kSsWin floats of shared memory when m is in global memory, nullptr when m itself is in shared memory.
-__device__ inline void ss_select_and_sum(float* m, int nd, int inlier_num, bool do_select, float gt, bool want_lb,
-                                         float& ub_out, float& lb_out, float* win = nullptr)
+__device__ inline void ss_sum_selected(const float* m, int inlier_num, float gt, bool want_lb, float& ub_out, float& lb_out, float* win = nullptr)
 {
-    if (do_select) { if (win) ss_intro_select_global(m, 0, nd - 1, inlier_num - 1, win); else ss_intro_select(m, 0, nd - 1, inlier_num - 1); }
     float ub = 0.0f, lb = 0.0f;
     if (win) {
         for (int base = 0; base < inlier_num; base += 2 * kSsWin) {

@@ -213,6 +213,12 @@ int goicp_kdtree_host(const float* model_xyz, int n, int32_t* nodes7_out, int ca
  * values (descending) and V with the reference's float roundings, sort and sign normalisation.  Exposed for parity tests. */
 int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3_out, float* V9_out);
 
+/* intro_select (jly_sorting.hpp:228-313) of a[0..n) for position k, in place: the permutation the reference leaves behind decides the
+ * order of its sequential residual sums (jly_goicp.cpp:293-315), so the strict kernels reproduce it -- with the partition sweep done by a
+ * whole thread block (csrc/strict_sum.cuh).  threads: block size (multiple of 32, <= 1024); in_global != 0 keeps the array in device
+ * global memory (the path of clouds beyond shared memory).  Exposed for parity tests. */
+int goicp_intro_select(goicp_handle* h, float* a, int n, int k, int threads, int in_global);
+
 /* ICP3D<float>::Run (jly_icp3d.hpp:180-295) from (R0,t0). err_diff<0 -> mse_threshold/10000
  * (jly_goicp.cpp:186); max_iter<=0 -> params.icp_max_iter. */
 int goicp_icp(goicp_handle* h, const float R0[9], const float t0[3], int max_iter, float err_diff,

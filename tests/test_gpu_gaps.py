@@ -236,6 +236,36 @@ def test_two_rank_nccl_registration_vs_golden(pkg, runs):
         assert per_rank[0]["R"] == per_rank[1]["R"] and per_rank[0]["sse"] == per_rank[1]["sse"]
 
 
+def test_cta_select_matches_reference_permutation(pkg, restated):
+    """intro_select by a whole thread block (csrc/strict_sum.cuh: ranked stop lists + K independent exchanges per partition
+    sweep) leaves exactly the reference's permutation (oracle go_intro_select, pinned to jly_sorting.hpp in test_oracle.py):
+    random, tie-heavy, constant, sorted and reverse-sorted arrays, DT-like residuals with many exact zeros, 1 .. 200 000
+    elements, k at both ends / the middle / the untrimmed n - 1, block sizes 64 .. 1024, arrays in shared and in global memory."""
+    g = pkg.GoICP(1e-3)
+    rng = np.random.default_rng(2024)
+    cases = []
+    for n in (1, 2, 5, 6, 7, 63, 64, 65, 127, 128, 129, 500, 3019, 4097, 20000, 130001, 200000):
+        ks = sorted({0, n // 2, max(0, int(0.9 * n) - 1), n - 1})
+        kinds = [(rng.random(n), ks), (np.arange(n), ks), (np.arange(n)[::-1], ks), (np.repeat(rng.random((n + 9) // 10), 10)[:n], ks),
+                 (np.maximum(rng.normal(size=n), -0.3) + 0.3, ks[2:])]          # DT-like: a third exact zeros, selected above them
+        if n <= 4097:                                                           # (a selection INSIDE a run of equal values costs the reference O(n^2))
+            kinds += [(rng.integers(0, 4, n), ks), (np.zeros(n), ks), (np.maximum(rng.normal(size=n), 0.0), ks)]
+        for a, kk in kinds:
+            for k in kk:
+                cases.append((np.asarray(a, np.float32), k))
+    checked = 0
+    for i, (a, k) in enumerate(cases):
+        want = restated.intro_select(a, k)
+        threads = (64, 256, 512, 1024)[i % 4]
+        for in_global in ((False, True) if len(a) <= 15000 else (True,)):
+            if len(a) >= 100000 and i % 3: continue                    # the largest sizes: a third of the (kind, k) pairs
+            got = g.IntroSelect(a, k, threads=threads, in_global=in_global)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (len(a), k, threads, in_global, int((got != want).sum()))
+            checked += 1
+    g.close()
+    assert checked > 500
+
+
 def test_svd3_matches_reference_bit_for_bit(pkg, small, restated):
     """Matrix::svd on the device (register-resident restatement inside the ICP kernel) against the reference's outputs for the
     32 golden matrices (scales 1e-3 .. 1e3, every eighth rank-deficient) and against the oracle on 4 000 random ones,
