@@ -169,6 +169,65 @@ __device__ inline int ss_partition_cta(float* a, int lo, int hi, float pivot, in
     __syncthreads();
     return (int)(unsigned)sh[33];
 }
+// median_of_medians (:148-210) by the whole CTA.  One level of the reference's loop takes the median of every group of five
+// (ss_med5, which also reorders its group) and swaps it to the front, a[st + i] <-> a[med_i], group after group.  Group i lies
+// wholly behind a[st + i], so every group is still untouched when its turn comes: the medians are independent.  The swaps
+// chain only through the front: the value swap i finds at a[st + i] is the one swap floor(i / 5) left there if that swap's
+// median position was a[st + i] (and so on down that chain, <= log5 n steps), else the group-reordered original.  So: all
+// groups in parallel, then every i resolves (median value, displaced value) by walking its chain, then two conflict-free
+// write phases (displaced values first, the front -- which later swaps own -- last).  The ragged last group and ranges of a
+// few hundred elements stay with thread 0, in the reference's order.  scratch: 3 * groups 32-bit words.
+constexpr int kSsMomSeqBelow = 320;
+__device__ inline int ss_mom_cta(float* a, int st, int en, int* scratch, unsigned long long* sh)
+{
+    const int T = (int)blockDim.x, t = (int)threadIdx.x;
+    for (;;) {
+        const int l = en - st + 1;
+        if (l < kSsMomSeqBelow) {
+            if (t == 0) sh[36] = (unsigned long long)(unsigned)ss_mom(a, st, en);
+            __syncthreads();
+            const int med = (int)(unsigned)sh[36];
+            __syncthreads();
+            return med;
+        }
+        const int groups = l / 5 + (l % 5 != 0), full = groups - 1;        // groups 0 .. full-1 are whole
+        int* medpos = scratch; float* Mv = reinterpret_cast<float*>(scratch + groups); float* Vv = reinterpret_cast<float*>(scratch + 2 * groups);
+        for (int i = t; i < full; i += T) {
+            float* g = a + st + 5 * i;
+            float b[5] = {g[0], g[1], g[2], g[3], g[4]};
+            float x; int m;
+            if (b[0] > b[1]) { x = b[0]; b[0] = b[1]; b[1] = x; }
+            if (b[2] > b[3]) { x = b[2]; b[2] = b[3]; b[3] = x; }
+            if (b[0] < b[2]) { x = b[4]; b[4] = b[0]; if (x < b[1]) b[0] = x; else { b[0] = b[1]; b[1] = x; } }
+            else             { x = b[4]; b[4] = b[2]; if (x < b[3]) b[2] = x; else { b[2] = b[3]; b[3] = x; } }
+            if (b[0] < b[2]) m = b[1] < b[2] ? 1 : 2; else m = b[0] < b[3] ? 0 : 3;
+            g[0] = b[0]; g[1] = b[1]; g[2] = b[2]; g[3] = b[3]; g[4] = b[4];
+            medpos[i] = st + 5 * i + m;
+        }
+        __syncthreads();
+        for (int i = t; i < full; i += T) {
+            Mv[i] = a[medpos[i]];
+            int ii = i;
+            while (ii > 0 && medpos[ii / 5] == st + ii) ii /= 5;           // swap ii/5 left its displaced value on a[st + ii]
+            Vv[i] = a[st + ii];
+        }
+        __syncthreads();
+        for (int i = t; i < full; i += T) a[medpos[i]] = Vv[i];
+        __syncthreads();
+        for (int i = t; i < full; i += T) a[st + i] = Mv[i];
+        __syncthreads();
+        if (t == 0) {                                                       // the last group, as the reference does it
+            const int sub = st + 5 * full, rest = en - sub + 1;
+            int med;
+            if (rest == 3 || rest == 4) med = ss_med3(a, sub);
+            else if (rest == 5) med = ss_med5(a, sub);
+            else med = sub;
+            const float x = a[st + full]; a[st + full] = a[med]; a[med] = x;
+        }
+        __syncthreads();
+        en = st + groups - 1;                                               // groups > 5 here: next level over the medians
+    }
+}
 __device__ inline void ss_intro_select_cta(float* a, int st, int en, int k, int* idx, unsigned long long* sh)
 {
     int l_pre = en - st + 1, tries = 0;
@@ -181,8 +240,9 @@ __device__ inline void ss_intro_select_cta(float* a, int st, int en, int k, int*
             if (l * 2 > l_pre) quick = false;
             l_pre = l; tries = 0;
         }
+        const int mom = quick ? -1 : ss_mom_cta(a, st, en, idx, sh);
         if (threadIdx.x == 0) {
-            const int med = quick ? ss_med_ends(a, st, en) : ss_mom(a, st, en);
+            const int med = quick ? ss_med_ends(a, st, en) : mom;
             if (med != st) { const float t = a[st]; a[st] = a[med]; a[med] = t; }
             sh[34] = (unsigned long long)__float_as_uint(a[st]);
         }

@@ -248,6 +248,7 @@ def test_cta_select_matches_reference_permutation(pkg, restated):
         ks = sorted({0, n // 2, max(0, int(0.9 * n) - 1), n - 1})
         kinds = [(rng.random(n), ks), (np.arange(n), ks), (np.arange(n)[::-1], ks), (np.repeat(rng.random((n + 9) // 10), 10)[:n], ks),
                  (np.maximum(rng.normal(size=n), -0.3) + 0.3, ks[2:])]          # DT-like: a third exact zeros, selected above them
+        kinds.append((np.round(np.abs(rng.normal(size=n)) * 3) / 3, ks[2:]))     # a handful of distinct values: the median-of-medians fallback at every size
         if n <= 4097:                                                           # (a selection INSIDE a run of equal values costs the reference O(n^2))
             kinds += [(rng.integers(0, 4, n), ks), (np.zeros(n), ks), (np.maximum(rng.normal(size=n), 0.0), ks)]
         for a, kk in kinds:
