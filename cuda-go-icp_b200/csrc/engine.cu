@@ -166,6 +166,7 @@ struct goicp_handle {
 
     // distance transform
     DevBuf<float> d_dt; int dt_size = 0; double dt_meta[4] = {0, 0, 0, 0}; bool have_dt = false;
+    cudaTextureObject_t dt_tex = 0; const float* dt_tex_ptr = nullptr; int dt_tex_size = 0;      // the grid as a linear texture (dt_texture())
     // data cloud on device (x,y,z,norm)
     DevBuf<float4> d_data; bool data_uploaded = false;
     // kd-tree
@@ -394,11 +395,37 @@ int initialize(goicp_handle* h)
     return GOICP_OK;
 }
 
+// The DT grid as a 1-D linear texture: the bound kernels fetch their look-ups through the TEX pipe (same values, same L1TEX
+// sector rate -- measured 296 vs 293 G look-ups/s for the plain gather kernel), which leaves the LSU pipe to the shared-memory
+// traffic and shuffles of the inner BnB's owner warp: its queue maintenance no longer queues behind the CTA's own gathers
+// (7.2 k -> 5.7 k cycles per expansion).  GOICP_DT_TEX=0 keeps the plain loads (A/B, and the fallback
+// for grids beyond the device's linear-texture width).  Returns 0 when no texture is in use.
+cudaTextureObject_t dt_texture(goicp_handle* h)
+{
+    static const bool want = !(getenv("GOICP_DT_TEX") && atoi(getenv("GOICP_DT_TEX")) == 0);
+    if (!want || !h->have_dt) return 0;
+    if (h->dt_tex && (h->dt_tex_ptr != h->d_dt.p || h->dt_tex_size != h->dt_size)) { cudaDestroyTextureObject(h->dt_tex); h->dt_tex = 0; h->dt_tex_ptr = nullptr; }
+    if (!h->dt_tex && (h->dt_tex_ptr != h->d_dt.p || h->dt_tex_size != h->dt_size)) {  // (one attempt per grid)
+        h->dt_tex_ptr = h->d_dt.p; h->dt_tex_size = h->dt_size;
+        const size_t n3 = (size_t)h->dt_size * h->dt_size * h->dt_size;
+        cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+        size_t max_width = 0;
+        if (cudaDeviceGetTexture1DLinearMaxWidth(&max_width, &fd, h->p.device) != cudaSuccess || n3 > max_width) { cudaGetLastError(); return 0; }
+        cudaResourceDesc rd; std::memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = h->d_dt.p; rd.res.linear.desc = fd; rd.res.linear.sizeInBytes = n3 * sizeof(float);
+        cudaTextureDesc td; std::memset(&td, 0, sizeof td);
+        td.readMode = cudaReadModeElementType; td.filterMode = cudaFilterModePoint; td.addressMode[0] = cudaAddressModeClamp;
+        if (cudaCreateTextureObject(&h->dt_tex, &rd, &td, nullptr) != cudaSuccess) { h->dt_tex = 0; cudaGetLastError(); }
+    }
+    return h->dt_tex;
+}
+
 int make_const(goicp_handle* h, BnbConst& c)
 {
     if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "distance transform not built (call goicp_build_dt or goicp_set_dt first)");
     if (!h->initialized) { int rc = initialize(h); if (rc) return rc; }
     c.dt.grid = h->d_dt.p; c.dt.S = h->dt_size; c.dt.S2 = h->dt_size * h->dt_size;
+    c.dt.tex = dt_texture(h);
     c.dt.xmin = h->dt_meta[0]; c.dt.ymin = h->dt_meta[1]; c.dt.zmin = h->dt_meta[2]; c.dt.scale = h->dt_meta[3]; c.dt.inv_scale = 1.0 / h->dt_meta[3];
     c.data = h->d_data.p; c.nd = h->nd; c.inlier_num = h->inlier_num; c.do_trim = h->p.do_trim; c.sse_thresh = h->sse_thresh;
     c.tx = h->p.trans_cube[0]; c.ty = h->p.trans_cube[1]; c.tz = h->p.trans_cube[2]; c.tw = h->p.trans_cube[3];
@@ -947,6 +974,7 @@ int goicp_destroy(goicp_handle* h)
         if (h->stream_dt) cudaStreamSynchronize(h->stream_dt);
         h->nccl = nullptr;                        // communicators are shared process-wide (goicp_nccl_init)
         h->d_gather.release(); h->d_share.release();
+        if (h->dt_tex) { cudaDestroyTextureObject(h->dt_tex); h->dt_tex = 0; } h->dt_tex_ptr = nullptr;
         h->d_dt.release(); h->d_data.release(); h->d_kd_nodes.release(); h->d_kd_boxes.release(); h->d_kd_vind.release(); h->d_kd_leaf.release(); h->d_model.release(); h->d_grid_start.release(); h->d_grid_pts.release();
         h->d_tasks.release(); h->d_results.release(); h->d_spill.release(); h->d_cands.release(); h->d_trim_keys.release(); h->d_dbg.release(); h->d_strict.release(); h->d_pairs.release(); h->d_f32a.release(); h->d_f32b.release();
         h->d_i32.release(); h->d_q.release(); h->d_score_scratch.release(); h->d_icp_state.release(); h->d_icp_q.release(); h->d_icp_d2.release(); h->d_icp_stage.release(); h->d_icp_nn.release(); h->d_icp_pos.release(); h->d_icp_keys.release(); h->d_icp_keys2.release(); h->d_icp_hist.release(); h->d_icp_order.release(); h->d_icp_partials.release(); h->d_icp_xch.release();
@@ -1062,7 +1090,7 @@ int goicp_dt_distance(goicp_handle* h, const float* q_xyz, int n, float* dist_ou
     if (!h || !q_xyz || !dist_out || n < 0) return fail(h, GOICP_ERR_INVALID, "dt_distance: bad arguments");
     if (!h->have_dt) return fail(h, GOICP_ERR_INVALID, "dt_distance: no distance transform");
     if (n == 0) return GOICP_OK;
-    DtView dt; dt.grid = h->d_dt.p; dt.S = h->dt_size; dt.S2 = h->dt_size * h->dt_size;
+    DtView dt; dt.tex = 0; dt.grid = h->d_dt.p; dt.S = h->dt_size; dt.S2 = h->dt_size * h->dt_size;
     dt.xmin = h->dt_meta[0]; dt.ymin = h->dt_meta[1]; dt.zmin = h->dt_meta[2]; dt.scale = h->dt_meta[3]; dt.inv_scale = 1.0 / h->dt_meta[3];
     CUDA_TRY(h, h->d_q.reserve((size_t)3 * n));
     CUDA_TRY(h, h->d_f32b.reserve(n));

@@ -19,6 +19,7 @@ struct DtView {
     int S2;                 // S*S
     double xmin, ymin, zmin, scale;
     double inv_scale;       // 1/scale, used only by the search kernels' tree-sum path (see accumulate_point8)
+    cudaTextureObject_t tex; // the same grid as a 1-D linear texture: the bound kernels gather through the TEX pipe (engine.cu: dt_texture); 0 = none, plain loads
 };
 
 // One axis of DT3D::Distance (jly_3ddt.cpp:983-1016): idx = int((q - min)*scale + 0.5) in
@@ -133,7 +134,13 @@ __device__ __forceinline__ void point_residuals8(const DtView& dt, float px, flo
     }
     float d[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) d[j] = __ldg(dt.grid + (zo[(j >> 2) & 1] + yo[(j >> 1) & 1] + xi[j & 1]));
+    if (dt.tex) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] = tex1Dfetch<float>(dt.tex, zo[(j >> 2) & 1] + yo[(j >> 1) & 1] + xi[j & 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] = __ldg(dt.grid + (zo[(j >> 2) & 1] + yo[(j >> 1) & 1] + xi[j & 1]));
+    }
     if ((ax2[0] + ax2[1] + ay2[0] + ay2[1] + az2[0] + az2[1]) != 0.0f) {
         // some child of this point leaves the grid: sqrt(a^2+b^2+c^2)/scale + clamped distance
         // (jly_3ddt.cpp:1025).  The search path multiplies by 1/scale instead of dividing in double

@@ -31,10 +31,14 @@ def _bumpy_surface(n, seed):
     return (u * r[:, None]).astype(np.float32)
 
 
-@pytest.mark.parametrize("cluster,variant", [(1, "lat"), (2, "thr"), (4, "lat"), (8, "lat"), (8, "thr"), (16, "lat"), (16, "thr"), (4, "legacy")])
+@pytest.mark.parametrize("cluster,variant", [(1, "lat"), (2, "thr"), (4, "lat"), (8, "lat"), (8, "thr"), (16, "lat"), (16, "thr"), (4, "legacy"), (4, "lat-notex"), (4, "thr-notex")])
 def test_inner_bnb_every_cluster_size_and_kernel_variant(pkg, small, bunny, cluster, variant, monkeypatch):
     """The 48 known-answer InnerBnB calls of the reference (tests/golden/small_vectors.npz) through clusters of 1..16 CTAs,
-    the low-latency and the two-CTAs-per-SM variants of the pipelined kernel, and the unpipelined kernel."""
+    the low-latency and the two-CTAs-per-SM variants of the pipelined kernel, the unpipelined kernel, and the DT look-ups as
+    plain loads (GOICP_DT_TEX=0) instead of texture fetches."""
+    if variant.endswith("-notex"):                     # plain loads instead of the texture path for the DT look-ups
+        monkeypatch.setenv("GOICP_DT_TEX", "0")
+        variant = variant[:-6]
     if variant == "legacy":
         monkeypatch.setenv("GOICP_NO_PIPELINE", "1")
     else:
