@@ -57,11 +57,16 @@ WORKLOADS = {
                                   ref_register_s=338.6, ref_evals=1696656),
     # BASELINE.json configs[4]: synthetic sweep point -- throughput-bound regime (one bound evaluation = 1e5 look-ups into a
     # 537 MB grid that does not fit L2).  Seeds fixed: model 1, data 2, pose 3.
+    # BASELINE.json configs[3]: test/spanner_goicp.toml as written (mse 1e-4, translation cube [-1,1]^3; noisy + flipped model
+    # against a rotated copy): a throughput-bound search -- 5 305 rotation pops, 19.3 M translation pops, 154 M bound
+    # evaluations to the certificate; 17 034 s (4.7 h) of the unmodified reference on one core of the build container.
+    "spanner_goicp_toml": dict(model="spanner_model_noisy_flipped_s0.02_seed1234.f32", data="spanner_data_rotated_s0.02_seed1235.f32", mse=1e-4, S=300,
+                               trans_cube=[-1.0, -1.0, -1.0, 2.0], ref_register_s=17034.4, ref_evals=153867445),
     "sweep_100k": dict(synth=dict(nm=1_000_000, nd=100_000), mse=1e-4, S=512, ref_register_s=None, ref_evals=None),
     "sweep_10k": dict(synth=dict(nm=100_000, nd=10_000), mse=1e-4, S=300, ref_register_s=None, ref_evals=None),
 }
-KERNEL_NAMES = {1: "inner_bnb_pipelined_kernel<1,1>", 2: "inner_bnb_pipelined_kernel<1,0>", 4: "inner_bnb_pipelined_kernel<0,1>",
-                8: "inner_bnb_pipelined_kernel<0,0>", 16: "inner_bnb_kernel"}
+KERNEL_NAMES = {1: "inner_bnb_pipelined_kernel<1,1,512,1>", 2: "inner_bnb_pipelined_kernel<1,0,512,2>", 4: "inner_bnb_pipelined_kernel<0,1,512,1>",
+                8: "inner_bnb_pipelined_kernel<0,0,512,2>", 16: "inner_bnb_kernel", 32: "inner_bnb_pipelined_kernel<1,0,192,5>", 64: "inner_bnb_pipelined_kernel<0,0,192,5>"}
 L2_BYTES = 126 * 1000 * 1000
 
 
@@ -165,7 +170,7 @@ def cpu_reference_sample(wl, seconds, model=None, data=None):
         model, data = clouds_of(wl)
     if orc.Reference.available():
         rf = orc.Reference()
-        g = rf.create(model, data, wl["mse"], 0.0, wl["S"])
+        g = rf.create(model, data, wl["mse"], 0.0, wl["S"], trans_cube=wl.get("trans_cube"))
         with _Quiet():
             dt_s = rf.build_dt(g)
             counter = ctypes.c_longlong.in_dll(rf.L, "ref_select_calls")
@@ -184,7 +189,7 @@ def cpu_reference_sample(wl, seconds, model=None, data=None):
                 "sample": f"{t1 - t0:.1f} s of GoICP::Register on Nd={len(data)}, Nm={len(model)}, S={wl['S']} (after its first second); DT build excluded ({dt_s:.1f} s)",
                 "dt_build_s": dt_s}
     rs = orc.Restated()
-    g = rs.create(model, data, wl["mse"], 0.0, wl["S"])
+    g = rs.create(model, data, wl["mse"], 0.0, wl["S"], trans_cube=wl.get("trans_cube"))
     t0 = time.perf_counter(); rs.L.go_build_dt(g); dt_s = time.perf_counter() - t0
     rs.L.go_set_budget(g, float(seconds))
     r = rs.register(g)
@@ -199,7 +204,7 @@ def cpu_reference_job(wl):
     model, data = clouds_of(wl)
     if orc.Reference.available():
         rf = orc.Reference()
-        g = rf.create(model, data, wl["mse"], 0.0, wl["S"])
+        g = rf.create(model, data, wl["mse"], 0.0, wl["S"], trans_cube=wl.get("trans_cube"))
         with _Quiet():
             dt_s = rf.build_dt(g)
             counter = ctypes.c_longlong.in_dll(rf.L, "ref_select_calls")
@@ -209,7 +214,7 @@ def cpu_reference_job(wl):
         return {"kind": "reference", "dt_build_s": dt_s, "register_s": t1 - t0, "job_s": dt_s + (t1 - t0),
                 "register_rate": wl["ref_evals"] / (t1 - t0), "select_calls": c1 - c0}
     rs = orc.Restated()
-    g = rs.create(model, data, wl["mse"], 0.0, wl["S"])
+    g = rs.create(model, data, wl["mse"], 0.0, wl["S"], trans_cube=wl.get("trans_cube"))
     t0 = time.perf_counter(); rs.L.go_build_dt(g); dt_s = time.perf_counter() - t0
     r = rs.register(g)
     return {"kind": "port", "dt_build_s": dt_s, "register_s": r["register_s"], "job_s": dt_s + r["register_s"],
@@ -295,7 +300,7 @@ def main():
         print(json.dumps({"impl": "reference", "metric": "goicp_bound_evals_per_sec", "value": reg_rate, "unit": "bound-evals/s",
                           "n_gpus": 0, "steps": len(steps), "warmup": 0, "ms_per_step": None if reg_s is None else 1e3 * reg_s,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                          "data": "reference bunny scans, deterministic subsample (committed fixtures)" if "synth" not in wl else "synthetic (seeded)",
+                          "data": "the reference's own clouds, deterministic subsample (committed fixtures)" if "synth" not in wl else "synthetic (seeded)",
                           "config": config, "time_to_optimum_s": reg_s, "cpu_baseline": base,
                           "e2e": {"value": e2e_v, "unit": "bound-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                   "seconds_per_step": job_s}}))
@@ -326,6 +331,8 @@ def main():
         g.pModel, g.pData = model, data
         g.dt.SIZE = wl["S"]
         g.numerics = args.numerics
+        if "trans_cube" in wl:
+            g.initNodeTrans = wl["trans_cube"]
         if dt_mode is not None:
             g.dt_mode = dt_mode
         if world > 1 and os.environ.get("GOICP_EXCHANGE", "nccl") == "nccl":
@@ -514,7 +521,7 @@ def main():
     out = {"metric": "goicp_bound_evals_per_sec", "value": value, "unit": "bound-evals/s", "n_gpus": world, "steps": args.steps,
            "warmup": warm, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-           "data": "reference bunny scans, deterministic subsample (committed fixtures tests/golden/*.f32)" if "synth" not in wl else "synthetic (seeded closed surface + noisy moved subset)",
+           "data": "the reference's own clouds, deterministic subsample (committed fixtures tests/golden/*.f32)" if "synth" not in wl else "synthetic (seeded closed surface + noisy moved subset)",
            "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
            "time_to_optimum_s": total_s / args.steps, "exit_path": res["exit_path"], "sse": res["sse"],
            "bound_evals_per_step": evals // args.steps, "bound_evals_executed_per_step": executed // args.steps,

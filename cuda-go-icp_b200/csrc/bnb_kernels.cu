@@ -609,6 +609,7 @@ inner_bnb_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* _
         r.pops = own.pops; r.evals = own.evals; r.status = own.status; r.max_heap = own.max_heap;
         r.pad[0] = own.flags; r.pad[1] = ub_pass ? (uint32_t)own.n_cand : 0u;
         r.kcycles = (uint32_t)((clock64() - t_begin) >> 10);
+        r.reuse_gt = 3.402823466e+38f; r.reuse_poplb = 0.0f;       // this kernel does not track it: never reusable
         results[task_id] = r;
     }
 }
@@ -629,15 +630,13 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // arrival that publishes nothing (no fence needed on the arriving side)
 __device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
-constexpr int kGatherThreads = kBnbThreads - 32;
-constexpr int kGatherWarps = kBnbWarps - 1;
 
 // LOWLAT: for rounds bound by their longest inner BnB (not by throughput) the kernel trades the second resident CTA
 // for 128 registers, so that the batched queue maintenance of the owner warp stays out of local memory (local traffic
 // would queue behind the gathers in L1TEX).  Measured on the bunny config: the longest task of a round gets 1.4x
 // faster, the sum of all task cycles 1.5x smaller, with half the resident clusters; the engine picks per round.
-template <bool PTS_SMEM, bool LOWLAT>
-__global__ void __launch_bounds__(kBnbThreads, LOWLAT ? 1 : 2)
+template <bool PTS_SMEM, bool LOWLAT, int THREADS = kBnbThreads, int MINB = (LOWLAT ? 1 : 2)>
+__global__ void __launch_bounds__(THREADS, MINB)
 inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, InnerResult* __restrict__ results,
                            int heap_cap_sm, HeapEntry* __restrict__ spill, int spill_cap, CandList* __restrict__ cands)
 {
@@ -648,7 +647,9 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     const int task_id = blockIdx.x / C;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float red[kGatherWarps][16];
+    constexpr int kVirtWarps = kBnbWarps - 1, kGW = THREADS / 32 - 1;     // virtual / real gather warps
+    static_assert(kVirtWarps % kGW == 0, "the real gather warps must share the 15 virtual ones evenly");
+    __shared__ float red[kVirtWarps][16];
     __shared__ InnerCtrl ctrl;                       // written by the leader into every CTA of the cluster
     __shared__ float partials[kMaxCluster][16];      // leader: one row per CTA
     __shared__ float4 cand_node[kMaxCand];
@@ -669,7 +670,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
 
     if (PTS_SMEM) {
         const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
-        for (int i = tid; i < np; i += kBnbThreads) {
+        for (int i = tid; i < np; i += THREADS) {
             float4 p = __ldg(c.data + p_begin + i);
             pts[i] = make_float4(dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
                                  dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w));
@@ -679,37 +680,46 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
 
     if (warp != 0) {
         // ================================ gather warps ======================================
-        const int gt = tid - 32;
         long long g_waitA = 0, g_gather = 0, g_reduce = 0, g_waitB = 0;      // cycle breakdown (reported when c.dbg is set)
         for (;;) {
             long long g0 = clock64();
             cluster_arrive_relaxed(); cluster_wait();               // (A) next cube published
             if (ctrl.done) break;
             long long g1 = clock64(); g_waitA += g1 - g0;
-            float acc[16];
+            // The sums are formed by kVirtWarps = 15 VIRTUAL gather warps whatever the CTA size: virtual thread g = 32 * vw + lane
+            // adds up the points g, g + 480, ... and its warp reduces by shuffles; a CTA with fewer real gather warps (5 or 3,
+            // the dense variants) lets each of them play 3 or 5 virtual warps in turn.  Same numbers in the same order in every
+            // variant, so the engine's per-round choice of variant (a function of measured cycles) never changes a result.
+#pragma unroll 1
+            for (int v = 0; v < kVirtWarps / kGW; v++) {
+                const int vw = warp - 1 + v * kGW;
+                const int vgt = vw * 32 + lane;
+                float acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) acc[k] = 0.0f;
-            if (PTS_SMEM) {
-                for (int i = gt; i < np; i += kGatherThreads) {
-                    const float4 p = pts[i];
-                    accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+                for (int k = 0; k < 16; k++) acc[k] = 0.0f;
+                if (PTS_SMEM) {
+                    for (int i = vgt; i < np; i += kVirtWarps * 32) {
+                        const float4 p = pts[i];
+                        accumulate_point8(c.dt, p.x, p.y, p.z, p.w, ctrl.tr, acc);
+                    }
+                } else {
+                    const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
+                    for (int i = p_begin + vgt; i < p_end; i += kVirtWarps * 32) {
+                        const float4 p = __ldg(c.data + i);
+                        accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
+                                          dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
+                    }
                 }
-            } else {
-                const float cg_ = task.level >= 0 ? c.cgamma[task.level] : 0.0f;
-                for (int i = p_begin + gt; i < p_end; i += kGatherThreads) {
-                    const float4 p = __ldg(c.data + i);
-                    accumulate_point8(c.dt, dot3_ref(task.R[0], task.R[1], task.R[2], p.x, p.y, p.z), dot3_ref(task.R[3], task.R[4], task.R[5], p.x, p.y, p.z),
-                                      dot3_ref(task.R[6], task.R[7], task.R[8], p.x, p.y, p.z), __fmul_rn(cg_, p.w), ctrl.tr, acc);
-                }
+                if (kGW == kVirtWarps) { g0 = clock64(); g_gather += g0 - g1; }
+                warp_reduce16(acc, lane);
+                if ((lane & 1) == 0) red[vw][(lane >> 1) & 15] = acc[0];
             }
-            g0 = clock64(); g_gather += g0 - g1;
-            warp_reduce16(acc, lane);
-            if ((lane & 1) == 0) red[warp - 1][(lane >> 1) & 15] = acc[0];
-            asm volatile("bar.sync 1, %0;" :: "r"(kGatherThreads) : "memory");
+            if (kGW != kVirtWarps) { g0 = clock64(); g_gather += g0 - g1; }
+            asm volatile("bar.sync 1, %0;" :: "r"(THREADS - 32) : "memory");
             if (warp == 1 && lane < 16) {
                 float s = 0.0f;
 #pragma unroll
-                for (int w = 0; w < kGatherWarps; w++) s += red[w][lane];
+                for (int w = 0; w < kVirtWarps; w++) s += red[w][lane];
                 cluster.map_shared_rank(&partials[0][0], 0)[rank * 16 + lane] = s;
             }
             g1 = clock64(); g_reduce += g1 - g0;
@@ -748,6 +758,8 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     uint32_t pmask = 0, pend_level = 0; unsigned long long pend_base = 0ull; int pend_shift = 0; bool need_pop = false;
     HeapEntry expect; expect.lb = 0.0f; expect.level = 0; expect.path_lo = expect.path_hi = 0;
     bool done = false;
+    // validity range of the result under a smaller initial optErrorT (InnerResult::reuse_*): tracked while opt_t is still the initial value
+    bool first_phase = true; float reuse_gt = 0.0f, reuse_poplb = 0.0f;
 
     auto publish = [&](bool fin) {                                       // lane r writes the control block of CTA r
         if (lane < C) {
@@ -767,6 +779,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
     auto adopt = [&](const HeapEntry& e) {
         pops++;                                                               // tNodeCount++ (:248)
         if (__fsub_rn(opt_t, e.lb) < c.sse_thresh) { done = true; return; }  // :257
+        if (first_phase) reuse_poplb = fmaxf(reuse_poplb, e.lb);
         if (e.level >= (uint32_t)kMaxTransLevel) { done = true; status = 4; return; }
         // corner: replay the reference's float additions parent.x + (j&1)*w down the octant path (:267-269)
         float x = c.tx, y = c.ty, z = c.tz, w = c.tw;
@@ -842,6 +855,16 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         for (int d = 1; d < 8; d <<= 1) { const float o = __shfl_up_sync(kFull, run, d, 8); if (cj >= d && o < run) run = o; }
         if (opt_t < run) run = opt_t;                                                // optErrorT after child cj was looked at
         evals += 8;
+        if (first_phase) {
+            // children the reference looks at while optErrorT is still the caller's: all 8, or those up to the first one whose ub
+            // improves it (that one's ub and the queued lbs before it bound the smaller incumbents this call is also valid for)
+            const unsigned imp = __ballot_sync(kFull, lane < 8 && ub < opt_t);
+            const int jfirst = imp ? __ffs(imp) - 1 : 8;
+            unsigned key = lane < jfirst && lane < 8 && lb < opt_t ? __float_as_uint(lb) : 0u;       // lbs are >= +0: bit patterns order like values
+            if (imp && lane == jfirst) key = __float_as_uint(ub);
+            reuse_gt = fmaxf(reuse_gt, __uint_as_float(__reduce_max_sync(kFull, key)));
+            if (imp) first_phase = false;
+        }
         {
             const float fin = __shfl_sync(kFull, run, 7);
             if (fin < opt_t) {                                                       // taken by the first child that reaches the final value
@@ -924,6 +947,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
                     if (__fsub_rn(opt_t, expect.lb) < c.sse_thresh) done = true;         // :257
                     else if (expect.level >= (uint32_t)kMaxTransLevel) { done = true; status = 4; }
                     else {
+                        if (first_phase) reuse_poplb = fmaxf(reuse_poplb, expect.lb);
                         px = __fadd_rn(px, (wl & 1) ? cw : 0.0f); py = __fadd_rn(py, (wl & 2) ? cw : 0.0f); pz = __fadd_rn(pz, (wl & 4) ? cw : 0.0f);
                         cw = cw / 2; plevel = expect.level; ppath = ((unsigned long long)expect.path_hi << 32) | expect.path_lo;
                     }
@@ -958,6 +982,7 @@ inner_bnb_pipelined_kernel(BnbConst c, const InnerTask* __restrict__ tasks, Inne
         r.pops = pops; r.evals = evals; r.status = status == 5 ? 3 : status; r.max_heap = max_heap;
         r.pad[0] = flags | (status == 5 ? 0x100u : 0u); r.pad[1] = ub_pass ? (uint32_t)n_cand : 0u;
         r.kcycles = (uint32_t)((clock64() - t_begin) >> 10);
+        r.reuse_gt = (status || (flags & 1u)) ? 3.402823466e+38f : reuse_gt; r.reuse_poplb = reuse_poplb;
         results[task_id] = r;
     }
 }
@@ -1209,6 +1234,10 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
         if ((e = conf(inner_bnb_pipelined_kernel<true, true>)) != cudaSuccess) return e;
         if ((e = conf(inner_bnb_pipelined_kernel<false, false>)) != cudaSuccess) return e;
         if ((e = conf(inner_bnb_pipelined_kernel<false, true>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<true, false, 192, 5>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<false, false, 192, 5>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<true, false, 128, 8>)) != cudaSuccess) return e;
+        if ((e = conf(inner_bnb_pipelined_kernel<false, false, 128, 8>)) != cudaSuccess) return e;
     }
     // both carry the select's two global-memory windows as static shared memory (strict_sum.cuh)
     e = cudaFuncSetAttribute(strict_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024 - kStrictStaticSmem);
@@ -1218,9 +1247,10 @@ cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out)
     return e;
 }
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency, unsigned* d_trim_keys, cudaStream_t s)
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, int variant /* 0: 512 threads x 2 CTAs per SM, 1: low latency (512 x 1, 128 registers), 2: 192 x 5, 3: 128 x 8 */, unsigned* d_trim_keys, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
+    const bool low_latency = variant == 1;
     const bool trim = c.inlier_num < c.nd;
     const int per = (c.nd + cluster - 1) / cluster;
     size_t smem = (size_t)heap_cap_sm * sizeof(HeapEntry) + (pts_in_smem ? (size_t)per * sizeof(float4) : 0)
@@ -1237,6 +1267,13 @@ cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerR
     BnbConst cc = c;
     static const bool legacy = getenv("GOICP_NO_PIPELINE") != nullptr;     // A/B switch for profiling
     if (!trim && !legacy) {
+        if (variant >= 2) {
+            cfg.blockDim = dim3(variant == 2 ? 192 : 128);
+            if (variant == 2) return pts_in_smem ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, false, 192, 5>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
+                                                 : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, false, 192, 5>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+            return pts_in_smem ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, false, 128, 8>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
+                               : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, false, 128, 8>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
+        }
         if (pts_in_smem) return low_latency ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)
                                             : cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<true, false>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands);
         return low_latency ? cudaLaunchKernelEx(&cfg, inner_bnb_pipelined_kernel<false, true>, cc, d_tasks, d_results, heap_cap_sm, d_spill, spill_cap, d_cands)

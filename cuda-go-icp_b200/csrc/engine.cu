@@ -74,10 +74,19 @@ struct ChildEval {
     bool skipped = true;            // outside the pi-ball (jly_goicp.cpp:443)
     float R[9];
     InnerResult ub, lb;
-    float ub_opt_error = 0;         // optError the ub pass was run with
+    bool have_ub = false, have_lb = false;   // result present and valid under the current incumbent
+    float ub_opt_error = 0, lb_opt_error = 0;   // optError the pass was run with (or has been re-validated for)
     std::shared_ptr<CandList> cands;    // arg-min contenders of the ub pass (when it has any)
 };
-struct CubeEval { long epoch = -1; ChildEval ch[8]; };
+struct CubeEval {
+    long epoch = -1; bool committed = false; ChildEval ch[8];
+    bool complete() const { for (const ChildEval& c : ch) if (!c.skipped && !(c.have_ub && c.have_lb)) return false; return true; }
+};
+// Would this inner BnB, run with initial optErrorT = e_old, have gone exactly the same way with e_new < e_old?  (InnerResult::reuse_*)
+inline bool reusable_under(const InnerResult& r, float e_new, float sse_thresh)
+{
+    return r.status == 0 && e_new > r.reuse_gt && !((float)(e_new - r.reuse_poplb) < sse_thresh);
+}
 
 // Angle-axis vector of the cube centre -> rotation matrix, in float with glibc sinf/cosf exactly
 // like jly_goicp.cpp:437-467.  false = cube wholly outside the pi-ball.
@@ -191,6 +200,8 @@ struct goicp_handle {
     // multi-GPU exchange
     goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
     bool low_latency = true;             // inner-BnB kernel variant of the next round (see run_inner_batch)
+    int dense = 0;                       // when not low_latency: 0 = 512 threads x 2 CTAs per SM, 2 = 192 threads x 5, 3 = 128 x 8
+    double pred_max = 0, pred_sum = 0;   // expected cost of the next batch's longest task / of all its tasks (parent pops; 0 = unknown)
     NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather; DevBuf<unsigned char> d_share;      // native exchange: all-gather of the round's result records on the stream
 
     // timing
@@ -438,7 +449,7 @@ int make_const(goicp_handle* h, BnbConst& c)
 // Shared-memory plan of the persistent inner-BnB kernel: rotated points on chip when two CTAs
 // per SM still fit, the rest of the per-CTA budget goes to the priority queue.
 struct InnerPlan { bool pts_smem; bool keys_smem; int heap_cap_sm; int cluster; };
-InnerPlan plan_inner(const goicp_handle* h)
+InnerPlan plan_inner(const goicp_handle* h, int ctas_per_sm = 2)
 {
     InnerPlan p;
     // Cluster size: one expansion step costs 8*Nd scattered lookups and an SM retires ~1 per clock,
@@ -453,7 +464,7 @@ InnerPlan plan_inner(const goicp_handle* h)
     // Signed arithmetic: what does not fit next to a 16 KB queue stays in global memory (the trimming keys first claim the
     // space -- the radix select reads them five times per expansion --, then the rotated points).
     const long stat = (long)h->max_smem_optin - h->inner_dyn_smem;
-    const long per_cta = (long)h->max_smem_optin / 2 - stat - 2048;
+    const long per_cta = (long)h->max_smem_optin / ctas_per_sm - stat - 2048;
     const long per = (h->nd + cl - 1) / cl;
     const long pts = per * (long)sizeof(float4);
     const bool trim = h->initialized && h->inlier_num < h->nd;
@@ -512,7 +523,28 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
 {
     if (n <= 0) return GOICP_OK;
     int rc = ensure_task_buffers(h, (size_t)n + 64); if (rc) return rc;
-    const InnerPlan plan = plan_inner(h);
+    const bool trim_run = c.inlier_num < c.nd;
+    {
+        // Kernel variant of this batch.  Three shapes of the same kernel (same sums in the same order, so the choice never
+        // changes a result): low latency (512 threads, 1 CTA per SM, 128 registers), 512 x 2 and the dense one, 192 x 5.  Per
+        // task the denser shapes are slower (measured on the bunny and spanner configs: 1.4x / 2.0x) and their summed task
+        // cycles larger (1.45x / 2.1x) but 2 / 5 clusters share an SM: a batch costs about max(longest task, sum / resident
+        // clusters) in each.  The expected cost of a task is what the same pass cost on the parent cube (pops; the caller
+        // leaves it in pred_max / pred_sum); without a forecast the previous batch's measured cycles decide (below).
+        static const char* force = getenv("GOICP_BNB_VARIANT");       // "lat" / "thr" / "q5" / "q3": pin the variant (experiments)
+        if (force) { h->low_latency = force[0] == 'l'; h->dense = force[0] == 'q' ? (force[1] == '3' ? 3 : 2) : 0; }
+        else if (h->pred_sum > 0 && !trim_run) {
+            const int Wq = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
+            const int clq = plan_inner(h).cluster;
+            const double slots = std::max(1, h->sm_count / clq), sum = h->pred_sum / Wq;
+            const double t_lat = std::max(h->pred_max, sum / slots), t_thr = std::max(1.4 * h->pred_max, 1.45 * sum / (2 * slots)),
+                         t_q = std::max(2.0 * h->pred_max, 2.1 * sum / (5 * slots));
+            h->low_latency = t_lat <= t_thr && t_lat <= t_q;
+            h->dense = !h->low_latency && t_q < t_thr ? 2 : 0;
+        }
+    }
+    const int variant = h->low_latency || trim_run ? (h->low_latency ? 1 : 0) : h->dense;
+    const InnerPlan plan = plan_inner(h, variant == 2 ? 5 : (variant == 3 ? 8 : 2));
     const int W = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
     const int r = W > 1 ? h->p.rank : 0;
     const int per_rank = (n + W - 1) / W;
@@ -534,7 +566,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         const bool trim = c.inlier_num < c.nd;
         {
             static const bool legacy = getenv("GOICP_NO_PIPELINE") != nullptr;
-            h->bnb_variants |= (trim || legacy) ? 16 : (plan.pts_smem ? (h->low_latency ? 1 : 2) : (h->low_latency ? 4 : 8));
+            h->bnb_variants |= (trim || legacy) ? 16 : (variant >= 2 ? (plan.pts_smem ? 32 : 64) : (plan.pts_smem ? (variant == 1 ? 1 : 2) : (variant == 1 ? 4 : 8)));
         }
         if (trim && !plan.keys_smem) {
             // trimming a cloud whose keys do not fit in shared memory: per-CTA key slabs in global memory, the round launched
@@ -544,11 +576,11 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             CUDA_TRY(h, h->d_trim_keys.reserve(per_task * chunk));
             for (int off = 0; off < mine; off += chunk) {
                 CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p + off, h->d_results.p + off, std::min(chunk, mine - off), plan.cluster, plan.pts_smem, plan.heap_cap_sm,
-                                             h->d_spill.p, h->spill_cap, h->d_cands.p + off, h->low_latency, h->d_trim_keys.p, h->stream));
+                                             h->d_spill.p, h->spill_cap, h->d_cands.p + off, variant, h->d_trim_keys.p, h->stream));
                 h->launches++;
             }
         } else {
-            CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, h->low_latency, nullptr, h->stream));
+            CUDA_TRY(h, launch_inner_bnb(cdbg, h->d_tasks.p, h->d_results.p, mine, plan.cluster, plan.pts_smem, plan.heap_cap_sm, h->d_spill.p, h->spill_cap, h->d_cands.p, variant, nullptr, h->stream));
             h->launches++;
         }
     }
@@ -596,15 +628,16 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         // Variant for the next round, from this round's task cycle counts (all ranks' tasks).  In low-latency units
         // (measured ratios on the bunny config: a task is 1.43x slower, the sum of task cycles 1.54x larger in the
         // two-CTAs-per-SM variant) a round costs about max(longest task, sum / resident clusters) in either variant.
-        static const char* force = getenv("GOICP_BNB_VARIANT");       // "lat" / "thr": pin the variant (experiments)
         double maxc = 0, sumc = 0;
         for (int t = 0; t < n; t++) { const double k = h->h_results[t].kcycles; sumc += k; if (k > maxc) maxc = k; }
-        if (!h->low_latency) { maxc /= 1.43; sumc /= 1.54; }
+        if (variant == 0) { maxc /= 1.43; sumc /= 1.54; }
+        else if (variant >= 2) { maxc /= 2.0; sumc /= 2.1; }
         const double per_rank_sum = sumc / W;
         const double res_lat = std::max(1, h->sm_count / plan.cluster), res_thr = std::max(1, 2 * h->sm_count / plan.cluster);
         const double t_lat = std::max(maxc, per_rank_sum / res_lat), t_thr = std::max(1.43 * maxc, 1.54 * per_rank_sum / res_thr);
-        h->low_latency = force ? force[0] == 'l' : t_lat <= t_thr;
+        h->low_latency = t_lat <= t_thr; h->dense = 0;
     }
+    h->pred_max = h->pred_sum = 0;                                   // a forecast is for one batch
     if (lists) {
         // contender lists of the upper-bound passes that have any (local tasks only; a rank that
         // needs a list it does not hold re-runs that one task, see commit)
@@ -1435,6 +1468,8 @@ int goicp_register(goicp_handle* h, goicp_result* out)
 
     std::unordered_map<CubeKey, CubeEval, CubeKeyHash> cache;
     long epoch = 0;
+    const bool reuse_ok = !(getenv("GOICP_NO_REUSE") && atoi(getenv("GOICP_NO_REUSE")) != 0);      // A/B switch (tests): 1 = drop everything on an improvement
+    long st_cubes_evaluated = 0, st_cubes_dropped_by_improvement = 0, st_tasks = 0, st_tasks_reused = 0, st_tasks_kept = 0, st_tasks_invalid = 0;       // GOICP_ROUND_STATS
     // default speculation width: ~4 SMs' worth of clusters per cube (36 cubes = 576 inner BnBs per round on 148 SMs)
     int spec = h->p.spec_cubes > 0 ? h->p.spec_cubes : std::max(1, h->sm_count / 4);
     if ((h->xchg || h->nccl) && h->p.world_size > 1) spec *= h->p.world_size;
@@ -1451,7 +1486,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 const CubeKey k = key_of(n);
                 if (k == fk) continue;
                 auto it = cache.find(k);
-                if (it != cache.end() && it->second.epoch == epoch) continue;
+                if (it != cache.end() && it->second.epoch == epoch && it->second.complete()) continue;
                 if ((E - n.lb) <= h->sse_thresh) continue;         // would certify, never expanded
                 cand.push_back(&n);
             }
@@ -1460,7 +1495,8 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                               [&](const RotNode* x, const RotNode* y) { return lower(*y, *x); });
             for (size_t i = 0; i < want; i++) cubes.push_back(*cand[i]);
         }
-        // task list: for every in-ball child an upper-bound pass and a lower-bound pass
+        // task list: for every in-ball child an upper-bound pass and a lower-bound pass -- those the cache does not already
+        // hold (a cube evaluated before the last improvement keeps the passes that are provably unchanged, see revalidate)
         struct Slot { size_t cube; int child; int pass; };
         std::vector<Slot> slots;
         std::vector<CubeEval> evs(cubes.size());
@@ -1469,6 +1505,10 @@ int goicp_register(goicp_handle* h, goicp_result* out)
         for (size_t ci = 0; ci < cubes.size(); ci++) {
             const RotNode& P = cubes[ci];
             if (P.l + 1 >= kMaxRotLevel) return fail(h, GOICP_ERR_DEPTH, "rotation search reached level 20 (the reference indexes maxRotDis out of bounds there)");
+            {
+                auto it = cache.find(key_of(P));
+                if (it != cache.end() && it->second.epoch == epoch) evs[ci] = it->second;
+            }
             const float w = P.w / 2;
             for (int j = 0; j < 8; j++) {
                 const float a = P.a + (j & 1) * w, b = P.b + (j >> 1 & 1) * w, cc = P.c + (j >> 2 & 1) * w;
@@ -1476,6 +1516,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                 ce.skipped = !cube_rotation(a, b, cc, w, ce.R);
                 if (ce.skipped) continue;
                 for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 0 ? ce.have_ub : ce.have_lb) { st_tasks_reused++; continue; }
                     InnerTask& t = h->h_tasks[n++];
                     std::memcpy(t.R, ce.R, sizeof ce.R);
                     t.level = pass == 0 ? -1 : P.l + 1;              // maxRotDis[nodeRot.l] (jly_goicp.cpp:551)
@@ -1497,14 +1538,17 @@ int goicp_register(goicp_handle* h, goicp_result* out)
             std::vector<InnerTask> tk(n); std::vector<Slot> sl(n);
             for (int t = 0; t < n; t++) { tk[t] = h->h_tasks[ord[t]]; sl[t] = slots[ord[t]]; }
             std::memcpy(h->h_tasks, tk.data(), sizeof(InnerTask) * n); slots.swap(sl);
+            h->pred_max = n > 0 ? (double)cost(0) : 0; h->pred_sum = 0;
+            for (int t = 0; t < n; t++) h->pred_sum += (double)cost(t);
         }
         std::vector<std::shared_ptr<CandList>> lists;
         rcl = run_inner_batch(h, c, n, &res.bound_evals_executed, &lists, &res.bound_evals_executed_local); if (rcl) return rcl;
-        res.rounds++;
+        res.rounds++; st_cubes_evaluated += (long)cubes.size(); st_tasks += n;
         for (int t = 0; t < n; t++) {
             ChildEval& ce = evs[slots[t].cube].ch[slots[t].child];
             (slots[t].pass == 0 ? ce.ub : ce.lb) = h->h_results[t];
-            if (slots[t].pass == 0) { ce.cands = lists[t]; ce.ub_opt_error = E; }
+            if (slots[t].pass == 0) { ce.cands = lists[t]; ce.ub_opt_error = E; ce.have_ub = true; }
+            else { ce.lb_opt_error = E; ce.have_lb = true; }
         }
         for (size_t ci = 0; ci < cubes.size(); ci++) { evs[ci].epoch = epoch; cache[key_of(cubes[ci])] = evs[ci]; }
         return GOICP_OK;
@@ -1522,10 +1566,11 @@ int goicp_register(goicp_handle* h, goicp_result* out)
         }
         {
             auto it = cache.find(key_of(P));
-            if (it == cache.end() || it->second.epoch != epoch) { rc = evaluate_round(P); if (rc) return rc; }
+            if (it == cache.end() || it->second.epoch != epoch || !it->second.complete()) { rc = evaluate_round(P); if (rc) return rc; }
         }
         std::pop_heap(heap.begin(), heap.end(), lower); heap.pop_back(); res.rot_pops++;
         const CubeKey pk = key_of(P);
+        cache[pk].committed = true;
         int j0 = 0; bool skip_ub = false;
         bool restart = true;
         while (restart && exit_path == GOICP_EXIT_NONE) {
@@ -1573,8 +1618,47 @@ int goicp_register(goicp_handle* h, goicp_result* out)
                             }
                             heap.swap(fresh);
                         }
-                        epoch++; cache.clear();
-                        rc = evaluate_round(P); if (rc) return rc;                        // rest of P under the new E
+                        {
+                            // Speculative results were computed under the old incumbent.  An inner BnB depends on its initial
+                            // optErrorT only through decisions taken before its own first improvement; the kernel reports the
+                            // range of smaller values for which every one of them comes out the same (InnerResult::reuse_*).
+                            // Passes inside that range are kept -- same pops, same arg-min, and a value that was the initial
+                            // optErrorT itself becomes the new one --, the others are run again when their cube is needed.
+                            // (Measured on test/spanner_goicp.toml: one improvement of 8e-4 relative after 1 921 rotation pops
+                            // found 2 490 evaluated cubes waiting in the cache -- a third of the run's work.)
+                            long kept = 0, invalid = 0, dropped = 0;
+                            for (auto it = cache.begin(); it != cache.end();) {
+                                CubeEval& cev = it->second;
+                                if (cev.committed && !(it->first == pk)) { it = cache.erase(it); continue; }
+                                bool any = false;
+                                for (int q = 0; q < 8; q++) {
+                                    ChildEval& cq = cev.ch[q];
+                                    if (cq.skipped) continue;
+                                    if (it->first == pk && (q < j || (q == j))) {       // P itself: children before j are done, child j's ub pass too
+                                        if (q < j) { cq.have_ub = cq.have_lb = true; continue; }
+                                        cq.have_ub = true;
+                                    } else if (cq.have_ub) {
+                                        if (reuse_ok && reusable_under(cq.ub, E, h->sse_thresh) && !(cq.ub.pad[0] & 1u)) {
+                                            if (cq.ub.value == cq.ub_opt_error) cq.ub.value = E;
+                                            cq.ub_opt_error = E; kept++; any = true;
+                                        } else { cq.have_ub = false; cq.cands.reset(); invalid++; }
+                                    }
+                                    if (cq.have_lb) {
+                                        if (reuse_ok && reusable_under(cq.lb, E, h->sse_thresh)) {
+                                            if (cq.lb.value == cq.lb_opt_error) cq.lb.value = E;
+                                            cq.lb_opt_error = E; kept++; any = true;
+                                        } else { cq.have_lb = false; invalid++; }
+                                    }
+                                }
+                                if (!any && !(it->first == pk)) { dropped++; it = cache.erase(it); continue; }
+                                cev.epoch = epoch + 1;
+                                ++it;
+                            }
+                            st_cubes_dropped_by_improvement += dropped; st_tasks_kept += kept; st_tasks_invalid += invalid;
+                            if (getenv("GOICP_ROUND_STATS")) fprintf(stderr, "[improvement] after %lld rotation pops: E -> %.9g; cached passes kept %ld, to be re-run %ld, cubes dropped %ld\n", (long long)res.rot_pops, (double)E, kept, invalid, dropped);
+                        }
+                        epoch++;
+                        if (!cache[pk].complete()) { rc = evaluate_round(P); if (rc) return rc; }                        // rest of P under the new E
                         j0 = j; skip_ub = true; restart = true;
                         break;
                     }
@@ -1597,6 +1681,12 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     res.strict_resolves = h->strict_resolves; res.contender_overflows = h->cand_overflows; res.bnb_kernel_variants = h->bnb_variants;
     res.seconds_dt_score = h->t_score; res.seconds_strict = h->t_strict; res.seconds_setup = h->t_setup;
     res.seconds_host = res.seconds_total - h->t_setup - h->t_kernels - h->t_icp - h->t_score - h->t_strict;
+    if (getenv("GOICP_ROUND_STATS")) {
+        long left = 0;
+        for (const auto& kv : cache) left += !kv.second.committed;
+        fprintf(stderr, "[register] cubes evaluated %ld (tasks run %ld, taken from the cache across an improvement %ld of %ld kept; %ld invalidated) in %d rounds, committed %lld, cubes dropped by an improvement %ld, evaluated but never popped %ld\n",
+                st_cubes_evaluated, st_tasks, st_tasks_reused, st_tasks_kept, st_tasks_invalid, (int)res.rounds, (long long)res.rot_pops, st_cubes_dropped_by_improvement, left);
+    }
     if (getenv("GOICP_ROUND_STATS"))
         fprintf(stderr, "[register] total %.3f s: setup (upload, gamma table, kd-tree) %.3f, BnB kernels + exchange %.3f, ICP %.3f, DT scoring %.3f, strict resolves %.3f (%lld), rest (host commit, copies) %.3f\n",
                 res.seconds_total, h->t_setup, h->t_kernels, h->t_icp, h->t_score, h->t_strict, (long long)h->strict_resolves,

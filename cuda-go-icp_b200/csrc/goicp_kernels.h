@@ -10,7 +10,7 @@ cudaError_t launch_pair_bounds(const BnbConst& c, const PairTask* d_tasks, int n
 cudaError_t launch_expand_bounds(const BnbConst& c, const PairTask* d_tasks, int n, float* d_out16, cudaStream_t s);
 cudaError_t inner_bnb_configure(int smem_optin, int* max_dyn_out);
 cudaError_t launch_inner_bnb(const BnbConst& c, const InnerTask* d_tasks, InnerResult* d_results, int n, int cluster,
-                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, bool low_latency,
+                             bool pts_in_smem, int heap_cap_sm, HeapEntry* d_spill, int spill_cap, CandList* d_cands, int variant,
                              unsigned* d_trim_keys /* trimming: per-CTA slabs of 8 * ceil(nd/cluster) keys in global memory, or null = shared memory */, cudaStream_t s);
 cudaError_t launch_select_test(float* d_a, int n, int k, int* d_idx, int threads, int smem_limit, bool allow_smem, cudaStream_t s);
 int strict_smem_mode(int nd, int smem_limit);        // 2 / 1 / 0: see bnb_kernels.cu

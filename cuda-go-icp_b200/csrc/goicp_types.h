@@ -44,6 +44,13 @@ struct InnerResult {
     uint32_t max_heap;
     uint32_t pad[2];     // [0] flags, [1] number of arg-min contenders (ub pass)
     uint32_t kcycles;    // SM cycles / 1024 this task took
+    // For which smaller incumbents E' < opt_error the call would have run EXACTLY the same way (same pops, same pushes, same
+    // arg-min; `value` the same unless it is opt_error itself, in which case it becomes E'): every decision that involves the
+    // initial optErrorT directly is taken before the call's first own improvement, and it comes out the same iff
+    //   E' > reuse_gt       (no queued child's lb lies in [E', opt_error); the first improving ub is below E' too), and
+    //   E' - reuse_poplb >= SSEThresh in float (no popped node of that phase would have ended the call, jly_goicp.cpp:257).
+    // The engine keeps speculative results across an improvement of the incumbent when both hold (engine.cu: revalidate).
+    float reuse_gt, reuse_poplb;
 };
 
 // Translation-BnB heap entry (16 B): lb, level, and the octant path from the root cube.

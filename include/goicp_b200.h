@@ -126,7 +126,8 @@ typedef struct {
     double seconds_host;                 /* the rest of seconds_total: the host side of the rotation frontier (queue, prune, commit in the
                                             reference's order, task lists) -- the part a device-side frontier would absorb */
     int64_t bnb_kernel_variants;         /* which translation-BnB kernels ran: bit 0 inner_bnb_pipelined_kernel<1,1> (points in shared memory,
-                                            low-latency), bit 1 <1,0>, bit 2 <0,1>, bit 3 <0,0>, bit 4 inner_bnb_kernel (trimming / GOICP_NO_PIPELINE) */
+                                            low-latency), bit 1 <1,0>, bit 2 <0,1>, bit 3 <0,0>, bit 4 inner_bnb_kernel (trimming / GOICP_NO_PIPELINE),
+                                            bit 5 / 6 the dense shape <1,0,192,5> / <0,0,192,5> (192 threads, five CTAs per SM) */
 } goicp_result;
 
 typedef struct {

@@ -3,6 +3,7 @@ weak" 1-5): every cluster size and both inner-BnB kernels against the reference'
 (rotated points / trimming keys in global memory) against the oracle, the reference-order DT at S = 512, GoICP::doTrim =
 false, poll / cancel from a second thread, and a 2-rank NCCL registration (skipped with one device).
 """
+import json
 import os
 import subprocess
 import sys
@@ -31,11 +32,12 @@ def _bumpy_surface(n, seed):
     return (u * r[:, None]).astype(np.float32)
 
 
-@pytest.mark.parametrize("cluster,variant", [(1, "lat"), (2, "thr"), (4, "lat"), (8, "lat"), (8, "thr"), (16, "lat"), (16, "thr"), (4, "legacy"), (4, "lat-notex"), (4, "thr-notex")])
+@pytest.mark.parametrize("cluster,variant", [(1, "lat"), (2, "thr"), (4, "lat"), (8, "lat"), (8, "thr"), (16, "lat"), (16, "thr"), (4, "legacy"), (4, "lat-notex"), (4, "thr-notex"),
+                                             (2, "q5"), (4, "q5"), (16, "q5"), (4, "q3")])
 def test_inner_bnb_every_cluster_size_and_kernel_variant(pkg, small, bunny, cluster, variant, monkeypatch):
     """The 48 known-answer InnerBnB calls of the reference (tests/golden/small_vectors.npz) through clusters of 1..16 CTAs,
-    the low-latency and the two-CTAs-per-SM variants of the pipelined kernel, the unpipelined kernel, and the DT look-ups as
-    plain loads (GOICP_DT_TEX=0) instead of texture fetches."""
+    the low-latency, the two-CTAs-per-SM and the dense (192 threads x 5 / 128 x 8 CTAs per SM: "q5" / "q3") shapes of the
+    pipelined kernel, the unpipelined kernel, and the DT look-ups as plain loads (GOICP_DT_TEX=0) instead of texture fetches."""
     if variant.endswith("-notex"):                     # plain loads instead of the texture path for the DT look-ups
         monkeypatch.setenv("GOICP_DT_TEX", "0")
         variant = variant[:-6]
@@ -66,6 +68,38 @@ def test_inner_bnb_every_cluster_size_and_kernel_variant(pkg, small, bunny, clus
         else:
             assert o[0] == pytest.approx(row[11], rel=1e-5, abs=1e-6)
         assert _close_counts(o[5], int(row[16])) and _close_counts(o[6], int(row[17]))
+
+
+@pytest.mark.parametrize("name", ["spanner_s0.02_mse3e-4", "bunny_s0.033_mse1e-3", "bunny_s0.1_mse5e-4"])
+def test_kernel_shape_and_result_reuse_change_nothing(pkg, runs, name):
+    """The engine picks the inner-BnB kernel shape per round from cost forecasts and measured cycles, and keeps speculative
+    results across an improvement of the incumbent when the kernel's validity range (InnerResult::reuse_*) says the call
+    would have run identically.  Neither may change anything: every forced shape, and reuse switched off (GOICP_NO_REUSE=1:
+    every cached result dropped at an improvement, as the reference-order semantics trivially allow), must end on the same
+    pose bits, SSE, exit path and committed counters as the default."""
+    code = ("import importlib, json, sys, numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "pkg = importlib.import_module('cuda-go-icp_b200')\n"
+            "gold = json.load(open(%r))[%r]; ld = lambda n: np.fromfile(%r + '/' + n, np.float32).reshape(-1, 3)\n"
+            "g = pkg.GoICP(gold['mse']); g.pModel, g.pData = ld(gold['model']), ld(gold['data']); g.trimFraction = gold['trim']\n"
+            "if 'trans_cube' in gold: g.initNodeTrans = gold['trans_cube']\n"
+            "g.BuildDT(); g.Register(); r = g.result\n"
+            "json.dump({'R': r['R'].tobytes().hex(), 't': r['t'].tobytes().hex(), 'sse': float(r['sse']), 'exit': r['exit_path'], 'rot_pops': int(r['rot_pops']),\n"
+            "           'trans_pops': int(r['trans_pops']), 'evals': int(r['bound_evals']), 'executed': int(r['bound_evals_executed'])}, open(sys.argv[1], 'w'))\n"
+            % (ROOT, os.path.join(ROOT, "tests", "golden", "goicp_runs.json"), name, os.path.join(ROOT, "tests", "golden")))
+    got = {}
+    for tag, env in {"default": {}, "lat": {"GOICP_BNB_VARIANT": "lat"}, "thr": {"GOICP_BNB_VARIANT": "thr"}, "dense": {"GOICP_BNB_VARIANT": "q5"},
+                     "no_reuse": {"GOICP_NO_REUSE": "1"}}.items():
+        out_path = os.path.join(ROOT, "gpurun_out", f"_shape_{name}_{tag}.json")
+        os.makedirs(os.path.dirname(out_path), exist_ok=True)
+        subprocess.run([sys.executable, "-c", code, out_path], check=True, env=dict(os.environ, **env))
+        got[tag] = json.load(open(out_path))
+        os.remove(out_path)
+    ref = {k: v for k, v in got["default"].items() if k != "executed"}
+    for tag, g in got.items():
+        assert {k: v for k, v in g.items() if k != "executed"} == ref, (tag, g, ref)
+    assert got["default"]["executed"] <= got["no_reuse"]["executed"]
+    assert _close_counts(got["default"]["rot_pops"], runs[name]["rot_pops"]) and got["default"]["exit"] == runs[name]["exit_path"]
 
 
 @pytest.mark.parametrize("nd,trim,cluster", [(100000, 0.0, 0), (100000, 0.1, 0), (30000, 0.1, 2), (90000, 0.0, 8)])
