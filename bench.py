@@ -244,6 +244,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the certified / reference-DT / gather side measurements")
+    ap.add_argument("--e2e-samples", type=int, default=0, help="timed end-to-end passes (default: 3..5 by --steps); the passes are whole jobs, so long workloads may want fewer")
     ap.add_argument("--numerics", type=int, default=0, help="goicp_numerics flags of the engine (0 = strict, the library default; 3 = tree sums + parallel ICP moments)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -419,8 +420,8 @@ def main():
     value = evals / total_s
 
     # ---- e2e through the C ABI from host buffers, default configuration
-    n_e2e = max(3, min(args.steps, 5))
-    e2e = timed_e2e(n_e2e, 2)
+    n_e2e = args.e2e_samples if args.e2e_samples > 0 else max(3, min(args.steps, 5))
+    e2e = timed_e2e(n_e2e, 2 if args.e2e_samples == 0 else 1)
     e2e["includes"] = "create + H2D clouds + GPU DT build (library default: exact EDT with the reference's corner seed) + Register + result D2H"
     out_extra = {}
     S = wl["S"]

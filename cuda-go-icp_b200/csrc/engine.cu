@@ -201,6 +201,7 @@ struct goicp_handle {
     goicp_allgather_fn xchg = nullptr; void* xchg_user = nullptr; int xchg_device = 0;
     bool low_latency = true;             // inner-BnB kernel variant of the next round (see run_inner_batch)
     int dense = 0;                       // when not low_latency: 0 = 512 threads x 2 CTAs per SM, 2 = 192 threads x 5, 3 = 128 x 8
+    double prev_max_pops = 0;            // longest inner BnB of the previous batch (pops)
     double pred_max = 0, pred_sum = 0;   // expected cost of the next batch's longest task / of all its tasks (parent pops; 0 = unknown)
     NcclComm nccl = nullptr; DevBuf<InnerResult> d_gather; DevBuf<unsigned char> d_share;      // native exchange: all-gather of the round's result records on the stream
 
@@ -533,17 +534,22 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         // leaves it in pred_max / pred_sum); without a forecast the previous batch's measured cycles decide (below).
         static const char* force = getenv("GOICP_BNB_VARIANT");       // "lat" / "thr" / "q5" / "q3": pin the variant (experiments)
         if (force) { h->low_latency = force[0] == 'l'; h->dense = force[0] == 'q' ? (force[1] == '3' ? 3 : 2) : 0; }
-        else if (h->pred_sum > 0 && !trim_run) {
+        else if (h->pred_sum > 0 && !trim_run && !(getenv("GOICP_BNB_FORECAST") && atoi(getenv("GOICP_BNB_FORECAST")) == 0)) {
             const int Wq = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
             const int clq = plan_inner(h).cluster;
             const double slots = std::max(1, h->sm_count / clq), sum = h->pred_sum / Wq;
-            const double t_lat = std::max(h->pred_max, sum / slots), t_thr = std::max(1.4 * h->pred_max, 1.45 * sum / (2 * slots)),
-                         t_q = std::max(2.0 * h->pred_max, 2.1 * sum / (5 * slots));
+            // the longest task is the hard one to foresee (a child's search can be ten times its parent's): the forecast is
+            // floored by half the previous batch's longest (fitted on per-round times of six golden runs in all three shapes,
+            // profiles/r2x_shape_rule_fit.txt: 3 % above the per-round oracle on average, the cycles-only rule 10 %)
+            const double pm = std::max(h->pred_max, 0.5 * h->prev_max_pops);
+            const double t_lat = std::max(pm, sum / slots), t_thr = std::max(1.4 * pm, 1.45 * sum / (2 * slots)),
+                         t_q = std::max(2.0 * pm, 2.1 * sum / (5 * slots));
             h->low_latency = t_lat <= t_thr && t_lat <= t_q;
             h->dense = !h->low_latency && t_q < t_thr ? 2 : 0;
         }
     }
     const int variant = h->low_latency || trim_run ? (h->low_latency ? 1 : 0) : h->dense;
+    const double pred_max_used = h->pred_max, pred_sum_used = h->pred_sum;
     const InnerPlan plan = plan_inner(h, variant == 2 ? 5 : (variant == 3 ? 8 : 2));
     const int W = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
     const int r = W > 1 ? h->p.rank : 0;
@@ -614,6 +620,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
     if (getenv("GOICP_ROUND_STATS")) {
         uint32_t maxc = 0, maxp = 0, sump = 0, maxh = 0; uint64_t sumc = 0; int arg = 0, flagged = 0;
         for (int t = 0; t < n; t++) { const InnerResult& q = h->h_results[t]; sumc += q.kcycles; sump += q.pops; if (q.kcycles > maxc) { maxc = q.kcycles; arg = t; } if (q.pops > maxp) maxp = q.pops; if (q.max_heap > maxh) maxh = q.max_heap; if (q.pad[1]) flagged++; }
+        fprintf(stderr, "[round] shape %d forecast max %.0f sum %.0f; ", variant, pred_max_used, pred_sum_used);
         fprintf(stderr, "[round] tasks %d kernel %.3f ms; slowest task %.3f Mcyc (pops %u, level %d); max pops %u; total pops %u; sum task cycles %.1f Mcyc; max heap %u; tasks with contenders %d\n",
                 n, ms, maxc * 1024e-6, h->h_results[arg].pops, h->h_tasks[arg].level, maxp, sump, sumc * 1024e-6, maxh, flagged);
         if (W == 1) {
@@ -638,6 +645,7 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         h->low_latency = t_lat <= t_thr; h->dense = 0;
     }
     h->pred_max = h->pred_sum = 0;                                   // a forecast is for one batch
+    { double mp = 0; for (int t = 0; t < n; t++) mp = std::max(mp, (double)h->h_results[t].pops); h->prev_max_pops = mp; }
     if (lists) {
         // contender lists of the upper-bound passes that have any (local tasks only; a rank that
         // needs a list it does not hold re-runs that one task, see commit)
@@ -1432,7 +1440,7 @@ int goicp_register(goicp_handle* h, goicp_result* out)
     if (!h || !out) return fail(h, GOICP_ERR_INVALID, "register: bad arguments");
     std::memset(out, 0, sizeof *out);
     h->cancel_flag.store(0);
-    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->t_score = h->t_strict = 0; h->strict_resolves = 0; h->cand_overflows = 0; h->bnb_variants = 0;
+    h->t_kernels = 0; h->t_icp = 0; h->launches = 0; h->low_latency = true; h->dense = 0; h->prev_max_pops = 0; h->pred_max = h->pred_sum = 0; h->t_score = h->t_strict = 0; h->strict_resolves = 0; h->cand_overflows = 0; h->bnb_variants = 0;
     if (h->p.search_mode == GOICP_SEARCH_FGOICP) return register_fgoicp(h, out);
     const double t_begin = now_s();
     h->initialized = false;
