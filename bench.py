@@ -327,9 +327,9 @@ def main():
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().numpy().tobytes())
 
-    def make_engine(mse=None, dt_mode=None):
+    def make_engine(mse=None, dt_mode=None, wl=wl, clouds=None):
         g = pkg.GoICP(wl["mse"] if mse is None else mse, device=local_rank)
-        g.pModel, g.pData = model, data
+        g.pModel, g.pData = clouds if clouds is not None else (model, data)
         g.dt.SIZE = wl["S"]
         g.numerics = args.numerics
         if "trans_cube" in wl:
@@ -464,6 +464,39 @@ def main():
                                                 "bound_evals": int(fr["bound_evals"]), "icp_calls": int(fr["icp_calls"]), "nn_sse": fr["sse"],
                                                 "pose_vs_default_mode": {"dR_rad": dR, "dt": float(np.abs(fr["t"] - res["t"]).max())},
                                                 "note": "strategy of icp::FastGoICP (quaternion cube, span cut-offs 0.1 / 0.12, ub < 2 best => ICP) on this engine's kernels; no executable oracle"}
+
+        if args.workload == "bunny_goicp_toml":
+            # BASELINE config 4 next to the default line: test/spanner_goicp.toml as written (mse 1e-4, [-1,1]^3 translation cube) -- the
+            # throughput-bound certified search (5 305 rotation pops, 154 M bound evaluations; 4.7 h of the reference on one core)
+            sp = WORKLOADS["spanner_goicp_toml"]
+            sm_, sd_ = clouds_of(sp)
+            se = make_engine(wl=sp, clouds=(sm_, sd_))
+            se.BuildDT()
+            s_total, s_results = timed_registers(se, 2, 1)
+            sr = s_results[-1]
+            s_kern = sum(r["seconds_bnb_kernels"] for r in s_results)
+            s_lookups = sum(r["bound_evals_executed_local"] for r in s_results) * len(sd_)
+            rng2 = np.random.default_rng(7)
+            npar2 = 148 * 16
+            Rs2 = np.stack([np.linalg.qr(rng2.normal(size=(3, 3)))[0] for _ in range(npar2)]).astype(np.float32)
+            tc2 = np.concatenate([rng2.uniform(-0.5, 0.25, (npar2, 3)), np.full((npar2, 1), 0.25)], 1).astype(np.float32)
+            _, _, ms2 = se.ExpandBounds(Rs2.reshape(npar2, 9), np.full(npar2, -1, np.int32), tc2, repeats=20)
+            pat2 = npar2 * 8 * len(sd_) / (ms2 * 1e-3)
+            smask = 0
+            for r in s_results:
+                smask |= int(r["bnb_kernel_variants"])
+            se.close()
+            out_extra["spanner_goicp_toml"] = {
+                "config": "test/spanner_goicp.toml as written: Nd %d, Nm %d, S 300, mse 1e-4, translation cube [-1,1]^3, trim 0" % (len(sd_), len(sm_)),
+                "exit_path": sr["exit_path"], "time_to_certified_optimum_s": s_total / len(s_results), "value": sum(r["bound_evals"] for r in s_results) / s_total,
+                "unit": "bound-evals/s", "bound_evals": int(sr["bound_evals"]), "bound_evals_executed": int(sr["bound_evals_executed"]), "rot_pops": int(sr["rot_pops"]),
+                "trans_pops": int(sr["trans_pops"]), "rounds": int(sr["rounds"]), "sse": sr["sse"], "seconds_bnb_kernels": s_kern / len(s_results),
+                "seconds_icp": float(np.mean([r["seconds_icp"] for r in s_results])),
+                "roofline": {"kernel": " + ".join(v for k, v in KERNEL_NAMES.items() if smask & k), "lookups_per_s": s_lookups / s_kern,
+                             "achieved": s_lookups * 32 / s_kern / 1e9, "peak": pat2 * 32 / 1e9, "unit": "GB/s", "frac": s_lookups / s_kern / pat2,
+                             "peak_source": "pattern gather of this cloud in this run (expand_bounds_kernel, %.1f G look-ups/s) x 32 B sector" % (pat2 / 1e9)},
+                "reference_cpu_published_here": {"register_s": sp["ref_register_s"], "bound_evals": sp["ref_evals"],
+                                                 "note": "oracle/_ref (unmodified reference) in the build container, 1 core (tests/golden/goicp_runs.json)"}}
 
     # ---- roofline of the dominant kernel (this rank's GPU only)
     peaks = {}
