@@ -10,6 +10,15 @@ model = np.fromfile(os.path.join(G, "bunny_model_s0.1_seed1234.f32"), np.float32
 data = np.fromfile(os.path.join(G, "bunny_data_s0.1_seed1235.f32"), np.float32).reshape(-1, 3)
 g = pkg.GoICP(1e-3)
 g.pModel, g.pData = model, data
+if "PROFILE_GOLDEN" in os.environ:                    # any committed golden run instead (e.g. spanner_s0.02_mse3e-4 with GOICP_BNB_VARIANT=q5: the dense shape)
+    import json
+    gold = json.load(open(os.path.join(G, "goicp_runs.json")))[os.environ["PROFILE_GOLDEN"]]
+    g.close()
+    g = pkg.GoICP(gold["mse"])
+    g.pModel, g.pData = [np.fromfile(os.path.join(G, gold[k]), np.float32).reshape(-1, 3) for k in ("model", "data")]
+    g.trimFraction = gold["trim"]
+    if "trans_cube" in gold:
+        g.initNodeTrans = gold["trans_cube"]
 if "DT_MODE" in os.environ:
     g.dt_mode = int(os.environ["DT_MODE"])          # default: the library's (exact EDT + reference corner seed)
 g.BuildDT()

@@ -53,7 +53,8 @@ def main():
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"\"{k}\",{a[0]},{a[1]},{a[1] / tot:.4f}\n")
     if len(sys.argv) > 3:
-        raw = subprocess.run(["ncu", "-i", sys.argv[3], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a .ncu-rep, or its `ncu -i REP --page raw --csv` export made on the GPU box (reports of --set full are too large to bring back)
+        raw = open(sys.argv[3]).read() if sys.argv[3].endswith(".csv") else subprocess.run(["ncu", "-i", sys.argv[3], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rd = list(csv.reader(io.StringIO(raw)))
         hdr, units, body = rd[0], rd[1], rd[2:]
         idx = [hdr.index(m) for m in SELECT if m in hdr]
