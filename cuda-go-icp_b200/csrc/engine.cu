@@ -534,8 +534,8 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
         // leaves it in pred_max / pred_sum); without a forecast the previous batch's measured cycles decide (below).
         static const char* force = getenv("GOICP_BNB_VARIANT");       // "lat" / "thr" / "q5" / "q3": pin the variant (experiments)
         if (force) { h->low_latency = force[0] == 'l'; h->dense = force[0] == 'q' ? (force[1] == '3' ? 3 : 2) : 0; }
-        else if (h->pred_sum > 0 && !trim_run && plan_inner(h).pts_smem && !(getenv("GOICP_BNB_FORECAST") && atoi(getenv("GOICP_BNB_FORECAST")) == 0)) {
-            // (clouds whose rotated points stay in global memory keep the cycles-only rule and the two 512-thread shapes: measured on
+        else if (h->pred_sum > 0 && !trim_run && plan_inner(h, 5).pts_smem && !(getenv("GOICP_BNB_FORECAST") && atoi(getenv("GOICP_BNB_FORECAST")) == 0)) {
+            // (clouds whose rotated points would not fit a fifth of an SM's shared memory keep the cycles-only rule and the two 512-thread shapes: measured on
             // the 1e5-point sweep case, 512^3 grid in HBM, the dense shape loses -- BnB kernels 0.62 -> 0.77 s)
             const int Wq = ((h->xchg || h->nccl) && h->p.world_size > 1) ? h->p.world_size : 1;
             const int clq = plan_inner(h).cluster;
