@@ -71,7 +71,8 @@ class Snapshot(C.Structure):
 
 
 class InnerResult(C.Structure):
-    _fields_ = [("value", C.c_float), ("node", C.c_float * 4), ("pops", C.c_uint32), ("evals", C.c_uint32), ("status", C.c_int32)]
+    _fields_ = [("value", C.c_float), ("node", C.c_float * 4), ("pops", C.c_uint32), ("evals", C.c_uint32), ("status", C.c_int32),
+                ("reuse_gt", C.c_float), ("reuse_poplb", C.c_float)]
 
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
@@ -366,7 +367,8 @@ class GoICP:
         n = len(R)
         out = (InnerResult * n)()
         self._check(self.L.goicp_inner_bnb(self._handle(), n, R.ctypes.data, level.ctypes.data, oe.ctypes.data, out))
-        return [{"value": float(o.value), "node": np.array(o.node, np.float32), "pops": o.pops, "evals": o.evals} for o in out]
+        return [{"value": float(o.value), "node": np.array(o.node, np.float32), "pops": o.pops, "evals": o.evals,
+                 "reuse_gt": np.float32(o.reuse_gt), "reuse_poplb": np.float32(o.reuse_poplb)} for o in out]
 
     def NN(self, q):
         q = _f32(q, 3)

@@ -1229,6 +1229,7 @@ int goicp_inner_bnb(goicp_handle* h, int n, const float* R9, const int32_t* leve
     for (int k = 0; k < n; k++) {
         out[k].value = h->h_results[k].value; std::memcpy(out[k].node, h->h_results[k].node, sizeof out[k].node);
         out[k].pops = h->h_results[k].pops; out[k].evals = h->h_results[k].evals; out[k].status = h->h_results[k].status;
+        out[k].reuse_gt = (h->h_results[k].pad[0] & 1u) ? 3.402823466e+38f : h->h_results[k].reuse_gt; out[k].reuse_poplb = h->h_results[k].reuse_poplb;
     }
     return GOICP_OK;
 }

@@ -149,6 +149,11 @@ typedef struct {
     float node[4];           /* nodeTransOut x,y,z,w (upper-bound pass only) */
     uint32_t pops, evals;
     int32_t status;
+    /* For which SMALLER starting optErrors E' the call would have run exactly the same way (same pops, evaluations, arg-min;
+       `value` unchanged unless it is the starting optError itself, which becomes E'): E' > reuse_gt and, in float,
+       E' - reuse_poplb >= SSEThresh.  This is what lets goicp_register keep speculative results across an improvement of
+       the incumbent; FLT_MAX when the call cannot vouch for itself (trimming kernel, overflow). */
+    float reuse_gt, reuse_poplb;
 } goicp_inner_result;
 
 void goicp_default_params(goicp_params* p);

@@ -228,6 +228,14 @@ class Restated:
         v = self.L.go_inner(g, R, level, opt_error, out, cnt)
         return {"value": float(np.float32(v)), "node": out[1:5].copy(), "pops": int(cnt[0]), "evals": int(cnt[1])}
 
+    def inner_reuse(self, g):
+        """(reuse_gt, reuse_poplb, SSEThresh) of the last inner() call: the range of smaller optErrors it would have run identically for"""
+        out = np.zeros(3, np.float32)
+        self.L.go_inner_reuse.restype = None
+        self.L.go_inner_reuse.argtypes = [C.c_void_p, _f32p]
+        self.L.go_inner_reuse(g, out)
+        return np.float32(out[0]), np.float32(out[1]), np.float32(out[2])
+
     def cube_rotation(self, a, b, c, w):
         R = np.zeros(9, np.float32)
         ok = self.L.go_cube_rotation(a, b, c, w, R)
