@@ -80,7 +80,7 @@ ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size
 # every symbol include/goicp_b200.h declares (tests/test_abi.py checks the header against this)
 ABI_SYMBOLS = ["goicp_default_params", "goicp_create", "goicp_destroy", "goicp_last_error", "goicp_set_model",
                "goicp_set_data", "goicp_build_dt", "goicp_set_dt", "goicp_get_dt", "goicp_dt_size", "goicp_dt_distance",
-               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_svd3", "goicp_intro_select", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
+               "goicp_eval_bounds", "goicp_expand_bounds", "goicp_inner_bnb", "goicp_nn", "goicp_kdtree_host", "goicp_svd3", "goicp_intro_select", "goicp_bnb_shape_rule", "goicp_icp", "goicp_icp_dt", "goicp_dt_score",
                "goicp_register", "goicp_poll", "goicp_cancel", "goicp_trim_memory", "goicp_transfer_bytes", "goicp_measure_gather", "goicp_set_exchange", "goicp_nccl_unique_id", "goicp_nccl_init", "goicp_selftest_shard", "goicp_run_toml", "goicp_load_cloud", "goicp_free_cloud", "goicp_io_last_error"]
 
 

@@ -517,6 +517,19 @@ int shard_exchange(goicp_allgather_fn fn, void* user, int W, int n, const InnerR
     return 0;
 }
 
+// Shape of the inner-BnB kernel for a batch (1 = low latency, 0 = 512 threads x 2 CTAs per SM, 2 = dense 192 x 5) from the
+// forecast cost of its longest task and of all this rank's tasks (pops) and the previous batch's longest task; `slots` =
+// clusters one GPU holds in the low-latency shape.  A pure function: tests/test_host_io.py scores it on the committed
+// per-round measurements (profiles/r2x_rounds/) through goicp_bnb_shape_rule.
+int bnb_shape_rule(double pred_max, double pred_sum_rank, double prev_max_pops, double slots)
+{
+    const double pm = std::max(pred_max, 0.5 * prev_max_pops);
+    const double t_lat = std::max(pm, pred_sum_rank / slots), t_thr = std::max(1.4 * pm, 1.45 * pred_sum_rank / (2 * slots)),
+                 t_q = std::max(2.0 * pm, 2.1 * pred_sum_rank / (5 * slots));
+    if (t_lat <= t_thr && t_lat <= t_q) return 1;
+    return t_q < t_thr ? 2 : 0;
+}
+
 // Runs `n` inner BnBs (tasks in h->h_tasks) and leaves the results in h->h_results.
 // With an exchange hook installed, rank r runs tasks r, r+W, r+2W, ... and the per-rank result
 // blocks are all-gathered, so every rank ends up with all n results.
@@ -543,11 +556,9 @@ int run_inner_batch(goicp_handle* h, const BnbConst& c, int n, int64_t* executed
             // the longest task is the hard one to foresee (a child's search can be ten times its parent's): the forecast is
             // floored by half the previous batch's longest (fitted on per-round times of six golden runs in all three shapes,
             // profiles/r2x_shape_rule_fit.txt: 3 % above the per-round oracle on average, the cycles-only rule 10 %)
-            const double pm = std::max(h->pred_max, 0.5 * h->prev_max_pops);
-            const double t_lat = std::max(pm, sum / slots), t_thr = std::max(1.4 * pm, 1.45 * sum / (2 * slots)),
-                         t_q = std::max(2.0 * pm, 2.1 * sum / (5 * slots));
-            h->low_latency = t_lat <= t_thr && t_lat <= t_q;
-            h->dense = !h->low_latency && t_q < t_thr ? 2 : 0;
+            const int shape = bnb_shape_rule(h->pred_max, sum, h->prev_max_pops, slots);
+            h->low_latency = shape == 1;
+            h->dense = shape == 2 ? 2 : 0;
         }
     }
     const int variant = h->low_latency || trim_run ? (h->low_latency ? 1 : 0) : h->dense;
@@ -1267,6 +1278,10 @@ int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3
     return GOICP_OK;
 }
 
+int goicp_bnb_shape_rule(double forecast_longest_pops, double forecast_sum_pops_this_rank, double previous_longest_pops, int cluster_slots)
+{
+    return bnb_shape_rule(forecast_longest_pops, forecast_sum_pops_this_rank, previous_longest_pops, (double)std::max(1, cluster_slots));
+}
 int goicp_intro_select(goicp_handle* h, float* a, int n, int k, int threads, int in_global)
 {
     if (!h || !a || n <= 0 || k < 0 || k >= n || threads < 32 || threads > 1024 || (threads & 31)) return fail(h, GOICP_ERR_INVALID, "intro_select: bad arguments");

@@ -224,6 +224,12 @@ int goicp_svd3(goicp_handle* h, const float* H9, int n, float* U9_out, float* W3
  * whole thread block (csrc/strict_sum.cuh).  threads: block size (multiple of 32, <= 1024); in_global != 0 keeps the array in device
  * global memory (the path of clouds beyond shared memory).  Exposed for parity tests. */
 int goicp_intro_select(goicp_handle* h, float* a, int n, int k, int threads, int in_global);
+/* Diagnostic (host only, no device needed): the engine's per-round choice of inner-BnB kernel shape -- 1 = low latency (512
+   threads, one CTA per SM), 0 = 512 x 2, 2 = dense (192 x 5) -- from the forecast pops of the round's longest task and of
+   all of this rank's tasks, the previous round's longest task, and the number of clusters a GPU holds in the low-latency
+   shape (SMs / cluster size).  No reference counterpart: the reference runs its InnerBnB calls one after the other
+   (jly_goicp.cpp:471-551); every shape returns the same bits, so this only decides speed. */
+int goicp_bnb_shape_rule(double forecast_longest_pops, double forecast_sum_pops_this_rank, double previous_longest_pops, int cluster_slots);
 
 /* ICP3D<float>::Run (jly_icp3d.hpp:180-295) from (R0,t0). err_diff<0 -> mse_threshold/10000
  * (jly_goicp.cpp:186); max_iter<=0 -> params.icp_max_iter. */

@@ -6,7 +6,7 @@ import struct
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 
 def write_txt(path, pts):
@@ -139,3 +139,42 @@ def test_host_kdtree_layout_is_the_reference_layout(pkg, restated, bunny, case):
     assert np.array_equal(vind, ref_vind)
     assert np.array_equal(bbox.view(np.uint32), ref_bbox.view(np.uint32))
     assert _same_tree(nodes, ref_nodes)
+
+
+def test_bnb_shape_rule_on_the_committed_round_measurements(pkg):
+    """Host logic, no device: the engine's per-round choice of inner-BnB kernel shape (engine.cu: bnb_shape_rule, exported as
+    goicp_bnb_shape_rule) scored on the measurements it was fitted on -- profiles/r2x_rounds/: the GOICP_ROUND_STATS lines of six
+    golden runs, each forced into every shape.  The rounds of a run are the same in every shape (same results), so a rule's cost
+    is the sum of the measured kernel time of the shape it picks.  It must stay within 6 % of the per-round oracle on average,
+    beat every fixed shape on average, and never be worse than 12 % above the best fixed shape of a run."""
+    import ctypes as C
+    import re
+    L = pkg.lib()
+    L.goicp_bnb_shape_rule.restype = C.c_int
+    L.goicp_bnb_shape_rule.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+    pat = re.compile(r"\[round\] shape (\d+) forecast max (\d+) sum (\d+); \[round\] tasks (\d+) kernel ([\d.]+) ms; slowest task ([\d.]+) Mcyc "
+                     r"\(pops (\d+), level (-?\d+)\); max pops (\d+);")
+    cfgs = ["bunny_s0.1_mse1e-3", "bunny_s0.1_mse5e-4", "bunny_s0.033_mse1e-3", "spanner_s0.02_mse3e-4", "skull_s0.03_mse1e-3", "spanner_s0.02_mse1e-4"]
+    shape_of = {1: "lat", 0: "thr", 2: "q5"}
+    ratios, fixed = [], {"lat": [], "thr": [], "q5": []}
+    for c in cfgs:
+        rows = {}
+        for v in ("lat", "thr", "q5"):
+            with open(os.path.join(ROOT, "profiles", "r2x_rounds", f"r2x_rounds_{c}_{v}.txt")) as f:
+                rows[v] = [[float(x) for x in m.groups()] for m in map(pat.match, f) if m]
+        n = len(rows["lat"])
+        assert n > 0 and len(rows["thr"]) == n and len(rows["q5"]) == n
+        total, oracle, prev_max = 0.0, 0.0, 0.0
+        for i in range(n):
+            fmax, fsum = rows["lat"][i][1], rows["lat"][i][2]
+            pick = "lat" if fsum <= 0 else shape_of[L.goicp_bnb_shape_rule(fmax, fsum, prev_max, 148 // 4)]
+            total += rows[pick][i][4]
+            oracle += min(rows[v][i][4] for v in rows)
+            prev_max = rows["lat"][i][8]
+        best_fixed = min(sum(r[4] for r in rows[v]) for v in rows)
+        assert total <= 1.12 * best_fixed, (c, total, best_fixed)
+        ratios.append(total / oracle)
+        for v in rows:
+            fixed[v].append(sum(r[4] for r in rows[v]) / oracle)
+    assert np.mean(ratios) < 1.06, ratios
+    assert all(np.mean(ratios) < np.mean(fixed[v]) for v in fixed), (ratios, fixed)
